@@ -1,0 +1,258 @@
+/* gcnbmp.h -- C-ABI of the B200-native GCN-BMP message-passing hot path.
+ *
+ * The reference (Minys233/GCN-BMP) has no FFI layer: its hot path sits behind
+ * Chainer `Link.__call__` and every FLOP runs inside Chainer/CuPy.  This header
+ * is the boundary a maintainer binds with ctypes: plain
+ * device pointers (CuPy `arr.data.ptr`, Torch `t.data_ptr()`), sizes and a
+ * caller-supplied `cudaStream_t` (passed as void*).  All entry points are
+ * asynchronous on that stream, never allocate, never synchronise, and return an
+ * int status (0 = ok).  `bmp_last_error()` is thread-local.
+ *
+ * Layouts are the reference's: atoms int32 (mb, N), 0 = padding (still embedded);
+ * adj fp32 (mb, E, N, N); atom features fp32 (mb, N, H) row-major; `Linear.W`
+ * is (out, in); the message GraphLinear's W is (E*H, H) with row index c*E+e
+ * (channel-major / edge-minor, models/update/ggnn_update.py:35-39).
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef GCNBMP_H_
+#define GCNBMP_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMP_OK       0
+#define BMP_EINVAL  -1   /* null pointer / bad enum                       */
+#define BMP_ESHAPE  -2   /* shape outside what the kernels are built for  */
+#define BMP_EARCH   -3   /* device is not sm_100                          */
+#define BMP_ECUDA   -4   /* a CUDA runtime call failed                    */
+
+#define BMP_MAX_STEPS   16
+#define BMP_MAX_ATOMS   64   /* padded atoms per molecule handled by one CTA */
+#define BMP_MAX_HIDDEN 256
+
+/* activations (chainer.functions.{identity,tanh,relu,sigmoid}) */
+enum { BMP_ACT_IDENTITY = 0, BMP_ACT_TANH = 1, BMP_ACT_RELU = 2, BMP_ACT_SIGMOID = 3 };
+/* readout variants: R1 = models/readout/ggnn_readout.py:42-58 (i and j see [h|h0]);
+ * R2 = models/ggnn_att.py:338-346 (j sees h only); SUM = models/ggnn_dev.py:167 */
+enum { BMP_READOUT_R1 = 1, BMP_READOUT_R2 = 2, BMP_READOUT_SUM = 3 };
+/* co-attention variants: NIE/VQA = nie_coattention.py:312-396 /
+ * vqa_parallel_coattention.py:13-103 (same math); POOL = PoolingFineCoattention.py:13-83 */
+enum { BMP_COATTN_FINE = 0, BMP_COATTN_POOL = 1 };
+/* arithmetic mode of the encoder kernels */
+enum { BMP_MODE_F32 = 0,    /* fp32 FFMA everywhere: parity <= 1e-4 vs the oracle */
+       BMP_MODE_BF16 = 1 }; /* tcgen05 bf16 operands, fp32 accumulate/state       */
+
+/* One chainer links.GRU (= StatefulGRU): six Linear sub-links, W (out,in). */
+typedef struct {
+    const float *W_r, *b_Wr, *U_r, *b_Ur;   /* (H,2H),(H),(H,H),(H) */
+    const float *W_z, *b_Wz, *U_z, *b_Uz;
+    const float *W,   *b_W,  *U,   *b_U;
+} bmp_gru_t;
+
+typedef struct {                             /* gradients, same shapes; accumulated (+=) */
+    float *W_r, *b_Wr, *U_r, *b_Ur;
+    float *W_z, *b_Wz, *U_z, *b_Uz;
+    float *W,   *b_W,  *U,   *b_U;
+} bmp_gru_grad_t;
+
+/* ---- GGNN encoder: embed -> T x GGNNUpdate --------------------------------
+ * replaces models/models/ggnn.py:72-106 (loop), models/update/ggnn_update.py:31-63
+ * (one step), models/ggnn_att.py:220-268,589-660, models/ggnn_dev.py:69-111,135-168.
+ * Step t uses msg_W[t]/msg_b[t] and gru[t]; `stateful[t]` != 0 means the GRU has a
+ * state at that call (the StatefulGRU "h is not None" branch); the state is
+ * `state_in` for t == 0 and the step's own input h for t > 0 (which is what every
+ * reference GGNN feeds it).  Tied weights = the same pointers at every t.
+ * Stash buffers (needed by bmp_ggnn_backward, NULL for inference):
+ *   Hs (T+1, mb*N, H)  h_0 .. h_T           Ms (T, mb*N, H)   messages
+ *   Gs (T, mb*N, 3H)   r | z | h_bar        RSs (T, mb*N, H)  r*state            */
+typedef struct {
+    int mb, n_atoms, hidden, n_edge, n_steps, n_atom_types, mode;
+    const int32_t *atoms;        /* (mb,N) or NULL when h_in is given              */
+    const float   *h_in;         /* (mb,N,H) or NULL                                */
+    const float   *embed_W;      /* (n_atom_types,H); used when atoms != NULL       */
+    const float   *adj;          /* (mb,E,N,N)                                      */
+    const float   *state_in;     /* (mb,N,H) or NULL (= after reset_state)          */
+    const float   *msg_W[BMP_MAX_STEPS];   /* (E*H,H) */
+    const float   *msg_b[BMP_MAX_STEPS];   /* (E*H)   */
+    bmp_gru_t      gru[BMP_MAX_STEPS];
+    int            stateful[BMP_MAX_STEPS];
+    float *h_out;                /* (mb,N,H) final atom states (get_atom_array)     */
+    float *h0_out;               /* (mb,N,H) copy of h_0 for the readout, or NULL   */
+    float *Hs, *Ms, *Gs, *RSs;   /* stash or NULL                                   */
+} bmp_ggnn_fwd_t;
+
+int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
+
+/* Backward of the above (Chainer autograd through the same lines).
+ * dHs (T+1, mb*N, H): on entry the external gradient w.r.t. every h_t (zero where
+ * none; dHs[T] = grad of h_out, dHs[0] += grad of h0 from the readout); on exit
+ * dHs[0] holds the total gradient w.r.t. h_0 (feed it to bmp_embed_backward or
+ * return it as d h_in).  Gs is overwritten with dr|dz|dh_bar pre-activation
+ * gradients, Ps (T, mb*N, E*H) receives A_e^T dm.  Parameter gradients are
+ * accumulated (+=) into the per-step pointers (tied = same pointers).
+ * d_state_in (mb,N,H) or NULL.                                                  */
+typedef struct {
+    int mb, n_atoms, hidden, n_edge, n_steps, mode;
+    const float *adj, *state_in;
+    const float *msg_W[BMP_MAX_STEPS];
+    bmp_gru_t    gru[BMP_MAX_STEPS];
+    int          stateful[BMP_MAX_STEPS];
+    const float *Hs, *Ms, *RSs;
+    float *Gs, *Ps, *dHs;
+    float *d_msg_W[BMP_MAX_STEPS], *d_msg_b[BMP_MAX_STEPS];
+    bmp_gru_grad_t d_gru[BMP_MAX_STEPS];
+    float *d_state_in;
+} bmp_ggnn_bwd_t;
+
+int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
+
+/* EmbedAtomID (models/models/ggnn.py:55,89-92): forward gather is fused into the
+ * encoders; this is its backward: d_embed_W[atoms[r], :] += dh[r, :].            */
+int bmp_embed_backward(const int32_t *atoms, const float *dh, float *d_embed_W,
+                       int rows, int hidden, int n_atom_types, void *stream);
+
+/* ---- RelGCN encoder: embed -> [rescale_adj] -> L x tanh(RelGCNUpdate) ------
+ * replaces models/relgcn.py:61-73, :20-28 and models/update/relgcn_update.py:24-44.
+ * ch[0..L] are the channel sizes.  Hs stash: concatenation over l = 0..L of
+ * (mb*N, ch[l]) activations (h_0 = embedding, h_l = tanh(conv_l)).  `scale_adj`
+ * applies the column-degree normalisation inside the kernel.                     */
+typedef struct {
+    int mb, n_atoms, n_edge, n_layers, n_atom_types, scale_adj;
+    int ch[BMP_MAX_STEPS + 1];
+    const int32_t *atoms;  const float *h_in;  const float *embed_W;
+    const float *adj;
+    const float *self_W[BMP_MAX_STEPS], *self_b[BMP_MAX_STEPS];   /* (Cout,Cin),(Cout)     */
+    const float *edge_W[BMP_MAX_STEPS], *edge_b[BMP_MAX_STEPS];   /* (Cout*E,Cin),(Cout*E) */
+    float *h_out;      /* (mb,N,ch[L]) */
+    float *Hs;         /* stash or NULL */
+} bmp_relgcn_fwd_t;
+
+int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream);
+
+/* Ds: workspace, concatenation over l of (mb*N, ch[l+1]) pre-tanh gradients;
+ * Ps: workspace, concatenation over l of (mb*N, E*ch[l+1]) (A_e^T delta);
+ * d_h0 (mb*N, ch[0]) receives the gradient w.r.t. h_0.                           */
+typedef struct {
+    int mb, n_atoms, n_edge, n_layers, scale_adj;
+    int ch[BMP_MAX_STEPS + 1];
+    const float *adj;
+    const float *self_W[BMP_MAX_STEPS], *edge_W[BMP_MAX_STEPS];
+    const float *Hs;
+    const float *d_h_out;   /* (mb,N,ch[L]) */
+    float *Ds, *Ps, *d_h0;
+    float *d_self_W[BMP_MAX_STEPS], *d_self_b[BMP_MAX_STEPS];
+    float *d_edge_W[BMP_MAX_STEPS], *d_edge_b[BMP_MAX_STEPS];
+} bmp_relgcn_bwd_t;
+
+int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream);
+
+/* ---- gated readout ---------------------------------------------------------
+ * replaces models/readout/ggnn_readout.py:42-58 (R1), models/ggnn_att.py:338-346
+ * (R2), models/ggnn_dev.py:167 (SUM).  h0 may be NULL (R1 on h alone, relgcn.py:72).
+ * is_real_node (mb,N) fp32 or NULL.  W_i (O, Kin), W_j (O, Kin or H); b may be NULL. */
+typedef struct {
+    int mb, n_atoms, hidden, out_dim, variant, act, act_agg;
+    const float *h, *h0, *is_real_node;
+    const float *W_i, *b_i, *W_j, *b_j;
+    float *g;                          /* (mb,O) ; (mb,H) for SUM */
+} bmp_readout_fwd_t;
+
+int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream);
+
+/* DU/DV: workspaces (mb*N, O) receiving the pre-activation gradients of the i and
+ * j linears; dh/dh0 are ACCUMULATED (+=) so they can point into bmp_ggnn dHs.     */
+typedef struct {
+    int mb, n_atoms, hidden, out_dim, variant, act, act_agg;
+    const float *h, *h0, *is_real_node;
+    const float *W_i, *b_i, *W_j, *b_j;
+    const float *g, *dg;
+    float *DU, *DV, *dh, *dh0;
+    float *d_W_i, *d_b_i, *d_W_j, *d_b_j;
+} bmp_readout_bwd_t;
+
+int bmp_readout_backward(const bmp_readout_bwd_t *a, void *stream);
+
+/* ---- fine-grained co-attention ---------------------------------------------
+ * replaces models/coattention/nie_coattention.py:335-396,
+ * vqa_parallel_coattention.py:42-103 (variant FINE) and
+ * PoolingFineCoattention.py:31-83 (variant POOL).  The tile-materialised
+ * (mb*N2*N1, H) bilinear operands of the reference never exist here.
+ * W (H,H) [= Bilinear.W[:,:,0]], V1 (H), V2 (H), b (1), lt_k (head,H), wa_k (head),
+ * W_j (O,H), b_j (O).                                                            */
+typedef struct {
+    int mb, n1, n2, hidden, out_dim, head, variant, act;
+    const float *atoms_1, *atoms_2;    /* (mb,N1,H), (mb,N2,H) */
+    const float *W, *V1, *V2, *b, *lt_1, *lt_2, *wa_1, *wa_2, *W_j, *b_j;
+    float *compact_1, *compact_2;      /* (mb,O) */
+} bmp_coattn_fwd_t;
+
+int bmp_coattn_forward(const bmp_coattn_fwd_t *a, void *stream);
+
+/* R (mb*N1, H), P1/P2 (mb, H) and DL1/DL2 (mb*N1 / mb*N2, head) are workspaces the
+ * parameter-gradient GEMMs read.  d_atoms_k are ACCUMULATED (+=).               */
+typedef struct {
+    int mb, n1, n2, hidden, out_dim, head, variant, act;
+    const float *atoms_1, *atoms_2;
+    const float *W, *V1, *V2, *b, *lt_1, *lt_2, *wa_1, *wa_2, *W_j, *b_j;
+    const float *d_compact_1, *d_compact_2;
+    float *R, *P1, *P2, *DL1, *DL2;
+    float *d_atoms_1, *d_atoms_2;
+    float *d_W, *d_V1, *d_V2, *d_b, *d_lt_1, *d_lt_2, *d_wa_1, *d_wa_2, *d_W_j, *d_b_j;
+} bmp_coattn_bwd_t;
+
+int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream);
+
+/* ---- HolE circular correlation ----------------------------------------------
+ * replaces models/link_prediction/hole.py:28-50 (= models/mlp.py:128-151):
+ * c[b,k] = sum_i l[b,i] r[b,(i+k) mod D], computed directly (no FFT).            */
+int bmp_hole_corr_forward(const float *left, const float *right, float *out,
+                          int mb, int dim, void *stream);
+int bmp_hole_corr_backward(const float *left, const float *right, const float *d_out,
+                           float *d_left, float *d_right, int mb, int dim, void *stream);
+
+/* ---- dense layers of the heads (links.Linear; hole.py:21-26) ----------------
+ * y = act(x W^T + b); W (out,in), b NULL allowed.                                */
+int bmp_linear_forward(const float *x, const float *W, const float *b, float *y,
+                       int rows, int in_dim, int out_dim, int act, void *stream);
+/* dy is overwritten with the pre-activation gradient; dx (=), dW/db (+=). dx may be NULL. */
+int bmp_linear_backward(const float *x, const float *W, const float *y, float *dy,
+                        float *dx, float *dW, float *db,
+                        int rows, int in_dim, int out_dim, int act, void *stream);
+
+/* C (M,N) += A^T B with A (rows,M; lda), B (rows,N; ldb): the parameter-gradient
+ * contraction over all atoms of a batch (split over CTAs, fp32 atomics at the end). */
+int bmp_wgrad(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+              int64_t rows, int M, int N, void *stream);
+/* out[n * out_stride] += sum_r B[r*ldb + n] */
+int bmp_colsum(const float *B, int ldb, float *out, int out_stride, int64_t rows, int N, void *stream);
+
+/* ---- loss (train_binary.py:524: F.sigmoid_cross_entropy, mean over t != -1) --
+ * `count` = number of non-ignored elements the mean divides by (pass the GLOBAL
+ * count under data parallelism); loss_sum[0] += sum of per-element losses / count;
+ * d_logits = (sigmoid(x) - t) / count.                                            */
+int bmp_sigmoid_ce(const float *logits, const int32_t *labels, float *loss_sum,
+                   float *d_logits, int n, float count, void *stream);
+
+/* Adam as chainer.optimizers.Adam (alpha, beta1, beta2, eps, weight_decay_rate):
+ * train_binary.py:533-536.  step = t (1-based).                                   */
+int bmp_adam_step(float *param, const float *grad, float *m, float *v, int n,
+                  float alpha, float beta1, float beta2, float eps,
+                  float weight_decay_rate, int step, void *stream);
+
+/* ---- housekeeping ------------------------------------------------------------ */
+const char *bmp_last_error(void);
+int         bmp_version(void);
+int         bmp_device_check(void);           /* BMP_OK iff current device is sm_100 */
+uint64_t    bmp_launch_count(void);           /* kernels launched by this library    */
+void        bmp_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNBMP_H_ */

@@ -1,0 +1,496 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  **parity unpinned** (see minichainer.py).
+
+CPU restatement of the GCN-BMP message-passing hot path, executing the SAME op
+sequence the reference's Chainer links execute (same reshapes, transposes,
+per-edge-type batched matmul, six separate GRU linears, tile-materialised
+bilinear operands, FFT-based HolE), on the NumPy tape in minichainer.py.
+Every function cites the reference file:line it follows (paths are relative to
+the reference repository root).  Parameters are passed as a flat dict keyed by
+Chainer-style parameter paths (what `Link.namedparams()` / an npz snapshot
+would contain), e.g. ``update_layers/0/graph_linear/W``.
+
+dtype: whatever the parameter/input arrays are (float32 = "reference CPU path",
+float64 = ground truth for tolerance tests).
+"""
+import numpy as np
+
+from . import minichainer as F
+
+MAX_ATOMIC_NUM = 117  # chainer_chemistry.config.MAX_ATOMIC_NUM
+ACT = {"identity": F.identity, "tanh": F.tanh, "relu": F.relu, "sigmoid": F.sigmoid}
+
+
+class P(object):
+    """View of a flat {path: Var} dict under a prefix."""
+
+    def __init__(self, table, prefix=""):
+        self.table, self.prefix = table, prefix
+
+    def __getitem__(self, name):
+        return self.table[self.prefix + name]
+
+    def sub(self, name):
+        return P(self.table, self.prefix + name + "/")
+
+    def has(self, name):
+        return (self.prefix + name) in self.table
+
+
+def wrap_params(arrays, dtype=None):
+    """{path: ndarray} -> {path: Var(requires grad)}."""
+    return {k: F.param(np.asarray(v, dtype=dtype or v.dtype)) for k, v in arrays.items()}
+
+
+def grads_of(table):
+    return {k: (v.grad if v.grad is not None else np.zeros_like(v.data)) for k, v in table.items()}
+
+
+# ----------------------------------------------------------------------------
+# Chainer links.GRU (= StatefulGRU); used at models/update/ggnn_update.py:28,60
+# ----------------------------------------------------------------------------
+class StatefulGRU(object):
+    def __init__(self, p):
+        self.p, self.h = p, None
+
+    def reset_state(self):
+        self.h = None
+
+    def _lin(self, name, x):
+        q = self.p.sub(name)
+        return F.linear(x, q["W"], q["b"])
+
+    def __call__(self, x):
+        z = self._lin("W_z", x)
+        h_bar = self._lin("W", x)
+        if self.h is not None:
+            r = F.sigmoid(F.add(self._lin("W_r", x), self._lin("U_r", self.h)))
+            z = F.add(z, self._lin("U_z", self.h))
+            h_bar = F.add(h_bar, self._lin("U", F.mul(r, self.h)))
+        z = F.sigmoid(z)
+        h_bar = F.tanh(h_bar)
+        if self.h is not None:
+            out = F.linear_interpolate(z, h_bar, self.h)
+        else:
+            out = F.mul(z, h_bar)
+        self.h = out
+        return out
+
+
+def _edge_messages(lin_out, mb, n, ch, n_edge):
+    """(mb, n, ch*E) -> (mb, E, n, ch): channel-major / edge-minor split.
+    models/update/ggnn_update.py:35-39, models/update/relgcn_update.py:33-37."""
+    m = F.reshape(lin_out, (mb, n, ch, n_edge))
+    return F.transpose(m, (0, 3, 1, 2))
+
+
+# ----------------------------------------------------------------------------
+# models/update/ggnn_update.py:31-63
+# ----------------------------------------------------------------------------
+class GGNNUpdate(object):
+    def __init__(self, p, hidden_dim=16, num_edge_type=4, gru=None):
+        self.p, self.E = p, num_edge_type
+        self.update_layer = gru if gru is not None else StatefulGRU(p.sub("update_layer"))
+
+    def message(self, h, adj):
+        mb, n, ch = h.shape
+        gl = self.p.sub("graph_linear")
+        m = _edge_messages(F.graph_linear(h, gl["W"], gl["b"]), mb, n, ch, self.E)   # :34-39
+        a = F.reshape(F.as_var(adj), (mb * self.E, n, n))                              # :41
+        m = F.reshape(m, (mb * self.E, n, ch))                                         # :43
+        m = F.matmul(a, m)                                                             # :45
+        m = F.reshape(m, (mb, self.E, n, ch))                                          # :48
+        return F.sum_(m, axis=1)                                                       # :49
+
+    def __call__(self, h, adj):
+        mb, n, ch = h.shape
+        m = self.message(h, adj)
+        x = F.concat((F.reshape(h, (mb * n, ch)), F.reshape(m, (mb * n, ch))), axis=1)  # :54-60
+        return F.reshape(self.update_layer(x), (mb, n, ch))                             # :62
+
+    def reset_state(self):
+        self.update_layer.reset_state()
+
+
+# ----------------------------------------------------------------------------
+# models/update/relgcn_update.py:24-44
+# ----------------------------------------------------------------------------
+class RelGCNUpdate(object):
+    def __init__(self, p, in_channels, out_channels, num_edge_type=4):
+        self.p, self.E, self.cout = p, num_edge_type, out_channels
+
+    def __call__(self, h, adj):
+        mb, n, _ = h.shape
+        ps, pe = self.p.sub("graph_linear_self"), self.p.sub("graph_linear_edge")
+        hs = F.graph_linear(h, ps["W"], ps["b"])                                        # :28
+        m = _edge_messages(F.graph_linear(h, pe["W"], pe["b"]), mb, n, self.cout, self.E)  # :32-37
+        m = F.matmul(F.as_var(adj), m)                                                  # :40 (4-D batched)
+        return F.add(hs, F.sum_(m, axis=1))                                             # :43-44
+
+
+def rescale_adj(adj):
+    """models/relgcn.py:20-28 -- column-degree normalisation over (edge, row)."""
+    deg = adj.sum(axis=(1, 2))
+    inv = 1.0 / np.where(deg != 0, deg, np.ones_like(deg))
+    return (adj * inv[:, None, None, :]).astype(adj.dtype)
+
+
+# ----------------------------------------------------------------------------
+# models/readout/ggnn_readout.py:42-58   (variant R1)
+# ----------------------------------------------------------------------------
+class GGNNReadout(object):
+    def __init__(self, p, out_dim, hidden_dim=16, nobias=False,
+                 activation="identity", activation_agg="identity"):
+        self.p, self.nobias = p, nobias
+        self.act, self.act_agg = ACT[activation], ACT[activation_agg]
+
+    def _gl(self, name, x):
+        q = self.p.sub(name)
+        return F.graph_linear(x, q["W"], None if self.nobias else q["b"])
+
+    def __call__(self, h, h0=None, is_real_node=None):
+        h1 = F.concat((h, h0), axis=2) if h0 is not None else h                        # :45
+        g = F.mul(F.sigmoid(self._gl("i_layer", h1)), self.act(self._gl("j_layer", h1)))  # :47-49
+        if is_real_node is not None:                                                    # :50-54
+            mask = np.broadcast_to(np.asarray(is_real_node)[:, :, None], g.shape).astype(g.dtype)
+            g = F.mul(g, F.const(mask))
+        return self.act_agg(F.sum_(g, axis=1))                                          # :56
+
+
+# ----------------------------------------------------------------------------
+# models/models/ggnn.py:46-109  (modular GGNN: GGNNUpdate + GGNNReadout)
+# ----------------------------------------------------------------------------
+class GGNN(object):
+    def __init__(self, p, out_dim, hidden_dim=16, n_layers=4, n_atom_types=MAX_ATOMIC_NUM,
+                 concat_hidden=False, weight_tying=True, activation="identity", num_edge_type=4):
+        self.p = p
+        self.n_layers, self.concat_hidden, self.weight_tying = n_layers, concat_hidden, weight_tying
+        n_msg = 1 if weight_tying else n_layers
+        n_ro = n_layers if concat_hidden else 1
+        self.update_layers = [GGNNUpdate(p.sub("update_layers/%d" % i), hidden_dim, num_edge_type)
+                              for i in range(n_msg)]
+        self.readout_layers = [GGNNReadout(p.sub("readout_layers/%d" % i), out_dim, hidden_dim,
+                                           activation=activation, activation_agg=activation)
+                               for i in range(n_ro)]
+        self.atoms = None
+
+    def reset_state(self):
+        for u in self.update_layers:
+            u.reset_state()
+
+    def __call__(self, atom_array, adj, is_real_node=None):
+        self.reset_state()                                                             # :88
+        if np.asarray(getattr(atom_array, "data", atom_array)).ndim <= 2:              # :89
+            h = F.embed_id(atom_array, self.p["embed/W"])
+        else:
+            h = F.as_var(atom_array)
+        h0 = F.copy(h)                                                                 # :93
+        gs = []
+        for step in range(self.n_layers):                                              # :95
+            u = self.update_layers[0 if self.weight_tying else step]
+            h = u(h, adj)
+            if self.concat_hidden:
+                gs.append(self.readout_layers[step](h, h0, is_real_node))
+        self.atoms = h
+        if self.concat_hidden:
+            return F.concat(gs, axis=1)                                                # :103
+        return self.readout_layers[0](h, h0, is_real_node)                             # :105
+
+    def get_atom_array(self):
+        return self.atoms
+
+
+# ----------------------------------------------------------------------------
+# models/ggnn_att.py:220-268,338-346,589-664 (default flags) and
+# models/ggnn_dev.py:69-122,135-172: monolithic GGNN -- per-step message
+# GraphLinears, ONE shared stateful GRU, readout R2 (j sees only h), optional
+# sum readout (ggnn_dev.py:165-167), final atom states exposed.
+# ----------------------------------------------------------------------------
+class GGNNMono(object):
+    NUM_EDGE_TYPE = 4
+
+    def __init__(self, p, out_dim, hidden_dim=16, n_layers=4, n_atom_types=MAX_ATOMIC_NUM,
+                 concat_hidden=False, weight_tying=True, sum_readout=False):
+        self.p, self.n_layers = p, n_layers
+        self.concat_hidden, self.weight_tying, self.sum_readout = concat_hidden, weight_tying, sum_readout
+        self.gru = StatefulGRU(p.sub("update_layer"))
+        self.atoms_list = []
+
+    def update(self, h, adj, step):
+        mb, n, ch = h.shape
+        idx = 0 if self.weight_tying else step
+        q = self.p.sub("message_layers/%d" % idx)
+        m = _edge_messages(F.graph_linear(h, q["W"], q["b"]), mb, n, ch, self.NUM_EDGE_TYPE)
+        a = F.reshape(F.as_var(adj), (mb * self.NUM_EDGE_TYPE, n, n))
+        m = F.matmul(a, F.reshape(m, (mb * self.NUM_EDGE_TYPE, n, ch)))
+        m = F.sum_(F.reshape(m, (mb, self.NUM_EDGE_TYPE, n, ch)), axis=1)
+        x = F.concat((F.reshape(h, (mb * n, ch)), F.reshape(m, (mb * n, ch))), axis=1)
+        return F.reshape(self.gru(x), (mb, n, ch))
+
+    def readout(self, h, h0, step=0):
+        idx = step if self.concat_hidden else 0
+        qi, qj = self.p.sub("i_layers/%d" % idx), self.p.sub("j_layers/%d" % idx)
+        gate = F.sigmoid(F.graph_linear(F.concat((h, h0), axis=2), qi["W"], qi["b"]))
+        g = F.mul(gate, F.graph_linear(h, qj["W"], qj["b"]))
+        return F.sum_(g, axis=1)
+
+    def __call__(self, atom_array, adj):
+        self.gru.reset_state()
+        self.atoms_list = []
+        a = np.asarray(getattr(atom_array, "data", atom_array))
+        h = F.embed_id(a, self.p["embed/W"]) if a.dtype == np.int32 else F.as_var(atom_array)
+        h0 = F.copy(h)
+        gs = []
+        for step in range(self.n_layers):
+            h = self.update(h, adj, step)
+            if self.concat_hidden:
+                gs.append(self.readout(h, h0, step))
+            self.atoms_list.append(h)
+        if self.concat_hidden:
+            return F.concat(gs, axis=1)
+        if self.sum_readout:
+            return F.sum_(h, axis=1)          # ggnn_dev.py:167
+        return self.readout(h, h0, 0)
+
+    def get_atom_array(self, step=-1):
+        return self.atoms_list[step]
+
+
+# ----------------------------------------------------------------------------
+# models/relgcn.py:32-73
+# ----------------------------------------------------------------------------
+class RelGCN(object):
+    def __init__(self, p, out_channels=64, num_edge_type=4, ch_list=None,
+                 n_atom_types=MAX_ATOMIC_NUM, input_type="int", scale_adj=None):
+        if ch_list is None:
+            ch_list = [16, 128, 64]
+        if input_type not in ("int", "float"):
+            raise ValueError("[ERROR] Unexpected value input type={}".format(input_type))
+        self.p, self.scale_adj, self.input_type = p, scale_adj, input_type
+        self.convs = [RelGCNUpdate(p.sub("rgcn_convs/%d" % i), ch_list[i], ch_list[i + 1], num_edge_type)
+                      for i in range(len(ch_list) - 1)]
+        self.readout = GGNNReadout(p.sub("rgcn_readout"), out_channels, ch_list[-1],
+                                   nobias=True, activation="tanh")
+        self.atoms = None
+
+    def __call__(self, h, adj):
+        if self.input_type == "int":
+            h = F.embed_id(h, self.p["embed/W"])                                       # :67
+        else:
+            q = self.p.sub("embed")
+            h = F.graph_linear(F.as_var(h), q["W"], q["b"])
+        if self.scale_adj:
+            adj = rescale_adj(adj)                                                     # :68-69
+        for conv in self.convs:
+            h = F.tanh(conv(h, adj))                                                   # :70-71
+        self.atoms = h
+        return self.readout(h)                                                         # :72
+
+    def get_atom_array(self):
+        return self.atoms
+
+
+# ----------------------------------------------------------------------------
+# Fine-grained co-attention.
+#   models/coattention/nie_coattention.py:312-396          (NieFineCoattention)
+#   models/coattention/vqa_parallel_coattention.py:13-103  (VQAParallelCoattention)
+#   models/coattention/PoolingFineCoattention.py:13-83     (PoolingFineCoattention)
+# ----------------------------------------------------------------------------
+def _energy(p, act, query, key):
+    """compute_attention (nie_coattention.py:371-396): act(Bilinear(key, query))
+    over tile-materialised (mb*Nq*Nk, H) operands -> (mb, Nq, Nk)."""
+    mb, nq, hd = query.shape
+    nk = key.shape[1]
+    q = F.reshape(F.tile(F.expand_dims(query, 2), (1, 1, nk, 1)), (mb * nq * nk, hd))
+    k = F.reshape(F.tile(F.expand_dims(key, 1), (1, nq, 1, 1)), (mb * nq * nk, hd))
+    e = p.sub("energy_layer")
+    y = F.bilinear(k, q, e["W"], e["V1"], e["V2"], e["b"])
+    return F.reshape(act(y), (mb, nq, nk))
+
+
+class NieFineCoattention(object):
+    default_activation = "identity"   # nie_coattention.py:316
+
+    def __init__(self, p, hidden_dim, out_dim, head, activation=None):
+        self.p, self.out_dim = p, out_dim
+        self.act = ACT[activation or self.default_activation]
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        p = self.p
+        C = _energy(p, self.act, query=atoms_2, key=atoms_1)                           # (mb, N2, N1) :344
+        L_2 = F.softmax(C, axis=1)                                                     # :347
+        L_1 = F.softmax(F.transpose(C, (0, 2, 1)), axis=1)                             # :349
+        lt_1 = F.graph_linear(atoms_1, p["lt_layer_1/W"])                              # :352
+        lt_2 = F.graph_linear(atoms_2, p["lt_layer_2/W"])                              # :354
+        H_1 = F.tanh(F.add(lt_1, F.matmul(L_1, lt_2)))                                 # :356-358
+        H_2 = F.tanh(F.add(lt_2, F.matmul(L_2, lt_1)))                                 # :361-362
+        attn_1 = F.softmax(F.graph_linear(H_1, p["attention_layer_1/W"]))              # :364
+        attn_2 = F.softmax(F.graph_linear(H_2, p["attention_layer_2/W"]))              # :366
+        j1 = F.graph_linear(atoms_1, p["j_layer/W"], p["j_layer/b"])
+        j2 = F.graph_linear(atoms_2, p["j_layer/W"], p["j_layer/b"])
+        c1 = F.sum_(F.mul(F.tile(attn_1, (1, 1, self.out_dim)), j1), axis=1)           # :368
+        c2 = F.sum_(F.mul(F.tile(attn_2, (1, 1, self.out_dim)), j2), axis=1)           # :369
+        return c1, c2
+
+
+class VQAParallelCoattention(NieFineCoattention):
+    default_activation = "tanh"       # vqa_parallel_coattention.py:23
+
+
+class PoolingFineCoattention(object):
+    def __init__(self, p, hidden_dim, out_dim, activation="tanh"):
+        self.p, self.out_dim, self.act = p, out_dim, ACT[activation]
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        p = self.p
+        energy = _energy(p, self.act, query=atoms_2, key=atoms_1)                      # (mb, N2, N1) :40
+        attn_1 = F.softmax(F.mean(energy, axis=1), axis=1)                             # :42-44
+        attn_2 = F.softmax(F.mean(energy, axis=2), axis=1)                             # :48-50
+        attn_1 = F.tile(F.expand_dims(attn_1, 2), (1, 1, self.out_dim))
+        attn_2 = F.tile(F.expand_dims(attn_2, 2), (1, 1, self.out_dim))
+        j1 = F.graph_linear(atoms_1, p["j_layer/W"], p["j_layer/b"])
+        j2 = F.graph_linear(atoms_2, p["j_layer/W"], p["j_layer/b"])
+        return F.sum_(F.mul(attn_1, j1), axis=1), F.sum_(F.mul(attn_2, j2), axis=1)    # :54-56
+
+
+# ----------------------------------------------------------------------------
+# models/link_prediction/hole.py:53-91 (= models/mlp.py:113-151)
+# ----------------------------------------------------------------------------
+class HolE(object):
+    def __init__(self, p, out_dim, hidden_dims=(32, 16), activation="relu",
+                 layers_name="hidden_layers"):
+        self.p, self.n_hidden, self.act, self.layers_name = p, len(hidden_dims), ACT[activation], layers_name
+
+    def circular_correlation(self, left_x, right_x):
+        zeros = lambda v: F.const(np.zeros_like(v.data))
+        lr, li = F.fft((left_x, zeros(left_x)))                                        # :38-40
+        rr, ri = F.fft((right_x, zeros(right_x)))                                      # :42-44
+        pr = F.add(F.mul(lr, rr), F.mul(li, ri))                                       # :46
+        pi = F.sub(F.mul(lr, ri), F.mul(li, rr))                                       # :47
+        out, _ = F.ifft((pr, pi))                                                      # :49
+        return out
+
+    def __call__(self, left_x, right_x):
+        h = self.circular_correlation(left_x, right_x)
+        for i in range(self.n_hidden):
+            q = self.p.sub("%s/%d" % (self.layers_name, i))
+            h = self.act(F.linear(h, q["W"], q["b"]))
+        q = self.p.sub("l_out")
+        return F.linear(h, q["W"], q["b"])
+
+
+# ----------------------------------------------------------------------------
+# train_binary.py:84-118 (pair composition) and :524 (loss)
+# ----------------------------------------------------------------------------
+class GraphConvPredictorForPair(object):
+    def __init__(self, graph_conv, attn=None, mlp=None):
+        self.graph_conv, self.attn, self.mlp = graph_conv, attn, mlp
+
+    def __call__(self, atoms_1, adjs_1, atoms_2, adjs_2):
+        g1 = self.graph_conv(atoms_1, adjs_1)
+        a1 = self.graph_conv.get_atom_array()
+        g2 = self.graph_conv(atoms_2, adjs_2)
+        a2 = self.graph_conv.get_atom_array()
+        if self.attn is not None:
+            g1, g2 = self.attn(a1, g1, a2, g2)
+        return self.mlp(g1, g2)
+
+
+def loss_and_grads(predictor, table, inputs, labels):
+    """One Classifier iteration: sigmoid-CE loss + backward (train_binary.py:524-530)."""
+    for v in table.values():
+        v.grad = None
+    logits = predictor(*inputs)
+    loss = F.sigmoid_cross_entropy(logits, labels)
+    loss.backward()
+    return loss.data, logits.data, grads_of(table)
+
+
+# ----------------------------------------------------------------------------
+# parameter shapes (Chainer names) + Chainer-like initialisation
+# ----------------------------------------------------------------------------
+def _gru_shapes(pre, H):
+    s = {}
+    for n in ("W_r", "W_z", "W"):
+        s[pre + n + "/W"], s[pre + n + "/b"] = (H, 2 * H), (H,)
+    for n in ("U_r", "U_z", "U"):
+        s[pre + n + "/W"], s[pre + n + "/b"] = (H, H), (H,)
+    return s
+
+
+def ggnn_shapes(out_dim, hidden_dim, n_layers, concat_hidden=False, weight_tying=True, E=4,
+                n_atom_types=MAX_ATOMIC_NUM):
+    H = hidden_dim
+    s = {"embed/W": (n_atom_types, H)}
+    for i in range(1 if weight_tying else n_layers):
+        pre = "update_layers/%d/" % i
+        s[pre + "graph_linear/W"], s[pre + "graph_linear/b"] = (E * H, H), (E * H,)
+        s.update(_gru_shapes(pre + "update_layer/", H))
+    for i in range(n_layers if concat_hidden else 1):
+        pre = "readout_layers/%d/" % i
+        for n in ("i_layer", "j_layer"):
+            s[pre + n + "/W"], s[pre + n + "/b"] = (out_dim, 2 * H), (out_dim,)
+    return s
+
+
+def ggnn_mono_shapes(out_dim, hidden_dim, n_layers, concat_hidden=False, weight_tying=True, E=4,
+                     n_atom_types=MAX_ATOMIC_NUM):
+    H = hidden_dim
+    s = {"embed/W": (n_atom_types, H)}
+    for i in range(1 if weight_tying else n_layers):
+        s["message_layers/%d/W" % i], s["message_layers/%d/b" % i] = (E * H, H), (E * H,)
+    s.update(_gru_shapes("update_layer/", H))
+    for i in range(n_layers if concat_hidden else 1):
+        s["i_layers/%d/W" % i], s["i_layers/%d/b" % i] = (out_dim, 2 * H), (out_dim,)
+        s["j_layers/%d/W" % i], s["j_layers/%d/b" % i] = (out_dim, H), (out_dim,)
+    return s
+
+
+def relgcn_shapes(out_channels, ch_list, E=4, n_atom_types=MAX_ATOMIC_NUM):
+    s = {"embed/W": (n_atom_types, ch_list[0])}
+    for i in range(len(ch_list) - 1):
+        pre = "rgcn_convs/%d/" % i
+        s[pre + "graph_linear_self/W"], s[pre + "graph_linear_self/b"] = (ch_list[i + 1], ch_list[i]), (ch_list[i + 1],)
+        s[pre + "graph_linear_edge/W"] = (ch_list[i + 1] * E, ch_list[i])
+        s[pre + "graph_linear_edge/b"] = (ch_list[i + 1] * E,)
+    s["rgcn_readout/i_layer/W"] = (out_channels, ch_list[-1])
+    s["rgcn_readout/j_layer/W"] = (out_channels, ch_list[-1])
+    return s
+
+
+def coattn_shapes(hidden_dim, out_dim, head=None):
+    s = {"energy_layer/W": (hidden_dim, hidden_dim, 1), "energy_layer/V1": (hidden_dim, 1),
+         "energy_layer/V2": (hidden_dim, 1), "energy_layer/b": (1,),
+         "j_layer/W": (out_dim, hidden_dim), "j_layer/b": (out_dim,)}
+    if head is not None:
+        s.update({"attention_layer_1/W": (1, head), "attention_layer_2/W": (1, head),
+                  "lt_layer_1/W": (head, hidden_dim), "lt_layer_2/W": (head, hidden_dim)})
+    return s
+
+
+def hole_shapes(in_dim, out_dim, hidden_dims=(32, 16), layers_name="hidden_layers"):
+    s, d = {}, in_dim
+    for i, hdim in enumerate(hidden_dims):
+        s["%s/%d/W" % (layers_name, i)], s["%s/%d/b" % (layers_name, i)] = (hdim, d), (hdim,)
+        d = hdim
+    s["l_out/W"], s["l_out/b"] = (out_dim, d), (out_dim,)
+    return s
+
+
+def init_params(shapes, rng, dtype=np.float32, bias_scale=0.1, prefix=""):
+    """Chainer-like init: LeCunNormal (std 1/sqrt(fan_in)) for matrices, N(0,1)
+    embedding; biases are small random instead of zero so bias paths are tested."""
+    out = {}
+    for name in sorted(shapes):
+        shp = shapes[name]
+        if name.endswith("embed/W") and len(shp) == 2 and shp[0] == MAX_ATOMIC_NUM:
+            a = rng.standard_normal(shp) * 0.5
+        elif len(shp) == 1:
+            a = rng.standard_normal(shp) * bias_scale
+        elif len(shp) == 3:
+            a = rng.standard_normal(shp) / np.sqrt(shp[0])
+        elif name.endswith("/V1") or name.endswith("/V2"):
+            a = rng.standard_normal(shp) / np.sqrt(shp[0])
+        else:
+            a = rng.standard_normal(shp) / np.sqrt(shp[1])
+        out[prefix + name] = a.astype(dtype)
+    return out
