@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relgcn_fwd_kernel(const bmp_relgc
                             acc[oc][q][2] += bb * d.z; acc[oc][q][3] += bb * d.w;
                         }
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[oc][q][b] = tanhf(acc[oc][q][b]);
+                    for (int b = 0; b < 4; ++b) acc[oc][q][b] = act_fwd(a.act, acc[oc][q][b]);
                 }
             }
             __syncthreads();   // every reader of hs is done
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) relgcn_bwd_kernel(const bmp_relgc
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) g[q][b] *= (1.f - y[q][b] * y[q][b]);
+                    for (int b = 0; b < 4; ++b) g[q][b] *= act_bwd(a.act, y[q][b], y[q][b]);
                 tile_store_s(gs, oc * 64, g);
                 tile_store_g(a.Ds + ds_off[l] + row0 * Cout, Cout, oc * 64, Cout, N, g);
             }

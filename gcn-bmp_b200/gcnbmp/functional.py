@@ -1,0 +1,378 @@
+"""torch.autograd glue over the C-ABI: every forward/backward here is ONE call into
+libgcnbmp.so (plus workspace allocation).  Torch supplies device memory, the
+current stream and the tape between ops -- no arithmetic of the hot path is done
+with torch operators."""
+import ctypes as C
+
+import torch
+
+from . import _capi as K
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.contiguous().float()
+    return t
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gcnbmp: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def act_code(a):
+    """chainer.functions.{identity,tanh,relu,sigmoid} | their names -> enum."""
+    if a is None:
+        return K.ACT["identity"]
+    name = a if isinstance(a, str) else getattr(a, "__name__", str(a))
+    if name not in K.ACT:
+        raise ValueError("gcnbmp: unsupported activation %r" % (a,))
+    return K.ACT[name]
+
+
+GRU_FIELDS = ("W_r", "b_Wr", "U_r", "b_Ur", "W_z", "b_Wz", "U_z", "b_Uz", "W", "b_W", "U", "b_U")
+
+
+def _fill_gru(dst, tensors):
+    for name, t in zip(GRU_FIELDS, tensors):
+        setattr(dst, name, _p(t))
+
+
+class GGNNEncode(torch.autograd.Function):
+    """embed -> T x GGNNUpdate.  `plan` = list of (msg_idx, gru_idx, stateful) per step;
+    `params` = [embed_W or None] + n_msg*(W,b) + n_gru*12 tensors.
+    Returns Hs (T+1, mb, N, H) when a tape is needed, else a (2, mb, N, H) tensor [h_0, h_T]."""
+
+    @staticmethod
+    def forward(ctx, x, adj, state_in, plan, n_msg, n_gru, mode, want_stash, *params):
+        _need_cuda(x, adj)
+        adj = _f32(adj)
+        mb, E, N, _ = adj.shape
+        embed_W = params[0]
+        msg = [(params[1 + 2 * i], params[2 + 2 * i]) for i in range(n_msg)]
+        base = 1 + 2 * n_msg
+        gru = [params[base + 12 * i: base + 12 * (i + 1)] for i in range(n_gru)]
+        H = msg[0][0].shape[1]
+        T = len(plan)
+        a = K.GgnnFwd()
+        a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
+        is_ids = x.dtype in (torch.int32, torch.int64)
+        if is_ids:
+            x = x.to(torch.int32).contiguous()
+            a.atoms, a.embed_W, a.n_atom_types = _p(x), _p(embed_W), embed_W.shape[0]
+        else:
+            x = _f32(x)
+            a.h_in = _p(x)
+        state_in = _f32(state_in)
+        a.adj, a.state_in = _p(adj), _p(state_in)
+        for t, (mi, gi, st) in enumerate(plan):
+            a.msg_W[t], a.msg_b[t] = _p(msg[mi][0]), _p(msg[mi][1])
+            _fill_gru(a.gru[t], gru[gi])
+            a.stateful[t] = int(st)
+        dev = adj.device
+        rows = mb * N
+        if want_stash:
+            Hs = torch.empty((T + 1, mb, N, H), device=dev, dtype=torch.float32)
+            Ms = torch.empty((T, rows, H), device=dev, dtype=torch.float32)
+            Gs = torch.empty((T, rows, 3 * H), device=dev, dtype=torch.float32)
+            RSs = torch.empty((T, rows, H), device=dev, dtype=torch.float32)
+            a.Hs, a.Ms, a.Gs, a.RSs = _p(Hs), _p(Ms), _p(Gs), _p(RSs)
+            K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
+            ctx.saved = (x, adj, state_in, Hs, Ms, Gs, RSs, params)
+            ctx.meta = (plan, n_msg, n_gru, mode, is_ids)
+            return Hs
+        out = torch.empty((2, mb, N, H), device=dev, dtype=torch.float32)   # [h_0, h_T]
+        a.h0_out, a.h_out = _p(out[0]), _p(out[1])
+        K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, dHs):
+        x, adj, state_in, Hs, Ms, Gs, RSs, params = ctx.saved
+        plan, n_msg, n_gru, mode, is_ids = ctx.meta
+        T = len(plan)
+        _, mb, N, H = Hs.shape
+        E = adj.shape[1]
+        rows = mb * N
+        dHs = dHs.contiguous().clone()
+        grads = [torch.zeros_like(p) if p is not None else None for p in params]
+        Ps = torch.empty((T, rows, E * H), device=Hs.device, dtype=torch.float32)
+        a = K.GgnnBwd()
+        a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
+        a.adj, a.state_in = _p(adj), _p(state_in)
+        base = 1 + 2 * n_msg
+        for t, (mi, gi, st) in enumerate(plan):
+            a.msg_W[t] = _p(params[1 + 2 * mi])
+            _fill_gru(a.gru[t], params[base + 12 * gi: base + 12 * (gi + 1)])
+            a.stateful[t] = int(st)
+            a.d_msg_W[t], a.d_msg_b[t] = _p(grads[1 + 2 * mi]), _p(grads[2 + 2 * mi])
+            _fill_gru(a.d_gru[t], grads[base + 12 * gi: base + 12 * (gi + 1)])
+        a.Hs, a.Ms, a.RSs, a.Gs, a.Ps, a.dHs = _p(Hs), _p(Ms), _p(RSs), _p(Gs), _p(Ps), _p(dHs)
+        d_state = torch.zeros_like(state_in) if state_in is not None else None
+        a.d_state_in = _p(d_state)
+        K.check(K.lib.bmp_ggnn_backward(C.byref(a), _stream()))
+        dx = None
+        if is_ids:
+            K.check(K.lib.bmp_embed_backward(_p(x), _p(dHs[0]), _p(grads[0]), rows, H, grads[0].shape[0], _stream()))
+        else:
+            dx = dHs[0]
+            grads[0] = None
+        return (dx, None, d_state, None, None, None, None, None) + tuple(grads)
+
+
+class RelGCNEncode(torch.autograd.Function):
+    """embed -> [rescale_adj] -> L x tanh(RelGCNUpdate).  params = [embed_W or None] + L*(Ws,bs,We,be).
+    Returns the final atom states (mb, N, ch[L])."""
+
+    @staticmethod
+    def forward(ctx, x, adj, ch, scale_adj, act, want_stash, *params):
+        _need_cuda(x, adj)
+        adj = _f32(adj)
+        mb, E, N, _ = adj.shape
+        L = len(ch) - 1
+        a = K.RelgcnFwd()
+        a.mb, a.n_atoms, a.n_edge, a.n_layers, a.scale_adj, a.act = mb, N, E, L, int(bool(scale_adj)), act
+        for l, c in enumerate(ch):
+            a.ch[l] = c
+        is_ids = x.dtype in (torch.int32, torch.int64)
+        if is_ids:
+            x = x.to(torch.int32).contiguous()
+            a.atoms, a.embed_W, a.n_atom_types = _p(x), _p(params[0]), params[0].shape[0]
+        else:
+            x = _f32(x)
+            a.h_in = _p(x)
+        a.adj = _p(adj)
+        for l in range(L):
+            Ws, bs, We, be = params[1 + 4 * l: 5 + 4 * l]
+            a.self_W[l], a.self_b[l], a.edge_W[l], a.edge_b[l] = _p(Ws), _p(bs), _p(We), _p(be)
+        rows = mb * N
+        h_out = torch.empty((mb, N, ch[-1]), device=adj.device, dtype=torch.float32)
+        a.h_out = _p(h_out)
+        Hs = None
+        if want_stash:
+            Hs = torch.empty((rows * sum(ch),), device=adj.device, dtype=torch.float32)
+            a.Hs = _p(Hs)
+        K.check(K.lib.bmp_relgcn_forward(C.byref(a), _stream()))
+        if want_stash:
+            ctx.saved = (x, adj, Hs, params)
+            ctx.meta = (tuple(ch), int(bool(scale_adj)), act, is_ids)
+        return h_out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, adj, Hs, params = ctx.saved
+        ch, scale_adj, act, is_ids = ctx.meta
+        mb, E, N, _ = adj.shape
+        L = len(ch) - 1
+        rows = mb * N
+        dev = adj.device
+        d_out = _f32(d_out)
+        grads = [torch.zeros_like(p) if p is not None else None for p in params]
+        Ds = torch.empty((rows * sum(ch[1:]),), device=dev, dtype=torch.float32)
+        Ps = torch.empty((rows * E * sum(ch[1:]),), device=dev, dtype=torch.float32)
+        d_h0 = torch.empty((mb, N, ch[0]), device=dev, dtype=torch.float32)
+        a = K.RelgcnBwd()
+        a.mb, a.n_atoms, a.n_edge, a.n_layers, a.scale_adj, a.act = mb, N, E, L, scale_adj, act
+        for l, c in enumerate(ch):
+            a.ch[l] = c
+        a.adj, a.Hs, a.d_h_out, a.Ds, a.Ps, a.d_h0 = _p(adj), _p(Hs), _p(d_out), _p(Ds), _p(Ps), _p(d_h0)
+        for l in range(L):
+            Ws, bs, We, be = params[1 + 4 * l: 5 + 4 * l]
+            a.self_W[l], a.edge_W[l] = _p(Ws), _p(We)
+            gWs, gbs, gWe, gbe = grads[1 + 4 * l: 5 + 4 * l]
+            a.d_self_W[l], a.d_self_b[l], a.d_edge_W[l], a.d_edge_b[l] = _p(gWs), _p(gbs), _p(gWe), _p(gbe)
+        K.check(K.lib.bmp_relgcn_backward(C.byref(a), _stream()))
+        dx = None
+        if is_ids:
+            K.check(K.lib.bmp_embed_backward(_p(x), _p(d_h0), _p(grads[0]), rows, ch[0], grads[0].shape[0], _stream()))
+        else:
+            dx = d_h0
+            grads[0] = None
+        return (dx, None, None, None, None, None) + tuple(grads)
+
+
+class Readout(torch.autograd.Function):
+    """GGNNReadout variants R1 / R2 / SUM."""
+
+    @staticmethod
+    def forward(ctx, h, h0, mask, variant, act, act_agg, W_i, b_i, W_j, b_j):
+        _need_cuda(h)
+        h, h0, mask = _f32(h), _f32(h0), _f32(mask)
+        mb, N, H = h.shape
+        O = H if variant == K.READOUT_SUM else W_i.shape[0]
+        g = torch.empty((mb, O), device=h.device, dtype=torch.float32)
+        a = K.ReadoutFwd()
+        a.mb, a.n_atoms, a.hidden, a.out_dim, a.variant, a.act, a.act_agg = mb, N, H, O, variant, act, act_agg
+        a.h, a.h0, a.is_real_node = _p(h), _p(h0), _p(mask)
+        a.W_i, a.b_i, a.W_j, a.b_j, a.g = _p(W_i), _p(b_i), _p(W_j), _p(b_j), _p(g)
+        K.check(K.lib.bmp_readout_forward(C.byref(a), _stream()))
+        ctx.saved = (h, h0, mask, W_i, b_i, W_j, b_j, g)
+        ctx.meta = (variant, act, act_agg)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        h, h0, mask, W_i, b_i, W_j, b_j, g = ctx.saved
+        variant, act, act_agg = ctx.meta
+        mb, N, H = h.shape
+        O = g.shape[1]
+        dev = h.device
+        dg = _f32(dg)
+        z = lambda t: torch.zeros_like(t) if t is not None else None
+        dh, dh0 = torch.zeros_like(h), z(h0)
+        gWi, gbi, gWj, gbj = z(W_i), z(b_i), z(W_j), z(b_j)
+        a = K.ReadoutBwd()
+        a.mb, a.n_atoms, a.hidden, a.out_dim, a.variant, a.act, a.act_agg = mb, N, H, O, variant, act, act_agg
+        a.h, a.h0, a.is_real_node = _p(h), _p(h0), _p(mask)
+        a.W_i, a.b_i, a.W_j, a.b_j, a.g, a.dg = _p(W_i), _p(b_i), _p(W_j), _p(b_j), _p(g), _p(dg)
+        if variant != K.READOUT_SUM:
+            DU = torch.empty((mb * N, O), device=dev, dtype=torch.float32)
+            DV = torch.empty((mb * N, O), device=dev, dtype=torch.float32)
+            a.DU, a.DV = _p(DU), _p(DV)
+        a.dh, a.dh0 = _p(dh), _p(dh0)
+        a.d_W_i, a.d_b_i, a.d_W_j, a.d_b_j = _p(gWi), _p(gbi), _p(gWj), _p(gbj)
+        K.check(K.lib.bmp_readout_backward(C.byref(a), _stream()))
+        return dh, dh0, None, None, None, None, gWi, gbi, gWj, gbj
+
+
+class Coattention(torch.autograd.Function):
+    """Fine-grained co-attention (Nie / VQA / Pooling)."""
+
+    @staticmethod
+    def forward(ctx, atoms_1, atoms_2, variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j):
+        _need_cuda(atoms_1, atoms_2)
+        atoms_1, atoms_2 = _f32(atoms_1), _f32(atoms_2)
+        mb, n1, H = atoms_1.shape
+        n2 = atoms_2.shape[1]
+        O = W_j.shape[0]
+        head = lt_1.shape[0] if lt_1 is not None else 0
+        c1 = torch.empty((mb, O), device=atoms_1.device, dtype=torch.float32)
+        c2 = torch.empty_like(c1)
+        a = K.CoattnFwd()
+        a.mb, a.n1, a.n2, a.hidden, a.out_dim, a.head, a.variant, a.act = mb, n1, n2, H, O, head, variant, act
+        a.atoms_1, a.atoms_2 = _p(atoms_1), _p(atoms_2)
+        ps = (W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j)
+        for n, t in zip(K._CO_PARAMS, ps):
+            setattr(a, n, _p(t))
+        a.compact_1, a.compact_2 = _p(c1), _p(c2)
+        K.check(K.lib.bmp_coattn_forward(C.byref(a), _stream()))
+        ctx.saved = (atoms_1, atoms_2) + ps
+        ctx.meta = (variant, act, head)
+        return c1, c2
+
+    @staticmethod
+    def backward(ctx, dc1, dc2):
+        atoms_1, atoms_2 = ctx.saved[:2]
+        ps = ctx.saved[2:]
+        variant, act, head = ctx.meta
+        mb, n1, H = atoms_1.shape
+        n2 = atoms_2.shape[1]
+        O = ps[8].shape[0]
+        dev = atoms_1.device
+        dc1, dc2 = _f32(dc1), _f32(dc2)
+        grads = [torch.zeros_like(t) if t is not None else None for t in ps]
+        da1, da2 = torch.zeros_like(atoms_1), torch.zeros_like(atoms_2)
+        e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        R, P1, P2 = e(mb * n1, H), e(mb, H), e(mb, H)
+        DL1 = e(mb * n1, head) if head else None
+        DL2 = e(mb * n2, head) if head else None
+        a = K.CoattnBwd()
+        a.mb, a.n1, a.n2, a.hidden, a.out_dim, a.head, a.variant, a.act = mb, n1, n2, H, O, head, variant, act
+        a.atoms_1, a.atoms_2 = _p(atoms_1), _p(atoms_2)
+        for n, t, g in zip(K._CO_PARAMS, ps, grads):
+            setattr(a, n, _p(t))
+            setattr(a, "d_" + n, _p(g))
+        a.d_compact_1, a.d_compact_2 = _p(dc1), _p(dc2)
+        a.R, a.P1, a.P2, a.DL1, a.DL2 = _p(R), _p(P1), _p(P2), _p(DL1), _p(DL2)
+        a.d_atoms_1, a.d_atoms_2 = _p(da1), _p(da2)
+        K.check(K.lib.bmp_coattn_backward(C.byref(a), _stream()))
+        return (da1, da2, None, None) + tuple(grads)
+
+
+class HoleCorr(torch.autograd.Function):
+    """circular_correlation(left, right) (hole.py:28-50), direct O(D^2) form."""
+
+    @staticmethod
+    def forward(ctx, left, right):
+        _need_cuda(left, right)
+        left, right = _f32(left), _f32(right)
+        mb, D = left.shape
+        out = torch.empty_like(left)
+        K.check(K.lib.bmp_hole_corr_forward(_p(left), _p(right), _p(out), mb, D, _stream()))
+        ctx.saved = (left, right)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        left, right = ctx.saved
+        mb, D = left.shape
+        d_out = _f32(d_out)
+        dl, dr = torch.empty_like(left), torch.empty_like(right)
+        K.check(K.lib.bmp_hole_corr_backward(_p(left), _p(right), _p(d_out), _p(dl), _p(dr), mb, D, _stream()))
+        return dl, dr
+
+
+class Linear(torch.autograd.Function):
+    """links.Linear + activation: act(x W^T + b)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        _need_cuda(x)
+        x = _f32(x)
+        rows, in_dim = x.shape
+        out_dim = W.shape[0]
+        y = torch.empty((rows, out_dim), device=x.device, dtype=torch.float32)
+        K.check(K.lib.bmp_linear_forward(_p(x), _p(W), _p(b), _p(y), rows, in_dim, out_dim, act, _stream()))
+        ctx.saved = (x, W, b, y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, b, y = ctx.saved
+        rows, in_dim = x.shape
+        out_dim = W.shape[0]
+        dy = dy.contiguous().float().clone()
+        dx = torch.empty_like(x)
+        dW = torch.zeros_like(W)
+        db = torch.zeros_like(b) if b is not None else None
+        K.check(K.lib.bmp_linear_backward(_p(x), _p(W), _p(y), _p(dy), _p(dx), _p(dW), _p(db),
+                                          rows, in_dim, out_dim, ctx.act, _stream()))
+        return dx, dW, db, None
+
+
+class SigmoidCrossEntropy(torch.autograd.Function):
+    """F.sigmoid_cross_entropy(x, t) (train_binary.py:524); `count` overrides the
+    divisor (global element count under data parallelism)."""
+
+    @staticmethod
+    def forward(ctx, x, t, count):
+        _need_cuda(x)
+        x = _f32(x)
+        t = t.to(torch.int32).contiguous()
+        if count is None:
+            count = float(max(int((t != -1).sum().item()), 1))
+        loss = torch.zeros((), device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        K.check(K.lib.bmp_sigmoid_ce(_p(x), _p(t), _p(loss), _p(dx), x.numel(), float(count), _stream()))
+        ctx.saved = dx
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.saved * g, None, None
+
+
+def sigmoid_cross_entropy(x, t, count=None):
+    return SigmoidCrossEntropy.apply(x, t, count)

@@ -1,0 +1,631 @@
+"""Drop-in mirrors of the reference's Chainer links for the message-passing hot
+path: same constructor/`__call__` signatures, same parameter names and shapes
+(`Linear.W` is (out, in), `Bilinear.W` is (H, H, 1), GRU sub-links
+W_r/U_r/W_z/U_z/W/U), same padded `(atom_ids[mb,N], adj[mb,E,N,N])` inputs.
+Every call goes through the ctypes C-ABI into hand-written sm_100a kernels; there
+is no CPU path.  Reference lines are cited per class.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _capi as K
+from . import functional as Fn
+
+MAX_ATOMIC_NUM = 117          # chainer_chemistry.config.MAX_ATOMIC_NUM
+
+
+class functions(object):
+    """Name-compatible stand-ins for the chainer.functions the reference passes as
+    `activation=` arguments (train_binary.py:226-227 passes functions.tanh)."""
+    @staticmethod
+    def identity(x):
+        return x
+
+    @staticmethod
+    def tanh(x):
+        return torch.tanh(x)
+
+    @staticmethod
+    def relu(x):
+        return torch.relu(x)
+
+    @staticmethod
+    def sigmoid(x):
+        return torch.sigmoid(x)
+
+
+_DEFAULT_DEVICE = "cuda" if torch.cuda.is_available() else "cpu"   # parameters only; ops need CUDA
+_GEN = torch.Generator().manual_seed(777)     # reference --seed default, train_binary.py:381
+
+
+def seed(s):
+    _GEN.manual_seed(int(s))
+
+
+def _dev():
+    return torch.device(_DEFAULT_DEVICE)
+
+
+def _as_device(x, dtype=None):
+    """numpy / torch (any device) -> CUDA tensor, like cuda.to_gpu at train_binary.py:85-89."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("gcnbmp: expected numpy.ndarray or torch.Tensor, got %r" % type(x))
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    if not x.is_cuda:
+        x = x.to(_dev(), non_blocking=True)
+    return x
+
+
+def _is_ids(x):
+    return x.dtype in (torch.int32, torch.int64, torch.int16, torch.uint8) if isinstance(x, torch.Tensor) \
+        else np.issubdtype(np.asarray(x).dtype, np.integer)
+
+
+class Link(object):
+    """Minimal chainer.Link look-alike: named parameters + children."""
+
+    def __init__(self):
+        self.__dict__["_params"] = OrderedDict()
+        self.__dict__["_children"] = OrderedDict()
+
+    # -- registration ---------------------------------------------------------
+    def add_param(self, name, shape=None, init="lecun", scale=1.0):
+        t = None
+        if shape is not None and all(s is not None for s in shape):
+            t = _init_tensor(shape, init, scale)
+        self._params[name] = t
+        self.__dict__.setdefault("_pending", {})[name] = (init, scale)
+        return t
+
+    def add_link(self, name, link):
+        self._children[name] = link
+        return link
+
+    def __getattr__(self, name):
+        d = self.__dict__
+        if name in d.get("_params", ()):
+            return d["_params"][name]
+        if name in d.get("_children", ()):
+            return d["_children"][name]
+        raise AttributeError(name)
+
+    def _materialise(self, name, shape):
+        if self._params[name] is None:
+            init, scale = self._pending[name]
+            self._params[name] = _init_tensor(shape, init, scale)
+        return self._params[name]
+
+    # -- chainer-like API -----------------------------------------------------
+    def namedparams(self, include_uninit=False):
+        for n, p in self._params.items():
+            if p is not None or include_uninit:
+                yield "/" + n, p
+        for cn, c in self._children.items():
+            for n, p in c.namedparams(include_uninit):
+                yield "/" + cn + n, p
+
+    def params(self):
+        for _, p in self.namedparams():
+            yield p
+
+    def namedlinks(self):
+        yield "", self
+        for cn, c in self._children.items():
+            for n, l in c.namedlinks():
+                yield "/" + cn + n, l
+
+    def cleargrads(self):
+        for p in self.params():
+            p.grad = None
+
+    zerograds = cleargrads
+
+    def to_gpu(self, device=None):
+        return self
+
+    def count_params(self):
+        return sum(p.numel() for p in self.params())
+
+    def load_params(self, table):
+        """{chainer path: ndarray/tensor}; paths may omit the leading '/'."""
+        table = {("/" + k.lstrip("/")): v for k, v in table.items()}
+        used = set()
+        for path, link in self.namedlinks():
+            for n in list(link._params):
+                key = path + "/" + n
+                if key in table:
+                    v = table[key]
+                    v = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v)
+                    t = v.to(device=_dev(), dtype=torch.float32).contiguous().clone().requires_grad_(True)
+                    cur = link._params[n]
+                    if cur is not None and tuple(cur.shape) != tuple(t.shape):
+                        raise ValueError("gcnbmp: shape mismatch for %s: %s vs %s" % (key, tuple(cur.shape), tuple(t.shape)))
+                    link._params[n] = t
+                    used.add(key)
+        missing = [k for k, p in self.namedparams(True) if k not in used and p is None]
+        if missing:
+            raise KeyError("gcnbmp: uninitialised parameters not found in table: %s" % missing)
+        return self
+
+    def param_dict(self):
+        return OrderedDict((k.lstrip("/"), p.detach().cpu().numpy()) for k, p in self.namedparams())
+
+    def grad_dict(self):
+        return OrderedDict((k.lstrip("/"), (p.grad.detach().cpu().numpy() if p.grad is not None
+                                            else np.zeros(tuple(p.shape), np.float32)))
+                           for k, p in self.namedparams())
+
+    def flatten_parameters(self):
+        """Re-home every parameter (and its gradient) as a view of ONE flat fp32 buffer each,
+        so data-parallel training needs a single allreduce and a single Adam launch."""
+        named = [(k, p) for k, p in self.namedparams()]
+        n = sum(p.numel() for _, p in named)
+        flat = torch.empty(n, device=_dev(), dtype=torch.float32)
+        gflat = torch.zeros(n, device=_dev(), dtype=torch.float32)
+        off = 0
+        index = {}
+        for k, p in named:
+            m = p.numel()
+            flat[off:off + m].copy_(p.detach().reshape(-1))
+            index[k] = (off, m, tuple(p.shape))
+            off += m
+        for path, link in self.namedlinks():
+            for nme in list(link._params):
+                key = path + "/" + nme
+                if key in index:
+                    o, m, shp = index[key]
+                    t = flat[o:o + m].view(shp).requires_grad_(True)
+                    t.grad = gflat[o:o + m].view(shp)
+                    link._params[nme] = t
+        self.__dict__["_flat"] = (flat, gflat, index)
+        return flat, gflat
+
+
+def _init_tensor(shape, init, scale):
+    shape = tuple(int(s) for s in shape)
+    if init == "zero":
+        t = torch.zeros(shape)
+    elif init == "normal":          # EmbedID: N(0, 1)
+        t = torch.randn(shape, generator=_GEN) * scale
+    else:                           # LeCunNormal: std = 1/sqrt(fan_in); Linear.W is (out, in)
+        fan_in = shape[1] if len(shape) == 2 else int(np.prod(shape[:-1])) if len(shape) == 3 else shape[0]
+        if len(shape) == 3:
+            fan_in = shape[0]
+        t = torch.randn(shape, generator=_GEN) * (scale / math.sqrt(max(fan_in, 1)))
+    return t.to(device=_dev(), dtype=torch.float32).requires_grad_(True)
+
+
+class _Linear(Link):
+    """chainer.links.Linear / chainer_chemistry GraphLinear parameters (W (out,in), b)."""
+
+    def __init__(self, in_size, out_size, nobias=False):
+        Link.__init__(self)
+        self.__dict__.update(in_size=in_size, out_size=out_size, nobias=nobias)
+        self.add_param("W", (out_size, in_size))
+        if not nobias:
+            self.add_param("b", (out_size,), init="zero")
+
+    def ensure(self, in_size):
+        self._materialise("W", (self.out_size, in_size))
+        return self
+
+    @property
+    def bias(self):
+        return None if self.nobias else self._params["b"]
+
+    def __call__(self, x, act="identity"):
+        self.ensure(x.shape[-1])
+        lead = x.shape[:-1]
+        y = Fn.Linear.apply(x.reshape(-1, x.shape[-1]), self.W, self.bias, Fn.act_code(act))
+        return y.reshape(lead + (self.out_size,))
+
+
+GraphLinear = _Linear
+
+
+class _GRU(Link):
+    """chainer.links.GRU (= StatefulGRU) parameters: W_r,U_r,W_z,U_z,W,U Linear sub-links."""
+
+    def __init__(self, in_size, out_size):
+        Link.__init__(self)
+        for n in ("W_r", "W_z", "W"):
+            self.add_link(n, _Linear(in_size, out_size))
+        for n in ("U_r", "U_z", "U"):
+            self.add_link(n, _Linear(out_size, out_size))
+        self.__dict__["h"] = None
+
+    def reset_state(self):
+        self.__dict__["h"] = None
+
+    def tensors(self):
+        c = self._children
+        return [c["W_r"].W, c["W_r"].b, c["U_r"].W, c["U_r"].b, c["W_z"].W, c["W_z"].b,
+                c["U_z"].W, c["U_z"].b, c["W"].W, c["W"].b, c["U"].W, c["U"].b]
+
+
+def _encode(x, adj, state, plan, msgs, grus, embed_W, mode):
+    want = torch.is_grad_enabled()
+    params = [embed_W]
+    for W, b in msgs:
+        params += [W, b]
+    for g in grus:
+        params += g.tensors()
+    return Fn.GGNNEncode.apply(x, adj, state, tuple(plan), len(msgs), len(grus), mode, want, *params), want
+
+
+class GGNNUpdate(Link):
+    """models/update/ggnn_update.py:14-66 -- one message-passing step with a stateful GRU."""
+
+    def __init__(self, hidden_dim=16, num_edge_type=4):
+        Link.__init__(self)
+        self.add_link("graph_linear", GraphLinear(hidden_dim, num_edge_type * hidden_dim))
+        self.add_link("update_layer", _GRU(2 * hidden_dim, hidden_dim))
+        self.__dict__.update(num_edge_type=num_edge_type, hidden_dim=hidden_dim, mode=K.MODE_F32)
+
+    def __call__(self, h, adj):
+        h, adj = _as_device(h, torch.float32), _as_device(adj, torch.float32)
+        gru = self.update_layer
+        state = gru.h
+        gl = self.graph_linear
+        out, stash = _encode(h, adj, state, [(0, 0, state is not None)], [(gl.W, gl.b)], [gru], None, self.mode)
+        out = out[1]
+        gru.__dict__["h"] = out
+        return out
+
+    def reset_state(self):
+        self.update_layer.reset_state()
+
+
+class RelGCNUpdate(Link):
+    """models/update/relgcn_update.py:12-44 -- one relational-GCN layer (no activation)."""
+
+    def __init__(self, in_channels, out_channels, num_edge_type=4):
+        Link.__init__(self)
+        self.add_link("graph_linear_self", GraphLinear(in_channels, out_channels))
+        self.add_link("graph_linear_edge", GraphLinear(in_channels, out_channels * num_edge_type))
+        self.__dict__.update(num_edge_type=num_edge_type, in_channels=in_channels, out_channels=out_channels)
+
+    def tensors(self):
+        s, e = self.graph_linear_self, self.graph_linear_edge
+        return [s.W, s.b, e.W, e.b]
+
+    def __call__(self, h, adj):
+        # the bare link has no activation (the tanh lives in models/relgcn.py:70-71)
+        h, adj = _as_device(h, torch.float32), _as_device(adj, torch.float32)
+        return Fn.RelGCNEncode.apply(h, adj, (self.in_channels, self.out_channels), 0, K.ACT["identity"],
+                                     torch.is_grad_enabled(), None, *self.tensors())
+
+
+class GGNNReadout(Link):
+    """models/readout/ggnn_readout.py:13-58 (variant R1: both linears see [h | h0])."""
+
+    def __init__(self, out_dim, hidden_dim=16, nobias=False,
+                 activation=functions.identity, activation_agg=functions.identity):
+        Link.__init__(self)
+        self.add_link("i_layer", GraphLinear(None, out_dim, nobias=nobias))
+        self.add_link("j_layer", GraphLinear(None, out_dim, nobias=nobias))
+        self.__dict__.update(out_dim=out_dim, hidden_dim=hidden_dim, nobias=nobias,
+                             activation=activation, activation_agg=activation_agg)
+
+    def __call__(self, h, h0=None, is_real_node=None):
+        h, h0 = _as_device(h, torch.float32), _as_device(h0, torch.float32)
+        mask = _as_device(is_real_node, torch.float32)
+        kin = h.shape[2] * (2 if h0 is not None else 1)
+        i, j = self.i_layer.ensure(kin), self.j_layer.ensure(kin)
+        return Fn.Readout.apply(h, h0, mask, K.READOUT_R1, Fn.act_code(self.activation),
+                                Fn.act_code(self.activation_agg), i.W, i.bias, j.W, j.bias)
+
+
+class GGNN(Link):
+    """models/models/ggnn.py:26-109 -- embed -> T x GGNNUpdate -> GGNNReadout, as ONE fused
+    encoder launch + one readout launch.  `get_atom_array()` (models/ggnn_att.py:662-664)
+    exposes the final atom states for the co-attention."""
+
+    def __init__(self, out_dim, hidden_dim=16, n_layers=4, n_atom_types=MAX_ATOMIC_NUM,
+                 concat_hidden=False, weight_tying=True, activation=functions.identity,
+                 num_edge_type=4):
+        Link.__init__(self)
+        n_readout_layer = n_layers if concat_hidden else 1
+        n_message_layer = 1 if weight_tying else n_layers
+        self.add_link("embed", _Embed(n_atom_types, hidden_dim))
+        ups = self.add_link("update_layers", ChainList(
+            [GGNNUpdate(hidden_dim=hidden_dim, num_edge_type=num_edge_type) for _ in range(n_message_layer)]))
+        self.add_link("readout_layers", ChainList(
+            [GGNNReadout(out_dim=out_dim, hidden_dim=hidden_dim, activation=activation, activation_agg=activation)
+             for _ in range(n_readout_layer)]))
+        for r in self.readout_layers:
+            r.i_layer.ensure(2 * hidden_dim)
+            r.j_layer.ensure(2 * hidden_dim)
+        self.__dict__.update(out_dim=out_dim, hidden_dim=hidden_dim, n_layers=n_layers,
+                             num_edge_type=num_edge_type, activation=activation,
+                             concat_hidden=concat_hidden, weight_tying=weight_tying,
+                             atoms=None, mode=K.MODE_F32)
+        del ups
+
+    def _plan(self):
+        # tied: one link called T times -> its GRU is stateful from step 1 on (ggnn.py:52,96-97);
+        # untied: T links, each called once after reset_state -> every step stateless (:56-58).
+        if self.weight_tying:
+            return [(0, 0, t > 0) for t in range(self.n_layers)]
+        return [(t, t, False) for t in range(self.n_layers)]
+
+    def __call__(self, atom_array, adj, is_real_node=None):
+        self.reset_state()
+        adj = _as_device(adj, torch.float32)
+        ids = _is_ids(atom_array) and getattr(atom_array, "ndim", 2) <= 2
+        x = _as_device(atom_array, torch.int32 if ids else torch.float32)
+        ups = list(self.update_layers)
+        msgs = [(u.graph_linear.W, u.graph_linear.b) for u in ups]
+        grus = [u.update_layer for u in ups]
+        T = self.n_layers
+        hs, stash = _encode(x, adj, None, self._plan(), msgs, grus, self.embed.W if ids else None, self.mode)
+        h0, hT = hs[0], hs[T if stash else 1]
+        self.__dict__["atoms"] = hT
+        for u in ups:
+            u.update_layer.__dict__["h"] = hT
+        if self.concat_hidden:
+            if not stash:
+                raise RuntimeError("gcnbmp: concat_hidden needs the per-step states; call with grad enabled")
+            gs = [self.readout_layers[t](hs[t + 1], h0, is_real_node) for t in range(T)]
+            return torch.cat(gs, dim=1)
+        return self.readout_layers[0](hT, h0, is_real_node)
+
+    def reset_state(self):
+        for u in self.update_layers:
+            u.reset_state()
+
+    def get_atom_array(self):
+        assert self.atoms is not None
+        return self.atoms
+
+
+class GGNNMono(Link):
+    """The monolithic GGNN the training scripts import (models/ggnn.py = ggnn.py,
+    models/ggnn_att.py:19-664 with default flags, models/ggnn_dev.py:20-172): per-step
+    message GraphLinears when untied, ONE shared stateful GRU (ggnn_att.py:134), readout R2
+    (:338-346) or the sum readout of ggnn_dev.py:167, `get_atom_array(step)`."""
+    NUM_EDGE_TYPE = 4
+
+    def __init__(self, out_dim, hidden_dim=16, n_layers=4, n_atom_types=MAX_ATOMIC_NUM,
+                 concat_hidden=False, weight_tying=True, sum_readout=False):
+        Link.__init__(self)
+        n_readout_layer = n_layers if concat_hidden else 1
+        n_message_layer = 1 if weight_tying else n_layers
+        E = self.NUM_EDGE_TYPE
+        self.add_link("embed", _Embed(n_atom_types, hidden_dim))
+        self.add_link("message_layers", ChainList([GraphLinear(hidden_dim, E * hidden_dim) for _ in range(n_message_layer)]))
+        self.add_link("update_layer", _GRU(2 * hidden_dim, hidden_dim))
+        self.add_link("i_layers", ChainList([GraphLinear(2 * hidden_dim, out_dim) for _ in range(n_readout_layer)]))
+        self.add_link("j_layers", ChainList([GraphLinear(hidden_dim, out_dim) for _ in range(n_readout_layer)]))
+        self.__dict__.update(out_dim=out_dim, hidden_dim=hidden_dim, n_layers=n_layers,
+                             concat_hidden=concat_hidden, weight_tying=weight_tying,
+                             sum_readout=sum_readout, atoms=None, atoms_list=None, mode=K.MODE_F32)
+
+    def readout(self, h, h0, step=0):
+        idx = step if self.concat_hidden else 0
+        i, j = self.i_layers[idx], self.j_layers[idx]
+        return Fn.Readout.apply(h, h0, None, K.READOUT_R2, 0, 0, i.W, i.b, j.W, j.b)
+
+    def __call__(self, atom_array, adj):
+        self.update_layer.reset_state()
+        adj = _as_device(adj, torch.float32)
+        ids = _is_ids(atom_array)
+        x = _as_device(atom_array, torch.int32 if ids else torch.float32)
+        T = self.n_layers
+        msgs = [(m.W, m.b) for m in self.message_layers]
+        plan = [(0 if self.weight_tying else t, 0, t > 0) for t in range(T)]
+        hs, stash = _encode(x, adj, None, plan, msgs, [self.update_layer], self.embed.W if ids else None, self.mode)
+        h0, hT = hs[0], hs[T if stash else 1]
+        self.__dict__["atoms"] = hT
+        self.__dict__["atoms_list"] = [hs[t + 1] for t in range(T)] if stash else None
+        self.update_layer.__dict__["h"] = hT
+        if self.concat_hidden:
+            if not stash:
+                raise RuntimeError("gcnbmp: concat_hidden needs the per-step states; call with grad enabled")
+            return torch.cat([self.readout(hs[t + 1], h0, t) for t in range(T)], dim=1)
+        if self.sum_readout:
+            return Fn.Readout.apply(hT, None, None, K.READOUT_SUM, 0, 0, None, None, None, None)
+        return self.readout(hT, h0, 0)
+
+    def get_atom_array(self, step=-1):
+        assert self.atoms is not None
+        if step in (-1, self.n_layers - 1) or self.atoms_list is None:
+            return self.atoms
+        return self.atoms_list[step]
+
+
+class RelGCN(Link):
+    """models/relgcn.py:31-73 -- embed -> (rescale_adj) -> [tanh(RelGCNUpdate)] x L ->
+    GGNNReadout(nobias, tanh) with h0=None."""
+
+    def __init__(self, out_channels=64, num_edge_type=4, ch_list=None,
+                 n_atom_types=MAX_ATOMIC_NUM, input_type='int', scale_adj=None):
+        Link.__init__(self)
+        if ch_list is None:
+            ch_list = [16, 128, 64]
+        if input_type == 'int':
+            self.add_link("embed", _Embed(n_atom_types, ch_list[0]))
+        elif input_type == 'float':
+            self.add_link("embed", GraphLinear(None, ch_list[0]))
+        else:
+            raise ValueError("[ERROR] Unexpected value input type={}".format(input_type))
+        self.add_link("rgcn_convs", ChainList([RelGCNUpdate(ch_list[i], ch_list[i + 1], num_edge_type)
+                                               for i in range(len(ch_list) - 1)]))
+        ro = self.add_link("rgcn_readout", GGNNReadout(out_dim=out_channels, hidden_dim=ch_list[-1],
+                                                       nobias=True, activation=functions.tanh))
+        ro.i_layer.ensure(ch_list[-1])
+        ro.j_layer.ensure(ch_list[-1])
+        self.__dict__.update(input_type=input_type, scale_adj=scale_adj, ch_list=list(ch_list),
+                             num_edge_type=num_edge_type, atoms=None)
+
+    def __call__(self, h, adj):
+        adj = _as_device(adj, torch.float32)
+        if _is_ids(h):
+            assert self.input_type == 'int'
+            x, emb = _as_device(h, torch.int32), self.embed.W
+        else:
+            assert self.input_type == 'float'
+            x, emb = self.embed(_as_device(h, torch.float32)), None
+        params = [emb]
+        for c in self.rgcn_convs:
+            params += c.tensors()
+        atoms = Fn.RelGCNEncode.apply(x, adj, tuple(self.ch_list), 1 if self.scale_adj else 0, K.ACT["tanh"],
+                                      torch.is_grad_enabled(), *params)
+        self.__dict__["atoms"] = atoms
+        return self.rgcn_readout(atoms)
+
+    def get_atom_array(self):
+        assert self.atoms is not None
+        return self.atoms
+
+
+class _Embed(Link):
+    """chainer_chemistry EmbedAtomID = links.EmbedID(in_size, out_size); W ~ N(0,1)."""
+
+    def __init__(self, in_size, out_size):
+        Link.__init__(self)
+        self.add_param("W", (in_size, out_size), init="normal")
+
+
+class ChainList(Link):
+    def __init__(self, links):
+        Link.__init__(self)
+        for i, l in enumerate(links):
+            self.add_link(str(i), l)
+
+    def __getitem__(self, i):
+        return self._children[str(i if i >= 0 else len(self._children) + i)]
+
+    def __len__(self):
+        return len(self._children)
+
+    def __iter__(self):
+        return iter(self._children.values())
+
+
+class _Bilinear(Link):
+    """chainer.links.Bilinear(left, right, out=1): W (L,R,1), V1 (L,1), V2 (R,1), b (1,)."""
+
+    def __init__(self, left, right, out):
+        Link.__init__(self)
+        self.add_param("W", (left, right, out))
+        self.add_param("V1", (left, out), scale=1.0 / math.sqrt(left))
+        self.add_param("V2", (right, out), scale=1.0 / math.sqrt(right))
+        self.add_param("b", (out,), init="zero")
+
+
+class NieFineCoattention(Link):
+    """models/coattention/nie_coattention.py:312-396."""
+    _default_activation = staticmethod(functions.identity)
+
+    def __init__(self, hidden_dim, out_dim, head, activation=None):
+        Link.__init__(self)
+        self.add_link("energy_layer", _Bilinear(hidden_dim, hidden_dim, 1))
+        self.add_link("attention_layer_1", GraphLinear(head, 1, nobias=True))
+        self.add_link("attention_layer_2", GraphLinear(head, 1, nobias=True))
+        self.add_link("lt_layer_1", GraphLinear(hidden_dim, head, nobias=True))
+        self.add_link("lt_layer_2", GraphLinear(hidden_dim, head, nobias=True))
+        self.add_link("j_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, head=head,
+                             activation=activation if activation is not None else self._default_activation)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        e = self.energy_layer
+        return Fn.Coattention.apply(
+            _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32), K.COATTN_FINE,
+            Fn.act_code(self.activation), e.W, e.V1, e.V2, e.b, self.lt_layer_1.W, self.lt_layer_2.W,
+            self.attention_layer_1.W, self.attention_layer_2.W, self.j_layer.W, self.j_layer.b)
+
+
+class VQAParallelCoattention(NieFineCoattention):
+    """models/coattention/vqa_parallel_coattention.py:13-103 (default activation tanh)."""
+    _default_activation = staticmethod(functions.tanh)
+
+
+class PoolingFineCoattention(Link):
+    """models/coattention/PoolingFineCoattention.py:13-83."""
+
+    def __init__(self, hidden_dim, out_dim, activation=functions.tanh):
+        Link.__init__(self)
+        self.add_link("energy_layer", _Bilinear(hidden_dim, hidden_dim, 1))
+        self.add_link("j_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, activation=activation)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        e = self.energy_layer
+        return Fn.Coattention.apply(
+            _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32), K.COATTN_POOL,
+            Fn.act_code(self.activation), e.W, e.V1, e.V2, e.b, None, None, None, None,
+            self.j_layer.W, self.j_layer.b)
+
+
+class HolE(Link):
+    """models/link_prediction/hole.py:53-91 (= models/mlp.py:113-151, where the layer list is
+    called `layers`): circular correlation -> hidden Linear+act stack -> l_out."""
+
+    def __init__(self, out_dim, hidden_dims=(32, 16), activation=functions.relu, layers_name="hidden_layers"):
+        Link.__init__(self)
+        self.add_link(layers_name, ChainList([_Linear(None, d) for d in hidden_dims]))
+        self.add_link("l_out", _Linear(None, out_dim))
+        self.__dict__.update(activation=activation, layers_name=layers_name)
+
+    def circular_correlation(self, left_x, right_x):
+        return Fn.HoleCorr.apply(_as_device(left_x, torch.float32), _as_device(right_x, torch.float32))
+
+    def __call__(self, left_x, right_x):
+        h = self.circular_correlation(left_x, right_x)
+        for l in self._children[self.layers_name]:
+            h = l(h, self.activation)
+        return self.l_out(h)
+
+
+HOLE = HolE   # hole.py:12-50 defines the same class twice under both spellings
+
+
+class GraphConvPredictorForPair(Link):
+    """train_binary.py:59-141 -- siamese encoder, co-attention, link-prediction head."""
+
+    def __init__(self, graph_conv, attn=None, mlp=None, symmetric=None):
+        Link.__init__(self)
+        self.add_link("graph_conv", graph_conv)
+        if isinstance(mlp, Link):
+            self.add_link("mlp", mlp)
+        else:
+            self.__dict__["mlp"] = mlp
+        if isinstance(attn, Link):
+            self.add_link("attn", attn)
+        else:
+            self.__dict__["attn"] = attn
+        self.__dict__["symmetric"] = symmetric
+
+    def __call__(self, atoms_1, adjs_1, atoms_2, adjs_2):
+        g1 = self.graph_conv(atoms_1, adjs_1)
+        a1 = self.graph_conv.get_atom_array()
+        g2 = self.graph_conv(atoms_2, adjs_2)
+        a2 = self.graph_conv.get_atom_array()
+        if self.attn is not None:
+            g1, g2 = self.attn(a1, g1, a2, g2)
+        if self.mlp is None:
+            raise ValueError('[ERROR] No methods for similarity prediction')
+        return self.mlp(g1, g2)
+
+    def predict(self, atoms_1, adjs_1, atoms_2, adjs_2):
+        with torch.no_grad():
+            x1 = torch.sigmoid(self(atoms_1, adjs_1, atoms_2, adjs_2))
+            if self.symmetric is None:
+                return x1
+            x2 = torch.sigmoid(self(atoms_2, adjs_2, atoms_1, adjs_1))
+            return torch.maximum(x1, x2) if self.symmetric == 'or' else torch.minimum(x1, x2)
+
+
+def sigmoid_cross_entropy(logits, labels, count=None):
+    """F.sigmoid_cross_entropy as used by the Classifier at train_binary.py:524."""
+    return Fn.sigmoid_cross_entropy(logits, _as_device(labels, torch.int32), count)

@@ -124,6 +124,7 @@ int bmp_embed_backward(const int32_t *atoms, const float *dh, float *d_embed_W,
  * applies the column-degree normalisation inside the kernel.                     */
 typedef struct {
     int mb, n_atoms, n_edge, n_layers, n_atom_types, scale_adj;
+    int act;               /* per-layer activation: BMP_ACT_TANH (RelGCN) or BMP_ACT_IDENTITY (bare RelGCNUpdate) */
     int ch[BMP_MAX_STEPS + 1];
     const int32_t *atoms;  const float *h_in;  const float *embed_W;
     const float *adj;
@@ -139,7 +140,7 @@ int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream);
  * Ps: workspace, concatenation over l of (mb*N, E*ch[l+1]) (A_e^T delta);
  * d_h0 (mb*N, ch[0]) receives the gradient w.r.t. h_0.                           */
 typedef struct {
-    int mb, n_atoms, n_edge, n_layers, scale_adj;
+    int mb, n_atoms, n_edge, n_layers, scale_adj, act;
     int ch[BMP_MAX_STEPS + 1];
     const float *adj;
     const float *self_W[BMP_MAX_STEPS], *edge_W[BMP_MAX_STEPS];

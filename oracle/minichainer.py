@@ -136,8 +136,7 @@ def mul(a, b):
 
 
 def sigmoid(x):
-    y = 1.0 / (1.0 + np.exp(-x.data))
-    y = y.astype(x.dtype, copy=False)
+    y = (0.5 * (1.0 + np.tanh(0.5 * x.data))).astype(x.dtype, copy=False)   # overflow-free logistic
     return Var(y, (x,), lambda g: (g * y * (1 - y),))
 
 
@@ -332,6 +331,6 @@ def sigmoid_cross_entropy(x, t):
     val = np.asarray(per.sum() / cnt, dtype=x.dtype)
 
     def push(g):
-        y = 1.0 / (1.0 + np.exp(-xd))
+        y = 0.5 * (1.0 + np.tanh(0.5 * xd))
         return ((g * keep * (y - t) / cnt).astype(x.dtype),)
     return Var(val, (x,), push)

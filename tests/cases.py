@@ -1,0 +1,96 @@
+"""Shared builders for the parity tests: small seeded inputs + parameter tables, and the
+oracle-side evaluation (values + gradients) the CUDA path and the golden files are checked
+against.  Sizes are chosen so the fp64 oracle finishes in well under a second."""
+import numpy as np
+
+from oracle import minichainer as F
+from oracle import reference_path as R
+from gcnbmp import synthetic
+
+
+def _prefixed(d, pre):
+    return {pre + k: v for k, v in d.items()}
+
+
+def pair_case(name, seed=0, dtype=np.float64):
+    """Returns dict(spec=..., params=..., inputs=...).  Specs mirror BASELINE.json configs
+    at parity-test scale."""
+    rng = np.random.default_rng(seed)
+    specs = {
+        # config A: GGNN H32 T4 tied, sum readout, N<=50 (ragged pads: N1=50, N2=47)
+        "A": dict(enc="mono", H=32, T=4, tied=True, sum_readout=True, O=32, attn=None, head=None,
+                  hole_hidden=(), K=1, mb=6, N1=50, N2=47),
+        # config C: GGNN H128 T6 tied + Nie co-attention + HolE -> 86 classes (reduced H for CPU speed)
+        "C": dict(enc="mono", H=32, T=6, tied=True, sum_readout=False, O=32, attn="nie", head=8,
+                  hole_hidden=(), K=86, mb=4, N1=64, N2=64),
+        # headline script: untied message layers, shared GRU, VQA attention, hidden head layers
+        "U": dict(enc="mono", H=16, T=3, tied=False, sum_readout=False, O=16, attn="vqa", head=8,
+                  hole_hidden=(32, 16), K=1, mb=5, N1=23, N2=31),
+        # modular GGNN (models/models/ggnn.py) tied + pooling attention
+        "M": dict(enc="ggnn", H=32, T=3, tied=True, concat_hidden=False, O=24, attn="pool", head=None,
+                  hole_hidden=(), K=1, mb=4, N1=20, N2=18, activation="tanh"),
+        # modular GGNN untied (every step stateless) + HolE without attention
+        "MU": dict(enc="ggnn", H=16, T=3, tied=False, concat_hidden=False, O=16, attn=None, head=None,
+                   hole_hidden=(8,), K=1, mb=3, N1=12, N2=12, activation="identity"),
+        # config B: RelGCN 64->64 x4 (reduced), scale_adj on
+        "B": dict(enc="relgcn", ch=[16, 32, 32], O=16, scale_adj=True, attn=None, head=None,
+                  hole_hidden=(), K=1, mb=5, N1=30, N2=28),
+    }
+    sp = dict(specs[name])
+    mb = sp["mb"]
+    a1, A1 = synthetic.random_molecules(rng, mb, sp["N1"])
+    a2, A2 = synthetic.random_molecules(rng, mb, sp["N2"])
+    if sp["K"] == 1:
+        y = (rng.random((mb, 1)) < 0.33).astype(np.int32)
+    else:
+        y = (rng.random((mb, sp["K"])) < 0.1).astype(np.int32)
+        y[0, 0] = -1      # one ignored label exercises the normaliser
+    if sp["enc"] == "mono":
+        enc_shapes = R.ggnn_mono_shapes(sp["O"], sp["H"], sp["T"], weight_tying=sp["tied"])
+        d_atoms = sp["H"]
+        d_g = sp["H"] if sp["sum_readout"] else sp["O"]
+    elif sp["enc"] == "ggnn":
+        enc_shapes = R.ggnn_shapes(sp["O"], sp["H"], sp["T"], weight_tying=sp["tied"])
+        d_atoms, d_g = sp["H"], sp["O"]
+    else:
+        enc_shapes = R.relgcn_shapes(sp["O"], sp["ch"])
+        d_atoms, d_g = sp["ch"][-1], sp["O"]
+    shapes = _prefixed(enc_shapes, "graph_conv/")
+    d_in = d_g
+    if sp["attn"]:
+        shapes.update(_prefixed(R.coattn_shapes(d_atoms, sp["O"], sp["head"]), "attn/"))
+        d_in = sp["O"]
+    shapes.update(_prefixed(R.hole_shapes(d_in, sp["K"], sp["hole_hidden"]), "mlp/"))
+    params = R.init_params(shapes, rng, dtype=dtype)
+    return dict(name=name, spec=sp, params=params,
+                inputs=(a1, A1.astype(dtype), a2, A2.astype(dtype)), labels=y)
+
+
+def oracle_model(spec, table):
+    P = R.P(table)
+    if spec["enc"] == "mono":
+        enc = R.GGNNMono(P.sub("graph_conv"), spec["O"], spec["H"], spec["T"], weight_tying=spec["tied"],
+                         sum_readout=spec["sum_readout"])
+    elif spec["enc"] == "ggnn":
+        enc = R.GGNN(P.sub("graph_conv"), spec["O"], spec["H"], spec["T"], weight_tying=spec["tied"],
+                     activation=spec.get("activation", "identity"))
+    else:
+        enc = R.RelGCN(P.sub("graph_conv"), spec["O"], ch_list=spec["ch"], scale_adj=spec["scale_adj"])
+    attn = None
+    d_atoms = spec["ch"][-1] if spec["enc"] == "relgcn" else spec["H"]
+    if spec["attn"] == "nie":
+        attn = R.NieFineCoattention(P.sub("attn"), d_atoms, spec["O"], spec["head"], activation="tanh")
+    elif spec["attn"] == "vqa":
+        attn = R.VQAParallelCoattention(P.sub("attn"), d_atoms, spec["O"], spec["head"])
+    elif spec["attn"] == "pool":
+        attn = R.PoolingFineCoattention(P.sub("attn"), d_atoms, spec["O"])
+    mlp = R.HolE(P.sub("mlp"), spec["K"], hidden_dims=spec["hole_hidden"])
+    return R.GraphConvPredictorForPair(enc, attn, mlp)
+
+
+def oracle_eval(case, dtype=np.float64):
+    table = R.wrap_params(case["params"], dtype=dtype)
+    model = oracle_model(case["spec"], table)
+    inputs = tuple(x.astype(dtype) if x.dtype.kind == "f" else x for x in case["inputs"])
+    loss, logits, grads = R.loss_and_grads(model, table, inputs, case["labels"])
+    return dict(loss=np.asarray(loss), logits=logits, grads=grads)

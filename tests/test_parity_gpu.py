@@ -1,0 +1,232 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the drop-in links ->
+ctypes C-ABI, against the fp64 NumPy oracle on the same seeded inputs.
+Bar (BASELINE.json north_star): <= 1e-4 relative in fp32 mode, forward AND gradients."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import product
+from product import rel_err
+from oracle import minichainer as F
+from oracle import reference_path as R
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name", ["A", "C", "U", "M", "MU", "B"])
+def test_pair_forward_backward_matches_oracle(name):
+    case = cases.pair_case(name, seed=11)
+    o = cases.oracle_eval(case)
+    p = product.product_eval(case)
+    assert rel_err(p["logits"], o["logits"]) <= TOL
+    assert abs(p["loss"] - float(o["loss"])) <= TOL * max(1.0, abs(float(o["loss"])))
+    assert set(p["grads"]) == set(o["grads"])
+    for k in sorted(o["grads"]):
+        assert p["grads"][k].shape == o["grads"][k].shape, k
+        assert rel_err(p["grads"][k], o["grads"][k]) <= TOL, (k, rel_err(p["grads"][k], o["grads"][k]))
+
+
+def test_inference_path_equals_training_path():
+    """no_grad takes the stash-free kernel path; outputs must be identical bit for bit."""
+    case = cases.pair_case("C", seed=2)
+    model = product.product_model(case["spec"], case["params"])
+    a1, A1, a2, A2 = case["inputs"]
+    A1, A2 = A1.astype(np.float32), A2.astype(np.float32)
+    y_train = model(a1, A1, a2, A2).detach().cpu().numpy()
+    with torch.no_grad():
+        y_eval = model(a1, A1, a2, A2).cpu().numpy()
+    np.testing.assert_array_equal(y_train, y_eval)
+
+
+def _np_params(shapes, seed):
+    return R.init_params(shapes, np.random.default_rng(seed), dtype=np.float64)
+
+
+def test_ggnn_update_link_state_threading():
+    """GGNNUpdate called repeatedly keeps the StatefulGRU state; after reset_state the first
+    call takes the stateless branch (models/update/ggnn_update.py:31-66)."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(1)
+    H, mb, N = 32, 3, 19
+    shapes = {k[len("update_layers/0/"):]: v for k, v in R.ggnn_shapes(8, H, 1).items() if k.startswith("update_layers/0/")}
+    params = _np_params(shapes, 5)
+    _, adj = synthetic.random_molecules(rng, mb, N)
+    h0 = rng.standard_normal((mb, N, H))
+    other = rng.standard_normal((mb, N, H))
+    # oracle: 3 calls, the third with an input that is NOT the state
+    tab = R.wrap_params(params)
+    hv, ov = F.param(h0), F.param(other)
+    upd = R.GGNNUpdate(R.P(tab), H)
+    o1 = upd(hv, adj.astype(np.float64))
+    o2 = upd(o1, adj.astype(np.float64))
+    o3 = upd(ov, adj.astype(np.float64))          # state (o2) != input (other)
+    F.sum_(F.mul(o3, o3)).backward()
+    link = gcnbmp.GGNNUpdate(hidden_dim=H)
+    link.load_params(params)
+    ht = torch.tensor(h0, dtype=torch.float32, device="cuda", requires_grad=True)
+    ot = torch.tensor(other, dtype=torch.float32, device="cuda", requires_grad=True)
+    A = torch.tensor(adj, device="cuda")
+    p1 = link(ht, A)
+    p2 = link(p1, A)
+    p3 = link(ot, A)
+    (p3 * p3).sum().backward()
+    assert rel_err(p1.detach().cpu().numpy(), o1.data) <= TOL
+    assert rel_err(p3.detach().cpu().numpy(), o3.data) <= TOL
+    assert rel_err(ht.grad.cpu().numpy(), hv.grad) <= TOL
+    assert rel_err(ot.grad.cpu().numpy(), ov.grad) <= TOL
+    g = link.grad_dict()
+    for k in g:
+        assert rel_err(g[k], tab[k].grad) <= TOL, k
+    link.reset_state()
+    p4 = link(ht.detach(), A)
+    assert rel_err(p4.detach().cpu().numpy(), o1.data) <= TOL
+
+
+@pytest.mark.parametrize("act,agg,use_h0,use_mask,nobias", [
+    ("identity", "identity", True, False, False), ("tanh", "tanh", True, True, False),
+    ("tanh", "identity", False, False, True), ("relu", "sigmoid", True, True, False)])
+def test_readout_variants(act, agg, use_h0, use_mask, nobias):
+    import gcnbmp
+    rng = np.random.default_rng(3)
+    mb, N, H, O = 4, 21, 32, 24
+    kin = 2 * H if use_h0 else H
+    shapes = {"i_layer/W": (O, kin), "j_layer/W": (O, kin)}
+    if not nobias:
+        shapes.update({"i_layer/b": (O,), "j_layer/b": (O,)})
+    params = _np_params(shapes, 7)
+    h, h0 = rng.standard_normal((mb, N, H)), rng.standard_normal((mb, N, H))
+    mask = (rng.random((mb, N)) < 0.7).astype(np.float64) if use_mask else None
+    tab = R.wrap_params(params)
+    hv, h0v = F.param(h), F.param(h0)
+    ro = R.GGNNReadout(R.P(tab), O, H, nobias=nobias, activation=act, activation_agg=agg)
+    og = ro(hv, h0v if use_h0 else None, mask)
+    w = rng.standard_normal(og.shape)
+    F.sum_(F.mul(og, F.const(w))).backward()
+    f = gcnbmp.functions
+    link = gcnbmp.GGNNReadout(O, H, nobias=nobias, activation=getattr(f, act), activation_agg=getattr(f, agg))
+    link.load_params(params)
+    ht = torch.tensor(h, dtype=torch.float32, device="cuda", requires_grad=True)
+    h0t = torch.tensor(h0, dtype=torch.float32, device="cuda", requires_grad=True)
+    pg = link(ht, h0t if use_h0 else None, None if mask is None else mask.astype(np.float32))
+    (pg * torch.tensor(w, dtype=torch.float32, device="cuda")).sum().backward()
+    assert rel_err(pg.detach().cpu().numpy(), og.data) <= TOL
+    assert rel_err(ht.grad.cpu().numpy(), hv.grad) <= TOL
+    if use_h0:
+        assert rel_err(h0t.grad.cpu().numpy(), h0v.grad) <= TOL
+    g = link.grad_dict()
+    for k in g:
+        assert rel_err(g[k], tab[k].grad) <= TOL, k
+
+
+def test_relgcn_update_bare_link_and_float_input():
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(8)
+    mb, N, cin, cout = 3, 17, 16, 40
+    _, adj = synthetic.random_molecules(rng, mb, N)
+    adj = adj * rng.random(adj.shape).astype(np.float32)      # fractional adjacency
+    h = rng.standard_normal((mb, N, cin))
+    shapes = {"graph_linear_self/W": (cout, cin), "graph_linear_self/b": (cout,),
+              "graph_linear_edge/W": (cout * 4, cin), "graph_linear_edge/b": (cout * 4,)}
+    params = _np_params(shapes, 2)
+    tab = R.wrap_params(params)
+    hv = F.param(h)
+    o = R.RelGCNUpdate(R.P(tab), cin, cout)(hv, adj.astype(np.float64))
+    F.sum_(F.mul(o, o)).backward()
+    link = gcnbmp.RelGCNUpdate(cin, cout)
+    link.load_params(params)
+    ht = torch.tensor(h, dtype=torch.float32, device="cuda", requires_grad=True)
+    p = link(ht, adj)
+    (p * p).sum().backward()
+    assert rel_err(p.detach().cpu().numpy(), o.data) <= TOL
+    assert rel_err(ht.grad.cpu().numpy(), hv.grad) <= TOL
+    g = link.grad_dict()
+    for k in g:
+        assert rel_err(g[k], tab[k].grad) <= TOL, k
+
+
+@pytest.mark.parametrize("variant,n1,n2,H,O", [("nie", 64, 64, 128, 128), ("vqa", 13, 37, 32, 16),
+                                                ("pool", 50, 9, 64, 32), ("nie", 1, 5, 16, 8)])
+def test_coattention_ragged(variant, n1, n2, H, O):
+    import gcnbmp
+    rng = np.random.default_rng(4)
+    mb, head = 3, 8
+    params = _np_params(R.coattn_shapes(H, O, None if variant == "pool" else head), 6)
+    a1, a2 = rng.standard_normal((mb, n1, H)) * 0.5, rng.standard_normal((mb, n2, H)) * 0.5
+    tab = R.wrap_params(params)
+    v1, v2 = F.param(a1), F.param(a2)
+    if variant == "pool":
+        oc = R.PoolingFineCoattention(R.P(tab), H, O)
+        link = gcnbmp.PoolingFineCoattention(H, O)
+    elif variant == "vqa":
+        oc = R.VQAParallelCoattention(R.P(tab), H, O, head)
+        link = gcnbmp.VQAParallelCoattention(H, O, head)
+    else:
+        oc = R.NieFineCoattention(R.P(tab), H, O, head)       # identity activation default
+        link = gcnbmp.NieFineCoattention(H, O, head)
+    c1, c2 = oc(v1, None, v2, None)
+    w1, w2 = rng.standard_normal(c1.shape), rng.standard_normal(c2.shape)
+    F.add(F.sum_(F.mul(c1, F.const(w1))), F.sum_(F.mul(c2, F.const(w2)))).backward()
+    link.load_params(params)
+    t1 = torch.tensor(a1, dtype=torch.float32, device="cuda", requires_grad=True)
+    t2 = torch.tensor(a2, dtype=torch.float32, device="cuda", requires_grad=True)
+    p1, p2 = link(t1, None, t2, None)
+    dev = lambda x: torch.tensor(x, dtype=torch.float32, device="cuda")
+    ((p1 * dev(w1)).sum() + (p2 * dev(w2)).sum()).backward()
+    assert rel_err(p1.detach().cpu().numpy(), c1.data) <= TOL
+    assert rel_err(p2.detach().cpu().numpy(), c2.data) <= TOL
+    assert rel_err(t1.grad.cpu().numpy(), v1.grad) <= TOL
+    assert rel_err(t2.grad.cpu().numpy(), v2.grad) <= TOL
+    g = link.grad_dict()
+    for k in g:
+        assert rel_err(g[k], tab[k].grad) <= TOL, k
+
+
+@pytest.mark.parametrize("D", [16, 33, 256])
+def test_hole_correlation_matches_fft_oracle(D):
+    import gcnbmp
+    rng = np.random.default_rng(5)
+    l, r = rng.standard_normal((37, D)), rng.standard_normal((37, D))
+    lv, rv = F.param(l), F.param(r)
+    oc = R.HolE(R.P({}), 1, ()).circular_correlation(lv, rv)
+    w = rng.standard_normal(oc.shape)
+    F.sum_(F.mul(oc, F.const(w))).backward()
+    lt = torch.tensor(l, dtype=torch.float32, device="cuda", requires_grad=True)
+    rt = torch.tensor(r, dtype=torch.float32, device="cuda", requires_grad=True)
+    pc = gcnbmp.HolE(1, ()).circular_correlation(lt, rt)
+    (pc * torch.tensor(w, dtype=torch.float32, device="cuda")).sum().backward()
+    assert rel_err(pc.detach().cpu().numpy(), oc.data) <= TOL
+    assert rel_err(lt.grad.cpu().numpy(), lv.grad) <= TOL
+    assert rel_err(rt.grad.cpu().numpy(), rv.grad) <= TOL
+
+
+def test_shape_errors_are_loud():
+    import gcnbmp
+    m = gcnbmp.GGNNMono(8, 16, 2)
+    atoms = np.zeros((1, 65), np.int32)
+    adj = np.zeros((1, 4, 65, 65), np.float32)
+    with pytest.raises(ValueError):
+        m(atoms, adj)
+    with pytest.raises(ValueError):
+        gcnbmp.RelGCN(input_type="complex")
+    with pytest.raises(RuntimeError):
+        gcnbmp.functional.HoleCorr.apply(torch.zeros(2, 4), torch.zeros(2, 4))   # CPU tensors: no fallback
+
+
+def test_single_molecule_and_hidden16_default():
+    """mb = 1, reference default hidden_dim = 16 (GGNN.__init__ default)."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(12)
+    shapes = R.ggnn_shapes(16, 16, 4)
+    params = _np_params(shapes, 13)
+    atoms, adj = synthetic.random_molecules(rng, 1, 9)
+    tab = R.wrap_params(params)
+    og = R.GGNN(R.P(tab), 16, 16, 4)(atoms, adj.astype(np.float64))
+    net = gcnbmp.GGNN(16)
+    net.load_params(params)
+    pg = net(atoms, adj)
+    assert rel_err(pg.detach().cpu().numpy(), og.data) <= TOL
