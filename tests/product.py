@@ -42,7 +42,9 @@ def product_eval(case):
     return dict(loss=loss.item(), logits=logits.detach().cpu().numpy(), grads=model.grad_dict(), model=model)
 
 
-def rel_err(a, b):
-    """max |a-b| / max |b| -- the '1e-4 relative' of BASELINE.json north_star."""
+def rel_err(a, b, floor=1e-30):
+    """max |a-b| / max |b| -- the '1e-4 relative' of BASELINE.json north_star.  `floor` bounds the
+    denominator for quantities that are exactly zero by symmetry (e.g. the gradient of the
+    bilinear bias under an identity activation: both softmaxes are shift-invariant)."""
     b = np.asarray(b, np.float64)
-    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), floor))

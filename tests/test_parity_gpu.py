@@ -182,7 +182,7 @@ def test_coattention_ragged(variant, n1, n2, H, O):
     assert rel_err(t2.grad.cpu().numpy(), v2.grad) <= TOL
     g = link.grad_dict()
     for k in g:
-        assert rel_err(g[k], tab[k].grad) <= TOL, k
+        assert rel_err(g[k], tab[k].grad, floor=1e-3) <= TOL, k
 
 
 @pytest.mark.parametrize("D", [16, 33, 256])
