@@ -553,6 +553,7 @@ extern "C" int bmp_coattn_forward(const bmp_coattn_fwd_t *a, void *stream) {
     }
     int rc = co_check(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant);
     if (rc) return rc;
+    if (!aligned16({a->atoms_1, a->atoms_2, a->W})) { set_error("bmp_coattn_forward: atoms_1, atoms_2, W must be 16-byte aligned"); return BMP_EINVAL; }
     CoArgs A = make_args(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant, a->act, a->atoms_1, a->atoms_2,
                          a->W, a->V1, a->V2, a->b, a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j);
     size_t smem = co_smem_floats(A.H, A.head) * sizeof(float);
@@ -577,6 +578,7 @@ extern "C" int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream) {
     int rc = co_check(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant);
     if (rc) return rc;
     if (a->hidden > BMP_MAX_HIDDEN) { set_error("coattn backward: hidden > %d", BMP_MAX_HIDDEN); return BMP_ESHAPE; }
+    if (!aligned16({a->atoms_1, a->atoms_2, a->W, a->R, a->d_atoms_1, a->d_atoms_2})) { set_error("bmp_coattn_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     CoArgs A = make_args(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant, a->act, a->atoms_1, a->atoms_2,
                          a->W, a->V1, a->V2, a->b, a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j);
     CoBwd B;

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <initializer_list>
 #include "../../include/gcnbmp.h"
 
 namespace bmp {
@@ -24,6 +25,8 @@ constexpr int STAGE_FLOATS = 2 * 64 * XLD;   // two buffers (>= 2*32*68)
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char *what);
+// true when every non-null pointer is 16-byte aligned (cp.async / float4 paths)
+bool aligned16(std::initializer_list<const void *> ps);
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -399,11 +399,21 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
     if (a->mode == BMP_MODE_BF16) return bmp_ggnn_forward_tc(a, stream);
     int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->mode);
     if (rc) return rc;
-    for (int t = 0; t < a->n_steps; ++t)
-        if (!a->msg_W[t] || !a->msg_b[t] || !a->gru[t].W_z || !a->gru[t].W) {
+    for (int t = 0; t < a->n_steps; ++t) {
+        const bmp_gru_t &g = a->gru[t];
+        if (!a->msg_W[t] || !a->msg_b[t] || !g.W_z || !g.W) {
             set_error("bmp_ggnn_forward: null parameter at step %d", t);
             return BMP_EINVAL;
         }
+        if (!aligned16({a->msg_W[t], g.W_r, g.U_r, g.W_z, g.U_z, g.W, g.U})) {
+            set_error("bmp_ggnn_forward: weight matrices must be 16-byte aligned (step %d)", t);
+            return BMP_EINVAL;
+        }
+    }
+    if (!aligned16({a->h_in, a->embed_W, a->state_in, a->h_out, a->h0_out, a->Hs, a->Ms, a->Gs, a->RSs})) {
+        set_error("bmp_ggnn_forward: activation buffers must be 16-byte aligned");
+        return BMP_EINVAL;
+    }
     const int H = a->hidden;
     const bool sep = a->state_in != nullptr;
     size_t smem = fwd_smem_bytes(H, sep, a->n_edge);
@@ -440,6 +450,17 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
     if (H > 128) {
         set_error("bmp_ggnn_backward: hidden=%d > 128 not supported by the fp32 backward kernel", H);
         return BMP_ESHAPE;
+    }
+    for (int t = 0; t < T; ++t) {
+        const bmp_gru_t &g = a->gru[t];
+        if (!aligned16({a->msg_W[t], g.W_r, g.U_r, g.W_z, g.U_z, g.W, g.U})) {
+            set_error("bmp_ggnn_backward: weight matrices must be 16-byte aligned (step %d)", t);
+            return BMP_EINVAL;
+        }
+    }
+    if (!aligned16({a->Hs, a->Ms, a->RSs, a->Gs, a->Ps, a->dHs, a->state_in, a->d_state_in})) {
+        set_error("bmp_ggnn_backward: stash buffers must be 16-byte aligned");
+        return BMP_EINVAL;
     }
     size_t smem = bwd_smem_bytes(H);
     int dev = 0, sms = 148;

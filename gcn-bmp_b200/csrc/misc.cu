@@ -17,6 +17,11 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+bool aligned16(std::initializer_list<const void *> ps) {
+    for (const void *q : ps)
+        if (q && ((uintptr_t)q & 15)) return false;
+    return true;
+}
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();

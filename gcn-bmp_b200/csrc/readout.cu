@@ -154,6 +154,7 @@ extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
         return check_launch("readout_sum_kernel");
     }
     if (!a->W_i || !a->W_j) { set_error("bmp_readout_forward: null weights"); return BMP_EINVAL; }
+    if (!aligned16({a->W_i, a->W_j, a->h, a->h0})) { set_error("bmp_readout_forward: h, h0, W_i, W_j must be 16-byte aligned"); return BMP_EINVAL; }
     const int Kcat = a->h0 ? 2 * a->hidden : a->hidden;
     size_t smem = sizeof(float) * ((size_t)Kcat * AT + STAGE_FLOATS);
     int grid = a->mb < 148 * 2 ? a->mb : 148 * 2;
@@ -179,6 +180,7 @@ extern "C" int bmp_readout_backward(const bmp_readout_bwd_t *a, void *stream) {
         return check_launch("readout_sum_bwd_kernel");
     }
     if (!a->W_i || !a->W_j || !a->g || !a->DU || !a->DV) { set_error("bmp_readout_backward: null argument"); return BMP_EINVAL; }
+    if (!aligned16({a->W_i, a->W_j, a->h, a->h0, a->DU, a->DV, a->dh, a->dh0})) { set_error("bmp_readout_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     const int Kcat = a->h0 ? 2 * H : H;
     const int Kj = a->variant == BMP_READOUT_R2 ? H : Kcat;
     size_t smem = sizeof(float) * ((size_t)(Kcat + 2 * O) * AT + STAGE_FLOATS);

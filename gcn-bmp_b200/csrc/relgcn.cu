@@ -210,7 +210,11 @@ extern "C" int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream) {
     int rc = relgcn_check(a->mb, a->n_atoms, a->n_edge, a->n_layers, a->ch, &cmax);
     if (rc) return rc;
     for (int l = 0; l < a->n_layers; ++l)
-        if (!a->self_W[l] || !a->edge_W[l]) { set_error("bmp_relgcn_forward: null weights at layer %d", l); return BMP_EINVAL; }
+        if (!a->self_W[l] || !a->edge_W[l] || !aligned16({a->self_W[l], a->edge_W[l]})) {
+            set_error("bmp_relgcn_forward: null or misaligned (16 B) weights at layer %d", l);
+            return BMP_EINVAL;
+        }
+    if (!aligned16({a->h_in, a->embed_W, a->h_out, a->Hs})) { set_error("bmp_relgcn_forward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     size_t smem = sizeof(float) * ((size_t)2 * cmax * AT + AT * AT + 8 * AT + AT + STAGE_FLOATS);
     int grid = a->mb < 148 ? a->mb : 148;
     cudaStream_t st = (cudaStream_t)stream;
@@ -236,6 +240,12 @@ extern "C" int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream) {
     int rc = relgcn_check(a->mb, a->n_atoms, a->n_edge, a->n_layers, a->ch, &cmax);
     if (rc) return rc;
     const int L = a->n_layers, E = a->n_edge;
+    for (int l = 0; l < L; ++l)
+        if (!a->self_W[l] || !a->edge_W[l] || !aligned16({a->self_W[l], a->edge_W[l]})) {
+            set_error("bmp_relgcn_backward: null or misaligned (16 B) weights at layer %d", l);
+            return BMP_EINVAL;
+        }
+    if (!aligned16({a->Hs, a->d_h_out, a->Ds, a->Ps, a->d_h0})) { set_error("bmp_relgcn_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     size_t smem = sizeof(float) * ((size_t)2 * cmax * AT + AT * AT + AT + STAGE_FLOATS);
     int grid = a->mb < 148 ? a->mb : 148;
     cudaStream_t st = (cudaStream_t)stream;

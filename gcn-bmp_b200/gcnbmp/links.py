@@ -167,8 +167,9 @@ class Link(object):
         """Re-home every parameter (and its gradient) as a view of ONE flat fp32 buffer each,
         so data-parallel training needs a single allreduce and a single Adam launch."""
         named = [(k, p) for k, p in self.namedparams()]
-        n = sum(p.numel() for _, p in named)
-        flat = torch.empty(n, device=_dev(), dtype=torch.float32)
+        pad = lambda m: (m + 63) // 64 * 64          # every view stays 256-byte aligned (cp.async needs 16)
+        n = sum(pad(p.numel()) for _, p in named)
+        flat = torch.zeros(n, device=_dev(), dtype=torch.float32)
         gflat = torch.zeros(n, device=_dev(), dtype=torch.float32)
         off = 0
         index = {}
@@ -176,7 +177,7 @@ class Link(object):
             m = p.numel()
             flat[off:off + m].copy_(p.detach().reshape(-1))
             index[k] = (off, m, tuple(p.shape))
-            off += m
+            off += pad(m)
         for path, link in self.namedlinks():
             for nme in list(link._params):
                 key = path + "/" + nme

@@ -1,0 +1,121 @@
+"""Training-step driver for the pair predictor: micro-batched forward+backward over a
+(large) batch of drug pairs, optional host->device streaming on a copy stream, one NCCL
+allreduce of the flat gradient buffer under data parallelism, Adam on the flat buffers.
+
+Replaces the StandardUpdater / ParallelUpdater iteration of the reference
+(train_binary.py:546-553: converter=concat_mols -> Classifier -> loss.backward ->
+optimizer.update; ParallelUpdater sums gradients over 2 hard-wired devices)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as K
+from . import links as L
+
+
+class Adam(object):
+    """chainer.optimizers.Adam(alpha, beta1, beta2, eps, weight_decay_rate) on flat buffers
+    (train_binary.py:533-536)."""
+
+    def __init__(self, flat, gflat, alpha=0.001, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay_rate=0.0):
+        self.flat, self.gflat = flat, gflat
+        self.m, self.v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.hp = (alpha, beta1, beta2, eps, weight_decay_rate)
+        self.t = 0
+
+    def update(self):
+        self.t += 1
+        a, b1, b2, eps, wd = self.hp
+        p = lambda t: C.c_void_p(t.data_ptr())
+        K.check(K.lib.bmp_adam_step(p(self.flat), p(self.gflat), p(self.m), p(self.v), self.flat.numel(),
+                                    a, b1, b2, eps, wd, self.t,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+class PairTrainer(object):
+    """One `step()` = forward + backward over all pairs given (split into micro-batches of
+    `chunk` pairs so the activation stash stays bounded), gradient allreduce, Adam update.
+    Inputs may be device tensors (resident) or host arrays/tensors (streamed per chunk through
+    a pinned staging ring on a copy stream, overlapping the previous chunk's compute)."""
+
+    def __init__(self, model, chunk=2048, optimizer=True, world_size=1, process_group=None, **adam):
+        self.model = model
+        self.chunk = int(chunk)
+        self.flat, self.gflat = model.flatten_parameters()
+        self.opt = Adam(self.flat, self.gflat, **adam) if optimizer else None
+        self.world_size = world_size
+        self.pg = process_group
+        self.copy_stream = torch.cuda.Stream()
+        self.loss_buf = torch.zeros((), device=self.flat.device)
+        self.h2d_bytes = 0
+
+    def _chunks(self, n):
+        return [(s, min(n, s + self.chunk)) for s in range(0, n, self.chunk)]
+
+    def _upload(self, arrs, s, e):
+        """host slices -> device on the copy stream; returns (tensors, event)."""
+        out = []
+        with torch.cuda.stream(self.copy_stream):
+            for a in arrs:
+                t = a[s:e]
+                if isinstance(t, np.ndarray):
+                    t = torch.from_numpy(t)
+                self.h2d_bytes += t.numel() * t.element_size()
+                out.append(t.to(self.flat.device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return out, ev
+
+    def step(self, atoms_1, adjs_1, atoms_2, adjs_2, labels, global_count=None):
+        """Returns the (device) scalar loss of this rank's shard, already divided by the
+        global element count so that the summed gradient equals the single-GPU gradient."""
+        arrs = (atoms_1, adjs_1, atoms_2, adjs_2, labels)
+        n = arrs[0].shape[0]
+        on_host = not (isinstance(adjs_1, torch.Tensor) and adjs_1.is_cuda)
+        if global_count is None:
+            global_count = float(n * labels.shape[1] * self.world_size)
+        self.gflat.zero_()
+        self.loss_buf.zero_()
+        chunks = self._chunks(n)
+        nxt = self._upload(arrs, *chunks[0]) if on_host else None
+        cur_stream = torch.cuda.current_stream()
+        for ci, (s, e) in enumerate(chunks):
+            if on_host:
+                (a1, A1, a2, A2, y), ev = nxt
+                cur_stream.wait_event(ev)
+                if ci + 1 < len(chunks):
+                    nxt = self._upload(arrs, *chunks[ci + 1])
+                for t in (a1, A1, a2, A2, y):
+                    t.record_stream(cur_stream)
+            else:
+                a1, A1, a2, A2, y = (a[s:e] for a in arrs)
+            logits = self.model(a1, A1, a2, A2)
+            loss = L.sigmoid_cross_entropy(logits, y, count=global_count)
+            loss.backward()
+            self.loss_buf += loss.detach()
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        if self.opt is not None:
+            self.opt.update()
+        return self.loss_buf
+
+    @torch.no_grad()
+    def predict(self, atoms_1, adjs_1, atoms_2, adjs_2):
+        """Forward only over all pairs (eval_coattention.py:102-126 predict loop)."""
+        n = atoms_1.shape[0]
+        outs = []
+        for s, e in self._chunks(n):
+            outs.append(self.model(atoms_1[s:e], adjs_1[s:e], atoms_2[s:e], adjs_2[s:e]))
+        return torch.cat(outs, dim=0)
+
+
+def algorithmic_flops(H, T, N, E=4, O=None, head=8, K=1, readout="r2", attn=True, D=None):
+    """Forward FLOPs per pair as defined in BASELINE.md section 2 (padded N, MAC = 2)."""
+    O = H if O is None else O
+    f_ro = {"r1": 8, "r2": 6, "sum": 0}[readout] * N * H * O
+    f_g = T * (2 * E * N * H * H + 2 * E * N * N * H + 12 * N * H * H) + (T - 1) * 6 * N * H * H + f_ro
+    f_attn = (2 * N * H * H + 2 * N * N * H + 4 * N * H * head + 4 * N * N * head + 4 * N * H * O) if attn else 0
+    D = O if D is None else D
+    f_head = 2 * D * D + 2 * D * K
+    return dict(encoder=f_g, encoder_steps=f_g - f_ro, attn=f_attn, head=f_head, pair_fwd=2 * f_g + f_attn + f_head)
