@@ -89,7 +89,7 @@ class GGNNEncode(torch.autograd.Function):
             RSs = torch.empty((T, rows, H), device=dev, dtype=torch.float32)
             a.Hs, a.Ms, a.Gs, a.RSs = _p(Hs), _p(Ms), _p(Gs), _p(RSs)
             K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
-            ctx.saved = (x, adj, state_in, Hs, Ms, Gs, RSs, params)
+            ctx.save_for_backward(x, adj, state_in, Hs, Ms, Gs, RSs, *params)
             ctx.meta = (plan, n_msg, n_gru, mode, is_ids)
             return Hs
         out = torch.empty((2, mb, N, H), device=dev, dtype=torch.float32)   # [h_0, h_T]
@@ -99,7 +99,8 @@ class GGNNEncode(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dHs):
-        x, adj, state_in, Hs, Ms, Gs, RSs, params = ctx.saved
+        x, adj, state_in, Hs, Ms, Gs, RSs = ctx.saved_tensors[:7]
+        params = ctx.saved_tensors[7:]
         plan, n_msg, n_gru, mode, is_ids = ctx.meta
         T = len(plan)
         _, mb, N, H = Hs.shape
@@ -165,13 +166,14 @@ class RelGCNEncode(torch.autograd.Function):
             a.Hs = _p(Hs)
         K.check(K.lib.bmp_relgcn_forward(C.byref(a), _stream()))
         if want_stash:
-            ctx.saved = (x, adj, Hs, params)
+            ctx.save_for_backward(x, adj, Hs, *params)
             ctx.meta = (tuple(ch), int(bool(scale_adj)), act, is_ids)
         return h_out
 
     @staticmethod
     def backward(ctx, d_out):
-        x, adj, Hs, params = ctx.saved
+        x, adj, Hs = ctx.saved_tensors[:3]
+        params = ctx.saved_tensors[3:]
         ch, scale_adj, act, is_ids = ctx.meta
         mb, E, N, _ = adj.shape
         L = len(ch) - 1
@@ -217,13 +219,13 @@ class Readout(torch.autograd.Function):
         a.h, a.h0, a.is_real_node = _p(h), _p(h0), _p(mask)
         a.W_i, a.b_i, a.W_j, a.b_j, a.g = _p(W_i), _p(b_i), _p(W_j), _p(b_j), _p(g)
         K.check(K.lib.bmp_readout_forward(C.byref(a), _stream()))
-        ctx.saved = (h, h0, mask, W_i, b_i, W_j, b_j, g)
+        ctx.save_for_backward(h, h0, mask, W_i, b_i, W_j, b_j, g)
         ctx.meta = (variant, act, act_agg)
         return g
 
     @staticmethod
     def backward(ctx, dg):
-        h, h0, mask, W_i, b_i, W_j, b_j, g = ctx.saved
+        h, h0, mask, W_i, b_i, W_j, b_j, g = ctx.saved_tensors
         variant, act, act_agg = ctx.meta
         mb, N, H = h.shape
         O = g.shape[1]
@@ -267,14 +269,14 @@ class Coattention(torch.autograd.Function):
             setattr(a, n, _p(t))
         a.compact_1, a.compact_2 = _p(c1), _p(c2)
         K.check(K.lib.bmp_coattn_forward(C.byref(a), _stream()))
-        ctx.saved = (atoms_1, atoms_2) + ps
+        ctx.save_for_backward(atoms_1, atoms_2, *ps)
         ctx.meta = (variant, act, head)
         return c1, c2
 
     @staticmethod
     def backward(ctx, dc1, dc2):
-        atoms_1, atoms_2 = ctx.saved[:2]
-        ps = ctx.saved[2:]
+        atoms_1, atoms_2 = ctx.saved_tensors[:2]
+        ps = ctx.saved_tensors[2:]
         variant, act, head = ctx.meta
         mb, n1, H = atoms_1.shape
         n2 = atoms_2.shape[1]
@@ -310,12 +312,12 @@ class HoleCorr(torch.autograd.Function):
         mb, D = left.shape
         out = torch.empty_like(left)
         K.check(K.lib.bmp_hole_corr_forward(_p(left), _p(right), _p(out), mb, D, _stream()))
-        ctx.saved = (left, right)
+        ctx.save_for_backward(left, right)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        left, right = ctx.saved
+        left, right = ctx.saved_tensors
         mb, D = left.shape
         d_out = _f32(d_out)
         dl, dr = torch.empty_like(left), torch.empty_like(right)
@@ -334,13 +336,13 @@ class Linear(torch.autograd.Function):
         out_dim = W.shape[0]
         y = torch.empty((rows, out_dim), device=x.device, dtype=torch.float32)
         K.check(K.lib.bmp_linear_forward(_p(x), _p(W), _p(b), _p(y), rows, in_dim, out_dim, act, _stream()))
-        ctx.saved = (x, W, b, y)
+        ctx.save_for_backward(x, W, b, y)
         ctx.act = act
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, W, b, y = ctx.saved
+        x, W, b, y = ctx.saved_tensors
         rows, in_dim = x.shape
         out_dim = W.shape[0]
         dy = dy.contiguous().float().clone()
@@ -366,12 +368,12 @@ class SigmoidCrossEntropy(torch.autograd.Function):
         loss = torch.zeros((), device=x.device, dtype=torch.float32)
         dx = torch.empty_like(x)
         K.check(K.lib.bmp_sigmoid_ce(_p(x), _p(t), _p(loss), _p(dx), x.numel(), float(count), _stream()))
-        ctx.saved = dx
+        ctx.save_for_backward(dx)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        return ctx.saved * g, None, None
+        return ctx.saved_tensors[0] * g, None, None
 
 
 def sigmoid_cross_entropy(x, t, count=None):

@@ -12,6 +12,7 @@ import torch
 
 from . import _capi as K
 from . import links as L
+from . import parallel
 
 
 class Adam(object):
@@ -95,7 +96,7 @@ class PairTrainer(object):
             loss.backward()
             self.loss_buf += loss.detach()
         if self.world_size > 1:
-            torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            parallel.allreduce_sum_(self.gflat, self.pg)
         if self.opt is not None:
             self.opt.update()
         return self.loss_buf

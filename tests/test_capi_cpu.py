@@ -1,0 +1,71 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/gcnbmp.h declares, and the ctypes structures mirror the C structs byte for byte
+(sizes/offsets checked against a gcc-compiled probe).  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gcnbmp.h")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from gcnbmp import _capi
+    text = open(HEADER).read()
+    declared = sorted(set(re.findall(r"\b(bmp_[a-z0-9_]+)\s*\(", text)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(_capi.lib, name), "libgcnbmp.so does not export %s" % name
+    assert sorted(_capi.EXPORTS) == declared
+    assert _capi.lib.bmp_version() >= 100
+
+
+def test_ctypes_structs_mirror_the_header():
+    from gcnbmp import _capi
+    structs = {"bmp_gru_t": _capi.GRU, "bmp_ggnn_fwd_t": _capi.GgnnFwd, "bmp_ggnn_bwd_t": _capi.GgnnBwd,
+               "bmp_relgcn_fwd_t": _capi.RelgcnFwd, "bmp_relgcn_bwd_t": _capi.RelgcnBwd,
+               "bmp_readout_fwd_t": _capi.ReadoutFwd, "bmp_readout_bwd_t": _capi.ReadoutBwd,
+               "bmp_coattn_fwd_t": _capi.CoattnFwd, "bmp_coattn_bwd_t": _capi.CoattnBwd}
+    probes = []
+    for cname, cls in structs.items():
+        probes.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            probes.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "gcnbmp.h"\nint main(void){%s return 0;}\n' % "\n".join(probes)
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "probe.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = subprocess.check_output([exe], text=True)
+    got = dict(line.split() for line in out.strip().splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """The product path has no CPU fallback: without libgcnbmp.so the import raises."""
+    pkg = tmp_path / "gcnbmp"
+    src = os.path.join(ROOT, "gcn-bmp_b200", "gcnbmp")
+    pkg.mkdir()
+    for f in os.listdir(src):
+        if f.endswith(".py"):
+            (pkg / f).write_text(open(os.path.join(src, f)).read())
+    code = "import sys; sys.path.insert(0, %r); import gcnbmp" % str(tmp_path)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    import gcnbmp
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gcnbmp.HolE(1, ()).circular_correlation(torch.zeros(2, 8), torch.zeros(2, 8)) if False else \
+            gcnbmp.functional.HoleCorr.apply(torch.zeros(2, 8), torch.zeros(2, 8))
