@@ -1,9 +1,634 @@
-// ggnn_tc.cu -- tcgen05 (BMP_MODE_BF16) GGNN encoder.  Placeholder until the
-// tensor-core kernel lands: fails loudly, never falls back.
+// ggnn_tc.cu -- fused GGNN encoder on the 5th-gen tensor cores (BMP_MODE_BF16).
+//
+// One persistent CTA per SM; a work item is a TILE of two padded molecules (2 x 64 atoms =
+// 128 rows = one UMMA M).  For all T message-passing steps the tile's adjacency (bf16, exact
+// for 0/1 bonds), its hidden state (bf16 operand copy in smem + fp32 master copy in the
+// epilogue threads' registers) and every intermediate stay on chip; accumulators live in
+// TMEM; the (pre-packed, pre-swizzled bf16) weights stream from L2 with cp.async.bulk (TMA)
+// through an mbarrier ring.  Per step (H = hidden):
+//   MMA-1  AH[(e,i), c]   = sum_j A_e[i,j] h[j,c]        per molecule, two bond types stacked
+//                           on M (128 x 64) x (64 x H); B = the h buffer read MN-major
+//   MMA-2  m[(mol,i), c]  = sum_{e,c'} AH_e[i,c'] W_e[c,c']      K = 4H  (+ deg_e b_e in the epilogue)
+//   MMA-3  [r|z|hbar]     = [h | m] [W_r+U_r | W_z+U_z | W]^T    K = 2H, N = 3H (U folded: state == h)
+//   MMA-4  hbar          += (r*h) U^T                            K = H
+//   epilogue: sigmoid/tanh, h <- z*hbar + (1-z)*h  (fp32), new bf16 operand copy
+// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp%4, column half = warp/4),
+// warp 8 TMA producer, warp 9 MMA issuer (one elected lane each).
+// Replaces models/update/ggnn_update.py:31-63 / models/models/ggnn.py:72-106 like ggnn.cu.
+#include <cuda_bf16.h>
 #include "common.cuh"
+
+namespace bmp {
+namespace tc {
+
+constexpr int NEPI = 256;
+constexpr int NTHR = 320;
+constexpr int PANEL_BYTES = 128 * 128;     // activation panel: 128 rows x 64 bf16, SW128 K-major
+constexpr int ADJ_TILE_BYTES = 64 * 128;   // one (mol, e) adjacency tile: 64 rows x 64 bf16
+
+template <int H>
+struct Cfg {
+    static constexpr int KP = H / 64;
+    static constexpr int TILE_BYTES = H * 128;            // weight tile: H rows (n) x 64 bf16 (k)
+    static constexpr int STAGES = (H == 128) ? 3 : 4;
+    static constexpr int T_MSG = 4 * KP, T_GATE = 2 * KP, T_U = KP;
+    static constexpr int TILES_STATEFUL = T_MSG + 3 * T_GATE + T_U;
+    static constexpr int TILES_STATELESS = T_MSG + 2 * T_GATE;
+    static constexpr int TMEM_COLS = 4 * H;               // 256 or 512 (power of two)
+    static constexpr int OFF_H = 0;
+    static constexpr int OFF_ADJ = OFF_H + KP * PANEL_BYTES;
+    static constexpr int OFF_AH = OFF_ADJ + 8 * ADJ_TILE_BYTES;
+    static constexpr int OFF_W = OFF_AH + 2 * KP * PANEL_BYTES;
+    static constexpr int OFF_BAR = OFF_W + STAGES * TILE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+};
+
+struct Args {
+    int mb, N, T, n_types;
+    const int32_t *atoms;
+    const float *embed_W, *h_in, *adj;
+    const uint8_t *img[BMP_MAX_STEPS];     // packed weight tiles of step t
+    const float *bias3[BMP_MAX_STEPS];     // [b_r | b_z | b_h] (U biases folded for stateful steps)
+    const float *msg_b[BMP_MAX_STEPS];     // (H*4) as in the reference: b[c*4+e]
+    int stateful[BMP_MAX_STEPS];
+    float *h_out, *h0_out, *Hs, *Ms, *Gs, *RSs;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+// smem matrix descriptors (SWIZZLE_128B, version 1).  K-major: SBO = 1024 B (8 rows x 128 B).
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major: LBO = stride between 64-element MN blocks (one panel = 16 KB), SBO = 8 k-rows = 1024 B.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(PANEL_BYTES >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc(int n, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// byte offset of element (row, k) inside a [rows][64] bf16 SW128 K-major block
+__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t k) {
+    return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));
+}
+
+template <int H>
+__global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
+    using C = Cfg<H>;
+    constexpr int KP = C::KP;
+    constexpr int NC = H / 2;   // columns per epilogue thread
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = s32(smem);
+    const uint32_t s_h = sbase + C::OFF_H, s_adj = sbase + C::OFF_ADJ, s_ah = sbase + C::OFF_AH, s_w = sbase + C::OFF_W;
+    const uint32_t s_bar = sbase + C::OFF_BAR;
+    // barriers (8 bytes each)
+    auto BAR = [&](int i) { return s_bar + 8u * i; };
+    constexpr int B_FULL = 0, B_EMPTY = 4, B_HREADY = 8, B_D1 = 9, B_AHREADY = 13, B_AHFREE = 15, B_M = 16,
+                  B_XREADY = 17, B_R = 18, B_RSREADY = 19, B_ZH = 20, NBAR = 21;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BAR + 8 * NBAR + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (a.mb + 1) / 2;
+    const long rows_total = (long)a.mb * a.N;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
+        mbar_init(BAR(B_HREADY), NEPI);
+        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_D1 + i), 1);
+        mbar_init(BAR(B_AHREADY), 2 * NEPI);
+        mbar_init(BAR(B_AHREADY + 1), 2 * NEPI);
+        mbar_init(BAR(B_AHFREE), 1);
+        mbar_init(BAR(B_M), 1);
+        mbar_init(BAR(B_XREADY), NEPI);
+        mbar_init(BAR(B_R), 1);
+        mbar_init(BAR(B_RSREADY), NEPI);
+        mbar_init(BAR(B_ZH), 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===================== TMA producer: stream the weight tiles in consumption order
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int t = 0; t < a.T; ++t) {
+                    const int ntiles = a.stateful[t] ? C::TILES_STATEFUL : C::TILES_STATELESS;
+                    const uint8_t *src = a.img[t];
+                    for (int s = 0; s < ntiles; ++s) {
+                        mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+                        mbar_expect_tx(BAR(B_FULL + stage), C::TILE_BYTES);
+                        tma_bulk_g2s(s_w + stage * C::TILE_BYTES, src + (size_t)s * C::TILE_BYTES, C::TILE_BYTES, BAR(B_FULL + stage));
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t ID_KK = idesc(H, 0), ID_KMN = idesc(H, 1);
+            uint32_t stage = 0, phase = 0, it = 0;
+            // one weight tile: 4 k-steps of 16; A panel base `a_addr` (K-major), D columns `dcol`
+            auto mma_wtile = [&](uint32_t a_addr, uint32_t dcol, bool first) {
+                mbar_wait(BAR(B_FULL + stage), phase);
+                tc_fence_after();
+                const uint32_t b_addr = s_w + stage * C::TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma(tmem + dcol, desc_kmajor(a_addr + k * 32), desc_kmajor(b_addr + k * 32), ID_KK, (first && k == 0) ? 0u : 1u);
+                tc_commit(BAR(B_EMPTY + stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int t = 0; t < a.T; ++t, ++it) {
+                    const uint32_t par = it & 1;
+                    const bool stateful = a.stateful[t] != 0;
+                    mbar_wait(BAR(B_HREADY), par);
+                    tc_fence_after();
+                    // MMA-1: D1[(mol,p)] = [A_2p ; A_2p+1](mol) x h(mol)   (B MN-major from the h panels)
+                    for (int p = 0; p < 2; ++p)
+                        for (int mol = 0; mol < 2; ++mol) {
+                            const uint32_t a_addr = s_adj + (mol * 4 + 2 * p) * ADJ_TILE_BYTES;
+                            const uint32_t b_addr = s_h + mol * 64 * 128;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma(tmem + (2 * p + mol) * H, desc_kmajor(a_addr + k * 32),
+                                       desc_mnmajor(b_addr + k * 16 * 128), ID_KMN, k ? 1u : 0u);
+                            tc_commit(BAR(B_D1 + 2 * p + mol));
+                        }
+                    // MMA-2: m = AHcat Wcat^T, in two K halves (the AH buffer holds one half)
+                    for (int p = 0; p < 2; ++p) {
+                        mbar_wait(BAR(B_AHREADY + p), par);
+                        tc_fence_after();
+                        for (int kp = 0; kp < 2 * KP; ++kp) mma_wtile(s_ah + kp * PANEL_BYTES, 0, p == 0 && kp == 0);
+                        tc_commit(BAR(p == 0 ? B_AHFREE : B_M));
+                    }
+                    // MMA-3: gates over x = [h | m]
+                    mbar_wait(BAR(B_XREADY), par);
+                    tc_fence_after();
+                    auto gate_block = [&](uint32_t dcol) {
+                        for (int kp = 0; kp < 2 * KP; ++kp)
+                            mma_wtile(kp < KP ? s_h + kp * PANEL_BYTES : s_ah + (kp - KP) * PANEL_BYTES, dcol, kp == 0);
+                    };
+                    if (stateful) gate_block(1 * H);
+                    tc_commit(BAR(B_R));
+                    gate_block(2 * H);
+                    gate_block(3 * H);
+                    // MMA-4: hbar += (r*h) U^T
+                    mbar_wait(BAR(B_RSREADY), par);
+                    tc_fence_after();
+                    if (stateful)
+                        for (int kp = 0; kp < KP; ++kp) mma_wtile(s_ah + (KP + kp) * PANEL_BYTES, 3 * H, false);
+                    tc_commit(BAR(B_ZH));
+                }
+        }
+    } else {
+        // ===================== epilogue warps 0..7
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = 32 * q + lane;            // TMEM lane == tile row
+        const int colbase = hf * NC;
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const int molslot = row >> 6, atom = row & 63;
+        float hreg[NC];
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int molg = tile * 2 + molslot;
+            const bool live = molg < a.mb && atom < a.N;
+            const long grow = (long)molg * a.N + atom;       // global row of this thread (if live)
+            // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
+            {
+                const int N = a.N;
+                for (int idx = tid; idx < 8 * 64 * 16; idx += NEPI) {      // (mol,e) x i x (j/4)
+                    const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
+                    const int mg = tile * 2 + (me >> 2);
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (mg < a.mb && i < N) {
+                        const float *src = a.adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j4;
+                        if ((N & 3) == 0 && j4 < N) {
+                            float4 t4 = *reinterpret_cast<const float4 *>(src);
+                            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+                                if (j4 + x < N) v[x] = src[x];
+                        }
+                    }
+                    uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+                    *reinterpret_cast<uint2 *>(smem + C::OFF_ADJ + me * ADJ_TILE_BYTES + sw128(i, j4)) = pk;
+                }
+            }
+            // ---- h_0: embedding gather (or h_in) -> fp32 registers + bf16 operand panels ----
+            {
+                const float *src = nullptr;
+                if (live) {
+                    if (a.atoms) {
+                        int id = a.atoms[grow];
+                        id = id < 0 ? 0 : (id >= a.n_types ? a.n_types - 1 : id);
+                        src = a.embed_W + (long)id * H + colbase;
+                    } else {
+                        src = a.h_in + grow * H + colbase;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NC; c += 4) {
+                    float4 v = src ? *reinterpret_cast<const float4 *>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    hreg[c] = v.x; hreg[c + 1] = v.y; hreg[c + 2] = v.z; hreg[c + 3] = v.w;
+                }
+                if (live) {
+                    if (a.h0_out) {
+#pragma unroll
+                        for (int c = 0; c < NC; c += 4)
+                            *reinterpret_cast<float4 *>(a.h0_out + grow * H + colbase + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
+                    }
+                    if (a.Hs) {
+#pragma unroll
+                        for (int c = 0; c < NC; c += 4)
+                            *reinterpret_cast<float4 *>(a.Hs + grow * H + colbase + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
+                    }
+                }
+            }
+            auto store_h_operand = [&]() {
+#pragma unroll
+                for (int g = 0; g < NC / 8; ++g) {
+                    const int kk = colbase + 8 * g;
+                    uint4 pk = make_uint4(pack_bf16(hreg[8 * g], hreg[8 * g + 1]), pack_bf16(hreg[8 * g + 2], hreg[8 * g + 3]),
+                                          pack_bf16(hreg[8 * g + 4], hreg[8 * g + 5]), pack_bf16(hreg[8 * g + 6], hreg[8 * g + 7]));
+                    *reinterpret_cast<uint4 *>(smem + C::OFF_H + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
+                }
+            };
+            store_h_operand();
+            // degrees deg_e[atom] = sum_j A_e[atom][j]  (from the staged bf16 tile; needs the staging complete)
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI));
+            float deg[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float s = 0.f;
+                const uint8_t *rowp = smem + C::OFF_ADJ + (molslot * 4 + e) * ADJ_TILE_BYTES + atom * 128;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint4 u = *reinterpret_cast<const uint4 *>(rowp + ch * 16);
+                    const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) { float2 f = __bfloat1622float2(b2[x]); s += f.x + f.y; }
+                }
+                deg[e] = s;
+            }
+            fence_proxy_async();
+            mbar_arrive(BAR(B_HREADY));
+
+            for (int t = 0; t < a.T; ++t, ++it) {
+                const uint32_t par = it & 1;
+                const bool stateful = a.stateful[t] != 0;
+                const float *b3 = a.bias3[t];
+                uint32_t v[32];
+                // ---- E1: AH accumulators -> bf16 A-operand panels (two K halves) ----
+                for (int p = 0; p < 2; ++p) {
+                    if (p == 1) mbar_wait(BAR(B_AHFREE), par);      // MMA-2 of half 0 has consumed the buffer
+                    for (int mol = 0; mol < 2; ++mol) {
+                        mbar_wait(BAR(B_D1 + 2 * p + mol), par);
+                        tc_fence_after();
+                        const int orow = mol * 64 + atom;           // row of (mol, atom) in the 128-row tile
+                        const int kbase = molslot * H + colbase;    // TMEM lane half = bond type within the pair
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc += 32) {
+                            tc_ld32(t_lane + (2 * p + mol) * H + colbase + cc, v);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int kk = kbase + cc + 8 * g;
+                                uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                                      pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                                      pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                                      pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                                *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
+                            }
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(BAR(B_AHREADY + p));
+                    }
+                }
+                // ---- E2: message m (+ bias through the degrees) -> bf16 operand (AH panels [0,KP)) ----
+                mbar_wait(BAR(B_M), par);
+                tc_fence_after();
+                {
+                    const float *mb_ = a.msg_b[t];
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc += 32) {
+                        tc_ld32(t_lane + 0 * H + colbase + cc, v);
+                        tc_wait_ld();
+                        float m[32];
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            float4 b4 = __ldg(reinterpret_cast<const float4 *>(mb_) + colbase + cc + x);
+                            m[x] = __uint_as_float(v[x]) + deg[0] * b4.x + deg[1] * b4.y + deg[2] * b4.z + deg[3] * b4.w;
+                        }
+                        if (a.Ms && live) {
+                            float *dst = a.Ms + ((long)t * rows_total + grow) * H + colbase + cc;
+#pragma unroll
+                            for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4 *>(dst + x) = make_float4(m[x], m[x + 1], m[x + 2], m[x + 3]);
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int kk = colbase + cc + 8 * g;
+                            uint4 pk = make_uint4(pack_bf16(m[8 * g], m[8 * g + 1]), pack_bf16(m[8 * g + 2], m[8 * g + 3]),
+                                                  pack_bf16(m[8 * g + 4], m[8 * g + 5]), pack_bf16(m[8 * g + 6], m[8 * g + 7]));
+                            *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(BAR(B_XREADY));
+                // ---- E3: reset gate, r*h -> bf16 operand (AH panels [KP,2KP)) ----
+                mbar_wait(BAR(B_R), par);
+                tc_fence_after();
+                if (stateful) {
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc += 32) {
+                        tc_ld32(t_lane + 1 * H + colbase + cc, v);
+                        tc_wait_ld();
+                        float r[32], rs[32];
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            r[x] = sigmoid_fast(__uint_as_float(v[x]) + __ldg(b3 + colbase + cc + x));
+                            rs[x] = r[x] * hreg[cc + x];
+                        }
+                        if (a.Gs && live) {
+                            float *dst = a.Gs + ((long)t * rows_total + grow) * 3 * H + colbase + cc;
+                            float *dst2 = a.RSs + ((long)t * rows_total + grow) * H + colbase + cc;
+#pragma unroll
+                            for (int x = 0; x < 32; x += 4) {
+                                *reinterpret_cast<float4 *>(dst + x) = make_float4(r[x], r[x + 1], r[x + 2], r[x + 3]);
+                                *reinterpret_cast<float4 *>(dst2 + x) = make_float4(rs[x], rs[x + 1], rs[x + 2], rs[x + 3]);
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int kk = colbase + cc + 8 * g;
+                            uint4 pk = make_uint4(pack_bf16(rs[8 * g], rs[8 * g + 1]), pack_bf16(rs[8 * g + 2], rs[8 * g + 3]),
+                                                  pack_bf16(rs[8 * g + 4], rs[8 * g + 5]), pack_bf16(rs[8 * g + 6], rs[8 * g + 7]));
+                            *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
+                        }
+                    }
+                } else if (a.Gs && live) {   // r / r*h slots of a stateless step: zeros (merged wgrad contractions stay exact)
+                    float *dst = a.Gs + ((long)t * rows_total + grow) * 3 * H + colbase;
+                    float *dst2 = a.RSs + ((long)t * rows_total + grow) * H + colbase;
+#pragma unroll
+                    for (int x = 0; x < NC; x += 4) {
+                        *reinterpret_cast<float4 *>(dst + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(dst2 + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(BAR(B_RSREADY));
+                // ---- E4: update gate + candidate -> new state ----
+                mbar_wait(BAR(B_ZH), par);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < NC; cc += 32) {
+                    uint32_t vz[32];
+                    tc_ld32(t_lane + 2 * H + colbase + cc, vz);
+                    tc_ld32(t_lane + 3 * H + colbase + cc, v);
+                    tc_wait_ld();
+                    float z[32], hb[32];
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) {
+                        z[x] = sigmoid_fast(__uint_as_float(vz[x]) + __ldg(b3 + H + colbase + cc + x));
+                        hb[x] = tanh_fast(__uint_as_float(v[x]) + __ldg(b3 + 2 * H + colbase + cc + x));
+                        hreg[cc + x] = stateful ? fmaf(z[x], hb[x] - hreg[cc + x], hreg[cc + x]) : z[x] * hb[x];
+                    }
+                    if (a.Gs && live) {
+                        float *dst = a.Gs + ((long)t * rows_total + grow) * 3 * H + H + colbase + cc;
+#pragma unroll
+                        for (int x = 0; x < 32; x += 4) {
+                            *reinterpret_cast<float4 *>(dst + x) = make_float4(z[x], z[x + 1], z[x + 2], z[x + 3]);
+                            *reinterpret_cast<float4 *>(dst + H + x) = make_float4(hb[x], hb[x + 1], hb[x + 2], hb[x + 3]);
+                        }
+                    }
+                }
+                if (live) {
+                    if (a.Hs) {
+                        float *dst = a.Hs + ((long)(t + 1) * rows_total + grow) * H + colbase;
+#pragma unroll
+                        for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
+                    }
+                    if (t == a.T - 1 && a.h_out) {
+                        float *dst = a.h_out + grow * H + colbase;
+#pragma unroll
+                        for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
+                    }
+                }
+                if (t + 1 < a.T) {
+                    store_h_operand();
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(BAR(B_HREADY));
+                } else {
+                    tc_fence_before();
+                    asm volatile("bar.sync 1, %0;" ::"n"(NEPI));   // everyone done with this tile's smem/TMEM
+                }
+            }
+        }
+    }
+    // teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------- weight packing
+// Builds the bf16, SW128-swizzled B-operand tiles ([H n][64 k]) of one step in consumption order:
+//   [MMA-2: 4KP tiles, K = e*H + c'] [r: 2KP] [z: 2KP] [hbar: 2KP] [U: KP]   (stateless: no r, no U)
+// and bias3 = [b_Wr+b_Ur | b_Wz(+b_Uz) | b_W(+b_U)].
+struct PackArgs {
+    int H, stateful;
+    const float *msg_W;
+    bmp_gru_t g;
+    uint8_t *img;
+    float *bias3;
+};
+
+__global__ void pack_kernel(const PackArgs p) {
+    const int H = p.H, KP = H / 64;
+    const int t_msg = 4 * KP, t_gate = 2 * KP;
+    const int ntiles = p.stateful ? t_msg + 3 * t_gate + KP : t_msg + 2 * t_gate;
+    const long total = (long)ntiles * H * 64;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int k = idx & 63, n = (idx >> 6) % H, tile = (int)(idx / (64L * H));
+        float w;
+        if (tile < t_msg) {                       // K index = e*H + c'
+            const int K = tile * 64 + k, e = K / H, cp = K % H;
+            w = p.msg_W[((long)n * 4 + e) * H + cp];
+        } else {
+            int g = (tile - t_msg) / t_gate, kp = (tile - t_msg) % t_gate;
+            if (!p.stateful) g += 1;              // stateless images start at the z block
+            if (g < 3) {
+                const int K = kp * 64 + k;        // column of the (H, 2H) gate matrix
+                const float *W = g == 0 ? p.g.W_r : (g == 1 ? p.g.W_z : p.g.W);
+                w = W[(long)n * 2 * H + K];
+                if (p.stateful && K < H && g < 2) w += (g == 0 ? p.g.U_r : p.g.U_z)[(long)n * H + K];   // state == h: fold U
+            } else {                              // U tiles (tile index past the three gate blocks)
+                const int K = (tile - t_msg - 3 * t_gate) * 64 + k;
+                w = p.g.U[(long)n * H + K];
+            }
+        }
+        __nv_bfloat16 b = __float2bfloat16_rn(w);
+        const uint32_t off = (uint32_t)n * 128u + ((((uint32_t)(k >> 3) ^ ((uint32_t)n & 7u)) << 4) | (((uint32_t)k & 7u) << 1));
+        *reinterpret_cast<__nv_bfloat16 *>(p.img + (size_t)tile * H * 128 + off) = b;
+    }
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < H; c += blockDim.x) {
+            p.bias3[c] = p.stateful ? p.g.b_Wr[c] + p.g.b_Ur[c] : 0.f;
+            p.bias3[H + c] = p.g.b_Wz[c] + (p.stateful ? p.g.b_Uz[c] : 0.f);
+            p.bias3[2 * H + c] = p.g.b_W[c] + (p.stateful ? p.g.b_U[c] : 0.f);
+        }
+}
+
+static size_t image_bytes(int H) { return (size_t)(11 * (H / 64)) * H * 128 + 3 * H * sizeof(float) + 256; }
+
+}  // namespace tc
+}  // namespace bmp
+
 using namespace bmp;
+
+extern "C" size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps) {
+    if (hidden != 64 && hidden != 128) return 0;
+    return tc::image_bytes(hidden) * (size_t)n_steps + 1024;
+}
+
 int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
-    (void)a; (void)stream;
-    set_error("BMP_MODE_BF16 encoder is not built in this revision");
-    return BMP_EINVAL;
+    const int H = a->hidden, T = a->n_steps;
+    if (H != 64 && H != 128) { set_error("BMP_MODE_BF16: hidden=%d not supported (64 or 128)", H); return BMP_ESHAPE; }
+    if (a->n_edge != 4) { set_error("BMP_MODE_BF16: n_edge=%d not supported (4)", a->n_edge); return BMP_ESHAPE; }
+    if (a->mb <= 0 || T <= 0 || T > BMP_MAX_STEPS || a->n_atoms <= 0 || a->n_atoms > BMP_MAX_ATOMS) {
+        set_error("BMP_MODE_BF16: bad shape mb=%d T=%d N=%d", a->mb, T, a->n_atoms);
+        return BMP_ESHAPE;
+    }
+    if (a->state_in) { set_error("BMP_MODE_BF16: an external GRU state is not supported (state must equal h)"); return BMP_ESHAPE; }
+    if (!a->tc_workspace || a->tc_workspace_bytes < bmp_ggnn_tc_workspace_bytes(H, T)) {
+        set_error("BMP_MODE_BF16: tc_workspace of >= %zu bytes required", bmp_ggnn_tc_workspace_bytes(H, T));
+        return BMP_EINVAL;
+    }
+    if (!aligned16({a->h_in, a->embed_W, a->adj, a->h_out, a->h0_out, a->Hs, a->Ms, a->Gs, a->RSs, a->tc_workspace})) {
+        set_error("BMP_MODE_BF16: buffers must be 16-byte aligned");
+        return BMP_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::Args k = {};
+    k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.n_types = a->n_atom_types;
+    k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj;
+    k.h_out = a->h_out; k.h0_out = a->h0_out; k.Hs = a->Hs; k.Ms = a->Ms; k.Gs = a->Gs; k.RSs = a->RSs;
+    uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
+    const size_t ib = tc::image_bytes(H);
+    int n_img = 0;
+    for (int t = 0; t < T; ++t) {
+        if (!a->msg_W[t] || !a->msg_b[t] || !a->gru[t].W_z || !a->gru[t].W) { set_error("BMP_MODE_BF16: null parameter at step %d", t); return BMP_EINVAL; }
+        if (((uintptr_t)a->msg_b[t]) & 15) { set_error("BMP_MODE_BF16: msg_b must be 16-byte aligned"); return BMP_EINVAL; }
+        int found = -1;
+        for (int u = 0; u < t; ++u)
+            if (a->msg_W[u] == a->msg_W[t] && a->gru[u].W == a->gru[t].W && a->gru[u].U == a->gru[t].U &&
+                (a->stateful[u] != 0) == (a->stateful[t] != 0)) { found = u; break; }
+        k.stateful[t] = a->stateful[t] != 0;
+        k.msg_b[t] = a->msg_b[t];
+        if (found >= 0) { k.img[t] = k.img[found]; k.bias3[t] = k.bias3[found]; continue; }
+        uint8_t *img = ws + (size_t)n_img * ib;
+        float *bias3 = reinterpret_cast<float *>(img + (size_t)(11 * (H / 64)) * H * 128);
+        tc::PackArgs p;
+        p.H = H; p.stateful = k.stateful[t]; p.msg_W = a->msg_W[t]; p.g = a->gru[t]; p.img = img; p.bias3 = bias3;
+        tc::pack_kernel<<<64, 256, 0, st>>>(p);
+        count_launch();
+        k.img[t] = img; k.bias3[t] = bias3;
+        ++n_img;
+    }
+    int rc = check_launch("pack_kernel");
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = (a->mb + 1) / 2;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    if (H == 64) {
+        cudaFuncSetAttribute(tc::ggnn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<64>::SMEM_BYTES);
+        tc::ggnn_tc_kernel<64><<<grid, tc::NTHR, tc::Cfg<64>::SMEM_BYTES, st>>>(k);
+    } else {
+        cudaFuncSetAttribute(tc::ggnn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<128>::SMEM_BYTES);
+        tc::ggnn_tc_kernel<128><<<grid, tc::NTHR, tc::Cfg<128>::SMEM_BYTES, st>>>(k);
+    }
+    count_launch();
+    return check_launch("ggnn_tc_kernel");
 }

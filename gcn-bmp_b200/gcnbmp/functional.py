@@ -82,6 +82,12 @@ class GGNNEncode(torch.autograd.Function):
             a.stateful[t] = int(st)
         dev = adj.device
         rows = mb * N
+        if mode == K.MODE_BF16:
+            nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
+            if nbytes == 0:
+                raise ValueError("gcnbmp: BMP_MODE_BF16 supports hidden 64 or 128 (got %d)" % H)
+            ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+            a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
         if want_stash:
             Hs = torch.empty((T + 1, mb, N, H), device=dev, dtype=torch.float32)
             Ms = torch.empty((T, rows, H), device=dev, dtype=torch.float32)
@@ -110,7 +116,7 @@ class GGNNEncode(torch.autograd.Function):
         grads = [torch.zeros_like(p) if p is not None else None for p in params]
         Ps = torch.empty((T, rows, E * H), device=Hs.device, dtype=torch.float32)
         a = K.GgnnBwd()
-        a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
+        a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, K.MODE_F32
         a.adj, a.state_in = _p(adj), _p(state_in)
         base = 1 + 2 * n_msg
         for t, (mi, gi, st) in enumerate(plan):

@@ -85,9 +85,13 @@ typedef struct {
     float *h_out;                /* (mb,N,H) final atom states (get_atom_array)     */
     float *h0_out;               /* (mb,N,H) copy of h_0 for the readout, or NULL   */
     float *Hs, *Ms, *Gs, *RSs;   /* stash or NULL                                   */
+    void  *tc_workspace;         /* BMP_MODE_BF16 only: packed bf16 weight tiles    */
+    size_t tc_workspace_bytes;   /* >= bmp_ggnn_tc_workspace_bytes(hidden, n_steps) */
 } bmp_ggnn_fwd_t;
 
 int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
+/* Bytes of device workspace the BMP_MODE_BF16 (tcgen05) encoder needs; 0 = shape unsupported. */
+size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps);
 
 /* Backward of the above (Chainer autograd through the same lines).
  * dHs (T+1, mb*N, H): on entry the external gradient w.r.t. every h_t (zero where

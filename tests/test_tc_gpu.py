@@ -1,0 +1,77 @@
+"""GPU tests of the tcgen05 (BMP_MODE_BF16) encoder: bf16 operands / fp32 accumulate and state.
+Stated bound (measured): atom states within 5e-2 max-relative and 1e-2 rms-relative
+of the fp64 oracle after T steps; pair logits within 5e-2 max-relative.  The fp32 mode stays the
+<= 1e-4 parity path."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import product
+from product import rel_err
+from oracle import reference_path as R
+
+pytestmark = pytest.mark.gpu
+MAX_TOL, RMS_TOL = 5e-2, 1e-2
+
+
+def _rms_rel(a, b):
+    b = np.asarray(b, np.float64)
+    return float(np.sqrt(((np.asarray(a, np.float64) - b) ** 2).mean()) / max(np.sqrt((b ** 2).mean()), 1e-30))
+
+
+@pytest.mark.parametrize("H,T,mb,N,tied", [(64, 3, 5, 64, True), (128, 6, 9, 64, True), (64, 4, 7, 50, False),
+                                           (128, 2, 1, 33, True), (64, 3, 301, 20, True)])
+def test_tc_encoder_matches_oracle_within_bf16_bound(H, T, mb, N, tied):
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(H + T + mb)
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    params = R.init_params(R.ggnn_mono_shapes(H, H, T, weight_tying=tied), rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    onet = R.GGNNMono(R.P(tab), H, H, T, weight_tying=tied)
+    og = onet(atoms, adj.astype(np.float64)).data
+    oatoms = onet.get_atom_array().data
+    net = gcnbmp.GGNNMono(H, H, T, weight_tying=tied)
+    net.load_params(params)
+    net.mode = gcnbmp.MODE_BF16
+    for grad in (False, True):          # stash-free and stashing launches
+        with torch.set_grad_enabled(grad):
+            pg = net(atoms, adj)
+            pa = net.get_atom_array()
+        pa, pg = pa.detach().cpu().numpy(), pg.detach().cpu().numpy()
+        assert np.isfinite(pa).all()
+        assert rel_err(pa, oatoms) <= MAX_TOL and _rms_rel(pa, oatoms) <= RMS_TOL
+        assert rel_err(pg, og) <= MAX_TOL
+
+
+def test_tc_mode_pair_training_step_close_to_oracle():
+    """Full pair fwd+bwd with the tensor-core forward feeding the fp32 backward kernels."""
+    case = cases.pair_case("C", seed=11)
+    sp = dict(case["spec"], H=64, O=64)
+    rng = np.random.default_rng(5)
+    shapes = {"graph_conv/" + k: v for k, v in R.ggnn_mono_shapes(64, 64, sp["T"]).items()}
+    shapes.update({"attn/" + k: v for k, v in R.coattn_shapes(64, 64, 8).items()})
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(64, sp["K"], ()).items()})
+    big = dict(case, spec=sp, params=R.init_params(shapes, rng, dtype=np.float64))
+    o = cases.oracle_eval(big)
+    model = product.product_model(sp, big["params"])
+    model.graph_conv.mode = __import__("gcnbmp").MODE_BF16
+    a1, A1, a2, A2 = big["inputs"]
+    logits = model(a1, A1.astype(np.float32), a2, A2.astype(np.float32))
+    loss = __import__("gcnbmp").sigmoid_cross_entropy(logits, big["labels"])
+    loss.backward()
+    assert rel_err(logits.detach().cpu().numpy(), o["logits"]) <= MAX_TOL
+    g = model.grad_dict()
+    worst = max(_rms_rel(g[k], o["grads"][k]) for k in o["grads"] if np.abs(o["grads"][k]).max() > 1e-6)
+    assert worst <= 5e-2, worst
+
+
+def test_tc_mode_rejects_unsupported_shapes():
+    import gcnbmp
+    from gcnbmp import synthetic
+    atoms, adj = synthetic.random_molecules(np.random.default_rng(0), 2, 10)
+    net = gcnbmp.GGNNMono(32, 32, 2)
+    net.mode = gcnbmp.MODE_BF16
+    with pytest.raises(ValueError):
+        net(atoms, adj)
