@@ -389,7 +389,8 @@ static int check_common(int mb, int N, int H, int E, int T, int mode) {
 
 using namespace bmp;
 
-int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream);   // ggnn_tc.cu
+int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream);    // ggnn_tc.cu
+int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream);   // ggnn_tc_bwd.cu
 
 extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
     if (!a || !a->adj || (!a->atoms && !a->h_in) || (a->atoms && !a->embed_W)) {
@@ -447,7 +448,16 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
     int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, BMP_MODE_F32);
     if (rc) return rc;
     const int H = a->hidden, T = a->n_steps, E = a->n_edge;
-    if (H > 128) {
+    // BMP_MODE_BF16: parameter-gradient contractions on tcgen05 (bias column sums fused in)
+    const bool tcw = a->mode == BMP_MODE_BF16 && (H == 64 || H == 128);
+    auto WG = [&](const float *A_, int lda, const float *B_, int ldb, float *C_, int ldc, long r_, float *db, int dbs) -> int {
+        if (tcw) return bmp_wgrad_tc(A_, lda, B_, ldb, C_, ldc, r_, H, H, db, dbs, stream);
+        int e_ = bmp_wgrad(A_, lda, B_, ldb, C_, ldc, r_, H, H, stream);
+        if (!e_ && db) e_ = bmp_colsum(A_, lda, db, dbs, r_, H, stream);
+        return e_;
+    };
+    const bool tc_data = tcw && E == 4 && !a->state_in;      // data part on tcgen05 as well
+    if (!tc_data && H > 128) {
         set_error("bmp_ggnn_backward: hidden=%d > 128 not supported by the fp32 backward kernel", H);
         return BMP_ESHAPE;
     }
@@ -462,22 +472,26 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         set_error("bmp_ggnn_backward: stash buffers must be 16-byte aligned");
         return BMP_EINVAL;
     }
-    size_t smem = bwd_smem_bytes(H);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = a->mb < sms ? a->mb : sms;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (H <= 64) {
-        cudaFuncSetAttribute(ggnn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ggnn_bwd_kernel<1><<<grid, NTHREADS, smem, st>>>(*a);
+    if (tc_data) {
+        if ((rc = bmp_ggnn_backward_tc(a, stream))) return rc;
     } else {
-        cudaFuncSetAttribute(ggnn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ggnn_bwd_kernel<2><<<grid, NTHREADS, smem, st>>>(*a);
+        size_t smem = bwd_smem_bytes(H);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int grid = a->mb < sms ? a->mb : sms;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (H <= 64) {
+            cudaFuncSetAttribute(ggnn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            ggnn_bwd_kernel<1><<<grid, NTHREADS, smem, st>>>(*a);
+        } else {
+            cudaFuncSetAttribute(ggnn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            ggnn_bwd_kernel<2><<<grid, NTHREADS, smem, st>>>(*a);
+        }
+        count_launch();
+        rc = check_launch("ggnn_bwd_kernel");
+        if (rc) return rc;
     }
-    count_launch();
-    rc = check_launch("ggnn_bwd_kernel");
-    if (rc) return rc;
 
     // ---- parameter gradients: C += A^T B over all atoms of the batch ----
     // Consecutive steps that share parameter pointers are contiguous in every stash,
@@ -500,20 +514,16 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         float *bg[3] = {D.b_Wr, D.b_Wz, D.b_W};
         for (int k = 0; k < 3; ++k) {
             if (!Wg[k]) continue;
-            if ((rc = bmp_wgrad(Gs + k * H, 3 * H, Hs, H, Wg[k], 2 * H, r, H, H, stream))) return rc;
-            if ((rc = bmp_wgrad(Gs + k * H, 3 * H, Ms, H, Wg[k] + H, 2 * H, r, H, H, stream))) return rc;
-            if (bg[k] && (rc = bmp_colsum(Gs + k * H, 3 * H, bg[k], 1, r, H, stream))) return rc;
+            if ((rc = WG(Gs + k * H, 3 * H, Hs, H, Wg[k], 2 * H, r, bg[k], 1))) return rc;
+            if ((rc = WG(Gs + k * H, 3 * H, Ms, H, Wg[k] + H, 2 * H, r, nullptr, 1))) return rc;
         }
         if (a->d_msg_W[t0]) {
-            // dW_m[c*E+e][c'] += sum_rows P[row][e*H+c] * h[row][c']  (row stride E*H in dW_m -> ldc)
+            // dW_m[c*E+e][c'] += sum_rows P[row][e*H+c] * h[row][c']  (row stride E*H in dW_m -> ldc);
+            // db_m[c*E+e] += column sums of P_e, scattered with stride E
             for (int e = 0; e < E; ++e)
-                if ((rc = bmp_wgrad(Ps + e * H, E * H, Hs, H, a->d_msg_W[t0] + (long)e * H, E * H, r, H, H, stream)))
+                if ((rc = WG(Ps + e * H, E * H, Hs, H, a->d_msg_W[t0] + (long)e * H, E * H, r,
+                             a->d_msg_b[t0] ? a->d_msg_b[t0] + e : nullptr, E)))
                     return rc;
-        }
-        if (a->d_msg_b[t0]) {
-            // db_m[c*E+e] += sum_rows P[row][e*H+c]: column sums scattered with stride E
-            for (int e = 0; e < E; ++e)
-                if ((rc = bmp_colsum(Ps + e * H, E * H, a->d_msg_b[t0] + e, E, r, H, stream))) return rc;
         }
         // U-type gradients only over stateful steps
         int s0 = t0;
@@ -526,12 +536,9 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
             const float *St = ext ? a->state_in : a->Hs + (long)s0 * rows * H;
             const float *RS = a->RSs + (long)s0 * rows * H;
             const long rs2 = (long)(s1 - s0 + 1) * rows;
-            if (D.U_r && (rc = bmp_wgrad(Gss, 3 * H, St, H, D.U_r, H, rs2, H, H, stream))) return rc;
-            if (D.U_z && (rc = bmp_wgrad(Gss + H, 3 * H, St, H, D.U_z, H, rs2, H, H, stream))) return rc;
-            if (D.U && (rc = bmp_wgrad(Gss + 2 * H, 3 * H, RS, H, D.U, H, rs2, H, H, stream))) return rc;
-            if (D.b_Ur && (rc = bmp_colsum(Gss, 3 * H, D.b_Ur, 1, rs2, H, stream))) return rc;
-            if (D.b_Uz && (rc = bmp_colsum(Gss + H, 3 * H, D.b_Uz, 1, rs2, H, stream))) return rc;
-            if (D.b_U && (rc = bmp_colsum(Gss + 2 * H, 3 * H, D.b_U, 1, rs2, H, stream))) return rc;
+            if (D.U_r && (rc = WG(Gss, 3 * H, St, H, D.U_r, H, rs2, D.b_Ur, 1))) return rc;
+            if (D.U_z && (rc = WG(Gss + H, 3 * H, St, H, D.U_z, H, rs2, D.b_Uz, 1))) return rc;
+            if (D.U && (rc = WG(Gss + 2 * H, 3 * H, RS, H, D.U, H, rs2, D.b_U, 1))) return rc;
             s0 = s1 + 1;
         }
         t0 = t1 + 1;

@@ -15,16 +15,10 @@
 // Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp%4, column half = warp/4),
 // warp 8 TMA producer, warp 9 MMA issuer (one elected lane each).
 // Replaces models/update/ggnn_update.py:31-63 / models/models/ggnn.py:72-106 like ggnn.cu.
-#include <cuda_bf16.h>
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace bmp {
 namespace tc {
-
-constexpr int NEPI = 256;
-constexpr int NTHR = 320;
-constexpr int PANEL_BYTES = 128 * 128;     // activation panel: 128 rows x 64 bf16, SW128 K-major
-constexpr int ADJ_TILE_BYTES = 64 * 128;   // one (mol, e) adjacency tile: 64 rows x 64 bf16
 
 template <int H>
 struct Cfg {
@@ -53,86 +47,6 @@ struct Args {
     int stateful[BMP_MAX_STEPS];
     float *h_out, *h0_out, *Hs, *Ms, *Gs, *RSs;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra D_%=;\n\t"
-        "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
-
-// smem matrix descriptors (SWIZZLE_128B, version 1).  K-major: SBO = 1024 B (8 rows x 128 B).
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// MN-major: LBO = stride between 64-element MN blocks (one panel = 16 KB), SBO = 8 k-rows = 1024 B.
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(PANEL_BYTES >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D fp32, A/B bf16, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc(int n, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-// byte offset of element (row, k) inside a [rows][64] bf16 SW128 K-major block
-__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t k) {
-    return row * 128u + ((((k >> 3) ^ (row & 7u)) << 4) | ((k & 7u) << 1));
-}
 
 template <int H>
 __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
@@ -266,27 +180,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;       // global row of this thread (if live)
             // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
-            {
-                const int N = a.N;
-                for (int idx = tid; idx < 8 * 64 * 16; idx += NEPI) {      // (mol,e) x i x (j/4)
-                    const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
-                    const int mg = tile * 2 + (me >> 2);
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (mg < a.mb && i < N) {
-                        const float *src = a.adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j4;
-                        if ((N & 3) == 0 && j4 < N) {
-                            float4 t4 = *reinterpret_cast<const float4 *>(src);
-                            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
-                        } else {
-#pragma unroll
-                            for (int x = 0; x < 4; ++x)
-                                if (j4 + x < N) v[x] = src[x];
-                        }
-                    }
-                    uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-                    *reinterpret_cast<uint2 *>(smem + C::OFF_ADJ + me * ADJ_TILE_BYTES + sw128(i, j4)) = pk;
-                }
-            }
+            stage_adjacency(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
             // ---- h_0: embedding gather (or h_in) -> fp32 registers + bf16 operand panels ----
             {
                 const float *src = nullptr;

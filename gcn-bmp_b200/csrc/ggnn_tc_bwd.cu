@@ -1,0 +1,449 @@
+// ggnn_tc_bwd.cu -- backward (data part) of the fused GGNN encoder on tcgen05 (BMP_MODE_BF16).
+//
+// Mirror of ggnn_tc.cu: persistent CTA per SM, a tile = two padded molecules = 128 rows, steps walked in
+// reverse over the forward stash.  The running gradient dL/dh_{t+1} lives in fp32 registers of the
+// epilogue threads; per step (state == step input so U_r/U_z fold into W_r/W_z):
+//   phase A   dz, dhbar -> delta_z, delta_h (bf16 operand panels, fp32 into Gs for the wgrad contractions)
+//   MMA-q     q = delta_h U                      -> phase B: delta_r = q*s*r(1-r), ds += q*r
+//   MMA-dx    [dh_x | dm] = [delta_r|delta_z|delta_h] [W_r+U_r ; W_z+U_z ; W]       K = 3H, N = 2H
+//   MMA-P     P[(e,j), c] = sum_i A_e[i,j] dm[i,c]   per (molecule, bond-type pair); A read MN-major
+//   MMA-dh    dh_x += Pcat Wcat                       K = 4H
+//   phase E   dh_t = dh_x + ds + external dHs[t]
+// Parameter gradients are the C += A^T B contractions of bmp_wgrad_tc over Gs / Ps / Hs / Ms / RSs.
+#include "tc_common.cuh"
+
+namespace bmp {
+namespace tcb {
+using namespace tc;
+
+template <int H>
+struct Cfg {
+    static constexpr int KP = H / 64;
+    static constexpr int TILE_BYTES = H * 128;
+    static constexpr int STAGES = (H == 128) ? 3 : 4;
+    static constexpr int TILES_STATEFUL = 11 * KP;     // q: KP, dx: 6KP, dh: 4KP
+    static constexpr int TILES_STATELESS = 8 * KP;     // dx (z, hbar): 4KP, dh: 4KP
+    static constexpr int TMEM_COLS = 4 * H;
+    static constexpr int OFF_D = 0;                                // delta panels [dr | dz | dh] : 3KP panels
+    static constexpr int OFF_ADJ = OFF_D + 3 * KP * PANEL_BYTES;   //   later: Pcat half (2KP panels) + dm (KP panels)
+    static constexpr int OFF_W = OFF_ADJ + 8 * ADJ_TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_W + STAGES * TILE_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+struct Args {
+    int mb, N, T;
+    const float *adj, *Hs;
+    float *Gs, *Ps, *dHs;
+    const uint8_t *img[BMP_MAX_STEPS];
+    int stateful[BMP_MAX_STEPS];
+};
+
+template <int H>
+__global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
+    using C = Cfg<H>;
+    constexpr int KP = C::KP;
+    constexpr int NC = H / 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = s32(smem);
+    const uint32_t s_d = sbase + C::OFF_D, s_adj = sbase + C::OFF_ADJ, s_w = sbase + C::OFF_W, s_bar = sbase + C::OFF_BAR;
+    const uint32_t s_dm = s_d + 2 * KP * PANEL_BYTES;     // dm panels alias the delta_h panels (dead after MMA-dx)
+    auto BAR = [&](int i) { return s_bar + 8u * i; };
+    constexpr int B_FULL = 0, B_EMPTY = 4, B_DRDY = 8, B_Q = 9, B_DRRDY = 10, B_DX = 11, B_DMRDY = 12, B_P = 13,
+                  B_PRDY = 17, B_PFREE = 19, B_DH = 20, NBAR = 21;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BAR + 8 * NBAR + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (a.mb + 1) / 2;
+    const long rows_total = (long)a.mb * a.N;
+
+    if (tid == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
+        mbar_init(BAR(B_DRDY), NEPI);
+        mbar_init(BAR(B_Q), 1);
+        mbar_init(BAR(B_DRRDY), NEPI);
+        mbar_init(BAR(B_DX), 1);
+        mbar_init(BAR(B_DMRDY), NEPI);
+        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_P + i), 1);
+        mbar_init(BAR(B_PRDY), 2 * NEPI);
+        mbar_init(BAR(B_PRDY + 1), 2 * NEPI);
+        mbar_init(BAR(B_PFREE), 1);
+        mbar_init(BAR(B_DH), 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(C::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns: [0,H) q, then P(0,0) and P(1,1) ; [H,2H) dh_x (+ dh_msg) ; [2H,3H) dm, then P(1,0) ; [3H,4H) P(0,1)
+    constexpr uint32_t COL_Q = 0, COL_DHX = H, COL_DM = 2 * H;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int t = a.T - 1; t >= 0; --t) {
+                    const int ntiles = a.stateful[t] ? C::TILES_STATEFUL : C::TILES_STATELESS;
+                    const uint8_t *src = a.img[t];
+                    for (int s = 0; s < ntiles; ++s) {
+                        mbar_wait(BAR(B_EMPTY + stage), phase ^ 1);
+                        mbar_expect_tx(BAR(B_FULL + stage), C::TILE_BYTES);
+                        tma_bulk_g2s(s_w + stage * C::TILE_BYTES, src + (size_t)s * C::TILE_BYTES, C::TILE_BYTES, BAR(B_FULL + stage));
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            constexpr uint32_t ID_KK = idesc2(H, 0, 0), ID_MNMN = idesc2(H, 1, 1);
+            uint32_t stage = 0, phase = 0, it = 0;
+            auto mma_wtile = [&](uint32_t a_addr, uint32_t dcol, bool first) {
+                mbar_wait(BAR(B_FULL + stage), phase);
+                tc_fence_after();
+                const uint32_t b_addr = s_w + stage * C::TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma(tmem + dcol, desc_kmajor(a_addr + k * 32), desc_kmajor(b_addr + k * 32), ID_KK, (first && k == 0) ? 0u : 1u);
+                tc_commit(BAR(B_EMPTY + stage));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            };
+            // P(mol,p) = [A_2p^T ; A_2p+1^T](mol) x dm(mol): both operands MN-major
+            auto mma_p = [&](int mol, int p, uint32_t dcol, int bar) {
+                const uint32_t a_addr = s_adj + (mol * 4 + 2 * p) * ADJ_TILE_BYTES;
+                const uint32_t b_addr = s_dm + mol * 64 * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma(tmem + dcol, desc_mnmajor_adj(a_addr + k * 16 * 128), desc_mnmajor(b_addr + k * 16 * 128), ID_MNMN, k ? 1u : 0u);
+                tc_commit(BAR(bar));
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int t = a.T - 1; t >= 0; --t, ++it) {
+                    const uint32_t par = it & 1;
+                    const bool stateful = a.stateful[t] != 0;
+                    mbar_wait(BAR(B_DRDY), par);
+                    tc_fence_after();
+                    if (stateful)
+                        for (int kp = 0; kp < KP; ++kp) mma_wtile(s_d + (2 * KP + kp) * PANEL_BYTES, COL_Q, kp == 0);
+                    tc_commit(BAR(B_Q));
+                    // dx over the delta_z and delta_h panels (K blocks 1, 2), both N blocks
+                    for (int kb = 1; kb <= 2; ++kb)
+                        for (int nb = 0; nb < 2; ++nb)
+                            for (int kp = 0; kp < KP; ++kp)
+                                mma_wtile(s_d + (kb * KP + kp) * PANEL_BYTES, nb ? COL_DM : COL_DHX, kb == 1 && kp == 0);
+                    mbar_wait(BAR(B_DRRDY), par);
+                    tc_fence_after();
+                    if (stateful)
+                        for (int nb = 0; nb < 2; ++nb)
+                            for (int kp = 0; kp < KP; ++kp) mma_wtile(s_d + kp * PANEL_BYTES, nb ? COL_DM : COL_DHX, false);
+                    tc_commit(BAR(B_DX));
+                    mbar_wait(BAR(B_DMRDY), par);
+                    tc_fence_after();
+                    mma_p(0, 0, 0 * H, B_P + 0);
+                    mma_p(1, 0, 2 * H, B_P + 1);
+                    mma_p(0, 1, 3 * H, B_P + 2);
+                    mbar_wait(BAR(B_PRDY + 0), par);          // P(0,0) has left columns [0,H); Pcat half 0 is ready
+                    tc_fence_after();
+                    mma_p(1, 1, 0 * H, B_P + 3);
+                    for (int kp = 0; kp < 2 * KP; ++kp) mma_wtile(s_d + kp * PANEL_BYTES, COL_DHX, false);
+                    tc_commit(BAR(B_PFREE));
+                    mbar_wait(BAR(B_PRDY + 1), par);
+                    tc_fence_after();
+                    for (int kp = 0; kp < 2 * KP; ++kp) mma_wtile(s_d + kp * PANEL_BYTES, COL_DHX, false);
+                    tc_commit(BAR(B_DH));
+                }
+        }
+    } else {
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = 32 * q + lane;
+        const int colbase = hf * NC;
+        const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const int molslot = row >> 6, atom = row & 63;
+        float acc[NC];       // dL/dh_{t+1}, then ds, then dL/dh_t
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int molg = tile * 2 + molslot;
+            const bool live = molg < a.mb && atom < a.N;
+            const long grow = (long)molg * a.N + atom;
+            stage_adjacency(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            {
+                const float *src = live ? a.dHs + ((long)a.T * rows_total + grow) * H + colbase : nullptr;
+#pragma unroll
+                for (int c = 0; c < NC; c += 4) {
+                    float4 v = src ? *reinterpret_cast<const float4 *>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[c] = v.x; acc[c + 1] = v.y; acc[c + 2] = v.z; acc[c + 3] = v.w;
+                }
+            }
+            for (int t = a.T - 1; t >= 0; --t, ++it) {
+                const uint32_t par = it & 1;
+                const bool stateful = a.stateful[t] != 0;
+                float *Gt = a.Gs + ((long)t * rows_total + grow) * 3 * H + colbase;          // r | z | hbar slots of this row
+                const float *St = a.Hs + ((long)t * rows_total + grow) * H + colbase;        // state of the step = h_t
+                uint32_t v[32];
+                // ---- phase A: gate derivatives ----
+#pragma unroll
+                for (int cc = 0; cc < NC; cc += 32) {
+                    float dz[32], dh[32];
+#pragma unroll
+                    for (int x = 0; x < 32; x += 4) {
+                        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = z4, s4 = z4;
+                        if (live) {
+                            z4 = *reinterpret_cast<const float4 *>(Gt + H + cc + x);
+                            h4 = *reinterpret_cast<const float4 *>(Gt + 2 * H + cc + x);
+                            if (stateful) s4 = *reinterpret_cast<const float4 *>(St + cc + x);
+                        }
+                        const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            const float g = acc[cc + x + y];
+                            dz[x + y] = g * (hh[y] - ss[y]) * zz[y] * (1.f - zz[y]);
+                            dh[x + y] = g * zz[y] * (1.f - hh[y] * hh[y]);
+                            acc[cc + x + y] = stateful ? g * (1.f - zz[y]) : 0.f;
+                        }
+                    }
+                    if (live) {
+#pragma unroll
+                        for (int x = 0; x < 32; x += 4) {
+                            *reinterpret_cast<float4 *>(Gt + H + cc + x) = make_float4(dz[x], dz[x + 1], dz[x + 2], dz[x + 3]);
+                            *reinterpret_cast<float4 *>(Gt + 2 * H + cc + x) = make_float4(dh[x], dh[x + 1], dh[x + 2], dh[x + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int kk = colbase + cc + 8 * g;
+                        uint4 pz = make_uint4(pack_bf16(dz[8 * g], dz[8 * g + 1]), pack_bf16(dz[8 * g + 2], dz[8 * g + 3]),
+                                              pack_bf16(dz[8 * g + 4], dz[8 * g + 5]), pack_bf16(dz[8 * g + 6], dz[8 * g + 7]));
+                        uint4 ph = make_uint4(pack_bf16(dh[8 * g], dh[8 * g + 1]), pack_bf16(dh[8 * g + 2], dh[8 * g + 3]),
+                                              pack_bf16(dh[8 * g + 4], dh[8 * g + 5]), pack_bf16(dh[8 * g + 6], dh[8 * g + 7]));
+                        *reinterpret_cast<uint4 *>(smem + C::OFF_D + (KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pz;
+                        *reinterpret_cast<uint4 *>(smem + C::OFF_D + (2 * KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = ph;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(BAR(B_DRDY));
+                // ---- phase B: through U and the reset gate ----
+                mbar_wait(BAR(B_Q), par);
+                tc_fence_after();
+                if (stateful) {
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc += 32) {
+                        tc_ld32(t_lane + COL_Q + colbase + cc, v);
+                        tc_wait_ld();
+                        float dr[32];
+#pragma unroll
+                        for (int x = 0; x < 32; x += 4) {
+                            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = r4;
+                            if (live) {
+                                r4 = *reinterpret_cast<const float4 *>(Gt + cc + x);
+                                s4 = *reinterpret_cast<const float4 *>(St + cc + x);
+                            }
+                            const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) {
+                                const float qv = __uint_as_float(v[x + y]);
+                                acc[cc + x + y] += qv * rr[y];
+                                dr[x + y] = qv * ss[y] * rr[y] * (1.f - rr[y]);
+                            }
+                        }
+                        if (live) {
+#pragma unroll
+                            for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4 *>(Gt + cc + x) = make_float4(dr[x], dr[x + 1], dr[x + 2], dr[x + 3]);
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int kk = colbase + cc + 8 * g;
+                            uint4 pr = make_uint4(pack_bf16(dr[8 * g], dr[8 * g + 1]), pack_bf16(dr[8 * g + 2], dr[8 * g + 3]),
+                                                  pack_bf16(dr[8 * g + 4], dr[8 * g + 5]), pack_bf16(dr[8 * g + 6], dr[8 * g + 7]));
+                            *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pr;
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(BAR(B_DRRDY));
+                // ---- phase C: dm -> bf16 operand panels (B of MMA-P) ----
+                mbar_wait(BAR(B_DX), par);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < NC; cc += 32) {
+                    tc_ld32(t_lane + COL_DM + colbase + cc, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int kk = colbase + cc + 8 * g;
+                        uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                              pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                              pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                              pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                        *reinterpret_cast<uint4 *>(smem + C::OFF_D + (2 * KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(BAR(B_DMRDY));
+                // ---- phase D: P accumulators -> bf16 A-operand panels (two K halves) + fp32 stash ----
+                for (int p = 0; p < 2; ++p) {
+                    if (p == 1) mbar_wait(BAR(B_PFREE), par);
+                    for (int mol = 0; mol < 2; ++mol) {
+                        const int pi = 2 * p + mol;                         // (0,0)->0 (1,0)->1 (0,1)->2 (1,1)->3
+                        const uint32_t pcol = (pi == 0 || pi == 3) ? 0u : (pi == 1 ? 2u * H : 3u * H);
+                        mbar_wait(BAR(B_P + pi), par);
+                        tc_fence_after();
+                        const int orow = mol * 64 + atom;                   // row of (mol, atom j) in the tile
+                        const int kbase = molslot * H + colbase;            // TMEM lane half = bond type within the pair
+                        const int omol = tile * 2 + mol;
+                        const bool olive = omol < a.mb && atom < a.N;
+                        float *Pt = a.Ps + (((long)t * rows_total + (long)omol * a.N + atom) * 4 + (2 * p + molslot)) * H + colbase;
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc += 32) {
+                            tc_ld32(t_lane + pcol + colbase + cc, v);
+                            tc_wait_ld();
+                            if (olive) {
+#pragma unroll
+                                for (int x = 0; x < 32; x += 4)
+                                    *reinterpret_cast<float4 *>(Pt + cc + x) = make_float4(__uint_as_float(v[x]), __uint_as_float(v[x + 1]),
+                                                                                           __uint_as_float(v[x + 2]), __uint_as_float(v[x + 3]));
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int kk = kbase + cc + 8 * g;
+                                uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                                      pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                                      pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                                      pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                                *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
+                            }
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(BAR(B_PRDY + p));
+                    }
+                }
+                // ---- phase E: dh_t = dh_x (+ dh_msg) + ds + external gradient ----
+                mbar_wait(BAR(B_DH), par);
+                tc_fence_after();
+                {
+                    float *ext = a.dHs + ((long)t * rows_total + grow) * H + colbase;
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc += 32) {
+                        tc_ld32(t_lane + COL_DHX + colbase + cc, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int x = 0; x < 32; x += 4) {
+                            float4 e4 = live ? *reinterpret_cast<const float4 *>(ext + cc + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            acc[cc + x] += __uint_as_float(v[x]) + e4.x;
+                            acc[cc + x + 1] += __uint_as_float(v[x + 1]) + e4.y;
+                            acc[cc + x + 2] += __uint_as_float(v[x + 2]) + e4.z;
+                            acc[cc + x + 3] += __uint_as_float(v[x + 3]) + e4.w;
+                        }
+                    }
+                    if (t == 0 && live) {
+#pragma unroll
+                        for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(ext + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                    }
+                }
+                tc_fence_before();
+                if (t == 0) asm volatile("bar.sync 1, %0;" ::"n"(NEPI));   // tile finished: smem/TMEM may be re-staged
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
+    }
+}
+
+// ---- weight images for the backward: tiles [H n][64 k] bf16, SW128, in consumption order
+//   stateful : [q: KP] [z: dhx KP, dm KP] [hbar: dhx KP, dm KP] [r: dhx KP, dm KP] [dh: 4KP]
+//   stateless:         [z: dhx KP, dm KP] [hbar: dhx KP, dm KP]                     [dh: 4KP]
+struct PackArgs {
+    int H, stateful;
+    const float *msg_W;
+    bmp_gru_t g;
+    uint8_t *img;
+};
+
+__global__ void pack_bwd_kernel(const PackArgs p) {
+    const int H = p.H, KP = H / 64;
+    const int nq = p.stateful ? KP : 0, ndx = p.stateful ? 6 * KP : 4 * KP;
+    const int ntiles = nq + ndx + 4 * KP;
+    const long total = (long)ntiles * H * 64;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int k = idx & 63, n = (idx >> 6) % H, tile = (int)(idx / (64L * H));
+        float w;
+        if (tile < nq) {                                   // q[row][n] = sum_c delta_h[row][c] U[c][n]
+            const int c = tile * 64 + k;
+            w = p.g.U[(long)c * H + n];
+        } else if (tile < nq + ndx) {
+            const int u = tile - nq, kb = u / (2 * KP), nb = (u / KP) & 1, kp = u % KP;
+            const int gate = kb == 0 ? 1 : (kb == 1 ? 2 : 0);                 // z, hbar, r
+            const int c = kp * 64 + k;
+            const float *W = gate == 0 ? p.g.W_r : (gate == 1 ? p.g.W_z : p.g.W);
+            w = W[(long)c * 2 * H + nb * H + n];
+            if (p.stateful && nb == 0 && gate < 2) w += (gate == 0 ? p.g.U_r : p.g.U_z)[(long)c * H + n];
+        } else {                                           // dh[row][n] = sum_{e,c} P_e[row][c] W_e[c][n]
+            const int K = (tile - nq - ndx) * 64 + k, e = K / H, c = K % H;
+            w = p.msg_W[((long)c * 4 + e) * H + n];
+        }
+        __nv_bfloat16 b = __float2bfloat16_rn(w);
+        const uint32_t off = (uint32_t)n * 128u + ((((uint32_t)(k >> 3) ^ ((uint32_t)n & 7u)) << 4) | (((uint32_t)k & 7u) << 1));
+        *reinterpret_cast<__nv_bfloat16 *>(p.img + (size_t)tile * H * 128 + off) = b;
+    }
+}
+
+static size_t image_bytes(int H) { return (size_t)(11 * (H / 64)) * H * 128 + 256; }
+
+}  // namespace tcb
+}  // namespace bmp
+
+using namespace bmp;
+
+// Data part of the backward on tcgen05; called by bmp_ggnn_backward when mode == BMP_MODE_BF16.
+int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
+    const int H = a->hidden, T = a->n_steps;
+    if (!a->tc_workspace || a->tc_workspace_bytes < bmp_ggnn_tc_workspace_bytes(H, T)) {
+        set_error("BMP_MODE_BF16 backward: tc_workspace of >= %zu bytes required", bmp_ggnn_tc_workspace_bytes(H, T));
+        return BMP_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    tcb::Args k = {};
+    k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.adj = a->adj; k.Hs = a->Hs; k.Gs = a->Gs; k.Ps = a->Ps; k.dHs = a->dHs;
+    uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
+    const size_t ib = tcb::image_bytes(H);
+    int n_img = 0;
+    for (int t = 0; t < T; ++t) {
+        int found = -1;
+        for (int u = 0; u < t; ++u)
+            if (a->msg_W[u] == a->msg_W[t] && a->gru[u].W == a->gru[t].W && a->gru[u].U == a->gru[t].U &&
+                (a->stateful[u] != 0) == (a->stateful[t] != 0)) { found = u; break; }
+        k.stateful[t] = a->stateful[t] != 0;
+        if (found >= 0) { k.img[t] = k.img[found]; continue; }
+        tcb::PackArgs p;
+        p.H = H; p.stateful = k.stateful[t]; p.msg_W = a->msg_W[t]; p.g = a->gru[t]; p.img = ws + (size_t)n_img * ib;
+        tcb::pack_bwd_kernel<<<64, 256, 0, st>>>(p);
+        count_launch();
+        k.img[t] = p.img;
+        ++n_img;
+    }
+    int rc = check_launch("pack_bwd_kernel");
+    if (rc) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = (a->mb + 1) / 2;
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    if (H == 64) {
+        cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<64>::SMEM_BYTES);
+        tcb::ggnn_tc_bwd_kernel<64><<<grid, tc::NTHR, tcb::Cfg<64>::SMEM_BYTES, st>>>(k);
+    } else {
+        cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<128>::SMEM_BYTES);
+        tcb::ggnn_tc_bwd_kernel<128><<<grid, tc::NTHR, tcb::Cfg<128>::SMEM_BYTES, st>>>(k);
+    }
+    count_launch();
+    return check_launch("ggnn_tc_bwd_kernel");
+}

@@ -38,7 +38,8 @@ class GgnnBwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "hidden", "n_edge", "n_steps", "mode")] + [
         ("adj", fp), ("state_in", fp), ("msg_W", _A()), ("gru", GRU * MAX_STEPS),
         ("stateful", C.c_int * MAX_STEPS), ("Hs", fp), ("Ms", fp), ("RSs", fp), ("Gs", fp), ("Ps", fp), ("dHs", fp),
-        ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS), ("d_state_in", fp)]
+        ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS), ("d_state_in", fp),
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
 
 
 class RelgcnFwd(C.Structure):
@@ -102,6 +103,7 @@ def _load():
         "bmp_linear_forward": [fp, fp, fp, fp, i, i, i, i, vp],
         "bmp_linear_backward": [fp, fp, fp, fp, fp, fp, fp, i, i, i, i, vp],
         "bmp_wgrad": [fp, i, fp, i, fp, i, i64, i, i, vp],
+        "bmp_wgrad_tc": [fp, i, fp, i, fp, i, i64, i, i, fp, i, vp],
         "bmp_colsum": [fp, i, fp, i, i64, i, vp],
         "bmp_sigmoid_ce": [fp, fp, fp, fp, i, f, vp],
         "bmp_adam_step": [fp, fp, fp, fp, i, f, f, f, f, f, i, vp],
@@ -122,7 +124,7 @@ lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
            "bmp_relgcn_backward", "bmp_readout_forward", "bmp_readout_backward", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
-           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_wgrad", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
+           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]
 
 

@@ -116,7 +116,7 @@ class GGNNEncode(torch.autograd.Function):
         grads = [torch.zeros_like(p) if p is not None else None for p in params]
         Ps = torch.empty((T, rows, E * H), device=Hs.device, dtype=torch.float32)
         a = K.GgnnBwd()
-        a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, K.MODE_F32
+        a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
         a.adj, a.state_in = _p(adj), _p(state_in)
         base = 1 + 2 * n_msg
         for t, (mi, gi, st) in enumerate(plan):
@@ -128,6 +128,10 @@ class GGNNEncode(torch.autograd.Function):
         a.Hs, a.Ms, a.RSs, a.Gs, a.Ps, a.dHs = _p(Hs), _p(Ms), _p(RSs), _p(Gs), _p(Ps), _p(dHs)
         d_state = torch.zeros_like(state_in) if state_in is not None else None
         a.d_state_in = _p(d_state)
+        if mode == K.MODE_BF16:
+            nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
+            ws = torch.empty((nbytes,), device=Hs.device, dtype=torch.uint8)
+            a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
         K.check(K.lib.bmp_ggnn_backward(C.byref(a), _stream()))
         dx = None
         if is_ids:

@@ -112,6 +112,8 @@ typedef struct {
     float *d_msg_W[BMP_MAX_STEPS], *d_msg_b[BMP_MAX_STEPS];
     bmp_gru_grad_t d_gru[BMP_MAX_STEPS];
     float *d_state_in;
+    void  *tc_workspace;         /* BMP_MODE_BF16 only (same size rule as the forward) */
+    size_t tc_workspace_bytes;
 } bmp_ggnn_bwd_t;
 
 int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
@@ -234,6 +236,10 @@ int bmp_linear_backward(const float *x, const float *W, const float *y, float *d
  * contraction over all atoms of a batch (split over CTAs, fp32 atomics at the end). */
 int bmp_wgrad(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
               int64_t rows, int M, int N, void *stream);
+/* Same contraction on tcgen05 (bf16 operands, fp32 accumulate; used by BMP_MODE_BF16): N in {64,128,256},
+ * 16-byte aligned operands, else BMP_ESHAPE.  dbias[m*bias_stride] += column sums of A when non-NULL. */
+int bmp_wgrad_tc(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                 int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream);
 /* out[n * out_stride] += sum_r B[r*ldb + n] */
 int bmp_colsum(const float *B, int ldb, float *out, int out_stride, int64_t rows, int N, void *stream);
 

@@ -75,3 +75,26 @@ def test_tc_mode_rejects_unsupported_shapes():
     net.mode = gcnbmp.MODE_BF16
     with pytest.raises(ValueError):
         net(atoms, adj)
+
+
+@pytest.mark.parametrize("rows,M,N,lda_pad", [(5000, 128, 128, 0), (777, 192, 64, 64), (20000, 384, 256, 0), (64, 64, 128, 128)])
+def test_wgrad_tc_matches_fp64(rows, M, N, lda_pad):
+    """C += A^T B on tcgen05 (bf16 operands) vs float64; bias = column sums of A (exact fp32 adds)."""
+    import ctypes as C
+    import gcnbmp
+    K = gcnbmp._capi
+    rng = np.random.default_rng(rows + M)
+    lda = M + lda_pad
+    A = rng.standard_normal((rows, lda)).astype(np.float32)
+    B = rng.standard_normal((rows, N)).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    At, Bt, Ct = torch.tensor(A).cuda(), torch.tensor(B).cuda(), torch.tensor(C0).cuda()
+    bias = torch.zeros(M * 2, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    K.check(K.lib.bmp_wgrad_tc(p(At), lda, p(Bt), N, p(Ct), N, rows, M, N, p(bias), 2,
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = C0.astype(np.float64) + A[:, :M].astype(np.float64).T @ B.astype(np.float64)
+    got = Ct.cpu().numpy()
+    assert np.sqrt(((got - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean()) <= 5e-3
+    np.testing.assert_allclose(bias.cpu().numpy()[::2], A[:, :M].astype(np.float64).sum(axis=0), rtol=1e-3, atol=1e-2)
