@@ -24,7 +24,7 @@ template <int H>
 struct Cfg {
     static constexpr int KP = H / 64;
     static constexpr int TILE_BYTES = H * 128;            // weight tile: H rows (n) x 64 bf16 (k)
-    static constexpr int STAGES = (H == 128) ? 3 : 4;
+    static constexpr int STAGES = (H == 128) ? 2 : 4;
     static constexpr int T_MSG = 4 * KP, T_GATE = 2 * KP, T_U = KP;
     static constexpr int TILES_STATEFUL = T_MSG + 3 * T_GATE + T_U;
     static constexpr int TILES_STATELESS = T_MSG + 2 * T_GATE;
@@ -33,7 +33,8 @@ struct Cfg {
     static constexpr int OFF_ADJ = OFF_H + KP * PANEL_BYTES;
     static constexpr int OFF_AH = OFF_ADJ + 8 * ADJ_TILE_BYTES;
     static constexpr int OFF_W = OFF_AH + 2 * KP * PANEL_BYTES;
-    static constexpr int OFF_BAR = OFF_W + STAGES * TILE_BYTES;
+    static constexpr int OFF_STG = OFF_W + STAGES * TILE_BYTES;   // 8 warps x 4 KB transposition staging
+    static constexpr int OFF_BAR = OFF_STG + 8 * 4096;
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
 };
 
@@ -174,11 +175,30 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
         const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
         const int molslot = row >> 6, atom = row & 63;
         float hreg[NC];
+        float *stg = reinterpret_cast<float *>(smem + C::OFF_STG + warp * 4096);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int molg = tile * 2 + molslot;
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;       // global row of this thread (if live)
+            // global row of warp row r (0..31), or -1: used by the coalesced (transposed) stash stores
+            auto wrow = [&](int r) -> long {
+                const int tr = 32 * q + r, mg = tile * 2 + (tr >> 6), at = tr & 63;
+                return (mg < a.mb && at < a.N) ? (long)mg * a.N + at : -1L;
+            };
+            // store 32 columns [col0, col0+32) of every live row of this warp to base[(grow*ld) + col0 ..]
+            auto store_rows = [&](float *base, long ld, int col0, const float *vals) {
+                warp_store_rows<32>(stg, vals, lane, [&](int r) -> float * {
+                    const long g = wrow(r);
+                    return g >= 0 ? base + g * ld + col0 : nullptr;
+                });
+            };
+            auto store_rows16 = [&](float *base, long ld, int col0, const float *vals) {
+                warp_store_rows<16>(stg, vals, lane, [&](int r) -> float * {
+                    const long g = wrow(r);
+                    return g >= 0 ? base + g * ld + col0 : nullptr;
+                });
+            };
             // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
             stage_adjacency(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
             // ---- h_0: embedding gather (or h_in) -> fp32 registers + bf16 operand panels ----
@@ -198,17 +218,10 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     float4 v = src ? *reinterpret_cast<const float4 *>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                     hreg[c] = v.x; hreg[c + 1] = v.y; hreg[c + 2] = v.z; hreg[c + 3] = v.w;
                 }
-                if (live) {
-                    if (a.h0_out) {
 #pragma unroll
-                        for (int c = 0; c < NC; c += 4)
-                            *reinterpret_cast<float4 *>(a.h0_out + grow * H + colbase + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
-                    }
-                    if (a.Hs) {
-#pragma unroll
-                        for (int c = 0; c < NC; c += 4)
-                            *reinterpret_cast<float4 *>(a.Hs + grow * H + colbase + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
-                    }
+                for (int cc = 0; cc < NC; cc += 32) {
+                    if (a.h0_out) store_rows(a.h0_out, H, colbase + cc, &hreg[cc]);
+                    if (a.Hs) store_rows(a.Hs, H, colbase + cc, &hreg[cc]);
                 }
             }
             auto store_h_operand = [&]() {
@@ -287,11 +300,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                             float4 b4 = __ldg(reinterpret_cast<const float4 *>(mb_) + colbase + cc + x);
                             m[x] = __uint_as_float(v[x]) + deg[0] * b4.x + deg[1] * b4.y + deg[2] * b4.z + deg[3] * b4.w;
                         }
-                        if (a.Ms && live) {
-                            float *dst = a.Ms + ((long)t * rows_total + grow) * H + colbase + cc;
-#pragma unroll
-                            for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4 *>(dst + x) = make_float4(m[x], m[x + 1], m[x + 2], m[x + 3]);
-                        }
+                        if (a.Ms) store_rows(a.Ms + (long)t * rows_total * H, H, colbase + cc, m);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const int kk = colbase + cc + 8 * g;
@@ -309,39 +318,36 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 tc_fence_after();
                 if (stateful) {
 #pragma unroll
-                    for (int cc = 0; cc < NC; cc += 32) {
-                        tc_ld32(t_lane + 1 * H + colbase + cc, v);
+                    for (int cc = 0; cc < NC; cc += 16) {
+                        uint32_t w[16];
+                        tc_ld16(t_lane + 1 * H + colbase + cc, w);
                         tc_wait_ld();
-                        float r[32], rs[32];
+                        float r[16], rs[16];
 #pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            r[x] = sigmoid_fast(__uint_as_float(v[x]) + __ldg(b3 + colbase + cc + x));
+                        for (int x = 0; x < 16; ++x) {
+                            r[x] = sigmoid_fast(__uint_as_float(w[x]) + __ldg(b3 + colbase + cc + x));
                             rs[x] = r[x] * hreg[cc + x];
                         }
-                        if (a.Gs && live) {
-                            float *dst = a.Gs + ((long)t * rows_total + grow) * 3 * H + colbase + cc;
-                            float *dst2 = a.RSs + ((long)t * rows_total + grow) * H + colbase + cc;
-#pragma unroll
-                            for (int x = 0; x < 32; x += 4) {
-                                *reinterpret_cast<float4 *>(dst + x) = make_float4(r[x], r[x + 1], r[x + 2], r[x + 3]);
-                                *reinterpret_cast<float4 *>(dst2 + x) = make_float4(rs[x], rs[x + 1], rs[x + 2], rs[x + 3]);
-                            }
+                        if (a.Gs) {
+                            store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, colbase + cc, r);
+                            store_rows16(a.RSs + (long)t * rows_total * H, H, colbase + cc, rs);
                         }
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < 2; ++g) {
                             const int kk = colbase + cc + 8 * g;
                             uint4 pk = make_uint4(pack_bf16(rs[8 * g], rs[8 * g + 1]), pack_bf16(rs[8 * g + 2], rs[8 * g + 3]),
                                                   pack_bf16(rs[8 * g + 4], rs[8 * g + 5]), pack_bf16(rs[8 * g + 6], rs[8 * g + 7]));
                             *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
                         }
                     }
-                } else if (a.Gs && live) {   // r / r*h slots of a stateless step: zeros (merged wgrad contractions stay exact)
-                    float *dst = a.Gs + ((long)t * rows_total + grow) * 3 * H + colbase;
-                    float *dst2 = a.RSs + ((long)t * rows_total + grow) * H + colbase;
+                } else if (a.Gs) {   // r / r*h slots of a stateless step: zeros (merged wgrad contractions stay exact)
+                    float zero[32];
 #pragma unroll
-                    for (int x = 0; x < NC; x += 4) {
-                        *reinterpret_cast<float4 *>(dst + x) = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4 *>(dst2 + x) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int x = 0; x < 32; ++x) zero[x] = 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc += 32) {
+                        store_rows(a.Gs + (long)t * rows_total * 3 * H, 3 * H, colbase + cc, zero);
+                        store_rows(a.RSs + (long)t * rows_total * H, H, colbase + cc, zero);
                     }
                 }
                 tc_fence_before();
@@ -351,38 +357,27 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 mbar_wait(BAR(B_ZH), par);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < NC; cc += 32) {
-                    uint32_t vz[32];
-                    tc_ld32(t_lane + 2 * H + colbase + cc, vz);
-                    tc_ld32(t_lane + 3 * H + colbase + cc, v);
+                for (int cc = 0; cc < NC; cc += 16) {
+                    uint32_t wz[16], wh[16];
+                    tc_ld16(t_lane + 2 * H + colbase + cc, wz);
+                    tc_ld16(t_lane + 3 * H + colbase + cc, wh);
                     tc_wait_ld();
-                    float z[32], hb[32];
+                    float z[16], hb[16];
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) {
-                        z[x] = sigmoid_fast(__uint_as_float(vz[x]) + __ldg(b3 + H + colbase + cc + x));
-                        hb[x] = tanh_fast(__uint_as_float(v[x]) + __ldg(b3 + 2 * H + colbase + cc + x));
+                    for (int x = 0; x < 16; ++x) {
+                        z[x] = sigmoid_fast(__uint_as_float(wz[x]) + __ldg(b3 + H + colbase + cc + x));
+                        hb[x] = tanh_fast(__uint_as_float(wh[x]) + __ldg(b3 + 2 * H + colbase + cc + x));
                         hreg[cc + x] = stateful ? fmaf(z[x], hb[x] - hreg[cc + x], hreg[cc + x]) : z[x] * hb[x];
                     }
-                    if (a.Gs && live) {
-                        float *dst = a.Gs + ((long)t * rows_total + grow) * 3 * H + H + colbase + cc;
-#pragma unroll
-                        for (int x = 0; x < 32; x += 4) {
-                            *reinterpret_cast<float4 *>(dst + x) = make_float4(z[x], z[x + 1], z[x + 2], z[x + 3]);
-                            *reinterpret_cast<float4 *>(dst + H + x) = make_float4(hb[x], hb[x + 1], hb[x + 2], hb[x + 3]);
-                        }
+                    if (a.Gs) {
+                        store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, H + colbase + cc, z);
+                        store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, 2 * H + colbase + cc, hb);
                     }
                 }
-                if (live) {
-                    if (a.Hs) {
-                        float *dst = a.Hs + ((long)(t + 1) * rows_total + grow) * H + colbase;
 #pragma unroll
-                        for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
-                    }
-                    if (t == a.T - 1 && a.h_out) {
-                        float *dst = a.h_out + grow * H + colbase;
-#pragma unroll
-                        for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(dst + c) = make_float4(hreg[c], hreg[c + 1], hreg[c + 2], hreg[c + 3]);
-                    }
+                for (int cc = 0; cc < NC; cc += 32) {
+                    if (a.Hs) store_rows(a.Hs + (long)(t + 1) * rows_total * H, H, colbase + cc, &hreg[cc]);
+                    if (t == a.T - 1 && a.h_out) store_rows(a.h_out, H, colbase + cc, &hreg[cc]);
                 }
                 if (t + 1 < a.T) {
                     store_h_operand();

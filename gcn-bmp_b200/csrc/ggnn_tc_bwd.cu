@@ -184,6 +184,19 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 const float *St = a.Hs + ((long)t * rows_total + grow) * H + colbase;        // state of the step = h_t
                 uint32_t v[32];
                 // ---- phase A: gate derivatives ----
+                if (t > 0 && live) {   // pull the next step's stash lines towards L2 while this step computes
+                    const char *pg = reinterpret_cast<const char *>(a.Gs + ((long)(t - 1) * rows_total + grow) * 3 * H + colbase);
+                    const char *ps = reinterpret_cast<const char *>(a.Hs + ((long)(t - 1) * rows_total + grow) * H + colbase);
+                    const char *pe = reinterpret_cast<const char *>(a.dHs + ((long)(t - 1) * rows_total + grow) * H + colbase);
+#pragma unroll
+                    for (int b = 0; b < NC * 4; b += 128) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + b));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + (long)H * 4 + b));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + (long)2 * H * 4 + b));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + b));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + b));
+                    }
+                }
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 32) {
                     float dz[32], dh[32];

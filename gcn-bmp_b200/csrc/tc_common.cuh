@@ -61,6 +61,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -102,26 +110,83 @@ __host__ __device__ constexpr uint32_t idesc2(int n, int a_mn_major, int b_mn_ma
            ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// stage the fp32 adjacency of a tile (2 molecules x 4 bond types) as bf16 SW128 tiles [mol][e][i][j]
+// stage the fp32 adjacency of a tile (2 molecules x 4 bond types) as bf16 SW128 tiles [mol][e][i][j].
+// Loads are issued in batches of 8 float4 per thread so the DRAM latency is paid 4 times per tile, not 32.
 __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const float *__restrict__ adj, int tile, int mb, int N, int tid) {
-    for (int idx = tid; idx < 8 * 64 * 16; idx += NEPI) {      // (mol,e) x i x (j/4)
-        const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
-        const int mg = tile * 2 + (me >> 2);
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (mg < mb && i < N) {
-            const float *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j4;
-            if ((N & 3) == 0 && j4 < N) {
-                float4 t4 = *reinterpret_cast<const float4 *>(src);
-                v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
-            } else {
+    constexpr int BATCH = 8;
+    for (int base = 0; base < 8 * 64 * 16; base += NEPI * BATCH) {      // items: (mol,e) x i x (j/4)
+        float4 v[BATCH];
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (j4 + x < N) v[x] = src[x];
+        for (int u = 0; u < BATCH; ++u) {
+            const int idx = base + u * NEPI + tid;
+            const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
+            const int mg = tile * 2 + (me >> 2);
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mg < mb && i < N) {
+                const float *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j4;
+                if ((N & 3) == 0) {
+                    if (j4 < N) v[u] = __ldg(reinterpret_cast<const float4 *>(src));
+                } else {
+                    if (j4 + 0 < N) v[u].x = src[0];
+                    if (j4 + 1 < N) v[u].y = src[1];
+                    if (j4 + 2 < N) v[u].z = src[2];
+                    if (j4 + 3 < N) v[u].w = src[3];
+                }
             }
         }
-        uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-        *reinterpret_cast<uint2 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, j4)) = pk;
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int idx = base + u * NEPI + tid;
+            const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
+            uint2 pk = make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
+            *reinterpret_cast<uint2 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, j4)) = pk;
+        }
     }
+}
+
+// ---- coalesced global I/O for the lane == row register layout -----------------------------------
+// An epilogue warp owns 32 tile rows; each lane holds W consecutive fp32 columns of ITS row (the
+// tcgen05.ld 32x32b layout).  Going to global memory lane-per-row touches 32 different lines per
+// instruction; these helpers transpose through a warp-private, XOR-swizzled staging block so that W/4
+// lanes cover one row segment and every instruction moves full sectors of 32/(W/4) rows.
+// rowptr(r) -> pointer to the first of the W columns of warp row r (0..31), or nullptr (row not live).
+template <int CH>
+__device__ __forceinline__ int swz_key(int r) { return (r * CH / 8) & (CH - 1); }
+template <int W, class RowPtr>
+__device__ __forceinline__ void warp_store_rows(float *stg, const float *v, int lane, RowPtr rowptr) {
+    constexpr int CH = W / 4, RPI = 32 / CH;         // 16-byte chunks per row, rows per instruction
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+        *reinterpret_cast<float4 *>(stg + lane * W + ((j ^ swz_key<CH>(lane)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int ch = lane & (CH - 1);
+#pragma unroll
+    for (int it = 0; it < 32 / RPI; ++it) {
+        const int r = it * RPI + lane / CH;
+        const float4 x = *reinterpret_cast<const float4 *>(stg + r * W + ((ch ^ swz_key<CH>(r)) << 2));
+        float *dst = rowptr(r);
+        if (dst) *reinterpret_cast<float4 *>(dst + ch * 4) = x;
+    }
+    __syncwarp();
+}
+template <int W, class RowPtr>
+__device__ __forceinline__ void warp_load_rows(float *stg, float *v, int lane, RowPtr rowptr) {
+    constexpr int CH = W / 4, RPI = 32 / CH;
+    const int ch = lane & (CH - 1);
+#pragma unroll
+    for (int it = 0; it < 32 / RPI; ++it) {
+        const int r = it * RPI + lane / CH;
+        const float *src = rowptr(r);
+        const float4 x = src ? *reinterpret_cast<const float4 *>(src + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(stg + r * W + ((ch ^ swz_key<CH>(r)) << 2)) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const float4 x = *reinterpret_cast<const float4 *>(stg + lane * W + ((j ^ swz_key<CH>(lane)) << 2));
+        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+    __syncwarp();
 }
 
 }  // namespace tc

@@ -269,3 +269,47 @@ def test_trainer_microbatching_and_flat_buffers():
     dev = [t.cuda() for t in host]
     loss2 = tr.step(*dev, global_count=count)
     assert abs(loss2.item() - loss.item()) <= 1e-6 * max(1.0, abs(loss.item()))
+
+
+def test_config_D_inference_hidden256():
+    """BASELINE config D at test scale: GGNN H256 T8 + GGNNReadout (R1) O=256 + HolE(hidden_dims=()) -> 1 logit,
+    forward only (the fp32 kernels with four 64-channel chunks; N = 64 = the maximum the kernels take)."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(41)
+    H, T, mb, N = 256, 8, 3, 64
+    a1, A1 = synthetic.random_molecules(rng, mb, N)
+    a2, A2 = synthetic.random_molecules(rng, mb, N)
+    shapes = {"graph_conv/" + k: v for k, v in R.ggnn_shapes(H, H, T).items()}
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(H, 1, ()).items()})
+    params = R.init_params(shapes, rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    P = R.P(tab)
+    omodel = R.GraphConvPredictorForPair(R.GGNN(P.sub("graph_conv"), H, H, T), None, R.HolE(P.sub("mlp"), 1, ()))
+    ologits = omodel(a1, A1.astype(np.float64), a2, A2.astype(np.float64)).data
+    model = gcnbmp.GraphConvPredictorForPair(gcnbmp.GGNN(H, H, T), None, gcnbmp.HolE(1, ()))
+    model.load_params(params)
+    with torch.no_grad():
+        logits = model(a1, A1, a2, A2).cpu().numpy()
+    assert rel_err(logits, ologits) <= TOL
+
+
+def test_config_B_relgcn_64x4():
+    """BASELINE config B at test scale: RelGCN 64->64 x4 layers, readout O=64, binary head, N = 64, fwd+bwd."""
+    import gcnbmp
+    case = cases.pair_case("B", seed=17)
+    sp = dict(case["spec"], ch=[64, 64, 64, 64, 64], O=64, N1=64, N2=64, scale_adj=False)
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(3)
+    a1, A1 = synthetic.random_molecules(rng, 4, 64)
+    a2, A2 = synthetic.random_molecules(rng, 4, 64)
+    y = (rng.random((4, 1)) < 0.33).astype(np.int32)
+    shapes = {"graph_conv/" + k: v for k, v in R.relgcn_shapes(64, sp["ch"]).items()}
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(64, 1, ()).items()})
+    big = dict(case, spec=sp, params=R.init_params(shapes, rng, dtype=np.float64),
+               inputs=(a1, A1.astype(np.float64), a2, A2.astype(np.float64)), labels=y)
+    o = cases.oracle_eval(big)
+    p = product.product_eval(big)
+    assert rel_err(p["logits"], o["logits"]) <= TOL
+    for k in sorted(o["grads"]):
+        assert rel_err(p["grads"][k], o["grads"][k], floor=1e-7) <= TOL, k
