@@ -142,6 +142,11 @@ static int readout_check(int mb, int N, int H, int O, int variant, const float *
 
 using namespace bmp;
 
+int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_agg, const float *h, const float *h0,
+                   const float *mask, const float *W_i, const float *b_i, const float *W_j, const float *b_j,
+                   float *g, const float *dg, float *DU, float *DV, float *dh, float *dh0, void *ws, size_t ws_bytes,
+                   bool bwd, void *stream);   // readout_tc.cu
+
 extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
     if (!a || !a->g) { set_error("bmp_readout_forward: null argument"); return BMP_EINVAL; }
     int rc = readout_check(a->mb, a->n_atoms, a->hidden, a->out_dim, a->variant, a->h);
@@ -155,6 +160,11 @@ extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
     }
     if (!a->W_i || !a->W_j) { set_error("bmp_readout_forward: null weights"); return BMP_EINVAL; }
     if (!aligned16({a->W_i, a->W_j, a->h, a->h0})) { set_error("bmp_readout_forward: h, h0, W_i, W_j must be 16-byte aligned"); return BMP_EINVAL; }
+    if (a->mode == BMP_MODE_BF16 && bmp_readout_tc_workspace_bytes(a->hidden, a->out_dim)) {
+        return bmp_readout_tc(a->mb, a->n_atoms, a->hidden, a->out_dim, a->variant, a->act, a->act_agg, a->h, a->h0,
+                              a->is_real_node, a->W_i, a->b_i, a->W_j, a->b_j, a->g, nullptr, nullptr, nullptr, nullptr, nullptr,
+                              a->tc_workspace, a->tc_workspace_bytes, false, stream);
+    }
     const int Kcat = a->h0 ? 2 * a->hidden : a->hidden;
     size_t smem = sizeof(float) * ((size_t)Kcat * AT + STAGE_FLOATS);
     int grid = a->mb < 148 * 2 ? a->mb : 148 * 2;
@@ -183,27 +193,44 @@ extern "C" int bmp_readout_backward(const bmp_readout_bwd_t *a, void *stream) {
     if (!aligned16({a->W_i, a->W_j, a->h, a->h0, a->DU, a->DV, a->dh, a->dh0})) { set_error("bmp_readout_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     const int Kcat = a->h0 ? 2 * H : H;
     const int Kj = a->variant == BMP_READOUT_R2 ? H : Kcat;
-    size_t smem = sizeof(float) * ((size_t)(Kcat + 2 * O) * AT + STAGE_FLOATS);
-    if (smem > 227 * 1024) {
-        set_error("bmp_readout_backward: hidden=%d out_dim=%d needs %zu B of shared memory", H, O, smem);
-        return BMP_ESHAPE;
+    const bool tc = a->mode == BMP_MODE_BF16 && bmp_readout_tc_workspace_bytes(H, O) != 0;
+    if (tc) {
+        if ((rc = bmp_readout_tc(a->mb, a->n_atoms, H, O, a->variant, a->act, a->act_agg, a->h, a->h0, a->is_real_node,
+                                 a->W_i, a->b_i, a->W_j, a->b_j, const_cast<float *>(a->g), a->dg, a->DU, a->DV, a->dh, a->dh0,
+                                 a->tc_workspace, a->tc_workspace_bytes, true, stream)))
+            return rc;
+    } else {
+        size_t smem = sizeof(float) * ((size_t)(Kcat + 2 * O) * AT + STAGE_FLOATS);
+        if (smem > 227 * 1024) {
+            set_error("bmp_readout_backward: hidden=%d out_dim=%d needs %zu B of shared memory", H, O, smem);
+            return BMP_ESHAPE;
+        }
+        int grid = a->mb < 148 ? a->mb : 148;
+        bmp_readout_fwd_t dummy = {};
+        cudaFuncSetAttribute(readout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        readout_kernel<true><<<grid, NTHREADS, smem, st>>>(dummy, *a);
+        count_launch();
+        if ((rc = check_launch("readout_kernel<bwd>"))) return rc;
     }
-    int grid = a->mb < 148 ? a->mb : 148;
-    bmp_readout_fwd_t dummy = {};
-    cudaFuncSetAttribute(readout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    readout_kernel<true><<<grid, NTHREADS, smem, st>>>(dummy, *a);
-    count_launch();
-    if ((rc = check_launch("readout_kernel<bwd>"))) return rc;
-    // parameter gradients
+    // parameter gradients: C += A^T B over all atoms (tcgen05 contraction with fused bias sums in BF16 mode)
+    auto WG = [&](const float *A_, const float *B_, float *C_, int ldc, float *db) -> int {
+        if (tc) return bmp_wgrad_tc(A_, O, B_, H, C_, ldc, rows, O, H, db, 1, stream);
+        int e_ = bmp_wgrad(A_, O, B_, H, C_, ldc, rows, O, H, stream);
+        if (!e_ && db) e_ = bmp_colsum(A_, O, db, 1, rows, O, stream);
+        return e_;
+    };
+    bool bi_done = false, bj_done = false;
     if (a->d_W_i) {
-        if ((rc = bmp_wgrad(a->DU, O, a->h, H, a->d_W_i, Kcat, rows, O, H, stream))) return rc;
-        if (a->h0 && (rc = bmp_wgrad(a->DU, O, a->h0, H, a->d_W_i + H, Kcat, rows, O, H, stream))) return rc;
+        if ((rc = WG(a->DU, a->h, a->d_W_i, Kcat, a->d_b_i))) return rc;
+        bi_done = true;
+        if (a->h0 && (rc = WG(a->DU, a->h0, a->d_W_i + H, Kcat, nullptr))) return rc;
     }
     if (a->d_W_j) {
-        if ((rc = bmp_wgrad(a->DV, O, a->h, H, a->d_W_j, Kj, rows, O, H, stream))) return rc;
-        if (a->h0 && Kj > H && (rc = bmp_wgrad(a->DV, O, a->h0, H, a->d_W_j + H, Kj, rows, O, H, stream))) return rc;
+        if ((rc = WG(a->DV, a->h, a->d_W_j, Kj, a->d_b_j))) return rc;
+        bj_done = true;
+        if (a->h0 && Kj > H && (rc = WG(a->DV, a->h0, a->d_W_j + H, Kj, nullptr))) return rc;
     }
-    if (a->d_b_i && (rc = bmp_colsum(a->DU, O, a->d_b_i, 1, rows, O, stream))) return rc;
-    if (a->d_b_j && (rc = bmp_colsum(a->DV, O, a->d_b_j, 1, rows, O, stream))) return rc;
+    if (a->d_b_i && !bi_done && (rc = bmp_colsum(a->DU, O, a->d_b_i, 1, rows, O, stream))) return rc;
+    if (a->d_b_j && !bj_done && (rc = bmp_colsum(a->DV, O, a->d_b_j, 1, rows, O, stream))) return rc;
     return BMP_OK;
 }

@@ -57,13 +57,15 @@ class RelgcnBwd(C.Structure):
 
 class ReadoutFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "hidden", "out_dim", "variant", "act", "act_agg")] + [
-        (n, fp) for n in ("h", "h0", "is_real_node", "W_i", "b_i", "W_j", "b_j", "g")]
+        (n, fp) for n in ("h", "h0", "is_real_node", "W_i", "b_i", "W_j", "b_j", "g")] + [
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
 
 
 class ReadoutBwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "hidden", "out_dim", "variant", "act", "act_agg")] + [
         (n, fp) for n in ("h", "h0", "is_real_node", "W_i", "b_i", "W_j", "b_j", "g", "dg",
-                          "DU", "DV", "dh", "dh0", "d_W_i", "d_b_i", "d_W_j", "d_b_j")]
+                          "DU", "DV", "dh", "dh0", "d_W_i", "d_b_i", "d_W_j", "d_b_j")] + [
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
 
 
 _CO_PARAMS = ("W", "V1", "V2", "b", "lt_1", "lt_2", "wa_1", "wa_2", "W_j", "b_j")
@@ -112,6 +114,7 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = args, C.c_int
     lib.bmp_ggnn_tc_workspace_bytes.argtypes, lib.bmp_ggnn_tc_workspace_bytes.restype = [i, i], C.c_size_t
+    lib.bmp_readout_tc_workspace_bytes.argtypes, lib.bmp_readout_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_last_error.restype = C.c_char_p
     lib.bmp_version.restype = C.c_int
     lib.bmp_device_check.restype = C.c_int
@@ -122,7 +125,7 @@ def _load():
 
 lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
-           "bmp_relgcn_backward", "bmp_readout_forward", "bmp_readout_backward", "bmp_coattn_forward",
+           "bmp_relgcn_backward", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]

@@ -214,11 +214,23 @@ class RelGCNEncode(torch.autograd.Function):
         return (dx, None, None, None, None, None) + tuple(grads)
 
 
+def _readout_ws(a, mode, H, O, variant, dev):
+    """BF16 mode: attach the packed-weight workspace of the tcgen05 readout when the shape is on that path."""
+    a.mode = K.MODE_F32
+    if mode == K.MODE_BF16 and variant != K.READOUT_SUM:
+        nbytes = int(K.lib.bmp_readout_tc_workspace_bytes(H, O))
+        if nbytes:
+            ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+            a.mode, a.tc_workspace, a.tc_workspace_bytes = K.MODE_BF16, _p(ws), nbytes
+            return ws
+    return None
+
+
 class Readout(torch.autograd.Function):
     """GGNNReadout variants R1 / R2 / SUM."""
 
     @staticmethod
-    def forward(ctx, h, h0, mask, variant, act, act_agg, W_i, b_i, W_j, b_j):
+    def forward(ctx, h, h0, mask, variant, act, act_agg, W_i, b_i, W_j, b_j, mode=0):
         _need_cuda(h)
         h, h0, mask = _f32(h), _f32(h0), _f32(mask)
         mb, N, H = h.shape
@@ -228,15 +240,16 @@ class Readout(torch.autograd.Function):
         a.mb, a.n_atoms, a.hidden, a.out_dim, a.variant, a.act, a.act_agg = mb, N, H, O, variant, act, act_agg
         a.h, a.h0, a.is_real_node = _p(h), _p(h0), _p(mask)
         a.W_i, a.b_i, a.W_j, a.b_j, a.g = _p(W_i), _p(b_i), _p(W_j), _p(b_j), _p(g)
+        ws = _readout_ws(a, mode, H, O, variant, h.device)
         K.check(K.lib.bmp_readout_forward(C.byref(a), _stream()))
         ctx.save_for_backward(h, h0, mask, W_i, b_i, W_j, b_j, g)
-        ctx.meta = (variant, act, act_agg)
+        ctx.meta = (variant, act, act_agg, mode)
         return g
 
     @staticmethod
     def backward(ctx, dg):
         h, h0, mask, W_i, b_i, W_j, b_j, g = ctx.saved_tensors
-        variant, act, act_agg = ctx.meta
+        variant, act, act_agg, mode = ctx.meta
         mb, N, H = h.shape
         O = g.shape[1]
         dev = h.device
@@ -254,8 +267,9 @@ class Readout(torch.autograd.Function):
             a.DU, a.DV = _p(DU), _p(DV)
         a.dh, a.dh0 = _p(dh), _p(dh0)
         a.d_W_i, a.d_b_i, a.d_W_j, a.d_b_j = _p(gWi), _p(gbi), _p(gWj), _p(gbj)
+        ws = _readout_ws(a, mode, H, O, variant, dev)
         K.check(K.lib.bmp_readout_backward(C.byref(a), _stream()))
-        return dh, dh0, None, None, None, None, gWi, gbi, gWj, gbj
+        return dh, dh0, None, None, None, None, gWi, gbi, gWj, gbj, None
 
 
 class Coattention(torch.autograd.Function):

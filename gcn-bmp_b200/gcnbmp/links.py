@@ -322,7 +322,8 @@ class GGNNReadout(Link):
         kin = h.shape[2] * (2 if h0 is not None else 1)
         i, j = self.i_layer.ensure(kin), self.j_layer.ensure(kin)
         return Fn.Readout.apply(h, h0, mask, K.READOUT_R1, Fn.act_code(self.activation),
-                                Fn.act_code(self.activation_agg), i.W, i.bias, j.W, j.bias)
+                                Fn.act_code(self.activation_agg), i.W, i.bias, j.W, j.bias,
+                                self.__dict__.get("mode", K.MODE_F32))
 
 
 class GGNN(Link):
@@ -370,6 +371,8 @@ class GGNN(Link):
         hs, stash = _encode(x, adj, None, self._plan(), msgs, grus, self.embed.W if ids else None, self.mode)
         h0, hT = hs[0], hs[T if stash else 1]
         self.__dict__["atoms"] = hT
+        for r in self.readout_layers:
+            r.__dict__["mode"] = self.mode
         for u in ups:
             u.update_layer.__dict__["h"] = hT
         if self.concat_hidden:
@@ -413,7 +416,7 @@ class GGNNMono(Link):
     def readout(self, h, h0, step=0):
         idx = step if self.concat_hidden else 0
         i, j = self.i_layers[idx], self.j_layers[idx]
-        return Fn.Readout.apply(h, h0, None, K.READOUT_R2, 0, 0, i.W, i.b, j.W, j.b)
+        return Fn.Readout.apply(h, h0, None, K.READOUT_R2, 0, 0, i.W, i.b, j.W, j.b, self.mode)
 
     def __call__(self, atom_array, adj):
         self.update_layer.reset_state()

@@ -168,9 +168,13 @@ typedef struct {
     const float *h, *h0, *is_real_node;
     const float *W_i, *b_i, *W_j, *b_j;
     float *g;                          /* (mb,O) ; (mb,H) for SUM */
+    int    mode;                       /* BMP_MODE_BF16: tcgen05 kernel when H,O in {64,128} (else fp32 kernel) */
+    void  *tc_workspace;               /* >= bmp_readout_tc_workspace_bytes(hidden, out_dim) in BF16 mode      */
+    size_t tc_workspace_bytes;
 } bmp_readout_fwd_t;
 
 int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream);
+size_t bmp_readout_tc_workspace_bytes(int hidden, int out_dim);   /* 0 = shape not on the tcgen05 path */
 
 /* DU/DV: workspaces (mb*N, O) receiving the pre-activation gradients of the i and
  * j linears; dh/dh0 are ACCUMULATED (+=) so they can point into bmp_ggnn dHs.     */
@@ -181,6 +185,9 @@ typedef struct {
     const float *g, *dg;
     float *DU, *DV, *dh, *dh0;
     float *d_W_i, *d_b_i, *d_W_j, *d_b_j;
+    int    mode;
+    void  *tc_workspace;
+    size_t tc_workspace_bytes;
 } bmp_readout_bwd_t;
 
 int bmp_readout_backward(const bmp_readout_bwd_t *a, void *stream);

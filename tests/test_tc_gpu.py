@@ -98,3 +98,41 @@ def test_wgrad_tc_matches_fp64(rows, M, N, lda_pad):
     got = Ct.cpu().numpy()
     assert np.sqrt(((got - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean()) <= 5e-3
     np.testing.assert_allclose(bias.cpu().numpy()[::2], A[:, :M].astype(np.float64).sum(axis=0), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("H,O,use_h0,act,agg,use_mask,nobias", [
+    (128, 128, True, "identity", "identity", False, False), (64, 128, True, "tanh", "tanh", True, False),
+    (128, 64, False, "tanh", "identity", False, True), (64, 64, True, "relu", "sigmoid", True, False)])
+def test_tc_readout_r1_variants(H, O, use_h0, act, agg, use_mask, nobias):
+    """GGNNReadout (R1) on the tcgen05 kernel: forward and all gradients vs the fp64 oracle (bf16 bound)."""
+    import gcnbmp
+    from oracle import minichainer as F
+    rng = np.random.default_rng(H + O)
+    mb, N = 5, 37
+    kin = 2 * H if use_h0 else H
+    shapes = {"i_layer/W": (O, kin), "j_layer/W": (O, kin)}
+    if not nobias:
+        shapes.update({"i_layer/b": (O,), "j_layer/b": (O,)})
+    params = R.init_params(shapes, rng, dtype=np.float64)
+    h, h0 = rng.standard_normal((mb, N, H)) * 0.5, rng.standard_normal((mb, N, H)) * 0.5
+    mask = (rng.random((mb, N)) < 0.7).astype(np.float64) if use_mask else None
+    tab = R.wrap_params(params)
+    hv, h0v = F.param(h), F.param(h0)
+    og = R.GGNNReadout(R.P(tab), O, H, nobias=nobias, activation=act, activation_agg=agg)(hv, h0v if use_h0 else None, mask)
+    w = rng.standard_normal(og.shape)
+    F.sum_(F.mul(og, F.const(w))).backward()
+    f = gcnbmp.functions
+    link = gcnbmp.GGNNReadout(O, H, nobias=nobias, activation=getattr(f, act), activation_agg=getattr(f, agg))
+    link.load_params(params)
+    link.mode = gcnbmp.MODE_BF16
+    ht = torch.tensor(h, dtype=torch.float32, device="cuda", requires_grad=True)
+    h0t = torch.tensor(h0, dtype=torch.float32, device="cuda", requires_grad=True)
+    pg = link(ht, h0t if use_h0 else None, None if mask is None else mask.astype(np.float32))
+    (pg * torch.tensor(w, dtype=torch.float32, device="cuda")).sum().backward()
+    assert rel_err(pg.detach().cpu().numpy(), og.data) <= MAX_TOL
+    assert _rms_rel(ht.grad.cpu().numpy(), hv.grad) <= 2e-2
+    if use_h0:
+        assert _rms_rel(h0t.grad.cpu().numpy(), h0v.grad) <= 2e-2
+    g = link.grad_dict()
+    for k in g:
+        assert _rms_rel(g[k], tab[k].grad) <= 2e-2, k
