@@ -47,6 +47,7 @@ struct Args {
     const float *msg_b[BMP_MAX_STEPS];     // (H*4) as in the reference: b[c*4+e]
     int stateful[BMP_MAX_STEPS];
     float *h_out, *h0_out, *Hs, *Ms, *Gs, *RSs;
+    long long *dbg;              // optional phase timestamps of CTA 0 (tools/tc_timeline.py)
 };
 
 template <int H>
@@ -257,6 +258,8 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 const uint32_t par = it & 1;
                 const bool stateful = a.stateful[t] != 0;
                 const float *b3 = a.bias3[t];
+#define TSF(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
+                TSF(0);
                 uint32_t v[32];
                 // ---- E1: AH accumulators -> bf16 A-operand panels (two K halves) ----
                 for (int p = 0; p < 2; ++p) {
@@ -286,7 +289,9 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     }
                 }
                 // ---- E2: message m (+ bias through the degrees) -> bf16 operand (AH panels [0,KP)) ----
+                TSF(1);
                 mbar_wait(BAR(B_M), par);
+                TSF(2);
                 tc_fence_after();
                 {
                     const float *mb_ = a.msg_b[t];
@@ -313,8 +318,10 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(BAR(B_XREADY));
+                TSF(3);
                 // ---- E3: reset gate, r*h -> bf16 operand (AH panels [KP,2KP)) ----
                 mbar_wait(BAR(B_R), par);
+                TSF(4);
                 tc_fence_after();
                 if (stateful) {
 #pragma unroll
@@ -353,8 +360,10 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(BAR(B_RSREADY));
+                TSF(5);
                 // ---- E4: update gate + candidate -> new state ----
                 mbar_wait(BAR(B_ZH), par);
+                TSF(6);
                 tc_fence_after();
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 16) {
@@ -379,6 +388,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     if (a.Hs) store_rows(a.Hs + (long)(t + 1) * rows_total * H, H, colbase + cc, &hreg[cc]);
                     if (t == a.T - 1 && a.h_out) store_rows(a.h_out, H, colbase + cc, &hreg[cc]);
                 }
+                TSF(7);
                 if (t + 1 < a.T) {
                     store_h_operand();
                     tc_fence_before();
@@ -457,8 +467,12 @@ using namespace bmp;
 
 extern "C" size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps) {
     if (hidden != 64 && hidden != 128) return 0;
-    return tc::image_bytes(hidden) * (size_t)n_steps + 1024;
+    return tc::image_bytes(hidden) * (size_t)n_steps + 2048;
 }
+
+extern long long *g_tc_dbg_fwd;
+long long *g_tc_dbg_fwd = nullptr;
+extern "C" void bmp_debug_set_buffer_fwd(void *p) { g_tc_dbg_fwd = (long long *)p; }
 
 int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     const int H = a->hidden, T = a->n_steps;
@@ -482,6 +496,7 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.n_types = a->n_atom_types;
     k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj;
     k.h_out = a->h_out; k.h0_out = a->h0_out; k.Hs = a->Hs; k.Ms = a->Ms; k.Gs = a->Gs; k.RSs = a->RSs;
+    k.dbg = g_tc_dbg_fwd;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
     const size_t ib = tc::image_bytes(H);
     int n_img = 0;

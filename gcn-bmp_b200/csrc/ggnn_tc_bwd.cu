@@ -37,7 +37,21 @@ struct Args {
     float *Gs, *Ps, *dHs;
     const uint8_t *img[BMP_MAX_STEPS];
     int stateful[BMP_MAX_STEPS];
+    const int *ext_flags;        // [T+1]: != 0 where dHs[t] holds a non-zero external gradient
+    long long *dbg;              // optional phase timestamps of CTA 0 (tools/tc_timeline.py)
 };
+
+// flags[t] |= 1 when dHs[t] has any non-zero entry (the intermediate states normally receive no external gradient)
+__global__ void nonzero_flags_kernel(const float *__restrict__ x, long n_per_t, int *flags) {
+    const int t = blockIdx.y;
+    const float4 *p = reinterpret_cast<const float4 *>(x + (long)t * n_per_t);
+    bool nz = false;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_t / 4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(p + i);
+        nz |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+    }
+    if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flags + t, 1);
+}
 
 template <int H>
 __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
@@ -183,6 +197,8 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 float *Gt = a.Gs + ((long)t * rows_total + grow) * 3 * H + colbase;          // r | z | hbar slots of this row
                 const float *St = a.Hs + ((long)t * rows_total + grow) * H + colbase;        // state of the step = h_t
                 uint32_t v[32];
+#define TS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
+                TS(0);
                 // ---- phase A: gate derivatives ----
                 if (t > 0 && live) {   // pull the next step's stash lines towards L2 while this step computes
                     const char *pg = reinterpret_cast<const char *>(a.Gs + ((long)(t - 1) * rows_total + grow) * 3 * H + colbase);
@@ -237,9 +253,27 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 }
                 fence_proxy_async();
                 mbar_arrive(BAR(B_DRDY));
+                TS(1);
                 // ---- phase B: through U and the reset gate ----
+                // r and the state of the first column chunk are requested BEFORE waiting for q, so their latency
+                // overlaps MMA-q; the second chunk is requested while the first is being consumed.
+                float rr[32], ss[32];
+                auto load_rs = [&](int cc) {
+#pragma unroll
+                    for (int x = 0; x < 32; x += 4) {
+                        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = r4;
+                        if (live) {
+                            r4 = *reinterpret_cast<const float4 *>(Gt + cc + x);
+                            s4 = *reinterpret_cast<const float4 *>(St + cc + x);
+                        }
+                        rr[x] = r4.x; rr[x + 1] = r4.y; rr[x + 2] = r4.z; rr[x + 3] = r4.w;
+                        ss[x] = s4.x; ss[x + 1] = s4.y; ss[x + 2] = s4.z; ss[x + 3] = s4.w;
+                    }
+                };
+                if (stateful) load_rs(0);
                 mbar_wait(BAR(B_Q), par);
                 tc_fence_after();
+                TS(2);
                 if (stateful) {
 #pragma unroll
                     for (int cc = 0; cc < NC; cc += 32) {
@@ -247,20 +281,12 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         tc_wait_ld();
                         float dr[32];
 #pragma unroll
-                        for (int x = 0; x < 32; x += 4) {
-                            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = r4;
-                            if (live) {
-                                r4 = *reinterpret_cast<const float4 *>(Gt + cc + x);
-                                s4 = *reinterpret_cast<const float4 *>(St + cc + x);
-                            }
-                            const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-                            for (int y = 0; y < 4; ++y) {
-                                const float qv = __uint_as_float(v[x + y]);
-                                acc[cc + x + y] += qv * rr[y];
-                                dr[x + y] = qv * ss[y] * rr[y] * (1.f - rr[y]);
-                            }
+                        for (int x = 0; x < 32; ++x) {
+                            const float qv = __uint_as_float(v[x]);
+                            acc[cc + x] += qv * rr[x];
+                            dr[x] = qv * ss[x] * rr[x] * (1.f - rr[x]);
                         }
+                        if (cc + 32 < NC) load_rs(cc + 32);
                         if (live) {
 #pragma unroll
                             for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4 *>(Gt + cc + x) = make_float4(dr[x], dr[x + 1], dr[x + 2], dr[x + 3]);
@@ -277,9 +303,11 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(BAR(B_DRRDY));
+                TS(3);
                 // ---- phase C: dm -> bf16 operand panels (B of MMA-P) ----
                 mbar_wait(BAR(B_DX), par);
                 tc_fence_after();
+                TS(4);
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 32) {
                     tc_ld32(t_lane + COL_DM + colbase + cc, v);
@@ -297,6 +325,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(BAR(B_DMRDY));
+                TS(5);
                 // ---- phase D: P accumulators -> bf16 A-operand panels (two K halves) + fp32 stash ----
                 for (int p = 0; p < 2; ++p) {
                     if (p == 1) mbar_wait(BAR(B_PFREE), par);
@@ -305,6 +334,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         const uint32_t pcol = (pi == 0 || pi == 3) ? 0u : (pi == 1 ? 2u * H : 3u * H);
                         mbar_wait(BAR(B_P + pi), par);
                         tc_fence_after();
+                        TS(6 + pi);
                         const int orow = mol * 64 + atom;                   // row of (mol, atom j) in the tile
                         const int kbase = molslot * H + colbase;            // TMEM lane half = bond type within the pair
                         const int omol = tile * 2 + mol;
@@ -335,18 +365,21 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         mbar_arrive(BAR(B_PRDY + p));
                     }
                 }
+                TS(10);
                 // ---- phase E: dh_t = dh_x (+ dh_msg) + ds + external gradient ----
                 mbar_wait(BAR(B_DH), par);
                 tc_fence_after();
+                TS(11);
                 {
                     float *ext = a.dHs + ((long)t * rows_total + grow) * H + colbase;
+                    const bool has_ext = live && a.ext_flags[t] != 0;
 #pragma unroll
                     for (int cc = 0; cc < NC; cc += 32) {
                         tc_ld32(t_lane + COL_DHX + colbase + cc, v);
                         tc_wait_ld();
 #pragma unroll
                         for (int x = 0; x < 32; x += 4) {
-                            float4 e4 = live ? *reinterpret_cast<const float4 *>(ext + cc + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 e4 = has_ext ? *reinterpret_cast<const float4 *>(ext + cc + x) : make_float4(0.f, 0.f, 0.f, 0.f);
                             acc[cc + x] += __uint_as_float(v[x]) + e4.x;
                             acc[cc + x + 1] += __uint_as_float(v[x + 1]) + e4.y;
                             acc[cc + x + 2] += __uint_as_float(v[x + 2]) + e4.z;
@@ -358,6 +391,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(ext + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
                     }
                 }
+                TS(12);
                 tc_fence_before();
                 if (t == 0) asm volatile("bar.sync 1, %0;" ::"n"(NEPI));   // tile finished: smem/TMEM may be re-staged
             }
@@ -416,6 +450,9 @@ static size_t image_bytes(int H) { return (size_t)(11 * (H / 64)) * H * 128 + 25
 
 using namespace bmp;
 
+static long long *g_tc_dbg = nullptr;
+extern "C" void bmp_debug_set_buffer(void *p) { g_tc_dbg = (long long *)p; }
+
 // Data part of the backward on tcgen05; called by bmp_ggnn_backward when mode == BMP_MODE_BF16.
 int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     const int H = a->hidden, T = a->n_steps;
@@ -427,6 +464,13 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     tcb::Args k = {};
     k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.adj = a->adj; k.Hs = a->Hs; k.Gs = a->Gs; k.Ps = a->Ps; k.dHs = a->dHs;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
+    int *flags = reinterpret_cast<int *>(ws);      // first 256 B of the workspace: per-step external-gradient flags
+    ws += 256;
+    cudaMemsetAsync(flags, 0, (T + 1) * sizeof(int), st);
+    tcb::nonzero_flags_kernel<<<dim3(64, T + 1), 256, 0, st>>>(a->dHs, (long)a->mb * a->n_atoms * H, flags);
+    count_launch();
+    k.ext_flags = flags;
+    k.dbg = g_tc_dbg;
     const size_t ib = tcb::image_bytes(H);
     int n_img = 0;
     for (int t = 0; t < T; ++t) {

@@ -189,5 +189,36 @@ __device__ __forceinline__ void warp_load_rows(float *stg, float *v, int lane, R
     __syncwarp();
 }
 
+// Split form of warp_load_rows: issue the coalesced global loads of several arrays first (so their
+// latencies overlap), then transpose each through the staging block.
+template <int W, class RowPtr>
+__device__ __forceinline__ void warp_ldg_rows(float4 (&x)[W / 4], int lane, RowPtr rowptr) {
+    constexpr int CH = W / 4, RPI = 32 / CH;
+    const int ch = lane & (CH - 1);
+#pragma unroll
+    for (int it = 0; it < CH; ++it) {
+        const int r = it * RPI + lane / CH;
+        const float *src = rowptr(r);
+        x[it] = src ? __ldg(reinterpret_cast<const float4 *>(src + ch * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int W>
+__device__ __forceinline__ void warp_transpose_in(float *stg, const float4 (&x)[W / 4], float *v, int lane) {
+    constexpr int CH = W / 4, RPI = 32 / CH;
+    const int ch = lane & (CH - 1);
+#pragma unroll
+    for (int it = 0; it < CH; ++it) {
+        const int r = it * RPI + lane / CH;
+        *reinterpret_cast<float4 *>(stg + r * W + ((ch ^ swz_key<CH>(r)) << 2)) = x[it];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        const float4 t = *reinterpret_cast<const float4 *>(stg + lane * W + ((j ^ swz_key<CH>(lane)) << 2));
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+    __syncwarp();
+}
+
 }  // namespace tc
 }  // namespace bmp
