@@ -391,6 +391,7 @@ using namespace bmp;
 
 int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream);    // ggnn_tc.cu
 int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream);   // ggnn_tc_bwd.cu
+int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream);   // ggnn_tc_bwd.cu (bf16 panel stash)
 
 extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
     if (!a || !a->adj || (!a->atoms && !a->h_in) || (a->atoms && !a->embed_W)) {
@@ -441,6 +442,13 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
 }
 
 extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
+    if (a && a->stash2) {
+        if (a->mode != BMP_MODE_BF16 || (a->hidden != 64 && a->hidden != 128) || a->n_edge != 4 || a->state_in || !a->adj || !a->dHs) {
+            set_error("bmp_ggnn_backward: the panel stash needs BMP_MODE_BF16, hidden 64/128, 4 bond types and no external state");
+            return BMP_EINVAL;
+        }
+        return bmp_ggnn_backward_v2(a, stream);
+    }
     if (!a || !a->adj || !a->Hs || !a->Ms || !a->Gs || !a->Ps || !a->dHs || !a->RSs) {
         set_error("bmp_ggnn_backward: null argument");
         return BMP_EINVAL;

@@ -48,9 +48,11 @@ struct Args {
     int stateful[BMP_MAX_STEPS];
     float *h_out, *h0_out, *Hs, *Ms, *Gs, *RSs;
     long long *dbg;              // optional phase timestamps of CTA 0 (tools/tc_timeline.py)
+    Stash2 st;                   // bf16 panel stash (use2 != 0): replaces the fp32 Hs/Ms/Gs/RSs stores
+    int use2;
 };
 
-template <int H>
+template <int H, bool V2>
 __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
     using C = Cfg<H>;
     constexpr int KP = C::KP;
@@ -131,6 +133,11 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     const bool stateful = a.stateful[t] != 0;
                     mbar_wait(BAR(B_HREADY), par);
                     tc_fence_after();
+                    if (V2) {   // every earlier panel dump has left shared memory; dump h_t (the step input)
+                        bulk_wait_read();
+                        tma_bulk_s2g(a.st.Xp + ((size_t)t * n_tiles + tile) * KP * PANEL_BYTES, s_h, KP * PANEL_BYTES);
+                        bulk_commit();
+                    }
                     // MMA-1: D1[(mol,p)] = [A_2p ; A_2p+1](mol) x h(mol)   (B MN-major from the h panels)
                     for (int p = 0; p < 2; ++p)
                         for (int mol = 0; mol < 2; ++mol) {
@@ -152,6 +159,10 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     // MMA-3: gates over x = [h | m]
                     mbar_wait(BAR(B_XREADY), par);
                     tc_fence_after();
+                    if (V2) {
+                        tma_bulk_s2g(a.st.Mp + ((size_t)t * n_tiles + tile) * KP * PANEL_BYTES, s_ah, KP * PANEL_BYTES);
+                        bulk_commit();
+                    }
                     auto gate_block = [&](uint32_t dcol) {
                         for (int kp = 0; kp < 2 * KP; ++kp)
                             mma_wtile(kp < KP ? s_h + kp * PANEL_BYTES : s_ah + (kp - KP) * PANEL_BYTES, dcol, kp == 0);
@@ -163,8 +174,13 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     // MMA-4: hbar += (r*h) U^T
                     mbar_wait(BAR(B_RSREADY), par);
                     tc_fence_after();
+                    if (V2 && stateful) {
+                        tma_bulk_s2g(a.st.RSp + ((size_t)t * n_tiles + tile) * KP * PANEL_BYTES, s_ah + KP * PANEL_BYTES, KP * PANEL_BYTES);
+                        bulk_commit();
+                    }
                     if (stateful)
                         for (int kp = 0; kp < KP; ++kp) mma_wtile(s_ah + (KP + kp) * PANEL_BYTES, 3 * H, false);
+                    if (V2) bulk_wait_read();      // h_t / m_t / r*h_t dumps are out before E4 rewrites the h panels
                     tc_commit(BAR(B_ZH));
                 }
         }
@@ -193,6 +209,16 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     const long g = wrow(r);
                     return g >= 0 ? base + g * ld + col0 : nullptr;
                 });
+            };
+            // bf16 gate values in the thread-native order [16-byte chunk j][thread]: coalesced 512 B per warp store
+            auto store_native16 = [&](int t, int arr, int cc, const float *vals) {
+                uint8_t *base = a.st.zn(t, tile, arr, H);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint4 pk = make_uint4(pack_bf16(vals[8 * g], vals[8 * g + 1]), pack_bf16(vals[8 * g + 2], vals[8 * g + 3]),
+                                          pack_bf16(vals[8 * g + 4], vals[8 * g + 5]), pack_bf16(vals[8 * g + 6], vals[8 * g + 7]));
+                    *reinterpret_cast<uint4 *>(base + ((size_t)((cc >> 3) + g) * NEPI + tid) * 16) = pk;
+                }
             };
             auto store_rows16 = [&](float *base, long ld, int col0, const float *vals) {
                 warp_store_rows<16>(stg, vals, lane, [&](int r) -> float * {
@@ -225,7 +251,11 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     if (a.Hs) store_rows(a.Hs, H, colbase + cc, &hreg[cc]);
                 }
             }
-            auto store_h_operand = [&]() {
+            auto store_h_operand = [&](int t_next) {
+                if (V2 && t_next < a.T) {
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc += 16) store_native16(t_next, 3, cc, &hreg[cc]);
+                }
 #pragma unroll
                 for (int g = 0; g < NC / 8; ++g) {
                     const int kk = colbase + 8 * g;
@@ -234,7 +264,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     *reinterpret_cast<uint4 *>(smem + C::OFF_H + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
                 }
             };
-            store_h_operand();
+            store_h_operand(0);
             // degrees deg_e[atom] = sum_j A_e[atom][j]  (from the staged bf16 tile; needs the staging complete)
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI));
             float deg[4];
@@ -335,6 +365,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                             r[x] = sigmoid_fast(__uint_as_float(w[x]) + __ldg(b3 + colbase + cc + x));
                             rs[x] = r[x] * hreg[cc + x];
                         }
+                        if (V2) store_native16(t, 2, cc, r);
                         if (a.Gs) {
                             store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, colbase + cc, r);
                             store_rows16(a.RSs + (long)t * rows_total * H, H, colbase + cc, rs);
@@ -378,6 +409,10 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                         hb[x] = tanh_fast(__uint_as_float(wh[x]) + __ldg(b3 + 2 * H + colbase + cc + x));
                         hreg[cc + x] = stateful ? fmaf(z[x], hb[x] - hreg[cc + x], hreg[cc + x]) : z[x] * hb[x];
                     }
+                    if (V2) {
+                        store_native16(t, 0, cc, z);
+                        store_native16(t, 1, cc, hb);
+                    }
                     if (a.Gs) {
                         store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, H + colbase + cc, z);
                         store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, 2 * H + colbase + cc, hb);
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 }
                 TSF(7);
                 if (t + 1 < a.T) {
-                    store_h_operand();
+                    store_h_operand(t + 1);
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(BAR(B_HREADY));
@@ -465,6 +500,11 @@ static size_t image_bytes(int H) { return (size_t)(11 * (H / 64)) * H * 128 + 3 
 
 using namespace bmp;
 
+extern "C" size_t bmp_ggnn_stash2_bytes(int mb, int hidden, int n_steps) {
+    if (hidden != 64 && hidden != 128) return 0;
+    return tc::Stash2::bytes((mb + 1) / 2, hidden, n_steps);
+}
+
 extern "C" size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps) {
     if (hidden != 64 && hidden != 128) return 0;
     return tc::image_bytes(hidden) * (size_t)n_steps + 2048;
@@ -497,6 +537,8 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj;
     k.h_out = a->h_out; k.h0_out = a->h0_out; k.Hs = a->Hs; k.Ms = a->Ms; k.Gs = a->Gs; k.RSs = a->RSs;
     k.dbg = g_tc_dbg_fwd;
+    k.use2 = a->stash2 != nullptr;
+    if (k.use2) k.st.carve(a->stash2, (a->mb + 1) / 2, H, T);
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
     const size_t ib = tc::image_bytes(H);
     int n_img = 0;
@@ -526,13 +568,14 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (a->mb + 1) / 2;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    if (H == 64) {
-        cudaFuncSetAttribute(tc::ggnn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<64>::SMEM_BYTES);
-        tc::ggnn_tc_kernel<64><<<grid, tc::NTHR, tc::Cfg<64>::SMEM_BYTES, st>>>(k);
-    } else {
-        cudaFuncSetAttribute(tc::ggnn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<128>::SMEM_BYTES);
-        tc::ggnn_tc_kernel<128><<<grid, tc::NTHR, tc::Cfg<128>::SMEM_BYTES, st>>>(k);
-    }
+#define LAUNCH_FWD(HH, VV)                                                                                              \
+    do {                                                                                                                 \
+        cudaFuncSetAttribute(tc::ggnn_tc_kernel<HH, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<HH>::SMEM_BYTES); \
+        tc::ggnn_tc_kernel<HH, VV><<<grid, tc::NTHR, tc::Cfg<HH>::SMEM_BYTES, st>>>(k);                                   \
+    } while (0)
+    if (H == 64) { if (k.use2) LAUNCH_FWD(64, true); else LAUNCH_FWD(64, false); }
+    else { if (k.use2) LAUNCH_FWD(128, true); else LAUNCH_FWD(128, false); }
+#undef LAUNCH_FWD
     count_launch();
     return check_launch("ggnn_tc_kernel");
 }

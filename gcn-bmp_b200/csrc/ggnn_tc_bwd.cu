@@ -39,6 +39,8 @@ struct Args {
     int stateful[BMP_MAX_STEPS];
     const int *ext_flags;        // [T+1]: != 0 where dHs[t] holds a non-zero external gradient
     long long *dbg;              // optional phase timestamps of CTA 0 (tools/tc_timeline.py)
+    Stash2 st;                   // bf16 panel stash (use2 != 0): gate values in, delta / P panels out
+    int use2;                    //   then dHs has two slices: [0] <-> h_0, [1] <-> h_T
 };
 
 // flags[t] |= 1 when dHs[t] has any non-zero entry (the intermediate states normally receive no external gradient)
@@ -53,7 +55,7 @@ __global__ void nonzero_flags_kernel(const float *__restrict__ x, long n_per_t, 
     if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flags + t, 1);
 }
 
-template <int H>
+template <int H, bool V2>
 __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
     using C = Cfg<H>;
     constexpr int KP = C::KP;
@@ -140,6 +142,13 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                     const bool stateful = a.stateful[t] != 0;
                     mbar_wait(BAR(B_DRDY), par);
                     tc_fence_after();
+                    uint8_t *Dt = V2 ? a.st.Dp + ((size_t)t * n_tiles + tile) * 3 * KP * PANEL_BYTES : nullptr;
+                    uint8_t *Pt2 = V2 ? a.st.Pp + ((size_t)t * n_tiles + tile) * 4 * KP * PANEL_BYTES : nullptr;
+                    if (V2) {   // delta_z | delta_h panels (and the zeroed delta_r of a stateless step)
+                        const uint32_t from = stateful ? KP : 0;
+                        tma_bulk_s2g(Dt + (size_t)from * PANEL_BYTES, s_d + from * PANEL_BYTES, (3 * KP - from) * PANEL_BYTES);
+                        bulk_commit();
+                    }
                     if (stateful)
                         for (int kp = 0; kp < KP; ++kp) mma_wtile(s_d + (2 * KP + kp) * PANEL_BYTES, COL_Q, kp == 0);
                     tc_commit(BAR(B_Q));
@@ -150,9 +159,14 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                                 mma_wtile(s_d + (kb * KP + kp) * PANEL_BYTES, nb ? COL_DM : COL_DHX, kb == 1 && kp == 0);
                     mbar_wait(BAR(B_DRRDY), par);
                     tc_fence_after();
+                    if (V2 && stateful) {
+                        tma_bulk_s2g(Dt, s_d, KP * PANEL_BYTES);      // delta_r panels
+                        bulk_commit();
+                    }
                     if (stateful)
                         for (int nb = 0; nb < 2; ++nb)
                             for (int kp = 0; kp < KP; ++kp) mma_wtile(s_d + kp * PANEL_BYTES, nb ? COL_DM : COL_DHX, false);
+                    if (V2) bulk_wait_read();      // the delta panels are about to be reused (dm, Pcat)
                     tc_commit(BAR(B_DX));
                     mbar_wait(BAR(B_DMRDY), par);
                     tc_fence_after();
@@ -161,12 +175,22 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                     mma_p(0, 1, 3 * H, B_P + 2);
                     mbar_wait(BAR(B_PRDY + 0), par);          // P(0,0) has left columns [0,H); Pcat half 0 is ready
                     tc_fence_after();
+                    if (V2) {
+                        tma_bulk_s2g(Pt2, s_d, 2 * KP * PANEL_BYTES);
+                        bulk_commit();
+                    }
                     mma_p(1, 1, 0 * H, B_P + 3);
                     for (int kp = 0; kp < 2 * KP; ++kp) mma_wtile(s_d + kp * PANEL_BYTES, COL_DHX, false);
+                    if (V2) bulk_wait_read();
                     tc_commit(BAR(B_PFREE));
                     mbar_wait(BAR(B_PRDY + 1), par);
                     tc_fence_after();
+                    if (V2) {
+                        tma_bulk_s2g(Pt2 + (size_t)2 * KP * PANEL_BYTES, s_d, 2 * KP * PANEL_BYTES);
+                        bulk_commit();
+                    }
                     for (int kp = 0; kp < 2 * KP; ++kp) mma_wtile(s_d + kp * PANEL_BYTES, COL_DHX, false);
+                    if (V2) bulk_wait_read();
                     tc_commit(BAR(B_DH));
                 }
         }
@@ -184,7 +208,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
             const long grow = (long)molg * a.N + atom;
             stage_adjacency(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
             {
-                const float *src = live ? a.dHs + ((long)a.T * rows_total + grow) * H + colbase : nullptr;
+                const float *src = live ? a.dHs + ((long)(V2 ? 1 : a.T) * rows_total + grow) * H + colbase : nullptr;
 #pragma unroll
                 for (int c = 0; c < NC; c += 4) {
                     float4 v = src ? *reinterpret_cast<const float4 *>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -200,7 +224,44 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
 #define TS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TS(0);
                 // ---- phase A: gate derivatives ----
-                if (t > 0 && live) {   // pull the next step's stash lines towards L2 while this step computes
+                uint4 sp[NC / 8];            // state of the step, packed bf16 (stash v2), reused by phase B
+                if (V2) {
+                    // all gate values of the step in one burst of coalesced 16-byte loads (thread-native bf16 order)
+                    uint4 zp[NC / 8], hp[NC / 8];
+                    const uint8_t *bz = a.st.zn(t, tile, 0, H), *bh = a.st.zn(t, tile, 1, H), *bs = a.st.zn(t, tile, 3, H);
+#pragma unroll
+                    for (int j = 0; j < NC / 8; ++j) {
+                        zp[j] = __ldg(reinterpret_cast<const uint4 *>(bz + ((size_t)j * NEPI + tid) * 16));
+                        hp[j] = __ldg(reinterpret_cast<const uint4 *>(bh + ((size_t)j * NEPI + tid) * 16));
+                        sp[j] = stateful ? __ldg(reinterpret_cast<const uint4 *>(bs + ((size_t)j * NEPI + tid) * 16)) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NC / 8; ++j) {
+                        const __nv_bfloat162 *z2 = reinterpret_cast<const __nv_bfloat162 *>(&zp[j]);
+                        const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&hp[j]);
+                        const __nv_bfloat162 *s2 = reinterpret_cast<const __nv_bfloat162 *>(&sp[j]);
+                        float dz[8], dh[8];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const float2 zz = __bfloat1622float2(z2[x]), hh = __bfloat1622float2(h2[x]), ss = __bfloat1622float2(s2[x]);
+                            const float g0 = live ? acc[8 * j + 2 * x] : 0.f, g1 = live ? acc[8 * j + 2 * x + 1] : 0.f;
+                            dz[2 * x] = g0 * (hh.x - ss.x) * zz.x * (1.f - zz.x);
+                            dz[2 * x + 1] = g1 * (hh.y - ss.y) * zz.y * (1.f - zz.y);
+                            dh[2 * x] = g0 * zz.x * (1.f - hh.x * hh.x);
+                            dh[2 * x + 1] = g1 * zz.y * (1.f - hh.y * hh.y);
+                            acc[8 * j + 2 * x] = stateful ? g0 * (1.f - zz.x) : 0.f;
+                            acc[8 * j + 2 * x + 1] = stateful ? g1 * (1.f - zz.y) : 0.f;
+                        }
+                        const int kk = colbase + 8 * j;
+                        uint4 pz = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
+                        uint4 ph = make_uint4(pack_bf16(dh[0], dh[1]), pack_bf16(dh[2], dh[3]), pack_bf16(dh[4], dh[5]), pack_bf16(dh[6], dh[7]));
+                        *reinterpret_cast<uint4 *>(smem + C::OFF_D + (KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pz;
+                        *reinterpret_cast<uint4 *>(smem + C::OFF_D + (2 * KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = ph;
+                        if (!stateful)   // delta_r panel of a stateless step: zeros (the merged W_r contraction reads it)
+                            *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = make_uint4(0, 0, 0, 0);
+                    }
+                } else {
+                if (t > 0 && live && !V2) {   // pull the next step's stash lines towards L2 while this step computes
                     const char *pg = reinterpret_cast<const char *>(a.Gs + ((long)(t - 1) * rows_total + grow) * 3 * H + colbase);
                     const char *ps = reinterpret_cast<const char *>(a.Hs + ((long)(t - 1) * rows_total + grow) * H + colbase);
                     const char *pe = reinterpret_cast<const char *>(a.dHs + ((long)(t - 1) * rows_total + grow) * H + colbase);
@@ -251,10 +312,48 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         *reinterpret_cast<uint4 *>(smem + C::OFF_D + (2 * KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = ph;
                     }
                 }
+                }
                 fence_proxy_async();
                 mbar_arrive(BAR(B_DRDY));
                 TS(1);
                 // ---- phase B: through U and the reset gate ----
+                if (V2) {
+                    uint4 rp[NC / 8];
+                    if (stateful) {   // requested before waiting for q: the latency overlaps MMA-q
+                        const uint8_t *br = a.st.zn(t, tile, 2, H);
+#pragma unroll
+                        for (int j = 0; j < NC / 8; ++j) rp[j] = __ldg(reinterpret_cast<const uint4 *>(br + ((size_t)j * NEPI + tid) * 16));
+                    }
+                    mbar_wait(BAR(B_Q), par);
+                    tc_fence_after();
+                    TS(2);
+                    if (stateful) {
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc += 32) {
+                            tc_ld32(t_lane + COL_Q + colbase + cc, v);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int j = (cc >> 3) + g;
+                                const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rp[j]);
+                                const __nv_bfloat162 *s2 = reinterpret_cast<const __nv_bfloat162 *>(&sp[j]);
+                                float dr[8];
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) {
+                                    const float2 rr = __bfloat1622float2(r2[x]), ss = __bfloat1622float2(s2[x]);
+                                    const float q0 = live ? __uint_as_float(v[8 * g + 2 * x]) : 0.f, q1 = live ? __uint_as_float(v[8 * g + 2 * x + 1]) : 0.f;
+                                    acc[8 * j + 2 * x] += q0 * rr.x;
+                                    acc[8 * j + 2 * x + 1] += q1 * rr.y;
+                                    dr[2 * x] = q0 * ss.x * rr.x * (1.f - rr.x);
+                                    dr[2 * x + 1] = q1 * ss.y * rr.y * (1.f - rr.y);
+                                }
+                                const int kk = colbase + 8 * j;
+                                uint4 pr = make_uint4(pack_bf16(dr[0], dr[1]), pack_bf16(dr[2], dr[3]), pack_bf16(dr[4], dr[5]), pack_bf16(dr[6], dr[7]));
+                                *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pr;
+                            }
+                        }
+                    }
+                } else {
                 // r and the state of the first column chunk are requested BEFORE waiting for q, so their latency
                 // overlaps MMA-q; the second chunk is requested while the first is being consumed.
                 float rr[32], ss[32];
@@ -300,6 +399,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         }
                     }
                 }
+                }
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(BAR(B_DRRDY));
@@ -344,7 +444,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                         for (int cc = 0; cc < NC; cc += 32) {
                             tc_ld32(t_lane + pcol + colbase + cc, v);
                             tc_wait_ld();
-                            if (olive) {
+                            if (olive && !V2) {
 #pragma unroll
                                 for (int x = 0; x < 32; x += 4)
                                     *reinterpret_cast<float4 *>(Pt + cc + x) = make_float4(__uint_as_float(v[x]), __uint_as_float(v[x + 1]),
@@ -371,8 +471,8 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 tc_fence_after();
                 TS(11);
                 {
-                    float *ext = a.dHs + ((long)t * rows_total + grow) * H + colbase;
-                    const bool has_ext = live && a.ext_flags[t] != 0;
+                    float *ext = a.dHs + ((long)(V2 ? 0 : t) * rows_total + grow) * H + colbase;
+                    const bool has_ext = live && (V2 ? t == 0 : a.ext_flags[t] != 0);
 #pragma unroll
                     for (int cc = 0; cc < NC; cc += 32) {
                         tc_ld32(t_lane + COL_DHX + colbase + cc, v);
@@ -466,11 +566,15 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
     int *flags = reinterpret_cast<int *>(ws);      // first 256 B of the workspace: per-step external-gradient flags
     ws += 256;
-    cudaMemsetAsync(flags, 0, (T + 1) * sizeof(int), st);
-    tcb::nonzero_flags_kernel<<<dim3(64, T + 1), 256, 0, st>>>(a->dHs, (long)a->mb * a->n_atoms * H, flags);
-    count_launch();
+    if (!a->stash2) {
+        cudaMemsetAsync(flags, 0, (T + 1) * sizeof(int), st);
+        tcb::nonzero_flags_kernel<<<dim3(64, T + 1), 256, 0, st>>>(a->dHs, (long)a->mb * a->n_atoms * H, flags);
+        count_launch();
+    }
     k.ext_flags = flags;
     k.dbg = g_tc_dbg;
+    k.use2 = a->stash2 != nullptr;
+    if (k.use2) k.st.carve(a->stash2, (a->mb + 1) / 2, H, T);
     const size_t ib = tcb::image_bytes(H);
     int n_img = 0;
     for (int t = 0; t < T; ++t) {
@@ -494,13 +598,77 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (a->mb + 1) / 2;
     const int grid = n_tiles < sms ? n_tiles : sms;
-    if (H == 64) {
-        cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<64>::SMEM_BYTES);
-        tcb::ggnn_tc_bwd_kernel<64><<<grid, tc::NTHR, tcb::Cfg<64>::SMEM_BYTES, st>>>(k);
-    } else {
-        cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<128>::SMEM_BYTES);
-        tcb::ggnn_tc_bwd_kernel<128><<<grid, tc::NTHR, tcb::Cfg<128>::SMEM_BYTES, st>>>(k);
-    }
+#define LAUNCH_BWD(HH, VV)                                                                                                   \
+    do {                                                                                                                      \
+        cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<HH, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<HH>::SMEM_BYTES); \
+        tcb::ggnn_tc_bwd_kernel<HH, VV><<<grid, tc::NTHR, tcb::Cfg<HH>::SMEM_BYTES, st>>>(k);                                  \
+    } while (0)
+    if (H == 64) { if (k.use2) LAUNCH_BWD(64, true); else LAUNCH_BWD(64, false); }
+    else { if (k.use2) LAUNCH_BWD(128, true); else LAUNCH_BWD(128, false); }
+#undef LAUNCH_BWD
     count_launch();
     return check_launch("ggnn_tc_bwd_kernel");
+}
+
+int bmp_wgrad_panels(const void *A, int a_ppt, const int a_panel[2], const void *B, int b_ppt, const int *b_panel, int nb,
+                     float *const C[2], int ldc, float *const bias[2], int bias_stride,
+                     int t0, int t1, int n_tiles, void *stream);   // wgrad_tc2.cu
+
+// Backward over the bf16 panel stash (stash v2): data kernel, then every parameter gradient as a
+// C += A^T B contraction whose operands are streamed straight from the dumped panels.
+int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
+    const int H = a->hidden, T = a->n_steps, KP = H / 64;
+    int rc = bmp_ggnn_backward_tc(a, stream);
+    if (rc) return rc;
+    tc::Stash2 S;
+    const int n_tiles = (a->mb + 1) / 2;
+    S.carve(a->stash2, n_tiles, H, T);
+    int bp[4] = {0, 1, 2, 3};
+    // one (A block pair) x (B panels) contraction; `col` selects which 64-row blocks of C this A pair covers
+    auto run = [&](const uint8_t *A, int a_ppt, int a_first, const uint8_t *B, int b_ppt, float *C, long c_row_stride, int ldc,
+                   float *bias, int bias_stride, int t0, int t1) -> int {
+        for (int mt = 0; mt < KP; mt += 2) {
+            int ap[2] = {a_first + mt, mt + 1 < KP ? a_first + mt + 1 : -1};
+            float *Cs[2] = {C ? C + (long)(mt * 64) * c_row_stride : nullptr, (C && mt + 1 < KP) ? C + (long)((mt + 1) * 64) * c_row_stride : nullptr};
+            float *bs[2] = {bias ? bias + (long)(mt * 64) * bias_stride : nullptr, (bias && mt + 1 < KP) ? bias + (long)((mt + 1) * 64) * bias_stride : nullptr};
+            int e = bmp_wgrad_panels(A, a_ppt, ap, B, b_ppt, bp, KP, Cs, ldc, bs, bias_stride, t0, t1, n_tiles, stream);
+            if (e) return e;
+        }
+        return BMP_OK;
+    };
+    int t0 = 0;
+    while (t0 < T) {
+        int t1 = t0;
+        while (t1 + 1 < T && a->d_msg_W[t1 + 1] == a->d_msg_W[t0] && a->d_gru[t1 + 1].W == a->d_gru[t0].W &&
+               a->d_gru[t1 + 1].U == a->d_gru[t0].U)
+            ++t1;
+        const bmp_gru_grad_t &D = a->d_gru[t0];
+        float *Wg[3] = {D.W_r, D.W_z, D.W};
+        float *bg[3] = {D.b_Wr, D.b_Wz, D.b_W};
+        for (int g = 0; g < 3; ++g) {
+            if (!Wg[g]) continue;
+            // dW_g[:, :H] += delta_g^T h_t ;  dW_g[:, H:] += delta_g^T m_t   (delta_r of stateless steps is zero)
+            if ((rc = run(S.Dp, 3 * KP, g * KP, S.Xp, KP, Wg[g], 2 * H, 2 * H, bg[g], 1, t0, t1))) return rc;
+            if ((rc = run(S.Dp, 3 * KP, g * KP, S.Mp, KP, Wg[g] + H, 2 * H, 2 * H, nullptr, 1, t0, t1))) return rc;
+        }
+        if (a->d_msg_W[t0]) {
+            // dW_m[c*E+e][:] += P_e^T h_t : C rows c with stride E*H, offset e*H; bias d_msg_b[c*E+e]
+            for (int e = 0; e < 4; ++e)
+                if ((rc = run(S.Pp, 4 * KP, e * KP, S.Xp, KP, a->d_msg_W[t0] + (long)e * H, 4L * H, 4 * H,
+                              a->d_msg_b[t0] ? a->d_msg_b[t0] + e : nullptr, 4, t0, t1)))
+                    return rc;
+        }
+        int s0 = t0;
+        while (s0 <= t1) {       // U-type gradients only over stateful steps
+            if (!a->stateful[s0]) { ++s0; continue; }
+            int s1 = s0;
+            while (s1 + 1 <= t1 && a->stateful[s1 + 1]) ++s1;
+            if (D.U_r && (rc = run(S.Dp, 3 * KP, 0 * KP, S.Xp, KP, D.U_r, H, H, D.b_Ur, 1, s0, s1))) return rc;
+            if (D.U_z && (rc = run(S.Dp, 3 * KP, 1 * KP, S.Xp, KP, D.U_z, H, H, D.b_Uz, 1, s0, s1))) return rc;
+            if (D.U && (rc = run(S.Dp, 3 * KP, 2 * KP, S.RSp, KP, D.U, H, H, D.b_U, 1, s0, s1))) return rc;
+            s0 = s1 + 1;
+        }
+        t0 = t1 + 1;
+    }
+    return BMP_OK;
 }

@@ -38,6 +38,13 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// smem -> global bulk store (async proxy; completion tracked by the issuing thread's bulk group)
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -219,6 +226,36 @@ __device__ __forceinline__ void warp_transpose_in(float *stg, const float4 (&x)[
     }
     __syncwarp();
 }
+
+// ---- bf16 panel stash (stash v2) -----------------------------------------------------------------
+// Per (step t, tile): forward dumps the operand panels h_t, m_t, r*h_t (KP panels each) verbatim and the
+// gate values z | hbar | r | state as bf16 in the epilogue threads' native order ([16-byte chunk][thread]);
+// backward dumps the delta panels (3KP) and the P panels (4KP).  A 64-row half of a panel is an MN-major
+// UMMA operand block for the parameter-gradient contraction (wgrad_tc2.cu).
+struct Stash2 {
+    uint8_t *Xp, *Mp, *RSp, *Zn, *Dp, *Pp;
+    long n_tiles;
+    int KP, T;
+    __host__ __device__ static size_t bytes(long n_tiles, int H, int T) {
+        const size_t KP = H / 64, per = (size_t)n_tiles * T;
+        return per * (3 * KP + 3 * KP + 4 * KP) * PANEL_BYTES + per * 4 * (size_t)NEPI * (H / 2) * 2 + 4096;
+    }
+    __host__ __device__ void carve(void *base, long nt, int H, int T_) {
+        n_tiles = nt; KP = H / 64; T = T_;
+        const size_t per = (size_t)nt * T_;
+        uint8_t *p = (uint8_t *)(((uintptr_t)base + 1023) & ~(uintptr_t)1023);
+        Xp = p; p += per * KP * PANEL_BYTES;
+        Mp = p; p += per * KP * PANEL_BYTES;
+        RSp = p; p += per * KP * PANEL_BYTES;
+        Dp = p; p += per * 3 * KP * PANEL_BYTES;
+        Pp = p; p += per * 4 * KP * PANEL_BYTES;
+        Zn = p;
+    }
+    // native gate block of (t, tile, array a in 0..3 = z, hbar, r, state): NEPI threads x H/2 bf16
+    __host__ __device__ uint8_t *zn(int t, long tile, int a, int H) const {
+        return Zn + (((size_t)t * n_tiles + tile) * 4 + a) * ((size_t)NEPI * (H / 2) * 2);
+    }
+};
 
 }  // namespace tc
 }  // namespace bmp

@@ -31,7 +31,7 @@ class GgnnFwd(C.Structure):
         ("atoms", fp), ("h_in", fp), ("embed_W", fp), ("adj", fp), ("state_in", fp),
         ("msg_W", _A()), ("msg_b", _A()), ("gru", GRU * MAX_STEPS), ("stateful", C.c_int * MAX_STEPS),
         ("h_out", fp), ("h0_out", fp), ("Hs", fp), ("Ms", fp), ("Gs", fp), ("RSs", fp),
-        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp)]
 
 
 class GgnnBwd(C.Structure):
@@ -39,7 +39,7 @@ class GgnnBwd(C.Structure):
         ("adj", fp), ("state_in", fp), ("msg_W", _A()), ("gru", GRU * MAX_STEPS),
         ("stateful", C.c_int * MAX_STEPS), ("Hs", fp), ("Ms", fp), ("RSs", fp), ("Gs", fp), ("Ps", fp), ("dHs", fp),
         ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS), ("d_state_in", fp),
-        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp)]
 
 
 class RelgcnFwd(C.Structure):
@@ -114,6 +114,7 @@ def _load():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = args, C.c_int
     lib.bmp_ggnn_tc_workspace_bytes.argtypes, lib.bmp_ggnn_tc_workspace_bytes.restype = [i, i], C.c_size_t
+    lib.bmp_ggnn_stash2_bytes.argtypes, lib.bmp_ggnn_stash2_bytes.restype = [i, i, i], C.c_size_t
     lib.bmp_readout_tc_workspace_bytes.argtypes, lib.bmp_readout_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_last_error.restype = C.c_char_p
     lib.bmp_version.restype = C.c_int
@@ -127,7 +128,7 @@ lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
            "bmp_relgcn_backward", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
-           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
+           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]
 
 

@@ -55,7 +55,7 @@ class GGNNEncode(torch.autograd.Function):
     Returns Hs (T+1, mb, N, H) when a tape is needed, else a (2, mb, N, H) tensor [h_0, h_T]."""
 
     @staticmethod
-    def forward(ctx, x, adj, state_in, plan, n_msg, n_gru, mode, want_stash, *params):
+    def forward(ctx, x, adj, state_in, plan, n_msg, n_gru, mode, want_stash, keep_steps, *params):
         _need_cuda(x, adj)
         adj = _f32(adj)
         mb, E, N, _ = adj.shape
@@ -88,6 +88,15 @@ class GGNNEncode(torch.autograd.Function):
                 raise ValueError("gcnbmp: BMP_MODE_BF16 supports hidden 64 or 128 (got %d)" % H)
             ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
+        if want_stash and mode == K.MODE_BF16 and not keep_steps:
+            # bf16 panel stash: the tape keeps operand panels + gate values; only [h_0, h_T] go back as fp32
+            out = torch.empty((2, mb, N, H), device=dev, dtype=torch.float32)
+            stash2 = torch.empty((int(K.lib.bmp_ggnn_stash2_bytes(mb, H, T)),), device=dev, dtype=torch.uint8)
+            a.h0_out, a.h_out, a.stash2 = _p(out[0]), _p(out[1]), _p(stash2)
+            K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
+            ctx.save_for_backward(x, adj, state_in, stash2, None, None, None, *params)
+            ctx.meta = (plan, n_msg, n_gru, mode, is_ids, (mb, N, H))
+            return out
         if want_stash:
             Hs = torch.empty((T + 1, mb, N, H), device=dev, dtype=torch.float32)
             Ms = torch.empty((T, rows, H), device=dev, dtype=torch.float32)
@@ -96,7 +105,7 @@ class GGNNEncode(torch.autograd.Function):
             a.Hs, a.Ms, a.Gs, a.RSs = _p(Hs), _p(Ms), _p(Gs), _p(RSs)
             K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
             ctx.save_for_backward(x, adj, state_in, Hs, Ms, Gs, RSs, *params)
-            ctx.meta = (plan, n_msg, n_gru, mode, is_ids)
+            ctx.meta = (plan, n_msg, n_gru, mode, is_ids, None)
             return Hs
         out = torch.empty((2, mb, N, H), device=dev, dtype=torch.float32)   # [h_0, h_T]
         a.h0_out, a.h_out = _p(out[0]), _p(out[1])
@@ -107,14 +116,19 @@ class GGNNEncode(torch.autograd.Function):
     def backward(ctx, dHs):
         x, adj, state_in, Hs, Ms, Gs, RSs = ctx.saved_tensors[:7]
         params = ctx.saved_tensors[7:]
-        plan, n_msg, n_gru, mode, is_ids = ctx.meta
+        plan, n_msg, n_gru, mode, is_ids, v2shape = ctx.meta
         T = len(plan)
-        _, mb, N, H = Hs.shape
         E = adj.shape[1]
+        stash2 = None
+        if v2shape is not None:
+            stash2, Hs = Hs, None
+            mb, N, H = v2shape
+        else:
+            _, mb, N, H = Hs.shape
         rows = mb * N
         dHs = dHs.contiguous().clone()
         grads = [torch.zeros_like(p) if p is not None else None for p in params]
-        Ps = torch.empty((T, rows, E * H), device=Hs.device, dtype=torch.float32)
+        Ps = torch.empty((T, rows, E * H), device=adj.device, dtype=torch.float32) if stash2 is None else None
         a = K.GgnnBwd()
         a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
         a.adj, a.state_in = _p(adj), _p(state_in)
@@ -126,11 +140,12 @@ class GGNNEncode(torch.autograd.Function):
             a.d_msg_W[t], a.d_msg_b[t] = _p(grads[1 + 2 * mi]), _p(grads[2 + 2 * mi])
             _fill_gru(a.d_gru[t], grads[base + 12 * gi: base + 12 * (gi + 1)])
         a.Hs, a.Ms, a.RSs, a.Gs, a.Ps, a.dHs = _p(Hs), _p(Ms), _p(RSs), _p(Gs), _p(Ps), _p(dHs)
+        a.stash2 = _p(stash2)
         d_state = torch.zeros_like(state_in) if state_in is not None else None
         a.d_state_in = _p(d_state)
         if mode == K.MODE_BF16:
             nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
-            ws = torch.empty((nbytes,), device=Hs.device, dtype=torch.uint8)
+            ws = torch.empty((nbytes,), device=adj.device, dtype=torch.uint8)
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
         K.check(K.lib.bmp_ggnn_backward(C.byref(a), _stream()))
         dx = None
@@ -139,7 +154,7 @@ class GGNNEncode(torch.autograd.Function):
         else:
             dx = dHs[0]
             grads[0] = None
-        return (dx, None, d_state, None, None, None, None, None) + tuple(grads)
+        return (dx, None, d_state, None, None, None, None, None, None) + tuple(grads)
 
 
 class RelGCNEncode(torch.autograd.Function):

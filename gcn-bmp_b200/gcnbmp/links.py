@@ -252,14 +252,17 @@ class _GRU(Link):
                 c["U_z"].W, c["U_z"].b, c["W"].W, c["W"].b, c["U"].W, c["U"].b]
 
 
-def _encode(x, adj, state, plan, msgs, grus, embed_W, mode):
+def _encode(x, adj, state, plan, msgs, grus, embed_W, mode, keep_steps=False):
+    """Returns (states, last): states[0] = h_0, states[last] = h_T; every step is present only when
+    `keep_steps` (or in fp32 mode with a tape) -- BF16 mode otherwise keeps a bf16 panel stash internally."""
     want = torch.is_grad_enabled()
     params = [embed_W]
     for W, b in msgs:
         params += [W, b]
     for g in grus:
         params += g.tensors()
-    return Fn.GGNNEncode.apply(x, adj, state, tuple(plan), len(msgs), len(grus), mode, want, *params), want
+    out = Fn.GGNNEncode.apply(x, adj, state, tuple(plan), len(msgs), len(grus), mode, want, keep_steps, *params)
+    return out, (out.shape[0] - 1)
 
 
 class GGNNUpdate(Link):
@@ -276,8 +279,8 @@ class GGNNUpdate(Link):
         gru = self.update_layer
         state = gru.h
         gl = self.graph_linear
-        out, stash = _encode(h, adj, state, [(0, 0, state is not None)], [(gl.W, gl.b)], [gru], None, self.mode)
-        out = out[1]
+        out, last = _encode(h, adj, state, [(0, 0, state is not None)], [(gl.W, gl.b)], [gru], None, self.mode)
+        out = out[last]
         gru.__dict__["h"] = out
         return out
 
@@ -368,8 +371,10 @@ class GGNN(Link):
         msgs = [(u.graph_linear.W, u.graph_linear.b) for u in ups]
         grus = [u.update_layer for u in ups]
         T = self.n_layers
-        hs, stash = _encode(x, adj, None, self._plan(), msgs, grus, self.embed.W if ids else None, self.mode)
-        h0, hT = hs[0], hs[T if stash else 1]
+        hs, last = _encode(x, adj, None, self._plan(), msgs, grus, self.embed.W if ids else None, self.mode,
+                           keep_steps=self.concat_hidden)
+        stash = last == T
+        h0, hT = hs[0], hs[last]
         self.__dict__["atoms"] = hT
         for r in self.readout_layers:
             r.__dict__["mode"] = self.mode
@@ -411,7 +416,8 @@ class GGNNMono(Link):
         self.add_link("j_layers", ChainList([GraphLinear(hidden_dim, out_dim) for _ in range(n_readout_layer)]))
         self.__dict__.update(out_dim=out_dim, hidden_dim=hidden_dim, n_layers=n_layers,
                              concat_hidden=concat_hidden, weight_tying=weight_tying,
-                             sum_readout=sum_readout, atoms=None, atoms_list=None, mode=K.MODE_F32)
+                             sum_readout=sum_readout, atoms=None, atoms_list=None, mode=K.MODE_F32,
+                             keep_steps=False)   # keep_steps: expose every step through get_atom_array(step)
 
     def readout(self, h, h0, step=0):
         idx = step if self.concat_hidden else 0
@@ -426,8 +432,10 @@ class GGNNMono(Link):
         T = self.n_layers
         msgs = [(m.W, m.b) for m in self.message_layers]
         plan = [(0 if self.weight_tying else t, 0, t > 0) for t in range(T)]
-        hs, stash = _encode(x, adj, None, plan, msgs, [self.update_layer], self.embed.W if ids else None, self.mode)
-        h0, hT = hs[0], hs[T if stash else 1]
+        hs, last = _encode(x, adj, None, plan, msgs, [self.update_layer], self.embed.W if ids else None, self.mode,
+                           keep_steps=self.concat_hidden or self.keep_steps)
+        stash = last == T
+        h0, hT = hs[0], hs[last]
         self.__dict__["atoms"] = hT
         self.__dict__["atoms_list"] = [hs[t + 1] for t in range(T)] if stash else None
         self.update_layer.__dict__["h"] = hT

@@ -87,11 +87,15 @@ typedef struct {
     float *Hs, *Ms, *Gs, *RSs;   /* stash or NULL                                   */
     void  *tc_workspace;         /* BMP_MODE_BF16 only: packed bf16 weight tiles    */
     size_t tc_workspace_bytes;   /* >= bmp_ggnn_tc_workspace_bytes(hidden, n_steps) */
+    void  *stash2;               /* BMP_MODE_BF16 training: bf16 panel stash of      */
+                                 /* bmp_ggnn_stash2_bytes() bytes; replaces Hs..RSs  */
 } bmp_ggnn_fwd_t;
 
 int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
 /* Bytes of device workspace the BMP_MODE_BF16 (tcgen05) encoder needs; 0 = shape unsupported. */
 size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps);
+/* Bytes of the bf16 panel stash (forward operand panels + gate values + backward delta/P panels). */
+size_t bmp_ggnn_stash2_bytes(int mb, int hidden, int n_steps);
 
 /* Backward of the above (Chainer autograd through the same lines).
  * dHs (T+1, mb*N, H): on entry the external gradient w.r.t. every h_t (zero where
@@ -114,6 +118,8 @@ typedef struct {
     float *d_state_in;
     void  *tc_workspace;         /* BMP_MODE_BF16 only (same size rule as the forward) */
     size_t tc_workspace_bytes;
+    void  *stash2;               /* the forward's panel stash; then Hs/Ms/RSs/Gs/Ps may be NULL and dHs has TWO
+                                    slices: [0] = gradient w.r.t. h_0, [1] = gradient w.r.t. h_T               */
 } bmp_ggnn_bwd_t;
 
 int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
