@@ -83,9 +83,11 @@ def build_model(mode="bf16"):
     gcnbmp.seed(777)
     enc = gcnbmp.GGNNMono(CFG["O"], CFG["H"], CFG["T"], weight_tying=True)
     enc.mode = gcnbmp.MODE_BF16 if mode == "bf16" else gcnbmp.MODE_F32
+    BF = enc.mode
     attn = gcnbmp.NieFineCoattention(CFG["H"], CFG["O"], CFG["head"], activation=gcnbmp.functions.tanh)
     mlp = gcnbmp.HolE(CFG["K"], hidden_dims=())
     mlp.l_out.ensure(CFG["O"])
+    attn.mode = BF      # BF16 mode: the co-attention's (H,H)/(O,H) weight-gradient contractions run on tcgen05
     return gcnbmp.GraphConvPredictorForPair(enc, attn, mlp)
 
 
@@ -204,9 +206,9 @@ def run_gpu(args):
     fp32_exact = None
     if args.mode == "bf16" and not args.no_fp32:
         import gcnbmp as _g
-        model.graph_conv.mode = _g.MODE_F32
+        model.graph_conv.mode = model.attn.mode = _g.MODE_F32
         ms32, _ = timed(lambda: trainer.step(*resident, global_count=gcount), 1, 1)
-        model.graph_conv.mode = _g.MODE_BF16
+        model.graph_conv.mode = model.attn.mode = _g.MODE_BF16
         fp32_exact = dict(value=round(args.pairs / (ms32 * 1e-3), 1), unit="pairs/s", ms_per_step=round(ms32, 3),
                           note="BMP_MODE_F32: parity <= 1e-4 vs the oracle")
     cpu = cpu_baseline(args) if rank == 0 and not args.no_cpu else None

@@ -594,10 +594,15 @@ extern "C" int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream) {
     const int H = a->hidden, O = a->out_dim, hd = a->head;
     const long rows1 = (long)a->mb * a->n1, rows2 = (long)a->mb * a->n2;
     // d W[h][k] += sum_{pairs,j} a1[j][h] R[j][k]
-    if (a->d_W && (rc = bmp_wgrad(a->atoms_1, H, a->R, H, a->d_W, H, rows1, H, H, stream))) return rc;
+    const bool tcw = a->mode == BMP_MODE_BF16 && (H == 64 || H == 128 || H == 256);
+    auto WG = [&](const float *A_, int lda, const float *B_, float *C_, long r_, int M_) -> int {
+        if (tcw && (M_ & 3) == 0) return bmp_wgrad_tc(A_, lda, B_, H, C_, H, r_, M_, H, nullptr, 1, stream);
+        return bmp_wgrad(A_, lda, B_, H, C_, H, r_, M_, H, stream);
+    };
+    if (a->d_W && (rc = WG(a->atoms_1, H, a->R, a->d_W, rows1, H))) return rc;
     if (a->d_W_j) {
-        if ((rc = bmp_wgrad(a->d_compact_1, O, a->P1, H, a->d_W_j, H, a->mb, O, H, stream))) return rc;
-        if ((rc = bmp_wgrad(a->d_compact_2, O, a->P2, H, a->d_W_j, H, a->mb, O, H, stream))) return rc;
+        if ((rc = WG(a->d_compact_1, O, a->P1, a->d_W_j, a->mb, O))) return rc;
+        if ((rc = WG(a->d_compact_2, O, a->P2, a->d_W_j, a->mb, O))) return rc;
     }
     if (a->d_b_j) {
         if ((rc = bmp_colsum(a->d_compact_1, O, a->d_b_j, 1, a->mb, O, stream))) return rc;

@@ -80,7 +80,7 @@ class CoattnBwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "out_dim", "head", "variant", "act")] + [
         (n, fp) for n in ("atoms_1", "atoms_2") + _CO_PARAMS + ("d_compact_1", "d_compact_2", "R", "P1", "P2",
                                                              "DL1", "DL2", "d_atoms_1", "d_atoms_2")
-        + tuple("d_" + p for p in _CO_PARAMS)]
+        + tuple("d_" + p for p in _CO_PARAMS)] + [("mode", C.c_int)]
 
 
 def _load():

@@ -291,7 +291,7 @@ class Coattention(torch.autograd.Function):
     """Fine-grained co-attention (Nie / VQA / Pooling)."""
 
     @staticmethod
-    def forward(ctx, atoms_1, atoms_2, variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j):
+    def forward(ctx, atoms_1, atoms_2, variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j, mode=0):
         _need_cuda(atoms_1, atoms_2)
         atoms_1, atoms_2 = _f32(atoms_1), _f32(atoms_2)
         mb, n1, H = atoms_1.shape
@@ -309,14 +309,14 @@ class Coattention(torch.autograd.Function):
         a.compact_1, a.compact_2 = _p(c1), _p(c2)
         K.check(K.lib.bmp_coattn_forward(C.byref(a), _stream()))
         ctx.save_for_backward(atoms_1, atoms_2, *ps)
-        ctx.meta = (variant, act, head)
+        ctx.meta = (variant, act, head, mode)
         return c1, c2
 
     @staticmethod
     def backward(ctx, dc1, dc2):
         atoms_1, atoms_2 = ctx.saved_tensors[:2]
         ps = ctx.saved_tensors[2:]
-        variant, act, head = ctx.meta
+        variant, act, head, mode = ctx.meta
         mb, n1, H = atoms_1.shape
         n2 = atoms_2.shape[1]
         O = ps[8].shape[0]
@@ -337,8 +337,9 @@ class Coattention(torch.autograd.Function):
         a.d_compact_1, a.d_compact_2 = _p(dc1), _p(dc2)
         a.R, a.P1, a.P2, a.DL1, a.DL2 = _p(R), _p(P1), _p(P2), _p(DL1), _p(DL2)
         a.d_atoms_1, a.d_atoms_2 = _p(da1), _p(da2)
+        a.mode = mode
         K.check(K.lib.bmp_coattn_backward(C.byref(a), _stream()))
-        return (da1, da2, None, None) + tuple(grads)
+        return (da1, da2, None, None) + tuple(grads) + (None,)
 
 
 class HoleCorr(torch.autograd.Function):

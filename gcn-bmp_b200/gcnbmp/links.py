@@ -554,7 +554,8 @@ class NieFineCoattention(Link):
         return Fn.Coattention.apply(
             _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32), K.COATTN_FINE,
             Fn.act_code(self.activation), e.W, e.V1, e.V2, e.b, self.lt_layer_1.W, self.lt_layer_2.W,
-            self.attention_layer_1.W, self.attention_layer_2.W, self.j_layer.W, self.j_layer.b)
+            self.attention_layer_1.W, self.attention_layer_2.W, self.j_layer.W, self.j_layer.b,
+            self.__dict__.get("mode", K.MODE_F32))
 
 
 class VQAParallelCoattention(NieFineCoattention):
@@ -576,7 +577,7 @@ class PoolingFineCoattention(Link):
         return Fn.Coattention.apply(
             _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32), K.COATTN_POOL,
             Fn.act_code(self.activation), e.W, e.V1, e.V2, e.b, None, None, None, None,
-            self.j_layer.W, self.j_layer.b)
+            self.j_layer.W, self.j_layer.b, self.__dict__.get("mode", K.MODE_F32))
 
 
 class HolE(Link):

@@ -224,6 +224,7 @@ typedef struct {
     float *R, *P1, *P2, *DL1, *DL2;
     float *d_atoms_1, *d_atoms_2;
     float *d_W, *d_V1, *d_V2, *d_b, *d_lt_1, *d_lt_2, *d_wa_1, *d_wa_2, *d_W_j, *d_b_j;
+    int    mode;   /* BMP_MODE_BF16: the (H,H) / (O,H) weight-gradient contractions run on tcgen05 */
 } bmp_coattn_bwd_t;
 
 int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream);
