@@ -199,7 +199,7 @@ def run_gpu(args):
         achieved = nmol * fl["encoder"] / (k_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=("ggnn_tc_kernel<128>" if args.mode == "bf16" else "ggnn_fwd_kernel<2>") + " (+readout launch)",
                     achieved=round(achieved, 3), peak=pk["bf16_sustained"], unit="TFLOP/s",
-                    frac=round(achieved / pk["bf16_sustained"], 5), traffic=224.6e6 if args.mode == "bf16" else 229.0e6,
+                    frac=round(achieved / pk["bf16_sustained"], 5), traffic=231.1e6 if args.mode == "bf16" else 229.0e6,
                     peak_source=pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                     note="algorithmic FLOPs = 188.8 MFLOP x %d molecules per launch; traffic = ncu dram bytes r+w per 2048-molecule launch" % nmol)
     # ---- the parity-exact fp32 mode on the same workload (1 warm-up + 1 step), for the record ----

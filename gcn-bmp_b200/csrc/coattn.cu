@@ -69,6 +69,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 struct CoArgs {
+    long long *dbg;
     int mb, n1, n2, H, O, head, variant, act;
     const float *atoms_1, *atoms_2, *W, *V1, *V2, *b, *lt_1, *lt_2, *wa_1, *wa_2, *W_j, *b_j;
 };
@@ -85,13 +86,16 @@ __device__ __forceinline__ void warp_softmax(float *x, int n, int lane) {
 
 // Forward for one pair into shared memory.  On exit (after the trailing sync):
 // Cs, L1t, L2p, lt*, H*, attn*, p* are valid.
+#define CTS(i) do { if (A.dbg && blockIdx.x == 0 && threadIdx.x == 0 && pair == 0) A.dbg[i] = clock64(); } while (0)
 __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
     const int H = A.H, N1 = A.n1, N2 = A.n2, hd = A.head;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    CTS(0);
     const float *a1 = A.atoms_1 + (long)pair * N1 * H, *a2 = A.atoms_2 + (long)pair * N2 * H;
     load_cm(S.a1s, a1, N1, H);
     load_cm(S.a2s, a2, N2, H);
     __syncthreads();
+    CTS(1);
     // v1[j] = V1 . a1_j ; v2[i] = V2 . a2_i
     if (tid < 2 * AT) {
         const int n = tid & 63;
@@ -108,6 +112,7 @@ __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
         if (oc * 64 + ty * 4 < H) tile_store_s(S.Qs, oc * 64, acc);
     }
     __syncthreads();
+    CTS(2);
     // C^T[j][i] = act(sum_h a1[j][h] Q[h][i] + v1[j] + v2[i] + b)
     {
         float acc[4][4];
@@ -133,6 +138,7 @@ __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
         }
         __syncthreads();
     }
+    CTS(3);
     if (A.variant == BMP_COATTN_FINE) {
         // column stats (softmax over i for each j) -> L2p ; row stats (over j for each i) -> L1t
         float *m2 = S.tmp, *s2 = S.tmp + AT, *m1 = S.tmp + 2 * AT, *s1 = S.tmp + 3 * AT;
@@ -160,15 +166,21 @@ __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
             S.L2p[j * PLD + i] = live ? expf(c - m2[j]) / s2[j] : 0.f;
             S.L1t[i * PLD + j] = live ? expf(c - m1[i]) / s1[i] : 0.f;
         }
-        // lt_k[d][n] = sum_h lt_k[d][h] a_k[n][h]
-        for (int idx = tid; idx < 2 * hd * AT; idx += NTHREADS) {
-            const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
-            const float *src = which ? S.a2s : S.a1s, *w = (which ? A.lt_2 : A.lt_1) + (long)d * H;
-            float s = 0.f;
-            for (int h = 0; h < H; ++h) s += w[h] * src[h * AT + n];
-            (which ? S.lt2 : S.lt1)[d * AT + n] = s;
+        CTS(4);
+        // lt_k[d][n] = sum_h lt_k[d][h] a_k[n][h]: two skinny (head x H) x (H x 64) register-tile contractions
+        __syncthreads();
+        for (int which = 0; which < 2; ++which) {
+            float acc[4][4];
+            zero_acc(acc);
+            gemm64_g<false>(acc, which ? A.lt_2 : A.lt_1, H, 0, hd, H, which ? S.a2s : S.a1s, S.stage);
+            float *dst = which ? S.lt2 : S.lt1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (ty * 4 + q < hd)
+                    *reinterpret_cast<float4 *>(dst + (ty * 4 + q) * AT + tx * 4) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
         }
         __syncthreads();
+        CTS(5);
         // H_1[j][d] = tanh(lt_1[j][d] + sum_i L_1[j][i] lt_2[i][d]) ; H_2[i][d] likewise
         for (int idx = tid; idx < 2 * hd * AT; idx += NTHREADS) {
             const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
@@ -205,9 +217,11 @@ __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
         }
     }
     __syncthreads();
+    CTS(6);
     if (warp == 0) warp_softmax(S.attn1, N1, lane);
     if (warp == 1) warp_softmax(S.attn2, N2, lane);
     __syncthreads();
+    CTS(7);
     // pooled atoms p_k[h] = sum_n attn_k[n] a_k[n][h]   (warp per channel)
     for (int r = warp; r < 2 * H; r += NTHREADS / 32) {
         const int which = r >= H, h = which ? r - H : r;
@@ -218,6 +232,7 @@ __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
         if (lane == 0) (which ? S.p2 : S.p1)[h] = s;
     }
     __syncthreads();
+    CTS(8);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) coattn_fwd_kernel(const CoArgs A, float *__restrict__ c1, float *__restrict__ c2) {
@@ -530,11 +545,15 @@ static int co_check(int mb, int n1, int n2, int H, int O, int head, int variant)
 
 using namespace bmp;
 
+static long long *g_co_dbg = nullptr;
+extern "C" void bmp_debug_set_buffer_co(void *p) { g_co_dbg = (long long *)p; }
+
 static CoArgs make_args(int mb, int n1, int n2, int H, int O, int head, int variant, int act,
                         const float *a1, const float *a2, const float *W, const float *V1, const float *V2,
                         const float *b, const float *lt1, const float *lt2, const float *wa1, const float *wa2,
                         const float *Wj, const float *bj) {
     CoArgs A;
+    A.dbg = g_co_dbg;
     A.mb = mb; A.n1 = n1; A.n2 = n2; A.H = H; A.O = O; A.head = head > 0 ? head : 1; A.variant = variant; A.act = act;
     A.atoms_1 = a1; A.atoms_2 = a2; A.W = W; A.V1 = V1; A.V2 = V2; A.b = b;
     A.lt_1 = lt1; A.lt_2 = lt2; A.wa_1 = wa1; A.wa_2 = wa2; A.W_j = Wj; A.b_j = bj;

@@ -22,3 +22,7 @@ for i in range(3):
     (g.sum() + net.get_atom_array().sum()).backward()
 torch.cuda.synchronize()
 print("ok")
+with torch.no_grad():
+    for i in range(2):
+        net(X, A)      # stash-free inference launch (ggnn_tc_kernel<128, false>)
+torch.cuda.synchronize()
