@@ -167,17 +167,13 @@ __device__ void co_forward(const CoArgs &A, const CoSmem &S, int pair) {
             S.L1t[i * PLD + j] = live ? expf(c - m1[i]) / s1[i] : 0.f;
         }
         CTS(4);
-        // lt_k[d][n] = sum_h lt_k[d][h] a_k[n][h]: two skinny (head x H) x (H x 64) register-tile contractions
-        __syncthreads();
-        for (int which = 0; which < 2; ++which) {
-            float acc[4][4];
-            zero_acc(acc);
-            gemm64_g<false>(acc, which ? A.lt_2 : A.lt_1, H, 0, hd, H, which ? S.a2s : S.a1s, S.stage);
-            float *dst = which ? S.lt2 : S.lt1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (ty * 4 + q < hd)
-                    *reinterpret_cast<float4 *>(dst + (ty * 4 + q) * AT + tx * 4) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        // lt_k[d][n] = sum_h lt_k[d][h] a_k[n][h]
+        for (int idx = tid; idx < 2 * hd * AT; idx += NTHREADS) {
+            const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
+            const float *src = which ? S.a2s : S.a1s, *w = (which ? A.lt_2 : A.lt_1) + (long)d * H;
+            float s = 0.f;
+            for (int h = 0; h < H; ++h) s += w[h] * src[h * AT + n];
+            (which ? S.lt2 : S.lt1)[d * AT + n] = s;
         }
         __syncthreads();
         CTS(5);

@@ -12,19 +12,20 @@
 //   MMA-3  [r|z|hbar]     = [h | m] [W_r+U_r | W_z+U_z | W]^T    K = 2H, N = 3H (U folded: state == h)
 //   MMA-4  hbar          += (r*h) U^T                            K = H
 //   epilogue: sigmoid/tanh, h <- z*hbar + (1-z)*h  (fp32), new bf16 operand copy
-// Warp roles: warps 0-7 epilogue (TMEM lane quarter = warp%4, column half = warp/4),
-// warp 8 TMA producer, warp 9 MMA issuer (one elected lane each).
+// Warp roles: H/8 epilogue warps (TMEM lane quarter = warp%4, 32-column group = warp/4),
+// then one TMA producer warp and one MMA issuer warp (one elected lane each).
 // Replaces models/update/ggnn_update.py:31-63 / models/models/ggnn.py:72-106 like ggnn.cu.
 #include "tc_common.cuh"
 
 namespace bmp {
 namespace tc {
 
-template <int H>
+// LEAN = no fp32 per-step stash (inference, or the bf16 panel stash): no transposition staging, deeper weight ring
+template <int H, bool LEAN>
 struct Cfg {
     static constexpr int KP = H / 64;
     static constexpr int TILE_BYTES = H * 128;            // weight tile: H rows (n) x 64 bf16 (k)
-    static constexpr int STAGES = (H == 128) ? 2 : 4;
+    static constexpr int STAGES = (H == 128 && !LEAN) ? 2 : 4;
     static constexpr int T_MSG = 4 * KP, T_GATE = 2 * KP, T_U = KP;
     static constexpr int TILES_STATEFUL = T_MSG + 3 * T_GATE + T_U;
     static constexpr int TILES_STATELESS = T_MSG + 2 * T_GATE;
@@ -33,8 +34,8 @@ struct Cfg {
     static constexpr int OFF_ADJ = OFF_H + KP * PANEL_BYTES;
     static constexpr int OFF_AH = OFF_ADJ + 8 * ADJ_TILE_BYTES;
     static constexpr int OFF_W = OFF_AH + 2 * KP * PANEL_BYTES;
-    static constexpr int OFF_STG = OFF_W + STAGES * TILE_BYTES;   // 8 warps x 4 KB transposition staging
-    static constexpr int OFF_BAR = OFF_STG + 8 * 4096;
+    static constexpr int OFF_STG = OFF_W + STAGES * TILE_BYTES;   // H/8 warps x 2 KB transposition staging
+    static constexpr int OFF_BAR = OFF_STG + (LEAN ? 0 : (H / 8) * 2048);
     static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
 };
 
@@ -52,11 +53,14 @@ struct Args {
     int use2;
 };
 
-template <int H, bool V2>
-__global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
-    using C = Cfg<H>;
+template <int H, bool V2, bool LEAN>
+__global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args a) {
+    static_assert(LEAN || !V2, "the panel stash implies LEAN");
+    using C = Cfg<H, LEAN>;
     constexpr int KP = C::KP;
-    constexpr int NC = H / 2;   // columns per epilogue thread
+    constexpr int EPW = H / 8;          // epilogue warps: 4 TMEM lane quarters x (H / 32) column groups
+    constexpr int NE = 32 * EPW;
+    constexpr int NC = 32;              // columns per epilogue thread
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = s32(smem);
@@ -74,19 +78,19 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
-        mbar_init(BAR(B_HREADY), NEPI);
+        mbar_init(BAR(B_HREADY), NE);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_D1 + i), 1);
-        mbar_init(BAR(B_AHREADY), 2 * NEPI);
-        mbar_init(BAR(B_AHREADY + 1), 2 * NEPI);
+        mbar_init(BAR(B_AHREADY), 2 * NE);
+        mbar_init(BAR(B_AHREADY + 1), 2 * NE);
         mbar_init(BAR(B_AHFREE), 1);
         mbar_init(BAR(B_M), 1);
-        mbar_init(BAR(B_XREADY), NEPI);
+        mbar_init(BAR(B_XREADY), NE);
         mbar_init(BAR(B_R), 1);
-        mbar_init(BAR(B_RSREADY), NEPI);
+        mbar_init(BAR(B_RSREADY), NE);
         mbar_init(BAR(B_ZH), 1);
         fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == EPW + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(C::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == EPW) {
         // ===================== TMA producer: stream the weight tiles in consumption order
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     }
                 }
         }
-    } else if (warp == 9) {
+    } else if (warp == EPW + 1) {
         // ===================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t ID_KK = idesc(H, 0), ID_KMN = idesc(H, 1);
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
         const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
         const int molslot = row >> 6, atom = row & 63;
         float hreg[NC];
-        float *stg = reinterpret_cast<float *>(smem + C::OFF_STG + warp * 4096);
+        float *stg = reinterpret_cast<float *>(smem + C::OFF_STG + warp * 2048);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int molg = tile * 2 + molslot;
@@ -205,10 +209,12 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
             };
             // store 32 columns [col0, col0+32) of every live row of this warp to base[(grow*ld) + col0 ..]
             auto store_rows = [&](float *base, long ld, int col0, const float *vals) {
-                warp_store_rows<32>(stg, vals, lane, [&](int r) -> float * {
-                    const long g = wrow(r);
-                    return g >= 0 ? base + g * ld + col0 : nullptr;
-                });
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)      // two 16-column passes: 2 KB of staging per warp
+                    warp_store_rows<16>(stg, vals + 16 * h2, lane, [&](int r) -> float * {
+                        const long g = wrow(r);
+                        return g >= 0 ? base + g * ld + col0 + 16 * h2 : nullptr;
+                    });
             };
             // bf16 gate values in the thread-native order [16-byte chunk j][thread]: coalesced 512 B per warp store
             auto store_native16 = [&](int t, int arr, int cc, const float *vals) {
@@ -217,8 +223,12 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 for (int g = 0; g < 2; ++g) {
                     uint4 pk = make_uint4(pack_bf16(vals[8 * g], vals[8 * g + 1]), pack_bf16(vals[8 * g + 2], vals[8 * g + 3]),
                                           pack_bf16(vals[8 * g + 4], vals[8 * g + 5]), pack_bf16(vals[8 * g + 6], vals[8 * g + 7]));
-                    *reinterpret_cast<uint4 *>(base + ((size_t)((cc >> 3) + g) * NEPI + tid) * 16) = pk;
+                    *reinterpret_cast<uint4 *>(base + ((size_t)((cc >> 3) + g) * NE + tid) * 16) = pk;
                 }
+            };
+            auto store_direct = [&](float *dst, const float *vals) {
+#pragma unroll
+                for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4 *>(dst + x) = make_float4(vals[x], vals[x + 1], vals[x + 2], vals[x + 3]);
             };
             auto store_rows16 = [&](float *base, long ld, int col0, const float *vals) {
                 warp_store_rows<16>(stg, vals, lane, [&](int r) -> float * {
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 });
             };
             // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
-            stage_adjacency(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
             // ---- h_0: embedding gather (or h_in) -> fp32 registers + bf16 operand panels ----
             {
                 const float *src = nullptr;
@@ -247,8 +257,12 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                 }
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 32) {
-                    if (a.h0_out) store_rows(a.h0_out, H, colbase + cc, &hreg[cc]);
-                    if (a.Hs) store_rows(a.Hs, H, colbase + cc, &hreg[cc]);
+                    if (LEAN) {     // once per tile: plain lane-per-row vector stores
+                        if (a.h0_out && live) store_direct(a.h0_out + grow * H + colbase + cc, &hreg[cc]);
+                    } else {
+                        if (a.h0_out) store_rows(a.h0_out, H, colbase + cc, &hreg[cc]);
+                        if (a.Hs) store_rows(a.Hs, H, colbase + cc, &hreg[cc]);
+                    }
                 }
             }
             auto store_h_operand = [&](int t_next) {
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
             };
             store_h_operand(0);
             // degrees deg_e[atom] = sum_j A_e[atom][j]  (from the staged bf16 tile; needs the staging complete)
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI));
+            asm volatile("bar.sync 1, %0;" ::"n"(NE));
             float deg[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                             float4 b4 = __ldg(reinterpret_cast<const float4 *>(mb_) + colbase + cc + x);
                             m[x] = __uint_as_float(v[x]) + deg[0] * b4.x + deg[1] * b4.y + deg[2] * b4.z + deg[3] * b4.w;
                         }
-                        if (a.Ms) store_rows(a.Ms + (long)t * rows_total * H, H, colbase + cc, m);
+                        if (!LEAN && a.Ms) store_rows(a.Ms + (long)t * rows_total * H, H, colbase + cc, m);
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const int kk = colbase + cc + 8 * g;
@@ -366,7 +380,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                             rs[x] = r[x] * hreg[cc + x];
                         }
                         if (V2) store_native16(t, 2, cc, r);
-                        if (a.Gs) {
+                        if (!LEAN && a.Gs) {
                             store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, colbase + cc, r);
                             store_rows16(a.RSs + (long)t * rows_total * H, H, colbase + cc, rs);
                         }
@@ -378,7 +392,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                             *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
                         }
                     }
-                } else if (a.Gs) {   // r / r*h slots of a stateless step: zeros (merged wgrad contractions stay exact)
+                } else if (!LEAN && a.Gs) {   // r / r*h slots of a stateless step: zeros (merged wgrad contractions stay exact)
                     float zero[32];
 #pragma unroll
                     for (int x = 0; x < 32; ++x) zero[x] = 0.f;
@@ -413,15 +427,19 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                         store_native16(t, 0, cc, z);
                         store_native16(t, 1, cc, hb);
                     }
-                    if (a.Gs) {
+                    if (!LEAN && a.Gs) {
                         store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, H + colbase + cc, z);
                         store_rows16(a.Gs + (long)t * rows_total * 3 * H, 3 * H, 2 * H + colbase + cc, hb);
                     }
                 }
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 32) {
-                    if (a.Hs) store_rows(a.Hs + (long)(t + 1) * rows_total * H, H, colbase + cc, &hreg[cc]);
-                    if (t == a.T - 1 && a.h_out) store_rows(a.h_out, H, colbase + cc, &hreg[cc]);
+                    if (LEAN) {
+                        if (t == a.T - 1 && a.h_out && live) store_direct(a.h_out + grow * H + colbase + cc, &hreg[cc]);
+                    } else {
+                        if (a.Hs) store_rows(a.Hs + (long)(t + 1) * rows_total * H, H, colbase + cc, &hreg[cc]);
+                        if (t == a.T - 1 && a.h_out) store_rows(a.h_out, H, colbase + cc, &hreg[cc]);
+                    }
                 }
                 TSF(7);
                 if (t + 1 < a.T) {
@@ -431,7 +449,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
                     mbar_arrive(BAR(B_HREADY));
                 } else {
                     tc_fence_before();
-                    asm volatile("bar.sync 1, %0;" ::"n"(NEPI));   // everyone done with this tile's smem/TMEM
+                    asm volatile("bar.sync 1, %0;" ::"n"(NE));   // everyone done with this tile's smem/TMEM
                 }
             }
         }
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_kernel(const Args a) {
     // teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == EPW + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
     }
@@ -568,13 +586,15 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (a->mb + 1) / 2;
     const int grid = n_tiles < sms ? n_tiles : sms;
-#define LAUNCH_FWD(HH, VV)                                                                                              \
+    const bool lean = !a->Hs && !a->Ms && !a->Gs && !a->RSs;
+    if (k.use2 && !lean) { set_error("BMP_MODE_BF16: the panel stash excludes the fp32 per-step stash"); return BMP_EINVAL; }
+#define LAUNCH_FWD(HH, VV, LL)                                                                                           \
     do {                                                                                                                 \
-        cudaFuncSetAttribute(tc::ggnn_tc_kernel<HH, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<HH>::SMEM_BYTES); \
-        tc::ggnn_tc_kernel<HH, VV><<<grid, tc::NTHR, tc::Cfg<HH>::SMEM_BYTES, st>>>(k);                                   \
+        cudaFuncSetAttribute(tc::ggnn_tc_kernel<HH, VV, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<HH, LL>::SMEM_BYTES); \
+        tc::ggnn_tc_kernel<HH, VV, LL><<<grid, 32 * (HH / 8 + 2), tc::Cfg<HH, LL>::SMEM_BYTES, st>>>(k);                      \
     } while (0)
-    if (H == 64) { if (k.use2) LAUNCH_FWD(64, true); else LAUNCH_FWD(64, false); }
-    else { if (k.use2) LAUNCH_FWD(128, true); else LAUNCH_FWD(128, false); }
+    if (H == 64) { if (k.use2) LAUNCH_FWD(64, true, true); else if (lean) LAUNCH_FWD(64, false, true); else LAUNCH_FWD(64, false, false); }
+    else { if (k.use2) LAUNCH_FWD(128, true, true); else if (lean) LAUNCH_FWD(128, false, true); else LAUNCH_FWD(128, false, false); }
 #undef LAUNCH_FWD
     count_launch();
     return check_launch("ggnn_tc_kernel");

@@ -20,7 +20,7 @@ template <int H>
 struct Cfg {
     static constexpr int KP = H / 64;
     static constexpr int TILE_BYTES = H * 128;
-    static constexpr int STAGES = (H == 128) ? 3 : 4;
+    static constexpr int STAGES = 4;
     static constexpr int TILES_STATEFUL = 11 * KP;     // q: KP, dx: 6KP, dh: 4KP
     static constexpr int TILES_STATELESS = 8 * KP;     // dx (z, hbar): 4KP, dh: 4KP
     static constexpr int TMEM_COLS = 4 * H;
@@ -56,10 +56,12 @@ __global__ void nonzero_flags_kernel(const float *__restrict__ x, long n_per_t, 
 }
 
 template <int H, bool V2>
-__global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
+__global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const Args a) {
     using C = Cfg<H>;
     constexpr int KP = C::KP;
-    constexpr int NC = H / 2;
+    constexpr int EPW = H / 8;          // epilogue warps: 4 TMEM lane quarters x (H / 32) column groups
+    constexpr int NE = 32 * EPW;
+    constexpr int NC = 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = s32(smem);
@@ -75,19 +77,19 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
-        mbar_init(BAR(B_DRDY), NEPI);
+        mbar_init(BAR(B_DRDY), NE);
         mbar_init(BAR(B_Q), 1);
-        mbar_init(BAR(B_DRRDY), NEPI);
+        mbar_init(BAR(B_DRRDY), NE);
         mbar_init(BAR(B_DX), 1);
-        mbar_init(BAR(B_DMRDY), NEPI);
+        mbar_init(BAR(B_DMRDY), NE);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_P + i), 1);
-        mbar_init(BAR(B_PRDY), 2 * NEPI);
-        mbar_init(BAR(B_PRDY + 1), 2 * NEPI);
+        mbar_init(BAR(B_PRDY), 2 * NE);
+        mbar_init(BAR(B_PRDY + 1), 2 * NE);
         mbar_init(BAR(B_PFREE), 1);
         mbar_init(BAR(B_DH), 1);
         fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == EPW + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(C::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
     // TMEM columns: [0,H) q, then P(0,0) and P(1,1) ; [H,2H) dh_x (+ dh_msg) ; [2H,3H) dm, then P(1,0) ; [3H,4H) P(0,1)
     constexpr uint32_t COL_Q = 0, COL_DHX = H, COL_DM = 2 * H;
 
-    if (warp == 8) {
+    if (warp == EPW) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                     }
                 }
         }
-    } else if (warp == 9) {
+    } else if (warp == EPW + 1) {
         if (lane == 0) {
             constexpr uint32_t ID_KK = idesc2(H, 0, 0), ID_MNMN = idesc2(H, 1, 1);
             uint32_t stage = 0, phase = 0, it = 0;
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
             const int molg = tile * 2 + molslot;
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;
-            stage_adjacency(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
             {
                 const float *src = live ? a.dHs + ((long)(V2 ? 1 : a.T) * rows_total + grow) * H + colbase : nullptr;
 #pragma unroll
@@ -231,9 +233,9 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                     const uint8_t *bz = a.st.zn(t, tile, 0, H), *bh = a.st.zn(t, tile, 1, H), *bs = a.st.zn(t, tile, 3, H);
 #pragma unroll
                     for (int j = 0; j < NC / 8; ++j) {
-                        zp[j] = __ldg(reinterpret_cast<const uint4 *>(bz + ((size_t)j * NEPI + tid) * 16));
-                        hp[j] = __ldg(reinterpret_cast<const uint4 *>(bh + ((size_t)j * NEPI + tid) * 16));
-                        sp[j] = stateful ? __ldg(reinterpret_cast<const uint4 *>(bs + ((size_t)j * NEPI + tid) * 16)) : make_uint4(0, 0, 0, 0);
+                        zp[j] = __ldg(reinterpret_cast<const uint4 *>(bz + ((size_t)j * NE + tid) * 16));
+                        hp[j] = __ldg(reinterpret_cast<const uint4 *>(bh + ((size_t)j * NE + tid) * 16));
+                        sp[j] = stateful ? __ldg(reinterpret_cast<const uint4 *>(bs + ((size_t)j * NE + tid) * 16)) : make_uint4(0, 0, 0, 0);
                     }
 #pragma unroll
                     for (int j = 0; j < NC / 8; ++j) {
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                     if (stateful) {   // requested before waiting for q: the latency overlaps MMA-q
                         const uint8_t *br = a.st.zn(t, tile, 2, H);
 #pragma unroll
-                        for (int j = 0; j < NC / 8; ++j) rp[j] = __ldg(reinterpret_cast<const uint4 *>(br + ((size_t)j * NEPI + tid) * 16));
+                        for (int j = 0; j < NC / 8; ++j) rp[j] = __ldg(reinterpret_cast<const uint4 *>(br + ((size_t)j * NE + tid) * 16));
                     }
                     mbar_wait(BAR(B_Q), par);
                     tc_fence_after();
@@ -493,13 +495,13 @@ __global__ void __launch_bounds__(NTHR, 1) ggnn_tc_bwd_kernel(const Args a) {
                 }
                 TS(12);
                 tc_fence_before();
-                if (t == 0) asm volatile("bar.sync 1, %0;" ::"n"(NEPI));   // tile finished: smem/TMEM may be re-staged
+                if (t == 0) asm volatile("bar.sync 1, %0;" ::"n"(NE));   // tile finished: smem/TMEM may be re-staged
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == EPW + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
     }
@@ -601,7 +603,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
 #define LAUNCH_BWD(HH, VV)                                                                                                   \
     do {                                                                                                                      \
         cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<HH, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<HH>::SMEM_BYTES); \
-        tcb::ggnn_tc_bwd_kernel<HH, VV><<<grid, tc::NTHR, tcb::Cfg<HH>::SMEM_BYTES, st>>>(k);                                  \
+        tcb::ggnn_tc_bwd_kernel<HH, VV><<<grid, 32 * (HH / 8 + 2), tcb::Cfg<HH>::SMEM_BYTES, st>>>(k);                                  \
     } while (0)
     if (H == 64) { if (k.use2) LAUNCH_BWD(64, true); else LAUNCH_BWD(64, false); }
     else { if (k.use2) LAUNCH_BWD(128, true); else LAUNCH_BWD(128, false); }

@@ -119,13 +119,14 @@ __host__ __device__ constexpr uint32_t idesc2(int n, int a_mn_major, int b_mn_ma
 
 // stage the fp32 adjacency of a tile (2 molecules x 4 bond types) as bf16 SW128 tiles [mol][e][i][j].
 // Loads are issued in batches of 8 float4 per thread so the DRAM latency is paid 4 times per tile, not 32.
+template <int NE>
 __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const float *__restrict__ adj, int tile, int mb, int N, int tid) {
     constexpr int BATCH = 8;
-    for (int base = 0; base < 8 * 64 * 16; base += NEPI * BATCH) {      // items: (mol,e) x i x (j/4)
+    for (int base = 0; base < 8 * 64 * 16; base += NE * BATCH) {      // items: (mol,e) x i x (j/4)
         float4 v[BATCH];
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
-            const int idx = base + u * NEPI + tid;
+            const int idx = base + u * NE + tid;
             const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
             const int mg = tile * 2 + (me >> 2);
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -143,7 +144,7 @@ __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const float *__r
         }
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) {
-            const int idx = base + u * NEPI + tid;
+            const int idx = base + u * NE + tid;
             const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
             uint2 pk = make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
             *reinterpret_cast<uint2 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, j4)) = pk;
@@ -251,7 +252,7 @@ struct Stash2 {
         Pp = p; p += per * 4 * KP * PANEL_BYTES;
         Zn = p;
     }
-    // native gate block of (t, tile, array a in 0..3 = z, hbar, r, state): NEPI threads x H/2 bf16
+    // native gate block of (t, tile, array a in 0..3 = z, hbar, r, state): 128 rows x H bf16 = [16-byte chunk][epilogue thread]
     __host__ __device__ uint8_t *zn(int t, long tile, int a, int H) const {
         return Zn + (((size_t)t * n_tiles + tile) * 4 + a) * ((size_t)NEPI * (H / 2) * 2);
     }
