@@ -78,15 +78,15 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
-        mbar_init(BAR(B_HREADY), NE);
+        mbar_init(BAR(B_HREADY), EPW);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_D1 + i), 1);
-        mbar_init(BAR(B_AHREADY), 2 * NE);
-        mbar_init(BAR(B_AHREADY + 1), 2 * NE);
+        mbar_init(BAR(B_AHREADY), 2 * EPW);
+        mbar_init(BAR(B_AHREADY + 1), 2 * EPW);
         mbar_init(BAR(B_AHFREE), 1);
         mbar_init(BAR(B_M), 1);
-        mbar_init(BAR(B_XREADY), NE);
+        mbar_init(BAR(B_XREADY), EPW);
         mbar_init(BAR(B_R), 1);
-        mbar_init(BAR(B_RSREADY), NE);
+        mbar_init(BAR(B_RSREADY), EPW);
         mbar_init(BAR(B_ZH), 1);
         fence_mbar_init();
     }
@@ -295,8 +295,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                 }
                 deg[e] = s;
             }
-            fence_proxy_async();
-            mbar_arrive(BAR(B_HREADY));
+            warp_arrive(BAR(B_HREADY), lane);
 
             for (int t = 0; t < a.T; ++t, ++it) {
                 const uint32_t par = it & 1;
@@ -327,9 +326,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                                 *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
                             }
                         }
-                        tc_fence_before();
-                        fence_proxy_async();
-                        mbar_arrive(BAR(B_AHREADY + p));
+                        warp_arrive(BAR(B_AHREADY + p), lane);
                     }
                 }
                 // ---- E2: message m (+ bias through the degrees) -> bf16 operand (AH panels [0,KP)) ----
@@ -359,9 +356,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                         }
                     }
                 }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(BAR(B_XREADY));
+                warp_arrive(BAR(B_XREADY), lane);
                 TSF(3);
                 // ---- E3: reset gate, r*h -> bf16 operand (AH panels [KP,2KP)) ----
                 mbar_wait(BAR(B_R), par);
@@ -375,9 +370,14 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                         tc_wait_ld();
                         float r[16], rs[16];
 #pragma unroll
-                        for (int x = 0; x < 16; ++x) {
-                            r[x] = sigmoid_fast(__uint_as_float(w[x]) + __ldg(b3 + colbase + cc + x));
-                            rs[x] = r[x] * hreg[cc + x];
+                        for (int x = 0; x < 16; x += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(b3 + colbase + cc + x));
+                            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) {
+                                r[x + y] = sigmoid_fast(__uint_as_float(w[x + y]) + bb[y]);
+                                rs[x + y] = r[x + y] * hreg[cc + x + y];
+                            }
                         }
                         if (V2) store_native16(t, 2, cc, r);
                         if (!LEAN && a.Gs) {
@@ -402,9 +402,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                         store_rows(a.RSs + (long)t * rows_total * H, H, colbase + cc, zero);
                     }
                 }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(BAR(B_RSREADY));
+                warp_arrive(BAR(B_RSREADY), lane);
                 TSF(5);
                 // ---- E4: update gate + candidate -> new state ----
                 mbar_wait(BAR(B_ZH), par);
@@ -418,10 +416,16 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                     tc_wait_ld();
                     float z[16], hb[16];
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) {
-                        z[x] = sigmoid_fast(__uint_as_float(wz[x]) + __ldg(b3 + H + colbase + cc + x));
-                        hb[x] = tanh_fast(__uint_as_float(wh[x]) + __ldg(b3 + 2 * H + colbase + cc + x));
-                        hreg[cc + x] = stateful ? fmaf(z[x], hb[x] - hreg[cc + x], hreg[cc + x]) : z[x] * hb[x];
+                    for (int x = 0; x < 16; x += 4) {
+                        const float4 bz4 = __ldg(reinterpret_cast<const float4 *>(b3 + H + colbase + cc + x));
+                        const float4 bh4 = __ldg(reinterpret_cast<const float4 *>(b3 + 2 * H + colbase + cc + x));
+                        const float bz[4] = {bz4.x, bz4.y, bz4.z, bz4.w}, bh[4] = {bh4.x, bh4.y, bh4.z, bh4.w};
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) {
+                            z[x + y] = sigmoid_fast(__uint_as_float(wz[x + y]) + bz[y]);
+                            hb[x + y] = tanh_fast(__uint_as_float(wh[x + y]) + bh[y]);
+                            hreg[cc + x + y] = stateful ? fmaf(z[x + y], hb[x + y] - hreg[cc + x + y], hreg[cc + x + y]) : z[x + y] * hb[x + y];
+                        }
                     }
                     if (V2) {
                         store_native16(t, 0, cc, z);
@@ -444,9 +448,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                 TSF(7);
                 if (t + 1 < a.T) {
                     store_h_operand(t + 1);
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(BAR(B_HREADY));
+                    warp_arrive(BAR(B_HREADY), lane);
                 } else {
                     tc_fence_before();
                     asm volatile("bar.sync 1, %0;" ::"n"(NE));   // everyone done with this tile's smem/TMEM

@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
 
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
-        mbar_init(BAR(B_DRDY), NE);
+        mbar_init(BAR(B_DRDY), EPW);
         mbar_init(BAR(B_Q), 1);
-        mbar_init(BAR(B_DRRDY), NE);
+        mbar_init(BAR(B_DRRDY), EPW);
         mbar_init(BAR(B_DX), 1);
-        mbar_init(BAR(B_DMRDY), NE);
+        mbar_init(BAR(B_DMRDY), EPW);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_P + i), 1);
-        mbar_init(BAR(B_PRDY), 2 * NE);
-        mbar_init(BAR(B_PRDY + 1), 2 * NE);
+        mbar_init(BAR(B_PRDY), 2 * EPW);
+        mbar_init(BAR(B_PRDY + 1), 2 * EPW);
         mbar_init(BAR(B_PFREE), 1);
         mbar_init(BAR(B_DH), 1);
         fence_mbar_init();
@@ -315,8 +315,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                     }
                 }
                 }
-                fence_proxy_async();
-                mbar_arrive(BAR(B_DRDY));
+                warp_arrive(BAR(B_DRDY), lane);
                 TS(1);
                 // ---- phase B: through U and the reset gate ----
                 if (V2) {
@@ -402,9 +401,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                     }
                 }
                 }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(BAR(B_DRRDY));
+                warp_arrive(BAR(B_DRRDY), lane);
                 TS(3);
                 // ---- phase C: dm -> bf16 operand panels (B of MMA-P) ----
                 mbar_wait(BAR(B_DX), par);
@@ -424,9 +421,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                         *reinterpret_cast<uint4 *>(smem + C::OFF_D + (2 * KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
                     }
                 }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(BAR(B_DMRDY));
+                warp_arrive(BAR(B_DMRDY), lane);
                 TS(5);
                 // ---- phase D: P accumulators -> bf16 A-operand panels (two K halves) + fp32 stash ----
                 for (int p = 0; p < 2; ++p) {
@@ -462,9 +457,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                                 *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
                             }
                         }
-                        tc_fence_before();
-                        fence_proxy_async();
-                        mbar_arrive(BAR(B_PRDY + p));
+                        warp_arrive(BAR(B_PRDY + p), lane);
                     }
                 }
                 TS(10);

@@ -97,6 +97,15 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(PANEL_BYTES >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Epilogue -> MMA hand-off, one mbarrier arrival per WARP: every thread orders its own shared-memory writes
+// (generic proxy) and TMEM reads before the warp converges, then lane 0 arrives for all 32.
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
 // instruction descriptor: D fp32, A/B bf16, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc(int n, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
