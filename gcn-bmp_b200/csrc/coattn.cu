@@ -541,6 +541,10 @@ static int co_check(int mb, int n1, int n2, int H, int O, int head, int variant)
 
 using namespace bmp;
 
+bool bmp_coattn_tc_supported(int H, int head, int variant, bool bwd);
+int bmp_coattn_forward_tc(const bmp_coattn_fwd_t *a, void *stream);
+int bmp_coattn_backward_tc(const bmp_coattn_bwd_t *a, void *stream);
+
 static long long *g_co_dbg = nullptr;
 extern "C" void bmp_debug_set_buffer_co(void *p) { g_co_dbg = (long long *)p; }
 
@@ -569,6 +573,7 @@ extern "C" int bmp_coattn_forward(const bmp_coattn_fwd_t *a, void *stream) {
     int rc = co_check(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant);
     if (rc) return rc;
     if (!aligned16({a->atoms_1, a->atoms_2, a->W})) { set_error("bmp_coattn_forward: atoms_1, atoms_2, W must be 16-byte aligned"); return BMP_EINVAL; }
+    if (a->mode == BMP_MODE_BF16 && bmp_coattn_tc_supported(a->hidden, a->head, a->variant, false)) return bmp_coattn_forward_tc(a, stream);
     CoArgs A = make_args(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant, a->act, a->atoms_1, a->atoms_2,
                          a->W, a->V1, a->V2, a->b, a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j);
     size_t smem = co_smem_floats(A.H, A.head) * sizeof(float);
@@ -594,18 +599,22 @@ extern "C" int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream) {
     if (rc) return rc;
     if (a->hidden > BMP_MAX_HIDDEN) { set_error("coattn backward: hidden > %d", BMP_MAX_HIDDEN); return BMP_ESHAPE; }
     if (!aligned16({a->atoms_1, a->atoms_2, a->W, a->R, a->d_atoms_1, a->d_atoms_2})) { set_error("bmp_coattn_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
-    CoArgs A = make_args(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant, a->act, a->atoms_1, a->atoms_2,
-                         a->W, a->V1, a->V2, a->b, a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j);
-    CoBwd B;
-    B.dc1 = a->d_compact_1; B.dc2 = a->d_compact_2; B.R = a->R; B.P1 = a->P1; B.P2 = a->P2;
-    B.DL1 = a->DL1; B.DL2 = a->DL2; B.d_a1 = a->d_atoms_1; B.d_a2 = a->d_atoms_2;
-    B.d_V1 = a->d_V1; B.d_V2 = a->d_V2; B.d_b = a->d_b; B.d_wa_1 = a->d_wa_1; B.d_wa_2 = a->d_wa_2;
-    size_t smem = co_smem_floats(A.H, A.head) * sizeof(float);
-    int grid = a->mb < 148 ? a->mb : 148;
-    cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    coattn_bwd_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(A, B);
-    count_launch();
-    if ((rc = check_launch("coattn_bwd_kernel"))) return rc;
+    if (a->mode == BMP_MODE_BF16 && bmp_coattn_tc_supported(a->hidden, a->head, a->variant, true)) {
+        if ((rc = bmp_coattn_backward_tc(a, stream))) return rc;
+    } else {
+        CoArgs A = make_args(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant, a->act, a->atoms_1, a->atoms_2,
+                             a->W, a->V1, a->V2, a->b, a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j);
+        CoBwd B;
+        B.dc1 = a->d_compact_1; B.dc2 = a->d_compact_2; B.R = a->R; B.P1 = a->P1; B.P2 = a->P2;
+        B.DL1 = a->DL1; B.DL2 = a->DL2; B.d_a1 = a->d_atoms_1; B.d_a2 = a->d_atoms_2;
+        B.d_V1 = a->d_V1; B.d_V2 = a->d_V2; B.d_b = a->d_b; B.d_wa_1 = a->d_wa_1; B.d_wa_2 = a->d_wa_2;
+        size_t smem = co_smem_floats(A.H, A.head) * sizeof(float);
+        int grid = a->mb < 148 ? a->mb : 148;
+        cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        coattn_bwd_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(A, B);
+        count_launch();
+        if ((rc = check_launch("coattn_bwd_kernel"))) return rc;
+    }
     const int H = a->hidden, O = a->out_dim, hd = a->head;
     const long rows1 = (long)a->mb * a->n1, rows2 = (long)a->mb * a->n2;
     // d W[h][k] += sum_{pairs,j} a1[j][h] R[j][k]

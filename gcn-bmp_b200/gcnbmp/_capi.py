@@ -73,14 +73,16 @@ _CO_PARAMS = ("W", "V1", "V2", "b", "lt_1", "lt_2", "wa_1", "wa_2", "W_j", "b_j"
 
 class CoattnFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "out_dim", "head", "variant", "act")] + [
-        (n, fp) for n in ("atoms_1", "atoms_2") + _CO_PARAMS + ("compact_1", "compact_2")]
+        (n, fp) for n in ("atoms_1", "atoms_2") + _CO_PARAMS + ("compact_1", "compact_2")] + [
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
 
 
 class CoattnBwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "out_dim", "head", "variant", "act")] + [
         (n, fp) for n in ("atoms_1", "atoms_2") + _CO_PARAMS + ("d_compact_1", "d_compact_2", "R", "P1", "P2",
                                                              "DL1", "DL2", "d_atoms_1", "d_atoms_2")
-        + tuple("d_" + p for p in _CO_PARAMS)] + [("mode", C.c_int)]
+        + tuple("d_" + p for p in _CO_PARAMS)] + [
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
 
 
 def _load():
@@ -116,6 +118,7 @@ def _load():
     lib.bmp_ggnn_tc_workspace_bytes.argtypes, lib.bmp_ggnn_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_ggnn_stash2_bytes.argtypes, lib.bmp_ggnn_stash2_bytes.restype = [i, i, i], C.c_size_t
     lib.bmp_readout_tc_workspace_bytes.argtypes, lib.bmp_readout_tc_workspace_bytes.restype = [i, i], C.c_size_t
+    lib.bmp_coattn_tc_workspace_bytes.argtypes, lib.bmp_coattn_tc_workspace_bytes.restype = [i], C.c_size_t
     lib.bmp_last_error.restype = C.c_char_p
     lib.bmp_version.restype = C.c_int
     lib.bmp_device_check.restype = C.c_int
@@ -127,7 +130,7 @@ def _load():
 lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
            "bmp_relgcn_backward", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
-           "bmp_coattn_backward", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
+           "bmp_coattn_backward", "bmp_coattn_tc_workspace_bytes", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]
 

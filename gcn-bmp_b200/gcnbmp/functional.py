@@ -287,6 +287,14 @@ class Readout(torch.autograd.Function):
         return dh, dh0, None, None, None, None, gWi, gbi, gWj, gbj, None
 
 
+def _coattn_workspace(mode, H, dev):
+    """Packed bf16 weight images of the tcgen05 co-attention (None when that path does not apply)."""
+    if mode != K.MODE_BF16:
+        return None
+    n = int(K.lib.bmp_coattn_tc_workspace_bytes(H))
+    return torch.empty((n,), device=dev, dtype=torch.uint8) if n else None
+
+
 class Coattention(torch.autograd.Function):
     """Fine-grained co-attention (Nie / VQA / Pooling)."""
 
@@ -307,6 +315,10 @@ class Coattention(torch.autograd.Function):
         for n, t in zip(K._CO_PARAMS, ps):
             setattr(a, n, _p(t))
         a.compact_1, a.compact_2 = _p(c1), _p(c2)
+        a.mode = mode
+        ws = _coattn_workspace(mode, H, atoms_1.device)
+        if ws is not None:
+            a.tc_workspace, a.tc_workspace_bytes = _p(ws), ws.numel()
         K.check(K.lib.bmp_coattn_forward(C.byref(a), _stream()))
         ctx.save_for_backward(atoms_1, atoms_2, *ps)
         ctx.meta = (variant, act, head, mode)
@@ -338,6 +350,9 @@ class Coattention(torch.autograd.Function):
         a.R, a.P1, a.P2, a.DL1, a.DL2 = _p(R), _p(P1), _p(P2), _p(DL1), _p(DL2)
         a.d_atoms_1, a.d_atoms_2 = _p(da1), _p(da2)
         a.mode = mode
+        ws = _coattn_workspace(mode, H, dev)
+        if ws is not None:
+            a.tc_workspace, a.tc_workspace_bytes = _p(ws), ws.numel()
         K.check(K.lib.bmp_coattn_backward(C.byref(a), _stream()))
         return (da1, da2, None, None) + tuple(grads) + (None,)
 

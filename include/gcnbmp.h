@@ -210,6 +210,9 @@ typedef struct {
     const float *atoms_1, *atoms_2;    /* (mb,N1,H), (mb,N2,H) */
     const float *W, *V1, *V2, *b, *lt_1, *lt_2, *wa_1, *wa_2, *W_j, *b_j;
     float *compact_1, *compact_2;      /* (mb,O) */
+    int    mode;                       /* BMP_MODE_BF16: contractions on tcgen05 (FINE variant, hidden 64/128, head <= 15) */
+    void  *tc_workspace;               /* BMP_MODE_BF16: >= bmp_coattn_tc_workspace_bytes(hidden) bytes, 16-byte aligned */
+    size_t tc_workspace_bytes;
 } bmp_coattn_fwd_t;
 
 int bmp_coattn_forward(const bmp_coattn_fwd_t *a, void *stream);
@@ -224,10 +227,14 @@ typedef struct {
     float *R, *P1, *P2, *DL1, *DL2;
     float *d_atoms_1, *d_atoms_2;
     float *d_W, *d_V1, *d_V2, *d_b, *d_lt_1, *d_lt_2, *d_wa_1, *d_wa_2, *d_W_j, *d_b_j;
-    int    mode;   /* BMP_MODE_BF16: the (H,H) / (O,H) weight-gradient contractions run on tcgen05 */
+    int    mode;   /* BMP_MODE_BF16: data contractions and the (H,H) / (O,H) weight gradients run on tcgen05 */
+    void  *tc_workspace;
+    size_t tc_workspace_bytes;
 } bmp_coattn_bwd_t;
 
 int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream);
+/* packed bf16 weight images of the tcgen05 co-attention kernels; 0 when hidden is not 64 or 128 */
+size_t bmp_coattn_tc_workspace_bytes(int hidden);
 
 /* ---- HolE circular correlation ----------------------------------------------
  * replaces models/link_prediction/hole.py:28-50 (= models/mlp.py:128-151):

@@ -137,3 +137,39 @@ def test_tc_readout_r1_variants(H, O, use_h0, act, agg, use_mask, nobias):
     g = link.grad_dict()
     for k in g:
         assert _rms_rel(g[k], tab[k].grad) <= gtol, k
+
+
+@pytest.mark.parametrize("variant,n1,n2,H,O,head,mb", [("nie", 64, 64, 128, 128, 8, 5), ("vqa", 13, 37, 64, 16, 4, 3),
+                                                       ("nie", 1, 5, 64, 8, 1, 2), ("vqa", 50, 64, 128, 32, 8, 300)])
+def test_tc_coattention_within_bf16_bound(variant, n1, n2, H, O, head, mb):
+    """tcgen05 co-attention (bf16 operands, fp32 accumulation / softmaxes) against the fp64 oracle."""
+    import gcnbmp
+    from oracle import minichainer as F
+    rng = np.random.default_rng(n1 + n2 + H)
+    params = R.init_params(R.coattn_shapes(H, O, head), rng, dtype=np.float64)
+    a1, a2 = rng.standard_normal((mb, n1, H)) * 0.5, rng.standard_normal((mb, n2, H)) * 0.5
+    tab = R.wrap_params(params)
+    v1, v2 = F.param(a1), F.param(a2)
+    if variant == "vqa":
+        oc, link = R.VQAParallelCoattention(R.P(tab), H, O, head), gcnbmp.VQAParallelCoattention(H, O, head)
+    else:
+        oc, link = R.NieFineCoattention(R.P(tab), H, O, head), gcnbmp.NieFineCoattention(H, O, head)
+    c1, c2 = oc(v1, None, v2, None)
+    w1, w2 = rng.standard_normal(c1.shape), rng.standard_normal(c2.shape)
+    F.add(F.sum_(F.mul(c1, F.const(w1))), F.sum_(F.mul(c2, F.const(w2)))).backward()
+    link.load_params(params)
+    link.mode = gcnbmp.MODE_BF16
+    dev = lambda x: torch.tensor(x, dtype=torch.float32, device="cuda")
+    with torch.no_grad():                       # forward-only kernel
+        q1, q2 = link(dev(a1), None, dev(a2), None)
+    assert rel_err(q1.cpu().numpy(), c1.data) <= MAX_TOL and rel_err(q2.cpu().numpy(), c2.data) <= MAX_TOL
+    t1, t2 = dev(a1).requires_grad_(), dev(a2).requires_grad_()
+    p1, p2 = link(t1, None, t2, None)
+    ((p1 * dev(w1)).sum() + (p2 * dev(w2)).sum()).backward()
+    assert rel_err(p1.detach().cpu().numpy(), c1.data) <= MAX_TOL
+    assert rel_err(p2.detach().cpu().numpy(), c2.data) <= MAX_TOL
+    assert rel_err(t1.grad.cpu().numpy(), v1.grad) <= MAX_TOL and _rms_rel(t1.grad.cpu().numpy(), v1.grad) <= 2 * RMS_TOL
+    assert rel_err(t2.grad.cpu().numpy(), v2.grad) <= MAX_TOL and _rms_rel(t2.grad.cpu().numpy(), v2.grad) <= 2 * RMS_TOL
+    g = link.grad_dict()
+    for k in g:
+        assert rel_err(g[k], tab[k].grad, floor=1e-3) <= MAX_TOL, k
