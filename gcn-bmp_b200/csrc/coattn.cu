@@ -440,15 +440,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) coattn_bwd_kernel(const CoArgs A,
                     acc[q][b] = v;
                 }
             }
-            // accumulate into global d_atoms_2
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const int i = tx * 4 + b;
                 if (i >= N2) continue;
-                float4 *dst = reinterpret_cast<float4 *>(B.d_a2 + (r2 + i) * H + k0);
-                float4 o = *dst;
-                o.x += acc[0][b]; o.y += acc[1][b]; o.z += acc[2][b]; o.w += acc[3][b];
-                *dst = o;
+                *reinterpret_cast<float4 *>(B.d_a2 + (r2 + i) * H + k0) = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
             }
         }
         __syncthreads();
@@ -503,10 +499,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) coattn_bwd_kernel(const CoArgs A,
             for (int b = 0; b < 4; ++b) {
                 const int j = tx * 4 + b;
                 if (j >= N1) continue;
-                float4 *dst = reinterpret_cast<float4 *>(B.d_a1 + (r1 + j) * H + h0);
-                float4 o = *dst;
-                o.x += acc[0][b]; o.y += acc[1][b]; o.z += acc[2][b]; o.w += acc[3][b];
-                *dst = o;
+                *reinterpret_cast<float4 *>(B.d_a1 + (r1 + j) * H + h0) = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
             }
         }
     }
@@ -599,7 +592,8 @@ extern "C" int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream) {
     if (rc) return rc;
     if (a->hidden > BMP_MAX_HIDDEN) { set_error("coattn backward: hidden > %d", BMP_MAX_HIDDEN); return BMP_ESHAPE; }
     if (!aligned16({a->atoms_1, a->atoms_2, a->W, a->R, a->d_atoms_1, a->d_atoms_2})) { set_error("bmp_coattn_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
-    if (a->mode == BMP_MODE_BF16 && bmp_coattn_tc_supported(a->hidden, a->head, a->variant, true)) {
+    const bool tc_data = a->mode == BMP_MODE_BF16 && bmp_coattn_tc_supported(a->hidden, a->head, a->variant, true);
+    if (tc_data) {     // also accumulates d W, d lt_k, d V_k, d wa_k, d b inside the kernel
         if ((rc = bmp_coattn_backward_tc(a, stream))) return rc;
     } else {
         CoArgs A = make_args(a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->variant, a->act, a->atoms_1, a->atoms_2,
@@ -623,7 +617,7 @@ extern "C" int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream) {
         if (tcw && (M_ & 3) == 0) return bmp_wgrad_tc(A_, lda, B_, H, C_, H, r_, M_, H, nullptr, 1, stream);
         return bmp_wgrad(A_, lda, B_, H, C_, H, r_, M_, H, stream);
     };
-    if (a->d_W && (rc = WG(a->atoms_1, H, a->R, a->d_W, rows1, H))) return rc;
+    if (!tc_data && a->d_W && (rc = WG(a->atoms_1, H, a->R, a->d_W, rows1, H))) return rc;
     if (a->d_W_j) {
         if ((rc = WG(a->d_compact_1, O, a->P1, a->d_W_j, a->mb, O))) return rc;
         if ((rc = WG(a->d_compact_2, O, a->P2, a->d_W_j, a->mb, O))) return rc;
@@ -632,7 +626,7 @@ extern "C" int bmp_coattn_backward(const bmp_coattn_bwd_t *a, void *stream) {
         if ((rc = bmp_colsum(a->d_compact_1, O, a->d_b_j, 1, a->mb, O, stream))) return rc;
         if ((rc = bmp_colsum(a->d_compact_2, O, a->d_b_j, 1, a->mb, O, stream))) return rc;
     }
-    if (fine) {
+    if (fine && !tc_data) {
         if (a->d_lt_1 && (rc = bmp_wgrad(a->DL1, hd, a->atoms_1, H, a->d_lt_1, H, rows1, hd, H, stream))) return rc;
         if (a->d_lt_2 && (rc = bmp_wgrad(a->DL2, hd, a->atoms_2, H, a->d_lt_2, H, rows2, hd, H, stream))) return rc;
     }

@@ -26,6 +26,7 @@ constexpr int MAXHD = 15;     // head projections share a 16-column group with t
 constexpr int STAGES = 2;
 
 #define EPI_SYNC() asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory")
+#define CTS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it == 1) a.dbg[i] = clock64(); } while (0)
 
 struct Args {
     int mb, n1, n2, O, head, act;
@@ -35,7 +36,8 @@ struct Args {
     // backward
     const float *dc1, *dc2;
     float *R, *P1, *P2, *DL1, *DL2, *d_a1, *d_a2;
-    float *d_V1, *d_V2, *d_b, *d_wa_1, *d_wa_2;
+    float *d_W, *d_lt_1, *d_lt_2, *d_V1, *d_V2, *d_b, *d_wa_1, *d_wa_2;
+    long long *dbg;              // optional phase timestamps of CTA 0, second pair (tools/co_timeline.py)
 };
 
 template <int H, bool BWD>
@@ -43,14 +45,16 @@ struct Cfg {
     static constexpr int KP = H / 64;
     static constexpr int W1_TILE = (H + 32) * 128;        // k-tile of img1: H + 32 rows (n) x 64 bf16 (k)
     static constexpr int WH_TILE = H * 128;
-    static constexpr int OFF_XP = 0;                                   // X panels; backward: R panels
+    static constexpr int OFF_XP = 0;                                   // X panels
     static constexpr int OFF_QP = OFF_XP + KP * PANEL_BYTES;           // Q blocks [KP][64 i][64 h]; backward: R extension panel
     static constexpr int OFF_W = OFF_QP + PANEL_BYTES;
-    static constexpr int OFF_SP = OFF_W + STAGES * W1_TILE;            // S panels (+ static rows 64..79: lt_2, V2)
-    static constexpr int OFF_DP = OFF_SP + (BWD ? KP * PANEL_BYTES : 0);   // [dC^T ; dC] panel + extension panel
+    static constexpr int OFF_SP = OFF_W + STAGES * W1_TILE;            // S panels (+ static rows 64..79: lt_2, V2), then R panels (rows 0-63)
+    static constexpr int OFF_DP = OFF_SP + (BWD ? KP * PANEL_BYTES : 0);   // [dC^T ; dC] panel + extension panel; then store staging
     static constexpr int OFF_F = OFF_DP + (BWD ? 2 * PANEL_BYTES : 0);     // fp32 area (carved at run time: depends on head)
     static constexpr int TMEM_COLS = BWD ? 512 : 256;
-    static constexpr uint32_t COL_D1 = 0, COL_D2 = 192, COL_R = 0, COL_A1 = H, COL_S = 256, COL_A2 = 256 + H;
+    // TMEM columns.  Per pair: D1 [0, H+32) -> R [0, H) -> d a1 [0, H) ; C^T [192, 256) ; S [256, 256+H) -> d a2 [256, 256+H).
+    // Persistent over the CTA's pairs: [d lt_1 | d V1] [160, 176), [d lt_2 | d V2] [176, 192), d W [384, 384+H).
+    static constexpr uint32_t COL_D1 = 0, COL_D2 = 192, COL_R = 0, COL_A1 = 0, COL_S = 256, COL_A2 = 256, COL_X1 = 160, COL_X2 = 176, COL_DW = 384;
 };
 
 __host__ __device__ inline int f32_floats(int H, int hd, bool bwd) {
@@ -58,7 +62,7 @@ __host__ __device__ inline int f32_floats(int H, int hd, bool bwd) {
     n += 4 * hd * AT;                               // lt1, lt2, H1, H2
     n += 4 * AT + 2 * H;                            // attn1, attn2, v1, v2, p1, p2
     n += 4 * AT + 16 * AT;                          // m2/is2/m1/is1 (later t1,t2,cs,rsum), partial stats
-    if (bwd) n += 2 * H + 2 * hd * AT + 2 * H + 2 * 16 + 4;   // dp1, dp2, dpre1, dpre2, gV1, gV2, gwa1, gwa2, gb
+    if (bwd) n += 2 * H + 2 * hd * AT + 2 * 16 + 4;   // dp1, dp2, dpre1, dpre2, gwa1, gwa2, gb
     return (n + 3) & ~3;
 }
 template <int H, bool BWD>
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
     float *st4 = fp; fp += 4 * AT;          // forward: m2 | 1/s2 | m1 | 1/s1 ; backward: t1 | t2 | cs | rsum
     float *part = fp; fp += 16 * AT;        // partial column statistics [2][8][64]
     float *dp1 = fp, *dp2 = fp + H, *dpre1 = fp + 2 * H, *dpre2 = dpre1 + hd * AT;
-    float *gV1 = dpre2 + hd * AT, *gV2 = gV1 + H, *gwa1 = gV2 + H, *gwa2 = gwa1 + 16, *gb = gwa2 + 16;
+    float *gwa1 = dpre2 + hd * AT, *gwa2 = gwa1 + 16, *gb = gwa2 + 16;
     const int f32n = f32_floats(H, hd, BWD);
     const uint32_t s_bar = sbase + C::OFF_F + f32n * 4;
     auto BAR = [&](int i) { return s_bar + 8u * i; };
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
     } else if (warp == EPW + 1) {
         // ===================== MMA issuer
         if (lane == 0) {
-            constexpr uint32_t ID_G1 = idesc2(H + 32, 0, 0), ID_H = idesc2(H, 0, 0), ID_64 = idesc2(64, 0, 0), ID_HMN = idesc2(H, 0, 1);
+            constexpr uint32_t ID_G1 = idesc2(H + 32, 0, 0), ID_H = idesc2(H, 0, 0), ID_64 = idesc2(64, 0, 0), ID_HMN = idesc2(H, 0, 1),
+                               ID_WMN = idesc2(H, 1, 1), ID_X = idesc2(16, 1, 1);
             uint32_t stage = 0, phase = 0, it = 0;
             // one weight tile against the K-major A panel at a_addr: ksteps k-steps of 16
             auto mma_wtile = [&](uint32_t a_addr, uint32_t dcol, uint32_t id, bool first, int ksteps) {
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                                (kp == 0 && k == 0) ? 0u : 1u);
                 tc_commit(BAR(B_G2));
                 if (BWD) {
+                    const uint32_t acc = it ? 1u : 0u;            // persistent parameter-gradient accumulators
                     mbar_wait(BAR(B_DRDY), par);
                     tc_fence_after();
 #pragma unroll
@@ -205,11 +211,20 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                     for (int k = 0; k < 5; ++k)       // d a2 = [dC | ext] [S ; ext rows]
                         tc_mma(tmem + C::COL_A2, desc_kmajor(k < 4 ? s_dp + k * 32 : s_dp + PANEL_BYTES), desc_mnmajor(s_sp + k * 16 * 128), ID_HMN,
                                k ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)       // [d lt_2 | d V2]^T += a2^T [dlt_2 | rsum]   (both operands MN-major)
+                        tc_mma(tmem + C::COL_X2, desc_mnmajor(s_xp + 64 * 128 + k * 16 * 128), desc_mnmajor(s_dp + PANEL_BYTES + 64 * 128 + k * 16 * 128),
+                               ID_X, (acc || k) ? 1u : 0u);
                     tc_commit(BAR(B_A2));
                     mbar_wait(BAR(B_RRDY), par);
                     tc_fence_after();
-                    for (int kp = 0; kp < KP; ++kp) mma_wtile(s_xp + kp * PANEL_BYTES, C::COL_A1, ID_H, kp == 0, 4);
+                    for (int kp = 0; kp < KP; ++kp) mma_wtile(s_sp + kp * PANEL_BYTES, C::COL_A1, ID_H, kp == 0, 4);
                     mma_wtile(s_qp, C::COL_A1, ID_H, false, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {     // d W += a1^T R ; [d lt_1 | d V1]^T += a1^T [dlt_1 | cs]
+                        tc_mma(tmem + C::COL_DW, desc_mnmajor(s_xp + k * 16 * 128), desc_mnmajor(s_sp + k * 16 * 128), ID_WMN, (acc || k) ? 1u : 0u);
+                        tc_mma(tmem + C::COL_X1, desc_mnmajor(s_xp + k * 16 * 128), desc_mnmajor(s_qp + k * 16 * 128), ID_X, (acc || k) ? 1u : 0u);
+                    }
                     tc_commit(BAR(B_A1));
                 }
             }
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
         const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
         uint32_t it = 0;
         if (BWD) {
-            for (int i = tid; i < 2 * H + 36; i += NE) gV1[i] = 0.f;
+            for (int i = tid; i < 36; i += NE) gwa1[i] = 0.f;
             // static part of the operands: rows 64..79 of the S panels = [lt_2 ; 0 ; V2], extension panel rows 0-63 = 0
             for (int idx = tid; idx < 16 * (H / 8); idx += NE) {
                 const int e = idx / (H / 8), c8 = idx % (H / 8);
@@ -240,23 +255,35 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             const uint32_t par = it & 1;
             const long r1 = (long)pair * N1, r2 = (long)pair * N2;
             EPI_SYNC();
+            CTS(0);
             // ---- X = [a1 ; a2] -> bf16 operand panels
-            for (int idx = tid; idx < 128 * (H / 8); idx += NE) {
-                const int r = idx / (H / 8), c8 = idx % (H / 8);
-                const int n = r & 63;
-                const bool live = r < 64 ? n < N1 : n < N2;
-                uint4 pk = make_uint4(0, 0, 0, 0);
-                if (live) {
-                    const float *src = (r < 64 ? a.atoms_1 + (r1 + n) * H : a.atoms_2 + (r2 + n) * H) + c8 * 8;
-                    const float4 x0 = __ldg(reinterpret_cast<const float4 *>(src)), x1 = __ldg(reinterpret_cast<const float4 *>(src) + 1);
-                    pk = make_uint4(pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w));
+            {
+                constexpr int PER = 128 * (H / 8) / NE;         // 16-byte operand chunks per thread
+                float4 x0[PER], x1[PER];
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int idx = tid + u * NE, r = idx / (H / 8), c8 = idx % (H / 8), n = r & 63;
+                    const bool live = r < 64 ? n < N1 : n < N2;
+                    x0[u] = x1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) {
+                        const float4 *src = reinterpret_cast<const float4 *>((r < 64 ? a.atoms_1 + (r1 + n) * H : a.atoms_2 + (r2 + n) * H) + c8 * 8);
+                        x0[u] = __ldg(src);
+                        x1[u] = __ldg(src + 1);
+                    }
                 }
-                *reinterpret_cast<uint4 *>(XP + (c8 >> 3) * PANEL_BYTES + sw128(r, (c8 & 7) * 8)) = pk;
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int idx = tid + u * NE, r = idx / (H / 8), c8 = idx % (H / 8);
+                    *reinterpret_cast<uint4 *>(XP + (c8 >> 3) * PANEL_BYTES + sw128(r, (c8 & 7) * 8)) =
+                        make_uint4(pack_bf16(x0[u].x, x0[u].y), pack_bf16(x0[u].z, x0[u].w), pack_bf16(x1[u].x, x1[u].y), pack_bf16(x1[u].z, x1[u].w));
+                }
             }
             warp_arrive(BAR(B_XRDY), lane);
+            CTS(1);
             // ---- G1 epilogue: Q (rows of a2) -> bf16 B-operand blocks; head projections and V terms -> fp32
             mbar_wait(BAR(B_G1), par);
             tc_fence_after();
+            CTS(2);
             if (q >= 2 && cg * 32 < H) {
                 uint32_t v[32];
                 tc_ld32(t_lane + C::COL_D1 + cg * 32, v);
@@ -301,10 +328,12 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 }
             }
             warp_arrive(BAR(B_QRDY), lane);
-            EPI_SYNC();                       // v1 / v2 / lt visible to every warp
+            EPI_SYNC();
+            CTS(3);                       // v1 / v2 / lt visible to every warp
             // ---- G2 epilogue: C^T[j][i] = act(a1_j . Q_i + v1[j] + v2[i] + b)
             mbar_wait(BAR(B_G2), par);
             tc_fence_after();
+            CTS(4);
             if (q < 2) {
                 uint32_t w[16];
                 tc_ld16(t_lane + C::COL_D2 + cg * 16, w);
@@ -323,6 +352,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             tc_fence_before();
             EPI_SYNC();
+            CTS(5);
             // ---- softmax statistics: over i for every j (rows of C^T, one warp each), over j for every i (8 partials)
             float *m2 = st4, *is2 = st4 + AT, *m1 = st4 + 2 * AT, *is1 = st4 + 3 * AT;
             {
@@ -369,6 +399,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 L1t[i * PLD + j] = live ? __expf(c - m1[i]) * is1[i] : 0.f;
             }
             EPI_SYNC();
+            CTS(6);
             // ---- H_1[j][d] = tanh(lt_1[j][d] + sum_i L_1[j][i] lt_2[i][d]) ; H_2 likewise
             for (int idx = tid; idx < 2 * hd * AT; idx += NE) {
                 const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
@@ -384,6 +415,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 }
             }
             EPI_SYNC();
+            CTS(7);
             if (tid < 2 * AT) {
                 const int n = tid & 63;
                 const float *Hk = tid < AT ? H1 : H2, *wa = tid < AT ? a.wa_1 : a.wa_2;
@@ -403,6 +435,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 x[lane + 32] = e1 / s;
             }
             EPI_SYNC();
+            CTS(8);
             // ---- pooled atoms p_k[h] = sum_n attn_k[n] a_k[n][h]
             if (tid < 2 * H) {
                 const int which = tid >= H, h = which ? tid - H : tid;
@@ -413,16 +446,29 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 (which ? p2 : p1)[h] = s;
             }
             EPI_SYNC();
+            CTS(9);
             if (!BWD) {
-                // compact_k[o] = W_j[o] . p_k + b_j[o]
-                for (int r = warp; r < 2 * O; r += EPW) {
-                    const int which = r >= O, o = which ? r - O : r;
-                    const float *p = which ? p2 : p1, *w = a.W_j + (long)o * H;
-                    float s = 0.f;
-                    for (int h = lane; h < H; h += 32) s += w[h] * p[h];
-                    s = warp_sum(s);
-                    if (lane == 0) (which ? a.c2 : a.c1)[(long)pair * O + o] = s + a.b_j[o];
+                // compact_k[o] = W_j[o] . p_k + b_j[o]: four lanes per output, interleaved 16-byte weight loads all in flight
+                for (int r = tid >> 2; r < 2 * O; r += NE / 4) {
+                    const int which = r >= O, o = which ? r - O : r, pt = tid & 3;
+                    const float *p = which ? p2 : p1;
+                    const float4 *w = reinterpret_cast<const float4 *>(a.W_j + (long)o * H);
+                    float4 ww[H / 16];
+#pragma unroll
+                    for (int u = 0; u < H / 16; ++u) ww[u] = __ldg(w + 4 * u + pt);
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int u = 0; u < H / 16; ++u) {
+                        const float4 pp = *reinterpret_cast<const float4 *>(p + 4 * (4 * u + pt));
+                        s0 = fmaf(ww[u].x, pp.x, fmaf(ww[u].y, pp.y, s0));
+                        s1 = fmaf(ww[u].z, pp.z, fmaf(ww[u].w, pp.w, s1));
+                    }
+                    float sum = s0 + s1;
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    if (pt == 0) (which ? a.c2 : a.c1)[(long)pair * O + o] = sum + a.b_j[o];
                 }
+                CTS(10);
                 continue;
             }
             // ======================================================== backward
@@ -432,11 +478,21 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 const int which = tid >= H, h = which ? tid - H : tid;
                 (which ? a.P2 : a.P1)[(long)pair * H + h] = (which ? p2 : p1)[h];
                 const float *dc = (which ? a.dc2 : a.dc1) + (long)pair * O;
-                float s = 0.f;
-                for (int o = 0; o < O; ++o) s += __ldg(a.W_j + (long)o * H + h) * __ldg(dc + o);
-                (which ? dp2 : dp1)[h] = s;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int o = 0;
+                for (; o + 8 <= O; o += 8) {          // eight coalesced weight rows in flight
+                    float w[8];
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) w[x] = __ldg(a.W_j + (long)(o + x) * H + h);
+                    const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dc + o)), d1 = __ldg(reinterpret_cast<const float4 *>(dc + o) + 1);
+                    s0 = fmaf(w[0], d0.x, s0); s1 = fmaf(w[1], d0.y, s1); s2 = fmaf(w[2], d0.z, s2); s3 = fmaf(w[3], d0.w, s3);
+                    s0 = fmaf(w[4], d1.x, s0); s1 = fmaf(w[5], d1.y, s1); s2 = fmaf(w[6], d1.z, s2); s3 = fmaf(w[7], d1.w, s3);
+                }
+                for (; o < O; ++o) s0 = fmaf(__ldg(a.W_j + (long)o * H + h), __ldg(dc + o), s0);
+                (which ? dp2 : dp1)[h] = (s0 + s1) + (s2 + s3);
             }
             EPI_SYNC();
+            CTS(10);
             // d attn_k[n] = dp_k . a_k[n]: four threads per atom, 16-byte operand chunks
             {
                 const int which = tid >> 8, n = (tid >> 2) & 63, hp = tid & 3;
@@ -466,6 +522,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 da[lane + 32] = lane + 32 < n ? at[lane + 32] * (da[lane + 32] - dot) : 0.f;
             }
             EPI_SYNC();
+            CTS(11);
             // dpre_k[d][n] = ds_k[n] wa_k[d] (1 - H_k^2) ; d wa_k[d] += sum_n ds_k[n] H_k[n][d]
             for (int idx = tid; idx < 2 * hd * AT; idx += NE) {
                 const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
@@ -479,6 +536,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 if (lane == 0) (which ? gwa2 : gwa1)[d] += s;
             }
             EPI_SYNC();
+            CTS(12);
             // u1[i] = sum_j L_1[j][i] dL_1[j][i] ; u2[j] = sum_i L_2[i][j] dL_2[i][j]   (four threads per output)
             {
                 const int out = tid >> 2, pt = tid & 3;
@@ -502,23 +560,22 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 u += __shfl_xor_sync(0xffffffffu, u, 2);
                 if (pt == 0) part[out] = u;          // u1 at [0,64), u2 at [64,128)
             }
-            // total d lt_k (direct + through the other molecule's H) -> DL_k (global) and over H_k (smem)
+            // total d lt_k (direct + through the other molecule's H) -> over H_k (smem)
             for (int idx = tid; idx < 2 * hd * AT; idx += NE) {
                 const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
                 float s;
                 if (!which) {
                     s = dpre1[d * AT + n];
                     for (int i = 0; i < N2; ++i) s += L2p[n * PLD + i] * dpre2[d * AT + i];
-                    if (n < N1) a.DL1[(r1 + n) * hd + d] = s;
                     H1[d * AT + n] = s;
                 } else {
                     s = dpre2[d * AT + n];
                     for (int j = 0; j < N1; ++j) s += L1t[n * PLD + j] * dpre1[d * AT + j];
-                    if (n < N2) a.DL2[(r2 + n) * hd + d] = s;
                     H2[d * AT + n] = s;
                 }
             }
             EPI_SYNC();
+            CTS(13);
             // dC^T[j][i] (pre-activation) in place of C^T
             for (int idx = tid; idx < AT * AT; idx += NE) {
                 const int j = idx >> 6, i = idx & 63;
@@ -532,6 +589,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 Cs[j * CLD + i] = g * act_bwd(a.act, c, c);
             }
             EPI_SYNC();
+            CTS(14);
             // rsum[i] = sum_j dC[i][j] ; cs[j] = sum_i dC[i][j]
             if (tid < AT) {
                 float s = 0.f;
@@ -543,17 +601,10 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 if (lane == 0) cs[j] = s;
             }
             EPI_SYNC();
+            CTS(15);
             if (warp == EPW - 1) {
                 const float s = warp_sum(rsum[lane] + rsum[lane + 32]);
                 if (lane == 0) gb[0] += s;
-            }
-            // d V1[h] += sum_j a1[j][h] cs[j] ; d V2[k] += sum_i a2[i][k] rsum[i]
-            if (tid < 2 * H) {
-                const int which = tid >= H, h = which ? tid - H : tid;
-                const float *w = which ? rsum : cs;
-                float s = 0.f;
-                for (int r = 0; r < AT; ++r) s += w[r] * bf16_at(XP, 64 * which + r, h);
-                (which ? gV2 : gV1)[h] += s;
             }
             // operand panel [dC^T ; dC] (+ extension columns [dlt_2 | rsum] of the a2 rows)
             for (int idx = tid; idx < 2 * AT * 8; idx += NE) {
@@ -583,82 +634,102 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 *reinterpret_cast<uint4 *>(dst + sw128(r, 8)) = pack8(v + 8);
             }
             warp_arrive(BAR(B_DRDY), lane);
-            // ---- R = dC^T a2 -> global (fp32, operand of the d W contraction) and bf16 A-operand panels (over X)
+            CTS(16);
+            // ---- both contractions of the dC panel are done: S is dead, the R panels take its place
             mbar_wait(BAR(B_R), par);
+            mbar_wait(BAR(B_A2), par);
             tc_fence_after();
-            if (q < 2 && cg * 32 < H) {
+            CTS(17);
+            float *stg = reinterpret_cast<float *>(DP + warp * 2048);      // the dC panels are dead too: store staging
+            if (cg * 32 < H) {
                 uint32_t v[32];
-                tc_ld32(t_lane + C::COL_R + cg * 32, v);
-                tc_wait_ld();
-                if (row < N1) {
-                    float *dst = a.R + (r1 + row) * H + cg * 32;
+                if (q < 2) {
+                    // R = dC^T a2 -> bf16 panels: A operand of d a1 = R W^T, B operand of d W += a1^T R
+                    tc_ld32(t_lane + C::COL_R + cg * 32, v);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int x = 0; x < 32; x += 4)
-                        *reinterpret_cast<float4 *>(dst + x) = make_float4(__uint_as_float(v[x]), __uint_as_float(v[x + 1]), __uint_as_float(v[x + 2]), __uint_as_float(v[x + 3]));
-                }
+                    for (int g = 0; g < 4; ++g) {
+                        const int kk = cg * 32 + 8 * g;
+                        float f[8];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int kk = cg * 32 + 8 * g;
-                    float f[8];
+                        for (int x = 0; x < 8; ++x) f[x] = __uint_as_float(v[8 * g + x]);
+                        *reinterpret_cast<uint4 *>(SP + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pack8(f);
+                    }
+                } else {
+                    // d a2 = dC S + dlt_2 lt_2 + rsum V2^T (all in the accumulator) + attn_2[i] dp2[k]
+                    tc_ld32(t_lane + C::COL_A2 + cg * 32, v);
+                    tc_wait_ld();
+                    const float at = attn2[row - 64];
+                    float f[32];
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) f[x] = __uint_as_float(v[8 * g + x]);
-                    *reinterpret_cast<uint4 *>(XP + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pack8(f);
+                    for (int x = 0; x < 32; x += 4) {
+                        const float4 d4 = *reinterpret_cast<const float4 *>(dp2 + cg * 32 + x);
+                        f[x] = fmaf(at, d4.x, __uint_as_float(v[x])); f[x + 1] = fmaf(at, d4.y, __uint_as_float(v[x + 1]));
+                        f[x + 2] = fmaf(at, d4.z, __uint_as_float(v[x + 2])); f[x + 3] = fmaf(at, d4.w, __uint_as_float(v[x + 3]));
+                    }
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2)
+                        warp_store_rows<16>(stg, f + 16 * h2, lane, [&](int r) -> float * {
+                            const int i = 32 * (q - 2) + r;
+                            return i < N2 ? a.d_a2 + (r2 + i) * H + cg * 32 + 16 * h2 : nullptr;
+                        });
                 }
             }
             warp_arrive(BAR(B_RRDY), lane);
-            // ---- d a2 += dC S + ... + attn_2[i] dp2[k]
-            mbar_wait(BAR(B_A2), par);
-            tc_fence_after();
-            if (q >= 2 && cg * 32 < H) {
-                uint32_t v[32];
-                tc_ld32(t_lane + C::COL_A2 + cg * 32, v);
-                tc_wait_ld();
-                const int i = row - 64;
-                if (i < N2) {
-                    const float at = attn2[i];
-                    float *dst = a.d_a2 + (r2 + i) * H + cg * 32;
-#pragma unroll
-                    for (int x = 0; x < 32; x += 4) {
-                        float4 o = *reinterpret_cast<float4 *>(dst + x);
-                        const float4 d4 = *reinterpret_cast<const float4 *>(dp2 + cg * 32 + x);
-                        o.x += __uint_as_float(v[x]) + at * d4.x;
-                        o.y += __uint_as_float(v[x + 1]) + at * d4.y;
-                        o.z += __uint_as_float(v[x + 2]) + at * d4.z;
-                        o.w += __uint_as_float(v[x + 3]) + at * d4.w;
-                        *reinterpret_cast<float4 *>(dst + x) = o;
-                    }
-                }
-            }
-            // ---- d a1 += R W^T + ... + attn_1[j] dp1[h]
+            CTS(18);
+            // ---- d a1 = R W^T + dlt_1 lt_1 + cs V1^T + attn_1[j] dp1[h]
             mbar_wait(BAR(B_A1), par);
             tc_fence_after();
+            CTS(19);
             if (q < 2 && cg * 32 < H) {
                 uint32_t v[32];
                 tc_ld32(t_lane + C::COL_A1 + cg * 32, v);
                 tc_wait_ld();
-                if (row < N1) {
-                    const float at = attn1[row];
-                    float *dst = a.d_a1 + (r1 + row) * H + cg * 32;
+                const float at = attn1[row];
+                float f[32];
 #pragma unroll
-                    for (int x = 0; x < 32; x += 4) {
-                        float4 o = *reinterpret_cast<float4 *>(dst + x);
-                        const float4 d4 = *reinterpret_cast<const float4 *>(dp1 + cg * 32 + x);
-                        o.x += __uint_as_float(v[x]) + at * d4.x;
-                        o.y += __uint_as_float(v[x + 1]) + at * d4.y;
-                        o.z += __uint_as_float(v[x + 2]) + at * d4.z;
-                        o.w += __uint_as_float(v[x + 3]) + at * d4.w;
-                        *reinterpret_cast<float4 *>(dst + x) = o;
-                    }
+                for (int x = 0; x < 32; x += 4) {
+                    const float4 d4 = *reinterpret_cast<const float4 *>(dp1 + cg * 32 + x);
+                    f[x] = fmaf(at, d4.x, __uint_as_float(v[x])); f[x + 1] = fmaf(at, d4.y, __uint_as_float(v[x + 1]));
+                    f[x + 2] = fmaf(at, d4.z, __uint_as_float(v[x + 2])); f[x + 3] = fmaf(at, d4.w, __uint_as_float(v[x + 3]));
                 }
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+                    warp_store_rows<16>(stg, f + 16 * h2, lane, [&](int r) -> float * {
+                        const int j = 32 * q + r;
+                        return j < N1 ? a.d_a1 + (r1 + j) * H + cg * 32 + 16 * h2 : nullptr;
+                    });
             }
+            CTS(20);
+            CTS(21);
             tc_fence_before();
         }
-        if (BWD) {
-            EPI_SYNC();
-            for (int h = tid; h < H; h += NE) {
-                if (a.d_V1) atomicAdd(a.d_V1 + h, gV1[h]);
-                if (a.d_V2) atomicAdd(a.d_V2 + h, gV2[h]);
+        if (BWD && it > 0) {
+            // every MMA of the last pair has completed (B_A1): flush the persistent parameter-gradient accumulators
+            tc_fence_after();
+            if (row < H && cg * 32 < H && a.d_W) {            // TMEM lane = row h of d W
+                uint32_t v[32];
+                tc_ld32(t_lane + C::COL_DW + cg * 32, v);
+                tc_wait_ld();
+                float *dst = a.d_W + (long)row * H + cg * 32;
+#pragma unroll
+                for (int x = 0; x < 32; x += 4)
+                    atomicAdd(reinterpret_cast<float4 *>(dst + x),
+                              make_float4(__uint_as_float(v[x]), __uint_as_float(v[x + 1]), __uint_as_float(v[x + 2]), __uint_as_float(v[x + 3])));
             }
+            if (row < H && cg >= 2) {                         // [d lt_k | d V_k]^T: lane = feature, column = head (15: V)
+                const int k2 = cg - 2;
+                uint32_t w[16];
+                tc_ld16(t_lane + (k2 ? C::COL_X2 : C::COL_X1), w);
+                tc_wait_ld();
+                float *dlt = k2 ? a.d_lt_2 : a.d_lt_1, *dV = k2 ? a.d_V2 : a.d_V1;
+#pragma unroll
+                for (int d = 0; d < MAXHD; ++d)
+                    if (d < hd && dlt) atomicAdd(dlt + (long)d * H + row, __uint_as_float(w[d]));
+                if (dV) atomicAdd(dV + row, __uint_as_float(w[15]));
+            }
+            tc_fence_before();
+            EPI_SYNC();
             if (tid < hd) {
                 if (a.d_wa_1) atomicAdd(a.d_wa_1 + tid, gwa1[tid]);
                 if (a.d_wa_2) atomicAdd(a.d_wa_2 + tid, gwa2[tid]);
@@ -726,6 +797,9 @@ static size_t img_bytes(int H) { return (size_t)(H / 64) * (H + 32) * 128 + (siz
 
 using namespace bmp;
 
+static long long *g_ctc_dbg = nullptr;
+extern "C" void bmp_debug_set_buffer_ctc(void *p) { g_ctc_dbg = (long long *)p; }
+
 extern "C" size_t bmp_coattn_tc_workspace_bytes(int hidden) {
     if (hidden != 64 && hidden != 128) return 0;
     return ctc::img_bytes(hidden) + 1024;
@@ -774,6 +848,7 @@ static int ctc_prepare(ctc::Args &k, int mb, int n1, int n2, int H, int O, int h
     k.mb = mb; k.n1 = n1; k.n2 = n2; k.O = O; k.head = head; k.act = act;
     k.atoms_1 = a1; k.atoms_2 = a2; k.b = b; k.wa_1 = wa1; k.wa_2 = wa2; k.W_j = Wj; k.b_j = bj; k.lt_2 = lt2; k.V2 = V2;
     k.img1 = p.img1; k.img2 = p.img2; k.img1x = p.img1x;
+    k.dbg = g_ctc_dbg;
     return BMP_OK;
 }
 
@@ -796,6 +871,7 @@ int bmp_coattn_backward_tc(const bmp_coattn_bwd_t *a, void *stream) {
     if (rc) return rc;
     k.dc1 = a->d_compact_1; k.dc2 = a->d_compact_2; k.R = a->R; k.P1 = a->P1; k.P2 = a->P2; k.DL1 = a->DL1; k.DL2 = a->DL2;
     k.d_a1 = a->d_atoms_1; k.d_a2 = a->d_atoms_2;
+    k.d_W = a->d_W; k.d_lt_1 = a->d_lt_1; k.d_lt_2 = a->d_lt_2;
     k.d_V1 = a->d_V1; k.d_V2 = a->d_V2; k.d_b = a->d_b; k.d_wa_1 = a->d_wa_1; k.d_wa_2 = a->d_wa_2;
     return a->hidden == 64 ? launch_ctc<64, true>(k, a->head, st) : launch_ctc<128, true>(k, a->head, st);
 }

@@ -335,7 +335,7 @@ class Coattention(torch.autograd.Function):
         dev = atoms_1.device
         dc1, dc2 = _f32(dc1), _f32(dc2)
         grads = [torch.zeros_like(t) if t is not None else None for t in ps]
-        da1, da2 = torch.zeros_like(atoms_1), torch.zeros_like(atoms_2)
+        da1, da2 = torch.empty_like(atoms_1), torch.empty_like(atoms_2)
         e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         R, P1, P2 = e(mb * n1, H), e(mb, H), e(mb, H)
         DL1 = e(mb * n1, head) if head else None

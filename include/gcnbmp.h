@@ -218,7 +218,9 @@ typedef struct {
 int bmp_coattn_forward(const bmp_coattn_fwd_t *a, void *stream);
 
 /* R (mb*N1, H), P1/P2 (mb, H) and DL1/DL2 (mb*N1 / mb*N2, head) are workspaces the
- * parameter-gradient GEMMs read.  d_atoms_k are ACCUMULATED (+=).               */
+ * parameter-gradient GEMMs read (the tcgen05 kernel leaves R and DL untouched: it contracts
+ * d W, d lt_k and d V_k on chip).  d_atoms_k are OVERWRITTEN (every live element is written);
+ * parameter gradients d_* are ACCUMULATED (+=).                                           */
 typedef struct {
     int mb, n1, n2, hidden, out_dim, head, variant, act;
     const float *atoms_1, *atoms_2;
