@@ -605,9 +605,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     return check_launch("ggnn_tc_bwd_kernel");
 }
 
-int bmp_wgrad_panels(const void *A, int a_ppt, const int a_panel[2], const void *B, int b_ppt, const int *b_panel, int nb,
-                     float *const C[2], int ldc, float *const bias[2], int bias_stride,
-                     int t0, int t1, int n_tiles, void *stream);   // wgrad_tc2.cu
+int bmp_wgrad_panels(bmp::w2::Args &k, void *stream);   // wgrad_tc2.cu
 
 // Backward over the bf16 panel stash (stash v2): data kernel, then every parameter gradient as a
 // C += A^T B contraction whose operands are streamed straight from the dumped panels.
@@ -618,15 +616,45 @@ int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
     tc::Stash2 S;
     const int n_tiles = (a->mb + 1) / 2;
     S.carve(a->stash2, n_tiles, H, T);
-    int bp[4] = {0, 1, 2, 3};
-    // one (A block pair) x (B panels) contraction; `col` selects which 64-row blocks of C this A pair covers
-    auto run = [&](const uint8_t *A, int a_ppt, int a_first, const uint8_t *B, int b_ppt, float *C, long c_row_stride, int ldc,
-                   float *bias, int bias_stride, int t0, int t1) -> int {
-        for (int mt = 0; mt < KP; mt += 2) {
-            int ap[2] = {a_first + mt, mt + 1 < KP ? a_first + mt + 1 : -1};
-            float *Cs[2] = {C ? C + (long)(mt * 64) * c_row_stride : nullptr, (C && mt + 1 < KP) ? C + (long)((mt + 1) * 64) * c_row_stride : nullptr};
-            float *bs[2] = {bias ? bias + (long)(mt * 64) * bias_stride : nullptr, (bias && mt + 1 < KP) ? bias + (long)((mt + 1) * 64) * bias_stride : nullptr};
-            int e = bmp_wgrad_panels(A, a_ppt, ap, B, b_ppt, bp, KP, Cs, ldc, bs, bias_stride, t0, t1, n_tiles, stream);
+    // Grouped contractions: every launch reads its A blocks and B blocks once (the kernel is HBM-bound), so the
+    // launches are arranged for the fewest operand reads:
+    //   per gate g and run of equal statefulness:  delta_g^T [h | m | r*h]  -> W_g (both halves) and U_g together
+    //   per pair of bond types:                    [P_e ; P_e']^T h         -> two row groups of W_msg
+    auto gate_launch = [&](int g, int ta, int tb, bool stateful, const bmp_gru_grad_t &D) -> int {
+        float *Wg = g == 0 ? D.W_r : (g == 1 ? D.W_z : D.W), *bW = g == 0 ? D.b_Wr : (g == 1 ? D.b_Wz : D.b_W);
+        float *Ug = !stateful ? nullptr : (g == 0 ? D.U_r : (g == 1 ? D.U_z : D.U));
+        float *bU = !stateful ? nullptr : (g == 0 ? D.b_Ur : (g == 1 ? D.b_Uz : D.b_U));
+        if (!Wg && !Ug) return BMP_OK;
+        for (int mt = 0; mt < KP; mt += 2) {          // 128 rows of the gradient per launch
+            w2::Args k = {};
+            k.A = S.Dp; k.a_ppt = 3 * KP; k.n_mt = 1;
+            k.a_panel[0][0] = g * KP + mt; k.a_panel[0][1] = mt + 1 < KP ? g * KP + mt + 1 : -1;
+            k.a_panel[1][0] = k.a_panel[1][1] = -1;
+            int nb = 0;
+            for (int j = 0; j < KP; ++j, ++nb) { k.B[nb] = S.Xp; k.b_ppt[nb] = KP; k.b_panel[nb] = j; }
+            for (int j = 0; j < KP; ++j, ++nb) { k.B[nb] = S.Mp; k.b_ppt[nb] = KP; k.b_panel[nb] = j; }
+            if (g == 2 && Ug)
+                for (int j = 0; j < KP; ++j, ++nb) { k.B[nb] = S.RSp; k.b_ppt[nb] = KP; k.b_panel[nb] = j; }
+            k.nb = nb;
+            for (int bl = 0; bl < 2; ++bl) {
+                if (k.a_panel[0][bl] < 0) continue;
+                const long row0 = (long)(mt + bl) * 64;
+                for (int j = 0; j < nb; ++j) {
+                    if (j < 2 * KP) {                  // W_g[:, j*64 ...] ; U_r / U_z see the h product as well
+                        k.C[0][bl][j] = Wg ? Wg + row0 * 2 * H + j * 64 : nullptr;
+                        k.ldc[j] = 2 * H;
+                        if (g < 2 && Ug && j < KP) { k.C2[0][bl][j] = Ug + row0 * H + j * 64; k.ldc2[j] = H; }
+                    } else {                           // U[:, ...] from the r*h panels
+                        k.C[0][bl][j] = Ug + row0 * H + (j - 2 * KP) * 64;
+                        k.ldc[j] = H;
+                    }
+                }
+                k.bias[0][bl] = bW ? bW + row0 : nullptr;
+                k.bias2[0][bl] = bU ? bU + row0 : nullptr;
+            }
+            k.bias_stride = 1;
+            k.t0 = ta; k.t1 = tb; k.n_tiles = n_tiles;
+            int e = bmp_wgrad_panels(k, stream);
             if (e) return e;
         }
         return BMP_OK;
@@ -638,30 +666,40 @@ int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
                a->d_gru[t1 + 1].U == a->d_gru[t0].U)
             ++t1;
         const bmp_gru_grad_t &D = a->d_gru[t0];
-        float *Wg[3] = {D.W_r, D.W_z, D.W};
-        float *bg[3] = {D.b_Wr, D.b_Wz, D.b_W};
-        for (int g = 0; g < 3; ++g) {
-            if (!Wg[g]) continue;
-            // dW_g[:, :H] += delta_g^T h_t ;  dW_g[:, H:] += delta_g^T m_t   (delta_r of stateless steps is zero)
-            if ((rc = run(S.Dp, 3 * KP, g * KP, S.Xp, KP, Wg[g], 2 * H, 2 * H, bg[g], 1, t0, t1))) return rc;
-            if ((rc = run(S.Dp, 3 * KP, g * KP, S.Mp, KP, Wg[g] + H, 2 * H, 2 * H, nullptr, 1, t0, t1))) return rc;
+        int s0 = t0;
+        while (s0 <= t1) {       // runs of equal statefulness (U-type gradients only over stateful steps)
+            const bool st = a->stateful[s0] != 0;
+            int s1 = s0;
+            while (s1 + 1 <= t1 && (a->stateful[s1 + 1] != 0) == st) ++s1;
+            for (int g = st ? 0 : 1; g < 3; ++g)       // delta_r of a stateless step is identically zero
+                if ((rc = gate_launch(g, s0, s1, st, D))) return rc;
+            s0 = s1 + 1;
         }
         if (a->d_msg_W[t0]) {
             // dW_m[c*E+e][:] += P_e^T h_t : C rows c with stride E*H, offset e*H; bias d_msg_b[c*E+e]
-            for (int e = 0; e < 4; ++e)
-                if ((rc = run(S.Pp, 4 * KP, e * KP, S.Xp, KP, a->d_msg_W[t0] + (long)e * H, 4L * H, 4 * H,
-                              a->d_msg_b[t0] ? a->d_msg_b[t0] + e : nullptr, 4, t0, t1)))
-                    return rc;
-        }
-        int s0 = t0;
-        while (s0 <= t1) {       // U-type gradients only over stateful steps
-            if (!a->stateful[s0]) { ++s0; continue; }
-            int s1 = s0;
-            while (s1 + 1 <= t1 && a->stateful[s1 + 1]) ++s1;
-            if (D.U_r && (rc = run(S.Dp, 3 * KP, 0 * KP, S.Xp, KP, D.U_r, H, H, D.b_Ur, 1, s0, s1))) return rc;
-            if (D.U_z && (rc = run(S.Dp, 3 * KP, 1 * KP, S.Xp, KP, D.U_z, H, H, D.b_Uz, 1, s0, s1))) return rc;
-            if (D.U && (rc = run(S.Dp, 3 * KP, 2 * KP, S.RSp, KP, D.U, H, H, D.b_U, 1, s0, s1))) return rc;
-            s0 = s1 + 1;
+            const bool pair_up = KP <= 3;              // two bond types (M tiles) per launch while N = 64 KP fits 192 columns
+            for (int e = 0; e < 4; e += pair_up ? 2 : 1)
+                for (int mt = 0; mt < KP; mt += 2) {
+                    w2::Args k = {};
+                    k.A = S.Pp; k.a_ppt = 4 * KP; k.n_mt = pair_up ? 2 : 1;
+                    for (int m = 0; m < 2; ++m) {
+                        const bool on = m < k.n_mt;
+                        k.a_panel[m][0] = on ? (e + m) * KP + mt : -1;
+                        k.a_panel[m][1] = on && mt + 1 < KP ? (e + m) * KP + mt + 1 : -1;
+                    }
+                    k.nb = KP;
+                    for (int j = 0; j < KP; ++j) { k.B[j] = S.Xp; k.b_ppt[j] = KP; k.b_panel[j] = j; k.ldc[j] = 4 * H; }
+                    for (int m = 0; m < k.n_mt; ++m)
+                        for (int bl = 0; bl < 2; ++bl) {
+                            if (k.a_panel[m][bl] < 0) continue;
+                            const long c0 = (long)(mt + bl) * 64;          // first channel c of this block
+                            for (int j = 0; j < KP; ++j) k.C[m][bl][j] = a->d_msg_W[t0] + (c0 * 4 + (e + m)) * H + j * 64;
+                            k.bias[m][bl] = a->d_msg_b[t0] ? a->d_msg_b[t0] + c0 * 4 + (e + m) : nullptr;
+                        }
+                    k.bias_stride = 4;
+                    k.t0 = t0; k.t1 = t1; k.n_tiles = n_tiles;
+                    if ((rc = bmp_wgrad_panels(k, stream))) return rc;
+                }
         }
         t0 = t1 + 1;
     }

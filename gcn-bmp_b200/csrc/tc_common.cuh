@@ -268,4 +268,25 @@ struct Stash2 {
 };
 
 }  // namespace tc
+
+// ---- grouped parameter-gradient contraction over the panel stash (wgrad_tc2.cu) -------------------
+namespace w2 {
+struct Args {
+    const uint8_t *A;                  // panel array of the A operand: [t][tile][a_ppt panels][16 KB]
+    int a_ppt;
+    int a_panel[2][2];                 // per M tile: the two 64-column blocks of A (= 64-row blocks of C); -1: absent
+    int n_mt;                          // M tiles (1 or 2; two only with nb <= 3)
+    const uint8_t *B[6];               // per B block: panel array, panels per tile, panel index
+    int b_ppt[6], b_panel[6];
+    int nb;
+    float *C[2][2][6];                 // target of (M tile, A block, B block): element (row 0, col 0), row-major; NULL: skip
+    int ldc[6];
+    float *C2[2][2][6];                // optional second target of the same sum
+    int ldc2[6];
+    float *bias[2][2], *bias2[2][2];   // column sums of the A block (stride bias_stride) or NULL
+    int bias_stride;
+    int t0, t1, n_tiles;               // steps [t0, t1], tiles per step
+    long chunks_per_cta;               // filled by bmp_wgrad_panels
+};
+}  // namespace w2
 }  // namespace bmp
