@@ -196,9 +196,13 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
         const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
         const int molslot = row >> 6, atom = row & 63;
         float hreg[NC];
-        float *stg = reinterpret_cast<float *>(smem + C::OFF_STG + warp * 2048);
+        // transposition staging for coalesced fp32 stores: a dedicated block, or (LEAN) the AH buffer, which is idle at
+        // the only two moments LEAN stores anything (tile start: h_0; tile end: h_T)
+        float *stg = reinterpret_cast<float *>(smem + (LEAN ? C::OFF_AH : C::OFF_STG) + warp * 2048);
         uint32_t it = 0;
+#define TSP(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + 8 + (i)] = clock64(); } while (0)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            TSP(0);
             const int molg = tile * 2 + molslot;
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;       // global row of this thread (if live)
@@ -226,24 +230,18 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                     *reinterpret_cast<uint4 *>(base + ((size_t)((cc >> 3) + g) * NE + tid) * 16) = pk;
                 }
             };
-            auto store_direct = [&](float *dst, const float *vals) {
-#pragma unroll
-                for (int x = 0; x < 32; x += 4) *reinterpret_cast<float4 *>(dst + x) = make_float4(vals[x], vals[x + 1], vals[x + 2], vals[x + 3]);
-            };
             auto store_rows16 = [&](float *base, long ld, int col0, const float *vals) {
                 warp_store_rows<16>(stg, vals, lane, [&](int r) -> float * {
                     const long g = wrow(r);
                     return g >= 0 ? base + g * ld + col0 : nullptr;
                 });
             };
-            // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
-            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
-            // ---- h_0: embedding gather (or h_in) -> fp32 registers + bf16 operand panels ----
+            // ---- h_0: embedding gather (or h_in) -> fp32 registers (requested first: the latency overlaps the staging)
             {
                 const float *src = nullptr;
                 if (live) {
                     if (a.atoms) {
-                        int id = a.atoms[grow];
+                        int id = __ldg(a.atoms + grow);
                         id = id < 0 ? 0 : (id >= a.n_types ? a.n_types - 1 : id);
                         src = a.embed_W + (long)id * H + colbase;
                     } else {
@@ -252,13 +250,19 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                 }
 #pragma unroll
                 for (int c = 0; c < NC; c += 4) {
-                    float4 v = src ? *reinterpret_cast<const float4 *>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = src ? __ldg(reinterpret_cast<const float4 *>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     hreg[c] = v.x; hreg[c + 1] = v.y; hreg[c + 2] = v.z; hreg[c + 3] = v.w;
                 }
+            }
+            // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
+            TSP(1);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            TSP(2);
+            {
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 32) {
-                    if (LEAN) {     // once per tile: plain lane-per-row vector stores
-                        if (a.h0_out && live) store_direct(a.h0_out + grow * H + colbase + cc, &hreg[cc]);
+                    if (LEAN) {
+                        if (a.h0_out) store_rows(a.h0_out, H, colbase + cc, &hreg[cc]);
                     } else {
                         if (a.h0_out) store_rows(a.h0_out, H, colbase + cc, &hreg[cc]);
                         if (a.Hs) store_rows(a.Hs, H, colbase + cc, &hreg[cc]);
@@ -278,23 +282,35 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                     *reinterpret_cast<uint4 *>(smem + C::OFF_H + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pk;
                 }
             };
+            TSP(3);
             store_h_operand(0);
+            TSP(4);
             // degrees deg_e[atom] = sum_j A_e[atom][j]  (from the staged bf16 tile; needs the staging complete)
             asm volatile("bar.sync 1, %0;" ::"n"(NE));
+            TSP(5);
+            // each column group sums ONE bond type for its 128 rows (H = 128: four groups; H = 64: two groups x two types),
+            // the four values per row are exchanged through the (idle) AH buffer
             float deg[4];
+            {
+                float *dsh = reinterpret_cast<float *>(smem + C::OFF_AH);       // [4][128]
+                for (int e = hf; e < 4; e += EPW / 4) {
+                    float s0 = 0.f, s1 = 0.f;
+                    const uint8_t *rowp = smem + C::OFF_ADJ + (molslot * 4 + e) * ADJ_TILE_BYTES + atom * 128;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float s = 0.f;
-                const uint8_t *rowp = smem + C::OFF_ADJ + (molslot * 4 + e) * ADJ_TILE_BYTES + atom * 128;
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint4 u = *reinterpret_cast<const uint4 *>(rowp + ((ch ^ (atom & 7)) << 4));     // any chunk order; rotated: conflict-free
+                        const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                    uint4 u = *reinterpret_cast<const uint4 *>(rowp + ch * 16);
-                    const __nv_bfloat162 *b2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) { float2 f = __bfloat1622float2(b2[x]); s += f.x + f.y; }
+                        for (int x = 0; x < 4; ++x) { float2 f = __bfloat1622float2(b2[x]); s0 += f.x; s1 += f.y; }
+                    }
+                    dsh[e * 128 + row] = s0 + s1;
                 }
-                deg[e] = s;
+                asm volatile("bar.sync 1, %0;" ::"n"(NE));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) deg[e] = dsh[e * 128 + row];
+                asm volatile("bar.sync 1, %0;" ::"n"(NE));      // AH is handed to the epilogue / staging again
             }
+            TSP(6);
             warp_arrive(BAR(B_HREADY), lane);
 
             for (int t = 0; t < a.T; ++t, ++it) {
@@ -303,6 +319,10 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                 const float *b3 = a.bias3[t];
 #define TSF(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TSF(0);
+                if (t == a.T - 1 && tile + (int)gridDim.x < n_tiles) {      // next tile of this CTA: adjacency and atom ids towards L2
+                    prefetch_adjacency_l2<NE>(a.adj, tile + gridDim.x, a.mb, a.N, tid);
+                    if (a.atoms && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
+                }
                 uint32_t v[32];
                 // ---- E1: AH accumulators -> bf16 A-operand panels (two K halves) ----
                 for (int p = 0; p < 2; ++p) {
@@ -439,7 +459,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
 #pragma unroll
                 for (int cc = 0; cc < NC; cc += 32) {
                     if (LEAN) {
-                        if (t == a.T - 1 && a.h_out && live) store_direct(a.h_out + grow * H + colbase + cc, &hreg[cc]);
+                        if (t == a.T - 1 && a.h_out) store_rows(a.h_out, H, colbase + cc, &hreg[cc]);
                     } else {
                         if (a.Hs) store_rows(a.Hs + (long)(t + 1) * rows_total * H, H, colbase + cc, &hreg[cc]);
                         if (t == a.T - 1 && a.h_out) store_rows(a.h_out, H, colbase + cc, &hreg[cc]);

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 uint32_t v[32];
 #define TS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TS(0);
+                if (t == 0 && tile + (int)gridDim.x < n_tiles) prefetch_adjacency_l2<NE>(a.adj, tile + gridDim.x, a.mb, a.N, tid);
                 // ---- phase A: gate derivatives ----
                 uint4 sp[NC / 8];            // state of the step, packed bf16 (stash v2), reused by phase B
                 if (V2) {
@@ -462,28 +463,39 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 }
                 TS(10);
                 // ---- phase E: dh_t = dh_x (+ dh_msg) + ds + external gradient ----
-                mbar_wait(BAR(B_DH), par);
-                tc_fence_after();
-                TS(11);
                 {
                     float *ext = a.dHs + ((long)(V2 ? 0 : t) * rows_total + grow) * H + colbase;
                     const bool has_ext = live && (V2 ? t == 0 : a.ext_flags[t] != 0);
+                    float4 e4[NC / 4];          // requested before waiting for the accumulator: the latency overlaps MMA-dh
+#pragma unroll
+                    for (int x = 0; x < NC / 4; ++x) e4[x] = has_ext ? __ldg(reinterpret_cast<const float4 *>(ext) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    mbar_wait(BAR(B_DH), par);
+                    tc_fence_after();
+                    TS(11);
 #pragma unroll
                     for (int cc = 0; cc < NC; cc += 32) {
                         tc_ld32(t_lane + COL_DHX + colbase + cc, v);
                         tc_wait_ld();
 #pragma unroll
                         for (int x = 0; x < 32; x += 4) {
-                            float4 e4 = has_ext ? *reinterpret_cast<const float4 *>(ext + cc + x) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            acc[cc + x] += __uint_as_float(v[x]) + e4.x;
-                            acc[cc + x + 1] += __uint_as_float(v[x + 1]) + e4.y;
-                            acc[cc + x + 2] += __uint_as_float(v[x + 2]) + e4.z;
-                            acc[cc + x + 3] += __uint_as_float(v[x + 3]) + e4.w;
+                            const float4 e = e4[(cc + x) >> 2];
+                            acc[cc + x] += __uint_as_float(v[x]) + e.x;
+                            acc[cc + x + 1] += __uint_as_float(v[x + 1]) + e.y;
+                            acc[cc + x + 2] += __uint_as_float(v[x + 2]) + e.z;
+                            acc[cc + x + 3] += __uint_as_float(v[x + 3]) + e.w;
                         }
                     }
-                    if (t == 0 && live) {
+                    if (t == 0) {
+                        // dL/dh_0 of the tile: coalesced rows through a transposition block (the delta panels are idle:
+                        // every MMA of the tile has completed)
+                        float *stg = reinterpret_cast<float *>(smem + C::OFF_D + warp * 2048);
+                        float *out = a.dHs + colbase;      // slice 0 in both stash layouts
 #pragma unroll
-                        for (int c = 0; c < NC; c += 4) *reinterpret_cast<float4 *>(ext + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+                        for (int h2 = 0; h2 < 2; ++h2)
+                            warp_store_rows<16>(stg, acc + 16 * h2, lane, [&](int r) -> float * {
+                                const int tr = 32 * q + r, mg = tile * 2 + (tr >> 6), at = tr & 63;
+                                return (mg < a.mb && at < a.N) ? out + ((long)mg * a.N + at) * H + 16 * h2 : nullptr;
+                            });
                     }
                 }
                 TS(12);

@@ -161,6 +161,15 @@ __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const float *__r
     }
 }
 
+// pull the next tile's adjacency (2 molecules x 4 bond types x N x N fp32, contiguous) towards L2
+template <int NE>
+__device__ __forceinline__ void prefetch_adjacency_l2(const float *__restrict__ adj, int tile, int mb, int N, int tid) {
+    const long first = (long)tile * 2, nmol = first + 2 <= mb ? 2 : (first < mb ? 1 : 0);
+    const char *base = reinterpret_cast<const char *>(adj + first * 4 * N * N);
+    const long bytes = nmol * 4L * N * N * 4;
+    for (long off = (long)tid * 128; off < bytes; off += (long)NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+}
+
 // ---- coalesced global I/O for the lane == row register layout -----------------------------------
 // An epilogue warp owns 32 tile rows; each lane holds W consecutive fp32 columns of ITS row (the
 // tcgen05.ld 32x32b layout).  Going to global memory lane-per-row touches 32 different lines per
