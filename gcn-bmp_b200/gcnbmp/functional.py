@@ -49,6 +49,37 @@ def _fill_gru(dst, tensors):
         setattr(dst, name, _p(t))
 
 
+_GRAD_SINK = False
+
+
+def set_grad_sink(flag):
+    """Opt-in fast path for training loops that own their gradient buffers (train.PairTrainer): the kernels
+    ACCUMULATE parameter gradients, so with the sink on they add straight into each parameter's existing
+    `.grad` and autograd is handed None for it -- no per-parameter zero-fill and no per-parameter add kernel.
+    Only valid when gradients are consumed through `.grad` (plain `.backward()`); leave it off for
+    `torch.autograd.grad`, hooks or double backward."""
+    global _GRAD_SINK
+    _GRAD_SINK = bool(flag)
+
+
+def _grad_targets(params):
+    """(buffers the kernels accumulate into, gradients returned to autograd) for a list of parameters."""
+    bufs, rets = [], []
+    for p in params:
+        if p is None:
+            bufs.append(None)
+            rets.append(None)
+        elif (_GRAD_SINK and p.requires_grad and p.grad is not None and p.grad.dtype == torch.float32
+              and p.grad.is_contiguous() and p.grad.shape == p.shape):
+            bufs.append(p.grad)
+            rets.append(None)
+        else:
+            z = torch.zeros_like(p)
+            bufs.append(z)
+            rets.append(z)
+    return bufs, rets
+
+
 class GGNNEncode(torch.autograd.Function):
     """embed -> T x GGNNUpdate.  `plan` = list of (msg_idx, gru_idx, stateful) per step;
     `params` = [embed_W or None] + n_msg*(W,b) + n_gru*12 tensors.
@@ -127,7 +158,7 @@ class GGNNEncode(torch.autograd.Function):
             _, mb, N, H = Hs.shape
         rows = mb * N
         dHs = dHs.contiguous().clone()
-        grads = [torch.zeros_like(p) if p is not None else None for p in params]
+        grads, rets = _grad_targets(params)
         Ps = torch.empty((T, rows, E * H), device=adj.device, dtype=torch.float32) if stash2 is None else None
         a = K.GgnnBwd()
         a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
@@ -153,8 +184,8 @@ class GGNNEncode(torch.autograd.Function):
             K.check(K.lib.bmp_embed_backward(_p(x), _p(dHs[0]), _p(grads[0]), rows, H, grads[0].shape[0], _stream()))
         else:
             dx = dHs[0]
-            grads[0] = None
-        return (dx, None, d_state, None, None, None, None, None, None) + tuple(grads)
+            rets[0] = None
+        return (dx, None, d_state, None, None, None, None, None, None) + tuple(rets)
 
 
 class RelGCNEncode(torch.autograd.Function):
@@ -271,7 +302,7 @@ class Readout(torch.autograd.Function):
         dg = _f32(dg)
         z = lambda t: torch.zeros_like(t) if t is not None else None
         dh, dh0 = torch.zeros_like(h), z(h0)
-        gWi, gbi, gWj, gbj = z(W_i), z(b_i), z(W_j), z(b_j)
+        (gWi, gbi, gWj, gbj), rets = _grad_targets([W_i, b_i, W_j, b_j])
         a = K.ReadoutBwd()
         a.mb, a.n_atoms, a.hidden, a.out_dim, a.variant, a.act, a.act_agg = mb, N, H, O, variant, act, act_agg
         a.h, a.h0, a.is_real_node = _p(h), _p(h0), _p(mask)
@@ -284,7 +315,7 @@ class Readout(torch.autograd.Function):
         a.d_W_i, a.d_b_i, a.d_W_j, a.d_b_j = _p(gWi), _p(gbi), _p(gWj), _p(gbj)
         ws = _readout_ws(a, mode, H, O, variant, dev)
         K.check(K.lib.bmp_readout_backward(C.byref(a), _stream()))
-        return dh, dh0, None, None, None, None, gWi, gbi, gWj, gbj, None
+        return (dh, dh0, None, None, None, None) + tuple(rets) + (None,)
 
 
 def _coattn_workspace(mode, H, dev):
@@ -334,7 +365,7 @@ class Coattention(torch.autograd.Function):
         O = ps[8].shape[0]
         dev = atoms_1.device
         dc1, dc2 = _f32(dc1), _f32(dc2)
-        grads = [torch.zeros_like(t) if t is not None else None for t in ps]
+        grads, rets = _grad_targets(ps)
         da1, da2 = torch.empty_like(atoms_1), torch.empty_like(atoms_2)
         e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         R, P1, P2 = e(mb * n1, H), e(mb, H), e(mb, H)
@@ -354,7 +385,7 @@ class Coattention(torch.autograd.Function):
         if ws is not None:
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), ws.numel()
         K.check(K.lib.bmp_coattn_backward(C.byref(a), _stream()))
-        return (da1, da2, None, None) + tuple(grads) + (None,)
+        return (da1, da2, None, None) + tuple(rets) + (None,)
 
 
 class HoleCorr(torch.autograd.Function):
@@ -402,11 +433,10 @@ class Linear(torch.autograd.Function):
         out_dim = W.shape[0]
         dy = dy.contiguous().float().clone()
         dx = torch.empty_like(x)
-        dW = torch.zeros_like(W)
-        db = torch.zeros_like(b) if b is not None else None
+        (dW, db), rets = _grad_targets([W, b])
         K.check(K.lib.bmp_linear_backward(_p(x), _p(W), _p(y), _p(dy), _p(dx), _p(dW), _p(db),
                                           rows, in_dim, out_dim, ctx.act, _stream()))
-        return dx, dW, db, None
+        return dx, rets[0], rets[1], None
 
 
 class SigmoidCrossEntropy(torch.autograd.Function):

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _capi as K
+from . import functional as Fn
 from . import links as L
 from . import parallel
 
@@ -93,7 +94,11 @@ class PairTrainer(object):
                 a1, A1, a2, A2, y = (a[s:e] for a in arrs)
             logits = self.model(a1, A1, a2, A2)
             loss = L.sigmoid_cross_entropy(logits, y, count=global_count)
-            loss.backward()
+            Fn.set_grad_sink(True)       # kernels add straight into the flat gradient buffer (the .grad views)
+            try:
+                loss.backward()
+            finally:
+                Fn.set_grad_sink(False)
             self.loss_buf += loss.detach()
         if self.world_size > 1:
             parallel.allreduce_sum_(self.gflat, self.pg)
