@@ -829,7 +829,8 @@ static int launch_ctc(const ctc::Args &k, int head, cudaStream_t st) {
 // Shared by forward and backward: pack the weight images into the workspace, fill the common arguments.
 static int ctc_prepare(ctc::Args &k, int mb, int n1, int n2, int H, int O, int head, int act, const float *a1, const float *a2,
                        const float *W, const float *V1, const float *V2, const float *b, const float *lt1, const float *lt2,
-                       const float *wa1, const float *wa2, const float *Wj, const float *bj, void *ws, size_t ws_bytes, cudaStream_t st) {
+                       const float *wa1, const float *wa2, const float *Wj, const float *bj, void *ws, size_t ws_bytes, bool images_ready,
+                       cudaStream_t st) {
     if (!ws || ws_bytes < bmp_coattn_tc_workspace_bytes(H)) {
         set_error("BMP_MODE_BF16 co-attention: tc_workspace of >= %zu bytes required", bmp_coattn_tc_workspace_bytes(H));
         return BMP_EINVAL;
@@ -840,10 +841,12 @@ static int ctc_prepare(ctc::Args &k, int mb, int n1, int n2, int H, int O, int h
     p.img1 = base;
     p.img2 = p.img1 + (size_t)(H / 64) * (H + 32) * 128;
     p.img1x = p.img2 + (size_t)(H / 64) * H * 128;
-    ctc::pack_coattn_kernel<<<32, 256, 0, st>>>(p);
-    count_launch();
-    int rc = check_launch("pack_coattn_kernel");
-    if (rc) return rc;
+    if (!images_ready) {
+        ctc::pack_coattn_kernel<<<32, 256, 0, st>>>(p);
+        count_launch();
+        int rc = check_launch("pack_coattn_kernel");
+        if (rc) return rc;
+    }
     k = ctc::Args{};
     k.mb = mb; k.n1 = n1; k.n2 = n2; k.O = O; k.head = head; k.act = act;
     k.atoms_1 = a1; k.atoms_2 = a2; k.b = b; k.wa_1 = wa1; k.wa_2 = wa2; k.W_j = Wj; k.b_j = bj; k.lt_2 = lt2; k.V2 = V2;
@@ -856,7 +859,7 @@ int bmp_coattn_forward_tc(const bmp_coattn_fwd_t *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ctc::Args k;
     int rc = ctc_prepare(k, a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->act, a->atoms_1, a->atoms_2, a->W, a->V1, a->V2, a->b,
-                         a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j, a->tc_workspace, a->tc_workspace_bytes, st);
+                         a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j, a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, st);
     if (rc) return rc;
     k.c1 = a->compact_1; k.c2 = a->compact_2;
     return a->hidden == 64 ? launch_ctc<64, false>(k, a->head, st) : launch_ctc<128, false>(k, a->head, st);
@@ -867,7 +870,7 @@ int bmp_coattn_backward_tc(const bmp_coattn_bwd_t *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ctc::Args k;
     int rc = ctc_prepare(k, a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->act, a->atoms_1, a->atoms_2, a->W, a->V1, a->V2, a->b,
-                         a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j, a->tc_workspace, a->tc_workspace_bytes, st);
+                         a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j, a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, st);
     if (rc) return rc;
     k.dc1 = a->d_compact_1; k.dc2 = a->d_compact_2; k.R = a->R; k.P1 = a->P1; k.P2 = a->P2; k.DL1 = a->DL1; k.DL2 = a->DL2;
     k.d_a1 = a->d_atoms_1; k.d_a2 = a->d_atoms_2;

@@ -596,8 +596,10 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
         float *bias3 = reinterpret_cast<float *>(img + (size_t)(11 * (H / 64)) * H * 128);
         tc::PackArgs p;
         p.H = H; p.stateful = k.stateful[t]; p.msg_W = a->msg_W[t]; p.g = a->gru[t]; p.img = img; p.bias3 = bias3;
-        tc::pack_kernel<<<64, 256, 0, st>>>(p);
-        count_launch();
+        if (!a->tc_images_ready) {
+            tc::pack_kernel<<<64, 256, 0, st>>>(p);
+            count_launch();
+        }
         k.img[t] = img; k.bias3[t] = bias3;
         ++n_img;
     }

@@ -593,8 +593,10 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
         if (found >= 0) { k.img[t] = k.img[found]; continue; }
         tcb::PackArgs p;
         p.H = H; p.stateful = k.stateful[t]; p.msg_W = a->msg_W[t]; p.g = a->gru[t]; p.img = ws + (size_t)n_img * ib;
-        tcb::pack_bwd_kernel<<<64, 256, 0, st>>>(p);
-        count_launch();
+        if (!a->tc_images_ready) {
+            tcb::pack_bwd_kernel<<<64, 256, 0, st>>>(p);
+            count_launch();
+        }
         k.img[t] = p.img;
         ++n_img;
     }

@@ -145,7 +145,7 @@ using namespace bmp;
 int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_agg, const float *h, const float *h0,
                    const float *mask, const float *W_i, const float *b_i, const float *W_j, const float *b_j,
                    float *g, const float *dg, float *DU, float *DV, float *dh, float *dh0, void *ws, size_t ws_bytes,
-                   bool bwd, void *stream);   // readout_tc.cu
+                   bool images_ready, bool bwd, void *stream);   // readout_tc.cu
 
 extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
     if (!a || !a->g) { set_error("bmp_readout_forward: null argument"); return BMP_EINVAL; }
@@ -163,7 +163,7 @@ extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
     if (a->mode == BMP_MODE_BF16 && bmp_readout_tc_workspace_bytes(a->hidden, a->out_dim)) {
         return bmp_readout_tc(a->mb, a->n_atoms, a->hidden, a->out_dim, a->variant, a->act, a->act_agg, a->h, a->h0,
                               a->is_real_node, a->W_i, a->b_i, a->W_j, a->b_j, a->g, nullptr, nullptr, nullptr, nullptr, nullptr,
-                              a->tc_workspace, a->tc_workspace_bytes, false, stream);
+                              a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, false, stream);
     }
     const int Kcat = a->h0 ? 2 * a->hidden : a->hidden;
     size_t smem = sizeof(float) * ((size_t)Kcat * AT + STAGE_FLOATS);
@@ -197,7 +197,7 @@ extern "C" int bmp_readout_backward(const bmp_readout_bwd_t *a, void *stream) {
     if (tc) {
         if ((rc = bmp_readout_tc(a->mb, a->n_atoms, H, O, a->variant, a->act, a->act_agg, a->h, a->h0, a->is_real_node,
                                  a->W_i, a->b_i, a->W_j, a->b_j, const_cast<float *>(a->g), a->dg, a->DU, a->DV, a->dh, a->dh0,
-                                 a->tc_workspace, a->tc_workspace_bytes, true, stream)))
+                                 a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, true, stream)))
             return rc;
     } else {
         size_t smem = sizeof(float) * ((size_t)(Kcat + 2 * O) * AT + STAGE_FLOATS);

@@ -335,7 +335,7 @@ static int launch_readout_tc(const rtc::Args &k, bool bwd, int grid, cudaStream_
 int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_agg, const float *h, const float *h0,
                    const float *mask, const float *W_i, const float *b_i, const float *W_j, const float *b_j,
                    float *g, const float *dg, float *DU, float *DV, float *dh, float *dh0, void *ws, size_t ws_bytes,
-                   bool bwd, void *stream) {
+                   bool images_ready, bool bwd, void *stream) {
     if ((H != 64 && H != 128) || (O != 64 && O != 128) || variant == BMP_READOUT_SUM || N > BMP_MAX_ATOMS) {
         set_error("readout tcgen05 path: unsupported shape H=%d O=%d variant=%d", H, O, variant);
         return BMP_ESHAPE;
@@ -350,10 +350,12 @@ int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_ag
     k.img = img;
     rtc::PackArgs p;
     p.H = H; p.O = O; p.Kcat = k.Kcat; p.Kj = k.Kj; p.W_i = W_i; p.W_j = W_j; p.img = img;
-    rtc::pack_readout_kernel<<<32, 256, 0, st>>>(p);
-    count_launch();
-    int rc = check_launch("pack_readout_kernel");
-    if (rc) return rc;
+    int rc = BMP_OK;
+    if (!images_ready) {
+        rtc::pack_readout_kernel<<<32, 256, 0, st>>>(p);
+        count_launch();
+        if ((rc = check_launch("pack_readout_kernel"))) return rc;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

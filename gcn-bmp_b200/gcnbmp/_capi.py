@@ -31,7 +31,7 @@ class GgnnFwd(C.Structure):
         ("atoms", fp), ("h_in", fp), ("embed_W", fp), ("adj", fp), ("state_in", fp),
         ("msg_W", _A()), ("msg_b", _A()), ("gru", GRU * MAX_STEPS), ("stateful", C.c_int * MAX_STEPS),
         ("h_out", fp), ("h0_out", fp), ("Hs", fp), ("Ms", fp), ("Gs", fp), ("RSs", fp),
-        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp)]
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
 
 
 class GgnnBwd(C.Structure):
@@ -39,7 +39,7 @@ class GgnnBwd(C.Structure):
         ("adj", fp), ("state_in", fp), ("msg_W", _A()), ("gru", GRU * MAX_STEPS),
         ("stateful", C.c_int * MAX_STEPS), ("Hs", fp), ("Ms", fp), ("RSs", fp), ("Gs", fp), ("Ps", fp), ("dHs", fp),
         ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS), ("d_state_in", fp),
-        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp)]
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
 
 
 class RelgcnFwd(C.Structure):
@@ -58,14 +58,14 @@ class RelgcnBwd(C.Structure):
 class ReadoutFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "hidden", "out_dim", "variant", "act", "act_agg")] + [
         (n, fp) for n in ("h", "h0", "is_real_node", "W_i", "b_i", "W_j", "b_j", "g")] + [
-        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("tc_images_ready", C.c_int)]
 
 
 class ReadoutBwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "hidden", "out_dim", "variant", "act", "act_agg")] + [
         (n, fp) for n in ("h", "h0", "is_real_node", "W_i", "b_i", "W_j", "b_j", "g", "dg",
                           "DU", "DV", "dh", "dh0", "d_W_i", "d_b_i", "d_W_j", "d_b_j")] + [
-        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("tc_images_ready", C.c_int)]
 
 
 _CO_PARAMS = ("W", "V1", "V2", "b", "lt_1", "lt_2", "wa_1", "wa_2", "W_j", "b_j")
@@ -74,7 +74,7 @@ _CO_PARAMS = ("W", "V1", "V2", "b", "lt_1", "lt_2", "wa_1", "wa_2", "W_j", "b_j"
 class CoattnFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "out_dim", "head", "variant", "act")] + [
         (n, fp) for n in ("atoms_1", "atoms_2") + _CO_PARAMS + ("compact_1", "compact_2")] + [
-        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("tc_images_ready", C.c_int)]
 
 
 class CoattnBwd(C.Structure):
@@ -82,7 +82,7 @@ class CoattnBwd(C.Structure):
         (n, fp) for n in ("atoms_1", "atoms_2") + _CO_PARAMS + ("d_compact_1", "d_compact_2", "R", "P1", "P2",
                                                              "DL1", "DL2", "d_atoms_1", "d_atoms_2")
         + tuple("d_" + p for p in _CO_PARAMS)] + [
-        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t)]
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("tc_images_ready", C.c_int)]
 
 
 def _load():

@@ -49,6 +49,40 @@ def _fill_gru(dst, tensors):
         setattr(dst, name, _p(t))
 
 
+_WEIGHT_CACHE = False
+_PARAM_EPOCH = 0
+_IMAGES = {}
+
+
+def set_weight_cache(flag):
+    """Opt-in (train.PairTrainer): keep the packed bf16 weight images of the tcgen05 kernels between calls instead
+    of re-packing them on every launch.  The owner MUST call `params_changed()` whenever parameter values change."""
+    global _WEIGHT_CACHE
+    _WEIGHT_CACHE = bool(flag)
+    if not flag:
+        _IMAGES.clear()
+
+
+def params_changed():
+    """Invalidate every cached weight image (parameters were updated, loaded or re-homed)."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
+    _IMAGES.clear()
+
+
+def _tc_images(kind, nbytes, dev, params):
+    """Workspace for the packed weight images of one launch kind -> (uint8 tensor, ready flag)."""
+    if not _WEIGHT_CACHE:
+        return torch.empty((nbytes,), device=dev, dtype=torch.uint8), 0
+    key = (kind, nbytes, str(dev)) + tuple(p.data_ptr() if p is not None else 0 for p in params)
+    ent = _IMAGES.get(key)
+    if ent is not None and ent[1] == _PARAM_EPOCH:
+        return ent[0], 1
+    ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    _IMAGES[key] = (ws, _PARAM_EPOCH)
+    return ws, 0
+
+
 _GRAD_SINK = False
 
 
@@ -117,7 +151,7 @@ class GGNNEncode(torch.autograd.Function):
             nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
             if nbytes == 0:
                 raise ValueError("gcnbmp: BMP_MODE_BF16 supports hidden 64 or 128 (got %d)" % H)
-            ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+            ws, a.tc_images_ready = _tc_images("ggnn_fwd", nbytes, dev, params)
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
         if want_stash and mode == K.MODE_BF16 and not keep_steps:
             # bf16 panel stash: the tape keeps operand panels + gate values; only [h_0, h_T] go back as fp32
@@ -176,7 +210,7 @@ class GGNNEncode(torch.autograd.Function):
         a.d_state_in = _p(d_state)
         if mode == K.MODE_BF16:
             nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
-            ws = torch.empty((nbytes,), device=adj.device, dtype=torch.uint8)
+            ws, a.tc_images_ready = _tc_images("ggnn_bwd", nbytes, adj.device, params)
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
         K.check(K.lib.bmp_ggnn_backward(C.byref(a), _stream()))
         dx = None
@@ -260,13 +294,13 @@ class RelGCNEncode(torch.autograd.Function):
         return (dx, None, None, None, None, None) + tuple(grads)
 
 
-def _readout_ws(a, mode, H, O, variant, dev):
+def _readout_ws(a, mode, H, O, variant, dev, params):
     """BF16 mode: attach the packed-weight workspace of the tcgen05 readout when the shape is on that path."""
     a.mode = K.MODE_F32
     if mode == K.MODE_BF16 and variant != K.READOUT_SUM:
         nbytes = int(K.lib.bmp_readout_tc_workspace_bytes(H, O))
         if nbytes:
-            ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+            ws, a.tc_images_ready = _tc_images("readout", nbytes, dev, params)
             a.mode, a.tc_workspace, a.tc_workspace_bytes = K.MODE_BF16, _p(ws), nbytes
             return ws
     return None
@@ -286,7 +320,7 @@ class Readout(torch.autograd.Function):
         a.mb, a.n_atoms, a.hidden, a.out_dim, a.variant, a.act, a.act_agg = mb, N, H, O, variant, act, act_agg
         a.h, a.h0, a.is_real_node = _p(h), _p(h0), _p(mask)
         a.W_i, a.b_i, a.W_j, a.b_j, a.g = _p(W_i), _p(b_i), _p(W_j), _p(b_j), _p(g)
-        ws = _readout_ws(a, mode, H, O, variant, h.device)
+        ws = _readout_ws(a, mode, H, O, variant, h.device, (W_i, W_j))
         K.check(K.lib.bmp_readout_forward(C.byref(a), _stream()))
         ctx.save_for_backward(h, h0, mask, W_i, b_i, W_j, b_j, g)
         ctx.meta = (variant, act, act_agg, mode)
@@ -313,17 +347,21 @@ class Readout(torch.autograd.Function):
             a.DU, a.DV = _p(DU), _p(DV)
         a.dh, a.dh0 = _p(dh), _p(dh0)
         a.d_W_i, a.d_b_i, a.d_W_j, a.d_b_j = _p(gWi), _p(gbi), _p(gWj), _p(gbj)
-        ws = _readout_ws(a, mode, H, O, variant, dev)
+        ws = _readout_ws(a, mode, H, O, variant, dev, (W_i, W_j))
         K.check(K.lib.bmp_readout_backward(C.byref(a), _stream()))
         return (dh, dh0, None, None, None, None) + tuple(rets) + (None,)
 
 
-def _coattn_workspace(mode, H, dev):
+def _coattn_workspace(a, mode, H, dev, params):
     """Packed bf16 weight images of the tcgen05 co-attention (None when that path does not apply)."""
     if mode != K.MODE_BF16:
         return None
     n = int(K.lib.bmp_coattn_tc_workspace_bytes(H))
-    return torch.empty((n,), device=dev, dtype=torch.uint8) if n else None
+    if not n:
+        return None
+    ws, a.tc_images_ready = _tc_images("coattn", n, dev, params)
+    a.tc_workspace, a.tc_workspace_bytes = _p(ws), n
+    return ws
 
 
 class Coattention(torch.autograd.Function):
@@ -347,9 +385,7 @@ class Coattention(torch.autograd.Function):
             setattr(a, n, _p(t))
         a.compact_1, a.compact_2 = _p(c1), _p(c2)
         a.mode = mode
-        ws = _coattn_workspace(mode, H, atoms_1.device)
-        if ws is not None:
-            a.tc_workspace, a.tc_workspace_bytes = _p(ws), ws.numel()
+        ws = _coattn_workspace(a, mode, H, atoms_1.device, ps)
         K.check(K.lib.bmp_coattn_forward(C.byref(a), _stream()))
         ctx.save_for_backward(atoms_1, atoms_2, *ps)
         ctx.meta = (variant, act, head, mode)
@@ -381,9 +417,7 @@ class Coattention(torch.autograd.Function):
         a.R, a.P1, a.P2, a.DL1, a.DL2 = _p(R), _p(P1), _p(P2), _p(DL1), _p(DL2)
         a.d_atoms_1, a.d_atoms_2 = _p(da1), _p(da2)
         a.mode = mode
-        ws = _coattn_workspace(mode, H, dev)
-        if ws is not None:
-            a.tc_workspace, a.tc_workspace_bytes = _p(ws), ws.numel()
+        ws = _coattn_workspace(a, mode, H, dev, ps)
         K.check(K.lib.bmp_coattn_backward(C.byref(a), _stream()))
         return (da1, da2, None, None) + tuple(rets) + (None,)
 

@@ -33,6 +33,7 @@ class Adam(object):
         K.check(K.lib.bmp_adam_step(p(self.flat), p(self.gflat), p(self.m), p(self.v), self.flat.numel(),
                                     a, b1, b2, eps, wd, self.t,
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        Fn.params_changed()
 
 
 class PairTrainer(object):
@@ -79,6 +80,16 @@ class PairTrainer(object):
             global_count = float(n * labels.shape[1] * self.world_size)
         self.gflat.zero_()
         self.loss_buf.zero_()
+        # parameters are constant within a step: pack the tcgen05 weight images once, not once per micro-batch
+        Fn.params_changed()
+        Fn.set_weight_cache(True)
+        try:
+            return self._step_chunks(arrs, n, on_host, global_count)
+        finally:
+            Fn.set_weight_cache(False)
+
+    def _step_chunks(self, arrs, n, on_host, global_count):
+        labels = arrs[4]
         chunks = self._chunks(n)
         nxt = self._upload(arrs, *chunks[0]) if on_host else None
         cur_stream = torch.cuda.current_stream()

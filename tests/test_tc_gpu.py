@@ -46,7 +46,7 @@ def test_tc_encoder_matches_oracle_within_bf16_bound(H, T, mb, N, tied):
 
 
 def test_tc_mode_pair_training_step_close_to_oracle():
-    """Full pair fwd+bwd with the tensor-core forward feeding the fp32 backward kernels."""
+    """Full pair fwd+bwd with encoder and co-attention on the tcgen05 kernels."""
     case = cases.pair_case("C", seed=11)
     sp = dict(case["spec"], H=64, O=64)
     rng = np.random.default_rng(5)
@@ -56,7 +56,7 @@ def test_tc_mode_pair_training_step_close_to_oracle():
     big = dict(case, spec=sp, params=R.init_params(shapes, rng, dtype=np.float64))
     o = cases.oracle_eval(big)
     model = product.product_model(sp, big["params"])
-    model.graph_conv.mode = __import__("gcnbmp").MODE_BF16
+    model.graph_conv.mode = model.attn.mode = __import__("gcnbmp").MODE_BF16
     a1, A1, a2, A2 = big["inputs"]
     logits = model(a1, A1.astype(np.float32), a2, A2.astype(np.float32))
     loss = __import__("gcnbmp").sigmoid_cross_entropy(logits, big["labels"])
@@ -173,3 +173,44 @@ def test_tc_coattention_within_bf16_bound(variant, n1, n2, H, O, head, mb):
     g = link.grad_dict()
     for k in g:
         assert rel_err(g[k], tab[k].grad, floor=1e-3) <= MAX_TOL, k
+
+
+def test_trainer_fast_paths_match_plain_autograd():
+    """PairTrainer's gradient sink and weight-image cache change the launches, not the result: gradients over three
+    micro-batches equal plain autograd with fresh images on every launch -- also after the parameters moved."""
+    import gcnbmp
+    from gcnbmp import train
+    case = cases.pair_case("C", seed=3)
+    sp = dict(case["spec"], H=64, O=64)
+    rng = np.random.default_rng(9)
+    shapes = {"graph_conv/" + k: v for k, v in R.ggnn_mono_shapes(64, 64, sp["T"]).items()}
+    shapes.update({"attn/" + k: v for k, v in R.coattn_shapes(64, 64, 8).items()})
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(64, sp["K"], ()).items()})
+    params = R.init_params(shapes, rng, dtype=np.float64)
+    a1, A1, a2, A2 = case["inputs"]
+    A1, A2, y = A1.astype(np.float32), A2.astype(np.float32), case["labels"]
+    dev = lambda x: torch.tensor(x, device="cuda")
+    args = [dev(a1), dev(A1), dev(a2), dev(A2), dev(y)]
+
+    def make():
+        m = product.product_model(sp, params)
+        m.graph_conv.mode = m.attn.mode = gcnbmp.MODE_BF16
+        return m
+
+    fast, plain = make(), make()
+    tr = train.PairTrainer(fast, chunk=2, optimizer=False)
+    pflat, pg = plain.flatten_parameters()
+    n = a1.shape[0]
+    count = float(n * y.shape[1])
+    for rnd in range(2):
+        tr.step(*args)
+        pg.zero_()
+        for s in range(0, n, 2):
+            logits = plain(*(t[s:s + 2] for t in args[:4]))
+            gcnbmp.sigmoid_cross_entropy(logits, args[4][s:s + 2], count=count).backward()
+        ga, gb = tr.gflat.cpu().numpy(), pg.cpu().numpy()
+        assert np.abs(gb).max() > 0
+        assert np.abs(ga - gb).max() <= 1e-5 * np.abs(gb).max(), rnd
+        with torch.no_grad():            # move the parameters: cached images must not survive into the next step
+            tr.flat.mul_(1.05)
+            pflat.mul_(1.05)
