@@ -107,6 +107,53 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int32_t *__restric
     }
 }
 
+// Atomic-free variant: a CTA owns a contiguous block of rows; its 256 threads form two row partitions of 128
+// column owners.  A thread is the only writer of "its" columns of its partition's private table, so the
+// scatter-add is a plain shared-memory read-modify-write in row order; the two tables are merged on the way out.
+// (fp32 shared-memory atomics are compare-and-swap loops and serialise on the few frequent atom types.)
+constexpr int EMB_U = 16;
+__global__ void __launch_bounds__(256) embed_bwd_owner_kernel(const int32_t *__restrict__ ids, const float *__restrict__ dh,
+                                                              float *__restrict__ dW, long rows, int H, int n_types,
+                                                              long rows_per_cta) {
+    extern __shared__ float tab[];   // [2][n_types][H]
+    const int n = n_types * H;
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) tab[i] = 0.f;
+    __syncthreads();
+    const int part = threadIdx.x >> 7, t = threadIdx.x & 127;
+    float *mine = tab + part * n;
+    const long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int c = t; c < H; c += 128) {
+        // partitions interleave blocks of EMB_U rows; the next block's loads are in flight while this one is applied
+        int id[2][EMB_U];
+        float v[2][EMB_U];
+        auto fetch = [&](int b, long r) {
+#pragma unroll
+            for (int u = 0; u < EMB_U; ++u) {
+                const bool ok = r + u < r1;
+                const int x = ok ? __ldg(ids + r + u) : 0;
+                id[b][u] = x < 0 ? 0 : (x >= n_types ? n_types - 1 : x);
+                v[b][u] = ok ? __ldg(dh + (r + u) * H + c) : 0.f;
+            }
+        };
+        long r = r0 + part * EMB_U;
+        if (r < r1) fetch(0, r);
+        for (; r < r1; r += 4 * EMB_U) {
+            if (r + 2 * EMB_U < r1) fetch(1, r + 2 * EMB_U);
+#pragma unroll
+            for (int u = 0; u < EMB_U; ++u) mine[id[0][u] * H + c] += v[0][u];
+            if (r + 2 * EMB_U >= r1) break;
+            if (r + 4 * EMB_U < r1) fetch(0, r + 4 * EMB_U);
+#pragma unroll
+            for (int u = 0; u < EMB_U; ++u) mine[id[1][u] * H + c] += v[1][u];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = tab[i] + tab[n + i];
+        if (v != 0.f) atomicAdd(dW + i, v);
+    }
+}
+
 // ---- sigmoid cross entropy ------------------------------------------------------
 __global__ void __launch_bounds__(256) sce_kernel(const float *__restrict__ x, const int32_t *__restrict__ t,
                                                   float *__restrict__ loss, float *__restrict__ dx, long n, float inv_count) {
@@ -194,6 +241,16 @@ extern "C" int bmp_embed_backward(const int32_t *atoms, const float *dh, float *
     if (!atoms || !dh || !d_embed_W) { set_error("bmp_embed_backward: null pointer"); return BMP_EINVAL; }
     if (rows <= 0) return BMP_OK;
     size_t smem = (size_t)n_atom_types * hidden * sizeof(float);
+    if (2 * smem <= 200 * 1024) {
+        const int ctas = 148;
+        long rpc = ((long)rows + ctas - 1) / ctas;
+        rpc = (rpc + 2 * EMB_U - 1) / (2 * EMB_U) * (2 * EMB_U);
+        const int grid = (int)(((long)rows + rpc - 1) / rpc);
+        cudaFuncSetAttribute(embed_bwd_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+        embed_bwd_owner_kernel<<<grid, 256, 2 * smem, (cudaStream_t)stream>>>(atoms, dh, d_embed_W, rows, hidden, n_atom_types, rpc);
+        count_launch();
+        return check_launch("embed_bwd_owner_kernel");
+    }
     if (smem > 200 * 1024) { set_error("bmp_embed_backward: table %d x %d does not fit shared memory", n_atom_types, hidden); return BMP_ESHAPE; }
     int grid = 148 * 2;
     long rpc = ((long)rows + grid - 1) / grid;
