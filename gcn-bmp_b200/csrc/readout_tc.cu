@@ -40,6 +40,16 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
     return v[0];
 }
 
+// BF16-mode gate math: tanh.approx based (as in the encoder epilogues)
+__device__ __forceinline__ float act_fast(int act, float x) {
+    switch (act) {
+        case BMP_ACT_TANH: return tanh_fast(x);
+        case BMP_ACT_RELU: return x > 0.f ? x : 0.f;
+        case BMP_ACT_SIGMOID: return sigmoid_fast(x);
+        default: return x;
+    }
+}
+
 template <int H, int O, bool BWD>
 __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
     constexpr int TILE_BYTES = O * 128;               // forward weight tile [O n][64 k]
@@ -148,22 +158,30 @@ __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
                 return (mg < a.mb && at < a.N) ? (long)mg * a.N + at : -1L;
             };
             // ---- X = [h | h0] -> bf16 panels (coalesced float4 loads, 8 in flight per thread) ----
-            for (int kp = 0; kp < KPX; ++kp) {
-                const float *src = (kp * 64 < H) ? a.h : a.h0;
-                const int c0 = (kp * 64) % H;
-                float4 v[8];
+            for (int kp0 = 0; kp0 < KPX; kp0 += 2) {          // two panels (16 float4 per thread) in flight
+                float4 v[2][8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = u * NEPI + tid, r = idx >> 4, c4 = (idx & 15) * 4;
-                    const int mg = tile * 2 + (r >> 6), at = r & 63;
-                    v[u] = (mg < a.mb && at < a.N) ? __ldg(reinterpret_cast<const float4 *>(src + ((long)mg * a.N + at) * H + c0 + c4))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p = 0; p < 2; ++p) {
+                    const int kp = kp0 + p;
+                    const float *src = (kp * 64 < H) ? a.h : a.h0;
+                    const int c0 = (kp * 64) % H;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int idx = u * NEPI + tid, r = idx >> 4, c4 = (idx & 15) * 4;
+                        const int mg = tile * 2 + (r >> 6), at = r & 63;
+                        v[p][u] = (kp < KPX && mg < a.mb && at < a.N) ? __ldg(reinterpret_cast<const float4 *>(src + ((long)mg * a.N + at) * H + c0 + c4))
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = u * NEPI + tid, r = idx >> 4, c4 = (idx & 15) * 4;
-                    *reinterpret_cast<uint2 *>(smem + OFF_X + kp * PANEL_BYTES + sw128(r, c4)) =
-                        make_uint2(pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
+                for (int p = 0; p < 2; ++p) {
+                    if (kp0 + p >= KPX) break;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int idx = u * NEPI + tid, r = idx >> 4, c4 = (idx & 15) * 4;
+                        *reinterpret_cast<uint2 *>(smem + OFF_X + (kp0 + p) * PANEL_BYTES + sw128(r, c4)) =
+                            make_uint2(pack_bf16(v[p][u].x, v[p][u].y), pack_bf16(v[p][u].z, v[p][u].w));
+                    }
                 }
             }
             fence_proxy_async();
@@ -177,13 +195,22 @@ __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
                 tc_ld32(t_lane + colbase + cc, vu);
                 tc_ld32(t_lane + O + colbase + cc, vv);
                 tc_wait_ld();
+                float bi[32], bj[32];          // biases of this thread's columns (16-byte loads)
+#pragma unroll
+                for (int x = 0; x < 32; x += 4) {
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 p4 = a.b_i ? __ldg(reinterpret_cast<const float4 *>(a.b_i + colbase + cc + x)) : z4;
+                    const float4 q4 = a.b_j ? __ldg(reinterpret_cast<const float4 *>(a.b_j + colbase + cc + x)) : z4;
+                    bi[x] = p4.x; bi[x + 1] = p4.y; bi[x + 2] = p4.z; bi[x + 3] = p4.w;
+                    bj[x] = q4.x; bj[x + 1] = q4.y; bj[x + 2] = q4.z; bj[x + 3] = q4.w;
+                }
                 if (!BWD) {
                     float gv[32];
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
-                        const float u = __uint_as_float(vu[x]) + (a.b_i ? __ldg(a.b_i + colbase + cc + x) : 0.f);
-                        const float v = __uint_as_float(vv[x]) + (a.b_j ? __ldg(a.b_j + colbase + cc + x) : 0.f);
-                        gv[x] = mk * sigmoidf_(u) * act_fwd(a.act, v);
+                        const float u = __uint_as_float(vu[x]) + bi[x];
+                        const float v = __uint_as_float(vv[x]) + bj[x];
+                        gv[x] = mk * sigmoid_fast(u) * act_fast(a.act, v);
                     }
                     const float s = warp_reduce_scatter32(gv, lane);
                     red[q * O + colbase + cc + lane] = s;
@@ -193,14 +220,14 @@ __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
                         const int col = colbase + cc + x;
-                        const float u = __uint_as_float(vu[x]) + (a.b_i ? __ldg(a.b_i + col) : 0.f);
-                        const float v = __uint_as_float(vv[x]) + (a.b_j ? __ldg(a.b_j + col) : 0.f);
+                        const float u = __uint_as_float(vu[x]) + bi[x];
+                        const float v = __uint_as_float(vv[x]) + bj[x];
                         float ds = 0.f;
                         if (mlive) {
                             const float go = __ldg(a.gin + (long)molg * O + col);
                             ds = __ldg(a.dg + (long)molg * O + col) * act_bwd(a.act_agg, go, go);
                         }
-                        const float su = sigmoidf_(u), av = act_fwd(a.act, v);
+                        const float su = sigmoid_fast(u), av = act_fast(a.act, v);
                         du[x] = ds * mk * av * su * (1.f - su);
                         dv[x] = ds * mk * su * act_bwd(a.act, v, av);
                     }
@@ -341,6 +368,7 @@ int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_ag
         return BMP_ESHAPE;
     }
     if (!ws || ws_bytes < bmp_readout_tc_workspace_bytes(H, O)) { set_error("readout tcgen05 path: workspace too small"); return BMP_EINVAL; }
+    if (!aligned16({b_i, b_j, h, h0})) { set_error("readout tcgen05 path: h, h0, b_i, b_j must be 16-byte aligned"); return BMP_ESHAPE; }
     cudaStream_t st = (cudaStream_t)stream;
     rtc::Args k = {};
     k.mb = mb; k.N = N; k.H = H; k.O = O; k.Kcat = h0 ? 2 * H : H; k.Kj = variant == BMP_READOUT_R2 ? H : k.Kcat;
