@@ -227,22 +227,26 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 TS(0);
                 if (t == 0 && tile + (int)gridDim.x < n_tiles) prefetch_adjacency_l2<NE>(a.adj, tile + gridDim.x, a.mb, a.N, tid);
                 // ---- phase A: gate derivatives ----
-                uint4 sp[NC / 8];            // state of the step, packed bf16 (stash v2), reused by phase B
                 if (V2) {
-                    // all gate values of the step in one burst of coalesced 16-byte loads (thread-native bf16 order)
-                    uint4 zp[NC / 8], hp[NC / 8];
+                    // gate values of the step: coalesced 16-byte loads in the thread-native bf16 order, two 16-column halves
+                    // (L2-resident: prefetched during the previous step) so the live set stays under the 96-register budget
                     const uint8_t *bz = a.st.zn(t, tile, 0, H), *bh = a.st.zn(t, tile, 1, H), *bs = a.st.zn(t, tile, 3, H);
 #pragma unroll
-                    for (int j = 0; j < NC / 8; ++j) {
-                        zp[j] = __ldg(reinterpret_cast<const uint4 *>(bz + ((size_t)j * NE + tid) * 16));
-                        hp[j] = __ldg(reinterpret_cast<const uint4 *>(bh + ((size_t)j * NE + tid) * 16));
-                        sp[j] = stateful ? __ldg(reinterpret_cast<const uint4 *>(bs + ((size_t)j * NE + tid) * 16)) : make_uint4(0, 0, 0, 0);
+                    for (int half = 0; half < NC / 16; ++half) {
+                    uint4 zp[2], hp[2], sp[2];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const size_t o = ((size_t)(2 * half + g) * NE + tid) * 16;
+                        zp[g] = __ldg(reinterpret_cast<const uint4 *>(bz + o));
+                        hp[g] = __ldg(reinterpret_cast<const uint4 *>(bh + o));
+                        sp[g] = stateful ? __ldg(reinterpret_cast<const uint4 *>(bs + o)) : make_uint4(0, 0, 0, 0);
                     }
 #pragma unroll
-                    for (int j = 0; j < NC / 8; ++j) {
-                        const __nv_bfloat162 *z2 = reinterpret_cast<const __nv_bfloat162 *>(&zp[j]);
-                        const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&hp[j]);
-                        const __nv_bfloat162 *s2 = reinterpret_cast<const __nv_bfloat162 *>(&sp[j]);
+                    for (int g = 0; g < 2; ++g) {
+                        const int j = 2 * half + g;
+                        const __nv_bfloat162 *z2 = reinterpret_cast<const __nv_bfloat162 *>(&zp[g]);
+                        const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&hp[g]);
+                        const __nv_bfloat162 *s2 = reinterpret_cast<const __nv_bfloat162 *>(&sp[g]);
                         float dz[8], dh[8];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                         *reinterpret_cast<uint4 *>(smem + C::OFF_D + (2 * KP + (kk >> 6)) * PANEL_BYTES + sw128(row, kk & 63)) = ph;
                         if (!stateful)   // delta_r panel of a stateless step: zeros (the merged W_r contraction reads it)
                             *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = make_uint4(0, 0, 0, 0);
+                    }
                     }
                 } else {
                 if (t > 0 && live && !V2) {   // pull the next step's stash lines towards L2 while this step computes
@@ -320,37 +325,50 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 TS(1);
                 // ---- phase B: through U and the reset gate ----
                 if (V2) {
-                    uint4 rp[NC / 8];
-                    if (stateful) {   // requested before waiting for q: the latency overlaps MMA-q
-                        const uint8_t *br = a.st.zn(t, tile, 2, H);
+                    // 16-column halves keep the live set under the 96-register budget: r and (again, L2-resident) the state of
+                    // the first half are requested before waiting for q (the latency overlaps MMA-q), the second half's while
+                    // the first is consumed
+                    const uint8_t *br = a.st.zn(t, tile, 2, H), *bs = a.st.zn(t, tile, 3, H);
+                    uint4 rp[2], sp[2];
+                    auto load_rs = [&](int half) {
 #pragma unroll
-                        for (int j = 0; j < NC / 8; ++j) rp[j] = __ldg(reinterpret_cast<const uint4 *>(br + ((size_t)j * NE + tid) * 16));
-                    }
+                        for (int j = 0; j < 2; ++j) {
+                            rp[j] = __ldg(reinterpret_cast<const uint4 *>(br + ((size_t)(2 * half + j) * NE + tid) * 16));
+                            sp[j] = __ldg(reinterpret_cast<const uint4 *>(bs + ((size_t)(2 * half + j) * NE + tid) * 16));
+                        }
+                    };
+                    if (stateful) load_rs(0);
                     mbar_wait(BAR(B_Q), par);
                     tc_fence_after();
                     TS(2);
                     if (stateful) {
 #pragma unroll
-                        for (int cc = 0; cc < NC; cc += 32) {
-                            tc_ld32(t_lane + COL_Q + colbase + cc, v);
+                        for (int half = 0; half < 2; ++half) {
+                            uint32_t w[16];
+                            tc_ld16(t_lane + COL_Q + colbase + 16 * half, w);
                             tc_wait_ld();
+                            float dr[16];
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const int j = (cc >> 3) + g;
-                                const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rp[j]);
-                                const __nv_bfloat162 *s2 = reinterpret_cast<const __nv_bfloat162 *>(&sp[j]);
-                                float dr[8];
+                            for (int g = 0; g < 2; ++g) {
+                                const int j = 2 * half + g;
+                                const __nv_bfloat162 *r2 = reinterpret_cast<const __nv_bfloat162 *>(&rp[g]);
+                                const __nv_bfloat162 *s2 = reinterpret_cast<const __nv_bfloat162 *>(&sp[g]);
 #pragma unroll
                                 for (int x = 0; x < 4; ++x) {
                                     const float2 rr = __bfloat1622float2(r2[x]), ss = __bfloat1622float2(s2[x]);
-                                    const float q0 = live ? __uint_as_float(v[8 * g + 2 * x]) : 0.f, q1 = live ? __uint_as_float(v[8 * g + 2 * x + 1]) : 0.f;
+                                    const float q0 = live ? __uint_as_float(w[8 * g + 2 * x]) : 0.f, q1 = live ? __uint_as_float(w[8 * g + 2 * x + 1]) : 0.f;
                                     acc[8 * j + 2 * x] += q0 * rr.x;
                                     acc[8 * j + 2 * x + 1] += q1 * rr.y;
-                                    dr[2 * x] = q0 * ss.x * rr.x * (1.f - rr.x);
-                                    dr[2 * x + 1] = q1 * ss.y * rr.y * (1.f - rr.y);
+                                    dr[8 * g + 2 * x] = q0 * ss.x * rr.x * (1.f - rr.x);
+                                    dr[8 * g + 2 * x + 1] = q1 * ss.y * rr.y * (1.f - rr.y);
                                 }
-                                const int kk = colbase + 8 * j;
-                                uint4 pr = make_uint4(pack_bf16(dr[0], dr[1]), pack_bf16(dr[2], dr[3]), pack_bf16(dr[4], dr[5]), pack_bf16(dr[6], dr[7]));
+                            }
+                            if (half == 0) load_rs(1);
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const int kk = colbase + 8 * (2 * half + g);
+                                uint4 pr = make_uint4(pack_bf16(dr[8 * g], dr[8 * g + 1]), pack_bf16(dr[8 * g + 2], dr[8 * g + 3]),
+                                                      pack_bf16(dr[8 * g + 4], dr[8 * g + 5]), pack_bf16(dr[8 * g + 6], dr[8 * g + 7]));
                                 *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(row, kk & 63)) = pr;
                             }
                         }
@@ -424,6 +442,10 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 }
                 warp_arrive(BAR(B_DMRDY), lane);
                 TS(5);
+                if (V2 && t > 0) {      // while MMA-P runs: gate values of the NEXT step (t-1) towards L2 (four 128 x H bf16 blocks)
+                    const char *nx = reinterpret_cast<const char *>(a.st.zn(t - 1, tile, 0, H));
+                    for (int off = tid * 128; off < 4 * 128 * H * 2; off += NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
+                }
                 // ---- phase D: P accumulators -> bf16 A-operand panels (two K halves) + fp32 stash ----
                 for (int p = 0; p < 2; ++p) {
                     if (p == 1) mbar_wait(BAR(B_PFREE), par);
@@ -466,9 +488,13 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 {
                     float *ext = a.dHs + ((long)(V2 ? 0 : t) * rows_total + grow) * H + colbase;
                     const bool has_ext = live && (V2 ? t == 0 : a.ext_flags[t] != 0);
-                    float4 e4[NC / 4];          // requested before waiting for the accumulator: the latency overlaps MMA-dh
+                    if (has_ext) {      // requested and folded in before waiting for the accumulator: the latency overlaps MMA-dh
 #pragma unroll
-                    for (int x = 0; x < NC / 4; ++x) e4[x] = has_ext ? __ldg(reinterpret_cast<const float4 *>(ext) + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int x = 0; x < NC; x += 4) {
+                            const float4 e = __ldg(reinterpret_cast<const float4 *>(ext + x));
+                            acc[x] += e.x; acc[x + 1] += e.y; acc[x + 2] += e.z; acc[x + 3] += e.w;
+                        }
+                    }
                     mbar_wait(BAR(B_DH), par);
                     tc_fence_after();
                     TS(11);
@@ -477,13 +503,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                         tc_ld32(t_lane + COL_DHX + colbase + cc, v);
                         tc_wait_ld();
 #pragma unroll
-                        for (int x = 0; x < 32; x += 4) {
-                            const float4 e = e4[(cc + x) >> 2];
-                            acc[cc + x] += __uint_as_float(v[x]) + e.x;
-                            acc[cc + x + 1] += __uint_as_float(v[x + 1]) + e.y;
-                            acc[cc + x + 2] += __uint_as_float(v[x + 2]) + e.z;
-                            acc[cc + x + 3] += __uint_as_float(v[x + 3]) + e.w;
-                        }
+                        for (int x = 0; x < 32; ++x) acc[cc + x] += __uint_as_float(v[x]);
                     }
                     if (t == 0) {
                         // dL/dh_0 of the tile: coalesced rows through a transposition block (the delta panels are idle:

@@ -17,6 +17,6 @@ for r in rows[hi + 1:]:
             pass
 tot = sum(l[0] for l in lines)
 print("total samples", tot)
-for s, ln, src, st in sorted(lines, reverse=True)[: int(sys.argv[1]) if len(sys.argv) > 1 else 30]:
+for s, ln, src, st in sorted(lines, key=lambda l: l[:3], reverse=True)[: int(sys.argv[1]) if len(sys.argv) > 1 else 30]:
     top = sorted(((int(v), k) for k, v in st.items() if v.isdigit()), reverse=True)[:2]
     print("%6d %5.1f%%  L%-4d %-70s %s" % (s, 100.0 * s / tot, ln, src[:70], " ".join("%s=%d" % (k[6:], v) for v, k in top)))
