@@ -58,6 +58,7 @@ struct Cfg {
 };
 
 __host__ __device__ inline int f32_floats(int H, int hd, bool bwd) {
+    hd = hd <= 8 ? 8 : 16;                          // padded head count HP
     int n = AT * CLD + 2 * AT * PLD + 4;            // Cs, L1t, L2p
     n += 4 * hd * AT;                               // lt1, lt2, H1, H2
     n += 4 * AT + 2 * H;                            // attn1, attn2, v1, v2, p1, p2
@@ -85,9 +86,12 @@ __device__ __forceinline__ uint4 pack8(const float *v) {
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-template <int H, bool BWD>
+// HP = padded head count (8 or 16): the head arrays are atom-major [64][HP] with the heads contiguous, so every
+// rank-head product is a few 16-byte loads per atom (mostly warp-wide broadcasts).
+template <int H, bool BWD, int HP>
 __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
     using C = Cfg<H, BWD>;
+    constexpr int HS = HP, HQ = HP / 4;
     constexpr int KP = C::KP;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -101,10 +105,10 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
     float *Cs = fp; fp += AT * CLD;
     float *L1t = fp; fp += AT * PLD;
     float *L2p = fp; fp += AT * PLD + 4;
-    float *lt1 = fp; fp += hd * AT;
-    float *lt2 = fp; fp += hd * AT;
-    float *H1 = fp; fp += hd * AT;
-    float *H2 = fp; fp += hd * AT;
+    float *lt1 = fp; fp += HS * AT;
+    float *lt2 = fp; fp += HS * AT;
+    float *H1 = fp; fp += HS * AT;
+    float *H2 = fp; fp += HS * AT;
     float *attn1 = fp; fp += AT;
     float *attn2 = fp; fp += AT;
     float *v1 = fp; fp += AT;
@@ -113,8 +117,8 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
     float *p2 = fp; fp += H;
     float *st4 = fp; fp += 4 * AT;          // forward: m2 | 1/s2 | m1 | 1/s1 ; backward: t1 | t2 | cs | rsum
     float *part = fp; fp += 16 * AT;        // partial column statistics [2][8][64]
-    float *dp1 = fp, *dp2 = fp + H, *dpre1 = fp + 2 * H, *dpre2 = dpre1 + hd * AT;
-    float *gwa1 = dpre2 + hd * AT, *gwa2 = gwa1 + 16, *gb = gwa2 + 16;
+    float *dp1 = fp, *dp2 = fp + H, *dpre1 = fp + 2 * H, *dpre2 = dpre1 + HS * AT;
+    float *gwa1 = dpre2 + HS * AT, *gwa2 = gwa1 + 16, *gb = gwa2 + 16;
     const int f32n = f32_floats(H, hd, BWD);
     const uint32_t s_bar = sbase + C::OFF_F + f32n * 4;
     auto BAR = [&](int i) { return s_bar + 8u * i; };
@@ -280,6 +284,12 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             warp_arrive(BAR(B_XRDY), lane);
             CTS(1);
+            if (pair + (int)gridDim.x < a.mb) {       // next pair of this CTA: its atom states towards L2
+                const long np = pair + gridDim.x;
+                const char *b1 = reinterpret_cast<const char *>(a.atoms_1 + np * N1 * H), *b2 = reinterpret_cast<const char *>(a.atoms_2 + np * N2 * H);
+                for (int off = tid * 128; off < N1 * H * 4; off += NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + off));
+                for (int off = tid * 128; off < N2 * H * 4; off += NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + off));
+            }
             // ---- G1 epilogue: Q (rows of a2) -> bf16 B-operand blocks; head projections and V terms -> fp32
             mbar_wait(BAR(B_G1), par);
             tc_fence_after();
@@ -303,10 +313,11 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 tc_ld16(t_lane + C::COL_D1 + H + (q >= 2 ? 16 : 0), w);
                 tc_wait_ld();
                 const int n = row & 63;
-                float *lt = q >= 2 ? lt2 : lt1;
+                float *lt = (q >= 2 ? lt2 : lt1) + n * HS;      // columns >= head are zero (zero weight rows); 15 is the V term
 #pragma unroll
-                for (int d = 0; d < MAXHD; ++d)
-                    if (d < hd) lt[d * AT + n] = __uint_as_float(w[d]);
+                for (int d4 = 0; d4 < HQ; ++d4)
+                    *reinterpret_cast<float4 *>(lt + 4 * d4) = make_float4(__uint_as_float(w[4 * d4]), __uint_as_float(w[4 * d4 + 1]), __uint_as_float(w[4 * d4 + 2]),
+                                                                           4 * d4 + 3 == 15 ? 0.f : __uint_as_float(w[4 * d4 + 3]));
                 (q >= 2 ? v2 : v1)[n] = __uint_as_float(w[15]);
             }
             if (BWD) {
@@ -369,12 +380,32 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 }
                 part[pt * AT + i] = m;
                 part[8 * AT + pt * AT + i] = s;
-                for (int j = warp; j < AT; j += EPW) {
-                    const float x0 = (j < N1 && lane < N2) ? Cs[j * CLD + lane] : -INFINITY;
-                    const float x1 = (j < N1 && lane + 32 < N2) ? Cs[j * CLD + lane + 32] : -INFINITY;
-                    const float mm = warp_max(fmaxf(x0, x1));
-                    const float ss = warp_sum((x0 > -INFINITY ? __expf(x0 - mm) : 0.f) + (x1 > -INFINITY ? __expf(x1 - mm) : 0.f));
-                    if (lane == 0) { m2[j] = mm; is2[j] = ss > 0.f ? 1.f / ss : 0.f; }
+                {   // rows j = warp + 16 k: the four reductions run in lockstep (independent shuffle chains)
+                    float x0[4], x1[4], mx[4], sm[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = warp + EPW * k;
+                        x0[k] = (j < N1 && lane < N2) ? Cs[j * CLD + lane] : -INFINITY;
+                        x1[k] = (j < N1 && lane + 32 < N2) ? Cs[j * CLD + lane + 32] : -INFINITY;
+                        mx[k] = fmaxf(x0[k], x1[k]);
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        sm[k] = (x0[k] > -INFINITY ? __expf(x0[k] - mx[k]) : 0.f) + (x1[k] > -INFINITY ? __expf(x1[k] - mx[k]) : 0.f);
+#pragma unroll
+                    for (int o = 16; o; o >>= 1)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) sm[k] += __shfl_xor_sync(0xffffffffu, sm[k], o);
+                    if (lane < 4) {
+                        const float mm = lane == 0 ? mx[0] : (lane == 1 ? mx[1] : (lane == 2 ? mx[2] : mx[3]));
+                        const float ss = lane == 0 ? sm[0] : (lane == 1 ? sm[1] : (lane == 2 ? sm[2] : sm[3]));
+                        m2[warp + EPW * lane] = mm;
+                        is2[warp + EPW * lane] = ss > 0.f ? 1.f / ss : 0.f;
+                    }
                 }
             }
             EPI_SYNC();
@@ -400,28 +431,47 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             EPI_SYNC();
             CTS(6);
-            // ---- H_1[j][d] = tanh(lt_1[j][d] + sum_i L_1[j][i] lt_2[i][d]) ; H_2 likewise
-            for (int idx = tid; idx < 2 * hd * AT; idx += NE) {
-                const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
-                float s;
-                if (!which) {
-                    s = lt1[d * AT + n];
-                    for (int i = 0; i < N2; ++i) s += L1t[i * PLD + n] * lt2[d * AT + i];
-                    H1[d * AT + n] = tanhf(s);
-                } else {
-                    s = lt2[d * AT + n];
-                    for (int j = 0; j < N1; ++j) s += L2p[j * PLD + n] * lt1[d * AT + j];
-                    H2[d * AT + n] = tanhf(s);
+            // ---- H_1[j][:] = tanh(lt_1[j][:] + sum_i L_1[j][i] lt_2[i][:]) ; H_2 likewise.  Four threads per atom, each a
+            // quarter of the inner index (interleaved), all heads in registers; quad shuffle reduction.
+            {
+                const int which = tid >> 8, n = (tid >> 2) & 63, pt = tid & 3;
+                const float *Lw = which ? L2p : L1t, *other = which ? lt1 : lt2;
+                float acc[HP];
+#pragma unroll
+                for (int d = 0; d < HP; ++d) acc[d] = 0.f;
+#pragma unroll 4
+                for (int mm = 0; mm < 16; ++mm) {
+                    const int m = 4 * mm + pt;
+                    const float l = Lw[m * PLD + n];
+#pragma unroll
+                    for (int d4 = 0; d4 < HQ; ++d4) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(other + m * HS + 4 * d4);
+                        acc[4 * d4] = fmaf(l, r4.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(l, r4.y, acc[4 * d4 + 1]);
+                        acc[4 * d4 + 2] = fmaf(l, r4.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(l, r4.w, acc[4 * d4 + 3]);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < HP; ++d) {
+                    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 1);
+                    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 2);
+                }
+                const float *self = (which ? lt2 : lt1) + n * HS;
+                float *Hk = (which ? H2 : H1) + n * HS;
+#pragma unroll
+                for (int d4 = 0; d4 < HQ; ++d4) {       // lane pt finishes head 4*d4 + pt
+                    const float v = pt == 0 ? acc[4 * d4] : (pt == 1 ? acc[4 * d4 + 1] : (pt == 2 ? acc[4 * d4 + 2] : acc[4 * d4 + 3]));
+                    Hk[4 * d4 + pt] = tanh_fast(self[4 * d4 + pt] + v);
                 }
             }
             EPI_SYNC();
             CTS(7);
             if (tid < 2 * AT) {
                 const int n = tid & 63;
-                const float *Hk = tid < AT ? H1 : H2, *wa = tid < AT ? a.wa_1 : a.wa_2;
-                float s = 0.f;
-                for (int d = 0; d < hd; ++d) s += wa[d] * Hk[d * AT + n];
-                (tid < AT ? attn1 : attn2)[n] = s;
+                const float *Hk = (tid < AT ? H1 : H2) + n * HS, *wa = tid < AT ? a.wa_1 : a.wa_2;
+                float sc = 0.f;
+#pragma unroll
+                for (int d = 0; d < HP; ++d) sc += d < hd ? __ldg(wa + d) * Hk[d] : 0.f;
+                (tid < AT ? attn1 : attn2)[n] = sc;
             }
             EPI_SYNC();
             if (warp < 2) {
@@ -473,23 +523,30 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             // ======================================================== backward
             float *t1 = st4, *t2 = st4 + AT, *cs = st4 + 2 * AT, *rsum = st4 + 3 * AT;
-            // pooled atoms for d W_j ; dp_k[h] = sum_o W_j[o][h] dc_k[o]
-            if (tid < 2 * H) {
-                const int which = tid >= H, h = which ? tid - H : tid;
-                (which ? a.P2 : a.P1)[(long)pair * H + h] = (which ? p2 : p1)[h];
-                const float *dc = (which ? a.dc2 : a.dc1) + (long)pair * O;
+            // pooled atoms for d W_j ; dp_k[h] = sum_o W_j[o][h] dc_k[o]: thread pair (two halves of the o range), eight
+            // coalesced weight rows in flight each, combined through shared memory
+            {
+                const int oh = tid >> 8, e = tid & 255;
+                const int which = e >= H, h = which ? e - H : e;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                int o = 0;
-                for (; o + 8 <= O; o += 8) {          // eight coalesced weight rows in flight
-                    float w[8];
+                if (e < 2 * H) {
+                    if (oh == 0) (which ? a.P2 : a.P1)[(long)pair * H + h] = (which ? p2 : p1)[h];
+                    const float *dc = (which ? a.dc2 : a.dc1) + (long)pair * O;
+                    const int ob = ((O + 1) / 2 + 7) & ~7, o_end = oh ? O : (ob < O ? ob : O);
+                    int o = oh ? (ob < O ? ob : O) : 0;
+                    for (; o + 8 <= o_end; o += 8) {
+                        float w[8];
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) w[x] = __ldg(a.W_j + (long)(o + x) * H + h);
-                    const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dc + o)), d1 = __ldg(reinterpret_cast<const float4 *>(dc + o) + 1);
-                    s0 = fmaf(w[0], d0.x, s0); s1 = fmaf(w[1], d0.y, s1); s2 = fmaf(w[2], d0.z, s2); s3 = fmaf(w[3], d0.w, s3);
-                    s0 = fmaf(w[4], d1.x, s0); s1 = fmaf(w[5], d1.y, s1); s2 = fmaf(w[6], d1.z, s2); s3 = fmaf(w[7], d1.w, s3);
+                        for (int x = 0; x < 8; ++x) w[x] = __ldg(a.W_j + (long)(o + x) * H + h);
+                        const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dc + o)), d1 = __ldg(reinterpret_cast<const float4 *>(dc + o) + 1);
+                        s0 = fmaf(w[0], d0.x, s0); s1 = fmaf(w[1], d0.y, s1); s2 = fmaf(w[2], d0.z, s2); s3 = fmaf(w[3], d0.w, s3);
+                        s0 = fmaf(w[4], d1.x, s0); s1 = fmaf(w[5], d1.y, s1); s2 = fmaf(w[6], d1.z, s2); s3 = fmaf(w[7], d1.w, s3);
+                    }
+                    for (; o < o_end; ++o) s0 = fmaf(__ldg(a.W_j + (long)o * H + h), __ldg(dc + o), s0);
                 }
-                for (; o < O; ++o) s0 = fmaf(__ldg(a.W_j + (long)o * H + h), __ldg(dc + o), s0);
-                (which ? dp2 : dp1)[h] = (s0 + s1) + (s2 + s3);
+                if (oh == 1 && e < 2 * H) part[e] = (s0 + s1) + (s2 + s3);
+                EPI_SYNC();
+                if (oh == 0 && e < 2 * H) (which ? dp2 : dp1)[h] = (s0 + s1) + (s2 + s3) + part[e];
             }
             EPI_SYNC();
             CTS(10);
@@ -523,70 +580,115 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             EPI_SYNC();
             CTS(11);
-            // dpre_k[d][n] = ds_k[n] wa_k[d] (1 - H_k^2) ; d wa_k[d] += sum_n ds_k[n] H_k[n][d]
-            for (int idx = tid; idx < 2 * hd * AT; idx += NE) {
-                const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
-                const float hv = (which ? H2 : H1)[d * AT + n];
-                (which ? dpre2 : dpre1)[d * AT + n] = (which ? t2 : t1)[n] * (which ? a.wa_2 : a.wa_1)[d] * (1.f - hv * hv);
+            // dpre_k[n][:] = ds_k[n] wa_k[:] (1 - H_k^2) ; d wa_k[d] += sum_n ds_k[n] H_k[n][d]
+            for (int idx = tid; idx < 2 * AT * HQ; idx += NE) {
+                const int which = idx / (AT * HQ), r = idx % (AT * HQ), n = r / HQ, d4 = r % HQ;
+                const float4 hv = *reinterpret_cast<const float4 *>((which ? H2 : H1) + n * HS + 4 * d4);
+                const float *wa = which ? a.wa_2 : a.wa_1;
+                const float ds = (which ? t2 : t1)[n];
+                float4 o;
+                o.x = 4 * d4 + 0 < hd ? ds * __ldg(wa + 4 * d4 + 0) * (1.f - hv.x * hv.x) : 0.f;
+                o.y = 4 * d4 + 1 < hd ? ds * __ldg(wa + 4 * d4 + 1) * (1.f - hv.y * hv.y) : 0.f;
+                o.z = 4 * d4 + 2 < hd ? ds * __ldg(wa + 4 * d4 + 2) * (1.f - hv.z * hv.z) : 0.f;
+                o.w = 4 * d4 + 3 < hd ? ds * __ldg(wa + 4 * d4 + 3) * (1.f - hv.w * hv.w) : 0.f;
+                *reinterpret_cast<float4 *>((which ? dpre2 : dpre1) + n * HS + 4 * d4) = o;
             }
             for (int r = warp; r < 2 * hd; r += EPW) {
                 const int which = r >= hd, d = which ? r - hd : r;
-                const float *Hk = (which ? H2 : H1) + d * AT, *ds = which ? t2 : t1;
-                const float s = warp_sum(ds[lane] * Hk[lane] + ds[lane + 32] * Hk[lane + 32]);
-                if (lane == 0) (which ? gwa2 : gwa1)[d] += s;
+                const float *Hk = (which ? H2 : H1) + d, *ds = which ? t2 : t1;
+                const float sw = warp_sum(ds[lane] * Hk[lane * HS] + ds[lane + 32] * Hk[(lane + 32) * HS]);
+                if (lane == 0) (which ? gwa2 : gwa1)[d] += sw;
             }
             EPI_SYNC();
             CTS(12);
-            // u1[i] = sum_j L_1[j][i] dL_1[j][i] ; u2[j] = sum_i L_2[i][j] dL_2[i][j]   (four threads per output)
+            // u1[i] = sum_j L_1[j][i] dL_1[j][i], dL_1[j][i] = dpre1[j] . lt2[i] ; u2[j] = sum_i L_2[i][j] (dpre2[i] . lt1[j])
+            // four threads per output (a quarter of the inner index each), the output's own head row in registers
             {
-                const int out = tid >> 2, pt = tid & 3;
+                const int out = tid >> 2, pt = tid & 3, which = out >= AT, n = out & 63;
+                const float *Lw = which ? L2p : L1t;            // L_1[j][i] at L1t[i*PLD + j] ; L_2[i][j] at L2p[j*PLD + i]
+                const float *other = which ? dpre2 : dpre1;
+                float own[HP];
+#pragma unroll
+                for (int d4 = 0; d4 < HQ; ++d4) {
+                    const float4 r4 = *reinterpret_cast<const float4 *>((which ? lt1 : lt2) + n * HS + 4 * d4);
+                    own[4 * d4] = r4.x; own[4 * d4 + 1] = r4.y; own[4 * d4 + 2] = r4.z; own[4 * d4 + 3] = r4.w;
+                }
                 float u = 0.f;
-                if (out < AT) {
-                    const int i = out;
-                    for (int j = pt * 16; j < pt * 16 + 16; ++j) {
-                        float dl = 0.f;
-                        for (int d = 0; d < hd; ++d) dl += dpre1[d * AT + j] * lt2[d * AT + i];
-                        u += L1t[i * PLD + j] * dl;
+#pragma unroll 4
+                for (int mm = 0; mm < 16; ++mm) {
+                    const int m = 4 * mm + pt;
+                    float dl = 0.f;
+#pragma unroll
+                    for (int d4 = 0; d4 < HQ; ++d4) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(other + m * HS + 4 * d4);
+                        dl = fmaf(r4.x, own[4 * d4], fmaf(r4.y, own[4 * d4 + 1], fmaf(r4.z, own[4 * d4 + 2], fmaf(r4.w, own[4 * d4 + 3], dl))));
                     }
-                } else {
-                    const int j = out - AT;
-                    for (int i = pt * 16; i < pt * 16 + 16; ++i) {
-                        float dl = 0.f;
-                        for (int d = 0; d < hd; ++d) dl += dpre2[d * AT + i] * lt1[d * AT + j];
-                        u += L2p[j * PLD + i] * dl;
-                    }
+                    u = fmaf(Lw[n * PLD + m], dl, u);
                 }
                 u += __shfl_xor_sync(0xffffffffu, u, 1);
                 u += __shfl_xor_sync(0xffffffffu, u, 2);
                 if (pt == 0) part[out] = u;          // u1 at [0,64), u2 at [64,128)
             }
-            // total d lt_k (direct + through the other molecule's H) -> over H_k (smem)
-            for (int idx = tid; idx < 2 * hd * AT; idx += NE) {
-                const int which = idx / (hd * AT), r = idx % (hd * AT), d = r / AT, n = r % AT;
-                float s;
-                if (!which) {
-                    s = dpre1[d * AT + n];
-                    for (int i = 0; i < N2; ++i) s += L2p[n * PLD + i] * dpre2[d * AT + i];
-                    H1[d * AT + n] = s;
-                } else {
-                    s = dpre2[d * AT + n];
-                    for (int j = 0; j < N1; ++j) s += L1t[n * PLD + j] * dpre1[d * AT + j];
-                    H2[d * AT + n] = s;
+            // total d lt_k (direct + through the other molecule's H) -> over H_k:
+            //   d lt_1[j][:] = dpre1[j][:] + sum_i L_2[i][j] dpre2[i][:] ; d lt_2[i][:] = dpre2[i][:] + sum_j L_1[j][i] dpre1[j][:]
+            {
+                const int which = tid >> 8, n = (tid >> 2) & 63, pt = tid & 3;
+                const float *Lw = which ? L1t : L2p, *other = which ? dpre1 : dpre2;
+                float acc[HP];
+#pragma unroll
+                for (int d = 0; d < HP; ++d) acc[d] = 0.f;
+#pragma unroll 4
+                for (int mm = 0; mm < 16; ++mm) {
+                    const int m = 4 * mm + pt;
+                    const float l = Lw[n * PLD + m];
+#pragma unroll
+                    for (int d4 = 0; d4 < HQ; ++d4) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(other + m * HS + 4 * d4);
+                        acc[4 * d4] = fmaf(l, r4.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(l, r4.y, acc[4 * d4 + 1]);
+                        acc[4 * d4 + 2] = fmaf(l, r4.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(l, r4.w, acc[4 * d4 + 3]);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < HP; ++d) {
+                    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 1);
+                    acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 2);
+                }
+                const float *self = (which ? dpre2 : dpre1) + n * HS;
+                float *dst = (which ? H2 : H1) + n * HS;       // H_k is dead: it becomes d lt_k
+#pragma unroll
+                for (int d4 = 0; d4 < HQ; ++d4) {
+                    const float v = pt == 0 ? acc[4 * d4] : (pt == 1 ? acc[4 * d4 + 1] : (pt == 2 ? acc[4 * d4 + 2] : acc[4 * d4 + 3]));
+                    dst[4 * d4 + pt] = self[4 * d4 + pt] + v;
                 }
             }
             EPI_SYNC();
             CTS(13);
-            // dC^T[j][i] (pre-activation) in place of C^T
-            for (int idx = tid; idx < AT * AT; idx += NE) {
-                const int j = idx >> 6, i = idx & 63;
-                float dl1 = 0.f, dl2 = 0.f;
-                for (int d = 0; d < hd; ++d) {
-                    dl1 += dpre1[d * AT + j] * lt2[d * AT + i];
-                    dl2 += dpre2[d * AT + i] * lt1[d * AT + j];
+            // dC^T[j][i] (pre-activation) in place of C^T: a thread keeps ITS column i (lt2[i], dpre2[i] in registers) and
+            // walks eight rows j whose head rows are warp-wide broadcasts
+            {
+                const int i = tid & 63;
+                float l2[HP], p2[HP];
+#pragma unroll
+                for (int d4 = 0; d4 < HQ; ++d4) {
+                    const float4 x4 = *reinterpret_cast<const float4 *>(lt2 + i * HS + 4 * d4), y4 = *reinterpret_cast<const float4 *>(dpre2 + i * HS + 4 * d4);
+                    l2[4 * d4] = x4.x; l2[4 * d4 + 1] = x4.y; l2[4 * d4 + 2] = x4.z; l2[4 * d4 + 3] = x4.w;
+                    p2[4 * d4] = y4.x; p2[4 * d4 + 1] = y4.y; p2[4 * d4 + 2] = y4.z; p2[4 * d4 + 3] = y4.w;
                 }
-                const float c = Cs[j * CLD + i];
-                const float g = L1t[i * PLD + j] * (dl1 - part[i]) + L2p[j * PLD + i] * (dl2 - part[AT + j]);
-                Cs[j * CLD + i] = g * act_bwd(a.act, c, c);
+                const float u1i = part[i];
+#pragma unroll 2
+                for (int u8 = 0; u8 < AT * AT / NE; ++u8) {
+                    const int j = (tid >> 6) + u8 * (NE / 64);
+                    float dl1 = 0.f, dl2 = 0.f;
+#pragma unroll
+                    for (int d4 = 0; d4 < HQ; ++d4) {
+                        const float4 x4 = *reinterpret_cast<const float4 *>(dpre1 + j * HS + 4 * d4), y4 = *reinterpret_cast<const float4 *>(lt1 + j * HS + 4 * d4);
+                        dl1 = fmaf(x4.x, l2[4 * d4], fmaf(x4.y, l2[4 * d4 + 1], fmaf(x4.z, l2[4 * d4 + 2], fmaf(x4.w, l2[4 * d4 + 3], dl1))));
+                        dl2 = fmaf(y4.x, p2[4 * d4], fmaf(y4.y, p2[4 * d4 + 1], fmaf(y4.z, p2[4 * d4 + 2], fmaf(y4.w, p2[4 * d4 + 3], dl2))));
+                    }
+                    const float c = Cs[j * CLD + i];
+                    const float g = L1t[i * PLD + j] * (dl1 - u1i) + L2p[j * PLD + i] * (dl2 - part[AT + j]);
+                    Cs[j * CLD + i] = g * act_bwd(a.act, c, c);
+                }
             }
             EPI_SYNC();
             CTS(14);
@@ -623,10 +725,10 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             if (tid < 2 * AT) {       // extension chunks: a2 rows of the dC panel (tid < 64), a1 rows of the R panel (tid >= 64)
                 const int which = tid < AT, n = tid & 63;
-                const float *dl = which ? H2 : H1;
+                const float *dl = (which ? H2 : H1) + n * HS;
                 float v[16];
 #pragma unroll
-                for (int d = 0; d < 16; ++d) v[d] = d < hd ? dl[d * AT + n] : 0.f;
+                for (int d = 0; d < 16; ++d) v[d] = d < HP ? dl[d] : 0.f;      // heads >= head are zero by construction
                 v[15] = which ? rsum[n] : cs[n];
                 uint8_t *dst = which ? DP + PANEL_BYTES : QP;
                 const int r = which ? 64 + n : n;
@@ -813,17 +915,22 @@ bool bmp_coattn_tc_supported(int H, int head, int variant, bool bwd) {
     return need <= 227 * 1024;
 }
 
-template <int H, bool BWD>
-static int launch_ctc(const ctc::Args &k, int head, cudaStream_t st) {
+template <int H, bool BWD, int HP>
+static int launch_ctc_hp(const ctc::Args &k, int head, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = k.mb < sms ? k.mb : sms;
     const size_t smem = ctc::smem_bytes<H, BWD>(head);
-    cudaFuncSetAttribute(ctc::coattn_tc_kernel<H, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ctc::coattn_tc_kernel<H, BWD><<<grid, ctc::NT, smem, st>>>(k);
+    cudaFuncSetAttribute(ctc::coattn_tc_kernel<H, BWD, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ctc::coattn_tc_kernel<H, BWD, HP><<<grid, ctc::NT, smem, st>>>(k);
     count_launch();
     return check_launch("coattn_tc_kernel");
+}
+
+template <int H, bool BWD>
+static int launch_ctc(const ctc::Args &k, int head, cudaStream_t st) {
+    return head <= 8 ? launch_ctc_hp<H, BWD, 8>(k, head, st) : launch_ctc_hp<H, BWD, 16>(k, head, st);
 }
 
 // Shared by forward and backward: pack the weight images into the workspace, fill the common arguments.
