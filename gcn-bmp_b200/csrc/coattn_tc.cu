@@ -354,10 +354,10 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 for (int x = 0; x < 16; x += 4) {
                     const float4 vv = *reinterpret_cast<const float4 *>(v2 + cg * 16 + x);
                     float4 o;
-                    o.x = act_fwd(a.act, __uint_as_float(w[x]) + base + vv.x);
-                    o.y = act_fwd(a.act, __uint_as_float(w[x + 1]) + base + vv.y);
-                    o.z = act_fwd(a.act, __uint_as_float(w[x + 2]) + base + vv.z);
-                    o.w = act_fwd(a.act, __uint_as_float(w[x + 3]) + base + vv.w);
+                    o.x = act_fast(a.act, __uint_as_float(w[x]) + base + vv.x);
+                    o.y = act_fast(a.act, __uint_as_float(w[x + 1]) + base + vv.y);
+                    o.z = act_fast(a.act, __uint_as_float(w[x + 2]) + base + vv.z);
+                    o.w = act_fast(a.act, __uint_as_float(w[x + 3]) + base + vv.w);
                     *reinterpret_cast<float4 *>(Cs + row * CLD + cg * 16 + x) = o;
                 }
             }

@@ -40,16 +40,6 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
     return v[0];
 }
 
-// BF16-mode gate math: tanh.approx based (as in the encoder epilogues)
-__device__ __forceinline__ float act_fast(int act, float x) {
-    switch (act) {
-        case BMP_ACT_TANH: return tanh_fast(x);
-        case BMP_ACT_RELU: return x > 0.f ? x : 0.f;
-        case BMP_ACT_SIGMOID: return sigmoid_fast(x);
-        default: return x;
-    }
-}
-
 template <int H, int O, bool BWD>
 __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
     constexpr int TILE_BYTES = O * 128;               // forward weight tile [O n][64 k]

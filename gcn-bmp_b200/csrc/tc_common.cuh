@@ -84,6 +84,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// BF16-mode gate math: tanh.approx based (as in the encoder epilogues)
+__device__ __forceinline__ float act_fast(int act, float x) {
+    switch (act) {
+        case BMP_ACT_TANH: return tanh_fast(x);
+        case BMP_ACT_RELU: return x > 0.f ? x : 0.f;
+        case BMP_ACT_SIGMOID: return sigmoid_fast(x);
+        default: return x;
+    }
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
