@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
         mbar_init(BAR(B_HREADY), EPW);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_D1 + i), 1);
-        mbar_init(BAR(B_AHREADY), 2 * EPW);
-        mbar_init(BAR(B_AHREADY + 1), 2 * EPW);
+        mbar_init(BAR(B_AHREADY), EPW);
+        mbar_init(BAR(B_AHREADY + 1), EPW);
         mbar_init(BAR(B_AHFREE), 1);
         mbar_init(BAR(B_M), 1);
         mbar_init(BAR(B_XREADY), EPW);
@@ -346,8 +346,8 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                                 *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
                             }
                         }
-                        warp_arrive(BAR(B_AHREADY + p), lane);
                     }
+                    warp_arrive(BAR(B_AHREADY + p), lane);      // one hand-off per K half (both molecules written)
                 }
                 // ---- E2: message m (+ bias through the degrees) -> bf16 operand (AH panels [0,KP)) ----
                 TSF(1);

@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
         mbar_init(BAR(B_DX), 1);
         mbar_init(BAR(B_DMRDY), EPW);
         for (int i = 0; i < 4; ++i) mbar_init(BAR(B_P + i), 1);
-        mbar_init(BAR(B_PRDY), 2 * EPW);
-        mbar_init(BAR(B_PRDY + 1), 2 * EPW);
+        mbar_init(BAR(B_PRDY), EPW);
+        mbar_init(BAR(B_PRDY + 1), EPW);
         mbar_init(BAR(B_PFREE), 1);
         mbar_init(BAR(B_DH), 1);
         fence_mbar_init();
@@ -480,8 +480,8 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                                 *reinterpret_cast<uint4 *>(smem + C::OFF_D + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
                             }
                         }
-                        warp_arrive(BAR(B_PRDY + p), lane);
                     }
+                    warp_arrive(BAR(B_PRDY + p), lane);         // one hand-off per K half (both molecules written)
                 }
                 TS(10);
                 // ---- phase E: dh_t = dh_x (+ dh_msg) + ds + external gradient ----
