@@ -121,8 +121,11 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
             constexpr uint32_t ID_KK = idesc(H, 0), ID_KMN = idesc(H, 1);
             uint32_t stage = 0, phase = 0, it = 0;
             // one weight tile: 4 k-steps of 16; A panel base `a_addr` (K-major), D columns `dcol`
+            long long wsum = 0;          // cycles this lane spent waiting for weight tiles (timeline slot 15)
             auto mma_wtile = [&](uint32_t a_addr, uint32_t dcol, bool first) {
+                const long long w0 = a.dbg ? clock64() : 0;
                 mbar_wait(BAR(B_FULL + stage), phase);
+                if (a.dbg) wsum += clock64() - w0;
                 tc_fence_after();
                 const uint32_t b_addr = s_w + stage * C::TILE_BYTES;
 #pragma unroll
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                         for (int kp = 0; kp < KP; ++kp) mma_wtile(s_ah + (KP + kp) * PANEL_BYTES, 3 * H, false);
                     if (V2) bulk_wait_read();      // h_t / m_t / r*h_t dumps are out before E4 rewrites the h panels
                     tc_commit(BAR(B_ZH));
+                    if (a.dbg && blockIdx.x == 0 && it < 64) { a.dbg[it * 16 + 15] = wsum; wsum = 0; }
                 }
         }
     } else {

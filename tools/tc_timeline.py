@@ -54,3 +54,4 @@ print("step ends   relative to the first (forward):", [int(f[i][7] - f[0][0]) fo
 print("step starts relative to the first (backward):", [int(d[i][0] - d[0][0]) for i in range(0, 20) if d[i][0]])
 print("step ends   relative to the first (backward):", [int(d[i][12] - d[0][0]) for i in range(0, 20) if d[i][0]])
 print("forward tile prologue (tile 1): ", "  ".join("%s %d" % (n, f[6][8 + i + 1] - f[6][8 + i]) for i, n in enumerate(["embed ld issue", "stage adj", "h0 store", "h operand", "bar", "degrees"])), " from prev E4 done:", f[6][8] - f[5][7], " to step start:", f[6][0] - f[6][14])
+print("forward: cycles the MMA lane waited for weight tiles, per step:", [int(f[i][15]) for i in range(0, 12)])
