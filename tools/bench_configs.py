@@ -1,0 +1,74 @@
+"""Throughput of the OTHER BASELINE.json configurations (parity-test cases, not bench.py lines) on one B200:
+A  GGNN H32 T4 tied, sum readout, HolE->1, 128 pairs N<=50, fwd+bwd           (fp32 kernels; H=32 is below the tcgen05 tiles)
+B  RelGCN 64->64 x4, scale_adj, readout O=64, HolE->1, 4096 pairs N<=64, fwd+bwd (fp32 kernels)
+D  GGNN H256 T8 + R1 readout O=256 + HolE->1, forward only                     (fp32 kernels; H=256 exceeds the TMEM tiling)
+Inputs resident on the device, CUDA events, median of 5 after 3 warm-ups."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gcn-bmp_b200")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+import gcnbmp
+from gcnbmp import synthetic
+
+
+def timed(fn, reps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def pairs(rng, mb, N):
+    a1, A1 = synthetic.random_molecules(rng, mb, N)
+    a2, A2 = synthetic.random_molecules(rng, mb, N)
+    y = (rng.random((mb, 1)) < 0.33).astype(np.int32)
+    return [torch.tensor(x).cuda() for x in (a1, A1, a2, A2, y)]
+
+
+def train_step(model, args):
+    def fn():
+        model.cleargrads()
+        loss = gcnbmp.sigmoid_cross_entropy(model(*args[:4]), args[4])
+        loss.backward()
+    return fn
+
+
+rng = np.random.default_rng(2018)
+f = gcnbmp.functions
+# A
+enc = gcnbmp.GGNNMono(32, 32, 4, weight_tying=True, sum_readout=True)
+mA = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
+aA = pairs(rng, 128, 50)
+ms = timed(train_step(mA, aA))
+print("A  GGNN H32 T4 sum-readout, 128 pairs fwd+bwd (fp32):   %8.3f ms  %10.0f pairs/s" % (ms, 128 / ms * 1e3))
+# B
+enc = gcnbmp.RelGCN(64, ch_list=[64, 64, 64, 64, 64], scale_adj=True)
+mB = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
+aB = pairs(rng, 4096, 64)
+ms = timed(train_step(mB, aB))
+print("B  RelGCN 64x4, 4096 pairs fwd+bwd (fp32):              %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
+# D
+enc = gcnbmp.GGNN(256, hidden_dim=256, n_layers=8, weight_tying=True)
+mD = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
+aD = pairs(rng, 4096, 64)
+
+
+def fwd():
+    with torch.no_grad():
+        mD(*aD[:4])
+
+
+ms = timed(fwd)
+print("D  GGNN H256 T8 + R1 + HolE, 4096 pairs forward (fp32): %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
