@@ -201,6 +201,10 @@ static int relgcn_check(int mb, int N, int E, int L, const int *ch, int *cmax) {
 
 using namespace bmp;
 
+bool bmp_relgcn_tc_supported(const int *ch, int n_layers, int n_edge);   // relgcn_tc.cu
+int bmp_relgcn_forward_tc(const bmp_relgcn_fwd_t *a, void *stream);
+int bmp_relgcn_backward_tc(const bmp_relgcn_bwd_t *a, void *stream);
+
 extern "C" int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream) {
     if (!a || !a->adj || (!a->atoms && !a->h_in) || (a->atoms && !a->embed_W)) {
         set_error("bmp_relgcn_forward: null argument");
@@ -215,6 +219,13 @@ extern "C" int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream) {
             return BMP_EINVAL;
         }
     if (!aligned16({a->h_in, a->embed_W, a->h_out, a->Hs})) { set_error("bmp_relgcn_forward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
+    if (a->mode == BMP_MODE_BF16) {
+        if (!bmp_relgcn_tc_supported(a->ch, a->n_layers, a->n_edge)) {
+            set_error("BMP_MODE_BF16 RelGCN: needs one channel count in {64,128} for all layers and 4 bond types");
+            return BMP_ESHAPE;
+        }
+        return bmp_relgcn_forward_tc(a, stream);
+    }
     size_t smem = sizeof(float) * ((size_t)2 * cmax * AT + AT * AT + 8 * AT + AT + STAGE_FLOATS);
     int grid = a->mb < 148 ? a->mb : 148;
     cudaStream_t st = (cudaStream_t)stream;
@@ -232,6 +243,14 @@ extern "C" int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream) {
 }
 
 extern "C" int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream) {
+    if (a && a->mode == BMP_MODE_BF16) {
+        if (!a->adj) { set_error("bmp_relgcn_backward: null argument"); return BMP_EINVAL; }
+        if (a->mb <= 0 || a->n_atoms <= 0 || a->n_atoms > BMP_MAX_ATOMS || !bmp_relgcn_tc_supported(a->ch, a->n_layers, a->n_edge)) {
+            set_error("BMP_MODE_BF16 RelGCN: needs one channel count in {64,128} for all layers, 4 bond types, N <= %d", BMP_MAX_ATOMS);
+            return BMP_ESHAPE;
+        }
+        return bmp_relgcn_backward_tc(a, stream);
+    }
     if (!a || !a->adj || !a->Hs || !a->d_h_out || !a->Ds || !a->Ps) {
         set_error("bmp_relgcn_backward: null argument");
         return BMP_EINVAL;

@@ -45,14 +45,16 @@ class GgnnBwd(C.Structure):
 class RelgcnFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "n_edge", "n_layers", "n_atom_types", "scale_adj", "act")] + [
         ("ch", C.c_int * (MAX_STEPS + 1)), ("atoms", fp), ("h_in", fp), ("embed_W", fp), ("adj", fp),
-        ("self_W", _A()), ("self_b", _A()), ("edge_W", _A()), ("edge_b", _A()), ("h_out", fp), ("Hs", fp)]
+        ("self_W", _A()), ("self_b", _A()), ("edge_W", _A()), ("edge_b", _A()), ("h_out", fp), ("Hs", fp),
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
 
 
 class RelgcnBwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "n_edge", "n_layers", "scale_adj", "act")] + [
         ("ch", C.c_int * (MAX_STEPS + 1)), ("adj", fp), ("self_W", _A()), ("edge_W", _A()), ("Hs", fp),
         ("d_h_out", fp), ("Ds", fp), ("Ps", fp), ("d_h0", fp),
-        ("d_self_W", _A()), ("d_self_b", _A()), ("d_edge_W", _A()), ("d_edge_b", _A())]
+        ("d_self_W", _A()), ("d_self_b", _A()), ("d_edge_W", _A()), ("d_edge_b", _A()),
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
 
 
 class ReadoutFwd(C.Structure):
@@ -98,6 +100,7 @@ def _load():
         "bmp_embed_backward": [fp, fp, fp, i, i, i, vp],
         "bmp_relgcn_forward": [C.POINTER(RelgcnFwd), vp],
         "bmp_relgcn_backward": [C.POINTER(RelgcnBwd), vp],
+        "bmp_rescale_adj": [fp, fp, i, i, i, vp],
         "bmp_readout_forward": [C.POINTER(ReadoutFwd), vp],
         "bmp_readout_backward": [C.POINTER(ReadoutBwd), vp],
         "bmp_coattn_forward": [C.POINTER(CoattnFwd), vp],
@@ -119,6 +122,7 @@ def _load():
     lib.bmp_ggnn_stash2_bytes.argtypes, lib.bmp_ggnn_stash2_bytes.restype = [i, i, i], C.c_size_t
     lib.bmp_readout_tc_workspace_bytes.argtypes, lib.bmp_readout_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_coattn_tc_workspace_bytes.argtypes, lib.bmp_coattn_tc_workspace_bytes.restype = [i], C.c_size_t
+    lib.bmp_relgcn_tc_workspace_bytes.argtypes, lib.bmp_relgcn_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_last_error.restype = C.c_char_p
     lib.bmp_version.restype = C.c_int
     lib.bmp_device_check.restype = C.c_int
@@ -129,7 +133,7 @@ def _load():
 
 lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
-           "bmp_relgcn_backward", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
+           "bmp_relgcn_backward", "bmp_relgcn_tc_workspace_bytes", "bmp_rescale_adj", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_coattn_tc_workspace_bytes", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]

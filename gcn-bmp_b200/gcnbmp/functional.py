@@ -227,11 +227,20 @@ class RelGCNEncode(torch.autograd.Function):
     Returns the final atom states (mb, N, ch[L])."""
 
     @staticmethod
-    def forward(ctx, x, adj, ch, scale_adj, act, want_stash, *params):
+    def forward(ctx, x, adj, ch, scale_adj, act, want_stash, mode, *params):
         _need_cuda(x, adj)
         adj = _f32(adj)
         mb, E, N, _ = adj.shape
         L = len(ch) - 1
+        tc = mode == K.MODE_BF16 and int(K.lib.bmp_relgcn_tc_workspace_bytes(ch[0], L)) > 0 and len(set(ch)) == 1 and E == 4
+        if mode == K.MODE_BF16 and not tc:
+            raise ValueError("gcnbmp: BMP_MODE_BF16 RelGCN needs one channel count in {64,128} for all layers and 4 bond types "
+                             "(got %r, %d bond types)" % (tuple(ch), E))
+        if tc and scale_adj:
+            # column-degree normalisation as a pre-pass; the tcgen05 kernels (forward and backward) see the scaled adjacency
+            scaled = torch.empty_like(adj)
+            K.check(K.lib.bmp_rescale_adj(_p(adj), _p(scaled), mb, E, N, _stream()))
+            adj, scale_adj = scaled, 0
         a = K.RelgcnFwd()
         a.mb, a.n_atoms, a.n_edge, a.n_layers, a.scale_adj, a.act = mb, N, E, L, int(bool(scale_adj)), act
         for l, c in enumerate(ch):
@@ -251,30 +260,44 @@ class RelGCNEncode(torch.autograd.Function):
         h_out = torch.empty((mb, N, ch[-1]), device=adj.device, dtype=torch.float32)
         a.h_out = _p(h_out)
         Hs = None
-        if want_stash:
+        if tc:
+            nbytes = int(K.lib.bmp_relgcn_tc_workspace_bytes(ch[0], L))
+            ws, a.tc_images_ready = _tc_images("relgcn_fwd", nbytes, adj.device, params)
+            a.mode, a.tc_workspace, a.tc_workspace_bytes = K.MODE_BF16, _p(ws), nbytes
+            if want_stash:       # bf16 panel tape (same layout as the GGNN encoder's)
+                Hs = torch.empty((int(K.lib.bmp_ggnn_stash2_bytes(mb, ch[0], L)),), device=adj.device, dtype=torch.uint8)
+                a.stash2 = _p(Hs)
+        elif want_stash:
             Hs = torch.empty((rows * sum(ch),), device=adj.device, dtype=torch.float32)
             a.Hs = _p(Hs)
         K.check(K.lib.bmp_relgcn_forward(C.byref(a), _stream()))
         if want_stash:
             ctx.save_for_backward(x, adj, Hs, *params)
-            ctx.meta = (tuple(ch), int(bool(scale_adj)), act, is_ids)
+            ctx.meta = (tuple(ch), int(bool(scale_adj)), act, is_ids, tc)
         return h_out
 
     @staticmethod
     def backward(ctx, d_out):
         x, adj, Hs = ctx.saved_tensors[:3]
         params = ctx.saved_tensors[3:]
-        ch, scale_adj, act, is_ids = ctx.meta
+        ch, scale_adj, act, is_ids, tc = ctx.meta
         mb, E, N, _ = adj.shape
         L = len(ch) - 1
         rows = mb * N
         dev = adj.device
         d_out = _f32(d_out)
-        grads = [torch.zeros_like(p) if p is not None else None for p in params]
-        Ds = torch.empty((rows * sum(ch[1:]),), device=dev, dtype=torch.float32)
-        Ps = torch.empty((rows * E * sum(ch[1:]),), device=dev, dtype=torch.float32)
+        grads, rets = _grad_targets(params)
+        Ds = Ps = None
+        if not tc:
+            Ds = torch.empty((rows * sum(ch[1:]),), device=dev, dtype=torch.float32)
+            Ps = torch.empty((rows * E * sum(ch[1:]),), device=dev, dtype=torch.float32)
         d_h0 = torch.empty((mb, N, ch[0]), device=dev, dtype=torch.float32)
         a = K.RelgcnBwd()
+        if tc:
+            nbytes = int(K.lib.bmp_relgcn_tc_workspace_bytes(ch[0], L))
+            ws, a.tc_images_ready = _tc_images("relgcn_bwd", nbytes, dev, params)
+            a.mode, a.tc_workspace, a.tc_workspace_bytes, a.stash2 = K.MODE_BF16, _p(ws), nbytes, _p(Hs)
+            Hs = None
         a.mb, a.n_atoms, a.n_edge, a.n_layers, a.scale_adj, a.act = mb, N, E, L, scale_adj, act
         for l, c in enumerate(ch):
             a.ch[l] = c
@@ -290,8 +313,8 @@ class RelGCNEncode(torch.autograd.Function):
             K.check(K.lib.bmp_embed_backward(_p(x), _p(d_h0), _p(grads[0]), rows, ch[0], grads[0].shape[0], _stream()))
         else:
             dx = d_h0
-            grads[0] = None
-        return (dx, None, None, None, None, None) + tuple(grads)
+            rets[0] = None
+        return (dx, None, None, None, None, None, None) + tuple(rets)
 
 
 def _readout_ws(a, mode, H, O, variant, dev, params):

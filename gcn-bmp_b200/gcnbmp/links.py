@@ -305,7 +305,7 @@ class RelGCNUpdate(Link):
         # the bare link has no activation (the tanh lives in models/relgcn.py:70-71)
         h, adj = _as_device(h, torch.float32), _as_device(adj, torch.float32)
         return Fn.RelGCNEncode.apply(h, adj, (self.in_channels, self.out_channels), 0, K.ACT["identity"],
-                                     torch.is_grad_enabled(), None, *self.tensors())
+                                     torch.is_grad_enabled(), self.__dict__.get("mode", K.MODE_F32), None, *self.tensors())
 
 
 class GGNNReadout(Link):
@@ -490,8 +490,9 @@ class RelGCN(Link):
         for c in self.rgcn_convs:
             params += c.tensors()
         atoms = Fn.RelGCNEncode.apply(x, adj, tuple(self.ch_list), 1 if self.scale_adj else 0, K.ACT["tanh"],
-                                      torch.is_grad_enabled(), *params)
+                                      torch.is_grad_enabled(), self.__dict__.get("mode", K.MODE_F32), *params)
         self.__dict__["atoms"] = atoms
+        self.rgcn_readout.__dict__["mode"] = self.__dict__.get("mode", K.MODE_F32)
         return self.rgcn_readout(atoms)
 
     def get_atom_array(self):

@@ -148,9 +148,19 @@ typedef struct {
     const float *edge_W[BMP_MAX_STEPS], *edge_b[BMP_MAX_STEPS];   /* (Cout*E,Cin),(Cout*E) */
     float *h_out;      /* (mb,N,ch[L]) */
     float *Hs;         /* stash or NULL */
+    /* BMP_MODE_BF16 (tcgen05): every ch[l] equal and in {64,128}, n_edge = 4, scale_adj = 0 (apply bmp_rescale_adj
+     * first); stash2 (bmp_ggnn_stash2_bytes(mb, ch[0], n_layers) bytes, or NULL for inference) replaces Hs. */
+    int    mode;
+    void  *tc_workspace;         /* >= bmp_relgcn_tc_workspace_bytes(ch[0], n_layers) */
+    size_t tc_workspace_bytes;
+    void  *stash2;
+    int    tc_images_ready;      /* as in bmp_ggnn_fwd_t */
 } bmp_relgcn_fwd_t;
 
 int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream);
+size_t bmp_relgcn_tc_workspace_bytes(int channels, int n_layers);   /* 0 = channel count not on the tcgen05 path */
+/* adj_out[b,e,i,j] = adj[b,e,i,j] / (sum_{e',i'} adj[b,e',i',j] or 1)   (rescale_adj, models/relgcn.py:20-28) */
+int bmp_rescale_adj(const float *adj, float *adj_out, int mb, int n_edge, int n_atoms, void *stream);
 
 /* Ds: workspace, concatenation over l of (mb*N, ch[l+1]) pre-tanh gradients;
  * Ps: workspace, concatenation over l of (mb*N, E*ch[l+1]) (A_e^T delta);
@@ -165,6 +175,12 @@ typedef struct {
     float *Ds, *Ps, *d_h0;
     float *d_self_W[BMP_MAX_STEPS], *d_self_b[BMP_MAX_STEPS];
     float *d_edge_W[BMP_MAX_STEPS], *d_edge_b[BMP_MAX_STEPS];
+    /* BMP_MODE_BF16: stash2 written by the forward (Hs, Ds, Ps unused), adj = the adjacency the forward saw */
+    int    mode;
+    void  *tc_workspace;
+    size_t tc_workspace_bytes;
+    void  *stash2;
+    int    tc_images_ready;
 } bmp_relgcn_bwd_t;
 
 int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream);

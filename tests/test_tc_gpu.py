@@ -214,3 +214,34 @@ def test_trainer_fast_paths_match_plain_autograd():
         with torch.no_grad():            # move the parameters: cached images must not survive into the next step
             tr.flat.mul_(1.05)
             pflat.mul_(1.05)
+
+
+@pytest.mark.parametrize("C,L,mb,N,scale", [(64, 4, 5, 64, True), (128, 2, 3, 37, False), (64, 1, 301, 20, True)])
+def test_tc_relgcn_within_bf16_bound(C, L, mb, N, scale):
+    """RelGCN stack on tcgen05 (forward, backward-data and the grouped panel contractions) against the fp64 oracle."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    from oracle import minichainer as F
+    rng = np.random.default_rng(C + L + mb)
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    ch = [C] * (L + 1)
+    params = R.init_params(R.relgcn_shapes(C, ch), rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    onet = R.RelGCN(R.P(tab), out_channels=C, ch_list=ch, scale_adj=scale)
+    og = onet(atoms, adj.astype(np.float64))
+    w = rng.standard_normal(og.data.shape)
+    F.sum_(F.mul(og, F.const(w))).backward()
+    net = gcnbmp.RelGCN(C, ch_list=ch, scale_adj=scale)
+    net.load_params(params)
+    net.mode = gcnbmp.MODE_BF16
+    with torch.no_grad():
+        g0 = net(atoms, adj).cpu().numpy()
+    assert rel_err(g0, og.data) <= MAX_TOL
+    g = net(atoms, adj)
+    (g * torch.tensor(w, dtype=torch.float32, device="cuda")).sum().backward()
+    assert rel_err(g.detach().cpu().numpy(), og.data) <= MAX_TOL
+    gd = net.grad_dict()
+    for k in gd:
+        ref = tab[k].grad
+        assert np.isfinite(gd[k]).all(), k
+        assert _rms_rel(gd[k], ref) <= 5e-2, (k, _rms_rel(gd[k], ref))

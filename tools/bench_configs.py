@@ -1,6 +1,6 @@
 """Throughput of the OTHER BASELINE.json configurations (parity-test cases, not bench.py lines) on one B200:
 A  GGNN H32 T4 tied, sum readout, HolE->1, 128 pairs N<=50, fwd+bwd           (fp32 kernels; H=32 is below the tcgen05 tiles)
-B  RelGCN 64->64 x4, scale_adj, readout O=64, HolE->1, 4096 pairs N<=64, fwd+bwd (fp32 kernels)
+B  RelGCN 64->64 x4, scale_adj, readout O=64, HolE->1, 4096 pairs N<=64, fwd+bwd (fp32 kernels and tcgen05)
 D  GGNN H256 T8 + R1 readout O=256 + HolE->1, forward only                     (fp32 kernels; H=256 exceeds the TMEM tiling)
 Inputs resident on the device, CUDA events, median of 5 after 3 warm-ups."""
 import os
@@ -59,6 +59,27 @@ mB = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
 aB = pairs(rng, 4096, 64)
 ms = timed(train_step(mB, aB))
 print("B  RelGCN 64x4, 4096 pairs fwd+bwd (fp32):              %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
+enc.mode = gcnbmp.MODE_BF16
+ms = timed(train_step(mB, aB))
+print("B  RelGCN 64x4, 4096 pairs fwd+bwd (BF16, tcgen05):     %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
+from gcnbmp import functional as Fn
+gflat = mB.flatten_parameters()[1]
+
+
+def sink_step():
+    gflat.zero_()
+    loss = gcnbmp.sigmoid_cross_entropy(mB(*aB[:4]), aB[4])
+    Fn.set_grad_sink(True)
+    Fn.set_weight_cache(True)
+    try:
+        loss.backward()
+    finally:
+        Fn.set_grad_sink(False)
+
+
+ms = timed(sink_step)
+Fn.set_weight_cache(False)
+print("B  same, gradient sink + cached weight images:          %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
 # D
 enc = gcnbmp.GGNN(256, hidden_dim=256, n_layers=8, weight_tying=True)
 mD = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
