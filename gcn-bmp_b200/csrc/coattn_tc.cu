@@ -29,7 +29,7 @@ constexpr int STAGES = 2;
 #define CTS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it == 1) a.dbg[i] = clock64(); } while (0)
 
 struct Args {
-    int mb, n1, n2, O, head, act;
+    int mb, n1, n2, O, head, act, pool;      // pool: PoolingFineCoattention (scores = means of C, no head path; head = 0)
     const float *atoms_1, *atoms_2, *b, *wa_1, *wa_2, *W_j, *b_j, *lt_2, *V2;
     const uint8_t *img1, *img2, *img1x;      // packed weight tiles
     float *c1, *c2;                          // forward outputs
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                    s_dp = sbase + C::OFF_DP;
     uint8_t *XP = smem + C::OFF_XP, *QP = smem + C::OFF_QP, *SP = smem + C::OFF_SP, *DP = smem + C::OFF_DP;
     const int hd = a.head, N1 = a.n1, N2 = a.n2, O = a.O;
+    const bool pool = a.pool != 0;
     // ---- fp32 area
     float *fp = reinterpret_cast<float *>(smem + C::OFF_F);
     float *Cs = fp; fp += AT * CLD;
@@ -364,6 +365,18 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             tc_fence_before();
             EPI_SYNC();
             CTS(5);
+            if (pool) {
+                // PoolingFineCoattention: attn_1 = softmax_j(mean_i C), attn_2 = softmax_i(mean_j C)
+                if (tid < AT) {
+                    float sm = 0.f;
+                    for (int j = 0; j < N1; ++j) sm += Cs[j * CLD + tid];
+                    attn2[tid] = sm / (float)N1;
+                }
+                for (int j = warp; j < AT; j += EPW) {
+                    const float sm = warp_sum((lane < N2 ? Cs[j * CLD + lane] : 0.f) + (lane + 32 < N2 ? Cs[j * CLD + lane + 32] : 0.f));
+                    if (lane == 0) attn1[j] = sm / (float)N2;
+                }
+            } else {
             // ---- softmax statistics: over i for every j (rows of C^T, one warp each), over j for every i (8 partials)
             float *m2 = st4, *is2 = st4 + AT, *m1 = st4 + 2 * AT, *is1 = st4 + 3 * AT;
             {
@@ -473,6 +486,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
                 for (int d = 0; d < HP; ++d) sc += d < hd ? __ldg(wa + d) * Hk[d] : 0.f;
                 (tid < AT ? attn1 : attn2)[n] = sc;
             }
+            }
             EPI_SYNC();
             if (warp < 2) {
                 float *x = warp ? attn2 : attn1;
@@ -580,6 +594,17 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             EPI_SYNC();
             CTS(11);
+            if (pool) {
+                // scores are means of C: dC[i][j] = ds_1[j] / N2 + ds_2[i] / N1 ; no head path (d lt = 0)
+                for (int idx = tid; idx < 2 * AT * HP; idx += NE) (idx < AT * HP ? H1 : H2 - AT * HP)[idx] = 0.f;
+                for (int idx = tid; idx < AT * AT; idx += NE) {
+                    const int j = idx >> 6, i = idx & 63;
+                    const float c = Cs[j * CLD + i];
+                    const float g = (j < N1 && i < N2) ? t1[j] / (float)N2 + t2[i] / (float)N1 : 0.f;
+                    Cs[j * CLD + i] = g * act_bwd(a.act, c, c);
+                }
+                EPI_SYNC();
+            } else {
             // dpre_k[n][:] = ds_k[n] wa_k[:] (1 - H_k^2) ; d wa_k[d] += sum_n ds_k[n] H_k[n][d]
             for (int idx = tid; idx < 2 * AT * HQ; idx += NE) {
                 const int which = idx / (AT * HQ), r = idx % (AT * HQ), n = r / HQ, d4 = r % HQ;
@@ -692,6 +717,7 @@ __global__ void __launch_bounds__(NT, 1) coattn_tc_kernel(const Args a) {
             }
             EPI_SYNC();
             CTS(14);
+            }
             // rsum[i] = sum_j dC[i][j] ; cs[j] = sum_i dC[i][j]
             if (tid < AT) {
                 float s = 0.f;
@@ -909,7 +935,9 @@ extern "C" size_t bmp_coattn_tc_workspace_bytes(int hidden) {
 
 // whether the tcgen05 kernel covers this problem (otherwise the fp32 kernel of coattn.cu runs)
 bool bmp_coattn_tc_supported(int H, int head, int variant, bool bwd) {
-    if (variant != BMP_COATTN_FINE || (H != 64 && H != 128) || head < 1 || head > ctc::MAXHD) return false;
+    if (H != 64 && H != 128) return false;
+    if (variant == BMP_COATTN_FINE ? (head < 1 || head > ctc::MAXHD) : variant != BMP_COATTN_POOL) return false;
+    if (variant == BMP_COATTN_POOL) head = 0;
     const size_t need = H == 64 ? (bwd ? ctc::smem_bytes<64, true>(head) : ctc::smem_bytes<64, false>(head))
                                 : (bwd ? ctc::smem_bytes<128, true>(head) : ctc::smem_bytes<128, false>(head));
     return need <= 227 * 1024;
@@ -965,23 +993,27 @@ static int ctc_prepare(ctc::Args &k, int mb, int n1, int n2, int H, int O, int h
 int bmp_coattn_forward_tc(const bmp_coattn_fwd_t *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ctc::Args k;
-    int rc = ctc_prepare(k, a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->act, a->atoms_1, a->atoms_2, a->W, a->V1, a->V2, a->b,
+    const int head = a->variant == BMP_COATTN_POOL ? 0 : a->head;
+    int rc = ctc_prepare(k, a->mb, a->n1, a->n2, a->hidden, a->out_dim, head, a->act, a->atoms_1, a->atoms_2, a->W, a->V1, a->V2, a->b,
                          a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j, a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, st);
     if (rc) return rc;
     k.c1 = a->compact_1; k.c2 = a->compact_2;
-    return a->hidden == 64 ? launch_ctc<64, false>(k, a->head, st) : launch_ctc<128, false>(k, a->head, st);
+    k.pool = a->variant == BMP_COATTN_POOL;
+    return a->hidden == 64 ? launch_ctc<64, false>(k, head, st) : launch_ctc<128, false>(k, head, st);
 }
 
 // data part of the backward; the parameter-gradient contractions stay with bmp_coattn_backward
 int bmp_coattn_backward_tc(const bmp_coattn_bwd_t *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ctc::Args k;
-    int rc = ctc_prepare(k, a->mb, a->n1, a->n2, a->hidden, a->out_dim, a->head, a->act, a->atoms_1, a->atoms_2, a->W, a->V1, a->V2, a->b,
+    const int head = a->variant == BMP_COATTN_POOL ? 0 : a->head;
+    int rc = ctc_prepare(k, a->mb, a->n1, a->n2, a->hidden, a->out_dim, head, a->act, a->atoms_1, a->atoms_2, a->W, a->V1, a->V2, a->b,
                          a->lt_1, a->lt_2, a->wa_1, a->wa_2, a->W_j, a->b_j, a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, st);
     if (rc) return rc;
     k.dc1 = a->d_compact_1; k.dc2 = a->d_compact_2; k.R = a->R; k.P1 = a->P1; k.P2 = a->P2; k.DL1 = a->DL1; k.DL2 = a->DL2;
     k.d_a1 = a->d_atoms_1; k.d_a2 = a->d_atoms_2;
     k.d_W = a->d_W; k.d_lt_1 = a->d_lt_1; k.d_lt_2 = a->d_lt_2;
     k.d_V1 = a->d_V1; k.d_V2 = a->d_V2; k.d_b = a->d_b; k.d_wa_1 = a->d_wa_1; k.d_wa_2 = a->d_wa_2;
-    return a->hidden == 64 ? launch_ctc<64, true>(k, a->head, st) : launch_ctc<128, true>(k, a->head, st);
+    k.pool = a->variant == BMP_COATTN_POOL;
+    return a->hidden == 64 ? launch_ctc<64, true>(k, head, st) : launch_ctc<128, true>(k, head, st);
 }

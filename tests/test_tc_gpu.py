@@ -140,7 +140,8 @@ def test_tc_readout_r1_variants(H, O, use_h0, act, agg, use_mask, nobias):
 
 
 @pytest.mark.parametrize("variant,n1,n2,H,O,head,mb", [("nie", 64, 64, 128, 128, 8, 5), ("vqa", 13, 37, 64, 16, 4, 3),
-                                                       ("nie", 1, 5, 64, 8, 1, 2), ("vqa", 50, 64, 128, 32, 8, 300)])
+                                                       ("nie", 1, 5, 64, 8, 1, 2), ("vqa", 50, 64, 128, 32, 8, 300),
+                                                       ("pool", 50, 9, 64, 32, None, 7), ("pool", 64, 64, 128, 128, None, 3)])
 def test_tc_coattention_within_bf16_bound(variant, n1, n2, H, O, head, mb):
     """tcgen05 co-attention (bf16 operands, fp32 accumulation / softmaxes) against the fp64 oracle."""
     import gcnbmp
@@ -152,6 +153,8 @@ def test_tc_coattention_within_bf16_bound(variant, n1, n2, H, O, head, mb):
     v1, v2 = F.param(a1), F.param(a2)
     if variant == "vqa":
         oc, link = R.VQAParallelCoattention(R.P(tab), H, O, head), gcnbmp.VQAParallelCoattention(H, O, head)
+    elif variant == "pool":
+        oc, link = R.PoolingFineCoattention(R.P(tab), H, O), gcnbmp.PoolingFineCoattention(H, O)
     else:
         oc, link = R.NieFineCoattention(R.P(tab), H, O, head), gcnbmp.NieFineCoattention(H, O, head)
     c1, c2 = oc(v1, None, v2, None)
