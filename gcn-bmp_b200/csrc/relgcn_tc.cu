@@ -12,7 +12,7 @@
 //   MMA-s  dh  = delta W_s ;  MMA-P  P_e = A_e^T delta (both operands MN-major) ;  MMA-dh  dh += Pcat Wcat
 // Parameter gradients are grouped contractions over the dumped panels (wgrad_tc2.cu): dW_s = delta^T h, dW_e = P_e^T h,
 // db_s = colsum(delta), db_e = colsum(P_e).  All layers must share one channel count C in {64, 128}; `rescale_adj` is
-// applied beforehand by bmp_rescale_adj (the kernels take the adjacency as given).
+// applied to the staged bf16 tiles (forward and backward alike); bmp_rescale_adj is the same normalisation as a stand-alone op.
 #include "tc_common.cuh"
 
 namespace bmp {
@@ -44,7 +44,7 @@ struct Cfg {
 };
 
 struct Args {
-    int mb, N, L, n_types, act;
+    int mb, N, L, n_types, act, scale_adj;
     const int32_t *atoms;
     const float *embed_W, *h_in, *adj;
     const uint8_t *img[BMP_MAX_STEPS];       // forward: [self KP][msg 4KP] tiles ; backward: [self^T KP][dh 4KP]
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(Cfg<H>::NT, 1) relgcn_tc_kernel(const Args a) 
                 }
             }
             stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            if (a.scale_adj) rescale_staged_adjacency<NE>(smem + C::OFF_ADJ, reinterpret_cast<float *>(smem + C::OFF_AH), tid);
             auto store_h_operand = [&]() {
 #pragma unroll
                 for (int g = 0; g < NC / 8; ++g) {
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(Cfg<H>::NT, 1) relgcn_tc_bwd_kernel(const Args
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;
             stage_adjacency<NE>(smem + C::B_OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            if (a.scale_adj) rescale_staged_adjacency<NE>(smem + C::B_OFF_ADJ, reinterpret_cast<float *>(smem + C::B_OFF_D), tid);
             {
                 const float *src = live ? a.d_h_out + grow * H + colbase : nullptr;
 #pragma unroll
@@ -535,16 +537,21 @@ __global__ void pack_relgcn_kernel(const PackArgs p) {
 static size_t image_bytes(int H) { return (size_t)(5 * (H / 64)) * H * 128 + 256; }
 
 // adj_out[b,e,i,j] = adj[b,e,i,j] / max-safe(sum_{e',i'} adj[b,e',i',j])   (models/relgcn.py:20-28)
-__global__ void rescale_adj_kernel(const float *__restrict__ adj, float *__restrict__ out, int E, int N) {
-    __shared__ float inv[BMP_MAX_ATOMS];
+__global__ void __launch_bounds__(256) rescale_adj_kernel(const float *__restrict__ adj, float *__restrict__ out, int E, int N) {
+    __shared__ float part[4][BMP_MAX_ATOMS], inv[BMP_MAX_ATOMS];
     const long base = (long)blockIdx.x * E * N * N;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        float s = 0.f;
-        for (int r = 0; r < E * N; ++r) s += adj[base + (long)r * N + j];
-        inv[j] = s != 0.f ? 1.f / s : 1.f;
+    const int j = threadIdx.x & 63, p = threadIdx.x >> 6;
+    float s = 0.f;
+    if (j < N)
+        for (int r = p; r < E * N; r += 4) s += __ldg(adj + base + (long)r * N + j);
+    part[p][j] = s;
+    __syncthreads();
+    if (threadIdx.x < N) {
+        const float t = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+        inv[threadIdx.x] = t != 0.f ? 1.f / t : 1.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < E * N * N; i += blockDim.x) out[base + i] = adj[base + i] * inv[i % N];
+    for (int i = threadIdx.x; i < E * N * N; i += blockDim.x) out[base + i] = __ldg(adj + base + i) * inv[i % N];
 }
 
 }  // namespace rgt
@@ -598,10 +605,9 @@ static int rgt_pack(rgt::Args &k, int H, int L, const float *const *self_W, cons
 int bmp_relgcn_forward_tc(const bmp_relgcn_fwd_t *a, void *stream) {
     const int H = a->ch[0], L = a->n_layers;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->scale_adj) { set_error("BMP_MODE_BF16 RelGCN: apply bmp_rescale_adj first (scale_adj must be 0 here)"); return BMP_EINVAL; }
     if (!aligned16({a->h_in, a->embed_W, a->adj, a->h_out, a->tc_workspace, a->stash2})) { set_error("BMP_MODE_BF16 RelGCN: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     rgt::Args k = {};
-    k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.n_types = a->n_atom_types; k.act = a->act;
+    k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.n_types = a->n_atom_types; k.act = a->act; k.scale_adj = a->scale_adj;
     k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.h_out = a->h_out;
     for (int l = 0; l < L; ++l) {
         k.self_b[l] = a->self_b[l]; k.edge_b[l] = a->edge_b[l];
@@ -634,7 +640,7 @@ int bmp_relgcn_backward_tc(const bmp_relgcn_bwd_t *a, void *stream) {
     if (!a->stash2 || !a->d_h_out || !a->d_h0) { set_error("BMP_MODE_BF16 RelGCN backward: stash2, d_h_out and d_h0 are required"); return BMP_EINVAL; }
     if (!aligned16({a->adj, a->d_h_out, a->d_h0, a->tc_workspace, a->stash2})) { set_error("BMP_MODE_BF16 RelGCN backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     rgt::Args k = {};
-    k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.act = a->act; k.adj = a->adj; k.d_h_out = a->d_h_out; k.d_h0 = a->d_h0;
+    k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.act = a->act; k.scale_adj = a->scale_adj; k.adj = a->adj; k.d_h_out = a->d_h_out; k.d_h0 = a->d_h0;
     int rc = rgt_pack(k, H, L, a->self_W, a->edge_W, a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, true, st);
     if (rc) return rc;
     const int n_tiles = (a->mb + 1) / 2;

@@ -170,6 +170,34 @@ __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const float *__r
     }
 }
 
+// rescale_adj (models/relgcn.py:20-28) on the STAGED tiles: adj[mol][e][i][j] /= sum_{e',i'} adj[mol][e'][i'][j] (1 where that
+// sum is 0).  `inv` is 128 floats of scratch shared memory; all NE epilogue threads call this (named barrier 1).
+template <int NE>
+__device__ __forceinline__ void rescale_staged_adjacency(uint8_t *s_adj, float *inv, int tid) {
+    asm volatile("bar.sync 1, %0;" ::"n"(NE));           // staging complete
+    if (tid < 128) {
+        const int mol = tid >> 6, j = tid & 63;
+        float s = 0.f;
+        for (int e = 0; e < 4; ++e) {
+            const uint8_t *t = s_adj + (mol * 4 + e) * ADJ_TILE_BYTES;
+#pragma unroll 8
+            for (int i = 0; i < 64; ++i) s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16 *>(t + sw128(i, j)));
+        }
+        inv[tid] = s != 0.f ? 1.f / s : 1.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NE));
+    for (int idx = tid; idx < 8 * 64 * 16; idx += NE) {   // items: (mol,e) x i x (j/4)
+        const int j4 = (idx & 15) * 4, i = (idx >> 4) & 63, me = idx >> 10;
+        uint2 *p = reinterpret_cast<uint2 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, j4));
+        const uint2 u = *p;
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+        const float *w = inv + (me >> 2) * 64 + j4;
+        *p = make_uint2(pack_bf16(a.x * w[0], a.y * w[1]), pack_bf16(b.x * w[2], b.y * w[3]));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NE));           // inv may be reused, tiles are final
+}
+
 // pull the next tile's adjacency (2 molecules x 4 bond types x N x N fp32, contiguous) towards L2
 template <int NE>
 __device__ __forceinline__ void prefetch_adjacency_l2(const float *__restrict__ adj, int tile, int mb, int N, int tid) {

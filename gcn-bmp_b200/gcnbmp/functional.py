@@ -236,11 +236,6 @@ class RelGCNEncode(torch.autograd.Function):
         if mode == K.MODE_BF16 and not tc:
             raise ValueError("gcnbmp: BMP_MODE_BF16 RelGCN needs one channel count in {64,128} for all layers and 4 bond types "
                              "(got %r, %d bond types)" % (tuple(ch), E))
-        if tc and scale_adj:
-            # column-degree normalisation as a pre-pass; the tcgen05 kernels (forward and backward) see the scaled adjacency
-            scaled = torch.empty_like(adj)
-            K.check(K.lib.bmp_rescale_adj(_p(adj), _p(scaled), mb, E, N, _stream()))
-            adj, scale_adj = scaled, 0
         a = K.RelgcnFwd()
         a.mb, a.n_atoms, a.n_edge, a.n_layers, a.scale_adj, a.act = mb, N, E, L, int(bool(scale_adj)), act
         for l, c in enumerate(ch):

@@ -148,8 +148,8 @@ typedef struct {
     const float *edge_W[BMP_MAX_STEPS], *edge_b[BMP_MAX_STEPS];   /* (Cout*E,Cin),(Cout*E) */
     float *h_out;      /* (mb,N,ch[L]) */
     float *Hs;         /* stash or NULL */
-    /* BMP_MODE_BF16 (tcgen05): every ch[l] equal and in {64,128}, n_edge = 4, scale_adj = 0 (apply bmp_rescale_adj
-     * first); stash2 (bmp_ggnn_stash2_bytes(mb, ch[0], n_layers) bytes, or NULL for inference) replaces Hs. */
+    /* BMP_MODE_BF16 (tcgen05): every ch[l] equal and in {64,128}, n_edge = 4; stash2 (bmp_ggnn_stash2_bytes(mb, ch[0],
+     * n_layers) bytes, or NULL for inference) replaces Hs. */
     int    mode;
     void  *tc_workspace;         /* >= bmp_relgcn_tc_workspace_bytes(ch[0], n_layers) */
     size_t tc_workspace_bytes;
