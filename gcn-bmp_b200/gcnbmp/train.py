@@ -42,9 +42,15 @@ class PairTrainer(object):
     Inputs may be device tensors (resident) or host arrays/tensors (streamed per chunk through
     a pinned staging ring on a copy stream, overlapping the previous chunk's compute)."""
 
-    def __init__(self, model, chunk=2048, optimizer=True, world_size=1, process_group=None, **adam):
+    def __init__(self, model, chunk=2048, optimizer=True, world_size=1, process_group=None, graph=False, **adam):
+        """`graph=True`: every micro-batch shape is captured once as a CUDA graph (forward, loss, backward with the
+        gradient sink) and replayed afterwards -- for small batches (the reference's default is 32 pairs) the step is
+        bound by ~60 kernel launches and the Python around them, not by the kernels."""
         self.model = model
         self.chunk = int(chunk)
+        self.use_graph = bool(graph)
+        self._graphs = {}
+        self._graph_stream = torch.cuda.Stream() if graph else None
         self.flat, self.gflat = model.flatten_parameters()
         self.opt = Adam(self.flat, self.gflat, **adam) if optimizer else None
         self.world_size = world_size
@@ -88,6 +94,51 @@ class PairTrainer(object):
         finally:
             Fn.set_weight_cache(False)
 
+    def _micro(self, a1, A1, a2, A2, y, global_count):
+        """forward + loss + backward of one micro-batch; gradients accumulate into the flat buffer, the loss into loss_buf."""
+        logits = self.model(a1, A1, a2, A2)
+        loss = L.sigmoid_cross_entropy(logits, y, count=global_count)
+        Fn.set_grad_sink(True)       # kernels add straight into the flat gradient buffer (the .grad views)
+        try:
+            loss.backward()
+        finally:
+            Fn.set_grad_sink(False)
+        self.loss_buf += loss.detach()
+
+    def _graph_for(self, tensors, global_count):
+        """CUDA graph of `_micro` for this micro-batch shape (captured on first use; static input buffers)."""
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors) + (float(global_count),)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static = [torch.empty_like(t) for t in tensors]
+            for s_, t in zip(static, tensors):
+                s_.copy_(t)
+            keep_g, keep_l = self.gflat.clone(), self.loss_buf.clone()
+            cache_was_on = Fn._WEIGHT_CACHE
+            Fn.set_weight_cache(False)              # the packing kernels must be PART of the graph (parameters move between replays)
+            # Warm-up and capture run on ONE dedicated stream, after dropping the activations the links cache for
+            # get_atom_array(): a cached output keeps its autograd graph -- and with it the parameters' AccumulateGrad
+            # nodes, which remember the stream they were created on -- alive; autograd's end-of-backward stream sync would
+            # then tie the capture to that (uncaptured) stream.
+            for _, link in self.model.namedlinks():
+                for k in ("atoms", "atoms_list"):
+                    if link.__dict__.get(k) is not None:
+                        link.__dict__[k] = None
+            side = self._graph_stream
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # warm-up outside the capture (lazy initialisations, allocator)
+                for _ in range(2):
+                    self._micro(*static, global_count)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._micro(*static, global_count)
+            Fn.set_weight_cache(cache_was_on)
+            self.gflat.copy_(keep_g)                # the warm-up runs accumulated into the real buffers
+            self.loss_buf.copy_(keep_l)
+            ent = self._graphs[key] = (g, static)
+        return ent
+
     def _step_chunks(self, arrs, n, on_host, global_count):
         labels = arrs[4]
         chunks = self._chunks(n)
@@ -103,14 +154,15 @@ class PairTrainer(object):
                     t.record_stream(cur_stream)
             else:
                 a1, A1, a2, A2, y = (a[s:e] for a in arrs)
-            logits = self.model(a1, A1, a2, A2)
-            loss = L.sigmoid_cross_entropy(logits, y, count=global_count)
-            Fn.set_grad_sink(True)       # kernels add straight into the flat gradient buffer (the .grad views)
-            try:
-                loss.backward()
-            finally:
-                Fn.set_grad_sink(False)
-            self.loss_buf += loss.detach()
+            if self.use_graph:
+                tensors = [t if isinstance(t, torch.Tensor) else torch.as_tensor(t) for t in (a1, A1, a2, A2, y)]
+                tensors = [t.to(self.flat.device) for t in tensors]
+                g, static = self._graph_for(tensors, global_count)
+                for s_, t in zip(static, tensors):
+                    s_.copy_(t, non_blocking=True)
+                g.replay()
+            else:
+                self._micro(a1, A1, a2, A2, y, global_count)
         if self.world_size > 1:
             parallel.allreduce_sum_(self.gflat, self.pg)
         if self.opt is not None:

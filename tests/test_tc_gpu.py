@@ -248,3 +248,39 @@ def test_tc_relgcn_within_bf16_bound(C, L, mb, N, scale):
         ref = tab[k].grad
         assert np.isfinite(gd[k]).all(), k
         assert _rms_rel(gd[k], ref) <= 5e-2, (k, _rms_rel(gd[k], ref))
+
+
+@pytest.mark.parametrize("mode", ["f32", "bf16"])
+def test_trainer_cuda_graph_replay_matches_eager(mode):
+    """PairTrainer(graph=True) captures the micro-batch once and replays it: same gradients as the eager path, also after
+    the parameters moved (the weight-image packing is part of the graph) and with new input data in the static buffers."""
+    import gcnbmp
+    from gcnbmp import train
+    case = cases.pair_case("C", seed=5)
+    sp = dict(case["spec"], H=64, O=64)
+    rng = np.random.default_rng(19)
+    shapes = {"graph_conv/" + k: v for k, v in R.ggnn_mono_shapes(64, 64, sp["T"]).items()}
+    shapes.update({"attn/" + k: v for k, v in R.coattn_shapes(64, 64, 8).items()})
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(64, sp["K"], ()).items()})
+    params = R.init_params(shapes, rng, dtype=np.float64)
+    a1, A1, a2, A2 = case["inputs"]
+    dev = lambda x: torch.tensor(x, device="cuda")
+    args = [dev(a1), dev(A1.astype(np.float32)), dev(a2), dev(A2.astype(np.float32)), dev(case["labels"])]
+
+    def make(graph):
+        m = product.product_model(sp, params)
+        if mode == "bf16":
+            m.graph_conv.mode = m.attn.mode = gcnbmp.MODE_BF16
+        return train.PairTrainer(m, chunk=2, optimizer=False, graph=graph)
+
+    tg, te = make(True), make(False)
+    for rnd in range(3):
+        shuffled = [t.flip(0) if rnd == 1 else t for t in args]        # new data in the static buffers
+        lg, le = float(tg.step(*shuffled)), float(te.step(*shuffled))
+        ga, gb = tg.gflat.cpu().numpy(), te.gflat.cpu().numpy()
+        assert abs(lg - le) <= 1e-5 * abs(le)
+        assert np.abs(ga - gb).max() <= 1e-5 * np.abs(gb).max(), rnd
+        with torch.no_grad():
+            tg.flat.mul_(1.03)
+            te.flat.mul_(1.03)
+    assert len(tg._graphs) == 1

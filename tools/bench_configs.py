@@ -53,6 +53,13 @@ mA = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
 aA = pairs(rng, 128, 50)
 ms = timed(train_step(mA, aA))
 print("A  GGNN H32 T4 sum-readout, 128 pairs fwd+bwd (fp32):   %8.3f ms  %10.0f pairs/s" % (ms, 128 / ms * 1e3))
+from gcnbmp import train as _train
+for nb in (128, 32):
+    sub = [t[:nb] for t in aA]
+    for graph in (False, True):
+        tr = _train.PairTrainer(mA, chunk=nb, optimizer=True, graph=graph, alpha=1e-3)
+        ms = timed(lambda: tr.step(*sub), reps=20)
+        print("A  PairTrainer step (fwd+bwd+Adam), %3d pairs, %s: %8.3f ms  %10.0f pairs/s" % (nb, "CUDA graph" if graph else "eager     ", ms, nb / ms * 1e3))
 # B
 enc = gcnbmp.RelGCN(64, ch_list=[64, 64, 64, 64, 64], scale_adj=True)
 mB = gcnbmp.GraphConvPredictorForPair(enc, None, gcnbmp.HolE(1, hidden_dims=()))
