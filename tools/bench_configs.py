@@ -100,3 +100,18 @@ def fwd():
 
 ms = timed(fwd)
 print("D  GGNN H256 T8 + R1 + HolE, 4096 pairs forward (fp32): %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
+# C (inference): the bench workload forward only, BF16 mode -- the shape class of config D at the hidden size the tcgen05 kernels cover
+enc = gcnbmp.GGNNMono(128, 128, 6)
+attn = gcnbmp.NieFineCoattention(128, 128, 8, activation=f.tanh)
+mC = gcnbmp.GraphConvPredictorForPair(enc, attn, gcnbmp.HolE(86, hidden_dims=()))
+enc.mode = attn.mode = gcnbmp.MODE_BF16
+aC = pairs(rng, 4096, 64)
+
+
+def fwdC():
+    with torch.no_grad():
+        mC(*aC[:4])
+
+
+ms = timed(fwdC)
+print("C  GGNN H128 T6 + co-attention + HolE->86, 4096 pairs FORWARD (BF16): %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
