@@ -69,3 +69,23 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gcnbmp.HolE(1, ()).circular_correlation(torch.zeros(2, 8), torch.zeros(2, 8)) if False else \
             gcnbmp.functional.HoleCorr.apply(torch.zeros(2, 8), torch.zeros(2, 8))
+
+
+def test_workspace_size_queries_are_host_only_and_consistent():
+    """The BF16-mode sizing functions run without a GPU: non-zero exactly for the shapes the tcgen05 kernels cover."""
+    from gcnbmp import _capi
+    lib = _capi.lib
+    for H in (64, 128):
+        assert lib.bmp_ggnn_tc_workspace_bytes(H, 6) > 11 * (H // 64) * H * 128 * 6
+        assert lib.bmp_relgcn_tc_workspace_bytes(H, 4) > 5 * (H // 64) * H * 128 * 4
+        assert lib.bmp_coattn_tc_workspace_bytes(H) > (H // 64) * (H + 32) * 128
+        assert lib.bmp_readout_tc_workspace_bytes(H, H) > 0
+        # bf16 panel stash: 448 KB (H=128) / 224 KB (H=64) per (step, 2-molecule tile)
+        per_unit = (3 + 3 + 4) * (H // 64) * 16384 + 4 * 128 * H * 2
+        assert lib.bmp_ggnn_stash2_bytes(2048, H, 6) >= per_unit * 1024 * 6
+        assert lib.bmp_ggnn_stash2_bytes(2047, H, 6) == lib.bmp_ggnn_stash2_bytes(2048, H, 6)      # odd batch: padded tile
+    for H in (16, 32, 96, 256):
+        assert lib.bmp_ggnn_tc_workspace_bytes(H, 6) == 0
+        assert lib.bmp_relgcn_tc_workspace_bytes(H, 4) == 0
+        assert lib.bmp_coattn_tc_workspace_bytes(H) == 0
+        assert lib.bmp_ggnn_stash2_bytes(64, H, 6) == 0
