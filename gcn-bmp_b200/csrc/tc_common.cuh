@@ -294,7 +294,7 @@ struct Stash2 {
     int KP, T;
     __host__ __device__ static size_t bytes(long n_tiles, int H, int T) {
         const size_t KP = H / 64, per = (size_t)n_tiles * T;
-        return per * (3 * KP + 3 * KP + 4 * KP) * PANEL_BYTES + per * 4 * (size_t)NEPI * (H / 2) * 2 + 4096;
+        return per * (3 * KP + 3 * KP + 4 * KP) * PANEL_BYTES + per * 4 * ((size_t)128 * H * 2) + 4096;
     }
     __host__ __device__ void carve(void *base, long nt, int H, int T_) {
         n_tiles = nt; KP = H / 64; T = T_;
@@ -309,7 +309,7 @@ struct Stash2 {
     }
     // native gate block of (t, tile, array a in 0..3 = z, hbar, r, state): 128 rows x H bf16 = [16-byte chunk][epilogue thread]
     __host__ __device__ uint8_t *zn(int t, long tile, int a, int H) const {
-        return Zn + (((size_t)t * n_tiles + tile) * 4 + a) * ((size_t)NEPI * (H / 2) * 2);
+        return Zn + (((size_t)t * n_tiles + tile) * 4 + a) * ((size_t)128 * H * 2);
     }
 };
 
