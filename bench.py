@@ -172,7 +172,7 @@ def run_gpu(args):
         losses.append(float(loss.item()))       # D2H of the step's result
 
     e2e_steps = max(1, args.e2e_steps if args.e2e_steps else min(args.steps, 3))
-    e2e_ms, _ = timed(e2e_step, e2e_steps, 1)
+    e2e_ms, _ = timed(e2e_step, e2e_steps, max(1, min(args.warmup, 3)))
     e2e_value = args.pairs / (e2e_ms / e2e_steps * 1e-3)
     sampler.stop_flag = True
     h2d = trainer.h2d_bytes * world
