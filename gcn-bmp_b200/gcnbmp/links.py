@@ -166,6 +166,10 @@ class Link(object):
     def flatten_parameters(self):
         """Re-home every parameter (and its gradient) as a view of ONE flat fp32 buffer each,
         so data-parallel training needs a single allreduce and a single Adam launch."""
+        lazy = [k for k, p in self.namedparams(include_uninit=True) if p is None]
+        if lazy:      # a parameter created after this call would live outside the flat buffers: no allreduce, no update
+            raise ValueError("flatten_parameters: lazily-shaped parameters are not initialised yet (%s); run one forward or "
+                             "call .ensure(in_size) on those layers first" % ", ".join(k.lstrip("/") for k in lazy))
         named = [(k, p) for k, p in self.namedparams()]
         pad = lambda m: (m + 63) // 64 * 64          # every view stays 256-byte aligned (cp.async needs 16)
         n = sum(pad(p.numel()) for _, p in named)

@@ -169,6 +169,38 @@ class PairTrainer(object):
             self.opt.update()
         return self.loss_buf
 
+    def step_indexed(self, table_atoms, table_adjs, idx_1, idx_2, labels, global_count=None):
+        """`step()` for pairs given as INDEX pairs into a device-resident drug table (a DDI data set has a few
+        hundred to a few thousand unique drugs; the reference re-copies each drug's padded arrays for every pair it occurs in).
+        `table_atoms (U,N)` / `table_adjs (U,E,N,N)` live on the device; per step only `idx_1`, `idx_2 (mb,)` and `labels`
+        cross PCIe.  The per-micro-batch gather is a device-side row copy."""
+        dev = self.flat.device
+        assert table_adjs.is_cuda and table_atoms.is_cuda, "the drug table must be device-resident"
+        to_dev = lambda t, dt: (t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t))).to(dev, dtype=dt, non_blocking=True)
+        i1, i2 = to_dev(idx_1, torch.int64), to_dev(idx_2, torch.int64)
+        y = to_dev(labels, torch.int32)
+        self.h2d_bytes = sum(int(np.asarray(t).nbytes) if not isinstance(t, torch.Tensor) else (0 if t.is_cuda else t.numel() * t.element_size())
+                             for t in (idx_1, idx_2, labels))
+        n = i1.shape[0]
+        if global_count is None:
+            global_count = float(n * y.shape[1] * self.world_size)
+        self.gflat.zero_()
+        self.loss_buf.zero_()
+        Fn.params_changed()
+        Fn.set_weight_cache(True)
+        try:
+            for s, e in self._chunks(n):
+                a1, a2 = table_atoms.index_select(0, i1[s:e]), table_atoms.index_select(0, i2[s:e])
+                A1, A2 = table_adjs.index_select(0, i1[s:e]), table_adjs.index_select(0, i2[s:e])
+                self._micro(a1, A1, a2, A2, y[s:e], global_count)
+        finally:
+            Fn.set_weight_cache(False)
+        if self.world_size > 1:
+            parallel.allreduce_sum_(self.gflat, self.pg)
+        if self.opt is not None:
+            self.opt.update()
+        return self.loss_buf
+
     @torch.no_grad()
     def predict(self, atoms_1, adjs_1, atoms_2, adjs_2):
         """Forward only over all pairs (eval_coattention.py:102-126 predict loop)."""

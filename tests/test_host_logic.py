@@ -139,3 +139,16 @@ def test_shard_bounds_cover_everything():
             spans = [parallel.shard_bounds(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_flatten_parameters_refuses_uninitialised_lazy_layers():
+    """A lazily-shaped layer created after flattening would sit outside the flat buffers (no allreduce, no Adam update)."""
+    import gcnbmp
+    enc = gcnbmp.GGNNMono(16, 16, 2)
+    head = gcnbmp.HolE(1, hidden_dims=())            # l_out is shaped at its first call
+    model = gcnbmp.GraphConvPredictorForPair(enc, None, head)
+    with pytest.raises(ValueError, match="lazily-shaped"):
+        model.flatten_parameters()
+    head.l_out.ensure(16)
+    flat, gflat = model.flatten_parameters()
+    assert flat.numel() == gflat.numel() > 0

@@ -284,3 +284,33 @@ def test_trainer_cuda_graph_replay_matches_eager(mode):
             tg.flat.mul_(1.03)
             te.flat.mul_(1.03)
     assert len(tg._graphs) == 1
+
+
+def test_trainer_step_indexed_matches_step_on_gathered_pairs():
+    """Pairs as index pairs into a device-resident drug table == the same pairs passed as per-pair arrays."""
+    import gcnbmp
+    from gcnbmp import synthetic, train
+    rng = np.random.default_rng(23)
+    U, N, mb, K = 9, 30, 14, 5
+    atoms, adj = synthetic.random_molecules(rng, U, N)
+    i1, i2 = rng.integers(0, U, mb), rng.integers(0, U, mb)
+    y = (rng.random((mb, K)) < 0.3).astype(np.int32)
+    dev = lambda x: torch.tensor(x, device="cuda")
+
+    def make():
+        gcnbmp.seed(5)
+        enc = gcnbmp.GGNNMono(64, 64, 3)
+        attn = gcnbmp.NieFineCoattention(64, 64, 8, activation=gcnbmp.functions.tanh)
+        mlp = gcnbmp.HolE(K, hidden_dims=())
+        mlp.l_out.ensure(64)             # materialise the lazily-shaped layer before the parameters are flattened
+        m = gcnbmp.GraphConvPredictorForPair(enc, attn, mlp)
+        enc.mode = attn.mode = gcnbmp.MODE_BF16
+        return train.PairTrainer(m, chunk=4, optimizer=False)
+
+    ta, tb = make(), make()
+    la = float(ta.step_indexed(dev(atoms), dev(adj), i1, i2, y))
+    lb = float(tb.step(dev(atoms[i1]), dev(adj[i1]), dev(atoms[i2]), dev(adj[i2]), dev(y)))
+    assert abs(la - lb) <= 1e-6 * abs(lb)
+    ga, gb = ta.gflat.cpu().numpy(), tb.gflat.cpu().numpy()
+    assert np.abs(ga - gb).max() <= 1e-5 * np.abs(gb).max()
+    assert ta.h2d_bytes == i1.nbytes + i2.nbytes + y.nbytes

@@ -28,7 +28,9 @@ def run(mode):
     gcnbmp.links.seed(777)          # identical initial parameters for both runs
     enc = gcnbmp.GGNNMono(O, H, T)
     attn = gcnbmp.NieFineCoattention(H, O, 8, activation=gcnbmp.functions.tanh)
-    model = gcnbmp.GraphConvPredictorForPair(enc, attn, gcnbmp.HolE(K, hidden_dims=()))
+    head = gcnbmp.HolE(K, hidden_dims=())
+    head.l_out.ensure(O)        # lazily-shaped layer: materialise before the trainer flattens the parameters
+    model = gcnbmp.GraphConvPredictorForPair(enc, attn, head)
     enc.mode = attn.mode = mode
     tr = train.PairTrainer(model, chunk=512, alpha=1e-3)
     return model, [float(tr.step(*args)) for _ in range(STEPS)]

@@ -17,7 +17,9 @@ a2, A2 = synthetic.random_molecules(rng, mb, N)
 y = (rng.random((mb, K)) < 0.1).astype(np.int32)
 enc = gcnbmp.GGNNMono(O, H, T)
 attn = gcnbmp.NieFineCoattention(H, O, 8, activation=gcnbmp.functions.tanh)
-model = gcnbmp.GraphConvPredictorForPair(enc, attn, gcnbmp.HolE(K, hidden_dims=()))
+head = gcnbmp.HolE(K, hidden_dims=())
+head.l_out.ensure(O)        # lazily-shaped layer: materialise before the trainer flattens the parameters
+model = gcnbmp.GraphConvPredictorForPair(enc, attn, head)
 enc.mode = attn.mode = gcnbmp.MODE_BF16
 tr = train.PairTrainer(model, chunk=2048)
 dev = lambda x: torch.tensor(x).cuda()
