@@ -148,11 +148,16 @@ class Link(object):
                     cur = link._params[n]
                     if cur is not None and tuple(cur.shape) != tuple(t.shape):
                         raise ValueError("gcnbmp: shape mismatch for %s: %s vs %s" % (key, tuple(cur.shape), tuple(t.shape)))
-                    link._params[n] = t
+                    if cur is not None and "_flat" in self.__dict__:
+                        with torch.no_grad():        # flattened model: keep the views of the flat buffer, copy in place
+                            cur.copy_(t)
+                    else:
+                        link._params[n] = t
                     used.add(key)
         missing = [k for k, p in self.namedparams(True) if k not in used and p is None]
         if missing:
             raise KeyError("gcnbmp: uninitialised parameters not found in table: %s" % missing)
+        Fn.params_changed()
         return self
 
     def param_dict(self):

@@ -152,3 +152,20 @@ def test_flatten_parameters_refuses_uninitialised_lazy_layers():
     head.l_out.ensure(16)
     flat, gflat = model.flatten_parameters()
     assert flat.numel() == gflat.numel() > 0
+
+
+def test_load_params_after_flattening_keeps_the_flat_views():
+    """Loading a snapshot into a flattened model must write THROUGH the views (the optimiser updates the flat buffer)."""
+    import gcnbmp
+    enc = gcnbmp.GGNNMono(16, 16, 2)
+    head = gcnbmp.HolE(1, hidden_dims=())
+    head.l_out.ensure(16)
+    model = gcnbmp.GraphConvPredictorForPair(enc, None, head)
+    flat, _ = model.flatten_parameters()
+    snap = {k: v + 1.0 for k, v in model.param_dict().items()}
+    before = flat.clone()
+    model.load_params(snap)
+    n_real = sum(v.size for v in snap.values())
+    assert abs(float((flat - before).sum()) - n_real) < 1e-2 * n_real          # every real element moved by +1 inside the flat buffer
+    for k, p in model.namedparams():
+        assert p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + flat.numel() * 4, k
