@@ -123,8 +123,13 @@ class Link(object):
                 yield "/" + cn + n, l
 
     def cleargrads(self):
+        """chainer.Link.cleargrads.  Gradients that are views of a flat gradient buffer (flatten_parameters) are zeroed in
+        place instead of dropped: the optimiser and the allreduce read that buffer."""
         for p in self.params():
-            p.grad = None
+            if p.grad is not None and p.grad._base is not None:
+                p.grad.zero_()
+            else:
+                p.grad = None
 
     zerograds = cleargrads
 

@@ -169,3 +169,22 @@ def test_load_params_after_flattening_keeps_the_flat_views():
     assert abs(float((flat - before).sum()) - n_real) < 1e-2 * n_real          # every real element moved by +1 inside the flat buffer
     for k, p in model.namedparams():
         assert p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + flat.numel() * 4, k
+
+
+def test_cleargrads_keeps_flat_gradient_views():
+    import gcnbmp
+    enc = gcnbmp.GGNNMono(16, 16, 2)
+    head = gcnbmp.HolE(1, hidden_dims=())
+    head.l_out.ensure(16)
+    model = gcnbmp.GraphConvPredictorForPair(enc, None, head)
+    _, gflat = model.flatten_parameters()
+    gflat.fill_(3.0)
+    model.cleargrads()
+    assert float(gflat.abs().sum()) == 0.0
+    for k, p in model.namedparams():
+        assert p.grad is not None and p.grad._base is not None, k
+    plain = gcnbmp.GGNNMono(16, 16, 2)              # unflattened model: chainer semantics (gradients dropped)
+    for p in plain.params():
+        p.grad = torch.ones_like(p)
+    plain.cleargrads()
+    assert all(p.grad is None for p in plain.params())
