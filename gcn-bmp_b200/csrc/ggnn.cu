@@ -399,6 +399,7 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
         return BMP_EINVAL;
     }
     if (a->mode == BMP_MODE_BF16) return bmp_ggnn_forward_tc(a, stream);
+    if (a->adj_u8) { set_error("bmp_ggnn_forward: a byte adjacency needs BMP_MODE_BF16"); return BMP_EINVAL; }
     int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->mode);
     if (rc) return rc;
     for (int t = 0; t < a->n_steps; ++t) {
@@ -465,6 +466,7 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         return e_;
     };
     const bool tc_data = tcw && E == 4 && !a->state_in;      // data part on tcgen05 as well
+    if (a->adj_u8 && !tc_data) { set_error("bmp_ggnn_backward: a byte adjacency needs the tcgen05 path"); return BMP_EINVAL; }
     if (!tc_data && H > 128) {
         set_error("bmp_ggnn_backward: hidden=%d > 128 not supported by the fp32 backward kernel", H);
         return BMP_ESHAPE;

@@ -42,7 +42,9 @@ struct Cfg {
 struct Args {
     int mb, N, T, n_types;
     const int32_t *atoms;
-    const float *embed_W, *h_in, *adj;
+    const float *embed_W, *h_in;
+    const void *adj;             // fp32 (mb,E,N,N), or bytes when adj_u8
+    int adj_u8;
     const uint8_t *img[BMP_MAX_STEPS];     // packed weight tiles of step t
     const float *bias3[BMP_MAX_STEPS];     // [b_r | b_z | b_h] (U biases folded for stateful steps)
     const float *msg_b[BMP_MAX_STEPS];     // (H*4) as in the reference: b[c*4+e]
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
             }
             // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
             TSP(1);
-            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
             TSP(2);
             {
 #pragma unroll
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
 #define TSF(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TSF(0);
                 if (t == a.T - 1 && tile + (int)gridDim.x < n_tiles) {      // next tile of this CTA: adjacency and atom ids towards L2
-                    prefetch_adjacency_l2<NE>(a.adj, tile + gridDim.x, a.mb, a.N, tid);
+                    prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid);
                     if (a.atoms && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
                 }
                 uint32_t v[32];
@@ -578,7 +580,7 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     tc::Args k = {};
     k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.n_types = a->n_atom_types;
-    k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj;
+    k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.adj_u8 = a->adj_u8;
     k.h_out = a->h_out; k.h0_out = a->h0_out; k.Hs = a->Hs; k.Ms = a->Ms; k.Gs = a->Gs; k.RSs = a->RSs;
     k.dbg = g_tc_dbg_fwd;
     k.use2 = a->stash2 != nullptr;

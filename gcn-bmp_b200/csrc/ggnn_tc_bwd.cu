@@ -33,7 +33,9 @@ struct Cfg {
 
 struct Args {
     int mb, N, T;
-    const float *adj, *Hs;
+    const void *adj;             // fp32 (mb,E,N,N), or bytes when adj_u8
+    int adj_u8;
+    const float *Hs;
     float *Gs, *Ps, *dHs;
     const uint8_t *img[BMP_MAX_STEPS];
     int stateful[BMP_MAX_STEPS];
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
             const int molg = tile * 2 + molslot;
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;
-            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
             {
                 const float *src = live ? a.dHs + ((long)(V2 ? 1 : a.T) * rows_total + grow) * H + colbase : nullptr;
 #pragma unroll
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 uint32_t v[32];
 #define TS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TS(0);
-                if (t == 0 && tile + (int)gridDim.x < n_tiles) prefetch_adjacency_l2<NE>(a.adj, tile + gridDim.x, a.mb, a.N, tid);
+                if (t == 0 && tile + (int)gridDim.x < n_tiles) prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid);
                 // ---- phase A: gate derivatives ----
                 if (V2) {
                     // gate values of the step: coalesced 16-byte loads in the thread-native bf16 order, two 16-column halves
@@ -589,7 +591,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     }
     cudaStream_t st = (cudaStream_t)stream;
     tcb::Args k = {};
-    k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.adj = a->adj; k.Hs = a->Hs; k.Gs = a->Gs; k.Ps = a->Ps; k.dHs = a->dHs;
+    k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.adj = a->adj; k.adj_u8 = a->adj_u8; k.Hs = a->Hs; k.Gs = a->Gs; k.Ps = a->Ps; k.dHs = a->dHs;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);
     int *flags = reinterpret_cast<int *>(ws);      // first 256 B of the workspace: per-step external-gradient flags
     ws += 256;

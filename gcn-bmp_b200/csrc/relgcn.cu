@@ -226,6 +226,7 @@ extern "C" int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream) {
         }
         return bmp_relgcn_forward_tc(a, stream);
     }
+    if (a->adj_u8) { set_error("bmp_relgcn_forward: a byte adjacency needs BMP_MODE_BF16"); return BMP_EINVAL; }
     size_t smem = sizeof(float) * ((size_t)2 * cmax * AT + AT * AT + 8 * AT + AT + STAGE_FLOATS);
     int grid = a->mb < 148 ? a->mb : 148;
     cudaStream_t st = (cudaStream_t)stream;
@@ -251,6 +252,7 @@ extern "C" int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream) {
         }
         return bmp_relgcn_backward_tc(a, stream);
     }
+    if (a && a->adj_u8) { set_error("bmp_relgcn_backward: a byte adjacency needs BMP_MODE_BF16"); return BMP_EINVAL; }
     if (!a || !a->adj || !a->Hs || !a->d_h_out || !a->Ds || !a->Ps) {
         set_error("bmp_relgcn_backward: null argument");
         return BMP_EINVAL;

@@ -46,7 +46,9 @@ struct Cfg {
 struct Args {
     int mb, N, L, n_types, act, scale_adj;
     const int32_t *atoms;
-    const float *embed_W, *h_in, *adj;
+    const float *embed_W, *h_in;
+    const void *adj;                         // fp32 (mb,E,N,N), or bytes when adj_u8
+    int adj_u8;
     const uint8_t *img[BMP_MAX_STEPS];       // forward: [self KP][msg 4KP] tiles ; backward: [self^T KP][dh 4KP]
     const float *self_b[BMP_MAX_STEPS], *edge_b[BMP_MAX_STEPS];
     float *h_out;                            // forward: (mb, N, H)
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(Cfg<H>::NT, 1) relgcn_tc_kernel(const Args a) 
                     hreg[c] = v.x; hreg[c + 1] = v.y; hreg[c + 2] = v.z; hreg[c + 3] = v.w;
                 }
             }
-            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
             if (a.scale_adj) rescale_staged_adjacency<NE>(smem + C::OFF_ADJ, reinterpret_cast<float *>(smem + C::OFF_AH), tid);
             auto store_h_operand = [&]() {
 #pragma unroll
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(Cfg<H>::NT, 1) relgcn_tc_bwd_kernel(const Args
             const int molg = tile * 2 + molslot;
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;
-            stage_adjacency<NE>(smem + C::B_OFF_ADJ, a.adj, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::B_OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
             if (a.scale_adj) rescale_staged_adjacency<NE>(smem + C::B_OFF_ADJ, reinterpret_cast<float *>(smem + C::B_OFF_D), tid);
             {
                 const float *src = live ? a.d_h_out + grow * H + colbase : nullptr;
@@ -608,7 +610,7 @@ int bmp_relgcn_forward_tc(const bmp_relgcn_fwd_t *a, void *stream) {
     if (!aligned16({a->h_in, a->embed_W, a->adj, a->h_out, a->tc_workspace, a->stash2})) { set_error("BMP_MODE_BF16 RelGCN: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     rgt::Args k = {};
     k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.n_types = a->n_atom_types; k.act = a->act; k.scale_adj = a->scale_adj;
-    k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.h_out = a->h_out;
+    k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.adj_u8 = a->adj_u8; k.h_out = a->h_out;
     for (int l = 0; l < L; ++l) {
         k.self_b[l] = a->self_b[l]; k.edge_b[l] = a->edge_b[l];
         if (!aligned16({a->self_b[l], a->edge_b[l]})) { set_error("BMP_MODE_BF16 RelGCN: biases must be 16-byte aligned"); return BMP_EINVAL; }
@@ -640,7 +642,7 @@ int bmp_relgcn_backward_tc(const bmp_relgcn_bwd_t *a, void *stream) {
     if (!a->stash2 || !a->d_h_out || !a->d_h0) { set_error("BMP_MODE_BF16 RelGCN backward: stash2, d_h_out and d_h0 are required"); return BMP_EINVAL; }
     if (!aligned16({a->adj, a->d_h_out, a->d_h0, a->tc_workspace, a->stash2})) { set_error("BMP_MODE_BF16 RelGCN backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     rgt::Args k = {};
-    k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.act = a->act; k.scale_adj = a->scale_adj; k.adj = a->adj; k.d_h_out = a->d_h_out; k.d_h0 = a->d_h0;
+    k.mb = a->mb; k.N = a->n_atoms; k.L = L; k.act = a->act; k.scale_adj = a->scale_adj; k.adj = a->adj; k.adj_u8 = a->adj_u8; k.d_h_out = a->d_h_out; k.d_h0 = a->d_h0;
     int rc = rgt_pack(k, H, L, a->self_W, a->edge_W, a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, true, st);
     if (rc) return rc;
     const int n_tiles = (a->mb + 1) / 2;

@@ -135,10 +135,50 @@ __host__ __device__ constexpr uint32_t idesc2(int n, int a_mn_major, int b_mn_ma
            ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// stage the fp32 adjacency of a tile (2 molecules x 4 bond types) as bf16 SW128 tiles [mol][e][i][j].
-// Loads are issued in batches of 8 float4 per thread so the DRAM latency is paid 4 times per tile, not 32.
+// stage the adjacency of a tile (2 molecules x 4 bond types) as bf16 SW128 tiles [mol][e][i][j].  The source is the reference's
+// fp32 array (mb,E,N,N) or, with `u8`, the same array stored as bytes (exact for 0/1 bonds, a quarter of the traffic).
+// Loads are issued in batches of 8 vectors per thread so the DRAM latency is paid a few times per tile, not per element.
 template <int NE>
-__device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const float *__restrict__ adj, int tile, int mb, int N, int tid) {
+__device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__restrict__ adj_any, int u8, int tile, int mb, int N, int tid) {
+    if (u8) {
+        const uint8_t *adj = reinterpret_cast<const uint8_t *>(adj_any);
+        constexpr int ITEMS = 8 * 64 * 4, PER = (ITEMS + NE - 1) / NE;     // items: (mol,e) x i x (j/16)
+        uint4 v[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = u * NE + tid;
+            const int j16 = (idx & 3) * 16, i = (idx >> 2) & 63, me = idx >> 8;
+            const int mg = tile * 2 + (me >> 2);
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (idx < ITEMS && mg < mb && i < N && j16 < N) {
+                const uint8_t *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j16;
+                if ((N & 15) == 0) {
+                    v[u] = __ldg(reinterpret_cast<const uint4 *>(src));
+                } else {
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    for (int x = 0; x < 16 && j16 + x < N; ++x) w[x >> 2] |= (uint32_t)src[x] << (8 * (x & 3));
+                    v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = u * NE + tid;
+            if (idx >= ITEMS) continue;
+            const int j16 = (idx & 3) * 16, i = (idx >> 2) & 63, me = idx >> 8;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t o[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const uint32_t b0 = (w[x >> 1] >> (16 * (x & 1))) & 0xFFu, b1 = (w[x >> 1] >> (16 * (x & 1) + 8)) & 0xFFu;
+                o[x] = pack_bf16((float)b0, (float)b1);
+            }
+            *reinterpret_cast<uint4 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, j16)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, j16 + 8)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        return;
+    }
+    const float *adj = reinterpret_cast<const float *>(adj_any);
     constexpr int BATCH = 8;
     for (int base = 0; base < 8 * 64 * 16; base += NE * BATCH) {      // items: (mol,e) x i x (j/4)
         float4 v[BATCH];
@@ -200,10 +240,11 @@ __device__ __forceinline__ void rescale_staged_adjacency(uint8_t *s_adj, float *
 
 // pull the next tile's adjacency (2 molecules x 4 bond types x N x N fp32, contiguous) towards L2
 template <int NE>
-__device__ __forceinline__ void prefetch_adjacency_l2(const float *__restrict__ adj, int tile, int mb, int N, int tid) {
+__device__ __forceinline__ void prefetch_adjacency_l2(const void *__restrict__ adj, int u8, int tile, int mb, int N, int tid) {
     const long first = (long)tile * 2, nmol = first + 2 <= mb ? 2 : (first < mb ? 1 : 0);
-    const char *base = reinterpret_cast<const char *>(adj + first * 4 * N * N);
-    const long bytes = nmol * 4L * N * N * 4;
+    const long esz = u8 ? 1 : 4;
+    const char *base = reinterpret_cast<const char *>(adj) + first * 4 * N * N * esz;
+    const long bytes = nmol * 4L * N * N * esz;
     for (long off = (long)tid * 128; off < bytes; off += (long)NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 

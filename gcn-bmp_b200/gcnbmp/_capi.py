@@ -31,7 +31,7 @@ class GgnnFwd(C.Structure):
         ("atoms", fp), ("h_in", fp), ("embed_W", fp), ("adj", fp), ("state_in", fp),
         ("msg_W", _A()), ("msg_b", _A()), ("gru", GRU * MAX_STEPS), ("stateful", C.c_int * MAX_STEPS),
         ("h_out", fp), ("h0_out", fp), ("Hs", fp), ("Ms", fp), ("Gs", fp), ("RSs", fp),
-        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int), ("adj_u8", C.c_int)]
 
 
 class GgnnBwd(C.Structure):
@@ -39,14 +39,14 @@ class GgnnBwd(C.Structure):
         ("adj", fp), ("state_in", fp), ("msg_W", _A()), ("gru", GRU * MAX_STEPS),
         ("stateful", C.c_int * MAX_STEPS), ("Hs", fp), ("Ms", fp), ("RSs", fp), ("Gs", fp), ("Ps", fp), ("dHs", fp),
         ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS), ("d_state_in", fp),
-        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
+        ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int), ("adj_u8", C.c_int)]
 
 
 class RelgcnFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "n_edge", "n_layers", "n_atom_types", "scale_adj", "act")] + [
         ("ch", C.c_int * (MAX_STEPS + 1)), ("atoms", fp), ("h_in", fp), ("embed_W", fp), ("adj", fp),
         ("self_W", _A()), ("self_b", _A()), ("edge_W", _A()), ("edge_b", _A()), ("h_out", fp), ("Hs", fp),
-        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int), ("adj_u8", C.c_int)]
 
 
 class RelgcnBwd(C.Structure):
@@ -54,7 +54,7 @@ class RelgcnBwd(C.Structure):
         ("ch", C.c_int * (MAX_STEPS + 1)), ("adj", fp), ("self_W", _A()), ("edge_W", _A()), ("Hs", fp),
         ("d_h_out", fp), ("Ds", fp), ("Ps", fp), ("d_h0", fp),
         ("d_self_W", _A()), ("d_self_b", _A()), ("d_edge_W", _A()), ("d_edge_b", _A()),
-        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int)]
+        ("mode", C.c_int), ("tc_workspace", fp), ("tc_workspace_bytes", C.c_size_t), ("stash2", fp), ("tc_images_ready", C.c_int), ("adj_u8", C.c_int)]
 
 
 class ReadoutFwd(C.Structure):

@@ -17,6 +17,15 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _adj(t, mode):
+    """Adjacency as the kernels take it: fp32, or -- BF16 mode only -- the caller's uint8 / bool array as is (exact for 0/1
+    bonds; a quarter of the PCIe and HBM traffic).  Returns (tensor, adj_u8 flag)."""
+    if mode == K.MODE_BF16 and t.dtype in (torch.uint8, torch.bool):
+        t = t.contiguous()
+        return (t.view(torch.uint8) if t.dtype == torch.bool else t), 1
+    return _f32(t), 0
+
+
 def _f32(t):
     if t is None:
         return None
@@ -122,7 +131,7 @@ class GGNNEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj, state_in, plan, n_msg, n_gru, mode, want_stash, keep_steps, *params):
         _need_cuda(x, adj)
-        adj = _f32(adj)
+        adj, adj_u8 = _adj(adj, mode)
         mb, E, N, _ = adj.shape
         embed_W = params[0]
         msg = [(params[1 + 2 * i], params[2 + 2 * i]) for i in range(n_msg)]
@@ -140,7 +149,7 @@ class GGNNEncode(torch.autograd.Function):
             x = _f32(x)
             a.h_in = _p(x)
         state_in = _f32(state_in)
-        a.adj, a.state_in = _p(adj), _p(state_in)
+        a.adj, a.state_in, a.adj_u8 = _p(adj), _p(state_in), adj_u8
         for t, (mi, gi, st) in enumerate(plan):
             a.msg_W[t], a.msg_b[t] = _p(msg[mi][0]), _p(msg[mi][1])
             _fill_gru(a.gru[t], gru[gi])
@@ -196,7 +205,7 @@ class GGNNEncode(torch.autograd.Function):
         Ps = torch.empty((T, rows, E * H), device=adj.device, dtype=torch.float32) if stash2 is None else None
         a = K.GgnnBwd()
         a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
-        a.adj, a.state_in = _p(adj), _p(state_in)
+        a.adj, a.state_in, a.adj_u8 = _p(adj), _p(state_in), int(adj.dtype == torch.uint8)
         base = 1 + 2 * n_msg
         for t, (mi, gi, st) in enumerate(plan):
             a.msg_W[t] = _p(params[1 + 2 * mi])
@@ -229,7 +238,7 @@ class RelGCNEncode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, adj, ch, scale_adj, act, want_stash, mode, *params):
         _need_cuda(x, adj)
-        adj = _f32(adj)
+        adj, adj_u8 = _adj(adj, mode)
         mb, E, N, _ = adj.shape
         L = len(ch) - 1
         tc = mode == K.MODE_BF16 and int(K.lib.bmp_relgcn_tc_workspace_bytes(ch[0], L)) > 0 and len(set(ch)) == 1 and E == 4
@@ -247,7 +256,7 @@ class RelGCNEncode(torch.autograd.Function):
         else:
             x = _f32(x)
             a.h_in = _p(x)
-        a.adj = _p(adj)
+        a.adj, a.adj_u8 = _p(adj), adj_u8
         for l in range(L):
             Ws, bs, We, be = params[1 + 4 * l: 5 + 4 * l]
             a.self_W[l], a.self_b[l], a.edge_W[l], a.edge_b[l] = _p(Ws), _p(bs), _p(We), _p(be)
@@ -297,6 +306,7 @@ class RelGCNEncode(torch.autograd.Function):
         for l, c in enumerate(ch):
             a.ch[l] = c
         a.adj, a.Hs, a.d_h_out, a.Ds, a.Ps, a.d_h0 = _p(adj), _p(Hs), _p(d_out), _p(Ds), _p(Ps), _p(d_h0)
+        a.adj_u8 = int(adj.dtype == torch.uint8)
         for l in range(L):
             Ws, bs, We, be = params[1 + 4 * l: 5 + 4 * l]
             a.self_W[l], a.edge_W[l] = _p(Ws), _p(We)

@@ -64,6 +64,15 @@ def _as_device(x, dtype=None):
     return x
 
 
+def _adj_device(adj, mode):
+    """Adjacency to the device: fp32 as in the reference; a uint8 / bool adjacency is kept as bytes in BF16 mode (the tcgen05
+    kernels stage it directly -- exact for 0/1 bonds, a quarter of the bytes) and widened to fp32 otherwise."""
+    dt = adj.dtype if isinstance(adj, torch.Tensor) else torch.from_numpy(np.empty(0, np.asarray(adj).dtype)).dtype
+    if mode == K.MODE_BF16 and dt in (torch.uint8, torch.bool):
+        return _as_device(adj)
+    return _as_device(adj, torch.float32)
+
+
 def _is_ids(x):
     return x.dtype in (torch.int32, torch.int64, torch.int16, torch.uint8) if isinstance(x, torch.Tensor) \
         else np.issubdtype(np.asarray(x).dtype, np.integer)
@@ -289,7 +298,7 @@ class GGNNUpdate(Link):
         self.__dict__.update(num_edge_type=num_edge_type, hidden_dim=hidden_dim, mode=K.MODE_F32)
 
     def __call__(self, h, adj):
-        h, adj = _as_device(h, torch.float32), _as_device(adj, torch.float32)
+        h, adj = _as_device(h, torch.float32), _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
         gru = self.update_layer
         state = gru.h
         gl = self.graph_linear
@@ -317,7 +326,7 @@ class RelGCNUpdate(Link):
 
     def __call__(self, h, adj):
         # the bare link has no activation (the tanh lives in models/relgcn.py:70-71)
-        h, adj = _as_device(h, torch.float32), _as_device(adj, torch.float32)
+        h, adj = _as_device(h, torch.float32), _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
         return Fn.RelGCNEncode.apply(h, adj, (self.in_channels, self.out_channels), 0, K.ACT["identity"],
                                      torch.is_grad_enabled(), self.__dict__.get("mode", K.MODE_F32), None, *self.tensors())
 
@@ -378,7 +387,7 @@ class GGNN(Link):
 
     def __call__(self, atom_array, adj, is_real_node=None):
         self.reset_state()
-        adj = _as_device(adj, torch.float32)
+        adj = _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
         ids = _is_ids(atom_array) and getattr(atom_array, "ndim", 2) <= 2
         x = _as_device(atom_array, torch.int32 if ids else torch.float32)
         ups = list(self.update_layers)
@@ -440,7 +449,7 @@ class GGNNMono(Link):
 
     def __call__(self, atom_array, adj):
         self.update_layer.reset_state()
-        adj = _as_device(adj, torch.float32)
+        adj = _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
         ids = _is_ids(atom_array)
         x = _as_device(atom_array, torch.int32 if ids else torch.float32)
         T = self.n_layers
@@ -493,7 +502,7 @@ class RelGCN(Link):
                              num_edge_type=num_edge_type, atoms=None)
 
     def __call__(self, h, adj):
-        adj = _as_device(adj, torch.float32)
+        adj = _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
         if _is_ids(h):
             assert self.input_type == 'int'
             x, emb = _as_device(h, torch.int32), self.embed.W

@@ -91,6 +91,8 @@ typedef struct {
                                  /* bmp_ggnn_stash2_bytes() bytes; replaces Hs..RSs  */
     int    tc_images_ready;      /* nonzero: tc_workspace already holds the images packed by an earlier call of the same
                                    kind with exactly these parameter values -- skip packing             */
+    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
+                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
 } bmp_ggnn_fwd_t;
 
 int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
@@ -124,6 +126,8 @@ typedef struct {
                                     slices: [0] = gradient w.r.t. h_0, [1] = gradient w.r.t. h_T               */
     int    tc_images_ready;      /* nonzero: tc_workspace already holds the images packed by an earlier call of the same
                                    kind with exactly these parameter values -- skip packing             */
+    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
+                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
 } bmp_ggnn_bwd_t;
 
 int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
@@ -155,6 +159,8 @@ typedef struct {
     size_t tc_workspace_bytes;
     void  *stash2;
     int    tc_images_ready;      /* as in bmp_ggnn_fwd_t */
+    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
+                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
 } bmp_relgcn_fwd_t;
 
 int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream);
@@ -181,6 +187,8 @@ typedef struct {
     size_t tc_workspace_bytes;
     void  *stash2;
     int    tc_images_ready;
+    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
+                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
 } bmp_relgcn_bwd_t;
 
 int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream);

@@ -314,3 +314,28 @@ def test_trainer_step_indexed_matches_step_on_gathered_pairs():
     ga, gb = ta.gflat.cpu().numpy(), tb.gflat.cpu().numpy()
     assert np.abs(ga - gb).max() <= 1e-5 * np.abs(gb).max()
     assert ta.h2d_bytes == i1.nbytes + i2.nbytes + y.nbytes
+
+
+@pytest.mark.parametrize("kind,N", [("ggnn", 64), ("ggnn", 37), ("relgcn", 64), ("relgcn", 20)])
+def test_byte_adjacency_is_bit_identical_to_fp32_adjacency(kind, N):
+    """BF16 mode stages a uint8 adjacency directly (a quarter of the PCIe / HBM bytes): outputs and gradients must equal
+    the fp32-adjacency run bit for bit (0/1 bonds are exact in both)."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(N)
+    atoms, adj = synthetic.random_molecules(rng, 7, N)
+    gcnbmp.seed(11)
+    net = gcnbmp.GGNNMono(64, 64, 3) if kind == "ggnn" else gcnbmp.RelGCN(64, ch_list=[64, 64, 64], scale_adj=True)
+    net.mode = gcnbmp.MODE_BF16
+    outs = []
+    for a in (torch.tensor(adj, device="cuda"), torch.tensor(adj.astype(np.uint8), device="cuda")):
+        net.cleargrads()
+        g = net(atoms, a)
+        (g.sum() + net.get_atom_array().sum() if kind == "ggnn" else g.sum()).backward()
+        outs.append((g.detach().clone(), {k: v.copy() for k, v in net.grad_dict().items()}))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:
+        ref = outs[0][1][k]
+        assert np.abs(outs[1][1][k] - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30), k      # fp32 atomics: order noise only
+    with torch.no_grad():
+        assert torch.equal(net(atoms, torch.tensor(adj.astype(bool), device="cuda")), net(atoms, adj))
