@@ -169,11 +169,15 @@ class PairTrainer(object):
             self.opt.update()
         return self.loss_buf
 
-    def step_indexed(self, table_atoms, table_adjs, idx_1, idx_2, labels, global_count=None):
+    def step_indexed(self, table_atoms, table_adjs, idx_1, idx_2, labels, global_count=None, dedupe=False):
         """`step()` for pairs given as INDEX pairs into a device-resident drug table (a DDI data set has a few
         hundred to a few thousand unique drugs; the reference re-copies each drug's padded arrays for every pair it occurs in).
         `table_atoms (U,N)` / `table_adjs (U,E,N,N)` live on the device; per step only `idx_1`, `idx_2 (mb,)` and `labels`
-        cross PCIe.  The per-micro-batch gather is a device-side row copy."""
+        cross PCIe.  The per-micro-batch gather is a device-side row copy.
+        `dedupe=True`: the parameters are constant within a step, so every drug that occurs in it is ENCODED ONCE (forward
+        and backward); the pairs only run the co-attention and the head on gathered encoder outputs, and their atom-state
+        gradients are summed per drug before the single encoder backward.  Same gradients, encoder work divided by the
+        average number of occurrences of a drug in the step."""
         dev = self.flat.device
         assert table_adjs.is_cuda and table_atoms.is_cuda, "the drug table must be device-resident"
         to_dev = lambda t, dt: (t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t))).to(dev, dtype=dt, non_blocking=True)
@@ -189,10 +193,13 @@ class PairTrainer(object):
         Fn.params_changed()
         Fn.set_weight_cache(True)
         try:
-            for s, e in self._chunks(n):
-                a1, a2 = table_atoms.index_select(0, i1[s:e]), table_atoms.index_select(0, i2[s:e])
-                A1, A2 = table_adjs.index_select(0, i1[s:e]), table_adjs.index_select(0, i2[s:e])
-                self._micro(a1, A1, a2, A2, y[s:e], global_count)
+            if dedupe:
+                self._dedupe_pass(table_atoms, table_adjs, i1, i2, y, global_count)
+            else:
+                for s, e in self._chunks(n):
+                    a1, a2 = table_atoms.index_select(0, i1[s:e]), table_atoms.index_select(0, i2[s:e])
+                    A1, A2 = table_adjs.index_select(0, i1[s:e]), table_adjs.index_select(0, i2[s:e])
+                    self._micro(a1, A1, a2, A2, y[s:e], global_count)
         finally:
             Fn.set_weight_cache(False)
         if self.world_size > 1:
@@ -200,6 +207,48 @@ class PairTrainer(object):
         if self.opt is not None:
             self.opt.update()
         return self.loss_buf
+
+    def _dedupe_pass(self, table_atoms, table_adjs, i1, i2, y, global_count):
+        """forward + backward with every occurring drug encoded once (GraphConvPredictorForPair.__call__ re-ordered)."""
+        m = self.model
+        uniq, inv = torch.unique(torch.cat([i1, i2]), return_inverse=True)
+        inv1, inv2 = inv[: i1.shape[0]], inv[i1.shape[0]:]
+        # 1. encode the unique drugs (micro-batches of `chunk` molecules; the tapes stay alive until step 3)
+        enc_out = []
+        for s, e in self._chunks(uniq.shape[0]):
+            rows = uniq[s:e]
+            g = m.graph_conv(table_atoms.index_select(0, rows), table_adjs.index_select(0, rows))
+            enc_out.append((g, m.graph_conv.get_atom_array()))
+        g_all = torch.cat([g for g, _ in enc_out]).detach().requires_grad_(True)
+        a_all = torch.cat([a for _, a in enc_out]).detach().requires_grad_(True)
+        # 2. pairs: co-attention + head on gathered encoder outputs; d g / d atoms accumulate per drug (index_add in autograd)
+        for s, e in self._chunks(i1.shape[0]):
+            g1, g2 = g_all.index_select(0, inv1[s:e]), g_all.index_select(0, inv2[s:e])
+            if m.attn is not None:
+                g1, g2 = m.attn(a_all.index_select(0, inv1[s:e]), g1, a_all.index_select(0, inv2[s:e]), g2)
+            loss = L.sigmoid_cross_entropy(m.mlp(g1, g2), y[s:e], count=global_count)
+            Fn.set_grad_sink(True)
+            try:
+                loss.backward()
+            finally:
+                Fn.set_grad_sink(False)
+            self.loss_buf += loss.detach()
+        # 3. one encoder backward per unique-drug micro-batch
+        off = 0
+        for g, a in enc_out:
+            k = g.shape[0]
+            outs, grads = [], []
+            if g_all.grad is not None and g.requires_grad:
+                outs.append(g); grads.append(g_all.grad[off:off + k])
+            if a_all.grad is not None and a.requires_grad:
+                outs.append(a); grads.append(a_all.grad[off:off + k])
+            off += k
+            if outs:
+                Fn.set_grad_sink(True)
+                try:
+                    torch.autograd.backward(outs, grads)
+                finally:
+                    Fn.set_grad_sink(False)
 
     @torch.no_grad()
     def predict(self, atoms_1, adjs_1, atoms_2, adjs_2):

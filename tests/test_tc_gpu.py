@@ -297,14 +297,14 @@ def test_trainer_step_indexed_matches_step_on_gathered_pairs():
     y = (rng.random((mb, K)) < 0.3).astype(np.int32)
     dev = lambda x: torch.tensor(x, device="cuda")
 
-    def make():
+    def make(mode=gcnbmp.MODE_BF16):
         gcnbmp.seed(5)
         enc = gcnbmp.GGNNMono(64, 64, 3)
         attn = gcnbmp.NieFineCoattention(64, 64, 8, activation=gcnbmp.functions.tanh)
         mlp = gcnbmp.HolE(K, hidden_dims=())
         mlp.l_out.ensure(64)             # materialise the lazily-shaped layer before the parameters are flattened
         m = gcnbmp.GraphConvPredictorForPair(enc, attn, mlp)
-        enc.mode = attn.mode = gcnbmp.MODE_BF16
+        enc.mode = attn.mode = mode
         return train.PairTrainer(m, chunk=4, optimizer=False)
 
     ta, tb = make(), make()
@@ -314,6 +314,15 @@ def test_trainer_step_indexed_matches_step_on_gathered_pairs():
     ga, gb = ta.gflat.cpu().numpy(), tb.gflat.cpu().numpy()
     assert np.abs(ga - gb).max() <= 1e-5 * np.abs(gb).max()
     assert ta.h2d_bytes == i1.nbytes + i2.nbytes + y.nbytes
+    # every occurring drug encoded once: same loss and gradients.  fp32 mode: equal up to summation order; BF16 mode: the
+    # per-drug gradient is summed BEFORE it is rounded to a bf16 operand instead of after (differences at the bf16 level)
+    for mode, tol in ((gcnbmp.MODE_F32, 2e-5), (gcnbmp.MODE_BF16, 2e-3)):
+        td, tp = make(mode), make(mode)
+        ld = float(td.step_indexed(dev(atoms), dev(adj), i1, i2, y, dedupe=True))
+        lp = float(tp.step_indexed(dev(atoms), dev(adj), i1, i2, y))
+        gd, gp = td.gflat.cpu().numpy(), tp.gflat.cpu().numpy()
+        assert abs(ld - lp) <= 1e-6 * abs(lp)
+        assert np.abs(gd - gp).max() <= tol * np.abs(gp).max(), mode
 
 
 @pytest.mark.parametrize("kind,N", [("ggnn", 64), ("ggnn", 37), ("relgcn", 64), ("relgcn", 20)])

@@ -115,3 +115,20 @@ def fwdC():
 
 ms = timed(fwdC)
 print("C  GGNN H128 T6 + co-attention + HolE->86, 4096 pairs FORWARD (BF16): %8.3f ms  %10.0f pairs/s" % (ms, 4096 / ms * 1e3))
+# f-1: pairs as index pairs into a device-resident drug table (KAIST-sized: 1704 unique drugs), 65 536 pairs per step, BF16 mode
+U, NP = 1704, 65536
+tab_a, tab_A = synthetic.random_molecules(rng, U, 64)
+tab_a, tab_A = torch.tensor(tab_a).cuda(), torch.tensor(tab_A.astype(np.uint8)).cuda()
+i1, i2 = rng.integers(0, U, NP), rng.integers(0, U, NP)
+yK = (rng.random((NP, 86)) < 0.05).astype(np.int32)
+head = gcnbmp.HolE(86, hidden_dims=())
+head.l_out.ensure(128)
+encI = gcnbmp.GGNNMono(128, 128, 6)
+attnI = gcnbmp.NieFineCoattention(128, 128, 8, activation=f.tanh)
+mI = gcnbmp.GraphConvPredictorForPair(encI, attnI, head)
+encI.mode = attnI.mode = gcnbmp.MODE_BF16
+trI = _train.PairTrainer(mI, chunk=2048, alpha=1e-3)
+for dd in (False, True):
+    ms = timed(lambda: trI.step_indexed(tab_a, tab_A, i1, i2, yK, dedupe=dd), reps=3, warm=2)
+    print("E  index pairs over a %d-drug device table, %d pairs/step, fwd+bwd+Adam, %s: %8.2f ms  %10.0f pairs/s  (H2D %.2f MB/step)"
+          % (U, NP, "each drug encoded once" if dd else "per-pair encoding     ", ms, NP / ms * 1e3, trI.h2d_bytes / 1e6))
