@@ -251,6 +251,31 @@ class PairTrainer(object):
                     Fn.set_grad_sink(False)
 
     @torch.no_grad()
+    def predict_indexed(self, table_atoms, table_adjs, idx_1, idx_2):
+        """Forward only over index pairs into a device-resident drug table: every occurring drug is encoded once, the pairs run
+        the co-attention (if any) and the head on gathered encoder outputs (eval_coattention.py:102-126 for a table of drugs)."""
+        dev, m = self.flat.device, self.model
+        to_dev = lambda t: (t if isinstance(t, torch.Tensor) else torch.as_tensor(np.asarray(t))).to(dev, dtype=torch.int64, non_blocking=True)
+        i1, i2 = to_dev(idx_1), to_dev(idx_2)
+        uniq, inv = torch.unique(torch.cat([i1, i2]), return_inverse=True)
+        inv1, inv2 = inv[: i1.shape[0]], inv[i1.shape[0]:]
+        gs, ats = [], []
+        for s, e in self._chunks(uniq.shape[0]):
+            rows = uniq[s:e]
+            gs.append(m.graph_conv(table_atoms.index_select(0, rows), table_adjs.index_select(0, rows)))
+            if m.attn is not None:
+                ats.append(m.graph_conv.get_atom_array())
+        g_all = torch.cat(gs)
+        a_all = torch.cat(ats) if ats else None
+        outs = []
+        for s, e in self._chunks(i1.shape[0]):
+            g1, g2 = g_all.index_select(0, inv1[s:e]), g_all.index_select(0, inv2[s:e])
+            if m.attn is not None:
+                g1, g2 = m.attn(a_all.index_select(0, inv1[s:e]), g1, a_all.index_select(0, inv2[s:e]), g2)
+            outs.append(m.mlp(g1, g2))
+        return torch.cat(outs, dim=0)
+
+    @torch.no_grad()
     def predict(self, atoms_1, adjs_1, atoms_2, adjs_2):
         """Forward only over all pairs (eval_coattention.py:102-126 predict loop)."""
         n = atoms_1.shape[0]

@@ -314,6 +314,10 @@ def test_trainer_step_indexed_matches_step_on_gathered_pairs():
     ga, gb = ta.gflat.cpu().numpy(), tb.gflat.cpu().numpy()
     assert np.abs(ga - gb).max() <= 1e-5 * np.abs(gb).max()
     assert ta.h2d_bytes == i1.nbytes + i2.nbytes + y.nbytes
+    # forward only: indexed prediction == prediction on the gathered arrays
+    pa = ta.predict_indexed(dev(atoms), dev(adj), i1, i2)
+    pb = tb.predict(dev(atoms[i1]), dev(adj[i1]), dev(atoms[i2]), dev(adj[i2]))
+    assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-6)
     # every occurring drug encoded once: same loss and gradients.  fp32 mode: equal up to summation order; BF16 mode: the
     # per-drug gradient is summed BEFORE it is rounded to a bf16 operand instead of after (differences at the bf16 level)
     for mode, tol in ((gcnbmp.MODE_F32, 2e-5), (gcnbmp.MODE_BF16, 2e-3)):
