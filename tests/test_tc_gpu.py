@@ -352,3 +352,16 @@ def test_byte_adjacency_is_bit_identical_to_fp32_adjacency(kind, N):
         assert np.abs(outs[1][1][k] - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-30), k      # fp32 atomics: order noise only
     with torch.no_grad():
         assert torch.equal(net(atoms, torch.tensor(adj.astype(bool), device="cuda")), net(atoms, adj))
+
+
+def test_metrics_run_on_device_and_match_the_host_result():
+    """The evaluation metrics consume device-resident predictions; same numbers as on the host."""
+    import gcnbmp
+    rng = np.random.default_rng(1)
+    t = (rng.random((4000, 86)) < 0.1).astype(np.int64)
+    t[0], t[1] = 1, 0
+    y = 1.0 / (1.0 + np.exp(-(rng.standard_normal(t.shape) + 2.0 * t - 1.0)))
+    host = gcnbmp.metrics.evaluate(torch.tensor(y), torch.tensor(t))
+    dev = gcnbmp.metrics.evaluate(torch.tensor(y, device="cuda"), torch.tensor(t, device="cuda"))
+    for k in host:
+        assert dev[k].is_cuda and abs(float(dev[k]) - float(host[k])) <= 1e-9, k
