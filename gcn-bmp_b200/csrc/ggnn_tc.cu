@@ -551,7 +551,11 @@ extern "C" size_t bmp_ggnn_stash2_bytes(int mb, int hidden, int n_steps) {
     return tc::Stash2::bytes((mb + 1) / 2, hidden, n_steps);
 }
 
+size_t bmp_ggnn_tc256_workspace_bytes(int n_steps);                   // ggnn_tc256.cu (hidden 256, forward only)
+int bmp_ggnn_forward_tc256(const bmp_ggnn_fwd_t *a, void *stream);
+
 extern "C" size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps) {
+    if (hidden == 256) return bmp_ggnn_tc256_workspace_bytes(n_steps);
     if (hidden != 64 && hidden != 128) return 0;
     return tc::image_bytes(hidden) * (size_t)n_steps + 2048;
 }
@@ -562,7 +566,8 @@ extern "C" void bmp_debug_set_buffer_fwd(void *p) { g_tc_dbg_fwd = (long long *)
 
 int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     const int H = a->hidden, T = a->n_steps;
-    if (H != 64 && H != 128) { set_error("BMP_MODE_BF16: hidden=%d not supported (64 or 128)", H); return BMP_ESHAPE; }
+    if (H == 256) return bmp_ggnn_forward_tc256(a, stream);
+    if (H != 64 && H != 128) { set_error("BMP_MODE_BF16: hidden=%d not supported (64, 128; 256 forward-only)", H); return BMP_ESHAPE; }
     if (a->n_edge != 4) { set_error("BMP_MODE_BF16: n_edge=%d not supported (4)", a->n_edge); return BMP_ESHAPE; }
     if (a->mb <= 0 || T <= 0 || T > BMP_MAX_STEPS || a->n_atoms <= 0 || a->n_atoms > BMP_MAX_ATOMS) {
         set_error("BMP_MODE_BF16: bad shape mb=%d T=%d N=%d", a->mb, T, a->n_atoms);

@@ -159,7 +159,10 @@ class GGNNEncode(torch.autograd.Function):
         if mode == K.MODE_BF16:
             nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
             if nbytes == 0:
-                raise ValueError("gcnbmp: BMP_MODE_BF16 supports hidden 64 or 128 (got %d)" % H)
+                raise ValueError("gcnbmp: BMP_MODE_BF16 supports hidden 64, 128 or (forward only) 256 (got %d)" % H)
+            if want_stash and H == 256:
+                raise ValueError("gcnbmp: BMP_MODE_BF16 at hidden 256 is forward-only (call under torch.no_grad(), "
+                                 "or train in MODE_F32)")
             ws, a.tc_images_ready = _tc_images("ggnn_fwd", nbytes, dev, params)
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
         if want_stash and mode == K.MODE_BF16 and not keep_steps:

@@ -45,6 +45,35 @@ def test_tc_encoder_matches_oracle_within_bf16_bound(H, T, mb, N, tied):
         assert rel_err(pg, og) <= MAX_TOL
 
 
+@pytest.mark.parametrize("T,mb,N,tied", [(3, 5, 64, True), (8, 9, 64, True), (4, 7, 50, False), (2, 1, 33, True), (3, 303, 20, True)])
+def test_tc_encoder_hidden256_forward_matches_oracle_within_bf16_bound(T, mb, N, tied):
+    """BASELINE config D shape: hidden 256 runs on its own tcgen05 kernel (csrc/ggnn_tc256.cu), forward only."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    H = 256
+    rng = np.random.default_rng(H + T + mb)
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    params = R.init_params(R.ggnn_mono_shapes(H, H, T, weight_tying=tied), rng, dtype=np.float64)
+    onet = R.GGNNMono(R.P(R.wrap_params(params)), H, H, T, weight_tying=tied)
+    og = onet(atoms, adj.astype(np.float64)).data
+    oatoms = onet.get_atom_array().data
+    net = gcnbmp.GGNNMono(H, H, T, weight_tying=tied)
+    net.load_params(params)
+    net.mode = gcnbmp.MODE_BF16
+    with torch.no_grad():
+        pg = net(atoms, adj)
+        pa = net.get_atom_array()
+        pg8 = net(atoms, torch.tensor(adj).to(torch.uint8).cuda())      # byte adjacency: same staging, same bits
+        pa8 = net.get_atom_array()
+    assert torch.equal(pa, pa8) and torch.equal(pg, pg8)
+    pa, pg = pa.cpu().numpy(), pg.cpu().numpy()
+    assert np.isfinite(pa).all()
+    assert rel_err(pa, oatoms) <= MAX_TOL and _rms_rel(pa, oatoms) <= RMS_TOL, (rel_err(pa, oatoms), _rms_rel(pa, oatoms))
+    assert rel_err(pg, og) <= MAX_TOL
+    with pytest.raises(ValueError):         # no training stash at hidden 256
+        net(atoms, adj)
+
+
 def test_tc_mode_pair_training_step_close_to_oracle():
     """Full pair fwd+bwd with encoder and co-attention on the tcgen05 kernels."""
     case = cases.pair_case("C", seed=11)
