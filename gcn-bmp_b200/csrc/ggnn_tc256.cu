@@ -46,6 +46,7 @@ struct Args {
     int stateful[BMP_MAX_STEPS];
     float *h_out, *h0_out;
     uint8_t *scratch;            // gridDim.x x 64 KB: bf16 adjacency image of the CTA's current tile
+    long long *dbg;              // optional: per step of CTA 0, the MMA lane's [total, weight wait, AH wait, x wait, rs wait, h wait] cycles
 };
 
 __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Args a) {
@@ -114,8 +115,11 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
         if (lane == 0) {
             constexpr uint32_t ID_W = idesc(128, 0), ID_AH = idesc(64, 1);
             uint32_t stage = 0, phase = 0, it = 0, nadj = 0;
+            long long wsum = 0, ahsum = 0;
             auto mma_wtile = [&](uint32_t a_addr, uint32_t dcol, bool first) {
+                const long long w0 = a.dbg ? clock64() : 0;
                 mbar_wait(BAR(B_FULL + stage), phase);
+                if (a.dbg) wsum += clock64() - w0;
                 tc_fence_after();
                 const uint32_t b_addr = s_w + stage * TILE_BYTES;
 #pragma unroll
@@ -145,15 +149,19 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
                 for (int t = 0; t < a.T; ++t, ++it) {
                     const uint32_t par = it & 1;
                     const bool stateful = a.stateful[t] != 0;
+                    const long long c0 = a.dbg ? clock64() : 0;
                     mbar_wait(BAR(B_HREADY), par);
                     if (t > 0) { mbar_wait(BAR(B_ADJ), nadj & 1); ++nadj; }
                     tc_fence_after();
+                    const long long c1 = a.dbg ? clock64() : 0;
                     // ---- message phase
                     mma1(0);
                     mma1(1);
                     for (int g = 0; g < 8; ++g) {
                         const int slot = g & 1;
+                        const long long w0 = a.dbg ? clock64() : 0;
                         mbar_wait(BAR(B_AHREADY + slot), (g >> 1) & 1);
+                        if (a.dbg) ahsum += clock64() - w0;
                         tc_fence_after();
                         for (int tp = 0; tp < 2; ++tp)
                             mma_kslice(s_y + (slot * 2 + tp) * PANEL_BYTES, REGA, g == 0 && tp == 0);
@@ -162,8 +170,10 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
                     }
                     tc_commit(BAR(B_M));
                     // ---- gate phase over x = [h | m]
+                    const long long c2 = a.dbg ? clock64() : 0;
                     mbar_wait(BAR(B_XREADY), par);
                     tc_fence_after();
+                    const long long c3 = a.dbg ? clock64() : 0;
                     auto gate_block = [&](uint32_t dbase) {
                         for (int kp = 0; kp < 2 * KP; ++kp)
                             mma_kslice(kp < KP ? s_h + kp * PANEL_BYTES : s_x + (kp - KP) * PANEL_BYTES, dbase, kp == 0);
@@ -171,12 +181,19 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
                     if (stateful) gate_block(REGA);         // r
                     tc_commit(BAR(B_R));
                     gate_block(REGB);                       // z
+                    const long long c4 = a.dbg ? clock64() : 0;
                     mbar_wait(BAR(B_RSREADY), par);         // r has been read, r*h panels are in place
                     tc_fence_after();
+                    const long long c5 = a.dbg ? clock64() : 0;
                     gate_block(REGA);                       // hbar (W part) overwrites r
                     if (stateful)
                         for (int kp = 0; kp < KP; ++kp) mma_kslice(s_y + kp * PANEL_BYTES, REGA, false);
                     tc_commit(BAR(B_ZH));
+                    if (a.dbg && blockIdx.x == 0 && it < 64) {
+                        long long *d = a.dbg + it * 8;
+                        d[0] = clock64() - c0; d[1] = wsum; d[2] = ahsum; d[3] = c3 - c2; d[4] = c5 - c4; d[5] = c1 - c0; d[6] = c0;
+                        wsum = ahsum = 0;
+                    }
                 }
         }
     } else {
@@ -445,6 +462,8 @@ static size_t image_bytes() { return (size_t)TILES_STATEFUL * TILE_BYTES + 3 * H
 
 using namespace bmp;
 
+extern long long *g_tc_dbg_fwd;                        // ggnn_tc.cu (bmp_debug_set_buffer_fwd)
+
 size_t bmp_ggnn_tc256_workspace_bytes(int n_steps) {
     return tc256::image_bytes() * (size_t)n_steps + (size_t)tc256::MAX_CTAS * tc256::ADJ_IMG_BYTES + 4096;
 }
@@ -474,6 +493,7 @@ int bmp_ggnn_forward_tc256(const bmp_ggnn_fwd_t *a, void *stream) {
     k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.n_types = a->n_atom_types;
     k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.adj_u8 = a->adj_u8;
     k.h_out = a->h_out; k.h0_out = a->h0_out;
+    k.dbg = g_tc_dbg_fwd;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
     const size_t ib = tc256::image_bytes();
     k.scratch = ws;
@@ -507,7 +527,8 @@ int bmp_ggnn_forward_tc256(const bmp_ggnn_fwd_t *a, void *stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms > tc256::MAX_CTAS) sms = tc256::MAX_CTAS;
     const int n_tiles = (a->mb + 1) / 2;
-    const int grid = n_tiles < sms ? n_tiles : sms;
+    int grid = n_tiles < sms ? n_tiles : sms;
+    if (const char *e = getenv("BMP_TC256_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // experiments only
     cudaFuncSetAttribute(tc256::ggnn_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc256::SMEM_BYTES);
     tc256::ggnn_tc256_kernel<<<grid, 32 * (tc256::EPW + 2), tc256::SMEM_BYTES, st>>>(k);
     count_launch();

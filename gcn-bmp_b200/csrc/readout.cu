@@ -193,7 +193,7 @@ extern "C" int bmp_readout_backward(const bmp_readout_bwd_t *a, void *stream) {
     if (!aligned16({a->W_i, a->W_j, a->h, a->h0, a->DU, a->DV, a->dh, a->dh0})) { set_error("bmp_readout_backward: buffers must be 16-byte aligned"); return BMP_EINVAL; }
     const int Kcat = a->h0 ? 2 * H : H;
     const int Kj = a->variant == BMP_READOUT_R2 ? H : Kcat;
-    const bool tc = a->mode == BMP_MODE_BF16 && bmp_readout_tc_workspace_bytes(H, O) != 0;
+    const bool tc = a->mode == BMP_MODE_BF16 && H <= 128 && O <= 128 && bmp_readout_tc_workspace_bytes(H, O) != 0;   // 256: forward-only
     if (tc) {
         if ((rc = bmp_readout_tc(a->mb, a->n_atoms, H, O, a->variant, a->act, a->act_agg, a->h, a->h0, a->is_real_node,
                                  a->W_i, a->b_i, a->W_j, a->b_j, const_cast<float *>(a->g), a->dg, a->DU, a->DV, a->dh, a->dh0,

@@ -15,6 +15,20 @@ namespace rtc {
 using namespace tc;
 
 constexpr int STAGES = 3;
+// shared-memory plan (hidden / out_dim 256 is forward-only: 8 X panels, 2 weight stages of 32 KB, no transposition staging)
+template <int H, int O> struct Plan {
+    static constexpr bool BIG = H == 256 || O == 256;
+    static constexpr int ST = BIG ? 2 : STAGES;
+    static constexpr int NXP = BIG ? 8 : 4;
+    static constexpr int WT = (O > H ? O : H) * 128;
+    static constexpr int OFF_W = NXP * PANEL_BYTES;
+    static constexpr int OFF_STG = OFF_W + ST * WT;
+    static constexpr int OFF_RED = OFF_STG + (BIG ? 0 : 8 * 4096);
+    static constexpr int OFF_BAR = OFF_RED + 4 * O * 4;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int MAXC = 2 * O > 2 * H ? 2 * O : 2 * H;
+    static constexpr int TMEM_COLS = MAXC <= 128 ? 128 : (MAXC <= 256 ? 256 : 512);
+};
 
 struct Args {
     int mb, N, H, O, Kcat, Kj, act, act_agg;
@@ -44,13 +58,15 @@ template <int H, int O, bool BWD>
 __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
     constexpr int TILE_BYTES = O * 128;               // forward weight tile [O n][64 k]
     constexpr int BT_BYTES = H * 128;                 // backward weight tile [H n][64 k]
-    constexpr int WT = TILE_BYTES > BT_BYTES ? TILE_BYTES : BT_BYTES;
+    using PL = Plan<H, O>;
+    static_assert(!(BWD && PL::BIG), "hidden / out_dim 256 is forward-only");
+    constexpr int WT = PL::WT, STAGES = PL::ST;
     constexpr int NC = O / 2;                         // U/V columns per epilogue thread
-    constexpr int OFF_X = 0;                          // X panels (<= 4), later du | dv panels
-    constexpr int OFF_W = 4 * PANEL_BYTES;
-    constexpr int OFF_STG = OFF_W + STAGES * WT;
-    constexpr int OFF_RED = OFF_STG + 8 * 4096;       // [4 quarters][O] column partial sums
-    constexpr int OFF_BAR = OFF_RED + 4 * O * 4;
+    constexpr int OFF_X = 0;                          // X panels, later du | dv panels
+    constexpr int OFF_W = PL::OFF_W;
+    constexpr int OFF_STG = PL::OFF_STG;
+    constexpr int OFF_RED = PL::OFF_RED;              // [4 quarters][O] column partial sums
+    constexpr int OFF_BAR = PL::OFF_BAR;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = s32(smem), s_x = sbase + OFF_X, s_w = sbase + OFF_W, s_bar = sbase + OFF_BAR;
@@ -63,7 +79,7 @@ __global__ void __launch_bounds__(NTHR, 1) readout_tc_kernel(const Args a) {
     const int KPX = a.Kcat / 64, KPJ = a.Kj / 64;     // K panels of W_i / W_j
     const int n_fwd = KPX + KPJ;
     const int n_bwd = (O / 64) * ((a.Kcat / H) + (a.Kj / H));   // per H-wide output block: du part, dv part
-    constexpr int TMEM_COLS = (2 * O > 2 * H ? 2 * O : 2 * H) <= 128 ? 128 : 256;
+    constexpr int TMEM_COLS = PL::TMEM_COLS;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
@@ -328,17 +344,22 @@ __global__ void pack_readout_kernel(const PackArgs p) {
 using namespace bmp;
 
 extern "C" size_t bmp_readout_tc_workspace_bytes(int hidden, int out_dim) {
+    if (hidden == 256 && out_dim == 256) return (size_t)16 * 256 * 128 + (size_t)16 * 256 * 128 + 1024;   // forward only
     if ((hidden != 64 && hidden != 128) || (out_dim != 64 && out_dim != 128)) return 0;
     return (size_t)8 * out_dim * 128 + (size_t)8 * hidden * 128 + 1024;
 }
 
 template <int H, int O>
 static int launch_readout_tc(const rtc::Args &k, bool bwd, int grid, cudaStream_t st) {
-    constexpr int WT = (O > H ? O : H) * 128;
-    constexpr int smem = 4 * tc::PANEL_BYTES + rtc::STAGES * WT + 8 * 4096 + 4 * O * 4 + 256 + 1024;
+    constexpr int smem = rtc::Plan<H, O>::SMEM;
     if (bwd) {
-        cudaFuncSetAttribute(rtc::readout_tc_kernel<H, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        rtc::readout_tc_kernel<H, O, true><<<grid, tc::NTHR, smem, st>>>(k);
+        if constexpr (rtc::Plan<H, O>::BIG) {
+            set_error("readout tcgen05 path: hidden / out_dim 256 is forward-only");
+            return BMP_ESHAPE;
+        } else {
+            cudaFuncSetAttribute(rtc::readout_tc_kernel<H, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            rtc::readout_tc_kernel<H, O, true><<<grid, tc::NTHR, smem, st>>>(k);
+        }
     } else {
         cudaFuncSetAttribute(rtc::readout_tc_kernel<H, O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         rtc::readout_tc_kernel<H, O, false><<<grid, tc::NTHR, smem, st>>>(k);
@@ -353,7 +374,8 @@ int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_ag
                    const float *mask, const float *W_i, const float *b_i, const float *W_j, const float *b_j,
                    float *g, const float *dg, float *DU, float *DV, float *dh, float *dh0, void *ws, size_t ws_bytes,
                    bool images_ready, bool bwd, void *stream) {
-    if ((H != 64 && H != 128) || (O != 64 && O != 128) || variant == BMP_READOUT_SUM || N > BMP_MAX_ATOMS) {
+    const bool big = H == 256 && O == 256;
+    if ((!big && ((H != 64 && H != 128) || (O != 64 && O != 128))) || variant == BMP_READOUT_SUM || N > BMP_MAX_ATOMS) {
         set_error("readout tcgen05 path: unsupported shape H=%d O=%d variant=%d", H, O, variant);
         return BMP_ESHAPE;
     }
@@ -379,6 +401,7 @@ int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_ag
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (mb + 1) / 2;
     const int grid = n_tiles < sms ? n_tiles : sms;
+    if (big) return launch_readout_tc<256, 256>(k, bwd, grid, st);
     if (H == 64 && O == 64) return launch_readout_tc<64, 64>(k, bwd, grid, st);
     if (H == 64 && O == 128) return launch_readout_tc<64, 128>(k, bwd, grid, st);
     if (H == 128 && O == 64) return launch_readout_tc<128, 64>(k, bwd, grid, st);

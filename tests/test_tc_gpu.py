@@ -168,6 +168,35 @@ def test_tc_readout_r1_variants(H, O, use_h0, act, agg, use_mask, nobias):
         assert _rms_rel(g[k], tab[k].grad) <= gtol, k
 
 
+@pytest.mark.parametrize("use_h0,act,agg,use_mask,mb,N", [(True, "identity", "identity", False, 5, 37), (True, "tanh", "tanh", True, 301, 64),
+                                                          (False, "tanh", "identity", False, 3, 50)])
+def test_tc_readout_hidden256_forward(use_h0, act, agg, use_mask, mb, N):
+    """GGNNReadout (R1) at hidden = out_dim = 256 (BASELINE config D) on the tcgen05 kernel, forward only."""
+    import gcnbmp
+    from oracle import minichainer as F
+    H = O = 256
+    rng = np.random.default_rng(mb + N)
+    kin = 2 * H if use_h0 else H
+    params = R.init_params({"i_layer/W": (O, kin), "j_layer/W": (O, kin), "i_layer/b": (O,), "j_layer/b": (O,)}, rng, dtype=np.float64)
+    h, h0 = rng.standard_normal((mb, N, H)) * 0.5, rng.standard_normal((mb, N, H)) * 0.5
+    mask = (rng.random((mb, N)) < 0.7).astype(np.float64) if use_mask else None
+    og = R.GGNNReadout(R.P(R.wrap_params(params)), O, H, activation=act, activation_agg=agg)(F.param(h), F.param(h0) if use_h0 else None, mask)
+    f = gcnbmp.functions
+    link = gcnbmp.GGNNReadout(O, H, activation=getattr(f, act), activation_agg=getattr(f, agg))
+    link.load_params(params)
+    ht = torch.tensor(h, dtype=torch.float32, device="cuda")
+    h0t = torch.tensor(h0, dtype=torch.float32, device="cuda")
+    with torch.no_grad():
+        ref = link(ht, h0t if use_h0 else None, None if mask is None else mask.astype(np.float32))     # fp32 kernel
+        link.mode = gcnbmp.MODE_BF16
+        n0 = gcnbmp.launch_count() if hasattr(gcnbmp, "launch_count") else None
+        pg = link(ht, h0t if use_h0 else None, None if mask is None else mask.astype(np.float32))
+    assert rel_err(ref.cpu().numpy(), og.data) <= 1e-4
+    err = rel_err(pg.cpu().numpy(), og.data)
+    assert err <= MAX_TOL, err
+    assert not torch.equal(pg, ref)         # the bf16 kernel ran, not the fp32 one
+
+
 @pytest.mark.parametrize("variant,n1,n2,H,O,head,mb", [("nie", 64, 64, 128, 128, 8, 5), ("vqa", 13, 37, 64, 16, 4, 3),
                                                        ("nie", 1, 5, 64, 8, 1, 2), ("vqa", 50, 64, 128, 32, 8, 300),
                                                        ("pool", 50, 9, 64, 32, None, 7), ("pool", 64, 64, 128, 128, None, 3)])
