@@ -12,7 +12,8 @@
 //     next step by one bulk copy from a per-CTA, L2-resident bf16 image dumped at tile start)
 //   * gate phase: r -> TMEM [0,256), z -> TMEM [256,512); E3 forms r*h panels over the AH ring while z runs;
 //     hbar = [h|m] W^T + (r*h) U^T overwrites r;  E4: h <- z*hbar + (1-z)*h (fp32 master state in registers).
-// Weights stream from L2 as [128 n][64 k] SW128 tiles (88 per stateful step) through a 2-stage mbarrier ring.
+// Weights stream from L2 as [256 n][16 k] slices (8 KB, un-swizzled core-matrix layout: one N = 256 UMMA each, so the A panel
+// is read once per 256 output columns) through a 4-stage mbarrier ring -- 176 slices per stateful step.
 // Warp roles as in ggnn_tc.cu: 16 epilogue warps (TMEM lane quarter = warp%4; 16-column chunk warp/4 of every 64-column
 // block), one TMA producer warp, one MMA issuer warp.
 // Replaces models/update/ggnn_update.py:31-63 / models/models/ggnn.py:72-106 at hidden 256 (forward).
@@ -23,16 +24,22 @@ namespace tc256 {
 using namespace bmp::tc;
 
 constexpr int H = 256, KP = 4, EPW = 16, NE = 32 * EPW;
-constexpr int TILE_BYTES = 128 * 128;                 // weight tile: 128 rows (n) x 64 bf16 (k)
-constexpr int STAGES = 2;
-constexpr int T_MSG = 32, T_GATE = 16, T_U = 8;
-constexpr int TILES_STATEFUL = T_MSG + 3 * T_GATE + T_U, TILES_STATELESS = T_MSG + 2 * T_GATE;
+constexpr int TILE_BYTES = 256 * 16 * 2;              // weight slice: 256 rows (n) x 16 bf16 (k) = one UMMA k-step
+constexpr int STAGES = 4;
+constexpr int S_MSG = 16, S_GATE = 8, S_U = 4;        // 64-wide K slices per block (4 ring slices each)
+constexpr int TILES_STATEFUL = 4 * (S_MSG + 3 * S_GATE + S_U), TILES_STATELESS = 4 * (S_MSG + 2 * S_GATE);
 constexpr int OFF_H = 0, OFF_X = 4 * PANEL_BYTES, OFF_Y = 8 * PANEL_BYTES, OFF_W = 12 * PANEL_BYTES;
 constexpr int OFF_BAR = OFF_W + STAGES * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr uint32_t REGA = 0, REGB = 256;              // TMEM column regions
 constexpr int ADJ_IMG_BYTES = 8 * ADJ_TILE_BYTES;     // staged adjacency of a tile: 64 KB
 constexpr int MAX_CTAS = 160;
+
+// un-swizzled K-major B slice [256 n][16 k]: core matrices (8 n x 16 B) contiguous; the two k halves 4096 B apart (LBO),
+// consecutive 8-row groups 128 B apart (SBO)
+__device__ __forceinline__ uint64_t desc_kmajor_plain(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
 
 struct Args {
     int mb, N, T, n_types;
@@ -56,8 +63,8 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
     const uint32_t s_h = sbase + OFF_H, s_x = sbase + OFF_X, s_y = sbase + OFF_Y, s_w = sbase + OFF_W;
     const uint32_t s_bar = sbase + OFF_BAR;
     auto BAR = [&](int i) { return s_bar + 8u * i; };
-    constexpr int B_FULL = 0, B_EMPTY = 2, B_HREADY = 4, B_ADJ = 5, B_D1 = 6, B_AHREADY = 10, B_AHFREE = 12, B_M = 14,
-                  B_XREADY = 15, B_R = 16, B_RSREADY = 17, B_ZH = 18, NBAR = 19;
+    constexpr int B_FULL = 0, B_EMPTY = 4, B_HREADY = 8, B_ADJ = 9, B_D1 = 10, B_AHREADY = 14, B_AHFREE = 16, B_M = 18,
+                  B_XREADY = 19, B_R = 20, B_RSREADY = 21, B_ZH = 22, NBAR = 23;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * NBAR + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,25 +120,21 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
     } else if (warp == EPW + 1) {
         // ===================== MMA issuer
         if (lane == 0) {
-            constexpr uint32_t ID_W = idesc(128, 0), ID_AH = idesc(64, 1);
+            constexpr uint32_t ID_W = idesc(256, 0), ID_AH = idesc(64, 1);
             uint32_t stage = 0, phase = 0, it = 0, nadj = 0;
             long long wsum = 0, ahsum = 0;
-            auto mma_wtile = [&](uint32_t a_addr, uint32_t dcol, bool first) {
-                const long long w0 = a.dbg ? clock64() : 0;
-                mbar_wait(BAR(B_FULL + stage), phase);
-                if (a.dbg) wsum += clock64() - w0;
-                tc_fence_after();
-                const uint32_t b_addr = s_w + stage * TILE_BYTES;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma(tmem + dcol, desc_kmajor(a_addr + k * 32), desc_kmajor(b_addr + k * 32), ID_W, (first && k == 0) ? 0u : 1u);
-                tc_commit(BAR(B_EMPTY + stage));
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            };
-            // both N halves of one 64-wide K slice
+            // one 64-wide K slice against all 256 output columns: four ring slices, one N = 256 UMMA each
             auto mma_kslice = [&](uint32_t a_addr, uint32_t dbase, bool first) {
-                mma_wtile(a_addr, dbase, first);
-                mma_wtile(a_addr, dbase + 128, first);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const long long w0 = a.dbg ? clock64() : 0;
+                    mbar_wait(BAR(B_FULL + stage), phase);
+                    if (a.dbg) wsum += clock64() - w0;
+                    tc_fence_after();
+                    tc_mma(tmem + dbase, desc_kmajor(a_addr + kk * 32), desc_kmajor_plain(s_w + stage * TILE_BYTES), ID_W, (first && kk == 0) ? 0u : 1u);
+                    tc_commit(BAR(B_EMPTY + stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
             };
             auto mma1 = [&](int g) {
                 const int slot = g & 1, p = g >> 2, cb = g & 3;
@@ -409,8 +412,8 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
 }
 
 // ---------------------------------------------------------------- weight packing
-// bf16 SW128 B-operand tiles [128 n][64 k] of one step in consumption order:
-//   [MMA-2: group g = (p, cb) x bond type tp x N half] [r: K block x N half] [z] [hbar] [U]   (stateless: no r, no U)
+// bf16 B-operand slices [256 n][16 k] of one step in consumption order (four per 64-wide K slice):
+//   [MMA-2: group g = (p, cb) x bond type tp] [r: K block] [z] [hbar] [U]   (stateless: no r, no U)
 struct PackArgs {
     int stateful;
     const float *msg_W;
@@ -420,32 +423,32 @@ struct PackArgs {
 };
 
 __global__ void pack256_kernel(const PackArgs p) {
-    const int ntiles = p.stateful ? TILES_STATEFUL : TILES_STATELESS;
-    const long total = (long)ntiles * 128 * 64;
+    const int nslices = p.stateful ? TILES_STATEFUL : TILES_STATELESS;
+    const long total = (long)nslices * 256 * 16;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int k = idx & 63, nl = (idx >> 6) & 127, tile = (int)(idx >> 13);
-        const int nh = tile & 1, n = nh * 128 + nl;
+        const int k = idx & 15, n = (idx >> 4) & 255, slice = (int)(idx >> 12);
+        const int ks = slice >> 2, kin = (slice & 3) * 16 + k;       // 64-wide K slice, column inside it
         float w;
-        if (tile < T_MSG) {
-            const int g = tile >> 2, tp = (tile >> 1) & 1, e = 2 * (g >> 2) + tp, cp = (g & 3) * 64 + k;
+        if (ks < S_MSG) {
+            const int g = ks >> 1, tp = ks & 1, e = 2 * (g >> 2) + tp, cp = (g & 3) * 64 + kin;
             w = p.msg_W[((long)n * 4 + e) * H + cp];
         } else {
-            const int idx2 = tile - T_MSG;
-            int g = idx2 / T_GATE;
-            const int kp = (idx2 % T_GATE) >> 1;
+            const int i2 = ks - S_MSG;
+            int g = i2 / S_GATE;
+            const int kp = i2 % S_GATE;
             if (!p.stateful) g += 1;
             if (g < 3) {
-                const int K = kp * 64 + k;
+                const int K = kp * 64 + kin;
                 const float *W = g == 0 ? p.g.W_r : (g == 1 ? p.g.W_z : p.g.W);
                 w = W[(long)n * 2 * H + K];
                 if (p.stateful && K < H && g < 2) w += (g == 0 ? p.g.U_r : p.g.U_z)[(long)n * H + K];
             } else {
-                const int K = ((tile - T_MSG - 3 * T_GATE) >> 1) * 64 + k;
+                const int K = (ks - S_MSG - 3 * S_GATE) * 64 + kin;
                 w = p.g.U[(long)n * H + K];
             }
         }
-        const uint32_t off = (uint32_t)nl * 128u + ((((uint32_t)(k >> 3) ^ ((uint32_t)nl & 7u)) << 4) | (((uint32_t)k & 7u) << 1));
-        *reinterpret_cast<__nv_bfloat16 *>(p.img + (size_t)tile * TILE_BYTES + off) = __float2bfloat16_rn(w);
+        const uint32_t off = (uint32_t)(k >> 3) * 4096u + (uint32_t)n * 16u + ((uint32_t)k & 7u) * 2u;
+        *reinterpret_cast<__nv_bfloat16 *>(p.img + (size_t)slice * TILE_BYTES + off) = __float2bfloat16_rn(w);
     }
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < H; c += blockDim.x) {
