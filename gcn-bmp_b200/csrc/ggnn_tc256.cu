@@ -173,22 +173,22 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
                     }
                     tc_commit(BAR(B_M));
                     // ---- gate phase over x = [h | m]
+                    // z, h part: needs only the state panels, runs while E2 forms the m panels (TMEM [256,512) is free after the last E1)
+                    for (int kp = 0; kp < KP; ++kp) mma_kslice(s_h + kp * PANEL_BYTES, REGB, kp == 0);
                     const long long c2 = a.dbg ? clock64() : 0;
                     mbar_wait(BAR(B_XREADY), par);
                     tc_fence_after();
                     const long long c3 = a.dbg ? clock64() : 0;
-                    auto gate_block = [&](uint32_t dbase) {
-                        for (int kp = 0; kp < 2 * KP; ++kp)
-                            mma_kslice(kp < KP ? s_h + kp * PANEL_BYTES : s_x + (kp - KP) * PANEL_BYTES, dbase, kp == 0);
-                    };
-                    if (stateful) gate_block(REGA);         // r
+                    auto xa = [&](int kp) { return kp < KP ? s_h + kp * PANEL_BYTES : s_x + (kp - KP) * PANEL_BYTES; };
+                    if (stateful)
+                        for (int kp = 0; kp < 2 * KP; ++kp) mma_kslice(xa(kp), REGA, kp == 0);        // r
                     tc_commit(BAR(B_R));
-                    gate_block(REGB);                       // z
+                    for (int kp = KP; kp < 2 * KP; ++kp) mma_kslice(xa(kp), REGB, false);             // z, m part (E3 overlaps)
                     const long long c4 = a.dbg ? clock64() : 0;
                     mbar_wait(BAR(B_RSREADY), par);         // r has been read, r*h panels are in place
                     tc_fence_after();
                     const long long c5 = a.dbg ? clock64() : 0;
-                    gate_block(REGA);                       // hbar (W part) overwrites r
+                    for (int kp = 0; kp < 2 * KP; ++kp) mma_kslice(xa(kp), REGA, kp == 0);            // hbar (W part) overwrites r
                     if (stateful)
                         for (int kp = 0; kp < KP; ++kp) mma_kslice(s_y + kp * PANEL_BYTES, REGA, false);
                     tc_commit(BAR(B_ZH));
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
 
 // ---------------------------------------------------------------- weight packing
 // bf16 B-operand slices [256 n][16 k] of one step in consumption order (four per 64-wide K slice):
-//   [MMA-2: group g = (p, cb) x bond type tp] [r: K block] [z] [hbar] [U]   (stateless: no r, no U)
+//   [MMA-2: group g = (p, cb) x bond type tp] [z: h blocks] [r: K block] [z: m blocks] [hbar] [U]   (stateless: no r, no U)
 struct PackArgs {
     int stateful;
     const float *msg_W;
@@ -433,18 +433,26 @@ __global__ void pack256_kernel(const PackArgs p) {
             const int g = ks >> 1, tp = ks & 1, e = 2 * (g >> 2) + tp, cp = (g & 3) * 64 + kin;
             w = p.msg_W[((long)n * 4 + e) * H + cp];
         } else {
-            const int i2 = ks - S_MSG;
-            int g = i2 / S_GATE;
-            const int kp = i2 % S_GATE;
-            if (!p.stateful) g += 1;
+            // gate K slices in issue order: z (h part: 4) | r (8, stateful only) | z (m part: 4) | hbar (8) | U (4, stateful only)
+            int j = ks - S_MSG, g, kp;
+            if (j < KP) { g = 1; kp = j; }
+            else {
+                j -= KP;
+                if (p.stateful && j < 2 * KP) { g = 0; kp = j; }
+                else {
+                    if (p.stateful) j -= 2 * KP;
+                    if (j < KP) { g = 1; kp = KP + j; }
+                    else if (j < 3 * KP) { g = 2; kp = j - KP; }
+                    else { g = 3; kp = j - 3 * KP; }
+                }
+            }
             if (g < 3) {
                 const int K = kp * 64 + kin;
                 const float *W = g == 0 ? p.g.W_r : (g == 1 ? p.g.W_z : p.g.W);
                 w = W[(long)n * 2 * H + K];
                 if (p.stateful && K < H && g < 2) w += (g == 0 ? p.g.U_r : p.g.U_z)[(long)n * H + K];
             } else {
-                const int K = (ks - S_MSG - 3 * S_GATE) * 64 + kin;
-                w = p.g.U[(long)n * H + K];
+                w = p.g.U[(long)n * H + kp * 64 + kin];
             }
         }
         const uint32_t off = (uint32_t)(k >> 3) * 4096u + (uint32_t)n * 16u + ((uint32_t)k & 7u) * 2u;
