@@ -1,0 +1,206 @@
+// heads.cu -- the remaining link-prediction heads of the reference and the optimizer hooks (f-2), fp32.
+//   pair features   SymMLP input [l + r | l * r] (models/mlp.py:104-105), DistMult product l * r (BilinearDiag, mlp.py:154-197:
+//                   a diagonal bilinear form is Linear(l * r)), MLP input [l | r] (train_binary.py:98-100)
+//   bilinear        chainer.links.Bilinear(left, right, out) of the NTN head (mlp.py:47-74):
+//                   y[b,k] = sum_ij e1[b,i] W[i,j,k] e2[b,j] + e1 V1 + e2 V2 + b, contracted as u = e1 W_flat (GEMM) and a
+//                   rank-R reduction -- Chainer's (B, L, R) outer product is never materialised
+//   gradient hooks  GradientClipping -> WeightDecay -> Lasso in the order train_binary.py:537-543 adds them
+// HBM-bound elementwise / reduction work: grid-stride loops, float4 where the shapes allow.
+#include "common.cuh"
+
+namespace bmp {
+
+// ---------------------------------------------------------------- pair features
+__global__ void pairfeat_fwd_kernel(const float *__restrict__ l, const float *__restrict__ r, float *__restrict__ out,
+                                    long n, int D, int kind) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / D;
+        const int c = (int)(i - b * D);
+        const float x = l[i], y = r[i];
+        if (kind == BMP_PAIR_SYM) { out[b * 2 * D + c] = x + y; out[b * 2 * D + D + c] = x * y; }
+        else if (kind == BMP_PAIR_PROD) out[i] = x * y;
+        else { out[b * 2 * D + c] = x; out[b * 2 * D + D + c] = y; }
+    }
+}
+__global__ void pairfeat_bwd_kernel(const float *__restrict__ l, const float *__restrict__ r, const float *__restrict__ dout,
+                                    float *__restrict__ dl, float *__restrict__ dr, long n, int D, int kind) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / D;
+        const int c = (int)(i - b * D);
+        if (kind == BMP_PAIR_SYM) {
+            const float ds = dout[b * 2 * D + c], dp = dout[b * 2 * D + D + c];
+            dl[i] = ds + dp * r[i];
+            dr[i] = ds + dp * l[i];
+        } else if (kind == BMP_PAIR_PROD) {
+            const float dp = dout[i];
+            dl[i] = dp * r[i];
+            dr[i] = dp * l[i];
+        } else {
+            dl[i] = dout[b * 2 * D + c];
+            dr[i] = dout[b * 2 * D + D + c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- bilinear (NTN)
+// y[b,k] = sum_j u[b,j,k] e2[b,j] + sum_i e1[b,i] V1[i,k] + sum_j e2[b,j] V2[j,k] + bias[k]; one thread per (b,k)
+__global__ void bilinear_reduce_kernel(const float *__restrict__ u, const float *__restrict__ e1, const float *__restrict__ e2,
+                                       const float *__restrict__ V1, const float *__restrict__ V2, const float *__restrict__ bias,
+                                       float *__restrict__ y, long rows, int L, int R, int K) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < rows * K; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / K;
+        const int k = (int)(t - b * K);
+        const float *ub = u + b * (long)R * K, *x1 = e1 + b * L, *x2 = e2 + b * R;
+        float s = bias ? bias[k] : 0.f;
+        for (int j = 0; j < R; ++j) s = fmaf(ub[(long)j * K + k] + (V2 ? V2[(long)j * K + k] : 0.f), x2[j], s);
+        if (V1)
+            for (int i = 0; i < L; ++i) s = fmaf(x1[i], V1[(long)i * K + k], s);
+        y[t] = s;
+    }
+}
+// du[b,j,k] = dy[b,k] e2[b,j];  de2[b,j] = sum_k (u[b,j,k] + V2[j,k]) dy[b,k]; one thread per (b,j)
+__global__ void bilinear_bwd_right_kernel(const float *__restrict__ u, const float *__restrict__ e2, const float *__restrict__ V2,
+                                          const float *__restrict__ dy, float *__restrict__ du, float *__restrict__ de2,
+                                          long rows, int R, int K) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < rows * R; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / R;
+        const int j = (int)(t - b * R);
+        const float x = e2[t];
+        const float *g = dy + b * K, *uj = u + t * K;
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) {
+            du[t * K + k] = g[k] * x;
+            s = fmaf(uj[k] + (V2 ? V2[(long)j * K + k] : 0.f), g[k], s);
+        }
+        de2[t] = s;
+    }
+}
+// de1[b,i] += sum_k V1[i,k] dy[b,k]
+__global__ void bilinear_bwd_left_kernel(const float *__restrict__ V1, const float *__restrict__ dy, float *__restrict__ de1,
+                                         long rows, int L, int K) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < rows * L; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / L;
+        const int i = (int)(t - b * L);
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s = fmaf(V1[(long)i * K + k], dy[b * K + k], s);
+        de1[t] += s;
+    }
+}
+
+// ---------------------------------------------------------------- optimizer hooks
+__global__ void sumsq_kernel(const float *__restrict__ g, long n, float *__restrict__ out) {
+    float s = 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s = fmaf(g[i], g[i], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        atomicAdd(out, tot);
+    }
+}
+__global__ void hooks_kernel(float *__restrict__ g, const float *__restrict__ p, long n, float clip, float l2, float l1,
+                             const float *__restrict__ sumsq) {
+    float scale = 1.f;
+    if (clip > 0.f) {
+        const float rate = clip / sqrtf(*sumsq);       // chainer.optimizer.GradientClipping: rate = threshold / norm
+        if (rate < 1.f) scale = rate;
+    }
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float w = p[i];
+        float v = g[i] * scale;
+        v = fmaf(l2, w, v);                                                // WeightDecay: g += rate * p
+        v = fmaf(l1, w > 0.f ? 1.f : (w < 0.f ? -1.f : 0.f), v);           // Lasso: g += rate * sign(p)
+        g[i] = v;
+    }
+}
+
+static int grid_for(long n) {
+    long g = (n + 255) / 256;
+    return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+}  // namespace bmp
+
+using namespace bmp;
+
+extern "C" int bmp_pair_features_forward(const float *left, const float *right, float *out, int rows, int dim, int kind, void *stream) {
+    if (!left || !right || !out) { set_error("bmp_pair_features_forward: null pointer"); return BMP_EINVAL; }
+    if (kind < BMP_PAIR_SYM || kind > BMP_PAIR_CONCAT) { set_error("bmp_pair_features_forward: bad kind %d", kind); return BMP_EINVAL; }
+    if (rows <= 0) return BMP_OK;
+    if (dim <= 0) { set_error("bmp_pair_features_forward: bad dim %d", dim); return BMP_ESHAPE; }
+    const long n = (long)rows * dim;
+    pairfeat_fwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(left, right, out, n, dim, kind);
+    count_launch();
+    return check_launch("pairfeat_fwd_kernel");
+}
+
+extern "C" int bmp_pair_features_backward(const float *left, const float *right, const float *d_out, float *d_left, float *d_right,
+                                          int rows, int dim, int kind, void *stream) {
+    if (!left || !right || !d_out || !d_left || !d_right) { set_error("bmp_pair_features_backward: null pointer"); return BMP_EINVAL; }
+    if (kind < BMP_PAIR_SYM || kind > BMP_PAIR_CONCAT) { set_error("bmp_pair_features_backward: bad kind %d", kind); return BMP_EINVAL; }
+    if (rows <= 0) return BMP_OK;
+    const long n = (long)rows * dim;
+    pairfeat_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(left, right, d_out, d_left, d_right, n, dim, kind);
+    count_launch();
+    return check_launch("pairfeat_bwd_kernel");
+}
+
+extern "C" int bmp_bilinear_forward(const float *e1, const float *e2, const float *W, const float *V1, const float *V2, const float *b,
+                                    float *u, float *y, int rows, int left, int right, int out, void *stream) {
+    if (!e1 || !e2 || !W || !u || !y) { set_error("bmp_bilinear_forward: null pointer"); return BMP_EINVAL; }
+    if ((V1 != nullptr) != (V2 != nullptr)) { set_error("bmp_bilinear_forward: V1 and V2 come together"); return BMP_EINVAL; }
+    if (rows <= 0) return BMP_OK;
+    if (left <= 0 || right <= 0 || out <= 0) { set_error("bmp_bilinear_forward: bad dims"); return BMP_ESHAPE; }
+    // u (rows, right*out) = e1 (rows, left) x W viewed as (left, right*out): the data-gradient form of the Linear kernel
+    int rc = bmp_linear_backward(e1, W, nullptr, const_cast<float *>(e1), u, nullptr, nullptr, rows, right * out, left, BMP_ACT_IDENTITY, stream);
+    if (rc) return rc;
+    bilinear_reduce_kernel<<<grid_for((long)rows * out), 256, 0, (cudaStream_t)stream>>>(u, e1, e2, V1, V2, b, y, rows, left, right, out);
+    count_launch();
+    return check_launch("bilinear_reduce_kernel");
+}
+
+extern "C" int bmp_bilinear_backward(const float *e1, const float *e2, const float *W, const float *V1, const float *V2, const float *u,
+                                     const float *dy, float *du, float *de1, float *de2, float *dW, float *dV1, float *dV2, float *db,
+                                     int rows, int left, int right, int out, void *stream) {
+    if (!e1 || !e2 || !W || !u || !dy || !du || !de1 || !de2) { set_error("bmp_bilinear_backward: null pointer"); return BMP_EINVAL; }
+    if (rows <= 0) return BMP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    bilinear_bwd_right_kernel<<<grid_for((long)rows * right), 256, 0, st>>>(u, e2, V2, dy, du, de2, rows, right, out);
+    count_launch();
+    if ((rc = check_launch("bilinear_bwd_right_kernel"))) return rc;
+    // de1 = du W_flat^T: the forward form of the Linear kernel with W_flat as a (left, right*out) weight
+    if ((rc = bmp_linear_forward(du, W, nullptr, de1, rows, right * out, left, BMP_ACT_IDENTITY, stream))) return rc;
+    if (V1) {
+        bilinear_bwd_left_kernel<<<grid_for((long)rows * left), 256, 0, st>>>(V1, dy, de1, rows, left, out);
+        count_launch();
+        if ((rc = check_launch("bilinear_bwd_left_kernel"))) return rc;
+    }
+    if (dW && (rc = bmp_wgrad(e1, left, du, right * out, dW, right * out, rows, left, right * out, stream))) return rc;
+    if (dV1 && (rc = bmp_wgrad(e1, left, dy, out, dV1, out, rows, left, out, stream))) return rc;
+    if (dV2 && (rc = bmp_wgrad(e2, right, dy, out, dV2, out, rows, right, out, stream))) return rc;
+    if (db && (rc = bmp_colsum(dy, out, db, 1, rows, out, stream))) return rc;
+    return BMP_OK;
+}
+
+extern "C" int bmp_grad_hooks(float *grad, const float *param, int n, float clip_threshold, float l2_rate, float l1_rate,
+                              float *norm_ws, void *stream) {
+    if (!grad || !param) { set_error("bmp_grad_hooks: null pointer"); return BMP_EINVAL; }
+    if (n <= 0 || (clip_threshold <= 0.f && l2_rate == 0.f && l1_rate == 0.f)) return BMP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (clip_threshold > 0.f) {
+        if (!norm_ws) { set_error("bmp_grad_hooks: GradientClipping needs one float of device scratch (norm_ws)"); return BMP_EINVAL; }
+        if (cudaMemsetAsync(norm_ws, 0, sizeof(float), st) != cudaSuccess) { set_error("bmp_grad_hooks: memset failed"); return BMP_ECUDA; }
+        sumsq_kernel<<<grid_for(n), 256, 0, st>>>(grad, n, norm_ws);
+        count_launch();
+        if ((rc = check_launch("sumsq_kernel"))) return rc;
+    }
+    hooks_kernel<<<grid_for(n), 256, 0, st>>>(grad, param, n, clip_threshold, l2_rate, l1_rate, norm_ws);
+    count_launch();
+    return check_launch("hooks_kernel");
+}

@@ -10,7 +10,7 @@ from . import functional
 from . import metrics
 from .links import (MAX_ATOMIC_NUM, functions, Link, ChainList, GraphLinear, GGNNUpdate, RelGCNUpdate,
                     GGNNReadout, GGNN, GGNNMono, RelGCN, NieFineCoattention, VQAParallelCoattention,
-                    PoolingFineCoattention, HolE, HOLE, GraphConvPredictorForPair,
+                    PoolingFineCoattention, HolE, HOLE, MLP, SymMLP, NTN, DistMult, BilinearDiag, GraphConvPredictorForPair,
                     sigmoid_cross_entropy, seed)
 
 __version__ = "0.1.0"

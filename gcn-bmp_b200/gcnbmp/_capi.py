@@ -16,6 +16,7 @@ OK, EINVAL, ESHAPE, EARCH, ECUDA = 0, -1, -2, -3, -4
 ACT = {"identity": 0, "tanh": 1, "relu": 2, "sigmoid": 3}
 READOUT_R1, READOUT_R2, READOUT_SUM = 1, 2, 3
 COATTN_FINE, COATTN_POOL = 0, 1
+PAIR_SYM, PAIR_PROD, PAIR_CONCAT = 0, 1, 2
 MODE_F32, MODE_BF16 = 0, 1
 
 fp = C.c_void_p   # device pointer
@@ -114,6 +115,11 @@ def _load():
         "bmp_colsum": [fp, i, fp, i, i64, i, vp],
         "bmp_sigmoid_ce": [fp, fp, fp, fp, i, f, vp],
         "bmp_adam_step": [fp, fp, fp, fp, i, f, f, f, f, f, i, vp],
+        "bmp_pair_features_forward": [fp, fp, fp, i, i, i, vp],
+        "bmp_pair_features_backward": [fp, fp, fp, fp, fp, i, i, i, vp],
+        "bmp_bilinear_forward": [fp, fp, fp, fp, fp, fp, fp, fp, i, i, i, i, vp],
+        "bmp_bilinear_backward": [fp] * 14 + [i, i, i, i, vp],
+        "bmp_grad_hooks": [fp, fp, i, f, f, f, fp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -136,6 +142,7 @@ EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_r
            "bmp_relgcn_backward", "bmp_relgcn_tc_workspace_bytes", "bmp_rescale_adj", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_coattn_tc_workspace_bytes", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
+           "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]
 
 

@@ -476,6 +476,64 @@ class HoleCorr(torch.autograd.Function):
         return dl, dr
 
 
+class PairFeatures(torch.autograd.Function):
+    """[l + r | l * r] (SymMLP, models/mlp.py:104-105), l * r (DistMult's diagonal bilinear form, mlp.py:154-197) or
+    [l | r] (MLP head, train_binary.py:98-100)."""
+
+    @staticmethod
+    def forward(ctx, left, right, kind):
+        _need_cuda(left, right)
+        left, right = _f32(left), _f32(right)
+        if left.shape != right.shape or left.dim() != 2:
+            raise ValueError("gcnbmp: pair features need two (mb, D) arrays of one shape, got %s and %s" % (tuple(left.shape), tuple(right.shape)))
+        mb, D = left.shape
+        out = torch.empty((mb, D if kind == K.PAIR_PROD else 2 * D), device=left.device, dtype=torch.float32)
+        K.check(K.lib.bmp_pair_features_forward(_p(left), _p(right), _p(out), mb, D, kind, _stream()))
+        ctx.save_for_backward(left, right)
+        ctx.kind = kind
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        left, right = ctx.saved_tensors
+        mb, D = left.shape
+        d_out = _f32(d_out)
+        dl, dr = torch.empty_like(left), torch.empty_like(right)
+        K.check(K.lib.bmp_pair_features_backward(_p(left), _p(right), _p(d_out), _p(dl), _p(dr), mb, D, ctx.kind, _stream()))
+        return dl, dr, None
+
+
+class Bilinear(torch.autograd.Function):
+    """chainer.links.Bilinear(left, right, out) with V1, V2, b (the NTN head's ntn_layer, models/mlp.py:51,67)."""
+
+    @staticmethod
+    def forward(ctx, e1, e2, W, V1, V2, b):
+        _need_cuda(e1, e2)
+        e1, e2 = _f32(e1), _f32(e2)
+        mb, L = e1.shape
+        R, Ko = W.shape[1], W.shape[2]
+        if e2.shape != (mb, R) or W.shape[0] != L:
+            raise ValueError("gcnbmp: Bilinear shapes e1 %s e2 %s W %s" % (tuple(e1.shape), tuple(e2.shape), tuple(W.shape)))
+        u = torch.empty((mb, R * Ko), device=e1.device, dtype=torch.float32)
+        y = torch.empty((mb, Ko), device=e1.device, dtype=torch.float32)
+        K.check(K.lib.bmp_bilinear_forward(_p(e1), _p(e2), _p(W), _p(V1), _p(V2), _p(b), _p(u), _p(y), mb, L, R, Ko, _stream()))
+        ctx.save_for_backward(e1, e2, W, V1, V2, b, u)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        e1, e2, W, V1, V2, b, u = ctx.saved_tensors
+        mb, L = e1.shape
+        R, Ko = W.shape[1], W.shape[2]
+        dy = _f32(dy)
+        du = torch.empty_like(u)
+        de1, de2 = torch.empty_like(e1), torch.empty_like(e2)
+        (dW, dV1, dV2, db), rets = _grad_targets([W, V1, V2, b])
+        K.check(K.lib.bmp_bilinear_backward(_p(e1), _p(e2), _p(W), _p(V1), _p(V2), _p(u), _p(dy), _p(du), _p(de1), _p(de2),
+                                            _p(dW), _p(dV1), _p(dV2), _p(db), mb, L, R, Ko, _stream()))
+        return (de1, de2) + tuple(rets)
+
+
 class Linear(torch.autograd.Function):
     """links.Linear + activation: act(x W^T + b)."""
 

@@ -627,6 +627,81 @@ class HolE(Link):
 HOLE = HolE   # hole.py:12-50 defines the same class twice under both spellings
 
 
+class MLP(Link):
+    """models/mlp.py:20-45: hidden Linear+act stack -> l_out on ONE input (the pair predictor feeds it [g1 | g2])."""
+
+    def __init__(self, out_dim, hidden_dims=(32, 16), activation=functions.relu):
+        Link.__init__(self)
+        self.add_link("layers", ChainList([_Linear(None, d) for d in hidden_dims]))
+        self.add_link("l_out", _Linear(None, out_dim))
+        self.__dict__.update(activation=activation)
+
+    def __call__(self, x):
+        h = _as_device(x, torch.float32)
+        for l in self._children["layers"]:
+            h = l(h, self.activation)
+        return self.l_out(h)
+
+
+class SymMLP(MLP):
+    """models/mlp.py:95-110: the same stack on [l + r | l * r] (symmetric in its two inputs)."""
+
+    def __call__(self, left_x, right_x):
+        h = Fn.PairFeatures.apply(_as_device(left_x, torch.float32), _as_device(right_x, torch.float32), K.PAIR_SYM)
+        return MLP.__call__(self, h)
+
+
+class NTN(Link):
+    """models/mlp.py:47-74: links.Bilinear(left, right, ntn_out_dim) -> hidden Linear+act stack -> l_out.  As in the reference
+    there is no non-linearity between the bilinear layer and the first Linear."""
+
+    def __init__(self, left_dim, right_dim, out_dim, ntn_out_dim=8, hidden_dims=(16,), activation=functions.relu):
+        Link.__init__(self)
+        self.add_link("ntn_layer", _Bilinear(left_dim, right_dim, ntn_out_dim))
+        self.add_link("mlp_layers", ChainList([_Linear(None, d) for d in hidden_dims]))
+        self.add_link("l_out", _Linear(None, out_dim))
+        self.__dict__.update(left_dim=left_dim, right_dim=right_dim, out_dim=out_dim, hidden_dims=hidden_dims, activation=activation)
+
+    def __call__(self, left_x, right_x):
+        n = self.ntn_layer
+        h = Fn.Bilinear.apply(_as_device(left_x, torch.float32), _as_device(right_x, torch.float32), n.W, n.V1, n.V2, n.b)
+        for l in self._children["mlp_layers"]:
+            h = l(h, self.activation)
+        return self.l_out(h)
+
+
+class BilinearDiag(Link):
+    """models/mlp.py:154-197: bilinear form with diagonal slices, y[b,k] = sum_i e1[b,i] W[k,i] e2[b,i].  The reference builds
+    the (L, R, out) tensor from `self.W.data` (mlp.py:186-192), so NO gradient reaches W; kept that way."""
+
+    def __init__(self, left_size, right_size, out_size):
+        Link.__init__(self)
+        if left_size != right_size:
+            raise AssertionError("BilinearDiag: left_size == right_size required (models/mlp.py:160)")
+        self.add_param("W", (out_size, left_size))
+
+    def __call__(self, e1, e2):
+        prod = Fn.PairFeatures.apply(_as_device(e1, torch.float32), _as_device(e2, torch.float32), K.PAIR_PROD)
+        return Fn.Linear.apply(prod, self.W.detach(), None, Fn.act_code(functions.identity))
+
+
+class DistMult(Link):
+    """models/mlp.py:77-93: BilinearDiag -> hidden Linear+act stack -> l_out."""
+
+    def __init__(self, left_dim, right_dim, out_dim, dm_out_dim=8, hidden_dims=(16,), activation=functions.relu):
+        Link.__init__(self)
+        self.add_link("dm_layer", BilinearDiag(left_dim, right_dim, dm_out_dim))
+        self.add_link("mlp_layers", ChainList([_Linear(None, d) for d in hidden_dims]))
+        self.add_link("l_out", _Linear(None, out_dim))
+        self.__dict__.update(activation=activation)
+
+    def __call__(self, left_x, right_x):
+        h = self.dm_layer(left_x, right_x)
+        for l in self._children["mlp_layers"]:
+            h = l(h, self.activation)
+        return self.l_out(h)
+
+
 class GraphConvPredictorForPair(Link):
     """train_binary.py:59-141 -- siamese encoder, co-attention, link-prediction head."""
 
@@ -652,6 +727,8 @@ class GraphConvPredictorForPair(Link):
             g1, g2 = self.attn(a1, g1, a2, g2)
         if self.mlp is None:
             raise ValueError('[ERROR] No methods for similarity prediction')
+        if type(self.mlp) is MLP:        # train_binary.py:98-100: the plain MLP head sees F.concat((g1, g2), axis=-1)
+            return self.mlp(Fn.PairFeatures.apply(g1, g2, K.PAIR_CONCAT))
         return self.mlp(g1, g2)
 
     def predict(self, atoms_1, adjs_1, atoms_2, adjs_2):

@@ -36,13 +36,60 @@ class Adam(object):
         Fn.params_changed()
 
 
+class GradientHooks(object):
+    """The optimizer hooks train_binary.py:537-543 installs, applied to the flat gradient in the reference's order right
+    before the update (after the allreduce under data parallelism, as ParallelUpdater sums gradients before
+    optimizer.update): GradientClipping(max_norm) -> WeightDecay(l2_rate) -> Lasso(l1_rate).  Zero / negative = off."""
+
+    def __init__(self, flat, gflat, max_norm=0.0, l2_rate=0.0, l1_rate=0.0):
+        self.flat, self.gflat = flat, gflat
+        self.max_norm, self.l2_rate, self.l1_rate = float(max_norm), float(l2_rate), float(l1_rate)
+        self.norm_ws = torch.zeros((1,), device=flat.device, dtype=torch.float32)
+
+    @property
+    def active(self):
+        return self.max_norm > 0 or self.l2_rate > 0 or self.l1_rate > 0
+
+    def apply(self):
+        p = lambda t: C.c_void_p(t.data_ptr())
+        K.check(K.lib.bmp_grad_hooks(p(self.gflat), p(self.flat), self.gflat.numel(), max(self.max_norm, 0.0),
+                                     max(self.l2_rate, 0.0), max(self.l1_rate, 0.0), p(self.norm_ws),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+class ExponentialShift(object):
+    """chainer.training.extensions.ExponentialShift('alpha', rate) as train_binary.py:638-646 uses it: every call multiplies
+    the optimizer's alpha by `rate` (value = init * rate**t, clamped at `target` when given).  `ManualScheduleTrigger`
+    becomes `epochs=[...]` + `maybe(epoch)`: the shift fires once when one of the listed epochs is reached."""
+
+    def __init__(self, optimizer, rate, init=None, target=None, epochs=None):
+        self.opt, self.rate, self.target, self.t = optimizer, float(rate), target, 0
+        self.init = optimizer.hp[0] if init is None else float(init)
+        self.epochs, self._fired = (set(epochs) if epochs is not None else None), set()
+
+    def __call__(self):
+        self.t += 1
+        value = self.init * self.rate ** self.t
+        if self.target is not None:
+            value = max(value, self.target) if self.rate < 1 else min(value, self.target)
+        self.opt.hp = (value,) + tuple(self.opt.hp[1:])
+        return value
+
+    def maybe(self, epoch):
+        if self.epochs is not None and epoch in self.epochs and epoch not in self._fired:
+            self._fired.add(epoch)
+            return self()
+        return None
+
+
 class PairTrainer(object):
     """One `step()` = forward + backward over all pairs given (split into micro-batches of
     `chunk` pairs so the activation stash stays bounded), gradient allreduce, Adam update.
     Inputs may be device tensors (resident) or host arrays/tensors (streamed per chunk through
     a pinned staging ring on a copy stream, overlapping the previous chunk's compute)."""
 
-    def __init__(self, model, chunk=2048, optimizer=True, world_size=1, process_group=None, graph=False, **adam):
+    def __init__(self, model, chunk=2048, optimizer=True, world_size=1, process_group=None, graph=False,
+                 max_norm=0.0, l2_rate=0.0, l1_rate=0.0, **adam):
         """`graph=True`: every micro-batch shape is captured once as a CUDA graph (forward, loss, backward with the
         gradient sink) and replayed afterwards -- for small batches (the reference's default is 32 pairs) the step is
         bound by ~60 kernel launches and the Python around them, not by the kernels."""
@@ -53,6 +100,7 @@ class PairTrainer(object):
         self._graph_stream = torch.cuda.Stream() if graph else None
         self.flat, self.gflat = model.flatten_parameters()
         self.opt = Adam(self.flat, self.gflat, **adam) if optimizer else None
+        self.hooks = GradientHooks(self.flat, self.gflat, max_norm, l2_rate, l1_rate)     # train_binary.py:537-543
         self.world_size = world_size
         self.pg = process_group
         self.copy_stream = torch.cuda.Stream()
@@ -166,6 +214,8 @@ class PairTrainer(object):
         if self.world_size > 1:
             parallel.allreduce_sum_(self.gflat, self.pg)
         if self.opt is not None:
+            if self.hooks.active:
+                self.hooks.apply()
             self.opt.update()
         return self.loss_buf
 
@@ -205,6 +255,8 @@ class PairTrainer(object):
         if self.world_size > 1:
             parallel.allreduce_sum_(self.gflat, self.pg)
         if self.opt is not None:
+            if self.hooks.active:
+                self.hooks.apply()
             self.opt.update()
         return self.loss_buf
 

@@ -315,6 +315,32 @@ int bmp_adam_step(float *param, const float *grad, float *m, float *v, int n,
                   float alpha, float beta1, float beta2, float eps,
                   float weight_decay_rate, int step, void *stream);
 
+/* ---- remaining link-prediction heads --------------------------------
+ * Pair features feeding a Linear stack:
+ *   BMP_PAIR_SYM    out (rows, 2*dim) = [l + r | l * r]     SymMLP, models/mlp.py:104-105
+ *   BMP_PAIR_PROD   out (rows, dim)   = l * r               DistMult: BilinearDiag (models/mlp.py:154-197) is Linear(l * r)
+ *   BMP_PAIR_CONCAT out (rows, 2*dim) = [l | r]             MLP head, train_binary.py:98-100 (F.concat)            */
+enum { BMP_PAIR_SYM = 0, BMP_PAIR_PROD = 1, BMP_PAIR_CONCAT = 2 };
+int bmp_pair_features_forward(const float *left, const float *right, float *out, int rows, int dim, int kind, void *stream);
+int bmp_pair_features_backward(const float *left, const float *right, const float *d_out, float *d_left, float *d_right,
+                               int rows, int dim, int kind, void *stream);
+
+/* chainer.links.Bilinear(left, right, out) as the NTN head uses it (models/mlp.py:47-74):
+ *   y[b,k] = sum_ij e1[b,i] W[i,j,k] e2[b,j] + e1 V1 + e2 V2 + b      W (left,right,out), V1 (left,out), V2 (right,out), b (out)
+ * u (rows, right*out) = e1 W_flat is caller-owned scratch kept for the backward; du (same size) is backward scratch.
+ * V1/V2/b may be NULL together (nobias).  Parameter gradients ACCUMULATE (+=); de1/de2 are overwritten.               */
+int bmp_bilinear_forward(const float *e1, const float *e2, const float *W, const float *V1, const float *V2, const float *b,
+                         float *u, float *y, int rows, int left, int right, int out, void *stream);
+int bmp_bilinear_backward(const float *e1, const float *e2, const float *W, const float *V1, const float *V2, const float *u,
+                          const float *dy, float *du, float *de1, float *de2, float *dW, float *dV1, float *dV2, float *db,
+                          int rows, int left, int right, int out, void *stream);
+
+/* Optimizer hooks of train_binary.py:537-543 on the flat gradient, in the order the reference adds them:
+ * GradientClipping(threshold) (g *= threshold/||g||_2 when that is < 1; off when threshold <= 0), WeightDecay(l2_rate)
+ * (g += l2 * p), Lasso(l1_rate) (g += l1 * sign(p)).  norm_ws: one float of device scratch (needed when clipping).     */
+int bmp_grad_hooks(float *grad, const float *param, int n, float clip_threshold, float l2_rate, float l1_rate,
+                   float *norm_ws, void *stream);
+
 /* ---- housekeeping ------------------------------------------------------------ */
 const char *bmp_last_error(void);
 int         bmp_version(void);

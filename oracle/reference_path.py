@@ -379,6 +379,97 @@ class HolE(object):
 
 
 # ----------------------------------------------------------------------------
+# models/mlp.py:20-110,154-197 -- the other link-prediction heads
+# ----------------------------------------------------------------------------
+def _stack(p, names, n_hidden, act, h):
+    for i in range(n_hidden):
+        q = p.sub("%s/%d" % (names, i))
+        h = act(F.linear(h, q["W"], q["b"]))
+    q = p.sub("l_out")
+    return F.linear(h, q["W"], q["b"])
+
+
+class MLP(object):
+    """models/mlp.py:20-45."""
+
+    def __init__(self, p, out_dim, hidden_dims=(32, 16), activation="relu"):
+        self.p, self.n_hidden, self.act = p, len(hidden_dims), ACT[activation]
+
+    def __call__(self, x):
+        return _stack(self.p, "layers", self.n_hidden, self.act, x)                    # :40-44
+
+
+class SymMLP(MLP):
+    """models/mlp.py:95-110."""
+
+    def __call__(self, left_x, right_x):
+        h = F.concat((F.add(left_x, right_x), F.mul(left_x, right_x)), axis=1)        # :105
+        return _stack(self.p, "layers", self.n_hidden, self.act, h)
+
+
+class NTN(object):
+    """models/mlp.py:47-74: links.Bilinear (with V1, V2, b) -> Linear stack; no activation after the bilinear layer."""
+
+    def __init__(self, p, left_dim, right_dim, out_dim, ntn_out_dim=8, hidden_dims=(16,), activation="relu"):
+        self.p, self.n_hidden, self.act = p, len(hidden_dims), ACT[activation]
+
+    def __call__(self, left_x, right_x):
+        q = self.p.sub("ntn_layer")
+        h = F.bilinear(left_x, right_x, q["W"], q["V1"], q["V2"], q["b"])              # :67
+        return _stack(self.p, "mlp_layers", self.n_hidden, self.act, h)               # :69-72
+
+
+class DistMult(object):
+    """models/mlp.py:77-93 with BilinearDiag (:154-197): the (L, R, out) tensor of diagonal slices is built from
+    `self.W.data` (:186-192), i.e. as a constant -- the diagonal weights receive no gradient in the reference."""
+
+    def __init__(self, p, left_dim, right_dim, out_dim, dm_out_dim=8, hidden_dims=(16,), activation="relu"):
+        self.p, self.n_hidden, self.act = p, len(hidden_dims), ACT[activation]
+
+    def __call__(self, left_x, right_x):
+        Wd = self.p.sub("dm_layer")["W"].data                                          # (out, L)
+        W_mat = np.stack([np.diag(v) for v in Wd], axis=0).transpose(1, 2, 0)          # :188-190 -> (L, R, out)
+        h = F.bilinear(left_x, right_x, F.const(W_mat))                                # :176 bilinear.bilinear(e1, e2, W_mat)
+        return _stack(self.p, "mlp_layers", self.n_hidden, self.act, h)
+
+
+def head_shapes(kind, in_dim, out_dim, hidden_dims, mid=8):
+    """Chainer parameter names/shapes of the heads above (kind in mlp / symmlp / ntn / distmult)."""
+    names = "layers" if kind in ("mlp", "symmlp") else "mlp_layers"
+    d = {"mlp": 2 * in_dim, "symmlp": 2 * in_dim, "ntn": mid, "distmult": mid}[kind]
+    s = {}
+    if kind == "ntn":
+        s.update({"ntn_layer/W": (in_dim, in_dim, mid), "ntn_layer/V1": (in_dim, mid), "ntn_layer/V2": (in_dim, mid), "ntn_layer/b": (mid,)})
+    if kind == "distmult":
+        s["dm_layer/W"] = (mid, in_dim)
+    for i, hdim in enumerate(hidden_dims):
+        s["%s/%d/W" % (names, i)], s["%s/%d/b" % (names, i)] = (hdim, d), (hdim,)
+        d = hdim
+    s["l_out/W"], s["l_out/b"] = (out_dim, d), (out_dim,)
+    return s
+
+
+def apply_hooks(grads, params, max_norm=0.0, l2_rate=0.0, l1_rate=0.0):
+    """chainer.optimizer hooks in the order train_binary.py:537-543 adds them, on dicts of arrays (in place on copies):
+    GradientClipping (rate = threshold / sqrt(sum of squared norms over ALL parameters); scale when rate < 1),
+    WeightDecay (g += rate * p), Lasso (g += rate * sign(p))."""
+    g = {k: np.array(v, dtype=np.float64) for k, v in grads.items()}
+    if max_norm > 0:
+        norm = np.sqrt(sum(float((v * v).sum()) for v in g.values()))
+        rate = max_norm / norm
+        if rate < 1:
+            for k in g:
+                g[k] *= rate
+    if l2_rate > 0:
+        for k in g:
+            g[k] += l2_rate * params[k]
+    if l1_rate > 0:
+        for k in g:
+            g[k] += l1_rate * np.sign(params[k])
+    return g
+
+
+# ----------------------------------------------------------------------------
 # train_binary.py:84-118 (pair composition) and :524 (loss)
 # ----------------------------------------------------------------------------
 class GraphConvPredictorForPair(object):
@@ -392,6 +483,8 @@ class GraphConvPredictorForPair(object):
         a2 = self.graph_conv.get_atom_array()
         if self.attn is not None:
             g1, g2 = self.attn(a1, g1, a2, g2)
+        if type(self.mlp) is MLP:                                                      # train_binary.py:98-100
+            return self.mlp(F.concat((g1, g2), axis=-1))
         return self.mlp(g1, g2)
 
 

@@ -84,8 +84,12 @@ def test_workspace_size_queries_are_host_only_and_consistent():
         per_unit = (3 + 3 + 4) * (H // 64) * 16384 + 4 * 128 * H * 2
         assert lib.bmp_ggnn_stash2_bytes(2048, H, 6) >= per_unit * 1024 * 6
         assert lib.bmp_ggnn_stash2_bytes(2047, H, 6) == lib.bmp_ggnn_stash2_bytes(2048, H, 6)      # odd batch: padded tile
+    # hidden 256: forward-only encoder / readout kernels (weight images + a 64 KB adjacency image per CTA), no stash
+    assert lib.bmp_ggnn_tc_workspace_bytes(256, 8) > 8 * 176 * 8192 + 148 * 65536
+    assert lib.bmp_readout_tc_workspace_bytes(256, 256) >= 32 * 256 * 128
+    assert lib.bmp_readout_tc_workspace_bytes(256, 128) == 0
     for H in (16, 32, 96, 256):
-        assert lib.bmp_ggnn_tc_workspace_bytes(H, 6) == 0
+        assert lib.bmp_ggnn_tc_workspace_bytes(H, 6) == 0 or H == 256
         assert lib.bmp_relgcn_tc_workspace_bytes(H, 4) == 0
         assert lib.bmp_coattn_tc_workspace_bytes(H) == 0
         assert lib.bmp_ggnn_stash2_bytes(64, H, 6) == 0
