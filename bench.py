@@ -227,6 +227,30 @@ def run_gpu(args):
         model.graph_conv.mode = model.attn.mode = _g.MODE_BF16
         fp32_exact = dict(value=round(args.pairs / (ms32 * 1e-3), 1), unit="pairs/s", ms_per_step=round(ms32, 3),
                           note="BMP_MODE_F32: parity <= 1e-4 vs the oracle")
+    # ---- informational: BASELINE config D (GGNN H256 T8 + R1 readout + HolE->1, forward only) on this rank's GPU, same inputs ----
+    config_d = None
+    if rank == 0 and args.mode == "bf16" and not args.no_config_d:
+        nd = min(n_local, 4096)
+        encD = gcnbmp.GGNN(256, hidden_dim=256, n_layers=8, weight_tying=True)
+        mD = gcnbmp.GraphConvPredictorForPair(encD, None, gcnbmp.HolE(1, hidden_dims=()))
+        encD.mode = gcnbmp.MODE_BF16
+        argsD = [t[:nd] for t in resident[:4]]
+        with torch.no_grad():
+            for _ in range(3):
+                mD(*argsD)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                mD(*argsD)
+            e1.record()
+            torch.cuda.synchronize()
+        d_ms = e0.elapsed_time(e1) / 5
+        fd = algorithmic_flops(256, 8, CFG["N"], CFG["E"], 256, K=1, readout="r1", attn=False, D=256)
+        config_d = dict(value=round(nd / (d_ms * 1e-3), 1), unit="pairs/s per GPU", ms=round(d_ms, 3), pairs=nd,
+                        achieved_tflops=round(nd * fd["pair_fwd"] / (d_ms * 1e-3) / 1e12, 1),
+                        note="forward only, inputs resident, hidden-256 tcgen05 encoder + readout (csrc/ggnn_tc256.cu); not the headline")
+        del mD, encD
     cpu = cpu_baseline(args) if rank == 0 and not args.no_cpu else None
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 1), unit="pairs/s", n_gpus=world, steps=args.steps,
@@ -242,7 +266,7 @@ def run_gpu(args):
                     e2e=dict(value=round(e2e_value, 1), unit="pairs/s", h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=4 * world, loss=losses[-1] if losses else None),
                     gpu_launches=int(launches), clocks=sampler.summary(), roofline=roof, cpu_baseline=cpu,
-                    fp32_exact=fp32_exact, e2e_u8=e2e_u8,
+                    fp32_exact=fp32_exact, e2e_u8=e2e_u8, config_d_forward=config_d,
                     flops_per_pair_fwd=fl["pair_fwd"], achieved_tflops_step=round(3 * fl["pair_fwd"] * value / 1e12, 3))
         print(json.dumps(line))
     if world > 1:
@@ -332,6 +356,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0: min(--steps, 3))")
     ap.add_argument("--no-e2e-u8", dest="e2e_u8", action="store_false", help="skip the informational uint8-adjacency e2e measurement")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config-d", action="store_true", help="skip the informational config-D forward measurement")
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: GGNN encoder fwd/bwd/wgrad on tcgen05 (stated bound); fp32: parity <= 1e-4 path")
     ap.add_argument("--no-fp32", action="store_true", help="skip the extra fp32-exact measurement")

@@ -725,9 +725,13 @@ class GraphConvPredictorForPair(Link):
         a2 = self.graph_conv.get_atom_array()
         if self.attn is not None:
             g1, g2 = self.attn(a1, g1, a2, g2)
+        return self.head(g1, g2)
+
+    def head(self, g1, g2):
+        """the link-prediction head on two graph vectors (train_binary.py:98-115)"""
         if self.mlp is None:
             raise ValueError('[ERROR] No methods for similarity prediction')
-        if type(self.mlp) is MLP:        # train_binary.py:98-100: the plain MLP head sees F.concat((g1, g2), axis=-1)
+        if type(self.mlp) is MLP:        # :98-100: the plain MLP head sees F.concat((g1, g2), axis=-1)
             return self.mlp(Fn.PairFeatures.apply(g1, g2, K.PAIR_CONCAT))
         return self.mlp(g1, g2)
 

@@ -278,7 +278,7 @@ class PairTrainer(object):
             g1, g2 = g_all.index_select(0, inv1[s:e]), g_all.index_select(0, inv2[s:e])
             if m.attn is not None:
                 g1, g2 = m.attn(a_all.index_select(0, inv1[s:e]), g1, a_all.index_select(0, inv2[s:e]), g2)
-            loss = L.sigmoid_cross_entropy(m.mlp(g1, g2), y[s:e], count=global_count)
+            loss = L.sigmoid_cross_entropy(m.head(g1, g2), y[s:e], count=global_count)
             Fn.set_grad_sink(True)
             try:
                 loss.backward()
@@ -324,7 +324,7 @@ class PairTrainer(object):
             g1, g2 = g_all.index_select(0, inv1[s:e]), g_all.index_select(0, inv2[s:e])
             if m.attn is not None:
                 g1, g2 = m.attn(a_all.index_select(0, inv1[s:e]), g1, a_all.index_select(0, inv2[s:e]), g2)
-            outs.append(m.mlp(g1, g2))
+            outs.append(m.head(g1, g2))
         return torch.cat(outs, dim=0)
 
     @torch.no_grad()
