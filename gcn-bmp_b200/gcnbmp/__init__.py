@@ -8,6 +8,7 @@ from . import _capi
 from ._capi import BmpError, launch_count, reset_launch_count, MODE_F32, MODE_BF16
 from . import functional
 from . import metrics
+from . import evaluate
 from .links import (MAX_ATOMIC_NUM, functions, Link, ChainList, GraphLinear, GGNNUpdate, RelGCNUpdate,
                     GGNNReadout, GGNN, GGNNMono, RelGCN, NieFineCoattention, VQAParallelCoattention,
                     PoolingFineCoattention, HolE, HOLE, MLP, SymMLP, NTN, DistMult, BilinearDiag, GraphConvPredictorForPair,

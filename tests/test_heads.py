@@ -213,3 +213,38 @@ def test_trainer_applies_hooks_before_adam_and_exponential_shift():
     shift = train.ExponentialShift(tr.opt, 0.5, epochs=[2, 4])
     assert shift.maybe(1) is None and abs(shift.maybe(2) - 5e-3) < 1e-12 and shift.maybe(2) is None
     assert abs(shift.maybe(4) - 2.5e-3) < 1e-12 and abs(tr.opt.hp[0] - 2.5e-3) < 1e-12
+
+
+@pytest.mark.gpu
+def test_batch_evaluator_scores_a_split_once_and_matches_sklearn():
+    """f-3: one forward pass over the split, metrics on the device == scikit-learn on the same sigmoid(logits)."""
+    sk = pytest.importorskip("sklearn.metrics")
+    import cases
+    import gcnbmp
+    import product
+    from gcnbmp import synthetic
+    from gcnbmp.evaluate import BatchEvaluator
+    case = cases.pair_case("A", seed=5)
+    model = product.product_model(case["spec"], case["params"])
+    rng = np.random.default_rng(0)
+    n = 300
+    a1, A1 = synthetic.random_molecules(rng, n, 50)
+    a2, A2 = synthetic.random_molecules(rng, n, 50)
+    y = (rng.random((n, 1)) < 0.4).astype(np.int32)
+    y[0], y[1] = 1, 0
+    ev = BatchEvaluator(model, name="val", batch=128)
+    gcnbmp.reset_launch_count()
+    obs = ev.evaluate(a1, A1, a2, A2, y)
+    with torch.no_grad():
+        logits = torch.cat([model(a1[s:s + 128], A1[s:s + 128], a2[s:s + 128], A2[s:s + 128]) for s in range(0, n, 128)])
+    p = torch.sigmoid(logits.double()).cpu().numpy()
+    pr, rc, _ = sk.precision_recall_curve(y[:, 0], p[:, 0], pos_label=1)
+    ref = {"val/roc_auc": sk.roc_auc_score(y, p), "val/prc_auc": sk.auc(rc, pr), "val/accuracy": sk.accuracy_score(y, np.round(p)),
+           "val/f1": sk.f1_score(y, np.round(p), average="macro", zero_division=0)}
+    for k, v in ref.items():
+        assert abs(obs[k] - v) <= 1e-6, (k, obs[k], v)
+    # table form: the same pairs as index pairs give the same numbers
+    tab_a, tab_A = torch.tensor(np.concatenate([a1, a2])).cuda(), torch.tensor(np.concatenate([A1, A2])).cuda()
+    obs2 = ev.evaluate_indexed(tab_a, tab_A, np.arange(n), n + np.arange(n), y)
+    for k in ref:
+        assert abs(obs2[k] - obs[k]) <= 1e-5, k
