@@ -1,4 +1,5 @@
-"""ORACLE -- TEST INFRASTRUCTURE ONLY.  **parity unpinned**.
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Pin status: the op SEQUENCES are pinned to the reference's own link files, the Chainer
+PRIMITIVES on this tape remain **parity unpinned** (see below).
 
 A ~300-line reverse-mode tape over NumPy that restates the semantics of the
 Chainer `functions` / `links` the GCN-BMP hot path executes (the reference
@@ -8,7 +9,11 @@ installable here -- see DESIGN.md).  The reference has no tests, golden
 vectors or fixtures for this path, and Chainer cannot run
 in this image, so this oracle is pinned only by: an independent Torch-autograd
 twin (tests/torch_twin.py), finite differences, and algebraic identities.
-That is why the header says "parity unpinned".
+That is why the header says "parity unpinned" for the primitives.  What IS pinned: oracle/chainer_shim exposes this tape
+under the module names `chainer` / `chainer_chemistry`, so the reference's OWN hot-path files (/root/reference/models/*.py,
+unmodified) execute in the build container; tests/golden/make_reference_golden.py generates tests/golden/ref_*.npz from
+them (GGNN modular + monolithic files, GGNNUpdate, RelGCN, readout, the three fine co-attentions, HolE / MLP / SymMLP /
+NTN / DistMult) and tests/test_reference_golden.py holds both the oracle (1e-10, fp64) and the CUDA links (1e-4) to them.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may import this package.  The product
@@ -66,6 +71,33 @@ class Var(object):
 
     def __rsub__(self, o):
         return sub(o, self)
+
+    # conveniences the reference's own files rely on when they run over oracle/chainer_shim (chainer.Variable has them too)
+    __radd__ = __add__
+    __rmul__ = __mul__
+    __array_ufunc__ = None        # ndarray (op) Var defers to Var's reflected operator, as with chainer.Variable
+
+    def __len__(self):
+        return len(self.data)
+
+    def __truediv__(self, o):
+        return div(self, o)
+
+    def __rtruediv__(self, o):
+        return div(o, self)
+
+    def __neg__(self):
+        return sub(0.0, self)
+
+    def __getitem__(self, idx):
+        return getitem(self, idx)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.data if dtype is None else self.data.astype(dtype)
+
+    @property
+    def array(self):
+        return self.data
 
     def backward(self, seed=None):
         order, seen = [], set()
@@ -133,6 +165,31 @@ def mul(a, b):
     a, b = as_var(a), as_var(b)
     return Var(a.data * b.data, (a, b),
                lambda g: (_unbroadcast(g * b.data, a.shape), _unbroadcast(g * a.data, b.shape)))
+
+
+def div(a, b):
+    a, b = as_var(a), as_var(b)
+    if not isinstance(a.data, np.ndarray) or a.data.ndim == 0:
+        a = const(np.asarray(a.data, dtype=b.dtype))
+    return Var(a.data / b.data, (a, b),
+               lambda g: (_unbroadcast(g / b.data, a.shape), _unbroadcast(-g * a.data / (b.data * b.data), b.shape)))
+
+
+def where(cond, x, y):
+    """functions.where(condition (plain bool array), x, y)."""
+    x, y = as_var(x), as_var(y)
+    c = np.asarray(cond)
+    return Var(np.where(c, x.data, y.data), (x, y),
+               lambda g: (_unbroadcast(np.where(c, g, 0), x.shape), _unbroadcast(np.where(c, 0, g), y.shape)))
+
+
+def getitem(x, idx):
+    """Variable.__getitem__ (basic slicing / None-insertion as the reference uses it)."""
+    def push(g):
+        gx = np.zeros_like(x.data)
+        np.add.at(gx, idx, g)
+        return (gx,)
+    return Var(x.data[idx], (x,), push)
 
 
 def sigmoid(x):

@@ -1,4 +1,5 @@
-"""ORACLE -- TEST INFRASTRUCTURE ONLY.  **parity unpinned** (see minichainer.py).
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Op sequences pinned to fixtures generated from the reference's own files
+(tests/golden/ref_*.npz); the Chainer primitives underneath remain **parity unpinned** (see minichainer.py).
 
 CPU restatement of the GCN-BMP message-passing hot path, executing the SAME op
 sequence the reference's Chainer links execute (same reshapes, transposes,
@@ -428,7 +429,7 @@ class DistMult(object):
 
     def __call__(self, left_x, right_x):
         Wd = self.p.sub("dm_layer")["W"].data                                          # (out, L)
-        W_mat = np.stack([np.diag(v) for v in Wd], axis=0).transpose(1, 2, 0)          # :188-190 -> (L, R, out)
+        W_mat = np.array([np.diag(v) for v in Wd], dtype=np.float32).transpose(1, 2, 0)  # :188-190 -> (L, R, out), float32 as there
         h = F.bilinear(left_x, right_x, F.const(W_mat))                                # :176 bilinear.bilinear(e1, e2, W_mat)
         return _stack(self.p, "mlp_layers", self.n_hidden, self.act, h)
 

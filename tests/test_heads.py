@@ -40,7 +40,8 @@ def _twin_head(kind, P, hidden):
         if kind == "ntn":
             h = (torch.einsum("bi,ijk,bj->bk", l, P["ntn_layer/W"], r) + l @ P["ntn_layer/V1"] + r @ P["ntn_layer/V2"] + P["ntn_layer/b"])
             return stack(h)
-        return stack(torch.einsum("bi,ki,bi->bk", l, P["dm_layer/W"].detach(), r))
+        # models/mlp.py:188 builds the diagonal slices as a float32 constant
+        return stack(torch.einsum("bi,ki,bi->bk", l, P["dm_layer/W"].detach().float().double(), r))
     return fn
 
 
