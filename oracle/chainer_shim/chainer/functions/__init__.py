@@ -3,10 +3,26 @@ import numpy
 
 from oracle import minichainer as _M
 
-reshape, transpose, expand_dims, tile, concat = _M.reshape, _M.transpose, _M.expand_dims, _M.tile, _M.concat
-softmax, matmul, add, sigmoid, tanh, relu, identity = _M.softmax, _M.matmul, _M.add, _M.sigmoid, _M.tanh, _M.relu, _M.identity
+
+
+def _v(fn, n=1):
+    """chainer functions take raw arrays as well as Variables: wrap the first n positional arguments"""
+    def wrapped(*args, **kw):
+        args = tuple(_M.as_var(a) if i < n and isinstance(a, numpy.ndarray) else a for i, a in enumerate(args))
+        return fn(*args, **kw)
+    wrapped.__name__ = fn.__name__
+    return wrapped
+
+
+reshape, transpose, expand_dims, tile = _v(_M.reshape), _v(_M.transpose), _v(_M.expand_dims), _v(_M.tile)
+softmax, sigmoid, tanh, relu, identity = _v(_M.softmax), _v(_M.sigmoid), _v(_M.tanh), _v(_M.relu), _v(_M.identity)
+matmul, add = _M.matmul, _M.add
 fft, ifft, linear, bilinear, sigmoid_cross_entropy = _M.fft, _M.ifft, _M.linear, _M.bilinear, _M.sigmoid_cross_entropy
 linear_interpolate, embed_id, where = _M.linear_interpolate, _M.embed_id, _M.where
+
+
+def concat(xs, axis=1):
+    return _M.concat(tuple(_M.as_var(x) for x in xs), axis=axis)
 
 
 def sum(x, axis=None):  # noqa: A001 (chainer's name)

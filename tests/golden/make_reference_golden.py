@@ -54,6 +54,17 @@ ref_mono = {"ggnn_py": load("ref_ggnn_py", "models/ggnn.py"), "ggnn_att": load("
             "ggnn_dev": load("ref_ggnn_dev", "models/ggnn_dev.py")}
 
 
+def load_class(rel, cls_name):
+    """The reference's training scripts cannot be imported (argparse / RDKit / trainer set-up at module level); the source text of
+    ONE class is taken from the file, unmodified, and executed against the shim."""
+    import ast
+    src = open(os.path.join(REF, rel)).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == cls_name)
+    ns = {"chainer": chainer, "cuda": chainer.cuda, "F": CF}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, rel), "exec"), ns)
+    return ns[cls_name]
+
+
 def load_params(link, table):
     """Chainer-path table -> the shim link's parameters (shapes checked; every table entry must be consumed)."""
     seen = set()
@@ -162,6 +173,47 @@ def main():
         o_out, o_gin = run(both(onet), [adj], ws)
         check_and_save(tag, params, [atoms], [adj], ws[:len(r_out)], r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab),
                        dict(kind="mono", H=H, O=O, T=T, tied=tied, sum_readout=sum_ro, with_atoms=with_atoms))
+    # ---- the whole pair: train_binary.py:59-141 (encoder twice, co-attention, head) and the no-attention form
+    # train_ddi_modify_eval2.py:50-104, with F.sigmoid_cross_entropy as the Classifier applies it (train_binary.py:524)
+    PairAttn = load_class("train_binary.py", "GraphConvPredictorForPair")
+    PairPlain = load_class("train_ddi_modify_eval2.py", "GraphConvPredictorForPair")
+    import cases
+    for cname in ("C", "U", "A", "MU", "B"):
+        case = cases.pair_case(cname, seed=7)
+        sp, params = case["spec"], case["params"]
+        if sp["enc"] == "mono":
+            mod = ref_mono["ggnn_dev"] if sp["sum_readout"] else ref_mono["ggnn_att"]
+            enc = mod.GGNN(sp["O"], hidden_dim=sp["H"], n_layers=sp["T"], weight_tying=sp["tied"])
+        elif sp["enc"] == "ggnn":
+            enc = ref_ggnn.GGNN(sp["O"], hidden_dim=sp["H"], n_layers=sp["T"], weight_tying=sp["tied"], activation=ACT[sp.get("activation", "identity")])
+        else:
+            enc = ref_relgcn.RelGCN(out_channels=sp["O"], ch_list=list(sp["ch"]), scale_adj=sp["scale_adj"])
+        d_atoms = sp["ch"][-1] if sp["enc"] == "relgcn" else sp["H"]
+        attn = None
+        if sp["attn"] == "nie":
+            attn = ref_nie.NieFineCoattention(d_atoms, sp["O"], sp["head"], activation=CF.tanh)
+        elif sp["attn"] == "vqa":
+            attn = ref_vqa.VQAParallelCoattention(d_atoms, sp["O"], sp["head"])
+        mlp = ref_hole.HolE(sp["K"], hidden_dims=sp["hole_hidden"])
+        net = PairAttn(enc, attn, mlp) if attn is not None else PairPlain(enc, mlp)
+        load_params(net, params)
+        a1, A1, a2, A2 = case["inputs"]
+        logits = net(a1, A1, a2, A2)
+        loss = CF.sigmoid_cross_entropy(logits, case["labels"])
+        loss.backward()
+        ref_gp = grads_of_link(net)
+        o = cases.oracle_eval(case)
+        np.testing.assert_allclose(logits.data, o["logits"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(loss.data, o["loss"], rtol=1e-10)
+        for k in params:
+            if ref_gp[k] is None or o["grads"][k] is None:      # e.g. the readout when the co-attention ignores g_1, g_2
+                assert (ref_gp[k] is None or not np.any(ref_gp[k])) and (o["grads"][k] is None or not np.any(o["grads"][k])), k
+                continue
+            np.testing.assert_allclose(ref_gp[k], o["grads"][k], rtol=1e-9, atol=1e-13, err_msg="pair %s: %s" % (cname, k))
+        blob = {"meta": np.array(repr(dict(kind="pair", case=cname, seed=7))), "logits": logits.data, "loss": np.asarray(loss.data)}
+        blob.update({"gparam:" + k: v for k, v in ref_gp.items() if v is not None})
+        np.savez_compressed(os.path.join(HERE, "ref_pair_%s.npz" % cname), **blob)
+        print("ref_pair_%s.npz: logits %s, loss %.6f, %d parameter gradients, reference == oracle to 1e-10" % (cname, logits.shape, float(loss.data), len(ref_gp)))
     # ---- bare GGNNUpdate with state threading (two calls, then reset, then one call)
     H, mb, N = 8, 2, 7
     _, adj = random_molecules(rng, mb, N)

@@ -13,7 +13,8 @@ from oracle import reference_path as R
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "ref_*.npz")))
-NAMES = [os.path.basename(f)[4:-4] for f in FIXTURES]
+NAMES = [os.path.basename(f)[4:-4] for f in FIXTURES if not os.path.basename(f).startswith("ref_pair_")]
+PAIRS = [os.path.basename(f)[9:-4] for f in FIXTURES if os.path.basename(f).startswith("ref_pair_")]
 
 
 def _load(name):
@@ -118,6 +119,45 @@ def test_fixture_set_covers_every_hot_path_file():
     kinds = {_load(n)["meta"]["kind"] for n in NAMES}
     assert {"ggnn", "mono", "ggnn_update", "relgcn", "coattn_nie", "coattn_vqa", "coattn_pool", "readout", "head_hole",
             "head_hole_mlp_py", "head_mlp", "head_symmlp", "head_ntn", "head_distmult"} <= kinds
+
+
+def _pair_fixture(name):
+    z = np.load(os.path.join(HERE, "golden", "ref_pair_%s.npz" % name), allow_pickle=False)
+    meta = eval(str(z["meta"]), {"__builtins__": {}}, {})
+    return meta, z["logits"], float(z["loss"]), {k[7:]: z[k] for k in z.files if k.startswith("gparam:")}
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_oracle_reproduces_reference_pair_step(name):
+    """The whole unit of the metric -- the reference's GraphConvPredictorForPair (train_binary.py:59-141 with co-attention,
+    train_ddi_modify_eval2.py:50-104 without) over its own encoder / attention / HolE files + sigmoid-CE, fwd+bwd."""
+    import cases
+    meta, logits, loss, gp = _pair_fixture(name)
+    o = cases.oracle_eval(cases.pair_case(meta["case"], seed=meta["seed"]))
+    np.testing.assert_allclose(o["logits"], logits, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(float(o["loss"]), loss, rtol=1e-10)
+    assert len(gp) >= 10
+    for k, g in gp.items():
+        np.testing.assert_allclose(o["grads"][k], g, rtol=1e-9, atol=1e-13, err_msg=k)
+
+
+def test_pair_fixtures_cover_the_baseline_shapes():
+    assert set(PAIRS) >= {"A", "B", "C", "U", "MU"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", PAIRS)
+def test_cuda_pair_step_reproduces_reference_pair_step(name):
+    import cases
+    import product
+    from product import rel_err
+    meta, logits, loss, gp = _pair_fixture(name)
+    p = product.product_eval(cases.pair_case(meta["case"], seed=meta["seed"]))
+    assert rel_err(p["logits"], logits) <= 1e-4
+    assert abs(float(p["loss"]) - loss) <= 1e-4 * max(1.0, abs(loss))
+    for k, g in gp.items():
+        if np.abs(g).max() > 1e-12:
+            assert rel_err(p["grads"][k], g) <= 1e-4, k
 
 
 # ------------------------------------------------------------------------------------------------ GPU
