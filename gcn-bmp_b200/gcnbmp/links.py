@@ -587,6 +587,60 @@ class VQAParallelCoattention(NieFineCoattention):
     _default_activation = staticmethod(functions.tanh)
 
 
+class DeepNieFineCoattention(Link):
+    """models/coattention/nie_coattention.py:13-104 (`--attn deep`), :107-203 (VeryDeep), :206-309 (ExtremeDeep): n GraphLinear(H,H)
+    layers in front of the head projections and j_layer, while the energy map keeps the original atom states.  Runs on the SAME fused
+    co-attention kernel: the atoms handed over are [a | prev(a)] (2H wide) and the parameters are embedded as blocks -- the energy
+    weights act on the first half, lt / j_layer on the second -- so the zero blocks change nothing and their gradients are dropped.
+    Needs 2 * hidden_dim inside the co-attention kernels' range (fp32: <= 192)."""
+    n_lt_layers = 1
+
+    def __init__(self, hidden_dim, out_dim, head, activation=functions.identity):
+        Link.__init__(self)
+        self.add_link("energy_layer", _Bilinear(hidden_dim, hidden_dim, 1))
+        self.add_link("attention_layer_1", GraphLinear(head, 1, nobias=True))
+        self.add_link("attention_layer_2", GraphLinear(head, 1, nobias=True))
+        for side in (1, 2):
+            if self.n_lt_layers == 1:
+                self.add_link("prev_lt_layer_%d" % side, GraphLinear(hidden_dim, hidden_dim))
+            else:
+                self.add_link("prev_lt_layers_%d" % side, ChainList([GraphLinear(hidden_dim, hidden_dim) for _ in range(self.n_lt_layers)]))
+        self.add_link("lt_layer_1", GraphLinear(hidden_dim, head, nobias=True))
+        self.add_link("lt_layer_2", GraphLinear(hidden_dim, head, nobias=True))
+        self.add_link("j_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, head=head, activation=activation)
+
+    def _wide(self, side, atoms):
+        t = atoms
+        layers = [self._children["prev_lt_layer_%d" % side]] if self.n_lt_layers == 1 else list(self._children["prev_lt_layers_%d" % side])
+        for l in layers:
+            t = l(t)
+        mb, n, H = atoms.shape
+        return Fn.PairFeatures.apply(atoms.reshape(mb * n, H), t.reshape(mb * n, H), K.PAIR_CONCAT).reshape(mb, n, 2 * H)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        H, e = self.hidden_dim, self.energy_layer
+        z = lambda *shape: torch.zeros(shape, device=a1.device, dtype=torch.float32)
+        # parameter-space block embedding (tiny tensors; autograd routes the used blocks back to the parameters)
+        Wb = torch.cat([torch.cat([e.W, z(H, H, 1)], dim=1), z(H, 2 * H, 1)], dim=0)
+        V1b, V2b = torch.cat([e.V1, z(H, 1)], dim=0), torch.cat([e.V2, z(H, 1)], dim=0)
+        lt1 = torch.cat([z(self.head, H), self.lt_layer_1.W], dim=1)
+        lt2 = torch.cat([z(self.head, H), self.lt_layer_2.W], dim=1)
+        Wj = torch.cat([z(self.out_dim, H), self.j_layer.W], dim=1)
+        return Fn.Coattention.apply(self._wide(1, a1), self._wide(2, a2), K.COATTN_FINE, Fn.act_code(self.activation),
+                                    Wb, V1b, V2b, e.b, lt1, lt2, self.attention_layer_1.W, self.attention_layer_2.W,
+                                    Wj, self.j_layer.b, self.__dict__.get("mode", K.MODE_F32))
+
+
+class VeryDeepNieFineCoattention(DeepNieFineCoattention):
+    n_lt_layers = 2
+
+
+class ExtremeDeepNieFineCoattention(DeepNieFineCoattention):
+    n_lt_layers = 3
+
+
 class PoolingFineCoattention(Link):
     """models/coattention/PoolingFineCoattention.py:13-83."""
 

@@ -337,6 +337,47 @@ class VQAParallelCoattention(NieFineCoattention):
     default_activation = "tanh"       # vqa_parallel_coattention.py:23
 
 
+class DeepNieFineCoattention(NieFineCoattention):
+    """nie_coattention.py:13-104 (one GraphLinear(H,H) before the head projection), :107-203 (VeryDeep, two),
+    :206-309 (ExtremeDeep, three).  The energy map sees the ORIGINAL atoms (:42,:144); the head projections and j_layer see
+    the transformed ones (:50-55,:73-74)."""
+    n_lt_layers = 1
+
+    def _prev(self, side, atoms):
+        for i in range(self.n_lt_layers):
+            name = "prev_lt_layer_%d" % side if self.n_lt_layers == 1 else "prev_lt_layers_%d/%d" % (side, i)
+            q = self.p.sub(name)
+            atoms = F.graph_linear(atoms, q["W"], q["b"])
+        return atoms
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        p = self.p
+        C = _energy(p, self.act, query=atoms_2, key=atoms_1)
+        L_2 = F.softmax(C, axis=1)
+        L_1 = F.softmax(F.transpose(C, (0, 2, 1)), axis=1)
+        atoms_1 = self._prev(1, atoms_1)
+        lt_1 = F.graph_linear(atoms_1, p["lt_layer_1/W"])
+        atoms_2 = self._prev(2, atoms_2)
+        lt_2 = F.graph_linear(atoms_2, p["lt_layer_2/W"])
+        H_1 = F.tanh(F.add(lt_1, F.matmul(L_1, lt_2)))
+        H_2 = F.tanh(F.add(lt_2, F.matmul(L_2, lt_1)))
+        attn_1 = F.softmax(F.graph_linear(H_1, p["attention_layer_1/W"]))
+        attn_2 = F.softmax(F.graph_linear(H_2, p["attention_layer_2/W"]))
+        j1 = F.graph_linear(atoms_1, p["j_layer/W"], p["j_layer/b"])
+        j2 = F.graph_linear(atoms_2, p["j_layer/W"], p["j_layer/b"])
+        c1 = F.sum_(F.mul(F.tile(attn_1, (1, 1, self.out_dim)), j1), axis=1)
+        c2 = F.sum_(F.mul(F.tile(attn_2, (1, 1, self.out_dim)), j2), axis=1)
+        return c1, c2
+
+
+class VeryDeepNieFineCoattention(DeepNieFineCoattention):
+    n_lt_layers = 2
+
+
+class ExtremeDeepNieFineCoattention(DeepNieFineCoattention):
+    n_lt_layers = 3
+
+
 class PoolingFineCoattention(object):
     def __init__(self, p, hidden_dim, out_dim, activation="tanh"):
         self.p, self.out_dim, self.act = p, out_dim, ACT[activation]
@@ -558,6 +599,15 @@ def coattn_shapes(hidden_dim, out_dim, head=None):
     if head is not None:
         s.update({"attention_layer_1/W": (1, head), "attention_layer_2/W": (1, head),
                   "lt_layer_1/W": (head, hidden_dim), "lt_layer_2/W": (head, hidden_dim)})
+    return s
+
+
+def deep_coattn_shapes(hidden_dim, out_dim, head, n_lt_layers=1):
+    s = coattn_shapes(hidden_dim, out_dim, head)
+    for side in (1, 2):
+        for i in range(n_lt_layers):
+            name = "prev_lt_layer_%d" % side if n_lt_layers == 1 else "prev_lt_layers_%d/%d" % (side, i)
+            s[name + "/W"], s[name + "/b"] = (hidden_dim, hidden_dim), (hidden_dim,)
     return s
 
 

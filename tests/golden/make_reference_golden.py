@@ -266,6 +266,21 @@ def main():
         onet = mk_ora(R.P(tab), H, O, head)
         o_out, o_gin = run(lambda x1, x2: onet(x1, M.const(g1), x2, M.const(g2)), [a1, a2], ws)
         check_and_save(tag, params, [], [a1, a2], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab), dict(kind=tag, H=H, O=O, head=head))
+    # ---- the Deep / VeryDeep / ExtremeDeep Nie variants (energy on the original atoms, heads on the transformed ones)
+    for tag, rcls, ocls, nl in (("coattn_deep", ref_nie.DeepNieFineCoattention, R.DeepNieFineCoattention, 1),
+                                ("coattn_very_deep", ref_nie.VeryDeepNieFineCoattention, R.VeryDeepNieFineCoattention, 2),
+                                ("coattn_extreme_deep", ref_nie.ExtremeDeepNieFineCoattention, R.ExtremeDeepNieFineCoattention, 3)):
+        H, O, mb, N1, N2, head = 12, 8, 3, 6, 9, 4
+        a1, a2 = rng.standard_normal((mb, N1, H)) * 0.5, rng.standard_normal((mb, N2, H)) * 0.5
+        params = R.init_params(R.deep_coattn_shapes(H, O, head, nl), rng, dtype=np.float64)
+        ws = [rng.standard_normal((mb, O)), rng.standard_normal((mb, O))]
+        net = rcls(H, O, head, activation=CF.tanh)
+        load_params(net, params)
+        r_out, r_gin = run(lambda x1, x2: net(x1, None, x2, None), [a1, a2], ws)
+        tab = R.wrap_params(params)
+        onet = ocls(R.P(tab), H, O, head, activation="tanh")
+        o_out, o_gin = run(lambda x1, x2: onet(x1, None, x2, None), [a1, a2], ws)
+        check_and_save(tag, params, [], [a1, a2], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab), dict(kind=tag, H=H, O=O, head=head))
     # ---- heads: HolE (both files), MLP, SymMLP, NTN, DistMult
     D, K, mb = 12, 3, 5
     l, r = rng.standard_normal((mb, D)), rng.standard_normal((mb, D))

@@ -66,7 +66,10 @@ def _oracle_fn(fx, tab):
     if kind.startswith("coattn"):
         cls = {"coattn_nie": lambda: R.NieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_vqa": lambda: R.VQAParallelCoattention(P, m["H"], m["O"], m["head"]),
-               "coattn_pool": lambda: R.PoolingFineCoattention(P, m["H"], m["O"])}[kind]()
+               "coattn_pool": lambda: R.PoolingFineCoattention(P, m["H"], m["O"]),
+               "coattn_deep": lambda: R.DeepNieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
+               "coattn_very_deep": lambda: R.VeryDeepNieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
+               "coattn_extreme_deep": lambda: R.ExtremeDeepNieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh")}[kind]()
         return lambda a1, a2: cls(a1, None, a2, None)
     if kind == "readout":
         net = R.GGNNReadout(P, m["O"], m["H"], nobias=m["nobias"], activation=m["act"], activation_agg=m["agg"])
@@ -191,7 +194,10 @@ def _product(fx):
     if kind.startswith("coattn"):
         net = {"coattn_nie": lambda: gcnbmp.NieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_vqa": lambda: gcnbmp.VQAParallelCoattention(m["H"], m["O"], m["head"]),
-               "coattn_pool": lambda: gcnbmp.PoolingFineCoattention(m["H"], m["O"])}[kind]()
+               "coattn_pool": lambda: gcnbmp.PoolingFineCoattention(m["H"], m["O"]),
+               "coattn_deep": lambda: gcnbmp.DeepNieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
+               "coattn_very_deep": lambda: gcnbmp.VeryDeepNieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
+               "coattn_extreme_deep": lambda: gcnbmp.ExtremeDeepNieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh)}[kind]()
         return (lambda a1, a2: net(a1, None, a2, None)), net
     if kind == "readout":
         net = gcnbmp.GGNNReadout(m["O"], m["H"], nobias=m["nobias"], activation=act(m["act"]), activation_agg=act(m["agg"]))
