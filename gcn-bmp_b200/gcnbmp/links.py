@@ -587,6 +587,34 @@ class VQAParallelCoattention(NieFineCoattention):
     _default_activation = staticmethod(functions.tanh)
 
 
+class FourierFineCoattention(NieFineCoattention):
+    """models/coattention/nie_coattention.py:399-515 (`--attn fourier`): the energy map is taken between the FFTs (over the hidden
+    axis) of the atom states, real parts and imaginary parts through the same Bilinear layer.  The DFT is linear, so the sum of the two
+    bilinear forms is ONE bilinear form of the original atoms with W' = Fc^T W Fc + Fs^T W Fs, V' = (Fc + Fs)^T V, b' = 2 b
+    (Fc / Fs = cosine / minus-sine DFT matrices): a parameter-space transform in front of the unchanged fused kernel, at every hidden
+    size that kernel covers (including the tcgen05 path)."""
+    _default_activation = staticmethod(functions.identity)
+
+    def _dft(self, dev):
+        key = (str(dev), self.hidden_dim)
+        if self.__dict__.get("_dft_key") != key:
+            n = torch.arange(self.hidden_dim, dtype=torch.float64)
+            ang = 2.0 * math.pi * torch.outer(n, n) / self.hidden_dim
+            self.__dict__.update(_dft_key=key, _Fc=torch.cos(ang).to(dev, torch.float32), _Fs=(-torch.sin(ang)).to(dev, torch.float32))
+        return self._Fc, self._Fs
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        e = self.energy_layer
+        Fc, Fs = self._dft(a1.device)
+        W = e.W[:, :, 0]
+        Wf = (Fc.t() @ W @ Fc + Fs.t() @ W @ Fs).unsqueeze(2).contiguous()
+        S = (Fc + Fs).t()
+        return Fn.Coattention.apply(a1, a2, K.COATTN_FINE, Fn.act_code(self.activation), Wf, (S @ e.V1).contiguous(), (S @ e.V2).contiguous(),
+                                    2.0 * e.b, self.lt_layer_1.W, self.lt_layer_2.W, self.attention_layer_1.W, self.attention_layer_2.W,
+                                    self.j_layer.W, self.j_layer.b, self.__dict__.get("mode", K.MODE_F32))
+
+
 class DeepNieFineCoattention(Link):
     """models/coattention/nie_coattention.py:13-104 (`--attn deep`), :107-203 (VeryDeep), :206-309 (ExtremeDeep): n GraphLinear(H,H)
     layers in front of the head projections and j_layer, while the energy map keeps the original atom states.  Runs on the SAME fused

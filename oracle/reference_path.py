@@ -337,6 +337,41 @@ class VQAParallelCoattention(NieFineCoattention):
     default_activation = "tanh"       # vqa_parallel_coattention.py:23
 
 
+class FourierFineCoattention(NieFineCoattention):
+    """nie_coattention.py:399-515: the energy map is act(Bilinear(Re fft(key), Re fft(query)) + Bilinear(Im fft(key), Im fft(query)))
+    with the FFT over the hidden axis (:484-491,:505-515); the head path sees the atoms themselves."""
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        p = self.p
+        C = self._energy(query=atoms_2, key=atoms_1)
+        L_2 = F.softmax(C, axis=1)
+        L_1 = F.softmax(F.transpose(C, (0, 2, 1)), axis=1)
+        lt_1 = F.graph_linear(atoms_1, p["lt_layer_1/W"])
+        lt_2 = F.graph_linear(atoms_2, p["lt_layer_2/W"])
+        H_1 = F.tanh(F.add(lt_1, F.matmul(L_1, lt_2)))
+        H_2 = F.tanh(F.add(lt_2, F.matmul(L_2, lt_1)))
+        attn_1 = F.softmax(F.graph_linear(H_1, p["attention_layer_1/W"]))
+        attn_2 = F.softmax(F.graph_linear(H_2, p["attention_layer_2/W"]))
+        j1 = F.graph_linear(atoms_1, p["j_layer/W"], p["j_layer/b"])
+        j2 = F.graph_linear(atoms_2, p["j_layer/W"], p["j_layer/b"])
+        c1 = F.sum_(F.mul(F.tile(attn_1, (1, 1, self.out_dim)), j1), axis=1)
+        c2 = F.sum_(F.mul(F.tile(attn_2, (1, 1, self.out_dim)), j2), axis=1)
+        return c1, c2
+
+    def _energy(self, query, key):
+        mb, nq, hd = query.shape
+        nk = key.shape[1]
+        zeros = lambda v: F.const(np.zeros_like(v.data))
+        q_re, q_im = F.fft((query, zeros(query)))                                      # :505-515
+        k_re, k_im = F.fft((key, zeros(key)))
+        tq = lambda v: F.reshape(F.tile(F.expand_dims(v, 2), (1, 1, nk, 1)), (mb * nq * nk, hd))
+        tk = lambda v: F.reshape(F.tile(F.expand_dims(v, 1), (1, nq, 1, 1)), (mb * nq * nk, hd))
+        e = self.p.sub("energy_layer")
+        bil = lambda a, b: F.bilinear(a, b, e["W"], e["V1"], e["V2"], e["b"])
+        y = F.add(bil(tk(k_re), tq(q_re)), bil(tk(k_im), tq(q_im)))                    # :497
+        return F.reshape(self.act(y), (mb, nq, nk))
+
+
 class DeepNieFineCoattention(NieFineCoattention):
     """nie_coattention.py:13-104 (one GraphLinear(H,H) before the head projection), :107-203 (VeryDeep, two),
     :206-309 (ExtremeDeep, three).  The energy map sees the ORIGINAL atoms (:42,:144); the head projections and j_layer see

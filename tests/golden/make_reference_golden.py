@@ -253,6 +253,7 @@ def main():
     for tag, mk_ref, mk_ora, head in (
             ("coattn_nie", lambda H, O, hd: ref_nie.NieFineCoattention(H, O, hd, activation=CF.tanh), lambda p, H, O, hd: R.NieFineCoattention(p, H, O, hd, activation="tanh"), 4),
             ("coattn_vqa", lambda H, O, hd: ref_vqa.VQAParallelCoattention(H, O, hd), lambda p, H, O, hd: R.VQAParallelCoattention(p, H, O, hd), 3),
+            ("coattn_fourier", lambda H, O, hd: ref_nie.FourierFineCoattention(H, O, hd, activation=CF.tanh), lambda p, H, O, hd: R.FourierFineCoattention(p, H, O, hd, activation="tanh"), 4),
             ("coattn_pool", lambda H, O, hd: ref_pool.PoolingFineCoattention(H, O), lambda p, H, O, hd: R.PoolingFineCoattention(p, H, O), None)):
         H, O, mb, N1, N2 = 12, 8, 3, 6, 9
         a1, a2 = rng.standard_normal((mb, N1, H)) * 0.5, rng.standard_normal((mb, N2, H)) * 0.5

@@ -67,6 +67,7 @@ def _oracle_fn(fx, tab):
         cls = {"coattn_nie": lambda: R.NieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_vqa": lambda: R.VQAParallelCoattention(P, m["H"], m["O"], m["head"]),
                "coattn_pool": lambda: R.PoolingFineCoattention(P, m["H"], m["O"]),
+               "coattn_fourier": lambda: R.FourierFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_deep": lambda: R.DeepNieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_very_deep": lambda: R.VeryDeepNieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_extreme_deep": lambda: R.ExtremeDeepNieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh")}[kind]()
@@ -195,6 +196,7 @@ def _product(fx):
         net = {"coattn_nie": lambda: gcnbmp.NieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_vqa": lambda: gcnbmp.VQAParallelCoattention(m["H"], m["O"], m["head"]),
                "coattn_pool": lambda: gcnbmp.PoolingFineCoattention(m["H"], m["O"]),
+               "coattn_fourier": lambda: gcnbmp.FourierFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_deep": lambda: gcnbmp.DeepNieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_very_deep": lambda: gcnbmp.VeryDeepNieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_extreme_deep": lambda: gcnbmp.ExtremeDeepNieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh)}[kind]()
