@@ -332,8 +332,13 @@ class PairTrainer(object):
         """Forward only over all pairs (eval_coattention.py:102-126 predict loop)."""
         n = atoms_1.shape[0]
         outs = []
-        for s, e in self._chunks(n):
-            outs.append(self.model(atoms_1[s:e], adjs_1[s:e], atoms_2[s:e], adjs_2[s:e]))
+        Fn.params_changed()
+        Fn.set_weight_cache(True)        # parameters are constant during a predict pass: pack the tcgen05 weight images once
+        try:
+            for s, e in self._chunks(n):
+                outs.append(self.model(atoms_1[s:e], adjs_1[s:e], atoms_2[s:e], adjs_2[s:e]))
+        finally:
+            Fn.set_weight_cache(False)
         return torch.cat(outs, dim=0)
 
 

@@ -135,7 +135,7 @@ for dd in (False, True):
     ms = timed(lambda: trI.step_indexed(tab_a, tab_A, i1, i2, yK, dedupe=dd), reps=3, warm=2)
     print("E  index pairs over a %d-drug device table, %d pairs/step, fwd+bwd+Adam, %s: %8.2f ms  %10.0f pairs/s  (H2D %.2f MB/step)"
           % (U, NP, "each drug encoded once" if dd else "per-pair encoding     ", ms, NP / ms * 1e3, trI.h2d_bytes / 1e6))
-# D via the drug table: GGNN H256 T8 + R1 readout + HolE (fp32 kernels), 1 M index pairs over 1704 drugs, forward only
+# D via the drug table: GGNN H256 T8 + R1 readout + HolE, 1 M index pairs over 1704 drugs, forward only (fp32 kernels, then BF16 mode)
 tab_Af = tab_A.float()
 encD = gcnbmp.GGNN(256, hidden_dim=256, n_layers=8, weight_tying=True)
 headD = gcnbmp.HolE(1, hidden_dims=())
@@ -144,3 +144,6 @@ trD = _train.PairTrainer(gcnbmp.GraphConvPredictorForPair(encD, None, headD), ch
 j1, j2 = rng.integers(0, U, 1 << 20), rng.integers(0, U, 1 << 20)
 ms = timed(lambda: trD.predict_indexed(tab_a, tab_Af, j1, j2), reps=3, warm=1)
 print("D  GGNN H256 T8 + R1 + HolE, 1 M index pairs over a %d-drug table, forward (fp32): %8.2f ms  %10.0f pairs/s" % (U, ms, (1 << 20) / ms * 1e3))
+encD.mode = gcnbmp.MODE_BF16
+ms = timed(lambda: trD.predict_indexed(tab_a, tab_A, j1, j2), reps=3, warm=1)
+print("D  same, encoder + readout on the hidden-256 tcgen05 kernels (byte adjacency):            %8.2f ms  %10.0f pairs/s" % (ms, (1 << 20) / ms * 1e3))
