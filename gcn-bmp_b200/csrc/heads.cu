@@ -87,6 +87,94 @@ __global__ void bilinear_bwd_left_kernel(const float *__restrict__ V1, const flo
     }
 }
 
+// ---------------------------------------------------------------- atom-wise primitives of the vector-query co-attentions
+// (alternating_coattention.py, parallel_coattention.py): a (mb, O) query vector against the (mb, N, C) atom arrays.
+// y[b,n,c] = act(x[b,n,c] + v[b,c]); x == NULL: tile of v (F.tile over the atoms); v == NULL: plain activation
+__global__ void bcast_add_act_fwd_kernel(const float *__restrict__ x, const float *__restrict__ v, float *__restrict__ y,
+                                         long total, int n_atoms, int ch, int act) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i / ((long)n_atoms * ch);
+        const int c = (int)(i % ch);
+        y[i] = act_fwd(act, (x ? x[i] : 0.f) + (v ? v[b * ch + c] : 0.f));
+    }
+}
+// dx = dy * act'(y) (optional); dv[b,c] = sum_n of the same (optional); one thread per (b,c)
+__global__ void bcast_add_act_bwd_kernel(const float *__restrict__ y, const float *__restrict__ dy, float *__restrict__ dx,
+                                         float *__restrict__ dv, long mbch, int n_atoms, int ch, int act) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < mbch; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / ch;
+        const int c = (int)(t - b * ch);
+        float s = 0.f;
+        for (int n = 0; n < n_atoms; ++n) {
+            const long i = (b * n_atoms + n) * ch + c;
+            const float yy = y[i];
+            const float g = dy[i] * act_bwd(act, yy, yy);
+            if (dx) dx[i] = g;
+            s += g;
+        }
+        if (dv) dv[t] = s;
+    }
+}
+// softmax over the atoms axis (F.softmax default axis=1 on (mb, N, C)); one thread per (b,c)
+__global__ void atoms_softmax_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, long mbch, int n_atoms, int ch) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < mbch; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / ch;
+        const int c = (int)(t - b * ch);
+        const float *xb = x + b * n_atoms * ch + c;
+        float m = -INFINITY, s = 0.f;
+        for (int n = 0; n < n_atoms; ++n) m = fmaxf(m, xb[(long)n * ch]);
+        for (int n = 0; n < n_atoms; ++n) s += expf(xb[(long)n * ch] - m);
+        const float inv = 1.f / s;
+        float *yb = y + b * n_atoms * ch + c;
+        for (int n = 0; n < n_atoms; ++n) yb[(long)n * ch] = expf(xb[(long)n * ch] - m) * inv;
+    }
+}
+__global__ void atoms_softmax_bwd_kernel(const float *__restrict__ y, const float *__restrict__ dy, float *__restrict__ dx,
+                                         long mbch, int n_atoms, int ch) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < mbch; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / ch;
+        const int c = (int)(t - b * ch);
+        const long base = b * n_atoms * ch + c;
+        float s = 0.f;
+        for (int n = 0; n < n_atoms; ++n) s = fmaf(y[base + (long)n * ch], dy[base + (long)n * ch], s);
+        for (int n = 0; n < n_atoms; ++n) dx[base + (long)n * ch] = y[base + (long)n * ch] * (dy[base + (long)n * ch] - s);
+    }
+}
+// out[b,c] = sum_n a[b,n,(a_ch == 1 ? 0 : c)] * z[b,n,c]   (F.sum(F.tile(attn) * z, axis=1)); one thread per (b,c)
+__global__ void atoms_pool_fwd_kernel(const float *__restrict__ a, int a_ch, const float *__restrict__ z, float *__restrict__ out,
+                                      long mbch, int n_atoms, int ch) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < mbch; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / ch;
+        const int c = (int)(t - b * ch);
+        float s = 0.f;
+        for (int n = 0; n < n_atoms; ++n) {
+            const long r = b * n_atoms + n;
+            s = fmaf(a[r * a_ch + (a_ch == 1 ? 0 : c)], z[r * ch + c], s);
+        }
+        out[t] = s;
+    }
+}
+// dz = a * dout;  da = dout * z (a_ch == ch) or sum_c dout z (a_ch == 1); one warp per (b,n)
+__global__ void atoms_pool_bwd_kernel(const float *__restrict__ a, int a_ch, const float *__restrict__ z, const float *__restrict__ dout,
+                                      float *__restrict__ da, float *__restrict__ dz, long rows, int n_atoms, int ch) {
+    const int lane = threadIdx.x & 31;
+    for (long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += ((long)gridDim.x * blockDim.x) >> 5) {
+        const long b = r / n_atoms;
+        float s = 0.f;
+        for (int c = lane; c < ch; c += 32) {
+            const float g = dout[b * ch + c], zz = z[r * ch + c];
+            dz[r * ch + c] = a[r * a_ch + (a_ch == 1 ? 0 : c)] * g;
+            if (a_ch == 1) s = fmaf(g, zz, s);
+            else da[r * ch + c] = g * zz;
+        }
+        if (a_ch == 1) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) da[r] = s;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- optimizer hooks
 __global__ void sumsq_kernel(const float *__restrict__ g, long n, float *__restrict__ out) {
     float s = 0.f;
@@ -185,6 +273,65 @@ extern "C" int bmp_bilinear_backward(const float *e1, const float *e2, const flo
     if (dV2 && (rc = bmp_wgrad(e2, right, dy, out, dV2, out, rows, right, out, stream))) return rc;
     if (db && (rc = bmp_colsum(dy, out, db, 1, rows, out, stream))) return rc;
     return BMP_OK;
+}
+
+extern "C" int bmp_atoms_bcast_add_act_forward(const float *x, const float *v, float *y, int mb, int n_atoms, int ch, int act, void *stream) {
+    if (!y || (!x && !v)) { set_error("bmp_atoms_bcast_add_act_forward: null pointer"); return BMP_EINVAL; }
+    if (mb <= 0) return BMP_OK;
+    if (n_atoms <= 0 || ch <= 0) { set_error("bmp_atoms_bcast_add_act_forward: bad shape"); return BMP_ESHAPE; }
+    const long total = (long)mb * n_atoms * ch;
+    bcast_add_act_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, v, y, total, n_atoms, ch, act);
+    count_launch();
+    return check_launch("bcast_add_act_fwd_kernel");
+}
+
+extern "C" int bmp_atoms_bcast_add_act_backward(const float *y, const float *dy, float *dx, float *dv, int mb, int n_atoms, int ch, int act, void *stream) {
+    if (!y || !dy || (!dx && !dv)) { set_error("bmp_atoms_bcast_add_act_backward: null pointer"); return BMP_EINVAL; }
+    if (mb <= 0) return BMP_OK;
+    const long mbch = (long)mb * ch;
+    bcast_add_act_bwd_kernel<<<grid_for(mbch), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, dv, mbch, n_atoms, ch, act);
+    count_launch();
+    return check_launch("bcast_add_act_bwd_kernel");
+}
+
+extern "C" int bmp_atoms_softmax_forward(const float *x, float *y, int mb, int n_atoms, int ch, void *stream) {
+    if (!x || !y) { set_error("bmp_atoms_softmax_forward: null pointer"); return BMP_EINVAL; }
+    if (mb <= 0) return BMP_OK;
+    if (n_atoms <= 0 || ch <= 0) { set_error("bmp_atoms_softmax_forward: bad shape"); return BMP_ESHAPE; }
+    const long mbch = (long)mb * ch;
+    atoms_softmax_fwd_kernel<<<grid_for(mbch), 256, 0, (cudaStream_t)stream>>>(x, y, mbch, n_atoms, ch);
+    count_launch();
+    return check_launch("atoms_softmax_fwd_kernel");
+}
+
+extern "C" int bmp_atoms_softmax_backward(const float *y, const float *dy, float *dx, int mb, int n_atoms, int ch, void *stream) {
+    if (!y || !dy || !dx) { set_error("bmp_atoms_softmax_backward: null pointer"); return BMP_EINVAL; }
+    if (mb <= 0) return BMP_OK;
+    const long mbch = (long)mb * ch;
+    atoms_softmax_bwd_kernel<<<grid_for(mbch), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, mbch, n_atoms, ch);
+    count_launch();
+    return check_launch("atoms_softmax_bwd_kernel");
+}
+
+extern "C" int bmp_atoms_pool_forward(const float *a, int a_ch, const float *z, float *out, int mb, int n_atoms, int ch, void *stream) {
+    if (!a || !z || !out) { set_error("bmp_atoms_pool_forward: null pointer"); return BMP_EINVAL; }
+    if (a_ch != 1 && a_ch != ch) { set_error("bmp_atoms_pool_forward: attention width %d must be 1 or %d", a_ch, ch); return BMP_ESHAPE; }
+    if (mb <= 0) return BMP_OK;
+    const long mbch = (long)mb * ch;
+    atoms_pool_fwd_kernel<<<grid_for(mbch), 256, 0, (cudaStream_t)stream>>>(a, a_ch, z, out, mbch, n_atoms, ch);
+    count_launch();
+    return check_launch("atoms_pool_fwd_kernel");
+}
+
+extern "C" int bmp_atoms_pool_backward(const float *a, int a_ch, const float *z, const float *d_out, float *da, float *dz,
+                                       int mb, int n_atoms, int ch, void *stream) {
+    if (!a || !z || !d_out || !da || !dz) { set_error("bmp_atoms_pool_backward: null pointer"); return BMP_EINVAL; }
+    if (a_ch != 1 && a_ch != ch) { set_error("bmp_atoms_pool_backward: attention width %d must be 1 or %d", a_ch, ch); return BMP_ESHAPE; }
+    if (mb <= 0) return BMP_OK;
+    const long rows = (long)mb * n_atoms;
+    atoms_pool_bwd_kernel<<<grid_for(rows * 32), 256, 0, (cudaStream_t)stream>>>(a, a_ch, z, d_out, da, dz, rows, n_atoms, ch);
+    count_launch();
+    return check_launch("atoms_pool_bwd_kernel");
 }
 
 extern "C" int bmp_grad_hooks(float *grad, const float *param, int n, float clip_threshold, float l2_rate, float l1_rate,

@@ -120,6 +120,12 @@ def _load():
         "bmp_bilinear_forward": [fp, fp, fp, fp, fp, fp, fp, fp, i, i, i, i, vp],
         "bmp_bilinear_backward": [fp] * 14 + [i, i, i, i, vp],
         "bmp_grad_hooks": [fp, fp, i, f, f, f, fp, vp],
+        "bmp_atoms_bcast_add_act_forward": [fp, fp, fp, i, i, i, i, vp],
+        "bmp_atoms_bcast_add_act_backward": [fp, fp, fp, fp, i, i, i, i, vp],
+        "bmp_atoms_softmax_forward": [fp, fp, i, i, i, vp],
+        "bmp_atoms_softmax_backward": [fp, fp, fp, i, i, i, vp],
+        "bmp_atoms_pool_forward": [fp, i, fp, fp, i, i, i, vp],
+        "bmp_atoms_pool_backward": [fp, i, fp, fp, fp, fp, i, i, i, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -143,6 +149,8 @@ EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_r
            "bmp_coattn_backward", "bmp_coattn_tc_workspace_bytes", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
+           "bmp_atoms_bcast_add_act_forward", "bmp_atoms_bcast_add_act_backward", "bmp_atoms_softmax_forward", "bmp_atoms_softmax_backward",
+           "bmp_atoms_pool_forward", "bmp_atoms_pool_backward",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]
 
 

@@ -534,6 +534,85 @@ class Bilinear(torch.autograd.Function):
         return (de1, de2) + tuple(rets)
 
 
+class AtomsBcastAddAct(torch.autograd.Function):
+    """y[b,n,c] = act(x[b,n,c] + v[b,c]); x None = F.tile of the per-molecule vector over the atoms, v None = activation only
+    (the query broadcasts of alternating_coattention.py:73-77 / parallel_coattention.py:72-79)."""
+
+    @staticmethod
+    def forward(ctx, x, v, n_atoms, act):
+        t = x if x is not None else v
+        _need_cuda(t)
+        x, v = _f32(x), _f32(v)
+        if x is not None:
+            mb, n_atoms, ch = x.shape
+        else:
+            mb, ch = v.shape
+        if v is not None and tuple(v.shape) != (mb, ch):
+            raise ValueError("gcnbmp: broadcast vector %s does not match atoms %s" % (tuple(v.shape), (mb, n_atoms, ch)))
+        y = torch.empty((mb, n_atoms, ch), device=t.device, dtype=torch.float32)
+        K.check(K.lib.bmp_atoms_bcast_add_act_forward(_p(x), _p(v), _p(y), mb, n_atoms, ch, act, _stream()))
+        ctx.save_for_backward(y)
+        ctx.meta = (x is not None, v is not None, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        has_x, has_v, act = ctx.meta
+        mb, n, ch = y.shape
+        dy = _f32(dy)
+        dx = torch.empty_like(y) if has_x else None
+        dv = torch.empty((mb, ch), device=y.device, dtype=torch.float32) if has_v else None
+        K.check(K.lib.bmp_atoms_bcast_add_act_backward(_p(y), _p(dy), _p(dx), _p(dv), mb, n, ch, act, _stream()))
+        return dx, dv, None, None
+
+
+class AtomsSoftmax(torch.autograd.Function):
+    """F.softmax(x) with Chainer's default axis=1 on a (mb, N, C) array: over the atoms."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = _f32(x)
+        mb, n, ch = x.shape
+        y = torch.empty_like(x)
+        K.check(K.lib.bmp_atoms_softmax_forward(_p(x), _p(y), mb, n, ch, _stream()))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        mb, n, ch = y.shape
+        dx = torch.empty_like(y)
+        K.check(K.lib.bmp_atoms_softmax_backward(_p(y), _p(_f32(dy)), _p(dx), mb, n, ch, _stream()))
+        return dx
+
+
+class AtomsPool(torch.autograd.Function):
+    """F.sum(F.tile(attn, (1, 1, C)) * z, axis=1) (attn (mb,N,1)) or F.sum(attn * z, axis=1) (attn (mb,N,C))."""
+
+    @staticmethod
+    def forward(ctx, attn, z):
+        _need_cuda(attn, z)
+        attn, z = _f32(attn), _f32(z)
+        mb, n, ch = z.shape
+        if attn.shape[:2] != z.shape[:2] or attn.shape[2] not in (1, ch):
+            raise ValueError("gcnbmp: attention %s does not pool atoms %s" % (tuple(attn.shape), tuple(z.shape)))
+        out = torch.empty((mb, ch), device=z.device, dtype=torch.float32)
+        K.check(K.lib.bmp_atoms_pool_forward(_p(attn), attn.shape[2], _p(z), _p(out), mb, n, ch, _stream()))
+        ctx.save_for_backward(attn, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        attn, z = ctx.saved_tensors
+        mb, n, ch = z.shape
+        da, dz = torch.empty_like(attn), torch.empty_like(z)
+        K.check(K.lib.bmp_atoms_pool_backward(_p(attn), attn.shape[2], _p(z), _p(_f32(d_out)), _p(da), _p(dz), mb, n, ch, _stream()))
+        return da, dz
+
+
 class Linear(torch.autograd.Function):
     """links.Linear + activation: act(x W^T + b)."""
 

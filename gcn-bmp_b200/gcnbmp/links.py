@@ -587,6 +587,85 @@ class VQAParallelCoattention(NieFineCoattention):
     _default_activation = staticmethod(functions.tanh)
 
 
+class AlternatingCoattention(Link):
+    """models/coattention/alternating_coattention.py:14-86 (`--attn alter`): attention over the atoms of molecule 1 queried by g_2,
+    then over the atoms of molecule 2 queried by the pooled compact_1.  The GraphLinear over concat(tile(query), key) is split into
+    its query and key column blocks, so the (mb, N, O + H) concatenation is never built."""
+
+    def __init__(self, hidden_dim, out_dim, head, weight_tying=True):
+        Link.__init__(self)
+        n = 1 if weight_tying else 2
+        self.add_link("energy_layers_1", ChainList([GraphLinear(hidden_dim + out_dim, head) for _ in range(n)]))
+        self.add_link("energy_layers_2", ChainList([GraphLinear(head, 1)]))
+        self.add_link("j_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, head=head, weight_tying=weight_tying)
+
+    def compute_attention(self, query, key, focus):
+        idx = 0 if self.weight_tying else focus - 1
+        l1, l2 = self.energy_layers_1[idx], self.energy_layers_2[idx]     # energy_layers_2 has one entry, as in the reference (:26-28)
+        mb, n, H = key.shape
+        O = self.out_dim
+        xk = Fn.Linear.apply(key.reshape(mb * n, H), l1.W[:, O:].contiguous(), l1.b, Fn.act_code(functions.identity)).reshape(mb, n, self.head)
+        vq = Fn.Linear.apply(query, l1.W[:, :O].contiguous(), None, Fn.act_code(functions.identity))
+        energy = Fn.AtomsBcastAddAct.apply(xk, vq, n, Fn.act_code(functions.tanh))                        # :77
+        return Fn.AtomsSoftmax.apply(l2(energy))                                                          # :78-79
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        c1 = Fn.AtomsPool.apply(self.compute_attention(_as_device(g_2, torch.float32), a1, 1), self.j_layer(a1))
+        c2 = Fn.AtomsPool.apply(self.compute_attention(c1, a2, 2), self.j_layer(a2))
+        return c1, c2
+
+
+class ParallelCoattention(Link):
+    """models/coattention/parallel_coattention.py:12-83 (`--attn para`, head = 1): act(Bilinear(atom, other molecule's graph vector))
+    weighs j_layer(atoms); no softmax."""
+
+    def __init__(self, hidden_dim, out_dim, head, activation=functions.tanh, weight_tying=True):
+        Link.__init__(self)
+        if head != 1:
+            raise ValueError("ParallelCoattention: F.tile(attn, (1, 1, out_dim)) at parallel_coattention.py:42 only lines up for head = 1")
+        n = 1 if weight_tying else 2
+        self.add_link("energy_layers", ChainList([_Bilinear(hidden_dim, out_dim, head) for _ in range(n)]))
+        self.add_link("j_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, head=head, activation=activation, weight_tying=weight_tying)
+
+    def compute_attention(self, query, key, focus):
+        e = self.energy_layers[0 if self.weight_tying else focus - 1]
+        mb, n, H = key.shape
+        qt = Fn.AtomsBcastAddAct.apply(None, query, n, Fn.act_code(functions.identity)).reshape(mb * n, self.out_dim)   # F.tile :73-75
+        energy = Fn.Bilinear.apply(key.reshape(mb * n, H), qt, e.W, e.V1, e.V2, e.b).reshape(mb, n, self.head)
+        return Fn.AtomsBcastAddAct.apply(energy, None, n, Fn.act_code(self.activation))
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        g1, g2 = _as_device(g_1, torch.float32), _as_device(g_2, torch.float32)
+        c1 = Fn.AtomsPool.apply(self.compute_attention(g2, a1, 1), self.j_layer(a1))
+        c2 = Fn.AtomsPool.apply(self.compute_attention(g1, a2, 2), self.j_layer(a2))
+        return c1, c2
+
+
+class CircularParallelCoattention(Link):
+    """models/coattention/parallel_coattention.py:86-187 (`--attn circ`): act(circular_correlation(j_layer(atom), other graph vector))
+    weighs j_layer(atoms) element-wise."""
+
+    def __init__(self, hidden_dim, out_dim, activation=functions.tanh, weight_tying=True):
+        Link.__init__(self)
+        self.add_link("j_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, head=out_dim, activation=activation, weight_tying=weight_tying)
+
+    def _side(self, atoms, query):
+        z = self.j_layer(atoms)
+        mb, n, O = z.shape
+        qt = Fn.AtomsBcastAddAct.apply(None, query, n, Fn.act_code(functions.identity)).reshape(mb * n, O)
+        corr = Fn.HoleCorr.apply(z.reshape(mb * n, O), qt).reshape(mb, n, O)                              # circular_correlation(key, query)
+        return Fn.AtomsPool.apply(Fn.AtomsBcastAddAct.apply(corr, None, n, Fn.act_code(self.activation)), z)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        return self._side(a1, _as_device(g_2, torch.float32)), self._side(a2, _as_device(g_1, torch.float32))
+
+
 class FourierFineCoattention(NieFineCoattention):
     """models/coattention/nie_coattention.py:399-515 (`--attn fourier`): the energy map is taken between the FFTs (over the hidden
     axis) of the atom states, real parts and imaginary parts through the same Bilinear layer.  The DFT is linear, so the sum of the two

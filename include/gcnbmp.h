@@ -335,6 +335,21 @@ int bmp_bilinear_backward(const float *e1, const float *e2, const float *W, cons
                           const float *dy, float *du, float *de1, float *de2, float *dW, float *dV1, float *dV2, float *db,
                           int rows, int left, int right, int out, void *stream);
 
+/* ---- atom-wise primitives of the vector-query co-attentions (`--attn alter | para | circ`) -------------------------
+ * models/coattention/alternating_coattention.py:34-80, parallel_coattention.py:33-80 (ParallelCoattention) and :107-160
+ * (CircularParallelCoattention): a (mb, O) query vector against (mb, N, C) atom arrays.
+ *   bcast_add_act   y[b,n,c] = act(x[b,n,c] + v[b,c]); x NULL = F.tile of v over the atoms, v NULL = plain activation.
+ *                   backward: dx = dy * act'(y) (NULL: skipped), dv[b,c] = sum over atoms of the same (NULL: skipped)
+ *   softmax         F.softmax(x, axis=1) over the atoms of each (b, c)
+ *   pool            out[b,c] = sum_n a[b,n,(a_ch == 1 ? 0 : c)] * z[b,n,c]  = F.sum(F.tile(attn) * z, axis=1)              */
+int bmp_atoms_bcast_add_act_forward(const float *x, const float *v, float *y, int mb, int n_atoms, int ch, int act, void *stream);
+int bmp_atoms_bcast_add_act_backward(const float *y, const float *dy, float *dx, float *dv, int mb, int n_atoms, int ch, int act, void *stream);
+int bmp_atoms_softmax_forward(const float *x, float *y, int mb, int n_atoms, int ch, void *stream);
+int bmp_atoms_softmax_backward(const float *y, const float *dy, float *dx, int mb, int n_atoms, int ch, void *stream);
+int bmp_atoms_pool_forward(const float *a, int a_ch, const float *z, float *out, int mb, int n_atoms, int ch, void *stream);
+int bmp_atoms_pool_backward(const float *a, int a_ch, const float *z, const float *d_out, float *da, float *dz,
+                            int mb, int n_atoms, int ch, void *stream);
+
 /* Optimizer hooks of train_binary.py:537-543 on the flat gradient, in the order the reference adds them:
  * GradientClipping(threshold) (g *= threshold/||g||_2 when that is < 1; off when threshold <= 0), WeightDecay(l2_rate)
  * (g += l2 * p), Lasso(l1_rate) (g += l1 * sign(p)).  norm_ws: one float of device scratch (needed when clipping).     */

@@ -337,6 +337,90 @@ class VQAParallelCoattention(NieFineCoattention):
     default_activation = "tanh"       # vqa_parallel_coattention.py:23
 
 
+class AlternatingCoattention(object):
+    """alternating_coattention.py:14-86."""
+
+    def __init__(self, p, hidden_dim, out_dim, head, weight_tying=True):
+        self.p, self.out_dim, self.weight_tying = p, out_dim, weight_tying
+
+    def compute_attention(self, query, key, focus):
+        idx = 0 if self.weight_tying else focus - 1
+        q1, q2 = self.p.sub("energy_layers_1/%d" % idx), self.p.sub("energy_layers_2/%d" % idx)
+        n = key.shape[1]
+        query = F.tile(F.expand_dims(query, 1), (1, n, 1))                             # :73-75
+        energy = F.tanh(F.graph_linear(F.concat((query, key), axis=2), q1["W"], q1["b"]))   # :77
+        return F.softmax(F.graph_linear(energy, q2["W"], q2["b"]), axis=1)            # :78-79
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        j = self.p.sub("j_layer")
+        attn_1 = F.tile(self.compute_attention(g_2, atoms_1, 1), (1, 1, self.out_dim))
+        c1 = F.sum_(F.mul(attn_1, F.graph_linear(atoms_1, j["W"], j["b"])), axis=1)    # :44-47
+        attn_2 = F.tile(self.compute_attention(c1, atoms_2, 2), (1, 1, self.out_dim))
+        c2 = F.sum_(F.mul(attn_2, F.graph_linear(atoms_2, j["W"], j["b"])), axis=1)    # :50-54
+        return c1, c2
+
+
+class ParallelCoattention(object):
+    """parallel_coattention.py:12-83."""
+
+    def __init__(self, p, hidden_dim, out_dim, head, activation="tanh", weight_tying=True):
+        self.p, self.hidden_dim, self.out_dim, self.head = p, hidden_dim, out_dim, head
+        self.act, self.weight_tying = ACT[activation], weight_tying
+
+    def compute_attention(self, query, key, focus):
+        e = self.p.sub("energy_layers/%d" % (0 if self.weight_tying else focus - 1))
+        mb, n, _ = key.shape
+        query = F.reshape(F.tile(F.expand_dims(query, 1), (1, n, 1)), (mb * n, self.out_dim))
+        key = F.reshape(key, (mb * n, self.hidden_dim))
+        energy = self.act(F.bilinear(key, query, e["W"], e["V1"], e["V2"], e["b"]))    # :79
+        return F.reshape(energy, (mb, n, self.head))
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        j = self.p.sub("j_layer")
+        attn_1 = F.tile(self.compute_attention(g_2, atoms_1, 1), (1, 1, self.out_dim))
+        c1 = F.sum_(F.mul(attn_1, F.graph_linear(atoms_1, j["W"], j["b"])), axis=1)
+        attn_2 = F.tile(self.compute_attention(g_1, atoms_2, 2), (1, 1, self.out_dim))
+        c2 = F.sum_(F.mul(attn_2, F.graph_linear(atoms_2, j["W"], j["b"])), axis=1)
+        return c1, c2
+
+
+class CircularParallelCoattention(object):
+    """parallel_coattention.py:86-187."""
+
+    def __init__(self, p, hidden_dim, out_dim, activation="tanh"):
+        self.p, self.out_dim, self.act = p, out_dim, ACT[activation]
+
+    def _corr(self, left_x, right_x):                                                  # :160-187, as hole.py:28-50
+        zeros = lambda v: F.const(np.zeros_like(v.data))
+        lr, li = F.fft((left_x, zeros(left_x)))
+        rr, ri = F.fft((right_x, zeros(right_x)))
+        out, _ = F.ifft((F.add(F.mul(lr, rr), F.mul(li, ri)), F.sub(F.mul(lr, ri), F.mul(li, rr))))
+        return out
+
+    def _side(self, atoms, query):
+        j = self.p.sub("j_layer")
+        atoms = F.graph_linear(atoms, j["W"], j["b"])                                  # :124
+        mb, n, _ = atoms.shape
+        q = F.reshape(F.tile(F.expand_dims(query, 1), (1, n, 1)), (mb * n, self.out_dim))
+        k = F.reshape(atoms, (mb * n, self.out_dim))
+        attn = F.reshape(self.act(self._corr(k, q)), (mb, n, self.out_dim))            # :156-157
+        return F.sum_(F.mul(attn, atoms), axis=1)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        return self._side(atoms_1, g_2), self._side(atoms_2, g_1)
+
+
+def vector_coattn_shapes(kind, hidden_dim, out_dim, head=1):
+    s = {"j_layer/W": (out_dim, hidden_dim), "j_layer/b": (out_dim,)}
+    if kind == "alter":
+        s.update({"energy_layers_1/0/W": (head, hidden_dim + out_dim), "energy_layers_1/0/b": (head,),
+                  "energy_layers_2/0/W": (1, head), "energy_layers_2/0/b": (1,)})
+    elif kind == "para":
+        s.update({"energy_layers/0/W": (hidden_dim, out_dim, head), "energy_layers/0/V1": (hidden_dim, head),
+                  "energy_layers/0/V2": (out_dim, head), "energy_layers/0/b": (head,)})
+    return s
+
+
 class FourierFineCoattention(NieFineCoattention):
     """nie_coattention.py:399-515: the energy map is act(Bilinear(Re fft(key), Re fft(query)) + Bilinear(Im fft(key), Im fft(query)))
     with the FFT over the hidden axis (:484-491,:505-515); the head path sees the atoms themselves."""

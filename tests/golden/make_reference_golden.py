@@ -48,6 +48,8 @@ ref_relgcn = load("ref_relgcn", "models/relgcn.py")
 ref_nie = load("ref_nie", "models/coattention/nie_coattention.py")
 ref_vqa = load("ref_vqa", "models/coattention/vqa_parallel_coattention.py")
 ref_pool = load("ref_pool", "models/coattention/PoolingFineCoattention.py")
+ref_alter = load("ref_alter", "models/coattention/alternating_coattention.py")
+ref_para = load("ref_para", "models/coattention/parallel_coattention.py")
 ref_hole = load("ref_hole", "models/link_prediction/hole.py")
 ref_mlp = load("ref_mlp", "models/mlp.py")
 ref_mono = {"ggnn_py": load("ref_ggnn_py", "models/ggnn.py"), "ggnn_att": load("ref_ggnn_att", "models/ggnn_att.py"),
@@ -267,6 +269,23 @@ def main():
         onet = mk_ora(R.P(tab), H, O, head)
         o_out, o_gin = run(lambda x1, x2: onet(x1, M.const(g1), x2, M.const(g2)), [a1, a2], ws)
         check_and_save(tag, params, [], [a1, a2], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab), dict(kind=tag, H=H, O=O, head=head))
+    # ---- vector-query co-attentions: alternating / parallel / circular (the graph vectors g_1, g_2 are live inputs here)
+    for tag, kind, mk_ref, mk_ora, head in (
+            ("coattn_alter", "alter", lambda H, O, hd: ref_alter.AlternatingCoattention(H, O, hd, weight_tying=True), lambda p, H, O, hd: R.AlternatingCoattention(p, H, O, hd), 4),
+            ("coattn_para", "para", lambda H, O, hd: ref_para.ParallelCoattention(H, O, hd, activation=CF.tanh, weight_tying=True), lambda p, H, O, hd: R.ParallelCoattention(p, H, O, hd), 1),
+            ("coattn_circ", "circ", lambda H, O, hd: ref_para.CircularParallelCoattention(H, O, activation=CF.tanh), lambda p, H, O, hd: R.CircularParallelCoattention(p, H, O), 1)):
+        H, O, mb, N1, N2 = 12, 8, 3, 6, 9
+        a1, a2 = rng.standard_normal((mb, N1, H)) * 0.5, rng.standard_normal((mb, N2, H)) * 0.5
+        g1, g2 = rng.standard_normal((mb, O)) * 0.5, rng.standard_normal((mb, O)) * 0.5
+        params = R.init_params(R.vector_coattn_shapes(kind, H, O, head), rng, dtype=np.float64)
+        ws = [rng.standard_normal((mb, O)), rng.standard_normal((mb, O))]
+        net = mk_ref(H, O, head)
+        load_params(net, params)
+        r_out, r_gin = run(lambda x1, x2, q1, q2: net(x1, q1, x2, q2), [a1, a2, g1, g2], ws)
+        tab = R.wrap_params(params)
+        onet = mk_ora(R.P(tab), H, O, head)
+        o_out, o_gin = run(lambda x1, x2, q1, q2: onet(x1, q1, x2, q2), [a1, a2, g1, g2], ws)
+        check_and_save(tag, params, [], [a1, a2, g1, g2], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab), dict(kind=tag, H=H, O=O, head=head))
     # ---- the Deep / VeryDeep / ExtremeDeep Nie variants (energy on the original atoms, heads on the transformed ones)
     for tag, rcls, ocls, nl in (("coattn_deep", ref_nie.DeepNieFineCoattention, R.DeepNieFineCoattention, 1),
                                 ("coattn_very_deep", ref_nie.VeryDeepNieFineCoattention, R.VeryDeepNieFineCoattention, 2),

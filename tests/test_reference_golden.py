@@ -63,6 +63,11 @@ def _oracle_fn(fx, tab):
     if kind == "relgcn":
         net = R.RelGCN(P, m["O"], ch_list=list(m["ch"]), scale_adj=m["scale"])
         return lambda: (net(fx["ints"][0], fx["floats"][0]),)
+    if kind in ("coattn_alter", "coattn_para", "coattn_circ"):
+        cls = {"coattn_alter": lambda: R.AlternatingCoattention(P, m["H"], m["O"], m["head"]),
+               "coattn_para": lambda: R.ParallelCoattention(P, m["H"], m["O"], m["head"]),
+               "coattn_circ": lambda: R.CircularParallelCoattention(P, m["H"], m["O"])}[kind]()
+        return lambda a1, a2, g1, g2: cls(a1, g1, a2, g2)
     if kind.startswith("coattn"):
         cls = {"coattn_nie": lambda: R.NieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_vqa": lambda: R.VQAParallelCoattention(P, m["H"], m["O"], m["head"]),
@@ -95,7 +100,7 @@ def _oracle_fn(fx, tab):
 
 def _n_var_inputs(fx):
     k = fx["meta"]["kind"]
-    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "readout": 2}.get(k, 2)
+    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4}.get(k, 2)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -192,6 +197,11 @@ def _product(fx):
     if kind == "relgcn":
         net = gcnbmp.RelGCN(m["O"], ch_list=list(m["ch"]), scale_adj=m["scale"])
         return (lambda: (net(fx["ints"][0], fx["floats"][0].astype(np.float32)),)), net
+    if kind in ("coattn_alter", "coattn_para", "coattn_circ"):
+        net = {"coattn_alter": lambda: gcnbmp.AlternatingCoattention(m["H"], m["O"], m["head"]),
+               "coattn_para": lambda: gcnbmp.ParallelCoattention(m["H"], m["O"], m["head"]),
+               "coattn_circ": lambda: gcnbmp.CircularParallelCoattention(m["H"], m["O"])}[kind]()
+        return (lambda a1, a2, g1, g2: net(a1, g1, a2, g2)), net
     if kind.startswith("coattn"):
         net = {"coattn_nie": lambda: gcnbmp.NieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_vqa": lambda: gcnbmp.VQAParallelCoattention(m["H"], m["O"], m["head"]),
