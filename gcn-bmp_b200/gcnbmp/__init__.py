@@ -11,7 +11,7 @@ from . import metrics
 from . import evaluate
 from .links import (MAX_ATOMIC_NUM, functions, Link, ChainList, GraphLinear, GGNNUpdate, RelGCNUpdate,
                     GGNNReadout, GGNN, GGNNMono, RelGCN, NieFineCoattention, VQAParallelCoattention,
-                    PoolingFineCoattention, AlternatingCoattention, ParallelCoattention, CircularParallelCoattention, FourierFineCoattention, DeepNieFineCoattention, VeryDeepNieFineCoattention, ExtremeDeepNieFineCoattention, HolE, HOLE, MLP, SymMLP, NTN, DistMult, BilinearDiag, GraphConvPredictorForPair,
+                    PoolingFineCoattention, AlternatingCoattention, ParallelCoattention, CircularParallelCoattention, GlobalCoattention, NeuralCoattention, FourierFineCoattention, DeepNieFineCoattention, VeryDeepNieFineCoattention, ExtremeDeepNieFineCoattention, HolE, HOLE, MLP, SymMLP, NTN, DistMult, BilinearDiag, GraphConvPredictorForPair,
                     sigmoid_cross_entropy, seed)
 
 __version__ = "0.1.0"

@@ -666,6 +666,67 @@ class CircularParallelCoattention(Link):
         return self._side(a1, _as_device(g_2, torch.float32)), self._side(a2, _as_device(g_1, torch.float32))
 
 
+def _atoms_mean(atoms):
+    """F.mean(atoms, axis=1) through the pooling kernel (constant attention 1/N)."""
+    mb, n, _ = atoms.shape
+    return Fn.AtomsPool.apply(torch.full((mb, n, 1), 1.0 / n, device=atoms.device, dtype=torch.float32), atoms)
+
+
+class GlobalCoattention(Link):
+    """models/coattention/global_coattention.py:9-73: sigmoid(Linear([atom | mean of the other molecule's atoms])) gates lt_layer(atoms)
+    channel by channel; the Linear over the concatenation is split into its two column blocks."""
+
+    def __init__(self, hidden_dim, out_dim, weight_tying=True):
+        Link.__init__(self)
+        n = 1 if weight_tying else 2
+        self.add_link("att_layers", ChainList([_Linear(2 * hidden_dim, out_dim) for _ in range(n)]))
+        self.add_link("lt_layer", GraphLinear(hidden_dim, out_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, weight_tying=weight_tying)
+
+    def compute_attention(self, query, key, focus):
+        l = self.att_layers[0 if self.weight_tying else focus - 1]
+        mb, n, H = key.shape
+        ident = Fn.act_code(functions.identity)
+        xk = Fn.Linear.apply(key.reshape(mb * n, H), l.W[:, :H].contiguous(), l.b, ident).reshape(mb, n, self.out_dim)   # concat((key, query)) :67
+        vq = Fn.Linear.apply(query, l.W[:, H:].contiguous(), None, ident)
+        return Fn.AtomsBcastAddAct.apply(xk, vq, n, Fn.act_code(functions.sigmoid))
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        m1, m2 = _atoms_mean(a1), _atoms_mean(a2)
+        c1 = Fn.AtomsPool.apply(self.compute_attention(m2, a1, 1), self.lt_layer(a1))
+        c2 = Fn.AtomsPool.apply(self.compute_attention(m1, a2, 2), self.lt_layer(a2))
+        return c1, c2
+
+
+class NeuralCoattention(Link):
+    """models/coattention/neural_coattention.py:8-71: doc = act(att(atoms)), context = act(att(mean of the other molecule's atoms)),
+    sigmoid(doc . context) weighs doc."""
+
+    def __init__(self, hidden_dim, out_dim, activation=functions.relu, weight_tying=True):
+        Link.__init__(self)
+        n = 1 if weight_tying else 2
+        self.add_link("att_layers", ChainList([GraphLinear(hidden_dim, out_dim) for _ in range(n)]))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, activation=activation, weight_tying=weight_tying)
+
+    def _side(self, query, key, focus):
+        l = self.att_layers[0 if self.weight_tying else focus - 1]
+        mb, n, _ = key.shape
+        O = self.out_dim
+        ctx = l(query, self.activation)                                                                    # (mb, O)   :66
+        doc = l(key, self.activation)                                                                      # (mb, N, O) :67
+        ctx_t = Fn.AtomsBcastAddAct.apply(None, ctx, n, Fn.act_code(functions.identity)).reshape(mb * n, O)
+        prod = Fn.PairFeatures.apply(doc.reshape(mb * n, O), ctx_t, K.PAIR_PROD)
+        ones = torch.ones((1, O), device=key.device, dtype=torch.float32)
+        dot = Fn.Linear.apply(prod, ones, None, Fn.act_code(functions.identity)).reshape(mb, n, 1)         # F.matmul(doc, context^T) :68
+        energy = Fn.AtomsBcastAddAct.apply(dot, None, n, Fn.act_code(functions.sigmoid))
+        return Fn.AtomsPool.apply(energy, doc)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        a1, a2 = _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32)
+        return self._side(_atoms_mean(a2), a1, 1), self._side(_atoms_mean(a1), a2, 2)
+
+
 class FourierFineCoattention(NieFineCoattention):
     """models/coattention/nie_coattention.py:399-515 (`--attn fourier`): the energy map is taken between the FFTs (over the hidden
     axis) of the atom states, real parts and imaginary parts through the same Bilinear layer.  The DFT is linear, so the sum of the two

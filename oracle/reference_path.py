@@ -410,6 +410,52 @@ class CircularParallelCoattention(object):
         return self._side(atoms_1, g_2), self._side(atoms_2, g_1)
 
 
+class GlobalCoattention(object):
+    """global_coattention.py:9-73."""
+
+    def __init__(self, p, hidden_dim, out_dim, weight_tying=True):
+        self.p, self.out_dim, self.weight_tying = p, out_dim, weight_tying
+
+    def compute_attention(self, query, key, focus):
+        q = self.p.sub("att_layers/%d" % (0 if self.weight_tying else focus - 1))
+        mb, n, hd = key.shape
+        query = F.reshape(F.tile(F.expand_dims(query, 1), (1, n, 1)), (mb * n, hd))    # :62-64
+        key = F.reshape(key, (mb * n, hd))
+        energy = F.sigmoid(F.linear(F.concat((key, query), axis=-1), q["W"], q["b"]))  # :67
+        return F.reshape(energy, (mb, n, self.out_dim))
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        lt = self.p.sub("lt_layer")
+        g1, g2 = F.mean(atoms_1, axis=1), F.mean(atoms_2, axis=1)                      # :36-37
+        c1 = F.sum_(F.mul(self.compute_attention(g2, atoms_1, 1), F.graph_linear(atoms_1, lt["W"], lt["b"])), axis=1)
+        c2 = F.sum_(F.mul(self.compute_attention(g1, atoms_2, 2), F.graph_linear(atoms_2, lt["W"], lt["b"])), axis=1)
+        return c1, c2
+
+
+class NeuralCoattention(object):
+    """neural_coattention.py:8-71."""
+
+    def __init__(self, p, hidden_dim, out_dim, activation="relu", weight_tying=True):
+        self.p, self.out_dim, self.act, self.weight_tying = p, out_dim, ACT[activation], weight_tying
+
+    def compute_attention(self, query, key, focus):
+        q = self.p.sub("att_layers/%d" % (0 if self.weight_tying else focus - 1))
+        query = F.expand_dims(query, 1)                                                # :64
+        context = self.act(F.graph_linear(query, q["W"], q["b"]))                      # :66
+        doc = self.act(F.graph_linear(key, q["W"], q["b"]))                            # :67
+        energy = F.sigmoid(F.matmul(doc, F.transpose(context, (0, 2, 1))))             # :68
+        return energy, doc
+
+    def _side(self, query, key, focus):
+        attn, doc = self.compute_attention(query, key, focus)
+        return F.sum_(F.mul(F.tile(attn, (1, 1, self.out_dim)), doc), axis=1)
+
+    def __call__(self, atoms_1, g_1, atoms_2, g_2):
+        c1 = self._side(F.mean(atoms_2, axis=1), atoms_1, 1)
+        c2 = self._side(F.mean(atoms_1, axis=1), atoms_2, 2)
+        return c1, c2
+
+
 def vector_coattn_shapes(kind, hidden_dim, out_dim, head=1):
     s = {"j_layer/W": (out_dim, hidden_dim), "j_layer/b": (out_dim,)}
     if kind == "alter":
@@ -418,6 +464,11 @@ def vector_coattn_shapes(kind, hidden_dim, out_dim, head=1):
     elif kind == "para":
         s.update({"energy_layers/0/W": (hidden_dim, out_dim, head), "energy_layers/0/V1": (hidden_dim, head),
                   "energy_layers/0/V2": (out_dim, head), "energy_layers/0/b": (head,)})
+    elif kind == "global":
+        s = {"lt_layer/W": (out_dim, hidden_dim), "lt_layer/b": (out_dim,),
+             "att_layers/0/W": (out_dim, 2 * hidden_dim), "att_layers/0/b": (out_dim,)}
+    elif kind == "neural":
+        s = {"att_layers/0/W": (out_dim, hidden_dim), "att_layers/0/b": (out_dim,)}
     return s
 
 

@@ -50,6 +50,8 @@ ref_vqa = load("ref_vqa", "models/coattention/vqa_parallel_coattention.py")
 ref_pool = load("ref_pool", "models/coattention/PoolingFineCoattention.py")
 ref_alter = load("ref_alter", "models/coattention/alternating_coattention.py")
 ref_para = load("ref_para", "models/coattention/parallel_coattention.py")
+ref_global = load("ref_global", "models/coattention/global_coattention.py")
+ref_neural = load("ref_neural", "models/coattention/neural_coattention.py")
 ref_hole = load("ref_hole", "models/link_prediction/hole.py")
 ref_mlp = load("ref_mlp", "models/mlp.py")
 ref_mono = {"ggnn_py": load("ref_ggnn_py", "models/ggnn.py"), "ggnn_att": load("ref_ggnn_att", "models/ggnn_att.py"),
@@ -273,7 +275,9 @@ def main():
     for tag, kind, mk_ref, mk_ora, head in (
             ("coattn_alter", "alter", lambda H, O, hd: ref_alter.AlternatingCoattention(H, O, hd, weight_tying=True), lambda p, H, O, hd: R.AlternatingCoattention(p, H, O, hd), 4),
             ("coattn_para", "para", lambda H, O, hd: ref_para.ParallelCoattention(H, O, hd, activation=CF.tanh, weight_tying=True), lambda p, H, O, hd: R.ParallelCoattention(p, H, O, hd), 1),
-            ("coattn_circ", "circ", lambda H, O, hd: ref_para.CircularParallelCoattention(H, O, activation=CF.tanh), lambda p, H, O, hd: R.CircularParallelCoattention(p, H, O), 1)):
+            ("coattn_circ", "circ", lambda H, O, hd: ref_para.CircularParallelCoattention(H, O, activation=CF.tanh), lambda p, H, O, hd: R.CircularParallelCoattention(p, H, O), 1),
+            ("coattn_global", "global", lambda H, O, hd: ref_global.GlobalCoattention(H, O, weight_tying=True), lambda p, H, O, hd: R.GlobalCoattention(p, H, O), 1),
+            ("coattn_neural", "neural", lambda H, O, hd: ref_neural.NeuralCoattention(H, O, activation=CF.tanh, weight_tying=True), lambda p, H, O, hd: R.NeuralCoattention(p, H, O, activation="tanh"), 1)):
         H, O, mb, N1, N2 = 12, 8, 3, 6, 9
         a1, a2 = rng.standard_normal((mb, N1, H)) * 0.5, rng.standard_normal((mb, N2, H)) * 0.5
         g1, g2 = rng.standard_normal((mb, O)) * 0.5, rng.standard_normal((mb, O)) * 0.5

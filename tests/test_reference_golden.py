@@ -63,8 +63,10 @@ def _oracle_fn(fx, tab):
     if kind == "relgcn":
         net = R.RelGCN(P, m["O"], ch_list=list(m["ch"]), scale_adj=m["scale"])
         return lambda: (net(fx["ints"][0], fx["floats"][0]),)
-    if kind in ("coattn_alter", "coattn_para", "coattn_circ"):
-        cls = {"coattn_alter": lambda: R.AlternatingCoattention(P, m["H"], m["O"], m["head"]),
+    if kind in ("coattn_alter", "coattn_para", "coattn_circ", "coattn_global", "coattn_neural"):
+        cls = {"coattn_global": lambda: R.GlobalCoattention(P, m["H"], m["O"]),
+               "coattn_neural": lambda: R.NeuralCoattention(P, m["H"], m["O"], activation="tanh"),
+               "coattn_alter": lambda: R.AlternatingCoattention(P, m["H"], m["O"], m["head"]),
                "coattn_para": lambda: R.ParallelCoattention(P, m["H"], m["O"], m["head"]),
                "coattn_circ": lambda: R.CircularParallelCoattention(P, m["H"], m["O"])}[kind]()
         return lambda a1, a2, g1, g2: cls(a1, g1, a2, g2)
@@ -100,7 +102,7 @@ def _oracle_fn(fx, tab):
 
 def _n_var_inputs(fx):
     k = fx["meta"]["kind"]
-    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4}.get(k, 2)
+    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4, "coattn_global": 4, "coattn_neural": 4}.get(k, 2)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -197,8 +199,10 @@ def _product(fx):
     if kind == "relgcn":
         net = gcnbmp.RelGCN(m["O"], ch_list=list(m["ch"]), scale_adj=m["scale"])
         return (lambda: (net(fx["ints"][0], fx["floats"][0].astype(np.float32)),)), net
-    if kind in ("coattn_alter", "coattn_para", "coattn_circ"):
-        net = {"coattn_alter": lambda: gcnbmp.AlternatingCoattention(m["H"], m["O"], m["head"]),
+    if kind in ("coattn_alter", "coattn_para", "coattn_circ", "coattn_global", "coattn_neural"):
+        net = {"coattn_global": lambda: gcnbmp.GlobalCoattention(m["H"], m["O"]),
+               "coattn_neural": lambda: gcnbmp.NeuralCoattention(m["H"], m["O"], activation=f.tanh),
+               "coattn_alter": lambda: gcnbmp.AlternatingCoattention(m["H"], m["O"], m["head"]),
                "coattn_para": lambda: gcnbmp.ParallelCoattention(m["H"], m["O"], m["head"]),
                "coattn_circ": lambda: gcnbmp.CircularParallelCoattention(m["H"], m["O"])}[kind]()
         return (lambda a1, a2, g1, g2: net(a1, g1, a2, g2)), net
