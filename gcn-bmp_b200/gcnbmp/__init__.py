@@ -10,7 +10,7 @@ from . import functional
 from . import metrics
 from . import evaluate
 from .links import (MAX_ATOMIC_NUM, functions, Link, ChainList, GraphLinear, GGNNUpdate, RelGCNUpdate,
-                    GGNNReadout, GGNN, GGNNMono, RelGCN, NieFineCoattention, VQAParallelCoattention,
+                    GGNNReadout, GGNN, GGNNMono, RelGCN, GIN, GINUpdate, NieFineCoattention, VQAParallelCoattention,
                     PoolingFineCoattention, AlternatingCoattention, ParallelCoattention, CircularParallelCoattention, GlobalCoattention, NeuralCoattention, FourierFineCoattention, DeepNieFineCoattention, VeryDeepNieFineCoattention, ExtremeDeepNieFineCoattention, HolE, HOLE, MLP, SymMLP, NTN, DistMult, BilinearDiag, GraphConvPredictorForPair,
                     sigmoid_cross_entropy, seed)
 

@@ -523,6 +523,79 @@ class RelGCN(Link):
         return self.atoms
 
 
+class GINUpdate(Link):
+    """models/gin.py:58-106: new_h = relu(linear_g2(relu(linear_g1(h + (sum_e A_e) h)))).  The aggregation h + sum_e A_e h is the
+    relational-GCN layer with identity self / edge weights, so it runs on that kernel; the two GraphLinears are Linear launches.
+    Dropout (the reference's stand-in for batch normalisation) is stochastic: only dropout_ratio = 0 is supported."""
+
+    def __init__(self, hidden_dim=16, dropout_ratio=0.5, num_edge_type=4):
+        Link.__init__(self)
+        self.add_link("linear_g1", GraphLinear(hidden_dim, hidden_dim))
+        self.add_link("linear_g2", GraphLinear(hidden_dim, hidden_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, dropout_ratio=dropout_ratio, num_edge_type=num_edge_type, _const=None)
+
+    def _constants(self, dev, edge=True):
+        H, E = self.hidden_dim, self.num_edge_type
+        if self._const is None or self._const[0] != str(dev):
+            eye = torch.eye(H, device=dev, dtype=torch.float32)
+            self.__dict__["_const"] = (str(dev), eye, torch.zeros(H, device=dev), eye.repeat_interleave(E, dim=0).contiguous(),
+                                       torch.zeros(H * E, device=dev), torch.zeros(H * E, H, device=dev))
+        _, eye, zb, eye_e, zb_e, zero_e = self._const
+        return [eye, zb, eye_e if edge else zero_e, zb_e]
+
+    def aggregate(self, h, adj, embed_W=None, edge=True):
+        return Fn.RelGCNEncode.apply(h, adj, (self.hidden_dim, self.hidden_dim), 0, K.ACT["identity"], torch.is_grad_enabled(),
+                                     K.MODE_F32, embed_W, *self._constants(adj.device, edge))
+
+    def __call__(self, h, adj):
+        if self.dropout_ratio > 0.0:
+            raise NotImplementedError("gcnbmp: GINUpdate with dropout_ratio > 0 is stochastic; construct it with dropout_ratio=0.0")
+        h, adj = _as_device(h, torch.float32), _adj_device(adj, K.MODE_F32)
+        return self.linear_g2(self.linear_g1(self.aggregate(h, adj), functions.relu), functions.relu)
+
+
+class GIN(Link):
+    """models/gin.py:109-190 -- embed -> GINUpdate steps -> GGNNReadout (R1).  As in the reference the loop runs over
+    `n_message_layers` (:154), i.e. ONE update when weight_tying=True whatever n_layers says."""
+
+    def __init__(self, out_dim, hidden_dim=16, n_layers=4, n_atom_types=MAX_ATOMIC_NUM, dropout_ratio=0.5,
+                 concat_hidden=False, weight_tying=True, activation=functions.identity):
+        Link.__init__(self)
+        n_message_layer = 1 if weight_tying else n_layers
+        n_readout_layer = n_layers if concat_hidden else 1
+        self.add_link("embed", _Embed(n_atom_types, hidden_dim))
+        self.add_link("update_layers", ChainList([GINUpdate(hidden_dim, dropout_ratio) for _ in range(n_message_layer)]))
+        self.add_link("readout_layers", ChainList([GGNNReadout(out_dim=out_dim, hidden_dim=hidden_dim, activation=activation,
+                                                               activation_agg=activation) for _ in range(n_readout_layer)]))
+        for r in self.readout_layers:
+            r.i_layer.ensure(2 * hidden_dim)
+            r.j_layer.ensure(2 * hidden_dim)
+        self.__dict__.update(out_dim=out_dim, hidden_dim=hidden_dim, n_message_layers=n_message_layer, concat_hidden=concat_hidden,
+                             weight_tying=weight_tying, atoms=None)
+
+    def __call__(self, atom_array, adj, is_real_node=None):
+        adj = _adj_device(adj, K.MODE_F32)
+        ups = list(self.update_layers)
+        if _is_ids(atom_array) and getattr(atom_array, "ndim", 2) <= 2:
+            # the embedding gather is fused into the relational-GCN kernel: identity self weights, zero edge weights
+            h = ups[0].aggregate(_as_device(atom_array, torch.int32), adj, self.embed.W, edge=False)
+        else:
+            h = _as_device(atom_array, torch.float32)
+        h0, gs = h, []
+        for step in range(self.n_message_layers):
+            h = ups[0 if self.weight_tying else step](h, adj)
+            if self.concat_hidden:
+                gs.append(self.readout_layers[step](h, h0, is_real_node))
+        self.__dict__["atoms"] = h
+        if self.concat_hidden:
+            return torch.cat(gs, dim=1)
+        return self.readout_layers[0](h, h0, is_real_node)
+
+    def get_atom_array(self):
+        assert self.atoms is not None
+        return self.atoms
+
+
 class _Embed(Link):
     """chainer_chemistry EmbedAtomID = links.EmbedID(in_size, out_size); W ~ N(0,1)."""
 

@@ -591,6 +591,54 @@ class HolE(object):
 
 
 # ----------------------------------------------------------------------------
+# models/gin.py:58-190 (GINUpdate, GIN; dropout_ratio = 0)
+# ----------------------------------------------------------------------------
+class GINUpdate(object):
+    def __init__(self, p, hidden_dim=16):
+        self.p = p
+
+    def __call__(self, h, adj):
+        a = F.sum_(F.as_var(adj), axis=1)                                              # :88
+        sum_h = F.add(F.matmul(a, h), h)                                               # :91-94
+        q1, q2 = self.p.sub("linear_g1"), self.p.sub("linear_g2")
+        new_h = F.relu(F.graph_linear(sum_h, q1["W"], q1["b"]))                        # :97
+        return F.relu(F.graph_linear(new_h, q2["W"], q2["b"]))                         # :103
+
+
+class GIN(object):
+    def __init__(self, p, out_dim, hidden_dim=16, n_layers=4, concat_hidden=False, weight_tying=True, activation="identity"):
+        self.p, self.concat_hidden, self.weight_tying = p, concat_hidden, weight_tying
+        self.n_message_layers = 1 if weight_tying else n_layers                        # :131,:154 (the loop bound)
+        self.readouts = [GGNNReadout(p.sub("readout_layers/%d" % i), out_dim, hidden_dim, activation=activation, activation_agg=activation)
+                         for i in range(n_layers if concat_hidden else 1)]
+        self.updates = [GINUpdate(p.sub("update_layers/%d" % i), hidden_dim) for i in range(self.n_message_layers)]
+        self.atoms = None
+
+    def __call__(self, atom_array, adj, is_real_node=None):
+        a = np.asarray(getattr(atom_array, "data", atom_array))
+        h = F.embed_id(a, self.p["embed/W"]) if a.ndim <= 2 else F.as_var(atom_array)  # :148-151
+        h0 = F.copy(h)
+        gs = []
+        for step in range(self.n_message_layers):
+            h = self.updates[0 if self.weight_tying else step](h, adj)
+            if self.concat_hidden:
+                gs.append(self.readouts[step](h, h0, is_real_node))
+        self.atoms = h
+        return F.concat(gs, axis=1) if self.concat_hidden else self.readouts[0](h, h0, is_real_node)
+
+
+def gin_shapes(out_dim, hidden_dim, n_layers, concat_hidden=False, weight_tying=True, n_atom_types=MAX_ATOMIC_NUM):
+    s = {"embed/W": (n_atom_types, hidden_dim)}
+    for i in range(1 if weight_tying else n_layers):
+        for l in ("linear_g1", "linear_g2"):
+            s["update_layers/%d/%s/W" % (i, l)], s["update_layers/%d/%s/b" % (i, l)] = (hidden_dim, hidden_dim), (hidden_dim,)
+    for i in range(n_layers if concat_hidden else 1):
+        for l in ("i_layer", "j_layer"):
+            s["readout_layers/%d/%s/W" % (i, l)], s["readout_layers/%d/%s/b" % (i, l)] = (out_dim, 2 * hidden_dim), (out_dim,)
+    return s
+
+
+# ----------------------------------------------------------------------------
 # models/mlp.py:20-110,154-197 -- the other link-prediction heads
 # ----------------------------------------------------------------------------
 def _stack(p, names, n_hidden, act, h):

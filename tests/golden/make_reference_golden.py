@@ -52,6 +52,7 @@ ref_alter = load("ref_alter", "models/coattention/alternating_coattention.py")
 ref_para = load("ref_para", "models/coattention/parallel_coattention.py")
 ref_global = load("ref_global", "models/coattention/global_coattention.py")
 ref_neural = load("ref_neural", "models/coattention/neural_coattention.py")
+ref_gin = load("ref_gin", "models/gin.py")
 ref_hole = load("ref_hole", "models/link_prediction/hole.py")
 ref_mlp = load("ref_mlp", "models/mlp.py")
 ref_mono = {"ggnn_py": load("ref_ggnn_py", "models/ggnn.py"), "ggnn_att": load("ref_ggnn_att", "models/ggnn_att.py"),
@@ -218,6 +219,21 @@ def main():
         blob.update({"gparam:" + k: v for k, v in ref_gp.items() if v is not None})
         np.savez_compressed(os.path.join(HERE, "ref_pair_%s.npz" % cname), **blob)
         print("ref_pair_%s.npz: logits %s, loss %.6f, %d parameter gradients, reference == oracle to 1e-10" % (cname, logits.shape, float(loss.data), len(ref_gp)))
+    # ---- GIN (models/gin.py; dropout off): tied (ONE update step, the loop bound at :154) and untied
+    for tag, tied, concat in (("gin_tied", True, False), ("gin_untied_concat", False, True)):
+        H, O, T, mb, N = 12, 8, 3, 3, 9
+        atoms, adj = random_molecules(rng, mb, N)
+        adj = adj.astype(np.float64)
+        params = R.init_params(R.gin_shapes(O, H, T, concat_hidden=concat, weight_tying=tied), rng, dtype=np.float64)
+        w = rng.standard_normal((mb, O * (T if concat else 1)))
+        net = ref_gin.GIN(O, hidden_dim=H, n_layers=T, dropout_ratio=0.0, concat_hidden=concat, weight_tying=tied, activation=CF.tanh)
+        load_params(net, params)
+        r_out, r_gin = run(lambda: net(atoms, adj), [], [w])
+        tab = R.wrap_params(params)
+        onet = R.GIN(R.P(tab), O, H, T, concat_hidden=concat, weight_tying=tied, activation="tanh")
+        o_out, o_gin = run(lambda: onet(atoms, adj), [], [w])
+        check_and_save(tag, params, [atoms], [adj], [w], r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab),
+                       dict(kind="gin", H=H, O=O, T=T, tied=tied, concat=concat, act="tanh"))
     # ---- bare GGNNUpdate with state threading (two calls, then reset, then one call)
     H, mb, N = 8, 2, 7
     _, adj = random_molecules(rng, mb, N)

@@ -46,6 +46,9 @@ def _oracle_fn(fx, tab):
     if kind == "ggnn":
         net = R.GGNN(P, m["O"], m["H"], m["T"], concat_hidden=m["concat"], weight_tying=m["tied"], activation=m["act"])
         return lambda A: (net(fx["ints"][0], A),)
+    if kind == "gin":
+        net = R.GIN(P, m["O"], m["H"], m["T"], concat_hidden=m["concat"], weight_tying=m["tied"], activation=m["act"])
+        return lambda: (net(fx["ints"][0], fx["floats"][0]),)
     if kind == "mono":
         net = R.GGNNMono(P, m["O"], m["H"], m["T"], weight_tying=m["tied"], sum_readout=m["sum_readout"])
 
@@ -102,7 +105,7 @@ def _oracle_fn(fx, tab):
 
 def _n_var_inputs(fx):
     k = fx["meta"]["kind"]
-    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4, "coattn_global": 4, "coattn_neural": 4}.get(k, 2)
+    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "gin": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4, "coattn_global": 4, "coattn_neural": 4}.get(k, 2)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -182,6 +185,9 @@ def _product(fx):
     if kind == "ggnn":
         net = gcnbmp.GGNN(m["O"], hidden_dim=m["H"], n_layers=m["T"], concat_hidden=m["concat"], weight_tying=m["tied"], activation=act(m["act"]))
         return (lambda A: (net(fx["ints"][0], A),)), net
+    if kind == "gin":
+        net = gcnbmp.GIN(m["O"], hidden_dim=m["H"], n_layers=m["T"], dropout_ratio=0.0, concat_hidden=m["concat"], weight_tying=m["tied"], activation=act(m["act"]))
+        return (lambda: (net(fx["ints"][0], fx["floats"][0].astype(np.float32)),)), net
     if kind == "mono":
         net = gcnbmp.GGNNMono(m["O"], m["H"], m["T"], weight_tying=m["tied"], sum_readout=m["sum_readout"])
 
