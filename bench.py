@@ -249,6 +249,7 @@ def run_gpu(args):
         fd = algorithmic_flops(256, 8, CFG["N"], CFG["E"], 256, K=1, readout="r1", attn=False, D=256)
         config_d = dict(value=round(nd / (d_ms * 1e-3), 1), unit="pairs/s per GPU", ms=round(d_ms, 3), pairs=nd,
                         achieved_tflops=round(nd * fd["pair_fwd"] / (d_ms * 1e-3) / 1e12, 1),
+                        frac_of_bf16_sustained_peak=round(nd * fd["pair_fwd"] / (d_ms * 1e-3) / 1e12 / peaks()["bf16_sustained"], 4),
                         note="forward only, inputs resident, hidden-256 tcgen05 encoder + readout (csrc/ggnn_tc256.cu); not the headline")
         del mD, encD
     cpu = cpu_baseline(args) if rank == 0 and not args.no_cpu else None

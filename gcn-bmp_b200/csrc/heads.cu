@@ -175,6 +175,35 @@ __global__ void atoms_pool_bwd_kernel(const float *__restrict__ a, int a_ch, con
     }
 }
 
+// ---------------------------------------------------------------- GIN aggregation (models/gin.py:88-94)
+// out[b,i,:] = h[b,i,:] + sum_e sum_j A[b,e,i,j] h[b,j,:]   (TRANS: A[b,e,j,i] -- the backward with respect to h).
+// One CTA per molecule: the bond types are summed into a 64 x 64 tile in shared memory once, then every thread owns
+// channels c, c + blockDim.x, ... of all atoms, reading h rows from shared memory.
+template <bool TRANS>
+__global__ void __launch_bounds__(256) gin_aggregate_kernel(const float *__restrict__ adj, const float *__restrict__ h,
+                                                            float *__restrict__ out, int mb, int E, int N, int H) {
+    extern __shared__ float sm[];
+    float *As = sm;                 // [N][N+1]
+    float *hs = sm + N * (N + 1);   // [N][H]
+    for (int b = blockIdx.x; b < mb; b += gridDim.x) {
+        for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+            const int i = idx / N, j = idx - i * N;
+            float s = 0.f;
+            for (int e = 0; e < E; ++e) s += adj[(((long)b * E + e) * N + (TRANS ? j : i)) * N + (TRANS ? i : j)];
+            As[i * (N + 1) + j] = s;
+        }
+        for (int idx = threadIdx.x; idx < N * H; idx += blockDim.x) hs[idx] = h[(long)b * N * H + idx];
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < N * H; idx += blockDim.x) {
+            const int i = idx / H, c = idx - i * H;
+            float s = hs[idx];
+            for (int j = 0; j < N; ++j) s = fmaf(As[i * (N + 1) + j], hs[j * H + c], s);
+            out[(long)b * N * H + idx] = s;
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- optimizer hooks
 __global__ void sumsq_kernel(const float *__restrict__ g, long n, float *__restrict__ out) {
     float s = 0.f;
@@ -332,6 +361,26 @@ extern "C" int bmp_atoms_pool_backward(const float *a, int a_ch, const float *z,
     atoms_pool_bwd_kernel<<<grid_for(rows * 32), 256, 0, (cudaStream_t)stream>>>(a, a_ch, z, d_out, da, dz, rows, n_atoms, ch);
     count_launch();
     return check_launch("atoms_pool_bwd_kernel");
+}
+
+extern "C" int bmp_gin_aggregate(const float *adj, const float *h, float *out, int mb, int n_edge, int n_atoms, int hidden,
+                                 int transpose, void *stream) {
+    if (!adj || !h || !out) { set_error("bmp_gin_aggregate: null pointer"); return BMP_EINVAL; }
+    if (mb <= 0) return BMP_OK;
+    if (n_atoms <= 0 || n_atoms > BMP_MAX_ATOMS || hidden <= 0 || n_edge <= 0) { set_error("bmp_gin_aggregate: bad shape N=%d H=%d E=%d", n_atoms, hidden, n_edge); return BMP_ESHAPE; }
+    const size_t smem = sizeof(float) * ((size_t)n_atoms * (n_atoms + 1) + (size_t)n_atoms * hidden);
+    if (smem > 227 * 1024) { set_error("bmp_gin_aggregate: hidden=%d needs %zu B of shared memory", hidden, smem); return BMP_ESHAPE; }
+    const int grid = mb < 148 * 4 ? mb : 148 * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (transpose) {
+        cudaFuncSetAttribute(gin_aggregate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gin_aggregate_kernel<true><<<grid, 256, smem, st>>>(adj, h, out, mb, n_edge, n_atoms, hidden);
+    } else {
+        cudaFuncSetAttribute(gin_aggregate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        gin_aggregate_kernel<false><<<grid, 256, smem, st>>>(adj, h, out, mb, n_edge, n_atoms, hidden);
+    }
+    count_launch();
+    return check_launch("gin_aggregate_kernel");
 }
 
 extern "C" int bmp_grad_hooks(float *grad, const float *param, int n, float clip_threshold, float l2_rate, float l1_rate,

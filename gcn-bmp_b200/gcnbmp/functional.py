@@ -613,6 +613,30 @@ class AtomsPool(torch.autograd.Function):
         return da, dz
 
 
+class GINAggregate(torch.autograd.Function):
+    """h + (sum_e A_e) h  (models/gin.py:88-94); the backward is the same kernel on the transposed adjacency."""
+
+    @staticmethod
+    def forward(ctx, h, adj):
+        _need_cuda(h, adj)
+        h, adj = _f32(h), _f32(adj)
+        mb, E, N, _ = adj.shape
+        H = h.shape[2]
+        out = torch.empty_like(h)
+        K.check(K.lib.bmp_gin_aggregate(_p(adj), _p(h), _p(out), mb, E, N, H, 0, _stream()))
+        ctx.save_for_backward(adj)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (adj,) = ctx.saved_tensors
+        mb, E, N, _ = adj.shape
+        d_out = _f32(d_out)
+        dh = torch.empty_like(d_out)
+        K.check(K.lib.bmp_gin_aggregate(_p(adj), _p(d_out), _p(dh), mb, E, N, d_out.shape[2], 1, _stream()))
+        return dh, None
+
+
 class Linear(torch.autograd.Function):
     """links.Linear + activation: act(x W^T + b)."""
 

@@ -524,9 +524,10 @@ class RelGCN(Link):
 
 
 class GINUpdate(Link):
-    """models/gin.py:58-106: new_h = relu(linear_g2(relu(linear_g1(h + (sum_e A_e) h)))).  The aggregation h + sum_e A_e h is the
-    relational-GCN layer with identity self / edge weights, so it runs on that kernel; the two GraphLinears are Linear launches.
-    Dropout (the reference's stand-in for batch normalisation) is stochastic: only dropout_ratio = 0 is supported."""
+    """models/gin.py:58-106: new_h = relu(linear_g2(relu(linear_g1(h + (sum_e A_e) h)))).  The aggregation is `bmp_gin_aggregate`
+    (one CTA per molecule), the two GraphLinears are Linear launches.  Dropout (the reference's stand-in for batch normalisation) is
+    stochastic: only dropout_ratio = 0 is supported.  `aggregate(ids, adj, embed_W, edge=False)` is the fused embedding gather of the
+    relational-GCN kernel (identity self weights, zero edge weights), used by GIN for h_0."""
 
     def __init__(self, hidden_dim=16, dropout_ratio=0.5, num_edge_type=4):
         Link.__init__(self)
@@ -551,7 +552,9 @@ class GINUpdate(Link):
         if self.dropout_ratio > 0.0:
             raise NotImplementedError("gcnbmp: GINUpdate with dropout_ratio > 0 is stochastic; construct it with dropout_ratio=0.0")
         h, adj = _as_device(h, torch.float32), _adj_device(adj, K.MODE_F32)
-        return self.linear_g2(self.linear_g1(self.aggregate(h, adj), functions.relu), functions.relu)
+        if adj.dtype != torch.float32:
+            adj = adj.float()
+        return self.linear_g2(self.linear_g1(Fn.GINAggregate.apply(h, adj), functions.relu), functions.relu)
 
 
 class GIN(Link):

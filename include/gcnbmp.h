@@ -350,6 +350,11 @@ int bmp_atoms_pool_forward(const float *a, int a_ch, const float *z, float *out,
 int bmp_atoms_pool_backward(const float *a, int a_ch, const float *z, const float *d_out, float *da, float *dz,
                             int mb, int n_atoms, int ch, void *stream);
 
+/* GIN aggregation, models/gin.py:88-94: out[b,i,:] = h[b,i,:] + sum_e sum_j adj[b,e,i,j] h[b,j,:]; `transpose` != 0 uses
+ * adj[b,e,j,i] instead -- the same call is the backward with respect to h (pass d_out as h).  fp32, N <= 64.            */
+int bmp_gin_aggregate(const float *adj, const float *h, float *out, int mb, int n_edge, int n_atoms, int hidden,
+                      int transpose, void *stream);
+
 /* Optimizer hooks of train_binary.py:537-543 on the flat gradient, in the order the reference adds them:
  * GradientClipping(threshold) (g *= threshold/||g||_2 when that is < 1; off when threshold <= 0), WeightDecay(l2_rate)
  * (g += l2 * p), Lasso(l1_rate) (g += l1 * sign(p)).  norm_ws: one float of device scratch (needed when clipping).     */
