@@ -215,9 +215,9 @@ def run_gpu(args):
         achieved = nmol * fl["encoder"] / (k_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=("ggnn_tc_kernel<128>" if args.mode == "bf16" else "ggnn_fwd_kernel<2>") + " (+readout launch)",
                     achieved=round(achieved, 3), peak=pk["bf16_sustained"], unit="TFLOP/s",
-                    frac=round(achieved / pk["bf16_sustained"], 5), traffic=231.1e6 if args.mode == "bf16" else 229.0e6,
+                    frac=round(achieved / pk["bf16_sustained"], 5), traffic=(231.1e6 if args.mode == "bf16" else 229.0e6) * nmol / 2048.0,
                     peak_source=pk["source"] + " bf16 sustained (kernel timed inside a long step)",
-                    note="algorithmic FLOPs = 188.8 MFLOP x %d molecules per launch; traffic = ncu dram bytes r+w per 2048-molecule launch" % nmol)
+                    note="algorithmic FLOPs = 188.8 MFLOP x %d molecules per launch; traffic = ncu dram bytes r+w per 2048-molecule launch, scaled to this launch" % nmol)
     # ---- the parity-exact fp32 mode on the same workload (1 warm-up + 1 step), for the record ----
     fp32_exact = None
     if args.mode == "bf16" and not args.no_fp32:
@@ -353,7 +353,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=GLOBAL_BATCH, help="global batch (pairs per step)")
-    ap.add_argument("--chunk", type=int, default=2048, help="micro-batch (pairs) per forward/backward")
+    ap.add_argument("--chunk", type=int, default=4144,
+                    help="micro-batch (pairs) per forward/backward; 4144 molecules = 2072 two-molecule tiles = 14 full waves of 148 CTAs")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0: min(--steps, 3))")
     ap.add_argument("--no-e2e-u8", dest="e2e_u8", action="store_false", help="skip the informational uint8-adjacency e2e measurement")
     ap.add_argument("--no-cpu", action="store_true")
