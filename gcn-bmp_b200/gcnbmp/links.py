@@ -185,6 +185,20 @@ class Link(object):
     def flatten_parameters(self):
         """Re-home every parameter (and its gradient) as a view of ONE flat fp32 buffer each,
         so data-parallel training needs a single allreduce and a single Adam launch."""
+        if "_flat" in self.__dict__:
+            # idempotent: a second trainer / evaluator built on the same model must share the buffers the first one
+            # (its optimiser, its allreduce) already owns -- re-homing the parameters would silently disconnect it
+            flat, gflat, index = self.__dict__["_flat"]
+            named = dict(self.namedparams())
+            ok = set(named) == set(index)
+            for k, (o, m, shp) in index.items():
+                p = named.get(k)
+                ok = ok and p is not None and p.data_ptr() == flat.data_ptr() + 4 * o and tuple(p.shape) == shp \
+                    and p.grad is not None and p.grad.data_ptr() == gflat.data_ptr() + 4 * o
+            if not ok:
+                raise RuntimeError("flatten_parameters: the model was flattened before and its parameters no longer view that "
+                                   "flat buffer (a parameter was replaced or added afterwards)")
+            return flat, gflat
         lazy = [k for k, p in self.namedparams(include_uninit=True) if p is None]
         if lazy:      # a parameter created after this call would live outside the flat buffers: no allreduce, no update
             raise ValueError("flatten_parameters: lazily-shaped parameters are not initialised yet (%s); run one forward or "
