@@ -27,6 +27,11 @@ void count_launch(int n = 1);
 int check_launch(const char *what);
 // true when every non-null pointer is 16-byte aligned (cp.async / float4 paths)
 bool aligned16(std::initializer_list<const void *> ps);
+// two steps may share one packed weight image only when EVERY parameter pointer that goes into it is the same
+inline bool same_gru(const bmp_gru_t &x, const bmp_gru_t &y) {
+    return x.W_r == y.W_r && x.b_Wr == y.b_Wr && x.U_r == y.U_r && x.b_Ur == y.b_Ur && x.W_z == y.W_z && x.b_Wz == y.b_Wz &&
+           x.U_z == y.U_z && x.b_Uz == y.b_Uz && x.W == y.W && x.b_W == y.b_W && x.U == y.U && x.b_U == y.b_U;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

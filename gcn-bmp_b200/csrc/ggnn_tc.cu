@@ -598,7 +598,7 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
         if (((uintptr_t)a->msg_b[t]) & 15) { set_error("BMP_MODE_BF16: msg_b must be 16-byte aligned"); return BMP_EINVAL; }
         int found = -1;
         for (int u = 0; u < t; ++u)
-            if (a->msg_W[u] == a->msg_W[t] && a->gru[u].W == a->gru[t].W && a->gru[u].U == a->gru[t].U &&
+            if (a->msg_W[u] == a->msg_W[t] && same_gru(a->gru[u], a->gru[t]) &&
                 (a->stateful[u] != 0) == (a->stateful[t] != 0)) { found = u; break; }
         k.stateful[t] = a->stateful[t] != 0;
         k.msg_b[t] = a->msg_b[t];

@@ -609,7 +609,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     for (int t = 0; t < T; ++t) {
         int found = -1;
         for (int u = 0; u < t; ++u)
-            if (a->msg_W[u] == a->msg_W[t] && a->gru[u].W == a->gru[t].W && a->gru[u].U == a->gru[t].U &&
+            if (a->msg_W[u] == a->msg_W[t] && same_gru(a->gru[u], a->gru[t]) &&
                 (a->stateful[u] != 0) == (a->stateful[t] != 0)) { found = u; break; }
         k.stateful[t] = a->stateful[t] != 0;
         if (found >= 0) { k.img[t] = k.img[found]; continue; }

@@ -23,18 +23,17 @@ class BatchEvaluator(object):
         t = (labels if isinstance(labels, torch.Tensor) else torch.as_tensor(labels)).to(dev)
         t = t.reshape(logits.shape)
         y = torch.sigmoid(logits.double())
+        mask = None
         if self.ignore is not None and bool((t == self.ignore).any()):
-            # the reference's evaluators drop ignored entries per column (roc_auc_evaluator.py: ignore_labels); rows with an ignored
-            # entry are dropped here only when the array is a single column, which is the only case the reference scripts produce
-            if t.shape[1] != 1:
-                raise ValueError("ignore_labels with more than one label column is not supported")
-            keep = (t[:, 0] != self.ignore)
-            y, t = y[keep], t[keep]
+            # the evaluators drop ignored entries before calling scikit-learn; with several label columns (the 86-class KAIST
+            # set) every column keeps its own non-ignored rows (gcnbmp.metrics `mask`)
+            mask = t != self.ignore
+            t = torch.where(mask, t, torch.zeros_like(t))
         fns = dict(accuracy=M.accuracy, roc_auc=M.roc_auc, prc_auc=M.prc_auc, f1=M.f1, precision=M.precision, recall=M.recall)
         out = {}
         for k in self.which:
             try:
-                out["%s/%s" % (self.name, k)] = float(fns[k](y, t))
+                out["%s/%s" % (self.name, k)] = float(fns[k](y, t, mask))
             except ValueError:
                 if self.raise_value_error:
                     raise

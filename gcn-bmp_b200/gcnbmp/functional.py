@@ -88,7 +88,9 @@ def _tc_images(kind, nbytes, dev, params):
     if ent is not None and ent[1] == _PARAM_EPOCH:
         return ent[0], 1
     ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
-    _IMAGES[key] = (ws, _PARAM_EPOCH)
+    # the entry keeps the keyed tensors alive: while it exists the allocator cannot hand one of those addresses to a
+    # different (derived, temporary) tensor, so an address match always means "the same values since params_changed()"
+    _IMAGES[key] = (ws, _PARAM_EPOCH, tuple(params))
     return ws, 0
 
 

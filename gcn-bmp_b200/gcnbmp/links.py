@@ -98,6 +98,13 @@ class Link(object):
         self._children[name] = link
         return link
 
+    def frozen_params(self):
+        """Paths of parameters that never receive a gradient (chainer: `grad is None`, so optimizer hooks and update rules
+        skip them -- e.g. BilinearDiag.W, models/mlp.py:186-192)."""
+        for path, link in self.namedlinks():
+            for n in link.__dict__.get("_nograd", ()):
+                yield path + "/" + n
+
     def __getattr__(self, name):
         d = self.__dict__
         if name in d.get("_params", ()):
@@ -203,9 +210,12 @@ class Link(object):
         if lazy:      # a parameter created after this call would live outside the flat buffers: no allreduce, no update
             raise ValueError("flatten_parameters: lazily-shaped parameters are not initialised yet (%s); run one forward or "
                              "call .ensure(in_size) on those layers first" % ", ".join(k.lstrip("/") for k in lazy))
+        frozen = set(self.frozen_params())
         named = [(k, p) for k, p in self.namedparams()]
+        named = [kp for kp in named if kp[0] not in frozen] + [kp for kp in named if kp[0] in frozen]   # frozen spans last
         pad = lambda m: (m + 63) // 64 * 64          # every view stays 256-byte aligned (cp.async needs 16)
         n = sum(pad(p.numel()) for _, p in named)
+        self.__dict__["_n_trainable"] = sum(pad(p.numel()) for k, p in named if k not in frozen)
         flat = torch.zeros(n, device=_dev(), dtype=torch.float32)
         gflat = torch.zeros(n, device=_dev(), dtype=torch.float32)
         off = 0
@@ -991,6 +1001,7 @@ class BilinearDiag(Link):
         if left_size != right_size:
             raise AssertionError("BilinearDiag: left_size == right_size required (models/mlp.py:160)")
         self.add_param("W", (out_size, left_size))
+        self.__dict__["_nograd"] = ("W",)      # no gradient in the reference => skipped by hooks / weight decay / Adam
 
     def __call__(self, e1, e2):
         prod = Fn.PairFeatures.apply(_as_device(e1, torch.float32), _as_device(e2, torch.float32), K.PAIR_PROD)

@@ -101,13 +101,26 @@ class PairTrainer(object):
         self._graphs = {}
         self._graph_stream = torch.cuda.Stream() if graph else None
         self.flat, self.gflat = model.flatten_parameters()
-        self.opt = Adam(self.flat, self.gflat, **adam) if optimizer else None
-        self.hooks = GradientHooks(self.flat, self.gflat, max_norm, l2_rate, l1_rate)     # train_binary.py:537-543
+        # parameters the reference never gives a gradient (BilinearDiag.W) sit at the end of the flat buffers, outside the
+        # spans the hooks, the weight decay and Adam see -- chainer skips parameters whose grad is None
+        nt = model.__dict__.get("_n_trainable", self.flat.numel())
+        self.opt = Adam(self.flat[:nt], self.gflat[:nt], **adam) if optimizer else None
+        self.hooks = GradientHooks(self.flat[:nt], self.gflat[:nt], max_norm, l2_rate, l1_rate)     # train_binary.py:537-543
         self.world_size = world_size
         self.pg = process_group
         self.copy_stream = torch.cuda.Stream()
         self.loss_buf = torch.zeros((), device=self.flat.device)
         self.h2d_bytes = 0
+
+    def _global_count(self, labels):
+        """Normaliser of F.sigmoid_cross_entropy(normalize=True) over the GLOBAL batch: the number of non-ignored (!= -1)
+        label entries, summed over the ranks (one small allreduce) -- shards may be uneven and may hold different numbers of
+        ignored entries, and every rank must divide by the same count for the summed gradient to equal the 1-GPU one."""
+        t = labels if isinstance(labels, torch.Tensor) else torch.as_tensor(np.asarray(labels))
+        cnt = (t != -1).sum().to(device=self.flat.device, dtype=torch.float64).reshape(1)
+        if self.world_size > 1:
+            parallel.allreduce_sum_(cnt, self.pg)
+        return max(float(cnt.item()), 1.0)
 
     def _chunks(self, n):
         return [(s, min(n, s + self.chunk)) for s in range(0, n, self.chunk)]
@@ -133,7 +146,7 @@ class PairTrainer(object):
         n = arrs[0].shape[0]
         on_host = not (isinstance(adjs_1, torch.Tensor) and adjs_1.is_cuda)
         if global_count is None:
-            global_count = float(n * labels.shape[1] * self.world_size)
+            global_count = self._global_count(labels)
         self.gflat.zero_()
         self.loss_buf.zero_()
         # parameters are constant within a step: pack the tcgen05 weight images once, not once per micro-batch
@@ -239,7 +252,7 @@ class PairTrainer(object):
                              for t in (idx_1, idx_2, labels))
         n = i1.shape[0]
         if global_count is None:
-            global_count = float(n * y.shape[1] * self.world_size)
+            global_count = self._global_count(y)
         self.gflat.zero_()
         self.loss_buf.zero_()
         Fn.params_changed()

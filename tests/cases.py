@@ -23,6 +23,11 @@ def pair_case(name, seed=0, dtype=np.float64):
         # config C: GGNN H128 T6 tied + Nie co-attention + HolE -> 86 classes (reduced H for CPU speed)
         "C": dict(enc="mono", H=32, T=6, tied=True, sum_readout=False, O=32, attn="nie", head=8,
                   hole_hidden=(), K=86, mb=4, N1=64, N2=64),
+        # config C / E at the FULL bench shape (bench.py): GGNN H128 T6 tied + Nie co-attention head 8, O128 + HolE -> 86;
+        # exercises exactly the kernel instantiations the bench times (ggnn_tc_kernel<128>, ggnn_tc_bwd_kernel<128>,
+        # wgrad2_kernel, coattn_tc_kernel<128>, and ggnn_fwd/bwd_kernel<2> in fp32 mode)
+        "CB": dict(enc="mono", H=128, T=6, tied=True, sum_readout=False, O=128, attn="nie", head=8,
+                   hole_hidden=(), K=86, mb=4, N1=64, N2=64),
         # headline script: untied message layers, shared GRU, VQA attention, hidden head layers
         "U": dict(enc="mono", H=16, T=3, tied=False, sum_readout=False, O=16, attn="vqa", head=8,
                   hole_hidden=(32, 16), K=1, mb=5, N1=23, N2=31),

@@ -183,7 +183,7 @@ def main():
     PairAttn = load_class("train_binary.py", "GraphConvPredictorForPair")
     PairPlain = load_class("train_ddi_modify_eval2.py", "GraphConvPredictorForPair")
     import cases
-    for cname in ("C", "U", "A", "MU", "B"):
+    for cname in ("C", "U", "A", "MU", "B", "CB"):
         case = cases.pair_case(cname, seed=7)
         sp, params = case["spec"], case["params"]
         if sp["enc"] == "mono":

@@ -249,3 +249,98 @@ def test_batch_evaluator_scores_a_split_once_and_matches_sklearn():
     obs2 = ev.evaluate_indexed(tab_a, tab_A, np.arange(n), n + np.arange(n), y)
     for k in ref:
         assert abs(obs2[k] - obs[k]) <= 1e-5, k
+
+
+@pytest.mark.gpu
+def test_trainer_and_evaluator_share_one_flat_buffer():
+    """flatten_parameters is idempotent: an evaluator built on a model that a trainer already owns must not re-home the
+    parameters (the optimiser would keep updating buffers the model no longer reads)."""
+    import cases
+    import product
+    from gcnbmp import train
+    from gcnbmp.evaluate import BatchEvaluator
+    case = cases.pair_case("A", seed=3)
+    a1, A1, a2, A2 = case["inputs"]
+    A1, A2, y = A1.astype(np.float32), A2.astype(np.float32), case["labels"]
+    model = product.product_model(case["spec"], case["params"])
+    tr = train.PairTrainer(model, chunk=64, alpha=1e-2)
+    tr.step(a1, A1, a2, A2, y)
+    p1 = tr.flat.detach().clone()
+    ev = BatchEvaluator(model, name="val", batch=64, which=("accuracy",))
+    assert ev.trainer.flat.data_ptr() == tr.flat.data_ptr() and ev.trainer.gflat.data_ptr() == tr.gflat.data_ptr()
+    before = ev.evaluate(a1, A1, a2, A2, y)
+    tr.step(a1, A1, a2, A2, y)
+    assert not torch.equal(tr.flat, p1)                      # the second step still moved the parameters ...
+    named = dict(model.namedparams())
+    k = next(iter(named))
+    assert named[k].data_ptr() >= tr.flat.data_ptr() and named[k].data_ptr() < tr.flat.data_ptr() + 4 * tr.flat.numel()
+    with torch.no_grad():                                     # ... and the model computes with the updated ones
+        l_model = model(a1, A1, a2, A2)
+        l_pred = tr.predict(a1, A1, a2, A2)
+    assert torch.equal(l_model, l_pred)
+    assert isinstance(before["val/accuracy"], float)
+
+
+@pytest.mark.gpu
+def test_hooks_and_adam_skip_parameters_without_gradient():
+    """BilinearDiag.W (DistMult) gets no gradient in the reference, so chainer's hooks / weight decay / Adam never touch it."""
+    import gcnbmp
+    from gcnbmp import synthetic, train
+    rng = np.random.default_rng(1)
+    a1, A1 = synthetic.random_molecules(rng, 6, 20)
+    a2, A2 = synthetic.random_molecules(rng, 6, 20)
+    y = (rng.random((6, 1)) < 0.5).astype(np.int32)
+    model = gcnbmp.GraphConvPredictorForPair(gcnbmp.GGNNMono(16, 16, 2), None, gcnbmp.DistMult(16, 16, 1, 4, (6,)))
+    with torch.no_grad():
+        model(a1, A1, a2, A2)                                 # materialise the lazily-shaped layers
+    tr = train.PairTrainer(model, chunk=64, alpha=1e-2, l2_rate=0.1, l1_rate=0.01, weight_decay_rate=0.1)
+    w0 = model.mlp.dm_layer.W.detach().clone()
+    e0 = model.graph_conv.embed.W.detach().clone()
+    tr.step(a1, A1, a2, A2, y)
+    assert torch.equal(model.mlp.dm_layer.W.detach(), w0)     # frozen, not decayed
+    assert not torch.equal(model.graph_conv.embed.W.detach(), e0)
+
+
+@pytest.mark.gpu
+def test_default_global_count_ignores_missing_labels():
+    """PairTrainer.step without `global_count` divides by the number of non-ignored labels, as F.sigmoid_cross_entropy does."""
+    import cases
+    import gcnbmp
+    import product
+    from gcnbmp import train
+    case = cases.pair_case("C", seed=2)                       # K = 86 with one ignored entry
+    a1, A1, a2, A2 = case["inputs"]
+    A1, A2, y = A1.astype(np.float32), A2.astype(np.float32), case["labels"]
+    assert (y == -1).sum() == 1
+    model = product.product_model(case["spec"], case["params"])
+    tr = train.PairTrainer(model, chunk=64, optimizer=False)
+    loss = float(tr.step(a1, A1, a2, A2, y).item())
+    with torch.no_grad():
+        ref = float(gcnbmp.sigmoid_cross_entropy(model(a1, A1, a2, A2), y).item())
+    assert abs(loss - ref) <= 1e-6 * max(abs(ref), 1.0)
+
+
+@pytest.mark.gpu
+def test_batch_evaluator_ignore_labels_with_several_columns():
+    sk = pytest.importorskip("sklearn.metrics")
+    import cases
+    import product
+    from gcnbmp.evaluate import BatchEvaluator
+    case = cases.pair_case("C", seed=9)
+    model = product.product_model(case["spec"], case["params"])
+    a1, A1, a2, A2 = case["inputs"]
+    rng = np.random.default_rng(3)
+    reps = 10
+    a1, A1, a2, A2 = (np.concatenate([x] * reps) for x in (a1, A1.astype(np.float32), a2, A2.astype(np.float32)))
+    n, k = a1.shape[0], case["spec"]["K"]
+    y = (rng.random((n, k)) < 0.4).astype(np.int32)
+    y[0], y[1] = 1, 0
+    y[rng.random((n, k)) < 0.15] = -1
+    y[:2] = np.where(y[:2] < 0, 0, y[:2])
+    y[0], y[1] = 1, 0
+    obs = BatchEvaluator(model, name="val", batch=16, which=("roc_auc", "accuracy")).evaluate(a1, A1, a2, A2, y)
+    with torch.no_grad():
+        p = torch.sigmoid(model(a1, A1, a2, A2).double()).cpu().numpy()
+    roc = np.mean([sk.roc_auc_score(y[y[:, c] >= 0, c], p[y[:, c] >= 0, c]) for c in range(k)])
+    acc = np.mean([sk.accuracy_score(y[y[:, c] >= 0, c], np.round(p[y[:, c] >= 0, c])) for c in range(k)])
+    assert abs(obs["val/roc_auc"] - roc) <= 1e-6 and abs(obs["val/accuracy"] - acc) <= 1e-6

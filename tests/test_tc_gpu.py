@@ -90,10 +90,10 @@ def test_tc_mode_pair_training_step_close_to_oracle():
     logits = model(a1, A1.astype(np.float32), a2, A2.astype(np.float32))
     loss = __import__("gcnbmp").sigmoid_cross_entropy(logits, big["labels"])
     loss.backward()
-    assert rel_err(logits.detach().cpu().numpy(), o["logits"]) <= MAX_TOL
+    assert rel_err(logits.detach().cpu().numpy(), o["logits"]) <= 1e-2          # measured 3.4e-3
     g = model.grad_dict()
     worst = max(_rms_rel(g[k], o["grads"][k]) for k in o["grads"] if np.abs(o["grads"][k]).max() > 1e-6)
-    assert worst <= 5e-2, worst
+    assert worst <= 2e-2, worst                                                  # measured 7.1e-3
 
 
 def test_tc_mode_rejects_unsupported_shapes():
@@ -423,3 +423,50 @@ def test_metrics_run_on_device_and_match_the_host_result():
     dev = gcnbmp.metrics.evaluate(torch.tensor(y, device="cuda"), torch.tensor(t, device="cuda"))
     for k in host:
         assert dev[k].is_cuda and abs(float(dev[k]) - float(host[k])) <= 1e-9, k
+
+
+def _bench_shape_errors(use_trainer):
+    """BF16-mode pair step at the FULL bench shape (case CB = H128 T6 N64 tied, Nie head 8, O128, K86) against the
+    reference-generated fixture: the kernel instantiations bench.py times -- ggnn_tc_kernel<128,1,1>, ggnn_tc_bwd_kernel<128,1>,
+    wgrad2_kernel, readout_tc_kernel<128,128>, coattn_tc_kernel<128> forward/backward."""
+    import gcnbmp
+    from gcnbmp import train
+    z = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ref_pair_CB.npz"))
+    ref_logits = z["logits"]
+    ref_grads = {k[7:]: z[k] for k in z.files if k.startswith("gparam:")}
+    case = cases.pair_case("CB", seed=7)
+    model = product.product_model(case["spec"], case["params"])
+    model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
+    a1, A1, a2, A2 = case["inputs"]
+    A1, A2 = A1.astype(np.float32), A2.astype(np.float32)
+    gcnbmp.reset_launch_count()
+    if use_trainer:      # the bench's own path: flat buffers, gradient sink, cached weight images, two micro-batches
+        tr = train.PairTrainer(model, chunk=3, optimizer=False)
+        tr.step(a1, A1, a2, A2, case["labels"])
+        with torch.no_grad():
+            logits = tr.predict(a1, A1, a2, A2)
+    else:
+        model.cleargrads()
+        logits = model(a1, A1, a2, A2)
+        gcnbmp.sigmoid_cross_entropy(logits, case["labels"]).backward()
+    assert gcnbmp.launch_count() > 0
+    g = model.grad_dict()
+    lerr = rel_err(logits.detach().cpu().numpy(), ref_logits)
+    gerr = {k: (_rms_rel(g[k], v), rel_err(g[k], v)) for k, v in ref_grads.items() if np.abs(v).max() > 1e-9}
+    return lerr, gerr
+
+
+# measured on the B200 (round 2): logits 2.1e-3 max-rel; worst parameter gradient 1.0e-2 rms-rel (attn/energy_layer/W) and
+# 8.5e-3 max-rel -- the asserted bounds are ~2x those
+BENCH_LOGIT_TOL, BENCH_GRAD_RMS_TOL, BENCH_GRAD_MAX_TOL = 5e-3, 2e-2, 2e-2
+
+
+@pytest.mark.parametrize("use_trainer", [False, True])
+def test_tc_mode_bench_shape_logits_and_every_gradient(use_trainer):
+    lerr, gerr = _bench_shape_errors(use_trainer)
+    worst_rms = max(v[0] for v in gerr.values())
+    worst_max = max(v[1] for v in gerr.values())
+    report = "logits %.2e; grads rms %.2e max %.2e; %s" % (lerr, worst_rms, worst_max, {k: "%.1e/%.1e" % v for k, v in gerr.items()})
+    print(report)
+    assert len(gerr) >= 25, sorted(gerr)
+    assert lerr <= BENCH_LOGIT_TOL and worst_rms <= BENCH_GRAD_RMS_TOL and worst_max <= BENCH_GRAD_MAX_TOL, report
