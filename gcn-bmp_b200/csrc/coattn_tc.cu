@@ -951,6 +951,7 @@ static int launch_ctc_hp(const ctc::Args &k, int head, cudaStream_t st) {
     const int grid = k.mb < sms ? k.mb : sms;
     const size_t smem = ctc::smem_bytes<H, BWD>(head);
     cudaFuncSetAttribute(ctc::coattn_tc_kernel<H, BWD, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ProfScope prof(BWD ? BMP_PROF_COATTN_BWD : BMP_PROF_COATTN_FWD, st);
     ctc::coattn_tc_kernel<H, BWD, HP><<<grid, ctc::NT, smem, st>>>(k);
     count_launch();
     return check_launch("coattn_tc_kernel");

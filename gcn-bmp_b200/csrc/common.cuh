@@ -27,6 +27,15 @@ void count_launch(int n = 1);
 int check_launch(const char *what);
 // true when every non-null pointer is 16-byte aligned (cp.async / float4 paths)
 bool aligned16(std::initializer_list<const void *> ps);
+// Optional per-kernel timing (bmp_profile_enable): CUDA events recorded on the launching stream right before and after a
+// hot kernel's launch, so a caller can time individual kernels INSIDE a real step.  No-op (one relaxed load) when off.
+struct ProfScope {
+    int kind;
+    cudaStream_t st;
+    void *slot;
+    ProfScope(int kind, cudaStream_t st);
+    ~ProfScope();
+};
 // two steps may share one packed weight image only when EVERY parameter pointer that goes into it is the same
 inline bool same_gru(const bmp_gru_t &x, const bmp_gru_t &y) {
     return x.W_r == y.W_r && x.b_Wr == y.b_Wr && x.U_r == y.U_r && x.b_Ur == y.b_Ur && x.W_z == y.W_z && x.b_Wz == y.b_Wz &&

@@ -628,6 +628,7 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
         cudaFuncSetAttribute(tc::ggnn_tc_kernel<HH, VV, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<HH, LL>::SMEM_BYTES); \
         tc::ggnn_tc_kernel<HH, VV, LL><<<grid, 32 * (HH / 8 + 2), tc::Cfg<HH, LL>::SMEM_BYTES, st>>>(k);                      \
     } while (0)
+    ProfScope prof(BMP_PROF_GGNN_FWD, st);
     if (H == 64) { if (k.use2) LAUNCH_FWD(64, true, true); else if (lean) LAUNCH_FWD(64, false, true); else LAUNCH_FWD(64, false, false); }
     else { if (k.use2) LAUNCH_FWD(128, true, true); else if (lean) LAUNCH_FWD(128, false, true); else LAUNCH_FWD(128, false, false); }
 #undef LAUNCH_FWD

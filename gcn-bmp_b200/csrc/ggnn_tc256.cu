@@ -541,6 +541,7 @@ int bmp_ggnn_forward_tc256(const bmp_ggnn_fwd_t *a, void *stream) {
     int grid = n_tiles < sms ? n_tiles : sms;
     if (const char *e = getenv("BMP_TC256_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }   // experiments only
     cudaFuncSetAttribute(tc256::ggnn_tc256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc256::SMEM_BYTES);
+    ProfScope prof(BMP_PROF_GGNN_FWD, st);
     tc256::ggnn_tc256_kernel<<<grid, 32 * (tc256::EPW + 2), tc256::SMEM_BYTES, st>>>(k);
     count_launch();
     return check_launch("ggnn_tc256_kernel");

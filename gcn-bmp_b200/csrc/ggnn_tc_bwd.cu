@@ -634,6 +634,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
         cudaFuncSetAttribute(tcb::ggnn_tc_bwd_kernel<HH, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::Cfg<HH>::SMEM_BYTES); \
         tcb::ggnn_tc_bwd_kernel<HH, VV><<<grid, 32 * (HH / 8 + 2), tcb::Cfg<HH>::SMEM_BYTES, st>>>(k);                                  \
     } while (0)
+    ProfScope prof(BMP_PROF_GGNN_BWD, st);
     if (H == 64) { if (k.use2) LAUNCH_BWD(64, true); else LAUNCH_BWD(64, false); }
     else { if (k.use2) LAUNCH_BWD(128, true); else LAUNCH_BWD(128, false); }
 #undef LAUNCH_BWD

@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace bmp {
@@ -23,6 +25,29 @@ bool aligned16(std::initializer_list<const void *> ps) {
     return true;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline legs)
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+ProfScope::ProfScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_), slot(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec *r = new ProfRec;
+    r->kind = kind;
+    cudaEventCreate(&r->e0);
+    cudaEventCreate(&r->e1);
+    cudaEventRecord(r->e0, st);
+    slot = r;
+}
+ProfScope::~ProfScope() {
+    if (!slot) return;
+    ProfRec *r = (ProfRec *)slot;
+    cudaEventRecord(r->e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(*r);
+    delete r;
+}
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -199,6 +224,23 @@ extern "C" const char *bmp_last_error(void) { return g_err; }
 extern "C" int bmp_version(void) { return 100; }
 extern "C" uint64_t bmp_launch_count(void) { return g_launches.load(); }
 extern "C" void bmp_reset_launch_count(void) { g_launches.store(0); }
+
+extern "C" void bmp_profile_enable(int on) { bmp::g_prof_on.store(on != 0); }
+extern "C" int bmp_profile_read(double *ms, long long *launches, int n_kinds) {
+    using namespace bmp;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < n_kinds; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    int rc = BMP_OK;
+    for (auto &r : g_prof) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.e1) != cudaSuccess || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) rc = BMP_ECUDA;
+        if (r.kind >= 0 && r.kind < n_kinds) { ms[r.kind] += t; launches[r.kind] += 1; }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    return rc;
+}
 
 extern "C" int bmp_device_check(void) {
     int dev = 0, major = 0, minor = 0;

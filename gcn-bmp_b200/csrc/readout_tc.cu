@@ -352,6 +352,7 @@ extern "C" size_t bmp_readout_tc_workspace_bytes(int hidden, int out_dim) {
 template <int H, int O>
 static int launch_readout_tc(const rtc::Args &k, bool bwd, int grid, cudaStream_t st) {
     constexpr int smem = rtc::Plan<H, O>::SMEM;
+    ProfScope prof(BMP_PROF_READOUT, st);
     if (bwd) {
         if constexpr (rtc::Plan<H, O>::BIG) {
             set_error("readout tcgen05 path: hidden / out_dim 256 is forward-only");

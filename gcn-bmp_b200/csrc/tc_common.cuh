@@ -136,10 +136,50 @@ __host__ __device__ constexpr uint32_t idesc2(int n, int a_mn_major, int b_mn_ma
 }
 
 // stage the adjacency of a tile (2 molecules x 4 bond types) as bf16 SW128 tiles [mol][e][i][j].  The source is the reference's
-// fp32 array (mb,E,N,N) or, with `u8`, the same array stored as bytes (exact for 0/1 bonds, a quarter of the traffic).
+// fp32 array (mb,E,N,N) or, with `u8` = 1, the same array stored as bytes (exact for 0/1 bonds, a quarter of the traffic), or,
+// with `u8` = 2, bit-packed rows (mb,E,N,ceil(N/8)): bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits(..., bitorder='little');
+// 2 KB per molecule at N = 64, 1/32 of the fp32 bytes).
 // Loads are issued in batches of 8 vectors per thread so the DRAM latency is paid a few times per tile, not per element.
 template <int NE>
 __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__restrict__ adj_any, int u8, int tile, int mb, int N, int tid) {
+    if (u8 == 2) {
+        const uint8_t *adj = reinterpret_cast<const uint8_t *>(adj_any);
+        const int W = (N + 7) >> 3;
+        constexpr int ROWS = 8 * 64, PER = (ROWS + NE - 1) / NE;      // items: (mol,e) x i ; one packed row each
+        uint64_t bits[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = u * NE + tid;
+            const int i = idx & 63, me = idx >> 6;
+            const int mg = tile * 2 + (me >> 2);
+            bits[u] = 0;
+            if (idx < ROWS && mg < mb && i < N) {
+                const uint8_t *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * W;
+                if (W == 8) {
+                    bits[u] = __ldg(reinterpret_cast<const unsigned long long *>(src));
+                } else {
+                    for (int x = 0; x < W; ++x) bits[u] |= (uint64_t)src[x] << (8 * x);
+                }
+                if (N < 64) bits[u] &= (1ull << N) - 1ull;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int idx = u * NE + tid;
+            if (idx >= ROWS) continue;
+            const int i = idx & 63, me = idx >> 6;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t b = (uint32_t)(bits[u] >> (8 * c)) & 0xFFu;
+                uint32_t o[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    o[x] = ((b >> (2 * x)) & 1u ? 0x3F80u : 0u) | ((b >> (2 * x + 1)) & 1u ? 0x3F800000u : 0u);
+                *reinterpret_cast<uint4 *>(s_adj + me * ADJ_TILE_BYTES + sw128(i, 8 * c)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        return;
+    }
     if (u8) {
         const uint8_t *adj = reinterpret_cast<const uint8_t *>(adj_any);
         constexpr int ITEMS = 8 * 64 * 4, PER = (ITEMS + NE - 1) / NE;     // items: (mol,e) x i x (j/16)
@@ -242,9 +282,9 @@ __device__ __forceinline__ void rescale_staged_adjacency(uint8_t *s_adj, float *
 template <int NE>
 __device__ __forceinline__ void prefetch_adjacency_l2(const void *__restrict__ adj, int u8, int tile, int mb, int N, int tid) {
     const long first = (long)tile * 2, nmol = first + 2 <= mb ? 2 : (first < mb ? 1 : 0);
-    const long esz = u8 ? 1 : 4;
-    const char *base = reinterpret_cast<const char *>(adj) + first * 4 * N * N * esz;
-    const long bytes = nmol * 4L * N * N * esz;
+    const long per_mol = u8 == 2 ? 4L * N * ((N + 7) >> 3) : 4L * N * N * (u8 ? 1 : 4);
+    const char *base = reinterpret_cast<const char *>(adj) + first * per_mol;
+    const long bytes = nmol * per_mol;
     for (long off = (long)tid * 128; off < bytes; off += (long)NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
 }
 

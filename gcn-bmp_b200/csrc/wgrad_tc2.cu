@@ -187,6 +187,7 @@ int bmp_wgrad_panels(w2::Args &k, void *stream) {
         cudaFuncSetAttribute(w2::wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::STAGES * 8 * w2::BLK + w2::BLK + 256 + 1024);
         attr = true;
     }
+    ProfScope prof(BMP_PROF_WGRAD, (cudaStream_t)stream);
     w2::wgrad2_kernel<<<(unsigned)ctas, w2::NTH, smem, (cudaStream_t)stream>>>(k);
     count_launch();
     return check_launch("wgrad2_kernel");

@@ -7,6 +7,7 @@ Importing this package loads libgcnbmp.so and fails loudly when it is missing.
 from . import _capi
 from ._capi import BmpError, launch_count, reset_launch_count, MODE_F32, MODE_BF16
 from . import functional
+from .functional import pack_adjacency, unpack_adjacency
 from . import metrics
 from . import evaluate
 from .links import (MAX_ATOMIC_NUM, functions, Link, ChainList, GraphLinear, GGNNUpdate, RelGCNUpdate,

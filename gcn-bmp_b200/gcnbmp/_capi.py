@@ -141,6 +141,8 @@ def _load():
     lib.bmp_device_check.restype = C.c_int
     lib.bmp_launch_count.restype = C.c_uint64
     lib.bmp_reset_launch_count.restype = None
+    lib.bmp_profile_enable.argtypes, lib.bmp_profile_enable.restype = [i], None
+    lib.bmp_profile_read.argtypes, lib.bmp_profile_read.restype = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), i], C.c_int
     return lib
 
 
@@ -152,7 +154,8 @@ EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_r
            "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
            "bmp_atoms_bcast_add_act_forward", "bmp_atoms_bcast_add_act_backward", "bmp_atoms_softmax_forward", "bmp_atoms_softmax_backward",
            "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate",
-           "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count"]
+           "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count",
+           "bmp_profile_enable", "bmp_profile_read"]
 
 
 class BmpError(RuntimeError):
@@ -175,3 +178,19 @@ def launch_count():
 
 def reset_launch_count():
     lib.bmp_reset_launch_count()
+
+
+PROF_KINDS = ("ggnn_fwd", "ggnn_bwd", "wgrad", "coattn_fwd", "coattn_bwd", "readout")
+
+
+def profile_enable(on=True):
+    """CUDA events around every launch of the hot tcgen05 kernels, on the launching stream (include/gcnbmp.h)."""
+    lib.bmp_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """-> {kind: (total ms, launches)} since the last read (synchronises on the recorded events)."""
+    n = len(PROF_KINDS)
+    ms, cnt = (C.c_double * n)(), (C.c_longlong * n)()
+    check(lib.bmp_profile_read(ms, cnt, n))
+    return {k: (float(ms[j]), int(cnt[j])) for j, k in enumerate(PROF_KINDS)}

@@ -17,12 +17,49 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def adj_format(t):
+    """Storage code of an adjacency tensor (include/gcnbmp.h `adj_u8`): 0 = fp32 (mb,E,N,N), 1 = bytes (mb,E,N,N),
+    2 = bit-packed rows (mb,E,N,ceil(N/8)) as produced by `pack_adjacency`."""
+    if t.dtype in (torch.uint8, torch.bool):
+        n, w = t.shape[-2], t.shape[-1]
+        return 2 if (t.dtype == torch.uint8 and w == (n + 7) // 8 and w != n) else 1
+    return 0
+
+
+def pack_adjacency(adj):
+    """0/1 adjacency (mb,E,N,N), any dtype, NumPy or Torch -> bit-packed uint8 (mb,E,N,ceil(N/8)): bit j&7 of byte j>>3 is
+    adj[..., i, j] (numpy.packbits(bitorder='little')).  2 KB per 64-atom molecule instead of 64 KB of fp32 -- the form a
+    data set is best kept in on the host; the tcgen05 kernels stage it directly (exact for 0/1 bonds)."""
+    if isinstance(adj, torch.Tensor):
+        n = adj.shape[-1]
+        w = (n + 7) // 8
+        b = (adj != 0).to(torch.uint8)
+        if w * 8 != n:
+            b = torch.nn.functional.pad(b, (0, w * 8 - n))
+        b = b.reshape(b.shape[:-1] + (w, 8))
+        weights = (1 << torch.arange(8, device=b.device, dtype=torch.int32))
+        return (b.to(torch.int32) * weights).sum(dim=-1).to(torch.uint8)
+    import numpy as np
+    return np.packbits(np.asarray(adj) != 0, axis=-1, bitorder="little")
+
+
+def unpack_adjacency(bits, n_atoms=None):
+    """Inverse of `pack_adjacency` on the tensor's device -> fp32 (mb,E,N,N)."""
+    n = bits.shape[-2] if n_atoms is None else n_atoms
+    sh = torch.arange(8, device=bits.device, dtype=torch.int32)
+    x = ((bits.to(torch.int32).unsqueeze(-1) >> sh) & 1).reshape(bits.shape[:-1] + (bits.shape[-1] * 8,))
+    return x[..., :n].to(torch.float32).contiguous()
+
+
 def _adj(t, mode):
-    """Adjacency as the kernels take it: fp32, or -- BF16 mode only -- the caller's uint8 / bool array as is (exact for 0/1
-    bonds; a quarter of the PCIe and HBM traffic).  Returns (tensor, adj_u8 flag)."""
-    if mode == K.MODE_BF16 and t.dtype in (torch.uint8, torch.bool):
+    """Adjacency as the kernels take it: fp32, or -- BF16 mode only -- the caller's uint8 / bool / bit-packed array as is
+    (exact for 0/1 bonds; 1/4 resp. 1/32 of the PCIe and HBM traffic).  Returns (tensor, storage code)."""
+    fmt = adj_format(t)
+    if fmt == 2 and mode != K.MODE_BF16:
+        return unpack_adjacency(t), 0
+    if mode == K.MODE_BF16 and fmt:
         t = t.contiguous()
-        return (t.view(torch.uint8) if t.dtype == torch.bool else t), 1
+        return (t.view(torch.uint8) if t.dtype == torch.bool else t), fmt
     return _f32(t), 0
 
 
@@ -210,7 +247,7 @@ class GGNNEncode(torch.autograd.Function):
         Ps = torch.empty((T, rows, E * H), device=adj.device, dtype=torch.float32) if stash2 is None else None
         a = K.GgnnBwd()
         a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
-        a.adj, a.state_in, a.adj_u8 = _p(adj), _p(state_in), int(adj.dtype == torch.uint8)
+        a.adj, a.state_in, a.adj_u8 = _p(adj), _p(state_in), adj_format(adj)
         base = 1 + 2 * n_msg
         for t, (mi, gi, st) in enumerate(plan):
             a.msg_W[t] = _p(params[1 + 2 * mi])
@@ -311,7 +348,7 @@ class RelGCNEncode(torch.autograd.Function):
         for l, c in enumerate(ch):
             a.ch[l] = c
         a.adj, a.Hs, a.d_h_out, a.Ds, a.Ps, a.d_h0 = _p(adj), _p(Hs), _p(d_out), _p(Ds), _p(Ps), _p(d_h0)
-        a.adj_u8 = int(adj.dtype == torch.uint8)
+        a.adj_u8 = adj_format(adj)
         for l in range(L):
             Ws, bs, We, be = params[1 + 4 * l: 5 + 4 * l]
             a.self_W[l], a.edge_W[l] = _p(Ws), _p(We)

@@ -65,11 +65,15 @@ def _as_device(x, dtype=None):
 
 
 def _adj_device(adj, mode):
-    """Adjacency to the device: fp32 as in the reference; a uint8 / bool adjacency is kept as bytes in BF16 mode (the tcgen05
-    kernels stage it directly -- exact for 0/1 bonds, a quarter of the bytes) and widened to fp32 otherwise."""
+    """Adjacency to the device: fp32 as in the reference; a uint8 / bool / bit-packed (functional.pack_adjacency) adjacency is
+    kept as is in BF16 mode (the tcgen05 kernels stage it directly -- exact for 0/1 bonds, 1/4 resp. 1/32 of the bytes) and
+    widened to fp32 otherwise."""
     dt = adj.dtype if isinstance(adj, torch.Tensor) else torch.from_numpy(np.empty(0, np.asarray(adj).dtype)).dtype
-    if mode == K.MODE_BF16 and dt in (torch.uint8, torch.bool):
-        return _as_device(adj)
+    if dt in (torch.uint8, torch.bool):
+        t = _as_device(adj)
+        if mode == K.MODE_BF16:
+            return t
+        return Fn.unpack_adjacency(t) if Fn.adj_format(t) == 2 else t.to(torch.float32)
     return _as_device(adj, torch.float32)
 
 

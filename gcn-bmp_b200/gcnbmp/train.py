@@ -111,6 +111,7 @@ class PairTrainer(object):
         self.copy_stream = torch.cuda.Stream()
         self.loss_buf = torch.zeros((), device=self.flat.device)
         self.h2d_bytes = 0
+        self._prefetched = None      # (key, (device tensors, event)): chunk 0 of the NEXT step, uploaded during this one
 
     def _global_count(self, labels):
         """Normaliser of F.sigmoid_cross_entropy(normalize=True) over the GLOBAL batch: the number of non-ignored (!= -1)
@@ -139,10 +140,14 @@ class PairTrainer(object):
             ev.record(self.copy_stream)
         return out, ev
 
-    def step(self, atoms_1, adjs_1, atoms_2, adjs_2, labels, global_count=None):
+    def step(self, atoms_1, adjs_1, atoms_2, adjs_2, labels, global_count=None, prefetch=None):
         """Returns the (device) scalar loss of this rank's shard, already divided by the
-        global element count so that the summed gradient equals the single-GPU gradient."""
+        global element count so that the summed gradient equals the single-GPU gradient.
+        `prefetch`: the host arrays of the NEXT step (same 5-tuple order).  Their first micro-batch is uploaded on the copy
+        stream while this step's last micro-batch computes, so no step starts with an un-overlapped host->device copy (with
+        few micro-batches per rank -- 8 GPUs -- that first copy is otherwise a large part of the step)."""
         arrs = (atoms_1, adjs_1, atoms_2, adjs_2, labels)
+        self._next_arrs = prefetch
         n = arrs[0].shape[0]
         on_host = not (isinstance(adjs_1, torch.Tensor) and adjs_1.is_cuda)
         if global_count is None:
@@ -205,7 +210,14 @@ class PairTrainer(object):
     def _step_chunks(self, arrs, n, on_host, global_count):
         labels = arrs[4]
         chunks = self._chunks(n)
-        nxt = self._upload(arrs, *chunks[0]) if on_host else None
+        nxt = None
+        if on_host:
+            key = tuple(id(a) for a in arrs) + chunks[0]
+            if self._prefetched is not None and self._prefetched[0] == key:
+                nxt = self._prefetched[1]
+            else:
+                nxt = self._upload(arrs, *chunks[0])
+            self._prefetched = None
         cur_stream = torch.cuda.current_stream()
         for ci, (s, e) in enumerate(chunks):
             if on_host:
@@ -213,6 +225,10 @@ class PairTrainer(object):
                 cur_stream.wait_event(ev)
                 if ci + 1 < len(chunks):
                     nxt = self._upload(arrs, *chunks[ci + 1])
+                elif getattr(self, "_next_arrs", None) is not None:
+                    nx = tuple(self._next_arrs)
+                    c0 = self._chunks(nx[0].shape[0])[0]
+                    self._prefetched = (tuple(id(a) for a in nx) + c0, self._upload(nx, *c0))
                 for t in (a1, A1, a2, A2, y):
                     t.record_stream(cur_stream)
             else:

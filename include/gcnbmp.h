@@ -91,8 +91,9 @@ typedef struct {
                                  /* bmp_ggnn_stash2_bytes() bytes; replaces Hs..RSs  */
     int    tc_images_ready;      /* nonzero: tc_workspace already holds the images packed by an earlier call of the same
                                    kind with exactly these parameter values -- skip packing             */
-    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
-                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
+    int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
+                                   array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
+                                   (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
 } bmp_ggnn_fwd_t;
 
 int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
@@ -126,8 +127,9 @@ typedef struct {
                                     slices: [0] = gradient w.r.t. h_0, [1] = gradient w.r.t. h_T               */
     int    tc_images_ready;      /* nonzero: tc_workspace already holds the images packed by an earlier call of the same
                                    kind with exactly these parameter values -- skip packing             */
-    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
-                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
+    int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
+                                   array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
+                                   (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
 } bmp_ggnn_bwd_t;
 
 int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
@@ -159,8 +161,9 @@ typedef struct {
     size_t tc_workspace_bytes;
     void  *stash2;
     int    tc_images_ready;      /* as in bmp_ggnn_fwd_t */
-    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
-                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
+    int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
+                                   array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
+                                   (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
 } bmp_relgcn_fwd_t;
 
 int bmp_relgcn_forward(const bmp_relgcn_fwd_t *a, void *stream);
@@ -187,8 +190,9 @@ typedef struct {
     size_t tc_workspace_bytes;
     void  *stash2;
     int    tc_images_ready;
-    int    adj_u8;               /* BMP_MODE_BF16 only: `adj` points to the same (mb,E,N,N) array stored as bytes
-                                   (exact for 0/1 bonds; a quarter of the PCIe / HBM traffic)              */
+    int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
+                                   array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
+                                   (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
 } bmp_relgcn_bwd_t;
 
 int bmp_relgcn_backward(const bmp_relgcn_bwd_t *a, void *stream);
@@ -367,6 +371,15 @@ int         bmp_version(void);
 int         bmp_device_check(void);           /* BMP_OK iff current device is sm_100 */
 uint64_t    bmp_launch_count(void);           /* kernels launched by this library    */
 void        bmp_reset_launch_count(void);
+
+/* ---- per-kernel timing (measurement aid, no reference counterpart) ----------
+ * With profiling enabled every launch of the hot tcgen05 kernels is bracketed by two CUDA events recorded on the
+ * launching stream; bmp_profile_read synchronises on them, adds the elapsed milliseconds and launch counts per kind
+ * into ms[] / launches[] (n_kinds entries, BMP_PROF_* order) and forgets them.  Off by default.                    */
+enum { BMP_PROF_GGNN_FWD = 0, BMP_PROF_GGNN_BWD = 1, BMP_PROF_WGRAD = 2, BMP_PROF_COATTN_FWD = 3, BMP_PROF_COATTN_BWD = 4,
+       BMP_PROF_READOUT = 5, BMP_PROF_KINDS = 6 };
+void bmp_profile_enable(int on);
+int  bmp_profile_read(double *ms, long long *launches, int n_kinds);
 
 #ifdef __cplusplus
 }

@@ -470,3 +470,59 @@ def test_tc_mode_bench_shape_logits_and_every_gradient(use_trainer):
     print(report)
     assert len(gerr) >= 25, sorted(gerr)
     assert lerr <= BENCH_LOGIT_TOL and worst_rms <= BENCH_GRAD_RMS_TOL and worst_max <= BENCH_GRAD_MAX_TOL, report
+
+
+@pytest.mark.parametrize("H,N,mb", [(128, 64, 7), (64, 50, 5), (128, 33, 3), (256, 64, 3)])
+def test_tc_encoder_bit_packed_adjacency_is_bit_identical(H, N, mb):
+    """adj_u8 = 2 (include/gcnbmp.h): bit-packed rows staged by the tcgen05 kernels == the float32 adjacency: forward bit for
+    bit, (hidden <= 128) gradients up to atomic summation order; the fp32 kernels take the same tensor through an unpack."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(H + N)
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    bits_np = gcnbmp.pack_adjacency(adj)
+    assert bits_np.shape == (mb, 4, N, (N + 7) // 8) and bits_np.dtype == np.uint8
+    A = torch.tensor(adj).cuda()
+    Bt = torch.tensor(bits_np).cuda()
+    assert torch.equal(gcnbmp.pack_adjacency(A), Bt) and torch.equal(gcnbmp.unpack_adjacency(Bt), A)
+    net = gcnbmp.GGNNMono(H, H, 3)
+    net.mode = gcnbmp.MODE_BF16
+    if H == 256:
+        with torch.no_grad():
+            g0, g1 = net(atoms, A), net(atoms, Bt)
+        assert torch.equal(g0, g1)
+        return
+    outs = []
+    for a in (A, Bt):
+        net.cleargrads()
+        g = net(atoms, a)
+        (g.sum() + net.get_atom_array().square().sum()).backward()
+        outs.append((g.detach().clone(), {k: v.copy() for k, v in net.grad_dict().items()}))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:      # parameter gradients are summed with fp32 atomics: equal up to the order of the additions
+        np.testing.assert_allclose(outs[0][1][k], outs[1][1][k], rtol=1e-4, atol=1e-5 * max(1.0, float(np.abs(outs[0][1][k]).max())), err_msg=k)
+    net.mode = gcnbmp.MODE_F32
+    with torch.no_grad():
+        assert torch.equal(net(atoms, A), net(atoms, Bt))
+
+
+def test_trainer_prefetches_the_next_steps_first_micro_batch():
+    """PairTrainer.step(prefetch=...) uploads chunk 0 of the next step during this one: same losses and parameters as without."""
+    import gcnbmp
+    from gcnbmp import synthetic, train
+    a1, A1, a2, A2, y = synthetic.random_pairs(3, 40, 32, 5)
+    host = [torch.from_numpy(x).pin_memory() for x in (a1, A1.astype(np.uint8), a2, A2.astype(np.uint8), y)]
+    res = []
+    for pf in (False, True):
+        gcnbmp.seed(11)
+        model = gcnbmp.GraphConvPredictorForPair(gcnbmp.GGNNMono(64, 64, 2), gcnbmp.NieFineCoattention(64, 64, 8, activation=gcnbmp.functions.tanh),
+                                                 gcnbmp.HolE(5, hidden_dims=()))
+        model.mlp.l_out.ensure(64)
+        model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
+        tr = train.PairTrainer(model, chunk=16, alpha=1e-2)
+        ls = [float(tr.step(*host, prefetch=host if pf else None).item()) for _ in range(3)]
+        if pf:
+            assert tr._prefetched is not None and tr.h2d_bytes > 0
+        res.append((ls, tr.flat.detach().cpu().numpy().copy()))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-5)
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-3, atol=1e-5)
