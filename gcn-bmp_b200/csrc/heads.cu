@@ -204,6 +204,70 @@ __global__ void __launch_bounds__(256) gin_aggregate_kernel(const float *__restr
     }
 }
 
+// ---------------------------------------------------------------- NFP update (models/models/nfp.py:35-59) + EmbedID forward
+// X[b,i,(d-1)*C + c] = fv[b,i,c] when the degree of atom i equals d (1..D), zero otherwise, with fv = adj[b] . h[b] and
+// degree[b,i] = sum_{i'} adj[b,i',i] (nfp.py:152: xp.sum(adj, axis=1)).  The D degree-specific GraphLinears of the reference,
+// each applied to where(deg == d, fv, 0), are then ONE Linear over X with the weights concatenated along the input axis (and
+// all D biases added to every atom, as the reference's zero-masked inputs still pick up every bias).
+// One CTA per molecule; adj (N x N) and h (N x C) staged in shared memory.  BWD: dfv = the degree block of dX, dh = adj^T dfv.
+template <bool BWD>
+__global__ void __launch_bounds__(256) nfp_gather_kernel(const float *__restrict__ adj, const float *__restrict__ src,
+                                                         float *__restrict__ dst, int mb, int N, int C, int D) {
+    extern __shared__ float sm[];
+    float *As = sm;                       // [N][N+1]
+    float *hs = As + N * (N + 1);         // [N][C]   forward: h ; backward: dfv
+    int *deg = reinterpret_cast<int *>(hs + N * C);   // [N] degree block index (0..D-1) or -1
+    for (int b = blockIdx.x; b < mb; b += gridDim.x) {
+        for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) As[(idx / N) * (N + 1) + idx % N] = adj[(long)b * N * N + idx];
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            float s = 0.f;
+            for (int r = 0; r < N; ++r) s += As[r * (N + 1) + i];
+            int d = -1;
+            for (int k = 1; k <= D; ++k)
+                if (s - (float)k == 0.f) d = k - 1;
+            deg[i] = d;
+        }
+        __syncthreads();
+        if (!BWD) {
+            for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) hs[idx] = src[(long)b * N * C + idx];
+            __syncthreads();
+            float *X = dst + (long)b * N * D * C;
+            for (int idx = threadIdx.x; idx < N * D * C; idx += blockDim.x) {
+                const int i = idx / (D * C), r = idx - i * D * C, d = r / C, c = r - d * C;
+                float v = 0.f;
+                if (d == deg[i])
+                    for (int j = 0; j < N; ++j) v = fmaf(As[i * (N + 1) + j], hs[j * C + c], v);
+                X[idx] = v;
+            }
+        } else {
+            const float *dX = src + (long)b * N * D * C;
+            for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+                const int i = idx / C, c = idx - i * C;
+                hs[idx] = deg[i] >= 0 ? dX[(long)i * D * C + deg[i] * C + c] : 0.f;
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+                const int j = idx / C, c = idx - j * C;
+                float v = 0.f;
+                for (int i = 0; i < N; ++i) v = fmaf(As[i * (N + 1) + j], hs[i * C + c], v);
+                dst[(long)b * N * C + idx] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void embed_fwd_kernel(const int32_t *__restrict__ ids, const float *__restrict__ W, float *__restrict__ out, long rows,
+                                 int H, int n_types) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * H; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx / H;
+        int id = ids[r];
+        id = id < 0 ? 0 : (id >= n_types ? n_types - 1 : id);
+        out[idx] = W[(long)id * H + (idx - r * H)];
+    }
+}
+
 // ---------------------------------------------------------------- optimizer hooks
 __global__ void sumsq_kernel(const float *__restrict__ g, long n, float *__restrict__ out) {
     float s = 0.f;
@@ -381,6 +445,36 @@ extern "C" int bmp_gin_aggregate(const float *adj, const float *h, float *out, i
     }
     count_launch();
     return check_launch("gin_aggregate_kernel");
+}
+
+extern "C" int bmp_nfp_gather(const float *adj, const float *src, float *dst, int mb, int n_atoms, int ch, int n_degree,
+                              int backward, void *stream) {
+    if (!adj || !src || !dst) { set_error("bmp_nfp_gather: null pointer"); return BMP_EINVAL; }
+    if (mb <= 0) return BMP_OK;
+    if (n_atoms <= 0 || n_atoms > BMP_MAX_ATOMS || ch <= 0 || n_degree <= 0) { set_error("bmp_nfp_gather: bad shape N=%d C=%d D=%d", n_atoms, ch, n_degree); return BMP_ESHAPE; }
+    const size_t smem = sizeof(float) * ((size_t)n_atoms * (n_atoms + 1) + (size_t)n_atoms * ch + n_atoms);
+    if (smem > 227 * 1024) { set_error("bmp_nfp_gather: channels=%d needs %zu B of shared memory", ch, smem); return BMP_ESHAPE; }
+    const int grid = mb < 148 * 4 ? mb : 148 * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (backward) {
+        cudaFuncSetAttribute(nfp_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nfp_gather_kernel<true><<<grid, 256, smem, st>>>(adj, src, dst, mb, n_atoms, ch, n_degree);
+    } else {
+        cudaFuncSetAttribute(nfp_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nfp_gather_kernel<false><<<grid, 256, smem, st>>>(adj, src, dst, mb, n_atoms, ch, n_degree);
+    }
+    count_launch();
+    return check_launch("nfp_gather_kernel");
+}
+
+extern "C" int bmp_embed_forward(const int32_t *atoms, const float *embed_W, float *out, int rows, int hidden, int n_atom_types,
+                                 void *stream) {
+    if (!atoms || !embed_W || !out) { set_error("bmp_embed_forward: null pointer"); return BMP_EINVAL; }
+    if (rows <= 0) return BMP_OK;
+    if (hidden <= 0 || n_atom_types <= 0) { set_error("bmp_embed_forward: bad shape"); return BMP_ESHAPE; }
+    embed_fwd_kernel<<<grid_for((long)rows * hidden), 256, 0, (cudaStream_t)stream>>>(atoms, embed_W, out, rows, hidden, n_atom_types);
+    count_launch();
+    return check_launch("embed_fwd_kernel");
 }
 
 extern "C" int bmp_grad_hooks(float *grad, const float *param, int n, float clip_threshold, float l2_rate, float l1_rate,

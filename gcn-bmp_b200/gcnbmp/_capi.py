@@ -127,6 +127,8 @@ def _load():
         "bmp_atoms_pool_forward": [fp, i, fp, fp, i, i, i, vp],
         "bmp_atoms_pool_backward": [fp, i, fp, fp, fp, fp, i, i, i, vp],
         "bmp_gin_aggregate": [fp, fp, fp, i, i, i, i, i, vp],
+        "bmp_nfp_gather": [fp, fp, fp, i, i, i, i, i, vp],
+        "bmp_embed_forward": [fp, fp, fp, i, i, i, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -153,7 +155,7 @@ EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_r
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
            "bmp_atoms_bcast_add_act_forward", "bmp_atoms_bcast_add_act_backward", "bmp_atoms_softmax_forward", "bmp_atoms_softmax_backward",
-           "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate",
+           "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate", "bmp_nfp_gather", "bmp_embed_forward",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count",
            "bmp_profile_enable", "bmp_profile_read"]
 

@@ -676,6 +676,54 @@ class GINAggregate(torch.autograd.Function):
         return dh, None
 
 
+class EmbedID(torch.autograd.Function):
+    """EmbedAtomID forward as a stand-alone op (the GGNN / RelGCN encoders fuse it): W[ids]."""
+
+    @staticmethod
+    def forward(ctx, ids, W):
+        _need_cuda(ids, W)
+        ids = ids.to(torch.int32).contiguous()
+        W = _f32(W)
+        out = torch.empty(tuple(ids.shape) + (W.shape[1],), device=W.device, dtype=torch.float32)
+        K.check(K.lib.bmp_embed_forward(_p(ids), _p(W), _p(out), ids.numel(), W.shape[1], W.shape[0], _stream()))
+        ctx.save_for_backward(ids, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ids, W = ctx.saved_tensors
+        (gW,), rets = _grad_targets([W])
+        K.check(K.lib.bmp_embed_backward(_p(ids), _p(_f32(d_out)), _p(gW), ids.numel(), W.shape[1], W.shape[0], _stream()))
+        return None, rets[0]
+
+
+class NFPGather(torch.autograd.Function):
+    """NFPUpdate's message + degree selection (models/models/nfp.py:35-59): (adj h) scattered into the block of each atom's
+    degree, (mb, N, D*C); followed by ONE Linear over the concatenated degree weights."""
+
+    @staticmethod
+    def forward(ctx, h, adj, n_degree):
+        _need_cuda(h, adj)
+        h, adj = _f32(h), _f32(adj)
+        mb, N, C = h.shape
+        if tuple(adj.shape) != (mb, N, N):
+            raise ValueError("gcnbmp: NFP takes the (mb, N, N) adjacency of its preprocessor, got %s" % (tuple(adj.shape),))
+        X = torch.empty((mb, N, n_degree * C), device=h.device, dtype=torch.float32)
+        K.check(K.lib.bmp_nfp_gather(_p(adj), _p(h), _p(X), mb, N, C, n_degree, 0, _stream()))
+        ctx.save_for_backward(adj)
+        ctx.meta = (C, n_degree)
+        return X
+
+    @staticmethod
+    def backward(ctx, dX):
+        (adj,) = ctx.saved_tensors
+        C, D = ctx.meta
+        mb, N, _ = adj.shape
+        dh = torch.empty((mb, N, C), device=adj.device, dtype=torch.float32)
+        K.check(K.lib.bmp_nfp_gather(_p(adj), _p(_f32(dX)), _p(dh), mb, N, C, D, 1, _stream()))
+        return dh, None, None
+
+
 class Linear(torch.autograd.Function):
     """links.Linear + activation: act(x W^T + b)."""
 

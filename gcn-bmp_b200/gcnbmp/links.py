@@ -627,6 +627,80 @@ class GIN(Link):
         return self.atoms
 
 
+class NFPUpdate(Link):
+    """models/models/nfp.py:15-59 -- one GraphLinear per atom degree 1..max_degree+1 (the NFP preprocessor's adjacency carries
+    the self connection), applied to the neighbour sum of the atoms of that degree; sigmoid.  Every degree's bias reaches every
+    atom (the reference feeds each GraphLinear a zero-masked copy of the full array)."""
+
+    def __init__(self, in_channels, out_channels, max_degree=6):
+        Link.__init__(self)
+        self.add_link("graph_linears", ChainList([_Linear(in_channels, out_channels) for _ in range(max_degree + 1)]))
+        self.__dict__.update(max_degree=max_degree, in_channels=in_channels, out_channels=out_channels)
+
+    def __call__(self, h, adj, deg_conds=None):
+        gl = list(self.graph_linears)
+        X = Fn.NFPGather.apply(_as_device(h, torch.float32), _as_device(adj, torch.float32), len(gl))
+        W = torch.cat([l.W for l in gl], dim=1)              # parameter re-packing: (out, D*in)
+        b = torch.stack([l.b for l in gl]).sum(dim=0)
+        mb, N, _ = X.shape
+        y = Fn.Linear.apply(X.reshape(mb * N, -1), W, b, Fn.act_code(functions.sigmoid))
+        return y.reshape(mb, N, self.out_channels)
+
+
+class NFPReadout(Link):
+    """models/models/nfp.py:62-91 -- softmax over the channels of GraphLinear(h), summed over the atoms."""
+
+    def __init__(self, in_channels, out_size):
+        Link.__init__(self)
+        self.add_link("output_weight", _Linear(in_channels, out_size))
+        self.__dict__.update(in_channels=in_channels, out_size=out_size)
+
+    def __call__(self, h):
+        mb, N, _ = h.shape
+        i = self.output_weight(h)                                                # (mb, N, O)
+        i = Fn.AtomsSoftmax.apply(i.reshape(mb * N, self.out_size, 1)).reshape(mb, N, self.out_size)   # softmax along the channel axis
+        ones = torch.ones((mb, N, 1), device=i.device, dtype=torch.float32)
+        return Fn.AtomsPool.apply(ones, i)                                       # sum along the atom axis
+
+
+class NFP(Link):
+    """models/models/nfp.py:94-181 -- Neural Fingerprint encoder (the default --method of train_binary.py:319): embed -> n_layers x
+    (NFPUpdate, NFPReadout), fingerprints summed over the layers; `adj` is the (mb, N, N) adjacency with self connections of the
+    NFP preprocessor; `get_atom_array()` returns the last layer's atom states."""
+
+    def __init__(self, out_dim, hidden_dim=16, n_layers=4, max_degree=6, n_atom_types=MAX_ATOMIC_NUM, concat_hidden=False):
+        Link.__init__(self)
+        self.add_link("embed", _Embed(n_atom_types, hidden_dim))
+        self.add_link("layers", ChainList([NFPUpdate(hidden_dim, hidden_dim, max_degree=max_degree) for _ in range(n_layers)]))
+        self.add_link("read_out_layers", ChainList([NFPReadout(hidden_dim, out_dim) for _ in range(n_layers)]))
+        self.__dict__.update(out_dim=out_dim, hidden_dim=hidden_dim, max_degree=max_degree, num_degree_type=max_degree + 1,
+                             n_layers=n_layers, concat_hidden=concat_hidden, atoms=None)
+
+    def __call__(self, atom_array, adj):
+        adj = _as_device(adj, torch.float32)
+        if _is_ids(atom_array):
+            h = Fn.EmbedID.apply(_as_device(atom_array, torch.int32), self.embed.W)
+        else:
+            h = _as_device(atom_array, torch.float32)
+        g, g_list = None, []
+        for update, readout in zip(self.layers, self.read_out_layers):
+            h = update(h, adj)
+            dg = readout(h)
+            g = dg if g is None else g + dg
+            if self.concat_hidden:
+                g_list.append(g)
+        self.__dict__["atoms"] = h
+        if self.concat_hidden:
+            # the reference concatenates 2-D arrays along axis 2 (nfp.py:172), which raises in Chainer: kept as an error
+            raise ValueError("NFP(concat_hidden=True): functions.concat(g_list, axis=2) on (mb, out_dim) arrays is invalid in the "
+                             "reference (models/models/nfp.py:172)")
+        return g
+
+    def get_atom_array(self):
+        assert self.atoms is not None
+        return self.atoms
+
+
 class _Embed(Link):
     """chainer_chemistry EmbedAtomID = links.EmbedID(in_size, out_size); W ~ N(0,1)."""
 

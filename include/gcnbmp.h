@@ -372,6 +372,17 @@ int         bmp_device_check(void);           /* BMP_OK iff current device is sm
 uint64_t    bmp_launch_count(void);           /* kernels launched by this library    */
 void        bmp_reset_launch_count(void);
 
+/* ---- NFP encoder pieces (models/models/nfp.py) ------------------------------
+ * EmbedAtomID forward (the GGNN / RelGCN encoders fuse this gather): out[r,:] = embed_W[clamp(atoms[r]), :].
+ * bmp_nfp_gather, NFPUpdate (nfp.py:35-59) on the (mb,N,N) adjacency of the NFP preprocessor:
+ *   forward  (backward == 0): src = h (mb,N,C) -> dst = X (mb,N,D*C), X[b,i,(d-1)C+c] = (adj[b] h[b])[i,c] if degree(b,i) == d
+ *            (degree = column sums of adj, nfp.py:152; d = 1..D), else 0; the D degree-specific GraphLinears are then one
+ *            Linear over X with their weights concatenated along the input axis and their biases summed;
+ *   backward (backward != 0): src = dX -> dst = dh = adj[b]^T (degree block of dX).  fp32, N <= 64.                        */
+int bmp_embed_forward(const int32_t *atoms, const float *embed_W, float *out, int rows, int hidden, int n_atom_types, void *stream);
+int bmp_nfp_gather(const float *adj, const float *src, float *dst, int mb, int n_atoms, int ch, int n_degree, int backward,
+                   void *stream);
+
 /* ---- per-kernel timing (measurement aid, no reference counterpart) ----------
  * With profiling enabled every launch of the hot tcgen05 kernels is bracketed by two CUDA events recorded on the
  * launching stream; bmp_profile_read synchronises on them, adds the elapsed milliseconds and launch counts per kind

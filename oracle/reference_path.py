@@ -639,6 +639,69 @@ def gin_shapes(out_dim, hidden_dim, n_layers, concat_hidden=False, weight_tying=
 
 
 # ----------------------------------------------------------------------------
+# models/models/nfp.py:15-181 -- Neural Fingerprint encoder (the default --method of train_binary.py:319)
+# ----------------------------------------------------------------------------
+class NFPUpdate(object):
+    def __init__(self, p, in_channels, out_channels, max_degree=6):
+        self.p, self.n_deg = p, max_degree + 1
+
+    def __call__(self, h, adj, deg_conds):
+        fv = F.matmul(F.as_var(adj), h)                                                # :44 neighbour sum (adj holds the self loop)
+        zero = np.zeros(fv.shape, dtype=fv.dtype)                                      # :48-51
+        out_h = None
+        for d, cond in enumerate(deg_conds):                                           # :53-57 one GraphLinear per degree, masked input
+            q = self.p.sub("graph_linears/%d" % d)
+            y = F.graph_linear(F.where(cond, fv, zero), q["W"], q["b"])
+            out_h = y if out_h is None else F.add(out_h, y)
+        return F.sigmoid(out_h)                                                        # :60
+
+
+class NFPReadout(object):
+    def __init__(self, p, in_channels, out_size):
+        self.p = p
+
+    def __call__(self, h):
+        q = self.p.sub("output_weight")
+        i = F.softmax(F.graph_linear(h, q["W"], q["b"]), axis=2)                       # :88-89 softmax along the channel axis
+        return F.sum_(i, axis=1)                                                       # :90 sum along the atom axis
+
+
+class NFP(object):
+    def __init__(self, p, out_dim, hidden_dim=16, n_layers=4, max_degree=6):
+        self.p, self.num_degree_type = p, max_degree + 1
+        self.layers = [NFPUpdate(p.sub("layers/%d" % i), hidden_dim, hidden_dim, max_degree) for i in range(n_layers)]
+        self.read_out_layers = [NFPReadout(p.sub("read_out_layers/%d" % i), hidden_dim, out_dim) for i in range(n_layers)]
+        self.atoms = None
+
+    def __call__(self, atom_array, adj):
+        a = np.asarray(getattr(atom_array, "data", atom_array))
+        h = F.embed_id(a, self.p["embed/W"]) if a.dtype.kind == "i" else F.as_var(atom_array)      # :142-146
+        adj_array = np.asarray(getattr(adj, "data", adj))
+        degree_mat = adj_array.sum(axis=1)                                             # :152
+        deg_conds = [np.broadcast_to(((degree_mat - degree) == 0)[:, :, None], h.shape)
+                     for degree in range(1, self.num_degree_type + 1)]                  # :154-156
+        g = None
+        for update, readout in zip(self.layers, self.read_out_layers):                 # :158-163
+            h = update(h, adj, deg_conds)
+            dg = readout(h)
+            g = dg if g is None else F.add(g, dg)
+        self.atoms = h
+        return g
+
+    def get_atom_array(self):
+        return self.atoms
+
+
+def nfp_shapes(out_dim, hidden_dim, n_layers, max_degree=6, n_atom_types=MAX_ATOMIC_NUM):
+    s = {"embed/W": (n_atom_types, hidden_dim)}
+    for i in range(n_layers):
+        for d in range(max_degree + 1):
+            s["layers/%d/graph_linears/%d/W" % (i, d)], s["layers/%d/graph_linears/%d/b" % (i, d)] = (hidden_dim, hidden_dim), (hidden_dim,)
+        s["read_out_layers/%d/output_weight/W" % i], s["read_out_layers/%d/output_weight/b" % i] = (out_dim, hidden_dim), (out_dim,)
+    return s
+
+
+# ----------------------------------------------------------------------------
 # models/mlp.py:20-110,154-197 -- the other link-prediction heads
 # ----------------------------------------------------------------------------
 def _stack(p, names, n_hidden, act, h):

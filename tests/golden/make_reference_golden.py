@@ -53,6 +53,7 @@ ref_para = load("ref_para", "models/coattention/parallel_coattention.py")
 ref_global = load("ref_global", "models/coattention/global_coattention.py")
 ref_neural = load("ref_neural", "models/coattention/neural_coattention.py")
 ref_gin = load("ref_gin", "models/gin.py")
+ref_nfp = load("ref_nfp", "models/models/nfp.py")
 ref_hole = load("ref_hole", "models/link_prediction/hole.py")
 ref_mlp = load("ref_mlp", "models/mlp.py")
 ref_mono = {"ggnn_py": load("ref_ggnn_py", "models/ggnn.py"), "ggnn_att": load("ref_ggnn_att", "models/ggnn_att.py"),
@@ -234,6 +235,30 @@ def main():
         o_out, o_gin = run(lambda: onet(atoms, adj), [], [w])
         check_and_save(tag, params, [atoms], [adj], [w], r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab),
                        dict(kind="gin", H=H, O=O, T=T, tied=tied, concat=concat, act="tanh"))
+    # ---- NFP (models/models/nfp.py): (mb, N, N) adjacency with self connections, as the NFP preprocessor builds it
+    nfp_rng = np.random.default_rng(20191105)          # its own stream: the fixtures above and below keep their bits
+    for tag, mb, N in (("nfp", 4, 9), ("nfp_ragged", 3, 13)):
+        H, O, T = 12, 8, 3
+        atoms, adj4 = random_molecules(nfp_rng, mb, N)
+        adj = adj4.sum(axis=1).astype(np.float64)
+        adj = adj + np.eye(N)[None] * (atoms > 0)[:, :, None]      # self connection on the real atoms; padded atoms keep degree 0
+        if tag == "nfp_ragged":
+            adj[0, 1, 2] = adj[0, 2, 1] = 0.0                       # degrees need not be symmetric-consistent: column sums rule
+        params = R.init_params(R.nfp_shapes(O, H, T), nfp_rng, dtype=np.float64)
+        ws = [nfp_rng.standard_normal((mb, O)), nfp_rng.standard_normal((mb, N, H))]
+        net = ref_nfp.NFP(O, hidden_dim=H, n_layers=T)
+        load_params(net, params)
+
+        def both(n):
+            def fn():
+                g = n(atoms, adj)
+                return g, n.get_atom_array()
+            return fn
+        r_out, r_gin = run(both(net), [], ws)
+        tab = R.wrap_params(params)
+        o_out, o_gin = run(both(R.NFP(R.P(tab), O, H, T)), [], ws)
+        check_and_save(tag, params, [atoms], [adj], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab),
+                       dict(kind="nfp", H=H, O=O, T=T))
     # ---- bare GGNNUpdate with state threading (two calls, then reset, then one call)
     H, mb, N = 8, 2, 7
     _, adj = random_molecules(rng, mb, N)

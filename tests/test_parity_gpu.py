@@ -313,3 +313,40 @@ def test_config_B_relgcn_64x4():
     assert rel_err(p["logits"], o["logits"]) <= TOL
     for k in sorted(o["grads"]):
         assert rel_err(p["grads"][k], o["grads"][k], floor=1e-7) <= TOL, k
+
+
+def test_nfp_pair_forward_backward_matches_oracle():
+    """train_binary.py --method nfp (the script's default encoder) + Nie co-attention + HolE: models/models/nfp.py on the
+    (mb, N, N) adjacency with self connections, logits and every parameter gradient vs the fp64 oracle."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(12)
+    mb, N, H, O, T, K = 5, 21, 16, 12, 3, 3
+    ins = []
+    for _ in range(2):
+        atoms, adj4 = synthetic.random_molecules(rng, mb, N)
+        adj = adj4.sum(axis=1) + np.eye(N, dtype=np.float32)[None] * (atoms > 0)[:, :, None]
+        ins += [atoms, adj.astype(np.float64)]
+    y = (rng.random((mb, K)) < 0.4).astype(np.int32)
+    shapes = {"graph_conv/" + k: v for k, v in R.nfp_shapes(O, H, T).items()}
+    shapes.update({"attn/" + k: v for k, v in R.coattn_shapes(H, O, 4).items()})
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(O, K, ()).items()})
+    params = R.init_params(shapes, rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    P = R.P(tab)
+    omodel = R.GraphConvPredictorForPair(R.NFP(P.sub("graph_conv"), O, H, T), R.NieFineCoattention(P.sub("attn"), H, O, 4, activation="tanh"),
+                                         R.HolE(P.sub("mlp"), K, hidden_dims=()))
+    loss, logits, grads = R.loss_and_grads(omodel, tab, tuple(ins), y)
+    model = gcnbmp.GraphConvPredictorForPair(gcnbmp.NFP(O, hidden_dim=H, n_layers=T),
+                                             gcnbmp.NieFineCoattention(H, O, 4, activation=gcnbmp.functions.tanh), gcnbmp.HolE(K, hidden_dims=()))
+    model.mlp.l_out.ensure(O)
+    model.load_params({k: np.asarray(v, np.float32) for k, v in params.items()})
+    model.cleargrads()
+    f32 = [x.astype(np.float32) if x.dtype.kind == "f" else x for x in ins]
+    plogits = model(*f32)
+    gcnbmp.sigmoid_cross_entropy(plogits, y).backward()
+    assert rel_err(plogits.detach().cpu().numpy(), logits) <= 1e-4
+    g = model.grad_dict()
+    for k, v in grads.items():
+        if v is not None and np.abs(v).max() > 1e-9:
+            assert rel_err(g[k], v) <= 1e-4, k

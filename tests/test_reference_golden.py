@@ -49,6 +49,13 @@ def _oracle_fn(fx, tab):
     if kind == "gin":
         net = R.GIN(P, m["O"], m["H"], m["T"], concat_hidden=m["concat"], weight_tying=m["tied"], activation=m["act"])
         return lambda: (net(fx["ints"][0], fx["floats"][0]),)
+    if kind == "nfp":
+        net = R.NFP(P, m["O"], m["H"], m["T"])
+
+        def fn():
+            g = net(fx["ints"][0], fx["floats"][0])
+            return g, net.get_atom_array()
+        return fn
     if kind == "mono":
         net = R.GGNNMono(P, m["O"], m["H"], m["T"], weight_tying=m["tied"], sum_readout=m["sum_readout"])
 
@@ -105,7 +112,7 @@ def _oracle_fn(fx, tab):
 
 def _n_var_inputs(fx):
     k = fx["meta"]["kind"]
-    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "gin": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4, "coattn_global": 4, "coattn_neural": 4}.get(k, 2)
+    return {"ggnn": 1, "mono": 1, "ggnn_update": 2, "relgcn": 0, "gin": 0, "nfp": 0, "readout": 2, "coattn_alter": 4, "coattn_para": 4, "coattn_circ": 4, "coattn_global": 4, "coattn_neural": 4}.get(k, 2)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -132,7 +139,7 @@ def test_oracle_reproduces_reference_generated_fixture(name):
 def test_fixture_set_covers_every_hot_path_file():
     kinds = {_load(n)["meta"]["kind"] for n in NAMES}
     assert {"ggnn", "mono", "ggnn_update", "relgcn", "coattn_nie", "coattn_vqa", "coattn_pool", "readout", "head_hole",
-            "head_hole_mlp_py", "head_mlp", "head_symmlp", "head_ntn", "head_distmult"} <= kinds
+            "head_hole_mlp_py", "head_mlp", "head_symmlp", "head_ntn", "head_distmult", "nfp"} <= kinds
 
 
 def _pair_fixture(name):
@@ -188,6 +195,13 @@ def _product(fx):
     if kind == "gin":
         net = gcnbmp.GIN(m["O"], hidden_dim=m["H"], n_layers=m["T"], dropout_ratio=0.0, concat_hidden=m["concat"], weight_tying=m["tied"], activation=act(m["act"]))
         return (lambda: (net(fx["ints"][0], fx["floats"][0].astype(np.float32)),)), net
+    if kind == "nfp":
+        net = gcnbmp.NFP(m["O"], hidden_dim=m["H"], n_layers=m["T"])
+
+        def fn():
+            g = net(fx["ints"][0], fx["floats"][0].astype(np.float32))
+            return g, net.get_atom_array()
+        return fn, net
     if kind == "mono":
         net = gcnbmp.GGNNMono(m["O"], m["H"], m["T"], weight_tying=m["tied"], sum_readout=m["sum_readout"])
 
