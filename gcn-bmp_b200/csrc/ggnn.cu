@@ -399,6 +399,7 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
         return BMP_EINVAL;
     }
     if (a->mode == BMP_MODE_BF16) return bmp_ggnn_forward_tc(a, stream);
+    if (a->mol_index) { set_error("bmp_ggnn_forward: mol_index (table indirection) is a BMP_MODE_BF16 feature; gather the rows first"); return BMP_ESHAPE; }
     if (a->adj_u8) { set_error("bmp_ggnn_forward: a byte adjacency needs BMP_MODE_BF16"); return BMP_EINVAL; }
     int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->mode);
     if (rc) return rc;

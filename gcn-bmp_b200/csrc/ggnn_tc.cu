@@ -53,6 +53,7 @@ struct Args {
     long long *dbg;              // optional phase timestamps of CTA 0 (tools/tc_timeline.py)
     Stash2 st;                   // bf16 panel stash (use2 != 0): replaces the fp32 Hs/Ms/Gs/RSs stores
     int use2;
+    const int32_t *midx;         // optional (mb,): atoms / adj are a drug table, molecule b = table row midx[b]
 };
 
 template <int H, bool V2, bool LEAN>
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                 const float *src = nullptr;
                 if (live) {
                     if (a.atoms) {
-                        int id = __ldg(a.atoms + grow);
+                        int id = __ldg(a.atoms + (a.midx ? (long)__ldg(a.midx + molg) * a.N + atom : grow));
                         id = id < 0 ? 0 : (id >= a.n_types ? a.n_types - 1 : id);
                         src = a.embed_W + (long)id * H + colbase;
                     } else {
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
             }
             // ---- stage the adjacency (fp32 global -> bf16 SW128 tiles [mol][e][i][j]) ----
             TSP(1);
-            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid, a.midx);
             TSP(2);
             {
 #pragma unroll
@@ -326,8 +327,8 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
 #define TSF(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TSF(0);
                 if (t == a.T - 1 && tile + (int)gridDim.x < n_tiles) {      // next tile of this CTA: adjacency and atom ids towards L2
-                    prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid);
-                    if (a.atoms && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
+                    prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid, a.midx);
+                    if (a.atoms && !a.midx && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
                 }
                 uint32_t v[32];
                 // ---- E1: AH accumulators -> bf16 A-operand panels (two K halves) ----
@@ -588,6 +589,8 @@ int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream) {
     k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.adj_u8 = a->adj_u8;
     k.h_out = a->h_out; k.h0_out = a->h0_out; k.Hs = a->Hs; k.Ms = a->Ms; k.Gs = a->Gs; k.RSs = a->RSs;
     k.dbg = g_tc_dbg_fwd;
+    k.midx = a->mol_index;
+    if (a->mol_index && !a->atoms) { set_error("BMP_MODE_BF16: mol_index needs atom ids (a drug table), not h_in"); return BMP_EINVAL; }
     k.use2 = a->stash2 != nullptr;
     if (k.use2) k.st.carve(a->stash2, (a->mb + 1) / 2, H, T);
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 255) & ~(uintptr_t)255);

@@ -52,6 +52,7 @@ struct Args {
     const float *msg_b[BMP_MAX_STEPS];
     int stateful[BMP_MAX_STEPS];
     float *h_out, *h0_out;
+    const int32_t *midx;         // optional (mb,): table-row indirection (see ggnn_tc.cu)
     uint8_t *scratch;            // gridDim.x x 64 KB: bf16 adjacency image of the CTA's current tile
     long long *dbg;              // optional: per step of CTA 0, the MMA lane's [total, weight wait, AH wait, x wait, rs wait, h wait] cycles
 };
@@ -224,13 +225,13 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
                         return g >= 0 ? base + g * H + 64 * kb + 16 * cg : nullptr;
                     });
             };
-            stage_adjacency<NE>(smem + OFF_X, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + OFF_X, a.adj, a.adj_u8, tile, a.mb, a.N, tid, a.midx);
             // ---- h_0: embedding gather (or h_in) -> fp32 registers
             {
                 const float *src = nullptr;
                 if (live) {
                     if (a.atoms) {
-                        int id = __ldg(a.atoms + grow);
+                        int id = __ldg(a.atoms + (a.midx ? (long)__ldg(a.midx + molg) * a.N + atom : grow));
                         id = id < 0 ? 0 : (id >= a.n_types ? a.n_types - 1 : id);
                         src = a.embed_W + (long)id * H;
                     } else {
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(32 * (EPW + 2), 1) ggnn_tc256_kernel(const Arg
                 const bool stateful = a.stateful[t] != 0;
                 const float *b3 = a.bias3[t];
                 if (t == a.T - 1 && tile + (int)gridDim.x < n_tiles) {
-                    prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid);
-                    if (a.atoms && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
+                    prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid, a.midx);
+                    if (a.atoms && !a.midx && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
                 }
                 uint32_t w[16];
                 // ---- E1: AH accumulators of group g -> the two bf16 A panels of ring slot g&1
@@ -504,6 +505,8 @@ int bmp_ggnn_forward_tc256(const bmp_ggnn_fwd_t *a, void *stream) {
     k.mb = a->mb; k.N = a->n_atoms; k.T = T; k.n_types = a->n_atom_types;
     k.atoms = a->atoms; k.embed_W = a->embed_W; k.h_in = a->h_in; k.adj = a->adj; k.adj_u8 = a->adj_u8;
     k.h_out = a->h_out; k.h0_out = a->h0_out;
+    k.midx = a->mol_index;
+    if (a->mol_index && !a->atoms) { set_error("BMP_MODE_BF16: mol_index needs atom ids (a drug table), not h_in"); return BMP_EINVAL; }
     k.dbg = g_tc_dbg_fwd;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
     const size_t ib = tc256::image_bytes();

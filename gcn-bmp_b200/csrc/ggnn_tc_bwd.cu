@@ -43,6 +43,7 @@ struct Args {
     long long *dbg;              // optional phase timestamps of CTA 0 (tools/tc_timeline.py)
     Stash2 st;                   // bf16 panel stash (use2 != 0): gate values in, delta / P panels out
     int use2;                    //   then dHs has two slices: [0] <-> h_0, [1] <-> h_T
+    const int32_t *midx;         // optional (mb,): adj is a drug table, molecule b = table row midx[b]
 };
 
 // flags[t] |= 1 when dHs[t] has any non-zero entry (the intermediate states normally receive no external gradient)
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
             const int molg = tile * 2 + molslot;
             const bool live = molg < a.mb && atom < a.N;
             const long grow = (long)molg * a.N + atom;
-            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid);
+            stage_adjacency<NE>(smem + C::OFF_ADJ, a.adj, a.adj_u8, tile, a.mb, a.N, tid, a.midx);
             {
                 const float *src = live ? a.dHs + ((long)(V2 ? 1 : a.T) * rows_total + grow) * H + colbase : nullptr;
 #pragma unroll
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_bwd_kernel(const 
                 uint32_t v[32];
 #define TS(i) do { if (a.dbg && blockIdx.x == 0 && tid == 0 && it < 64) a.dbg[it * 16 + (i)] = clock64(); } while (0)
                 TS(0);
-                if (t == 0 && tile + (int)gridDim.x < n_tiles) prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid);
+                if (t == 0 && tile + (int)gridDim.x < n_tiles) prefetch_adjacency_l2<NE>(a.adj, a.adj_u8, tile + gridDim.x, a.mb, a.N, tid, a.midx);
                 // ---- phase A: gate derivatives ----
                 if (V2) {
                     // gate values of the step: coalesced 16-byte loads in the thread-native bf16 order, two 16-column halves
@@ -602,6 +603,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     }
     k.ext_flags = flags;
     k.dbg = g_tc_dbg;
+    k.midx = a->mol_index;
     k.use2 = a->stash2 != nullptr;
     if (k.use2) k.st.carve(a->stash2, (a->mb + 1) / 2, H, T);
     const size_t ib = tcb::image_bytes(H);

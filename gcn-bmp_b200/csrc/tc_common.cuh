@@ -141,7 +141,10 @@ __host__ __device__ constexpr uint32_t idesc2(int n, int a_mn_major, int b_mn_ma
 // 2 KB per molecule at N = 64, 1/32 of the fp32 bytes).
 // Loads are issued in batches of 8 vectors per thread so the DRAM latency is paid a few times per tile, not per element.
 template <int NE>
-__device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__restrict__ adj_any, int u8, int tile, int mb, int N, int tid) {
+__device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__restrict__ adj_any, int u8, int tile, int mb, int N, int tid,
+                                                const int32_t *__restrict__ midx = nullptr) {
+    // midx: molecule b of this call is row midx[b] of a drug TABLE (atoms / adjacency read through the index, no gather copy)
+    auto srcmol = [&](int mg) -> long { return midx ? (long)__ldg(midx + mg) : (long)mg; };
     if (u8 == 2) {
         const uint8_t *adj = reinterpret_cast<const uint8_t *>(adj_any);
         const int W = (N + 7) >> 3;
@@ -154,7 +157,7 @@ __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__re
             const int mg = tile * 2 + (me >> 2);
             bits[u] = 0;
             if (idx < ROWS && mg < mb && i < N) {
-                const uint8_t *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * W;
+                const uint8_t *src = adj + ((srcmol(mg) * 4 + (me & 3)) * N + i) * W;
                 if (W == 8) {
                     bits[u] = __ldg(reinterpret_cast<const unsigned long long *>(src));
                 } else {
@@ -191,7 +194,7 @@ __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__re
             const int mg = tile * 2 + (me >> 2);
             v[u] = make_uint4(0, 0, 0, 0);
             if (idx < ITEMS && mg < mb && i < N && j16 < N) {
-                const uint8_t *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j16;
+                const uint8_t *src = adj + ((srcmol(mg) * 4 + (me & 3)) * N + i) * N + j16;
                 if ((N & 15) == 0) {
                     v[u] = __ldg(reinterpret_cast<const uint4 *>(src));
                 } else {
@@ -229,7 +232,7 @@ __device__ __forceinline__ void stage_adjacency(uint8_t *s_adj, const void *__re
             const int mg = tile * 2 + (me >> 2);
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (mg < mb && i < N) {
-                const float *src = adj + (((long)mg * 4 + (me & 3)) * N + i) * N + j4;
+                const float *src = adj + ((srcmol(mg) * 4 + (me & 3)) * N + i) * N + j4;
                 if ((N & 3) == 0) {
                     if (j4 < N) v[u] = __ldg(reinterpret_cast<const float4 *>(src));
                 } else {
@@ -280,9 +283,17 @@ __device__ __forceinline__ void rescale_staged_adjacency(uint8_t *s_adj, float *
 
 // pull the next tile's adjacency (2 molecules x 4 bond types x N x N fp32, contiguous) towards L2
 template <int NE>
-__device__ __forceinline__ void prefetch_adjacency_l2(const void *__restrict__ adj, int u8, int tile, int mb, int N, int tid) {
+__device__ __forceinline__ void prefetch_adjacency_l2(const void *__restrict__ adj, int u8, int tile, int mb, int N, int tid,
+                                                      const int32_t *__restrict__ midx = nullptr) {
     const long first = (long)tile * 2, nmol = first + 2 <= mb ? 2 : (first < mb ? 1 : 0);
     const long per_mol = u8 == 2 ? 4L * N * ((N + 7) >> 3) : 4L * N * N * (u8 ? 1 : 4);
+    if (midx) {      // table rows: the two molecules of the tile are not adjacent in memory
+        for (long m = 0; m < nmol; ++m) {
+            const char *base = reinterpret_cast<const char *>(adj) + (long)__ldg(midx + first + m) * per_mol;
+            for (long off = (long)tid * 128; off < per_mol; off += (long)NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+        return;
+    }
     const char *base = reinterpret_cast<const char *>(adj) + first * per_mol;
     const long bytes = nmol * per_mol;
     for (long off = (long)tid * 128; off < bytes; off += (long)NE * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));

@@ -168,10 +168,16 @@ class GGNNEncode(torch.autograd.Function):
     Returns Hs (T+1, mb, N, H) when a tape is needed, else a (2, mb, N, H) tensor [h_0, h_T]."""
 
     @staticmethod
-    def forward(ctx, x, adj, state_in, plan, n_msg, n_gru, mode, want_stash, keep_steps, *params):
+    def forward(ctx, x, adj, state_in, plan, n_msg, n_gru, mode, want_stash, keep_steps, mol_index, *params):
         _need_cuda(x, adj)
+        if mol_index is not None and (mode != K.MODE_BF16 or x.dtype not in (torch.int32, torch.int64)):
+            # table indirection is read inside the tcgen05 kernels only; elsewhere gather the rows (a device-side copy)
+            x, adj, mol_index = x.index_select(0, mol_index.long()), adj.index_select(0, mol_index.long()), None
         adj, adj_u8 = _adj(adj, mode)
         mb, E, N, _ = adj.shape
+        if mol_index is not None:
+            mol_index = mol_index.to(torch.int32).contiguous()
+            mb = mol_index.shape[0]
         embed_W = params[0]
         msg = [(params[1 + 2 * i], params[2 + 2 * i]) for i in range(n_msg)]
         base = 1 + 2 * n_msg
@@ -188,7 +194,7 @@ class GGNNEncode(torch.autograd.Function):
             x = _f32(x)
             a.h_in = _p(x)
         state_in = _f32(state_in)
-        a.adj, a.state_in, a.adj_u8 = _p(adj), _p(state_in), adj_u8
+        a.adj, a.state_in, a.adj_u8, a.mol_index = _p(adj), _p(state_in), adj_u8, _p(mol_index)
         for t, (mi, gi, st) in enumerate(plan):
             a.msg_W[t], a.msg_b[t] = _p(msg[mi][0]), _p(msg[mi][1])
             _fill_gru(a.gru[t], gru[gi])
@@ -211,6 +217,7 @@ class GGNNEncode(torch.autograd.Function):
             a.h0_out, a.h_out, a.stash2 = _p(out[0]), _p(out[1]), _p(stash2)
             K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
             ctx.save_for_backward(x, adj, state_in, stash2, None, None, None, *params)
+            ctx.mol_index = mol_index
             ctx.meta = (plan, n_msg, n_gru, mode, is_ids, (mb, N, H))
             return out
         if want_stash:
@@ -221,6 +228,7 @@ class GGNNEncode(torch.autograd.Function):
             a.Hs, a.Ms, a.Gs, a.RSs = _p(Hs), _p(Ms), _p(Gs), _p(RSs)
             K.check(K.lib.bmp_ggnn_forward(C.byref(a), _stream()))
             ctx.save_for_backward(x, adj, state_in, Hs, Ms, Gs, RSs, *params)
+            ctx.mol_index = mol_index
             ctx.meta = (plan, n_msg, n_gru, mode, is_ids, None)
             return Hs
         out = torch.empty((2, mb, N, H), device=dev, dtype=torch.float32)   # [h_0, h_T]
@@ -247,7 +255,8 @@ class GGNNEncode(torch.autograd.Function):
         Ps = torch.empty((T, rows, E * H), device=adj.device, dtype=torch.float32) if stash2 is None else None
         a = K.GgnnBwd()
         a.mb, a.n_atoms, a.hidden, a.n_edge, a.n_steps, a.mode = mb, N, H, E, T, mode
-        a.adj, a.state_in, a.adj_u8 = _p(adj), _p(state_in), adj_format(adj)
+        mol_index = ctx.mol_index
+        a.adj, a.state_in, a.adj_u8, a.mol_index = _p(adj), _p(state_in), adj_format(adj), _p(mol_index)
         base = 1 + 2 * n_msg
         for t, (mi, gi, st) in enumerate(plan):
             a.msg_W[t] = _p(params[1 + 2 * mi])
@@ -266,11 +275,12 @@ class GGNNEncode(torch.autograd.Function):
         K.check(K.lib.bmp_ggnn_backward(C.byref(a), _stream()))
         dx = None
         if is_ids:
-            K.check(K.lib.bmp_embed_backward(_p(x), _p(dHs[0]), _p(grads[0]), rows, H, grads[0].shape[0], _stream()))
+            ids = x if mol_index is None else x.index_select(0, mol_index.long()).contiguous()      # (mb, N) int32: tiny
+            K.check(K.lib.bmp_embed_backward(_p(ids), _p(dHs[0]), _p(grads[0]), rows, H, grads[0].shape[0], _stream()))
         else:
             dx = dHs[0]
             rets[0] = None
-        return (dx, None, d_state, None, None, None, None, None, None) + tuple(rets)
+        return (dx, None, d_state, None, None, None, None, None, None, None) + tuple(rets)
 
 
 class RelGCNEncode(torch.autograd.Function):

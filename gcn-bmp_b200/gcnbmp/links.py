@@ -303,7 +303,7 @@ class _GRU(Link):
                 c["U_z"].W, c["U_z"].b, c["W"].W, c["W"].b, c["U"].W, c["U"].b]
 
 
-def _encode(x, adj, state, plan, msgs, grus, embed_W, mode, keep_steps=False):
+def _encode(x, adj, state, plan, msgs, grus, embed_W, mode, keep_steps=False, mol_index=None):
     """Returns (states, last): states[0] = h_0, states[last] = h_T; every step is present only when
     `keep_steps` (or in fp32 mode with a tape) -- BF16 mode otherwise keeps a bf16 panel stash internally."""
     want = torch.is_grad_enabled()
@@ -312,7 +312,7 @@ def _encode(x, adj, state, plan, msgs, grus, embed_W, mode, keep_steps=False):
         params += [W, b]
     for g in grus:
         params += g.tensors()
-    out = Fn.GGNNEncode.apply(x, adj, state, tuple(plan), len(msgs), len(grus), mode, want, keep_steps, *params)
+    out = Fn.GGNNEncode.apply(x, adj, state, tuple(plan), len(msgs), len(grus), mode, want, keep_steps, mol_index, *params)
     return out, (out.shape[0] - 1)
 
 
@@ -413,9 +413,12 @@ class GGNN(Link):
             return [(0, 0, t > 0) for t in range(self.n_layers)]
         return [(t, t, False) for t in range(self.n_layers)]
 
-    def __call__(self, atom_array, adj, is_real_node=None):
+    def __call__(self, atom_array, adj, is_real_node=None, mol_index=None):
+        """`mol_index` (extension): rows of a device-resident drug table, as in GGNNMono.__call__."""
         self.reset_state()
         adj = _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
+        if mol_index is not None:
+            mol_index = _as_device(mol_index, torch.int32)
         ids = _is_ids(atom_array) and getattr(atom_array, "ndim", 2) <= 2
         x = _as_device(atom_array, torch.int32 if ids else torch.float32)
         ups = list(self.update_layers)
@@ -423,7 +426,7 @@ class GGNN(Link):
         grus = [u.update_layer for u in ups]
         T = self.n_layers
         hs, last = _encode(x, adj, None, self._plan(), msgs, grus, self.embed.W if ids else None, self.mode,
-                           keep_steps=self.concat_hidden)
+                           keep_steps=self.concat_hidden, mol_index=mol_index)
         stash = last == T
         h0, hT = hs[0], hs[last]
         self.__dict__["atoms"] = hT
@@ -475,16 +478,20 @@ class GGNNMono(Link):
         i, j = self.i_layers[idx], self.j_layers[idx]
         return Fn.Readout.apply(h, h0, None, K.READOUT_R2, 0, 0, i.W, i.b, j.W, j.b, self.mode)
 
-    def __call__(self, atom_array, adj):
+    def __call__(self, atom_array, adj, mol_index=None):
+        """`mol_index` (extension): int (mb,) -- `atom_array` (U,N) / `adj` (U,E,N,N) are a device-resident drug
+        table and molecule b of the batch is its row mol_index[b] (read inside the tcgen05 kernels, no gather copy)."""
         self.update_layer.reset_state()
         adj = _adj_device(adj, self.__dict__.get("mode", K.MODE_F32))
+        if mol_index is not None:
+            mol_index = _as_device(mol_index, torch.int32)
         ids = _is_ids(atom_array)
         x = _as_device(atom_array, torch.int32 if ids else torch.float32)
         T = self.n_layers
         msgs = [(m.W, m.b) for m in self.message_layers]
         plan = [(0 if self.weight_tying else t, 0, t > 0) for t in range(T)]
         hs, last = _encode(x, adj, None, plan, msgs, [self.update_layer], self.embed.W if ids else None, self.mode,
-                           keep_steps=self.concat_hidden or self.keep_steps)
+                           keep_steps=self.concat_hidden or self.keep_steps, mol_index=mol_index)
         stash = last == T
         h0, hT = hs[0], hs[last]
         self.__dict__["atoms"] = hT
@@ -1124,6 +1131,26 @@ class GraphConvPredictorForPair(Link):
         a1 = self.graph_conv.get_atom_array()
         g2 = self.graph_conv(atoms_2, adjs_2)
         a2 = self.graph_conv.get_atom_array()
+        if self.attn is not None:
+            g1, g2 = self.attn(a1, g1, a2, g2)
+        return self.head(g1, g2)
+
+    def encode_rows(self, table_atoms, table_adjs, rows):
+        """Encoder over rows of a device-resident drug table -> (graph vectors, atom states).  GGNN encoders in BF16 mode read
+        the table through the index inside the kernels; every other encoder gets a gathered copy of the rows."""
+        enc = self.graph_conv
+        if isinstance(enc, (GGNN, GGNNMono)) and enc.__dict__.get("mode", K.MODE_F32) == K.MODE_BF16 and _is_ids(table_atoms):
+            g = enc(table_atoms, table_adjs, mol_index=rows)
+        else:
+            rows = rows.long()
+            g = enc(table_atoms.index_select(0, rows), table_adjs.index_select(0, rows))
+        return g, (enc.get_atom_array() if hasattr(enc, "get_atom_array") else None)
+
+    def forward_indexed(self, table_atoms, table_adjs, idx_1, idx_2):
+        """`__call__` for pairs given as index pairs into a drug table (train_binary.py:285-294,552-553 build the
+        per-pair copies this replaces)."""
+        g1, a1 = self.encode_rows(table_atoms, table_adjs, idx_1)
+        g2, a2 = self.encode_rows(table_atoms, table_adjs, idx_2)
         if self.attn is not None:
             g1, g2 = self.attn(a1, g1, a2, g2)
         return self.head(g1, g2)

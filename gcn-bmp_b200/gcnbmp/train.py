@@ -278,9 +278,14 @@ class PairTrainer(object):
                 self._dedupe_pass(table_atoms, table_adjs, i1, i2, y, global_count)
             else:
                 for s, e in self._chunks(n):
-                    a1, a2 = table_atoms.index_select(0, i1[s:e]), table_atoms.index_select(0, i2[s:e])
-                    A1, A2 = table_adjs.index_select(0, i1[s:e]), table_adjs.index_select(0, i2[s:e])
-                    self._micro(a1, A1, a2, A2, y[s:e], global_count)
+                    logits = self.model.forward_indexed(table_atoms, table_adjs, i1[s:e], i2[s:e])   # rows read in-kernel
+                    loss = L.sigmoid_cross_entropy(logits, y[s:e], count=global_count)
+                    Fn.set_grad_sink(True)
+                    try:
+                        loss.backward()
+                    finally:
+                        Fn.set_grad_sink(False)
+                    self.loss_buf += loss.detach()
         finally:
             Fn.set_weight_cache(False)
         if self.world_size > 1:
@@ -299,9 +304,7 @@ class PairTrainer(object):
         # 1. encode the unique drugs (micro-batches of `chunk` molecules; the tapes stay alive until step 3)
         enc_out = []
         for s, e in self._chunks(uniq.shape[0]):
-            rows = uniq[s:e]
-            g = m.graph_conv(table_atoms.index_select(0, rows), table_adjs.index_select(0, rows))
-            enc_out.append((g, m.graph_conv.get_atom_array()))
+            enc_out.append(m.encode_rows(table_atoms, table_adjs, uniq[s:e]))
         g_all = torch.cat([g for g, _ in enc_out]).detach().requires_grad_(True)
         a_all = torch.cat([a for _, a in enc_out]).detach().requires_grad_(True)
         # 2. pairs: co-attention + head on gathered encoder outputs; d g / d atoms accumulate per drug (index_add in autograd)
@@ -344,10 +347,10 @@ class PairTrainer(object):
         inv1, inv2 = inv[: i1.shape[0]], inv[i1.shape[0]:]
         gs, ats = [], []
         for s, e in self._chunks(uniq.shape[0]):
-            rows = uniq[s:e]
-            gs.append(m.graph_conv(table_atoms.index_select(0, rows), table_adjs.index_select(0, rows)))
+            g, at = m.encode_rows(table_atoms, table_adjs, uniq[s:e])
+            gs.append(g)
             if m.attn is not None:
-                ats.append(m.graph_conv.get_atom_array())
+                ats.append(at)
         g_all = torch.cat(gs)
         a_all = torch.cat(ats) if ats else None
         outs = []

@@ -94,6 +94,9 @@ typedef struct {
     int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
                                    array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
                                    (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
+    const int32_t *mol_index;    /* BMP_MODE_BF16 only, or NULL.  (mb,) int32: `atoms` (U,N) and `adj` (U,E,N,N) are a device-resident
+                                   drug TABLE and molecule b of this call is its row mol_index[b] (train_binary.py:285-294 builds the
+                                   per-pair copies this replaces); read inside the kernels, no gather copy              */
 } bmp_ggnn_fwd_t;
 
 int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
@@ -130,6 +133,7 @@ typedef struct {
     int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
                                    array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
                                    (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
+    const int32_t *mol_index;    /* as in bmp_ggnn_fwd_t (the adjacency table rows of the forward), or NULL              */
 } bmp_ggnn_bwd_t;
 
 int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
