@@ -289,8 +289,9 @@ def run_gpu(args):
                  ("coattn_fwd", "coattn_tc_kernel<128,0,8>", fl["attn"] * n_local, n_local, "pairs")]
         roof_kernels = []
         for kind, kname, flops, units, unit_name in kinds:
-            group = 7 if kind == "wgrad" else 1          # parameter-gradient launches per encoder backward (tied weights)
             t_ms, cnt = prof[kind]
+            # parameter-gradient launches per encoder backward (one per run of equal statefulness; each covers all molecules)
+            group = max(1, round(cnt / max(prof["ggnn_bwd"][1], 1))) if kind == "wgrad" else 1
             if cnt == 0:
                 continue
             ach = flops / (t_ms * 1e-3) / 1e12

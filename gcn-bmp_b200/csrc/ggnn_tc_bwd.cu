@@ -644,7 +644,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     return check_launch("ggnn_tc_bwd_kernel");
 }
 
-int bmp_wgrad_panels(bmp::w2::Args &k, void *stream);   // wgrad_tc2.cu
+int bmp_wgrad_panels_multi(bmp::w2::Args *list, int n, void *stream);   // wgrad_tc2.cu
 
 // Backward over the bf16 panel stash (stash v2): data kernel, then every parameter gradient as a
 // C += A^T B contraction whose operands are streamed straight from the dumped panels.
@@ -659,12 +659,26 @@ int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
     // launches are arranged for the fewest operand reads:
     //   per gate g and run of equal statefulness:  delta_g^T [h | m | r*h]  -> W_g (both halves) and U_g together
     //   per pair of bond types:                    [P_e ; P_e']^T h         -> two row groups of W_msg
+    // One launch per run of equal statefulness: its gate classes and its message classes walk the same (step, tile) units in
+    // lockstep, so the h / m panels all of them read come from HBM once (w2::Multi).
+    w2::Args cls[w2::MAX_CLASSES];
+    int ncls = 0;
+    auto flush = [&]() -> int {
+        int e = ncls ? bmp_wgrad_panels_multi(cls, ncls, stream) : BMP_OK;
+        ncls = 0;
+        return e;
+    };
+    auto push = [&](const w2::Args &k) -> int {
+        if (ncls && (cls[0].t0 != k.t0 || cls[0].t1 != k.t1)) { int e = flush(); if (e) return e; }
+        cls[ncls++] = k;
+        return ncls == w2::MAX_CLASSES ? flush() : BMP_OK;
+    };
     auto gate_launch = [&](int g, int ta, int tb, bool stateful, const bmp_gru_grad_t &D) -> int {
         float *Wg = g == 0 ? D.W_r : (g == 1 ? D.W_z : D.W), *bW = g == 0 ? D.b_Wr : (g == 1 ? D.b_Wz : D.b_W);
         float *Ug = !stateful ? nullptr : (g == 0 ? D.U_r : (g == 1 ? D.U_z : D.U));
         float *bU = !stateful ? nullptr : (g == 0 ? D.b_Ur : (g == 1 ? D.b_Uz : D.b_U));
         if (!Wg && !Ug) return BMP_OK;
-        for (int mt = 0; mt < KP; mt += 2) {          // 128 rows of the gradient per launch
+        for (int mt = 0; mt < KP; mt += 2) {          // 128 rows of the gradient per class
             w2::Args k = {};
             k.A = S.Dp; k.a_ppt = 3 * KP; k.n_mt = 1;
             k.a_panel[0][0] = g * KP + mt; k.a_panel[0][1] = mt + 1 < KP ? g * KP + mt + 1 : -1;
@@ -693,9 +707,37 @@ int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
             }
             k.bias_stride = 1;
             k.t0 = ta; k.t1 = tb; k.n_tiles = n_tiles;
-            int e = bmp_wgrad_panels(k, stream);
+            int e = push(k);
             if (e) return e;
         }
+        return BMP_OK;
+    };
+    auto msg_launch = [&](int tw, int ta, int tb) -> int {
+        // dW_m[c*E+e][:] += P_e^T h_t : C rows c with stride E*H, offset e*H; bias d_msg_b[c*E+e]
+        const bool pair_up = KP <= 3;              // two bond types (M tiles) per class while N = 64 KP fits 192 columns
+        for (int e = 0; e < 4; e += pair_up ? 2 : 1)
+            for (int mt = 0; mt < KP; mt += 2) {
+                w2::Args k = {};
+                k.A = S.Pp; k.a_ppt = 4 * KP; k.n_mt = pair_up ? 2 : 1;
+                for (int m = 0; m < 2; ++m) {
+                    const bool on = m < k.n_mt;
+                    k.a_panel[m][0] = on ? (e + m) * KP + mt : -1;
+                    k.a_panel[m][1] = on && mt + 1 < KP ? (e + m) * KP + mt + 1 : -1;
+                }
+                k.nb = KP;
+                for (int j = 0; j < KP; ++j) { k.B[j] = S.Xp; k.b_ppt[j] = KP; k.b_panel[j] = j; k.ldc[j] = 4 * H; }
+                for (int m = 0; m < k.n_mt; ++m)
+                    for (int bl = 0; bl < 2; ++bl) {
+                        if (k.a_panel[m][bl] < 0) continue;
+                        const long c0 = (long)(mt + bl) * 64;          // first channel c of this block
+                        for (int j = 0; j < KP; ++j) k.C[m][bl][j] = a->d_msg_W[tw] + (c0 * 4 + (e + m)) * H + j * 64;
+                        k.bias[m][bl] = a->d_msg_b[tw] ? a->d_msg_b[tw] + c0 * 4 + (e + m) : nullptr;
+                    }
+                k.bias_stride = 4;
+                k.t0 = ta; k.t1 = tb; k.n_tiles = n_tiles;
+                int e2 = push(k);
+                if (e2) return e2;
+            }
         return BMP_OK;
     };
     int t0 = 0;
@@ -712,33 +754,9 @@ int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
             while (s1 + 1 <= t1 && (a->stateful[s1 + 1] != 0) == st) ++s1;
             for (int g = st ? 0 : 1; g < 3; ++g)       // delta_r of a stateless step is identically zero
                 if ((rc = gate_launch(g, s0, s1, st, D))) return rc;
+            if (a->d_msg_W[t0] && (rc = msg_launch(t0, s0, s1))) return rc;
+            if ((rc = flush())) return rc;
             s0 = s1 + 1;
-        }
-        if (a->d_msg_W[t0]) {
-            // dW_m[c*E+e][:] += P_e^T h_t : C rows c with stride E*H, offset e*H; bias d_msg_b[c*E+e]
-            const bool pair_up = KP <= 3;              // two bond types (M tiles) per launch while N = 64 KP fits 192 columns
-            for (int e = 0; e < 4; e += pair_up ? 2 : 1)
-                for (int mt = 0; mt < KP; mt += 2) {
-                    w2::Args k = {};
-                    k.A = S.Pp; k.a_ppt = 4 * KP; k.n_mt = pair_up ? 2 : 1;
-                    for (int m = 0; m < 2; ++m) {
-                        const bool on = m < k.n_mt;
-                        k.a_panel[m][0] = on ? (e + m) * KP + mt : -1;
-                        k.a_panel[m][1] = on && mt + 1 < KP ? (e + m) * KP + mt + 1 : -1;
-                    }
-                    k.nb = KP;
-                    for (int j = 0; j < KP; ++j) { k.B[j] = S.Xp; k.b_ppt[j] = KP; k.b_panel[j] = j; k.ldc[j] = 4 * H; }
-                    for (int m = 0; m < k.n_mt; ++m)
-                        for (int bl = 0; bl < 2; ++bl) {
-                            if (k.a_panel[m][bl] < 0) continue;
-                            const long c0 = (long)(mt + bl) * 64;          // first channel c of this block
-                            for (int j = 0; j < KP; ++j) k.C[m][bl][j] = a->d_msg_W[t0] + (c0 * 4 + (e + m)) * H + j * 64;
-                            k.bias[m][bl] = a->d_msg_b[t0] ? a->d_msg_b[t0] + c0 * 4 + (e + m) : nullptr;
-                        }
-                    k.bias_stride = 4;
-                    k.t0 = t0; k.t1 = t1; k.n_tiles = n_tiles;
-                    if ((rc = bmp_wgrad_panels(k, stream))) return rc;
-                }
         }
         t0 = t1 + 1;
     }

@@ -424,7 +424,17 @@ struct Args {
     float *bias[2][2], *bias2[2][2];   // column sums of the A block (stride bias_stride) or NULL
     int bias_stride;
     int t0, t1, n_tiles;               // steps [t0, t1], tiles per step
-    long chunks_per_cta;               // filled by bmp_wgrad_panels
+    long chunks_per_cta;               // unused (kept for layout stability)
+};
+// Several contractions over the SAME (step, tile) range in ONE launch: the CTAs are split into classes (one Args each) in
+// proportion to the bytes a class reads per unit, and every class walks the units in the same strided order, so all classes
+// are on the same few units at the same time -- a panel that several classes need (h, m) comes from HBM once and from L2 for
+// the others.
+constexpr int MAX_CLASSES = 6;
+struct Multi {
+    Args cls[MAX_CLASSES];
+    int n;
+    int cta0[MAX_CLASSES + 1];         // class c owns CTAs [cta0[c], cta0[c+1])
 };
 }  // namespace w2
 }  // namespace bmp

@@ -21,7 +21,11 @@ constexpr int BLK = 64 * 128;          // 8 KB operand block
 constexpr int STAGES = 3;
 constexpr int NTH = 192;               // warps 0-3 epilogue, 4 TMA, 5 MMA
 
-__global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const Args a) {
+__global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const __grid_constant__ Multi mm) {
+    int ci = 0;
+    while (ci + 1 < mm.n && (int)blockIdx.x >= mm.cta0[ci + 1]) ++ci;
+    const Args &a = mm.cls[ci];
+    const long k0 = (long)blockIdx.x - mm.cta0[ci], kn = mm.cta0[ci + 1] - mm.cta0[ci];      // this CTA: units k0, k0 + kn, ...
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = s32(smem);
@@ -35,8 +39,6 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const Args a) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + STAGES * stage_bytes + BLK + 8 * (2 * STAGES + 1) + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long total = (long)(a.t1 - a.t0 + 1) * a.n_tiles * 2;
-    const long c_begin = (long)blockIdx.x * a.chunks_per_cta;
-    const long c_end = min(total, c_begin + a.chunks_per_cta);
     bool want_bias = false;
     for (int m = 0; m < 2; ++m)
         for (int b = 0; b < 2; ++b) want_bias |= a.bias[m][b] != nullptr || a.bias2[m][b] != nullptr;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const Args a) {
             uint32_t stage = 0, phase = 0;
             int nblk = NB;
             for (int m = 0; m < NMT; ++m) nblk += (a.a_panel[m][0] >= 0) + (a.a_panel[m][1] >= 0);
-            for (long c = c_begin; c < c_end; ++c) {
+            for (long c = k0; c < total; c += kn) {
                 const long tt = c / 2;                       // (step, tile) index
                 const int half = (int)(c & 1);
                 const long step = tt / a.n_tiles, tile = tt % a.n_tiles;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const Args a) {
                 return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(BLK >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
             };
             bool first = true;
-            for (long c = c_begin; c < c_end; ++c) {
+            for (long c = k0; c < total; c += kn) {
                 mbar_wait(FULL(stage), phase);
                 tc_fence_after();
                 const uint32_t s0 = sbase + stage * stage_bytes, sb = s0 + NA * BLK;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const Args a) {
     } else {
         mbar_wait(DONE, 0);
         tc_fence_after();
-        if (c_end > c_begin) {
+        if (k0 < total) {
             const int q = warp, blk = q >> 1, r = (q & 1) * 32 + lane;     // TMEM lane 32q+lane = A column = C row
             const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
             for (int m = 0; m < NMT; ++m) {
@@ -160,14 +162,19 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const Args a) {
 
 using namespace bmp;
 
-// One grouped contraction over the panel stash (see w2::Args in tc_common.cuh).  The caller fills the operand /
-// target description; t0, t1, n_tiles select the rows; chunks_per_cta is set here.
-int bmp_wgrad_panels(w2::Args &k, void *stream) {
-    if (!k.A || k.nb < 1 || k.nb > 6 || k.n_mt < 1 || k.n_mt > 2 || (k.n_mt == 2 && k.nb > 3)) {
-        set_error("bmp_wgrad_panels: bad arguments");
-        return BMP_EINVAL;
+// Grouped contractions over the panel stash (see w2::Args / w2::Multi in tc_common.cuh): n classes over the same (step, tile)
+// range in one launch.  The caller fills the operand / target descriptions; t0, t1, n_tiles must agree between the classes.
+int bmp_wgrad_panels_multi(w2::Args *list, int n, void *stream) {
+    if (n < 1 || n > w2::MAX_CLASSES) { set_error("bmp_wgrad_panels: %d classes (1..%d)", n, w2::MAX_CLASSES); return BMP_EINVAL; }
+    for (int c = 0; c < n; ++c) {
+        const w2::Args &k = list[c];
+        if (!k.A || k.nb < 1 || k.nb > 6 || k.n_mt < 1 || k.n_mt > 2 || (k.n_mt == 2 && k.nb > 3) || k.t0 != list[0].t0 ||
+            k.t1 != list[0].t1 || k.n_tiles != list[0].n_tiles) {
+            set_error("bmp_wgrad_panels: bad arguments");
+            return BMP_EINVAL;
+        }
     }
-    if (k.t1 < k.t0 || k.n_tiles <= 0) return BMP_OK;
+    if (list[0].t1 < list[0].t0 || list[0].n_tiles <= 0) return BMP_OK;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -175,20 +182,59 @@ int bmp_wgrad_panels(w2::Args &k, void *stream) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    const long total = (long)(k.t1 - k.t0 + 1) * k.n_tiles * 2;
-    long ctas = sms;
-    if (ctas > (total + 7) / 8) ctas = (total + 7) / 8;
-    if (ctas < 1) ctas = 1;
-    k.chunks_per_cta = (total + ctas - 1) / ctas;
-    ctas = (total + k.chunks_per_cta - 1) / k.chunks_per_cta;
-    const int smem = w2::STAGES * (2 * k.n_mt + k.nb) * w2::BLK + w2::BLK + 256 + 1024;
+    const long total = (long)(list[0].t1 - list[0].t0 + 1) * list[0].n_tiles * 2;
+    w2::Multi m = {};
+    m.n = n;
+    // CTAs per class in proportion to the 8 KB blocks a class loads per unit (all classes then advance at the same unit rate)
+    int blocks[w2::MAX_CLASSES], sum = 0, smem = 0;
+    for (int c = 0; c < n; ++c) {
+        int na = 0;
+        for (int mt = 0; mt < list[c].n_mt; ++mt) na += (list[c].a_panel[mt][0] >= 0) + (list[c].a_panel[mt][1] >= 0);
+        blocks[c] = na + list[c].nb;
+        sum += blocks[c];
+        const int need = w2::STAGES * (2 * list[c].n_mt + list[c].nb) * w2::BLK + w2::BLK + 256 + 1024;
+        smem = need > smem ? need : smem;
+    }
+    long budget = sms;
+    if (budget > (total + 7) / 8 * n) budget = (total + 7) / 8 * n;       // small problems: at least ~8 units per CTA
+    if (budget < n) budget = n;
+    // largest-remainder split of `budget` CTAs (never more than one wave: every CTA must be resident from the start)
+    long share[w2::MAX_CLASSES], rem[w2::MAX_CLASSES], given = 0;
+    for (int c = 0; c < n; ++c) {
+        share[c] = budget * blocks[c] / sum;
+        rem[c] = budget * blocks[c] % sum;
+        if (share[c] < 1) { share[c] = 1; rem[c] = -1; }
+        given += share[c];
+    }
+    while (given < budget) {
+        int best = 0;
+        for (int c = 1; c < n; ++c) if (rem[c] > rem[best]) best = c;
+        if (rem[best] < 0) break;
+        ++share[best]; rem[best] = -1; ++given;
+    }
+    while (given > budget) {          // the >= 1 floor overshot: take from the largest class
+        int big = 0;
+        for (int c = 1; c < n; ++c) if (share[c] > share[big]) big = c;
+        if (share[big] <= 1) break;
+        --share[big]; --given;
+    }
+    int used = 0;
+    for (int c = 0; c < n; ++c) {
+        long ctas = share[c] > total ? total : share[c];
+        m.cta0[c] = used;
+        used += (int)ctas;
+        m.cls[c] = list[c];
+    }
+    m.cta0[n] = used;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(w2::wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::STAGES * 8 * w2::BLK + w2::BLK + 256 + 1024);
         attr = true;
     }
     ProfScope prof(BMP_PROF_WGRAD, (cudaStream_t)stream);
-    w2::wgrad2_kernel<<<(unsigned)ctas, w2::NTH, smem, (cudaStream_t)stream>>>(k);
+    w2::wgrad2_kernel<<<(unsigned)used, w2::NTH, smem, (cudaStream_t)stream>>>(m);
     count_launch();
     return check_launch("wgrad2_kernel");
 }
+
+int bmp_wgrad_panels(w2::Args &k, void *stream) { return bmp_wgrad_panels_multi(&k, 1, stream); }

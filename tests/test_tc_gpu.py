@@ -561,3 +561,35 @@ def test_encoder_reads_a_drug_table_through_mol_index(H, cls):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for k in res[0][2]:
         np.testing.assert_allclose(res[0][2][k], res[1][2][k], rtol=1e-4, atol=1e-5 * max(1.0, float(np.abs(res[1][2][k]).max())), err_msg=k)
+
+
+def test_bf16_mode_trains_like_the_fp32_parity_path():
+    """Training equivalence of BMP_MODE_BF16 (was tools/convergence_check.py): the bench model at hidden 128 on 512 synthetic
+    pairs with learnable labels, 25 Adam steps at lr 1e-3 from identical parameters -- the loss trajectories of the tcgen05 path
+    and of the <= 1e-4-parity fp32 path stay within 1 % of each other at every step (measured: <= 0.4 %) and the loss goes down."""
+    import gcnbmp
+    from gcnbmp import synthetic, train
+    H, T, N, O, K, mb, STEPS = 128, 6, 64, 128, 86, 512, 25
+    rng = np.random.default_rng(2018)
+    a1, A1 = synthetic.random_molecules(rng, mb, N)
+    a2, A2 = synthetic.random_molecules(rng, mb, N)
+    cnt = (np.asarray(a1) == 8).sum(1) + (np.asarray(a2) == 7).sum(1)      # learnable: the class is a statistic of the pair
+    y = np.zeros((mb, K), np.int32)
+    y[np.arange(mb), cnt % K] = 1
+    args = [torch.tensor(x).cuda() for x in (a1, A1, a2, A2, y)]
+
+    def run(mode):
+        gcnbmp.seed(777)
+        enc = gcnbmp.GGNNMono(O, H, T)
+        attn = gcnbmp.NieFineCoattention(H, O, 8, activation=gcnbmp.functions.tanh)
+        head = gcnbmp.HolE(K, hidden_dims=())
+        head.l_out.ensure(O)
+        model = gcnbmp.GraphConvPredictorForPair(enc, attn, head)
+        enc.mode = attn.mode = mode
+        tr = train.PairTrainer(model, chunk=256, alpha=1e-3)
+        return [float(tr.step(*args)) for _ in range(STEPS)]
+
+    l32, lbf = run(gcnbmp.MODE_F32), run(gcnbmp.MODE_BF16)
+    worst = max(abs(a - b) / abs(a) for a, b in zip(l32, lbf))
+    assert worst <= 1e-2, (worst, l32[-1], lbf[-1])
+    assert l32[-1] < 0.5 * l32[0] and lbf[-1] < 0.5 * lbf[0]
