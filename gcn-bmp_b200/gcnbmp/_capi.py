@@ -45,6 +45,13 @@ class GgnnBwd(C.Structure):
         ("mol_index", fp)]
 
 
+class Bimpm(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "head")] + [
+        ("atoms_1", fp), ("atoms_2", fp), ("max_pooling_W", fp), ("att_mean_W", fp), ("att_max_W", fp),
+        ("out_1", fp), ("out_2", fp), ("d_out_1", fp), ("d_out_2", fp), ("d_atoms_1", fp), ("d_atoms_2", fp),
+        ("d_max_pooling_W", fp), ("d_att_mean_W", fp), ("d_att_max_W", fp), ("workspace", fp), ("workspace_bytes", C.c_size_t)]
+
+
 class RelgcnFwd(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n_atoms", "n_edge", "n_layers", "n_atom_types", "scale_adj", "act")] + [
         ("ch", C.c_int * (MAX_STEPS + 1)), ("atoms", fp), ("h_in", fp), ("embed_W", fp), ("adj", fp),
@@ -130,6 +137,8 @@ def _load():
         "bmp_atoms_pool_backward": [fp, i, fp, fp, fp, fp, i, i, i, vp],
         "bmp_gin_aggregate": [fp, fp, fp, i, i, i, i, i, vp],
         "bmp_nfp_gather": [fp, fp, fp, i, i, i, i, i, vp],
+        "bmp_bimpm_forward": [C.POINTER(Bimpm), vp],
+        "bmp_bimpm_backward": [C.POINTER(Bimpm), vp],
         "bmp_embed_forward": [fp, fp, fp, i, i, i, vp],
     }
     for name, args in sig.items():
@@ -140,6 +149,7 @@ def _load():
     lib.bmp_readout_tc_workspace_bytes.argtypes, lib.bmp_readout_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_coattn_tc_workspace_bytes.argtypes, lib.bmp_coattn_tc_workspace_bytes.restype = [i], C.c_size_t
     lib.bmp_relgcn_tc_workspace_bytes.argtypes, lib.bmp_relgcn_tc_workspace_bytes.restype = [i, i], C.c_size_t
+    lib.bmp_bimpm_workspace_bytes.argtypes, lib.bmp_bimpm_workspace_bytes.restype = [i, i, i, i, i], C.c_size_t
     lib.bmp_last_error.restype = C.c_char_p
     lib.bmp_version.restype = C.c_int
     lib.bmp_device_check.restype = C.c_int
@@ -157,7 +167,7 @@ EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_r
            "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
            "bmp_atoms_bcast_add_act_forward", "bmp_atoms_bcast_add_act_backward", "bmp_atoms_softmax_forward", "bmp_atoms_softmax_backward",
-           "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate", "bmp_nfp_gather", "bmp_embed_forward",
+           "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate", "bmp_nfp_gather", "bmp_embed_forward", "bmp_bimpm_forward", "bmp_bimpm_backward", "bmp_bimpm_workspace_bytes",
            "bmp_last_error", "bmp_version", "bmp_device_check", "bmp_launch_count", "bmp_reset_launch_count",
            "bmp_profile_enable", "bmp_profile_read"]
 

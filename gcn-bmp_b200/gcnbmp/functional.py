@@ -686,6 +686,49 @@ class GINAggregate(torch.autograd.Function):
         return dh, None
 
 
+class BiMPMMatch(torch.autograd.Function):
+    """models/coattention/bimpm.py:45-197 in one launch each way (csrc/bimpm.cu)."""
+
+    @staticmethod
+    def _args(a1, a2, Wm, Wa, Wx):
+        mb, N1, H = a1.shape
+        a = K.Bimpm()
+        a.mb, a.n1, a.n2, a.hidden, a.head = mb, N1, a2.shape[1], H, Wm.shape[0]
+        a.atoms_1, a.atoms_2 = _p(a1), _p(a2)
+        a.max_pooling_W, a.att_mean_W, a.att_max_W = _p(Wm), _p(Wa), _p(Wx)
+        n = int(K.lib.bmp_bimpm_workspace_bytes(mb, N1, a2.shape[1], H, Wm.shape[0]))
+        ws = torch.empty((max(n, 4),), device=a1.device, dtype=torch.uint8)
+        a.workspace, a.workspace_bytes = _p(ws), n
+        return a, ws
+
+    @staticmethod
+    def forward(ctx, a1, a2, Wm, Wa, Wx):
+        _need_cuda(a1, a2)
+        a1, a2, Wm, Wa, Wx = _f32(a1), _f32(a2), _f32(Wm), _f32(Wa), _f32(Wx)
+        if a1.shape[0] != a2.shape[0] or a1.shape[2] != a2.shape[2] or tuple(Wm.shape) != tuple(Wa.shape) != tuple(Wx.shape):
+            raise ValueError("gcnbmp: BiMPM shapes %s %s %s" % (tuple(a1.shape), tuple(a2.shape), tuple(Wm.shape)))
+        a, ws = BiMPMMatch._args(a1, a2, Wm, Wa, Wx)
+        o1 = torch.empty((a.mb, 3 * a.head), device=a1.device, dtype=torch.float32)
+        o2 = torch.empty_like(o1)
+        a.out_1, a.out_2 = _p(o1), _p(o2)
+        K.check(K.lib.bmp_bimpm_forward(C.byref(a), _stream()))
+        ctx.save_for_backward(a1, a2, Wm, Wa, Wx)
+        return o1, o2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        a1, a2, Wm, Wa, Wx = ctx.saved_tensors
+        a, ws = BiMPMMatch._args(a1, a2, Wm, Wa, Wx)
+        g1 = _f32(g1) if g1 is not None else torch.zeros((a.mb, 3 * a.head), device=a1.device)
+        g2 = _f32(g2) if g2 is not None else torch.zeros((a.mb, 3 * a.head), device=a1.device)
+        d1, d2 = torch.empty_like(a1), torch.empty_like(a2)
+        (gm, ga, gx), rets = _grad_targets([Wm, Wa, Wx])
+        a.d_out_1, a.d_out_2, a.d_atoms_1, a.d_atoms_2 = _p(g1), _p(g2), _p(d1), _p(d2)
+        a.d_max_pooling_W, a.d_att_mean_W, a.d_att_max_W = _p(gm), _p(ga), _p(gx)
+        K.check(K.lib.bmp_bimpm_backward(C.byref(a), _stream()))
+        return (d1, d2) + tuple(rets)
+
+
 class EmbedID(torch.autograd.Function):
     """EmbedAtomID forward as a stand-alone op (the GGNN / RelGCN encoders fuse it): W[ids]."""
 

@@ -634,6 +634,24 @@ class GIN(Link):
         return self.atoms
 
 
+class BiMPM(Link):
+    """models/coattention/bimpm.py:17-197 (`--attn bimpm`) -- bilateral multi-perspective matching with all three matchings and
+    aggr = F.sum (the only configuration the reference's scripts build, train_binary.py:255-256).  Returns two (mb, 3*head)
+    arrays; `out_dim` is unused, as in the reference; g_1 / g_2 are ignored."""
+
+    def __init__(self, hidden_dim, out_dim, head, with_max_pool=True, with_att_mean=True, with_att_max=True, aggr=None):
+        Link.__init__(self)
+        if not (with_max_pool and with_att_mean and with_att_max) or aggr not in (None, "sum"):
+            raise ValueError("gcnbmp.BiMPM implements the configuration train_binary.py:255-256 builds: all three matchings, aggr = F.sum")
+        for n in ("max_pooling_W", "att_mean_W", "att_max_W"):
+            self.add_param(n, (head, hidden_dim))
+        self.__dict__.update(hidden_dim=hidden_dim, out_dim=out_dim, head=head)
+
+    def __call__(self, atoms_1, g1, atoms_2, g2):
+        return Fn.BiMPMMatch.apply(_as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32),
+                                   self.max_pooling_W, self.att_mean_W, self.att_max_W)
+
+
 class NFPUpdate(Link):
     """models/models/nfp.py:15-59 -- one GraphLinear per atom degree 1..max_degree+1 (the NFP preprocessor's adjacency carries
     the self connection), applied to the neighbour sum of the atoms of that degree; sigmoid.  Every degree's bias reaches every

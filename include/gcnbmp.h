@@ -133,7 +133,7 @@ typedef struct {
     int    adj_u8;               /* BMP_MODE_BF16 only, storage of `adj`: 0 = fp32 (mb,E,N,N) as the reference; 1 = the same
                                    array as bytes (exact for 0/1 bonds; 1/4 of the PCIe / HBM traffic); 2 = bit-packed rows
                                    (mb,E,N,ceil(N/8)), bit j&7 of byte j>>3 = adj[i][j] (numpy.packbits little; 1/32)  */
-    const int32_t *mol_index;    /* as in bmp_ggnn_fwd_t (the adjacency table rows of the forward), or NULL              */
+    const int32_t *mol_index;    /* the forward's mol_index: adjacency table rows, or NULL                          */
 } bmp_ggnn_bwd_t;
 
 int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream);
@@ -375,6 +375,27 @@ int         bmp_version(void);
 int         bmp_device_check(void);           /* BMP_OK iff current device is sm_100 */
 uint64_t    bmp_launch_count(void);           /* kernels launched by this library    */
 void        bmp_reset_launch_count(void);
+
+/* ---- BiMPM matching co-attention ---------------------------------------------
+ * replaces models/coattention/bimpm.py:17-197 (`--attn bimpm`, train_binary.py:253-256) with all three matchings on
+ * (max-pooling, attentive, max-attentive) and aggr = F.sum: out_k (mb, 3*head) = [max-pool | att-mean | att-max] matching
+ * vectors summed over the atoms of drug k.  As in the reference, mp_matching_func keeps column 0 of its head x head product
+ * (perspective k of an atom against perspective 0 of its attentive vector).  fp32; N1, N2 <= 64; head * hidden <= 16384.
+ * backward: d_atoms_k are overwritten, the three weight gradients accumulated (+=).  `workspace`: bmp_bimpm_workspace_bytes. */
+typedef struct {
+    int mb, n1, n2, hidden, head;
+    const float *atoms_1, *atoms_2;                              /* (mb,N1,H), (mb,N2,H) */
+    const float *max_pooling_W, *att_mean_W, *att_max_W;         /* (head,H) each        */
+    float *out_1, *out_2;                                        /* forward: (mb,3*head) */
+    const float *d_out_1, *d_out_2;                              /* backward inputs      */
+    float *d_atoms_1, *d_atoms_2;
+    float *d_max_pooling_W, *d_att_mean_W, *d_att_max_W;         /* may be NULL          */
+    void  *workspace;
+    size_t workspace_bytes;
+} bmp_bimpm_t;
+size_t bmp_bimpm_workspace_bytes(int mb, int n1, int n2, int hidden, int head);
+int bmp_bimpm_forward(const bmp_bimpm_t *a, void *stream);
+int bmp_bimpm_backward(const bmp_bimpm_t *a, void *stream);
 
 /* ---- NFP encoder pieces (models/models/nfp.py) ------------------------------
  * EmbedAtomID forward (the GGNN / RelGCN encoders fuse this gather): out[r,:] = embed_W[clamp(atoms[r]), :].

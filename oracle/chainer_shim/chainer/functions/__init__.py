@@ -21,12 +21,28 @@ fft, ifft, linear, bilinear, sigmoid_cross_entropy = _M.fft, _M.ifft, _M.linear,
 linear_interpolate, embed_id, where = _M.linear_interpolate, _M.embed_id, _M.where
 
 
+def stack(xs, axis=0):
+    return _M.stack(xs, axis=axis)
+
+
+def max(x, axis=None, keepdims=False):  # noqa: A001 (chainer's name)
+    return _M.max_(_M.as_var(x), axis=axis, keepdims=keepdims)
+
+
+maximum = _M.maximum
+
+
+def normalize(x, eps=1e-5, axis=1):
+    return _M.normalize(_M.as_var(x), eps=eps, axis=axis)
+
+
 def concat(xs, axis=1):
     return _M.concat(tuple(_M.as_var(x) for x in xs), axis=axis)
 
 
-def sum(x, axis=None):  # noqa: A001 (chainer's name)
-    return _M.sum_(_M.as_var(x), axis=axis)
+def sum(x, axis=None, keepdims=False):  # noqa: A001 (chainer's name)
+    y = _M.sum_(_M.as_var(x), axis=axis)
+    return _M.expand_dims(y, axis) if keepdims and axis is not None else y
 
 
 def mean(x, axis=None):

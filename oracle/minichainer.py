@@ -267,6 +267,47 @@ def mean(x, axis):
                lambda g: ((np.broadcast_to(np.expand_dims(g, axis), x.shape) / n).astype(x.dtype),))
 
 
+def stack(xs, axis=0):
+    """functions.stack."""
+    xs = tuple(as_var(x) for x in xs)
+    return Var(np.stack([v.data for v in xs], axis=axis), xs,
+               lambda g: tuple(np.take(g, i, axis=axis) for i in range(len(xs))))
+
+
+def max_(x, axis=None, keepdims=False):
+    """functions.max: the gradient goes to EVERY position that equals the maximum (chainer's `cond = x == y`), undivided."""
+    y = x.data.max(axis=axis, keepdims=True)
+    cond = (x.data == y)
+    out = y if keepdims else np.squeeze(y, axis=axis)
+
+    def push(g):
+        gk = g if keepdims else np.expand_dims(g, axis)
+        return ((cond * gk).astype(x.dtype),)
+    return Var(out, (x,), push)
+
+
+def maximum(a, b):
+    """functions.maximum: gradient to `a` where a >= b, to `b` elsewhere."""
+    a, b = as_var(a), as_var(b)
+    cond = a.data >= b.data
+    return Var(np.maximum(a.data, b.data), (a, b),
+               lambda g: (_unbroadcast(np.where(cond, g, 0), a.shape), _unbroadcast(np.where(cond, 0, g), b.shape)))
+
+
+def normalize(x, eps=1e-5, axis=1):
+    """functions.normalize: x / (||x||_2 + eps) along `axis` (the epsilon is added to the norm, chainer v2+)."""
+    n = np.sqrt((x.data * x.data).sum(axis=axis, keepdims=True))
+    s = 1.0 / (n + eps)
+    y = x.data * s
+
+    def push(g):
+        dot = (x.data * g).sum(axis=axis, keepdims=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            corr = np.where(n > 0, x.data * dot * s * s / n, 0.0)
+        return ((g * s - corr).astype(x.dtype),)
+    return Var(y.astype(x.dtype, copy=False), (x,), push)
+
+
 # ---- contractions -----------------------------------------------------------
 def matmul(a, b):
     """functions.matmul on >=2-D operands (batched over leading axes)."""

@@ -639,6 +639,71 @@ def gin_shapes(out_dim, hidden_dim, n_layers, concat_hidden=False, weight_tying=
 
 
 # ----------------------------------------------------------------------------
+# models/coattention/bimpm.py:17-197 -- bilateral multi-perspective matching (--attn bimpm, train_binary.py:253-256)
+# ----------------------------------------------------------------------------
+class BiMPM(object):
+    """Restated op by op, including what the file actually computes rather than what its comments say: `mp_matching_func`
+    multiplies (head x hidden) by (hidden x head) and keeps COLUMN 0 (:79-81), i.e. perspective k of v1 is matched against
+    perspective 0 of v2; `out_dim` is unused (the output has num_match * head columns)."""
+
+    def __init__(self, p, hidden_dim, out_dim, head, with_max_pool=True, with_att_mean=True, with_att_max=True):
+        self.p, self.hidden_dim, self.head = p, hidden_dim, head
+        self.flags = (with_max_pool, with_att_mean, with_att_max)
+
+    def _match(self, v1, v2, w):                                                       # :50-82
+        mb, n1, _ = v1.shape
+        wt = F.expand_dims(F.expand_dims(F.transpose(w, (1, 0)), 0), 0)               # (1,1,hidden,head)
+        tw = F.tile(wt, (mb, n1, 1, 1))
+        a = F.mul(tw, F.stack([v1] * self.head, axis=3))
+        b = F.mul(tw, F.stack([v2] * self.head, axis=3))
+        sim = F.matmul(F.transpose(F.normalize(a, axis=2), (0, 1, 3, 2)), F.normalize(b, axis=2))
+        return F.getitem(sim, (slice(None), slice(None), slice(None), 0))
+
+    def _match_pairwise(self, v1, v2, w):                                              # :84-108
+        mb, n1, _ = v1.shape
+        n2 = v2.shape[1]
+        we = F.expand_dims(F.expand_dims(w, 0), 2)                                     # (1,head,1,hidden)
+        a = F.mul(F.tile(we, (mb, 1, n1, 1)), F.stack([v1] * self.head, axis=1))
+        b = F.mul(F.tile(we, (mb, 1, n2, 1)), F.stack([v2] * self.head, axis=1))
+        sim = F.matmul(F.normalize(a, axis=3), F.transpose(F.normalize(b, axis=3), (0, 1, 3, 2)))
+        return F.transpose(sim, (0, 2, 3, 1))                                          # (mb,N1,N2,head)
+
+    @staticmethod
+    def _div(n, d, eps=1e-4):                                                          # :125-127
+        dd = F.maximum(d, np.ones_like(d.data) * eps)
+        return F.div(n, F.Var(np.broadcast_to(dd.data, n.shape).copy(), (dd,), lambda g: (F._unbroadcast(g, dd.shape),)))
+
+    def __call__(self, atoms_1, g1, atoms_2, g2):
+        atoms_1, atoms_2 = F.as_var(atoms_1), F.as_var(atoms_2)
+        mb, n1, _ = atoms_1.shape
+        n2 = atoms_2.shape[1]
+        with_max_pool, with_att_mean, with_att_max = self.flags
+        mv1, mv2 = [], []
+        if with_max_pool:                                                              # :136-146
+            mv = self._match_pairwise(atoms_1, atoms_2, self.p["max_pooling_W"])
+            mv1.append(F.max_(mv, axis=2))
+            mv2.append(F.max_(mv, axis=1))
+        if with_att_mean or with_att_max:                                              # :148-160
+            att = F.matmul(F.normalize(atoms_1, axis=2), F.transpose(F.normalize(atoms_2, axis=2), (0, 2, 1)))
+            att_e = F.tile(F.expand_dims(att, 3), (1, 1, 1, self.hidden_dim))
+            att_atoms2 = F.mul(F.tile(F.expand_dims(atoms_2, 1), (1, n1, 1, 1)), att_e)
+            att_atoms1 = F.mul(F.tile(F.expand_dims(atoms_1, 2), (1, 1, n2, 1)), att_e)
+            if with_att_mean:                                                          # :162-172
+                m2 = self._div(F.sum_(att_atoms2, axis=2), F.expand_dims(F.sum_(att, axis=2), 2))
+                m1 = self._div(F.sum_(att_atoms1, axis=1), F.transpose(F.expand_dims(F.sum_(att, axis=1), 1), (0, 2, 1)))
+                mv1.append(self._match(atoms_1, m2, self.p["att_mean_W"]))
+                mv2.append(self._match(atoms_2, m1, self.p["att_mean_W"]))
+            if with_att_max:                                                           # :174-186
+                mv1.append(self._match(atoms_1, F.max_(att_atoms2, axis=2), self.p["att_max_W"]))
+                mv2.append(self._match(atoms_2, F.max_(att_atoms1, axis=1), self.p["att_max_W"]))
+        return F.sum_(F.concat(mv1, axis=2), axis=1), F.sum_(F.concat(mv2, axis=2), axis=1)     # :188-197 (aggr = F.sum)
+
+
+def bimpm_shapes(hidden_dim, head):
+    return {"max_pooling_W": (head, hidden_dim), "att_mean_W": (head, hidden_dim), "att_max_W": (head, hidden_dim)}
+
+
+# ----------------------------------------------------------------------------
 # models/models/nfp.py:15-181 -- Neural Fingerprint encoder (SURVEY 8 f-4; the default --method of train_binary.py:319)
 # ----------------------------------------------------------------------------
 class NFPUpdate(object):

@@ -54,6 +54,7 @@ ref_global = load("ref_global", "models/coattention/global_coattention.py")
 ref_neural = load("ref_neural", "models/coattention/neural_coattention.py")
 ref_gin = load("ref_gin", "models/gin.py")
 ref_nfp = load("ref_nfp", "models/models/nfp.py")
+ref_bimpm = load("ref_bimpm", "models/coattention/bimpm.py")
 ref_hole = load("ref_hole", "models/link_prediction/hole.py")
 ref_mlp = load("ref_mlp", "models/mlp.py")
 ref_mono = {"ggnn_py": load("ref_ggnn_py", "models/ggnn.py"), "ggnn_att": load("ref_ggnn_att", "models/ggnn_att.py"),
@@ -259,6 +260,20 @@ def main():
         o_out, o_gin = run(both(R.NFP(R.P(tab), O, H, T)), [], ws)
         check_and_save(tag, params, [atoms], [adj], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab),
                        dict(kind="nfp", H=H, O=O, T=T))
+    # ---- BiMPM (models/coattention/bimpm.py): all three matchings; N1 != N2; outputs have 3 * head columns
+    bi_rng = np.random.default_rng(20190516)
+    for tag, mb, N1, N2, H, head in (("bimpm", 3, 6, 9, 12, 4), ("bimpm_wide", 2, 11, 7, 20, 5)):
+        a1, a2 = bi_rng.standard_normal((mb, N1, H)) * 0.7, bi_rng.standard_normal((mb, N2, H)) * 0.7
+        params = R.init_params(R.bimpm_shapes(H, head), bi_rng, dtype=np.float64)
+        ws = [bi_rng.standard_normal((mb, 3 * head)), bi_rng.standard_normal((mb, 3 * head))]
+        net = ref_bimpm.BiMPM(H, 8, head)
+        load_params(net, params)
+        r_out, r_gin = run(lambda x1, x2: net(x1, None, x2, None), [a1, a2], ws)
+        tab = R.wrap_params(params)
+        onet = R.BiMPM(R.P(tab), H, 8, head)
+        o_out, o_gin = run(lambda x1, x2: onet(x1, None, x2, None), [a1, a2], ws)
+        check_and_save(tag, params, [], [a1, a2], ws, r_out, r_gin, grads_of_link(net), o_out, o_gin, ora_grads(tab),
+                       dict(kind="coattn_bimpm", H=H, O=8, head=head))
     # ---- bare GGNNUpdate with state threading (two calls, then reset, then one call)
     H, mb, N = 8, 2, 7
     _, adj = random_molecules(rng, mb, N)

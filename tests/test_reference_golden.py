@@ -80,6 +80,9 @@ def _oracle_fn(fx, tab):
                "coattn_para": lambda: R.ParallelCoattention(P, m["H"], m["O"], m["head"]),
                "coattn_circ": lambda: R.CircularParallelCoattention(P, m["H"], m["O"])}[kind]()
         return lambda a1, a2, g1, g2: cls(a1, g1, a2, g2)
+    if kind == "coattn_bimpm":
+        net = R.BiMPM(P, m["H"], m["O"], m["head"])
+        return lambda a1, a2: net(a1, None, a2, None)
     if kind.startswith("coattn"):
         cls = {"coattn_nie": lambda: R.NieFineCoattention(P, m["H"], m["O"], m["head"], activation="tanh"),
                "coattn_vqa": lambda: R.VQAParallelCoattention(P, m["H"], m["O"], m["head"]),
@@ -139,7 +142,7 @@ def test_oracle_reproduces_reference_generated_fixture(name):
 def test_fixture_set_covers_every_hot_path_file():
     kinds = {_load(n)["meta"]["kind"] for n in NAMES}
     assert {"ggnn", "mono", "ggnn_update", "relgcn", "coattn_nie", "coattn_vqa", "coattn_pool", "readout", "head_hole",
-            "head_hole_mlp_py", "head_mlp", "head_symmlp", "head_ntn", "head_distmult", "nfp"} <= kinds
+            "head_hole_mlp_py", "head_mlp", "head_symmlp", "head_ntn", "head_distmult", "nfp", "coattn_bimpm"} <= kinds
 
 
 def _pair_fixture(name):
@@ -226,6 +229,9 @@ def _product(fx):
                "coattn_para": lambda: gcnbmp.ParallelCoattention(m["H"], m["O"], m["head"]),
                "coattn_circ": lambda: gcnbmp.CircularParallelCoattention(m["H"], m["O"])}[kind]()
         return (lambda a1, a2, g1, g2: net(a1, g1, a2, g2)), net
+    if kind == "coattn_bimpm":
+        net = gcnbmp.BiMPM(m["H"], m["O"], m["head"])
+        return (lambda a1, a2: net(a1, None, a2, None)), net
     if kind.startswith("coattn"):
         net = {"coattn_nie": lambda: gcnbmp.NieFineCoattention(m["H"], m["O"], m["head"], activation=f.tanh),
                "coattn_vqa": lambda: gcnbmp.VQAParallelCoattention(m["H"], m["O"], m["head"]),

@@ -21,7 +21,7 @@ head = gcnbmp.HolE(K, hidden_dims=())
 head.l_out.ensure(O)        # lazily-shaped layer: materialise before the trainer flattens the parameters
 model = gcnbmp.GraphConvPredictorForPair(enc, attn, head)
 enc.mode = attn.mode = gcnbmp.MODE_BF16
-tr = train.PairTrainer(model, chunk=2048)
+tr = train.PairTrainer(model, chunk=min(mb, 4144))
 dev = lambda x: torch.tensor(x).cuda()
 args = [dev(a1), dev(A1), dev(a2), dev(A2), dev(y)]
 for i in range(3):
