@@ -93,3 +93,15 @@ def test_workspace_size_queries_are_host_only_and_consistent():
         assert lib.bmp_relgcn_tc_workspace_bytes(H, 4) == 0
         assert lib.bmp_coattn_tc_workspace_bytes(H) == 0
         assert lib.bmp_ggnn_stash2_bytes(64, H, 6) == 0
+
+
+def test_chainer_adapter_is_import_guarded():
+    """the Chainer / CuPy adapter imports without either package and fails loudly, not silently, when used."""
+    from gcnbmp import chainer_adapter as B
+    if B.AVAILABLE:          # a Chainer-equipped process: nothing to guard
+        return
+    import pytest
+    with pytest.raises(ImportError):
+        B.ggnn_encode(None, None, None)
+    with pytest.raises(ImportError):
+        B.GGNNEncode(None, None, [], 0, 0)
