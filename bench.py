@@ -171,7 +171,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     gcnbmp._capi.check(gcnbmp._capi.lib.bmp_device_check())
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a desynchronised collective must fail in minutes, not hold N GPUs for NCCL's default ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local)
     n_local = args.pairs // world
     model = build_model(args.mode)
@@ -272,12 +274,15 @@ def run_gpu(args):
     fl = algorithmic_flops(CFG["H"], CFG["T"], CFG["N"], CFG["E"], CFG["O"], CFG["head"], CFG["K"])
     roof = roof_kernels = None
     pk = peaks()
-    if rank == 0 and bf16:
-        gcnbmp._capi.profile_read()
-        gcnbmp._capi.profile_enable(True)
+    if bf16:
+        # every rank runs the step (it holds the allreduce); rank 0 alone brackets its launches with events
+        if rank == 0:
+            gcnbmp._capi.profile_read()
+            gcnbmp._capi.profile_enable(True)
         trainer.step(*resident, global_count=gcount)
         torch.cuda.synchronize()
         gcnbmp._capi.profile_enable(False)
+    if rank == 0 and bf16:
         prof = gcnbmp._capi.profile_read()
         n_mol = 2 * n_local
         enc_flop = fl["encoder_steps"]                     # per molecule, message passing only (the readout is its own launch)
