@@ -71,8 +71,14 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
     const uint32_t s_bar = sbase + C::OFF_BAR;
     // barriers (8 bytes each)
     auto BAR = [&](int i) { return s_bar + 8u * i; };
-    constexpr int B_FULL = 0, B_EMPTY = 4, B_HREADY = 8, B_D1 = 9, B_AHREADY = 13, B_AHFREE = 15, B_M = 16,
-                  B_XREADY = 17, B_R = 18, B_RSREADY = 19, B_ZH = 20, NBAR = 21;
+    // AH slots: the AH buffer (one bond-type pair = 2KP panels) is handed over in KP slots of two panels (both bond types of
+    // a 64-column block), so the conversion of the next slot overlaps the UMMAs on the previous one
+    constexpr int B_FULL = 0, B_EMPTY = 4, B_HREADY = 8, B_D1 = 9, B_AHREADY = 13, B_AHFREE = 15, B_M = 17,
+                  B_XREADY = 18, B_R = 19, B_RSREADY = 20, B_ZH = 21, NBAR = 22;
+    // TMEM columns: [0,H) m ; [H,2H) r ; [2H,3H) z ; [3H,4H) hbar.  The two AH accumulators of a bond-type pair (one per
+    // molecule) use [2H,4H) -- z / hbar of the previous step are consumed by then -- for p = 0 and again for p = 1, so the
+    // message accumulator m never overlaps an AH accumulator that is still being read.
+    static_assert(KP <= 2, "two AH slots");
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::OFF_BAR + 8 * NBAR + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -82,10 +88,11 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
     if (tid == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
         mbar_init(BAR(B_HREADY), EPW);
-        for (int i = 0; i < 4; ++i) mbar_init(BAR(B_D1 + i), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(BAR(B_D1 + i), 1);
         mbar_init(BAR(B_AHREADY), EPW);
         mbar_init(BAR(B_AHREADY + 1), EPW);
         mbar_init(BAR(B_AHFREE), 1);
+        mbar_init(BAR(B_AHFREE + 1), 1);
         mbar_init(BAR(B_M), 1);
         mbar_init(BAR(B_XREADY), EPW);
         mbar_init(BAR(B_R), 1);
@@ -148,24 +155,30 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                         tma_bulk_s2g(a.st.Xp + ((size_t)t * n_tiles + tile) * KP * PANEL_BYTES, s_h, KP * PANEL_BYTES);
                         bulk_commit();
                     }
-                    // MMA-1: D1[(mol,p)] = [A_2p ; A_2p+1](mol) x h(mol)   (B MN-major from the h panels)
-                    for (int p = 0; p < 2; ++p)
+                    // MMA-1: D1[mol] = [A_2p ; A_2p+1](mol) x h(mol)   (B MN-major from the h panels), p = 0 now, p = 1 as soon as
+                    // the epilogue has read the p = 0 accumulators
+                    auto mma1 = [&](int p) {
                         for (int mol = 0; mol < 2; ++mol) {
                             const uint32_t a_addr = s_adj + (mol * 4 + 2 * p) * ADJ_TILE_BYTES;
                             const uint32_t b_addr = s_h + mol * 64 * 128;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                tc_mma(tmem + (2 * p + mol) * H, desc_kmajor(a_addr + k * 32),
+                                tc_mma(tmem + (2 + mol) * H, desc_kmajor(a_addr + k * 32),
                                        desc_mnmajor(b_addr + k * 16 * 128), ID_KMN, k ? 1u : 0u);
-                            tc_commit(BAR(B_D1 + 2 * p + mol));
+                            tc_commit(BAR(B_D1 + mol));
                         }
-                    // MMA-2: m = AHcat Wcat^T, in two K halves (the AH buffer holds one half)
-                    for (int p = 0; p < 2; ++p) {
-                        mbar_wait(BAR(B_AHREADY + p), par);
-                        tc_fence_after();
-                        for (int kp = 0; kp < 2 * KP; ++kp) mma_wtile(s_ah + kp * PANEL_BYTES, 0, p == 0 && kp == 0);
-                        tc_commit(BAR(p == 0 ? B_AHFREE : B_M));
-                    }
+                    };
+                    mma1(0);
+                    // MMA-2: m = AHcat Wcat^T, slot by slot: (bond-type pair p, 64-column block cp) = two K blocks of 64
+                    for (int p = 0; p < 2; ++p)
+                        for (int cp = 0; cp < KP; ++cp) {
+                            mbar_wait(BAR(B_AHREADY + cp), p);          // every slot barrier completes twice per step
+                            tc_fence_after();
+                            if (p == 0 && cp == KP - 1) mma1(1);        // both p = 0 accumulators have been read completely
+                            for (int ein = 0; ein < 2; ++ein) mma_wtile(s_ah + (ein * KP + cp) * PANEL_BYTES, 0, p == 0 && cp == 0 && ein == 0);
+                            tc_commit(BAR(B_AHFREE + cp));
+                            if (p == 1 && cp == KP - 1) tc_commit(BAR(B_M));
+                        }
                     // MMA-3: gates over x = [h | m]
                     mbar_wait(BAR(B_XREADY), par);
                     tc_fence_after();
@@ -331,30 +344,47 @@ __global__ void __launch_bounds__(32 * (H / 8 + 2), 1) ggnn_tc_kernel(const Args
                     if (a.atoms && !a.midx && tid < 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.atoms + (long)(tile + gridDim.x) * 2 * a.N + tid * 32));
                 }
                 uint32_t v[32];
-                // ---- E1: AH accumulators -> bf16 A-operand panels (two K halves) ----
-                for (int p = 0; p < 2; ++p) {
-                    if (p == 1) mbar_wait(BAR(B_AHFREE), par);      // MMA-2 of half 0 has consumed the buffer
-                    for (int mol = 0; mol < 2; ++mol) {
-                        mbar_wait(BAR(B_D1 + 2 * p + mol), par);
-                        tc_fence_after();
-                        const int orow = mol * 64 + atom;           // row of (mol, atom) in the 128-row tile
-                        const int kbase = molslot * H + colbase;    // TMEM lane half = bond type within the pair
+                // ---- E1: AH accumulators -> bf16 A-operand panels, one slot (64-column block of both bond types) at a time ----
+                {
+                    constexpr int W1 = 2048 / H;                   // columns per warp within a 64-column slot: 16 (H = 128) or 32 (H = 64)
+                    const int cg = hf;                             // column group of this warp inside the slot
+                    for (int p = 0; p < 2; ++p)
+                        for (int cp = 0; cp < KP; ++cp) {
+                            // the slot's previous use (same step, p - 1; or the previous step's p = 1) has been consumed by MMA-2
+                            if (it > 0 || p > 0) mbar_wait(BAR(B_AHFREE + cp), p ^ 1u);
+                            for (int mol = 0; mol < 2; ++mol) {
+                                if (cp == 0) mbar_wait(BAR(B_D1 + mol), p);
+                                tc_fence_after();
+                                const int orow = mol * 64 + atom;  // row of (mol, atom) in the 128-row tile; TMEM lane half = bond type
+                                uint8_t *pan = smem + C::OFF_AH + (molslot * KP + cp) * PANEL_BYTES;
+                                const uint32_t tcol = t_lane + (2 + mol) * H + 64 * cp + cg * W1;
+                                if (W1 == 16) {
+                                    uint32_t w[16];
+                                    tc_ld16(tcol, w);
+                                    tc_wait_ld();
 #pragma unroll
-                        for (int cc = 0; cc < NC; cc += 32) {
-                            tc_ld32(t_lane + (2 * p + mol) * H + colbase + cc, v);
-                            tc_wait_ld();
+                                    for (int g = 0; g < 2; ++g) {
+                                        uint4 pk = make_uint4(pack_bf16(__uint_as_float(w[8 * g]), __uint_as_float(w[8 * g + 1])),
+                                                              pack_bf16(__uint_as_float(w[8 * g + 2]), __uint_as_float(w[8 * g + 3])),
+                                                              pack_bf16(__uint_as_float(w[8 * g + 4]), __uint_as_float(w[8 * g + 5])),
+                                                              pack_bf16(__uint_as_float(w[8 * g + 6]), __uint_as_float(w[8 * g + 7])));
+                                        *reinterpret_cast<uint4 *>(pan + sw128(orow, cg * W1 + 8 * g)) = pk;
+                                    }
+                                } else {
+                                    tc_ld32(tcol, v);
+                                    tc_wait_ld();
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const int kk = kbase + cc + 8 * g;
-                                uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
-                                                      pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                                                      pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                                                      pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                                *reinterpret_cast<uint4 *>(smem + C::OFF_AH + (kk >> 6) * PANEL_BYTES + sw128(orow, kk & 63)) = pk;
+                                    for (int g = 0; g < 4; ++g) {
+                                        uint4 pk = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                                              pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                                              pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                                              pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                                        *reinterpret_cast<uint4 *>(pan + sw128(orow, cg * W1 + 8 * g)) = pk;
+                                    }
+                                }
                             }
+                            warp_arrive(BAR(B_AHREADY + cp), lane);
                         }
-                    }
-                    warp_arrive(BAR(B_AHREADY + p), lane);      // one hand-off per K half (both molecules written)
                 }
                 // ---- E2: message m (+ bias through the degrees) -> bf16 operand (AH panels [0,KP)) ----
                 TSF(1);
@@ -512,8 +542,8 @@ __global__ void pack_kernel(const PackArgs p) {
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int k = idx & 63, n = (idx >> 6) % H, tile = (int)(idx / (64L * H));
         float w;
-        if (tile < t_msg) {                       // K index = e*H + c'
-            const int K = tile * 64 + k, e = K / H, cp = K % H;
+        if (tile < t_msg) {                       // consumption order (pair p, 64-column block cb, bond type in the pair): K = e*H + c'
+            const int pr = tile / (2 * KP), rem = tile % (2 * KP), cb = rem / 2, e = 2 * pr + (rem & 1), cp = cb * 64 + k;
             w = p.msg_W[((long)n * 4 + e) * H + cp];
         } else {
             int g = (tile - t_msg) / t_gate, kp = (tile - t_msg) % t_gate;

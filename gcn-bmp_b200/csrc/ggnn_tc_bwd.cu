@@ -644,7 +644,7 @@ int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream) {
     return check_launch("ggnn_tc_bwd_kernel");
 }
 
-int bmp_wgrad_panels_multi(bmp::w2::Args *list, int n, void *stream, void *counters);   // wgrad_tc2.cu
+int bmp_wgrad_panels_multi(bmp::w2::Args *list, int n, void *stream);   // wgrad_tc2.cu
 
 // Backward over the bf16 panel stash (stash v2): data kernel, then every parameter gradient as a
 // C += A^T B contraction whose operands are streamed straight from the dumped panels.
@@ -664,7 +664,7 @@ int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream) {
     w2::Args cls[w2::MAX_CLASSES];
     int ncls = 0;
     auto flush = [&]() -> int {
-        int e = ncls ? bmp_wgrad_panels_multi(cls, ncls, stream, S.tail(H)) : BMP_OK;
+        int e = ncls ? bmp_wgrad_panels_multi(cls, ncls, stream) : BMP_OK;
         ncls = 0;
         return e;
     };

@@ -403,11 +403,7 @@ struct Stash2 {
     __host__ __device__ uint8_t *zn(int t, long tile, int a, int H) const {
         return Zn + (((size_t)t * n_tiles + tile) * 4 + a) * ((size_t)128 * H * 2);
     }
-    // >= 2 KB of slack behind the last gate block (bytes() reserves 4 KB, carve() spends < 1 KB on alignment): small counters
-    __host__ __device__ uint8_t *tail(int H) const {
-        uint8_t *e = Zn + (size_t)T * n_tiles * 4 * ((size_t)128 * H * 2);
-        return (uint8_t *)(((uintptr_t)e + 127) & ~(uintptr_t)127);
-    }
+
 };
 
 }  // namespace tc
@@ -440,8 +436,6 @@ struct Multi {
     Args cls[MAX_CLASSES];
     int n;
     int cta0[MAX_CLASSES + 1];         // class c owns CTAs [cta0[c], cta0[c+1])
-    unsigned long long *progress;      // optional, zeroed before the launch: units loaded so far, per class (lockstep throttle)
-    int window;                        // a class may run at most this many units ahead of the slowest one
 };
 }  // namespace w2
 }  // namespace bmp

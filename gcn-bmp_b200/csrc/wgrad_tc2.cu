@@ -68,20 +68,7 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const __grid_constant__ 
             uint32_t stage = 0, phase = 0;
             int nblk = NB;
             for (int m = 0; m < NMT; ++m) nblk += (a.a_panel[m][0] >= 0) + (a.a_panel[m][1] >= 0);
-            long allowed = mm.progress ? 0 : total;      // units below this position may be loaded without asking again
             for (long c = k0; c < total; c += kn) {
-                // Lockstep throttle: the classes share the h / m panels through L2 only while they are on the same units.  A class
-                // that is ahead of the slowest one by more than `window` units waits (bounded: after ~2 ms it goes on regardless,
-                // so a stalled neighbour can cost bandwidth but never a hang).
-                for (int spin = 0; c >= allowed && spin < 4096; ++spin) {
-                    unsigned long long mn = ~0ull;
-                    for (int cc = 0; cc < mm.n; ++cc) {
-                        const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(mm.progress + cc);
-                        mn = v < mn ? v : mn;
-                    }
-                    allowed = (long)mn + mm.window;
-                    if (c >= allowed) __nanosleep(200);
-                }
                 const long tt = c / 2;                       // (step, tile) index
                 const int half = (int)(c & 1);
                 const long step = tt / a.n_tiles, tile = tt % a.n_tiles;
@@ -95,7 +82,6 @@ __global__ void __launch_bounds__(NTH, 1) wgrad2_kernel(const __grid_constant__ 
                             tma_bulk_g2s(dst + (2 * m + b) * BLK, a.A + (tbase * a.a_ppt + a.a_panel[m][b]) * (long)PANEL_BYTES + half * BLK, BLK, FULL(stage));
                 for (int j = 0; j < NB; ++j)
                     tma_bulk_g2s(dst + (NA + j) * BLK, a.B[j] + (tbase * a.b_ppt[j] + a.b_panel[j]) * (long)PANEL_BYTES + half * BLK, BLK, FULL(stage));
-                if (mm.progress) atomicAdd(mm.progress + ci, 1ull);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -178,7 +164,7 @@ using namespace bmp;
 
 // Grouped contractions over the panel stash (see w2::Args / w2::Multi in tc_common.cuh): n classes over the same (step, tile)
 // range in one launch.  The caller fills the operand / target descriptions; t0, t1, n_tiles must agree between the classes.
-int bmp_wgrad_panels_multi(w2::Args *list, int n, void *stream, void *counters) {
+int bmp_wgrad_panels_multi(w2::Args *list, int n, void *stream) {
     if (n < 1 || n > w2::MAX_CLASSES) { set_error("bmp_wgrad_panels: %d classes (1..%d)", n, w2::MAX_CLASSES); return BMP_EINVAL; }
     for (int c = 0; c < n; ++c) {
         const w2::Args &k = list[c];
@@ -240,15 +226,6 @@ int bmp_wgrad_panels_multi(w2::Args *list, int n, void *stream, void *counters) 
         m.cls[c] = list[c];
     }
     m.cta0[n] = used;
-    if (counters && n > 1) {
-        m.progress = (unsigned long long *)counters;
-        m.window = 4 * used;          // ~4 rounds of every CTA: ~190 MB of panels at most in flight between the classes' fronts... see below
-        if (m.window > 256) m.window = 256;      // 256 units x 320 KB = 80 MB: inside the 126 MB L2
-        if (cudaMemsetAsync(counters, 0, w2::MAX_CLASSES * sizeof(unsigned long long), (cudaStream_t)stream) != cudaSuccess) {
-            set_error("bmp_wgrad_panels: memset of the progress counters failed");
-            return BMP_ECUDA;
-        }
-    }
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(w2::wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w2::STAGES * 8 * w2::BLK + w2::BLK + 256 + 1024);
@@ -260,4 +237,4 @@ int bmp_wgrad_panels_multi(w2::Args *list, int n, void *stream, void *counters) 
     return check_launch("wgrad2_kernel");
 }
 
-int bmp_wgrad_panels(w2::Args &k, void *stream) { return bmp_wgrad_panels_multi(&k, 1, stream, nullptr); }
+int bmp_wgrad_panels(w2::Args &k, void *stream) { return bmp_wgrad_panels_multi(&k, 1, stream); }
