@@ -1131,8 +1131,16 @@ class DistMult(Link):
 class GraphConvPredictorForPair(Link):
     """train_binary.py:59-141 -- siamese encoder, co-attention, link-prediction head."""
 
-    def __init__(self, graph_conv, attn=None, mlp=None, symmetric=None):
+    def __init__(self, graph_conv, attn=None, mlp=None, symmetric=None, first_last_atoms=False):
+        """`first_last_atoms=True`: the pair predictor of train_ddi_modify_eval3.py:110-134 (default flags) -- the co-attention sees
+        [atoms after the first step || atoms after the last step] (2*hidden wide; the encoder must expose its per-step states:
+        GGNNMono(..., keep_steps=True))."""
         Link.__init__(self)
+        self.__dict__["first_last_atoms"] = bool(first_last_atoms)
+        if first_last_atoms:
+            if "keep_steps" not in graph_conv.__dict__:
+                raise ValueError("first_last_atoms needs an encoder with per-step atom states (GGNNMono)")
+            graph_conv.__dict__["keep_steps"] = True
         self.add_link("graph_conv", graph_conv)
         if isinstance(mlp, Link):
             self.add_link("mlp", mlp)
@@ -1144,11 +1152,19 @@ class GraphConvPredictorForPair(Link):
             self.__dict__["attn"] = attn
         self.__dict__["symmetric"] = symmetric
 
+    def _atoms(self):
+        enc = self.graph_conv
+        if not self.first_last_atoms:
+            return enc.get_atom_array()
+        if enc.atoms_list is None:
+            raise RuntimeError("gcnbmp: the encoder did not keep its per-step atom states")
+        return torch.cat([enc.get_atom_array(0), enc.get_atom_array(-1)], dim=2)      # F.concat([...], 2), eval3 :117-120
+
     def __call__(self, atoms_1, adjs_1, atoms_2, adjs_2):
         g1 = self.graph_conv(atoms_1, adjs_1)
-        a1 = self.graph_conv.get_atom_array()
+        a1 = self._atoms()
         g2 = self.graph_conv(atoms_2, adjs_2)
-        a2 = self.graph_conv.get_atom_array()
+        a2 = self._atoms()
         if self.attn is not None:
             g1, g2 = self.attn(a1, g1, a2, g2)
         return self.head(g1, g2)

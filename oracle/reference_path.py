@@ -861,14 +861,22 @@ def apply_hooks(grads, params, max_norm=0.0, l2_rate=0.0, l1_rate=0.0):
 # train_binary.py:84-118 (pair composition) and :524 (loss)
 # ----------------------------------------------------------------------------
 class GraphConvPredictorForPair(object):
-    def __init__(self, graph_conv, attn=None, mlp=None):
-        self.graph_conv, self.attn, self.mlp = graph_conv, attn, mlp
+    """train_binary.py:84-118; `first_last_atoms=True`: train_ddi_modify_eval3.py:110-134 (default flags), where the co-attention
+    sees [atoms after the first step || atoms after the last step], 2*hidden wide."""
+
+    def __init__(self, graph_conv, attn=None, mlp=None, first_last_atoms=False):
+        self.graph_conv, self.attn, self.mlp, self.first_last_atoms = graph_conv, attn, mlp, first_last_atoms
+
+    def _atoms(self):
+        if not self.first_last_atoms:
+            return self.graph_conv.get_atom_array()
+        return F.concat([self.graph_conv.get_atom_array(0), self.graph_conv.get_atom_array(-1)], axis=2)   # eval3 :117-120
 
     def __call__(self, atoms_1, adjs_1, atoms_2, adjs_2):
         g1 = self.graph_conv(atoms_1, adjs_1)
-        a1 = self.graph_conv.get_atom_array()
+        a1 = self._atoms()
         g2 = self.graph_conv(atoms_2, adjs_2)
-        a2 = self.graph_conv.get_atom_array()
+        a2 = self._atoms()
         if self.attn is not None:
             g1, g2 = self.attn(a1, g1, a2, g2)
         if type(self.mlp) is MLP:                                                      # train_binary.py:98-100

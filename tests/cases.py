@@ -28,6 +28,10 @@ def pair_case(name, seed=0, dtype=np.float64):
         # wgrad2_kernel, coattn_tc_kernel<128>, and ggnn_fwd/bwd_kernel<2> in fp32 mode)
         "CB": dict(enc="mono", H=128, T=6, tied=True, sum_readout=False, O=128, attn="nie", head=8,
                    hole_hidden=(), K=86, mb=4, N1=64, N2=64),
+        # train_ddi_modify_eval3.py:110-134: ggnn_dev encoder (sum read-out), co-attention on [atoms after step 1 || atoms after
+        # the last step] (2 * hidden wide)
+        "E3": dict(enc="mono", H=32, T=3, tied=True, sum_readout=True, O=24, attn="nie", head=8, hole_hidden=(), K=5,
+                   mb=4, N1=20, N2=17, first_last=True),
         # headline script: untied message layers, shared GRU, VQA attention, hidden head layers
         "U": dict(enc="mono", H=16, T=3, tied=False, sum_readout=False, O=16, attn="vqa", head=8,
                   hole_hidden=(32, 16), K=1, mb=5, N1=23, N2=31),
@@ -62,6 +66,8 @@ def pair_case(name, seed=0, dtype=np.float64):
         d_atoms, d_g = sp["ch"][-1], sp["O"]
     shapes = _prefixed(enc_shapes, "graph_conv/")
     d_in = d_g
+    if sp.get("first_last"):
+        d_atoms = 2 * d_atoms
     if sp["attn"]:
         shapes.update(_prefixed(R.coattn_shapes(d_atoms, sp["O"], sp["head"]), "attn/"))
         d_in = sp["O"]
@@ -83,6 +89,8 @@ def oracle_model(spec, table):
         enc = R.RelGCN(P.sub("graph_conv"), spec["O"], ch_list=spec["ch"], scale_adj=spec["scale_adj"])
     attn = None
     d_atoms = spec["ch"][-1] if spec["enc"] == "relgcn" else spec["H"]
+    if spec.get("first_last"):
+        d_atoms = 2 * d_atoms
     if spec["attn"] == "nie":
         attn = R.NieFineCoattention(P.sub("attn"), d_atoms, spec["O"], spec["head"], activation="tanh")
     elif spec["attn"] == "vqa":
@@ -90,7 +98,7 @@ def oracle_model(spec, table):
     elif spec["attn"] == "pool":
         attn = R.PoolingFineCoattention(P.sub("attn"), d_atoms, spec["O"])
     mlp = R.HolE(P.sub("mlp"), spec["K"], hidden_dims=spec["hole_hidden"])
-    return R.GraphConvPredictorForPair(enc, attn, mlp)
+    return R.GraphConvPredictorForPair(enc, attn, mlp, first_last_atoms=bool(spec.get("first_last")))
 
 
 def oracle_eval(case, dtype=np.float64):

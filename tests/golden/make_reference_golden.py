@@ -67,7 +67,7 @@ def load_class(rel, cls_name):
     import ast
     src = open(os.path.join(REF, rel)).read()
     node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == cls_name)
-    ns = {"chainer": chainer, "cuda": chainer.cuda, "F": CF}
+    ns = {"chainer": chainer, "cuda": chainer.cuda, "F": CF, "L": chainer.links}
     exec(compile(ast.Module(body=[node], type_ignores=[]), os.path.join(REF, rel), "exec"), ns)
     return ns[cls_name]
 
@@ -184,8 +184,9 @@ def main():
     # train_ddi_modify_eval2.py:50-104, with F.sigmoid_cross_entropy as the Classifier applies it (train_binary.py:524)
     PairAttn = load_class("train_binary.py", "GraphConvPredictorForPair")
     PairPlain = load_class("train_ddi_modify_eval2.py", "GraphConvPredictorForPair")
+    PairEval3 = load_class("train_ddi_modify_eval3.py", "GraphConvPredictorForPair")     # co-attention on [h_first || h_last] atoms
     import cases
-    for cname in ("C", "U", "A", "MU", "B", "CB"):
+    for cname in ("C", "U", "A", "MU", "B", "CB", "E3"):
         case = cases.pair_case(cname, seed=7)
         sp, params = case["spec"], case["params"]
         if sp["enc"] == "mono":
@@ -196,13 +197,18 @@ def main():
         else:
             enc = ref_relgcn.RelGCN(out_channels=sp["O"], ch_list=list(sp["ch"]), scale_adj=sp["scale_adj"])
         d_atoms = sp["ch"][-1] if sp["enc"] == "relgcn" else sp["H"]
+        if sp.get("first_last"):
+            d_atoms = 2 * d_atoms
         attn = None
         if sp["attn"] == "nie":
             attn = ref_nie.NieFineCoattention(d_atoms, sp["O"], sp["head"], activation=CF.tanh)
         elif sp["attn"] == "vqa":
             attn = ref_vqa.VQAParallelCoattention(d_atoms, sp["O"], sp["head"])
         mlp = ref_hole.HolE(sp["K"], hidden_dims=sp["hole_hidden"])
-        net = PairAttn(enc, attn, mlp) if attn is not None else PairPlain(enc, mlp)
+        if sp.get("first_last"):
+            net = PairEval3(enc, attn, mlp)
+        else:
+            net = PairAttn(enc, attn, mlp) if attn is not None else PairPlain(enc, mlp)
         load_params(net, params)
         a1, A1, a2, A2 = case["inputs"]
         logits = net(a1, A1, a2, A2)

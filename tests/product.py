@@ -19,6 +19,8 @@ def product_model(spec, params):
         enc = gcnbmp.RelGCN(spec["O"], ch_list=spec["ch"], scale_adj=spec["scale_adj"])
         d_atoms = spec["ch"][-1]
     attn = None
+    if spec.get("first_last"):
+        d_atoms = 2 * d_atoms
     if spec["attn"] == "nie":
         attn = gcnbmp.NieFineCoattention(d_atoms, spec["O"], spec["head"], activation=f.tanh)
     elif spec["attn"] == "vqa":
@@ -26,7 +28,7 @@ def product_model(spec, params):
     elif spec["attn"] == "pool":
         attn = gcnbmp.PoolingFineCoattention(d_atoms, spec["O"])
     mlp = gcnbmp.HolE(spec["K"], hidden_dims=spec["hole_hidden"])
-    model = gcnbmp.GraphConvPredictorForPair(enc, attn, mlp)
+    model = gcnbmp.GraphConvPredictorForPair(enc, attn, mlp, first_last_atoms=bool(spec.get("first_last")))
     model.load_params({k: np.asarray(v, np.float32) for k, v in params.items()})
     return model
 
