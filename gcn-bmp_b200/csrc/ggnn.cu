@@ -376,6 +376,169 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_bwd_kernel(const bmp_ggnn_bw
     }
 }
 
+// ---------------------------------------------------------------------------
+// Backward (data part) for 128 < hidden <= 256.  The kernel above keeps five H x 64 fp32 buffers in shared memory (H <= 128);
+// here only TWO are resident -- `y`, the pre-activation gradient currently used as a GEMM operand (delta_h, then delta_z,
+// then delta_r, re-loaded from the Gs slots they were written to; later the P_e panels), and `s` (dm) -- the running
+// gradient dL/dh_{t+1} lives in dHs[t+1] / dHs[t] in global memory, and every contribution to dL/dh_t is accumulated in
+// one register tile set per 64-channel block.  Same arithmetic as ggnn_bwd_kernel, a slower schedule; the parity path for
+// training at hidden 192 / 256.  state == step input only (no external GRU state).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_cm_ld(float *dst, const float *__restrict__ src, long ld, int n, int C) {
+    const int nq = C >> 2;
+    for (int idx = threadIdx.x; idx < nq * AT; idx += NTHREADS) {
+        int i = idx & (AT - 1), cq = idx >> 6;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n) v = *reinterpret_cast<const float4 *>(src + (long)i * ld + cq * 4);
+        float *d = dst + (cq * 4) * AT + i;
+        d[0] = v.x; d[AT] = v.y; d[2 * AT] = v.z; d[3 * AT] = v.w;
+    }
+}
+
+static size_t bwd_big_smem_bytes(int H) {
+    return sizeof(float) * ((size_t)2 * H * AT + AT * AT + STAGE_FLOATS);
+}
+
+template <int HC>
+__global__ void __launch_bounds__(NTHREADS, 1) ggnn_bwd_big_kernel(const bmp_ggnn_bwd_t a) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = a.hidden, N = a.n_atoms, E = a.n_edge, T = a.n_steps;
+    float *Sy = smem, *Ss = Sy + H * AT, *Sadj = Ss + H * AT, *Sstage = Sadj + AT * AT;
+    const int ty = threadIdx.x >> 4;
+    const long rows_total = (long)a.mb * N;
+    const int K4 = (N + 3) & ~3;
+
+    for (int mol = blockIdx.x; mol < a.mb; mol += gridDim.x) {
+        const long row0 = (long)mol * N;
+        for (int t = T - 1; t >= 0; --t) {
+            const bool stateful = a.stateful[t] != 0;
+            const bmp_gru_t &G = a.gru[t];
+            float *Gt = a.Gs + ((long)t * rows_total + row0) * 3 * H;
+            const float *St = a.Hs + ((long)t * rows_total + row0) * H;                 // state of the step = h_t
+            const float *gin = a.dHs + ((long)(t + 1) * rows_total + row0) * H;          // dL/dh_{t+1} (running gradient)
+            float acc[HC][4][4], dm[HC][4][4];
+            __syncthreads();
+            // ---- gate derivatives (thread-owned elements): delta_z, delta_h -> Gs ; acc = g (1 - z)
+#pragma unroll
+            for (int oc = 0; oc < HC; ++oc) {
+                zero_acc(acc[oc]);
+                zero_acc(dm[oc]);
+                if (oc * 64 + ty * 4 >= H) continue;
+                float g[4][4], z[4][4], hb[4][4], sv[4][4];
+                tile_load_g(gin, H, oc * 64, H, N, g);
+                tile_load_g(Gt + H, 3 * H, oc * 64, H, N, z);
+                tile_load_g(Gt + 2 * H, 3 * H, oc * 64, H, N, hb);
+                if (stateful) tile_load_g(St, H, oc * 64, H, N, sv);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float s_ = stateful ? sv[q][b] : 0.f;
+                        const float dzv = g[q][b] * (hb[q][b] - s_);
+                        const float dhv = g[q][b] * z[q][b];
+                        if (stateful) acc[oc][q][b] = g[q][b] * (1.f - z[q][b]);
+                        hb[q][b] = dhv * (1.f - hb[q][b] * hb[q][b]);       // delta_h
+                        z[q][b] = dzv * z[q][b] * (1.f - z[q][b]);          // delta_z
+                    }
+                tile_store_g(Gt + H, 3 * H, oc * 64, H, N, z);
+                tile_store_g(Gt + 2 * H, 3 * H, oc * 64, H, N, hb);
+            }
+            __syncthreads();
+            // ---- operand delta_h: q = U^T delta_h -> delta_r, ds += q r ; dh_x += W_h^T delta_h ; dm += W_m^T delta_h
+            load_cm_ld(Sy, Gt + 2 * H, 3 * H, N, H);
+            __syncthreads();
+#pragma unroll
+            for (int oc = 0; oc < HC; ++oc) {
+                if (oc * 64 >= H) continue;
+                if (stateful) {
+                    float q_[4][4];
+                    zero_acc(q_);
+                    gemm64_g<true>(q_, G.U, H, oc * 64, H, H, Sy, Sstage);
+                    if (oc * 64 + ty * 4 < H) {
+                        float r[4][4], sv[4][4];
+                        tile_load_g(Gt, 3 * H, oc * 64, H, N, r);
+                        tile_load_g(St, H, oc * 64, H, N, sv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const float dr = q_[q][b] * sv[q][b];
+                                acc[oc][q][b] += q_[q][b] * r[q][b];
+                                r[q][b] = dr * r[q][b] * (1.f - r[q][b]);   // delta_r
+                            }
+                        tile_store_g(Gt, 3 * H, oc * 64, H, N, r);
+                    }
+                }
+                gemm64_g<true>(acc[oc], G.W, 2 * H, oc * 64, H, H, Sy, Sstage);
+                gemm64_g<true>(dm[oc], G.W + H, 2 * H, oc * 64, H, H, Sy, Sstage);
+            }
+            // ---- operand delta_z
+            __syncthreads();
+            load_cm_ld(Sy, Gt + H, 3 * H, N, H);
+            __syncthreads();
+#pragma unroll
+            for (int oc = 0; oc < HC; ++oc) {
+                if (oc * 64 >= H) continue;
+                gemm64_g<true>(acc[oc], G.W_z, 2 * H, oc * 64, H, H, Sy, Sstage);
+                gemm64_g<true>(dm[oc], G.W_z + H, 2 * H, oc * 64, H, H, Sy, Sstage);
+                if (stateful) gemm64_g<true>(acc[oc], G.U_z, H, oc * 64, H, H, Sy, Sstage);
+            }
+            // ---- operand delta_r
+            if (stateful) {
+                __syncthreads();
+                load_cm_ld(Sy, Gt, 3 * H, N, H);
+                __syncthreads();
+#pragma unroll
+                for (int oc = 0; oc < HC; ++oc) {
+                    if (oc * 64 >= H) continue;
+                    gemm64_g<true>(acc[oc], G.W_r, 2 * H, oc * 64, H, H, Sy, Sstage);
+                    gemm64_g<true>(dm[oc], G.W_r + H, 2 * H, oc * 64, H, H, Sy, Sstage);
+                    gemm64_g<true>(acc[oc], G.U_r, H, oc * 64, H, H, Sy, Sstage);
+                }
+            }
+            // ---- dm -> shared memory
+            __syncthreads();
+#pragma unroll
+            for (int oc = 0; oc < HC; ++oc)
+                if (oc * 64 + ty * 4 < H) tile_store_s(Ss, oc * 64, dm[oc]);
+            __syncthreads();
+            // ---- message backward: P_e = A_e^T dm ; dh += sum_e W_e^T P_e
+            for (int e = 0; e < E; ++e) {
+                load_adj<false>(Sadj, a.adj + ((long)mol * E + e) * N * N, N);
+                __syncthreads();
+#pragma unroll
+                for (int oc = 0; oc < HC; ++oc) {
+                    if (oc * 64 + ty * 4 >= H) continue;
+                    float p[4][4];
+                    zero_acc(p);
+                    gemm64_s(p, Ss, AT, oc * 64, K4, Sadj);       // P^T[c][j] = sum_i dm[c][i] A[i][j]
+                    tile_store_s(Sy, oc * 64, p);
+                    tile_store_g(a.Ps + ((long)t * rows_total + row0) * E * H + (long)e * H, (long)E * H, oc * 64, H, N, p);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int oc = 0; oc < HC; ++oc)
+                    if (oc * 64 < H)
+                        gemm64_g<true>(acc[oc], a.msg_W[t] + (long)e * H, (long)E * H, oc * 64, H, H, Sy, Sstage);
+            }
+            // ---- dh_t = acc + external dHs[t] -> dHs[t] (the running gradient of the next iteration)
+#pragma unroll
+            for (int oc = 0; oc < HC; ++oc) {
+                if (oc * 64 + ty * 4 >= H) continue;
+                float ext[4][4];
+                float *gout = a.dHs + ((long)t * rows_total + row0) * H;
+                tile_load_g(gout, H, oc * 64, H, N, ext);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[oc][q][b] += ext[q][b];
+                tile_store_g(gout, H, oc * 64, H, N, acc[oc]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 static int check_common(int mb, int N, int H, int E, int T, int mode) {
     if (mode != BMP_MODE_F32) { set_error("ggnn fp32 path called with mode %d", mode); return BMP_EINVAL; }
     if (mb <= 0 || T <= 0 || T > BMP_MAX_STEPS) { set_error("ggnn: bad mb=%d or n_steps=%d", mb, T); return BMP_ESHAPE; }
@@ -468,8 +631,8 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
     };
     const bool tc_data = tcw && E == 4 && !a->state_in;      // data part on tcgen05 as well
     if (a->adj_u8 && !tc_data) { set_error("bmp_ggnn_backward: a byte adjacency needs the tcgen05 path"); return BMP_EINVAL; }
-    if (!tc_data && H > 128) {
-        set_error("bmp_ggnn_backward: hidden=%d > 128 not supported by the fp32 backward kernel", H);
+    if (!tc_data && H > 128 && a->state_in) {
+        set_error("bmp_ggnn_backward: an external GRU state needs hidden <= 128 (hidden=%d)", H);
         return BMP_ESHAPE;
     }
     for (int t = 0; t < T; ++t) {
@@ -492,7 +655,16 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int grid = a->mb < sms ? a->mb : sms;
         cudaStream_t st = (cudaStream_t)stream;
-        if (H <= 64) {
+        if (H > 128) {
+            smem = bwd_big_smem_bytes(H);
+            if (H <= 192) {
+                cudaFuncSetAttribute(ggnn_bwd_big_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                ggnn_bwd_big_kernel<3><<<grid, NTHREADS, smem, st>>>(*a);
+            } else {
+                cudaFuncSetAttribute(ggnn_bwd_big_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                ggnn_bwd_big_kernel<4><<<grid, NTHREADS, smem, st>>>(*a);
+            }
+        } else if (H <= 64) {
             cudaFuncSetAttribute(ggnn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             ggnn_bwd_kernel<1><<<grid, NTHREADS, smem, st>>>(*a);
         } else {

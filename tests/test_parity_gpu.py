@@ -376,3 +376,49 @@ def test_bimpm_matches_oracle(mb, N1, N2, H, head):
     g = net.grad_dict()
     for k in params:
         assert rel_err(g[k], tab[k].grad) <= TOL, k
+
+
+@pytest.mark.parametrize("H,T,tied,N", [(256, 3, True, 64), (192, 2, False, 21), (256, 2, True, 9)])
+def test_fp32_training_at_hidden_above_128(H, T, tied, N):
+    """Training at hidden 192 / 256 in BMP_MODE_F32 (ggnn_bwd_big_kernel): graph vectors, atom states and every parameter gradient of
+    the GGNN encoder vs the fp64 oracle (the reference trains any --fp-hidden-dim, train_binary.py:297-429)."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    rng = np.random.default_rng(H + T)
+    mb, O = 3, 40
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    params = R.init_params(R.ggnn_mono_shapes(O, H, T, weight_tying=tied), rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    onet = R.GGNNMono(R.P(tab), O, H, T, weight_tying=tied)
+    w_g, w_a = rng.standard_normal((mb, O)), rng.standard_normal((mb, N, H)) * 0.1
+    og = onet(atoms, adj.astype(np.float64))
+    oa = onet.get_atom_array()
+    F.add(F.sum_(F.mul(og, F.const(w_g))), F.sum_(F.mul(oa, F.const(w_a)))).backward()
+    net = gcnbmp.GGNNMono(O, H, T, weight_tying=tied)
+    net.load_params(params)
+    net.cleargrads()
+    pg = net(atoms, adj)
+    pa = net.get_atom_array()
+    ((pg * torch.tensor(w_g, dtype=torch.float32, device="cuda")).sum() + (pa * torch.tensor(w_a, dtype=torch.float32, device="cuda")).sum()).backward()
+    assert rel_err(pg.detach().cpu().numpy(), og.data) <= TOL and rel_err(pa.detach().cpu().numpy(), oa.data) <= TOL
+    g = net.grad_dict()
+    for k in params:
+        if tab[k].grad is not None and np.abs(tab[k].grad).max() > 1e-12:
+            assert rel_err(g[k], tab[k].grad) <= TOL, k
+
+
+def test_config_d_model_trains_at_hidden_256_in_fp32():
+    """BASELINE config D's model (modular GGNN hidden 256 + R1 read-out + HolE, no co-attention) as a TRAINING step in fp32 mode:
+    logits and every parameter gradient vs the fp64 oracle."""
+    case = cases.pair_case("MU", seed=3)
+    sp = dict(case["spec"], H=256, O=64, T=2, tied=True, hole_hidden=())
+    rng = np.random.default_rng(21)
+    shapes = {"graph_conv/" + k: v for k, v in R.ggnn_shapes(64, 256, 2, weight_tying=True).items()}
+    shapes.update({"mlp/" + k: v for k, v in R.hole_shapes(64, sp["K"], ()).items()})
+    big = dict(case, spec=sp, params=R.init_params(shapes, rng, dtype=np.float64))
+    o = cases.oracle_eval(big)
+    p = product.product_eval(big)
+    assert rel_err(p["logits"], o["logits"]) <= TOL
+    for k, v in o["grads"].items():
+        if v is not None and np.abs(v).max() > 1e-12:
+            assert rel_err(p["grads"][k], v) <= TOL, k
