@@ -564,8 +564,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=GLOBAL_BATCH, help="global batch (pairs per step)")
-    ap.add_argument("--chunk", type=int, default=4144,
-                    help="micro-batch (pairs) per forward/backward; 4144 molecules = 2072 two-molecule tiles = 14 full waves of 148 CTAs")
+    ap.add_argument("--chunk", type=int, default=8288,
+                    help="micro-batch (pairs) per forward/backward; 8288 molecules = 4144 two-molecule tiles = 28 full waves of 148 CTAs")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0: min(--steps, 3))")
     ap.add_argument("--no-e2e-variants", dest="e2e_variants", action="store_false",
                     help="skip the informational float32 / bit-packed / indexed end-to-end measurements")

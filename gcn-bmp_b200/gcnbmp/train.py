@@ -88,10 +88,11 @@ class PairTrainer(object):
     Inputs may be device tensors (resident) or host arrays/tensors (streamed per chunk through
     a pinned staging ring on a copy stream, overlapping the previous chunk's compute)."""
 
-    def __init__(self, model, chunk=4144, optimizer=True, world_size=1, process_group=None, graph=False,
+    def __init__(self, model, chunk=8288, optimizer=True, world_size=1, process_group=None, graph=False,
                  max_norm=0.0, l2_rate=0.0, l1_rate=0.0, **adam):
-        """`chunk`: pairs per micro-batch; the default 4144 makes every encoder launch 2072 two-molecule tiles = 14 full waves of the
-        148 persistent CTAs (2048 -> 4144 was worth 6 % on the bench step; the BF16 panel stash is ~11 GB at that size).
+        """`chunk`: pairs per micro-batch; the default 8288 makes every encoder launch 4144 two-molecule tiles = 28 full waves of the
+        148 persistent CTAs (2048 -> 4144 was worth 6 % on the bench step, 4144 -> 8288 another 1 %; the BF16 panel stash is ~22 GB at
+        that size, and an 8-GPU rank of the 65 536-pair bench step is a single micro-batch).
         `graph=True`: every micro-batch shape is captured once as a CUDA graph (forward, loss, backward with the
         gradient sink) and replayed afterwards -- for small batches (the reference's default is 32 pairs) the step is
         bound by ~60 kernel launches and the Python around them, not by the kernels."""
