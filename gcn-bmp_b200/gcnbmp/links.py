@@ -547,8 +547,27 @@ class RelGCN(Link):
         params = [emb]
         for c in self.rgcn_convs:
             params += c.tensors()
-        atoms = Fn.RelGCNEncode.apply(x, adj, tuple(self.ch_list), 1 if self.scale_adj else 0, K.ACT["tanh"],
-                                      torch.is_grad_enabled(), self.__dict__.get("mode", K.MODE_F32), *params)
+        mode, ch = self.__dict__.get("mode", K.MODE_F32), tuple(self.ch_list)
+        if mode == K.MODE_BF16 and len(set(ch)) > 1 and max(ch) <= 128 and self.num_edge_type == 4:
+            # The tcgen05 RelGCN kernels take ONE channel count (64 or 128) for all layers; a non-uniform list such as the reference's
+            # default [16, 128, 64] runs on them zero-padded to the widest layer (parameter re-packing: padded input columns meet zero
+            # weights, padded output channels are tanh(0) = 0; autograd slices the gradients back out of the padded copies).
+            C, E = (64 if max(ch) <= 64 else 128), self.num_edge_type
+            pad = torch.nn.functional.pad
+            if emb is not None:
+                emb_p = pad(emb, (0, C - ch[0]))
+            else:
+                emb_p, x = None, pad(x, (0, C - ch[0]))
+            padded = [emb_p]
+            for l, c in enumerate(self.rgcn_convs):
+                Ws, bs, We, be = c.tensors()
+                cin, cout = ch[l], ch[l + 1]
+                padded += [pad(Ws, (0, C - cin, 0, C - cout)), pad(bs, (0, C - cout)),
+                           pad(We, (0, C - cin, 0, (C - cout) * E)), pad(be, (0, (C - cout) * E))]   # rows c*E+e: new channels append
+            atoms = Fn.RelGCNEncode.apply(x, adj, (C,) * len(ch), 1 if self.scale_adj else 0, K.ACT["tanh"],
+                                          torch.is_grad_enabled(), mode, *padded)[..., :ch[-1]].contiguous()
+        else:
+            atoms = Fn.RelGCNEncode.apply(x, adj, ch, 1 if self.scale_adj else 0, K.ACT["tanh"], torch.is_grad_enabled(), mode, *params)
         self.__dict__["atoms"] = atoms
         self.rgcn_readout.__dict__["mode"] = self.__dict__.get("mode", K.MODE_F32)
         return self.rgcn_readout(atoms)

@@ -616,3 +616,33 @@ def test_tc_mode_first_last_atoms_pair_step():
     g = model.grad_dict()
     worst = max(_rms_rel(g[k], o["grads"][k]) for k in o["grads"] if o["grads"][k] is not None and np.abs(o["grads"][k]).max() > 1e-6)
     assert worst <= MAX_TOL, worst          # measured 2.5e-2 (four pairs; the energy layer sees 128-wide bf16 atoms)
+
+
+@pytest.mark.parametrize("ch,O,scale", [([16, 128, 64], 64, True), ([16, 32, 64, 48], 64, False)])
+def test_tc_relgcn_non_uniform_channels_run_zero_padded(ch, O, scale):
+    """The reference's default RelGCN channel list [16, 128, 64] (models/relgcn.py:36-37) in BF16 mode: the tcgen05 kernels take one
+    channel count, so the stack runs zero-padded to the widest layer; outputs, atom states and every gradient vs the fp64 oracle."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    from oracle import minichainer as F
+    rng = np.random.default_rng(sum(ch))
+    mb, N = 6, 33
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    params = R.init_params(R.relgcn_shapes(O, ch), rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    onet = R.RelGCN(R.P(tab), out_channels=O, ch_list=ch, scale_adj=scale)
+    og = onet(atoms, adj.astype(np.float64))
+    w = rng.standard_normal(og.data.shape)
+    F.sum_(F.mul(og, F.const(w))).backward()
+    net = gcnbmp.RelGCN(O, ch_list=ch, scale_adj=scale)
+    net.load_params(params)
+    net.mode = gcnbmp.MODE_BF16
+    gcnbmp.reset_launch_count()
+    g = net(atoms, adj)
+    assert tuple(net.get_atom_array().shape) == (mb, N, ch[-1])
+    (g * torch.tensor(w, dtype=torch.float32, device="cuda")).sum().backward()
+    assert rel_err(g.detach().cpu().numpy(), og.data) <= MAX_TOL
+    gd = net.grad_dict()
+    for k in gd:
+        assert gd[k].shape == tab[k].grad.shape and np.isfinite(gd[k]).all(), k
+        assert _rms_rel(gd[k], tab[k].grad) <= 5e-2, (k, _rms_rel(gd[k], tab[k].grad))
