@@ -307,6 +307,28 @@ def _encode(x, adj, state, plan, msgs, grus, embed_W, mode, keep_steps=False, mo
     """Returns (states, last): states[0] = h_0, states[last] = h_T; every step is present only when
     `keep_steps` (or in fp32 mode with a tape) -- BF16 mode otherwise keeps a bf16 panel stash internally."""
     want = torch.is_grad_enabled()
+    H = msgs[0][0].shape[1]
+    if mode == K.MODE_BF16 and H not in (64, 128, 256) and H < 128 and state is None and msgs[0][0].shape[0] == 4 * H:
+        # The tcgen05 encoders exist for hidden 64 / 128 (256 forward only); any other hidden size <= 128 (the paper's 32, the
+        # reference's default 16) runs on them ZERO-PADDED to the next of those: padded input columns meet zero weights, a padded
+        # channel's gates see 0 (z = 1/2, hbar = tanh(0) = 0), so it stays exactly 0 through every GRU step; autograd slices the
+        # gradients back out of the padded parameter copies (parameter re-packing, no arithmetic on activations).
+        C, E, pad = (64 if H < 64 else 128), 4, torch.nn.functional.pad
+        d = C - H
+        params = [None if embed_W is None else pad(embed_W, (0, d))]
+        for W, b in msgs:                                   # (E*H, H), rows c*E+e: new channels append
+            params += [pad(W, (0, d, 0, d * E)), pad(b, (0, d * E))]
+        for g in grus:
+            t = g.tensors()
+            for i in range(0, 12, 4):                       # (W_g (H,2H) over [h | m], b), (U_g (H,H), b)
+                Wg, bW, Ug, bU = t[i:i + 4]
+                params += [torch.cat([pad(Wg[:, :H], (0, d, 0, d)), pad(Wg[:, H:], (0, d, 0, d))], dim=1), pad(bW, (0, d)),
+                           pad(Ug, (0, d, 0, d)), pad(bU, (0, d))]
+        if embed_W is None:
+            x = pad(x, (0, d))
+        out = Fn.GGNNEncode.apply(x, adj, state, tuple(plan), len(msgs), len(grus), mode, want, keep_steps, mol_index, *params)
+        out = out[..., :H].contiguous()
+        return out, (out.shape[0] - 1)
     params = [embed_W]
     for W, b in msgs:
         params += [W, b]

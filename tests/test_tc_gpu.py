@@ -100,10 +100,56 @@ def test_tc_mode_rejects_unsupported_shapes():
     import gcnbmp
     from gcnbmp import synthetic
     atoms, adj = synthetic.random_molecules(np.random.default_rng(0), 2, 10)
-    net = gcnbmp.GGNNMono(32, 32, 2)
+    net = gcnbmp.GGNNMono(32, 160, 2)          # hidden 160: neither a tcgen05 size nor paddable to one
     net.mode = gcnbmp.MODE_BF16
     with pytest.raises(ValueError):
         net(atoms, adj)
+
+
+@pytest.mark.parametrize("H,T,tied,cls", [(32, 4, True, "mono"), (16, 3, False, "mono"), (96, 2, True, "ggnn"), (32, 8, False, "mono")])
+def test_tc_encoder_runs_other_hidden_sizes_zero_padded(H, T, tied, cls):
+    """Hidden sizes other than 64 / 128 (the paper's 32, the reference's default 16) run on the tcgen05 encoders zero-padded:
+    graph vectors, atom states and every parameter gradient vs the fp64 oracle within the BF16-mode bound."""
+    import gcnbmp
+    from gcnbmp import synthetic
+    from oracle import minichainer as F
+    rng = np.random.default_rng(H + T)
+    mb, N, O = 5, 30, 24
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    if cls == "mono":
+        params = R.init_params(R.ggnn_mono_shapes(O, H, T, weight_tying=tied), rng, dtype=np.float64)
+        tab = R.wrap_params(params)
+        onet, net = R.GGNNMono(R.P(tab), O, H, T, weight_tying=tied), gcnbmp.GGNNMono(O, H, T, weight_tying=tied)
+    else:
+        params = R.init_params(R.ggnn_shapes(O, H, T, weight_tying=tied), rng, dtype=np.float64)
+        tab = R.wrap_params(params)
+        onet, net = R.GGNN(R.P(tab), O, H, T, weight_tying=tied), gcnbmp.GGNN(O, hidden_dim=H, n_layers=T, weight_tying=tied)
+    og = onet(atoms, adj.astype(np.float64))
+    oa = onet.get_atom_array() if cls == "mono" else None
+    w = rng.standard_normal(og.data.shape)
+    loss = F.sum_(F.mul(og, F.const(w)))
+    if oa is not None:
+        loss = F.add(loss, F.sum_(oa))
+    loss.backward()
+    net.load_params(params)
+    net.mode = gcnbmp.MODE_BF16
+    gcnbmp.reset_launch_count()
+    g = net(atoms, adj)
+    total = (g * torch.tensor(w, dtype=torch.float32, device="cuda")).sum()
+    if oa is not None:
+        pa = net.get_atom_array()
+        assert tuple(pa.shape) == (mb, N, H)
+        total = total + pa.sum()
+        assert rel_err(pa.detach().cpu().numpy(), oa.data) <= MAX_TOL
+    total.backward()
+    assert rel_err(g.detach().cpu().numpy(), og.data) <= MAX_TOL
+    gd = net.grad_dict()
+    for k in gd:
+        ref = tab[k].grad
+        if ref is None or np.abs(ref).max() < 1e-9:
+            continue
+        assert gd[k].shape == ref.shape and np.isfinite(gd[k]).all(), k
+        assert _rms_rel(gd[k], ref) <= 5e-2, (k, _rms_rel(gd[k], ref))
 
 
 @pytest.mark.parametrize("rows,M,N,lda_pad", [(5000, 128, 128, 0), (777, 192, 64, 64), (20000, 384, 256, 0), (64, 64, 128, 128)])
