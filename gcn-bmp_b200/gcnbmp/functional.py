@@ -151,7 +151,7 @@ def _grad_targets(params):
         if p is None:
             bufs.append(None)
             rets.append(None)
-        elif (_GRAD_SINK and p.requires_grad and p.grad is not None and p.grad.dtype == torch.float32
+        elif (_GRAD_SINK and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.dtype == torch.float32
               and p.grad.is_contiguous() and p.grad.shape == p.shape):
             bufs.append(p.grad)
             rets.append(None)
