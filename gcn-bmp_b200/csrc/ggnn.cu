@@ -623,8 +623,11 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
     const int H = a->hidden, T = a->n_steps, E = a->n_edge;
     // BMP_MODE_BF16: parameter-gradient contractions on tcgen05 (bias column sums fused in)
     const bool tcw = a->mode == BMP_MODE_BF16 && (H == 64 || H == 128);
+    const bool tc3 = a->mode == BMP_MODE_F32 && (H == 64 || H == 128 || H == 256);
     auto WG = [&](const float *A_, int lda, const float *B_, int ldb, float *C_, int ldc, long r_, float *db, int dbs) -> int {
         if (tcw) return bmp_wgrad_tc(A_, lda, B_, ldb, C_, ldc, r_, H, H, db, dbs, stream);
+        // BMP_MODE_F32: the same tensor-core contraction with a bf16 hi/lo split (three UMMAs per product): fp32-grade accuracy
+        if (tc3) return bmp_wgrad_tc3(A_, lda, B_, ldb, C_, ldc, r_, H, H, db, dbs, stream);
         int e_ = bmp_wgrad(A_, lda, B_, ldb, C_, ldc, r_, H, H, stream);
         if (!e_ && db) e_ = bmp_colsum(A_, lda, db, dbs, r_, H, stream);
         return e_;

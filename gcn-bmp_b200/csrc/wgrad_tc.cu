@@ -6,6 +6,10 @@
 // warps, one elected lane issues M=128 x N x 16 UMMAs into a TMEM accumulator that lives for the whole
 // row range of the CTA, and the epilogue adds the tile into C with fp32 atomics (split over rows across
 // CTAs).  Column sums of A (the bias gradients) are accumulated by the loaders on the way.
+//
+// SPLIT = true (bmp_wgrad_tc3, used by BMP_MODE_F32): fp32-grade contraction on the same pipeline -- every operand is staged as a
+// bf16 hi / lo pair (x = hi + lo up to 2^-17 relative) and each k-step issues three UMMAs, hi.hi + lo.hi + hi.lo, into the fp32
+// TMEM accumulator (the lo.lo term is below fp32 rounding of the sum).
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -42,6 +46,13 @@ __host__ __device__ constexpr uint32_t idesc_mnmn(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// lo part of a hi / lo bf16 split: bf16(x - float(hi)), for four values packed like `hi`
+__device__ __forceinline__ uint2 lo_of(const float4 &v, const uint2 &hi) {
+    const float h0 = __uint_as_float(hi.x << 16), h1 = __uint_as_float(hi.x & 0xFFFF0000u);
+    const float h2 = __uint_as_float(hi.y << 16), h3 = __uint_as_float(hi.y & 0xFFFF0000u);
+    return make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
+}
+
 struct Args {
     const float *A, *B;
     float *C, *dbias;
@@ -49,10 +60,11 @@ struct Args {
     long rows, rows_per_cta;
 };
 
-template <int N>
-__global__ void __launch_bounds__(NTHR, 2) wgrad_tc_kernel(const Args a) {
+template <int N, bool SPLIT>
+__global__ void __launch_bounds__(NTHR, SPLIT ? 1 : 2) wgrad_tc_kernel(const Args a) {
     constexpr int NB = N / 64;                       // MN blocks of the B stage
-    constexpr int A_BYTES = 2 * BLK, B_BYTES = NB * BLK, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int A_BYTES = 2 * BLK, B_BYTES = NB * BLK, HALF_BYTES = A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * HALF_BYTES;      // SPLIT: [A_hi | B_hi | A_lo | B_lo]
     constexpr int BQ = N / 4;                        // float4 per B row
     constexpr int BJ = KT * BQ / NLOAD;              // float4 of B per loader thread per chunk
     extern __shared__ uint8_t smem_raw[];
@@ -96,10 +108,18 @@ __global__ void __launch_bounds__(NTHR, 2) wgrad_tc_kernel(const Args a) {
                 for (int k = 0; k < KT / 16; ++k) {
                     const uint64_t da = desc_mn(sa + k * 16 * 128), db = desc_mn(sb + k * 16 * 128);
                     const uint32_t acc = (c | k) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem), "l"(da), "l"(db), "r"(ID), "r"(acc) : "memory");
+                    auto mma = [&](uint64_t xa, uint64_t xb, uint32_t ac) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem), "l"(xa), "l"(xb), "r"(ID), "r"(ac) : "memory");
+                    };
+                    mma(da, db, acc);                                                  // hi . hi
+                    if (SPLIT) {
+                        const uint64_t la = desc_mn(sa + HALF_BYTES + k * 16 * 128), lb = desc_mn(sb + HALF_BYTES + k * 16 * 128);
+                        mma(la, db, 1u);                                               // lo . hi
+                        mma(da, lb, 1u);                                               // hi . lo
+                    }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(EMPTY(s)) : "memory");
             }
@@ -132,13 +152,17 @@ __global__ void __launch_bounds__(NTHR, 2) wgrad_tc_kernel(const Args a) {
                 const int k = ak0 + 8 * j;
                 csum[0] += va[j].x; csum[1] += va[j].y; csum[2] += va[j].z; csum[3] += va[j].w;
                 const uint32_t off = (am4 >> 6) * BLK + k * 128 + (((((am4 & 63) >> 3) ^ (k & 7)) << 4) | ((am4 & 7) << 1));
-                *reinterpret_cast<uint2 *>(sa + off) = make_uint2(pack_bf16(va[j].x, va[j].y), pack_bf16(va[j].z, va[j].w));
+                const uint2 hi = make_uint2(pack_bf16(va[j].x, va[j].y), pack_bf16(va[j].z, va[j].w));
+                *reinterpret_cast<uint2 *>(sa + off) = hi;
+                if (SPLIT) *reinterpret_cast<uint2 *>(sa + HALF_BYTES + off) = lo_of(va[j], hi);
             }
 #pragma unroll
             for (int j = 0; j < BJ; ++j) {
                 const int k = bk0 + (NLOAD / BQ) * j;
                 const uint32_t off = (bn4 >> 6) * BLK + k * 128 + (((((bn4 & 63) >> 3) ^ (k & 7)) << 4) | ((bn4 & 7) << 1));
-                *reinterpret_cast<uint2 *>(sb + off) = make_uint2(pack_bf16(vb[j].x, vb[j].y), pack_bf16(vb[j].z, vb[j].w));
+                const uint2 hi = make_uint2(pack_bf16(vb[j].x, vb[j].y), pack_bf16(vb[j].z, vb[j].w));
+                *reinterpret_cast<uint2 *>(sb + off) = hi;
+                if (SPLIT) *reinterpret_cast<uint2 *>(sb + HALF_BYTES + off) = lo_of(vb[j], hi);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(FULL(s));
@@ -198,9 +222,9 @@ __global__ void __launch_bounds__(NTHR, 2) wgrad_tc_kernel(const Args a) {
     }
 }
 
-template <int N>
+template <int N, bool SPLIT>
 static int launch(const Args &a, cudaStream_t st, int sms) {
-    constexpr int smem = STAGES * (2 * BLK + (N / 64) * BLK) + 128 + 8 * 128 * 4 + 1024;
+    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (2 * BLK + (N / 64) * BLK) + 128 + 8 * 128 * 4 + 1024;
     const int mtiles = (a.M + 127) / 128;
     long split = (1L * sms + mtiles - 1) / mtiles;
     long max_split = (a.rows + 8 * KT - 1) / (8 * KT);
@@ -209,8 +233,8 @@ static int launch(const Args &a, cudaStream_t st, int sms) {
     Args k = a;
     k.rows_per_cta = ((a.rows + split - 1) / split + KT - 1) / KT * KT;
     split = (a.rows + k.rows_per_cta - 1) / k.rows_per_cta;
-    cudaFuncSetAttribute(wgrad_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    wgrad_tc_kernel<N><<<dim3(mtiles, (unsigned)split), NTHR, smem, st>>>(k);
+    cudaFuncSetAttribute(wgrad_tc_kernel<N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    wgrad_tc_kernel<N, SPLIT><<<dim3(mtiles, (unsigned)split), NTHR, smem, st>>>(k);
     count_launch();
     return check_launch("wgrad_tc_kernel");
 }
@@ -223,8 +247,8 @@ using namespace bmp;
 // C (M,N; ldc) += A^T B on the tensor cores (bf16 operands, fp32 accumulate); dbias[m*bias_stride] +=
 // column sums of A when non-NULL.  N must be 64, 128 or 256 and everything 16-byte aligned; returns
 // BMP_ESHAPE otherwise so the caller can use the fp32 bmp_wgrad.
-extern "C" int bmp_wgrad_tc(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
-                            int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream) {
+static int wgrad_tc_any(bool split3, const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                        int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream) {
     if (!A || !B || !C) { set_error("bmp_wgrad_tc: null pointer"); return BMP_EINVAL; }
     if (rows <= 0 || M <= 0) return BMP_OK;
     if ((N != 64 && N != 128 && N != 256) || (M & 3) || (lda & 3) || (ldb & 3) || !aligned16({A, B})) {
@@ -242,7 +266,27 @@ extern "C" int bmp_wgrad_tc(const float *A, int lda, const float *B, int ldb, fl
     a.A = A; a.B = B; a.C = C; a.dbias = dbias; a.lda = lda; a.ldb = ldb; a.ldc = ldc; a.M = M; a.N = N;
     a.bias_stride = bias_stride; a.rows = rows; a.rows_per_cta = 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (N == 64) return wtc::launch<64>(a, st, sms);
-    if (N == 128) return wtc::launch<128>(a, st, sms);
-    return wtc::launch<256>(a, st, sms);
+    if (split3) {
+        if (N == 64) return wtc::launch<64, true>(a, st, sms);
+        if (N == 128) return wtc::launch<128, true>(a, st, sms);
+        return wtc::launch<256, true>(a, st, sms);
+    }
+    if (N == 64) return wtc::launch<64, false>(a, st, sms);
+    if (N == 128) return wtc::launch<128, false>(a, st, sms);
+    return wtc::launch<256, false>(a, st, sms);
+}
+
+// C (M,N; ldc) += A^T B on the tensor cores (bf16 operands, fp32 accumulate); dbias[m*bias_stride] +=
+// column sums of A when non-NULL.  N must be 64, 128 or 256 and everything 16-byte aligned; returns
+// BMP_ESHAPE otherwise so the caller can use the fp32 bmp_wgrad.
+extern "C" int bmp_wgrad_tc(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                            int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream) {
+    return wgrad_tc_any(false, A, lda, B, ldb, C, ldc, rows, M, N, dbias, bias_stride, stream);
+}
+
+// The same contraction at fp32-grade accuracy: bf16 hi/lo split of both operands, three UMMAs per product, fp32 accumulate
+// (relative error ~1e-5 against fp64; the BMP_MODE_F32 encoder backward uses it for its parameter gradients).
+extern "C" int bmp_wgrad_tc3(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                             int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream) {
+    return wgrad_tc_any(true, A, lda, B, ldb, C, ldc, rows, M, N, dbias, bias_stride, stream);
 }

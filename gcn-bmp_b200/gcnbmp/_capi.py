@@ -121,6 +121,7 @@ def _load():
         "bmp_linear_backward": [fp, fp, fp, fp, fp, fp, fp, i, i, i, i, vp],
         "bmp_wgrad": [fp, i, fp, i, fp, i, i64, i, i, vp],
         "bmp_wgrad_tc": [fp, i, fp, i, fp, i, i64, i, i, fp, i, vp],
+        "bmp_wgrad_tc3": [fp, i, fp, i, fp, i, i64, i, i, fp, i, vp],
         "bmp_colsum": [fp, i, fp, i, i64, i, vp],
         "bmp_sigmoid_ce": [fp, fp, fp, fp, i, f, vp],
         "bmp_adam_step": [fp, fp, fp, fp, i, f, f, f, f, f, i, vp],
@@ -164,7 +165,7 @@ lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
            "bmp_relgcn_backward", "bmp_relgcn_tc_workspace_bytes", "bmp_rescale_adj", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_coattn_tc_workspace_bytes", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
-           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
+           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_wgrad_tc3", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
            "bmp_atoms_bcast_add_act_forward", "bmp_atoms_bcast_add_act_backward", "bmp_atoms_softmax_forward", "bmp_atoms_softmax_backward",
            "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate", "bmp_nfp_gather", "bmp_embed_forward", "bmp_bimpm_forward", "bmp_bimpm_backward", "bmp_bimpm_workspace_bytes",

@@ -307,6 +307,10 @@ int bmp_wgrad(const float *A, int lda, const float *B, int ldb, float *C, int ld
  * 16-byte aligned operands, else BMP_ESHAPE.  dbias[m*bias_stride] += column sums of A when non-NULL. */
 int bmp_wgrad_tc(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
                  int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream);
+/* The same contraction at fp32-grade accuracy on the tensor cores: bf16 hi/lo split of both operands, three UMMAs per product,
+ * fp32 TMEM accumulate (relative error ~1e-5); what BMP_MODE_F32 uses for the GGNN parameter gradients at hidden 64/128/256.   */
+int bmp_wgrad_tc3(const float *A, int lda, const float *B, int ldb, float *C, int ldc,
+                 int64_t rows, int M, int N, float *dbias, int bias_stride, void *stream);
 /* out[n * out_stride] += sum_r B[r*ldb + n] */
 int bmp_colsum(const float *B, int ldb, float *out, int out_stride, int64_t rows, int N, void *stream);
 

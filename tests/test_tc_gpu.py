@@ -731,3 +731,27 @@ def test_trainer_with_zero_padded_models_matches_plain_autograd():
     yb = (np.random.default_rng(0).random((40, 1)) < 0.3).astype(np.int32)
     ls = [float(tr3.step(a1, A1, a2, A2, yb)) for _ in range(6)]
     assert ls[-1] < ls[0]
+
+
+@pytest.mark.parametrize("rows,M,N,lda_pad", [(5000, 128, 128, 0), (20000, 384, 256, 0), (777, 64, 64, 192)])
+def test_wgrad_tc3_split_precision_is_fp32_grade(rows, M, N, lda_pad):
+    """bmp_wgrad_tc3: C += A^T B on tcgen05 with a bf16 hi/lo split of both operands (three UMMAs per product, fp32 accumulate) --
+    the contraction BMP_MODE_F32 uses for the GGNN parameter gradients.  Relative error vs float64 <= 2e-5 (plain bf16: ~3e-3)."""
+    import ctypes as C
+    import gcnbmp
+    K = gcnbmp._capi
+    rng = np.random.default_rng(rows + N)
+    lda = M + lda_pad
+    A = rng.standard_normal((rows, lda)).astype(np.float32)
+    B = rng.standard_normal((rows, N)).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    At, Bt, Ct = torch.tensor(A).cuda(), torch.tensor(B).cuda(), torch.tensor(C0).cuda()
+    bias = torch.zeros(M, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    K.check(K.lib.bmp_wgrad_tc3(p(At), lda, p(Bt), N, p(Ct), N, rows, M, N, p(bias), 1, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    ref = C0.astype(np.float64) + A[:, :M].astype(np.float64).T @ B.astype(np.float64)
+    got = Ct.cpu().numpy()
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= 2e-5, err
+    np.testing.assert_allclose(bias.cpu().numpy(), A[:, :M].astype(np.float64).sum(axis=0), rtol=1e-4, atol=1e-3)
