@@ -344,7 +344,8 @@ def run_gpu(args):
         model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
         fp32_exact = dict(value=round(v32, 1), unit="pairs/s", ms_per_step=round(ms32 / 2, 3), steps=2, warmup=1,
                           e2e=round(e32, 1) if e32 else None, achieved_tflops_step=round(3 * fl["pair_fwd"] * v32 / 1e12 / world, 2),
-                          note="BMP_MODE_F32 (fp32 FFMA kernels): parity <= 1e-4 vs the oracle; e2e with float32 host arrays")
+                          note="BMP_MODE_F32 (fp32 FFMA forward / backward-data kernels, parameter gradients on tcgen05 with a bf16 hi/lo split = "
+                               "fp32-grade): parity <= 1e-4 vs the oracle (measured 3e-6 at this shape); e2e with float32 host arrays")
     # ---- informational: BASELINE config D (GGNN H256 T8 + R1 readout + HolE->1, forward only) on this rank's GPU, same inputs ----
     config_d = None
     if rank == 0 and bf16 and not args.no_config_d:
