@@ -555,6 +555,10 @@ using namespace bmp;
 int bmp_ggnn_forward_tc(const bmp_ggnn_fwd_t *a, void *stream);    // ggnn_tc.cu
 int bmp_ggnn_backward_tc(const bmp_ggnn_bwd_t *a, void *stream);   // ggnn_tc_bwd.cu
 int bmp_ggnn_backward_v2(const bmp_ggnn_bwd_t *a, void *stream);   // ggnn_tc_bwd.cu (bf16 panel stash)
+// ggnn_x3.cu: BMP_MODE_F32 with the contractions on tcgen05 (bf16 hi/lo split, fp32-grade), when a workspace is given
+bool bmp_ggnn_x3_usable(int mb, int N, int H, int E, int T, const void *ws, size_t ws_bytes, const void *state_in, bool inference);
+int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream);
+int bmp_ggnn_backward_x3(const bmp_ggnn_bwd_t *a, void *stream);
 
 extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
     if (!a || !a->adj || (!a->atoms && !a->h_in) || (a->atoms && !a->embed_W)) {
@@ -582,6 +586,14 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
         return BMP_EINVAL;
     }
     const int H = a->hidden;
+    if (bmp_ggnn_x3_usable(a->mb, a->n_atoms, H, a->n_edge, a->n_steps, a->tc_workspace, a->tc_workspace_bytes, a->state_in, a->Hs == nullptr)) {
+        bool al = true;
+        for (int t = 0; t < a->n_steps; ++t) {
+            const bmp_gru_t &g = a->gru[t];
+            al = al && aligned16({a->msg_b[t], g.b_Wr, g.b_Ur, g.b_Wz, g.b_Uz, g.b_W, g.b_U});
+        }
+        if (al) return bmp_ggnn_forward_x3(a, stream);
+    }
     const bool sep = a->state_in != nullptr;
     size_t smem = fwd_smem_bytes(H, sep, a->n_edge);
     if (smem > 227 * 1024) {
@@ -649,8 +661,12 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         set_error("bmp_ggnn_backward: stash buffers must be 16-byte aligned");
         return BMP_EINVAL;
     }
+    const bool x3_data = a->mode == BMP_MODE_F32 &&
+                         bmp_ggnn_x3_usable(a->mb, a->n_atoms, H, E, T, a->tc_workspace, a->tc_workspace_bytes, a->state_in, false);
     if (tc_data) {
         if ((rc = bmp_ggnn_backward_tc(a, stream))) return rc;
+    } else if (x3_data) {
+        if ((rc = bmp_ggnn_backward_x3(a, stream))) return rc;
     } else {
         size_t smem = bwd_smem_bytes(H);
         int dev = 0, sms = 148;

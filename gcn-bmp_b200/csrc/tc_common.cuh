@@ -23,14 +23,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// A waiting thread is SUSPENDED (it wakes when the phase completes, or after this many nanoseconds to re-test) instead of
+// re-issuing try_wait back to back: a spinning elected lane would otherwise take most of its scheduler's issue slots from
+// the epilogue warps that share the scheduler.
+constexpr uint32_t MBAR_SUSPEND_NS = 20000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -25,14 +25,15 @@ constexpr int BLK = 64 * 128;     // one MN block: 64 k-rows x 64 columns bf16
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+constexpr uint32_t MBAR_SUSPEND_NS = 20000;     // suspend-time hint of try_wait (see tc_common.cuh)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);

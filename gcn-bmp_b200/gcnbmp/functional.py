@@ -131,6 +131,21 @@ def _tc_images(kind, nbytes, dev, params):
     return ws, 0
 
 
+F32_TENSOR_CORES = True     # MODE_F32: run the encoder's contractions on tcgen05 with a bf16 hi/lo split (fp32-grade); False = FFMA kernels
+
+
+def _x3_workspace(a, mb, N, H, E, T, dev, params, inference):
+    """MODE_F32 on the tensor cores: hand the call a workspace (weight images + temporaries) when the shape is covered."""
+    if not F32_TENSOR_CORES:
+        return None
+    nbytes = int(K.lib.bmp_ggnn_x3_workspace_bytes(mb, N, H, E, T, int(inference)))
+    if nbytes == 0:
+        return None
+    ws, a.tc_images_ready = _tc_images("ggnn_x3", nbytes, dev, params)
+    a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
+    return ws
+
+
 _GRAD_SINK = False
 
 
@@ -220,6 +235,9 @@ class GGNNEncode(torch.autograd.Function):
             ctx.mol_index = mol_index
             ctx.meta = (plan, n_msg, n_gru, mode, is_ids, (mb, N, H))
             return out
+        x3ws = None
+        if mode == K.MODE_F32 and state_in is None and mol_index is None and not adj_u8:
+            x3ws = _x3_workspace(a, mb, N, H, E, T, dev, params, not want_stash)
         if want_stash:
             Hs = torch.empty((T + 1, mb, N, H), device=dev, dtype=torch.float32)
             Ms = torch.empty((T, rows, H), device=dev, dtype=torch.float32)
@@ -230,6 +248,7 @@ class GGNNEncode(torch.autograd.Function):
             ctx.save_for_backward(x, adj, state_in, Hs, Ms, Gs, RSs, *params)
             ctx.mol_index = mol_index
             ctx.meta = (plan, n_msg, n_gru, mode, is_ids, None)
+            ctx.x3 = x3ws is not None
             return Hs
         out = torch.empty((2, mb, N, H), device=dev, dtype=torch.float32)   # [h_0, h_T]
         a.h0_out, a.h_out = _p(out[0]), _p(out[1])
@@ -272,6 +291,9 @@ class GGNNEncode(torch.autograd.Function):
             nbytes = int(K.lib.bmp_ggnn_tc_workspace_bytes(H, T))
             ws, a.tc_images_ready = _tc_images("ggnn_bwd", nbytes, adj.device, params)
             a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
+        if mode == K.MODE_F32 and getattr(ctx, "x3", False):
+            # same kind and size as the forward's: the images packed there (same parameter values) are found ready
+            _x3_workspace(a, mb, N, H, E, T, adj.device, params, False)
         K.check(K.lib.bmp_ggnn_backward(C.byref(a), _stream()))
         dx = None
         if is_ids:

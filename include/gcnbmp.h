@@ -102,6 +102,13 @@ typedef struct {
 int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream);
 /* Bytes of device workspace the BMP_MODE_BF16 (tcgen05) encoder needs; 0 = shape unsupported. */
 size_t bmp_ggnn_tc_workspace_bytes(int hidden, int n_steps);
+/* BMP_MODE_F32 on the tensor cores (csrc/ggnn_x3.cu): when tc_workspace / tc_workspace_bytes of a BMP_MODE_F32 call hold at
+ * least this many bytes (and state_in is NULL), every H x H contraction of the encoder runs on tcgen05 with a bf16 hi/lo
+ * operand split -- three UMMAs per product, fp32 accumulate: the <= 1e-4 parity of the mode is kept -- instead of the FFMA
+ * kernels; same stash, same results up to fp32 rounding order.  `inference` != 0: the call passes no stash (adds a one-step
+ * stash to the workspace).  The backward must be given a workspace sized with inference = 0; dHs[t] is then updated in
+ * place for every t (the FFMA path only writes dHs[0]).  0 = shape not covered (hidden 64/128/256, 4 bond types).          */
+size_t bmp_ggnn_x3_workspace_bytes(int mb, int n_atoms, int hidden, int n_edge, int n_steps, int inference);
 /* Bytes of the bf16 panel stash (forward operand panels + gate values + backward delta/P panels). */
 size_t bmp_ggnn_stash2_bytes(int mb, int hidden, int n_steps);
 
