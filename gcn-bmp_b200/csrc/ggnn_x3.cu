@@ -7,7 +7,7 @@
 // short sequence of launches over the FLAT row space (rows = mb * N atoms; the GEMMs never see molecule boundaries):
 //
 //   forward step t        agg_fwd      AH_e = A_e h_t (sparse rows of the dense adjacency, FFMA), deg_e = A_e 1
-//                         rowgemm3     m   = [AH_0 .. AH_3] [W_0 .. W_3]^T + sum_e deg_e b_e           -> Ms[t]
+//                         rowgemm3     m   = [AH_0 .. AH_3 | deg] [W_0 .. W_3 | b]^T  (the bias rides as a K block)  -> Ms[t]
 //                         rowgemm3     r,z = sigma([h | m] [W_r + U_r | ..]^T + b), r*h                -> Gs[t], RSs[t]
 //                         rowgemm3     hb  = tanh([h | m | r*h] [W | U]^T + b), h' = z hb + (1 - z) h  -> Gs[t], Hs[t+1]
 //   backward step t       gate_bwd     delta_z, delta_h, g (1 - z)            (pointwise)
@@ -19,28 +19,31 @@
 //
 // rowgemm3: one persistent CTA per SM; a work item = (128-row tile, job), jobs of one launch interleaved so the CTAs that
 // share an A tile run at the same time (second reader hits L2).  Warp roles: 8 epilogue warps (TMEM lane quarter x column half),
-// 6 converter warps (fp32 rows -> hi / lo SW128 K-major panels; two k-tiles of cp.async copies in flight per CTA in
-// thread-private shared-memory slots, later k-tiles prefetched towards L2), one producer lane (packed hi / lo weight k-tiles, cp.async.bulk + mbarrier), one MMA lane.  Two 128-column
+// 6 converter warps (fp32 rows, landed in a two-deep shared-memory ring by one cp.async.bulk copy per row, -> hi / lo
+// SW128 K-major panels), one producer warp (fp32 A rows and packed hi / lo weight k-tiles, cp.async.bulk + mbarrier), one MMA lane.  Two 128-column
 // TMEM accumulators alternate between consecutive items, so an item's epilogue overlaps the next item's MMAs.
 #include <cstring>
+#include <cuda.h>
 #include "tc_common.cuh"
 
 namespace bmp {
 namespace x3 {
 using namespace tc;
 
-constexpr int MAXB = 4, MAXJ = 4;
+constexpr int MAXB = 5, MAXJ = 4;
 constexpr int STAGES = 2;
-constexpr int STAGE_BYTES = 4 * PANEL_BYTES;      // [A_hi | A_lo | W_hi | W_lo]
-constexpr int F32_DEPTH = 2;                      // fp32 A k-tiles in flight per CTA (cp.async into thread-private slots)
+constexpr int STAGE_BYTES = 2 * PANEL_BYTES;      // converted A operand: [A_hi | A_lo]
+constexpr int WDEPTH = 3;                         // packed weight k-tiles in flight (own ring: the L2 latency of a tile is hidden)
+constexpr int F32_DEPTH = 2;                      // fp32 A k-tiles in flight per CTA (cp.async.bulk row copies)
 constexpr int WSLOT = 2 * PANEL_BYTES;            // one packed weight k-tile: hi (n x 64 bf16, SW128) then lo
 constexpr int NEPI_W = 8, NCONV_W = 6;
 constexpr int NT = 32 * (NEPI_W + NCONV_W + 2);   // 512 threads: 128 registers each
 constexpr int NCONV = 32 * NCONV_W;
 constexpr int NU = (2048 + NCONV - 1) / NCONV;    // float4 of a 128 x 64 fp32 k-tile per converter thread (last round partial)
-constexpr int OFF_F32 = STAGES * STAGE_BYTES;     // [depth][NU][NCONV threads] float4
-constexpr int OFF_STG = OFF_F32 + F32_DEPTH * NU * NCONV * 16;     // epilogue transposition staging: 2 KB per warp
-constexpr int OFF_BAR = OFF_STG + NEPI_W * 2048;
+constexpr int F32_SLOT = 128 * 256;                // one fp32 A k-tile: 128 rows x 64 floats, row-major (a bulk copy per row)
+constexpr int OFF_WR = STAGES * STAGE_BYTES;        // weight ring: WDEPTH x [W_hi | W_lo]
+constexpr int OFF_F32 = OFF_WR + WDEPTH * 2 * PANEL_BYTES;
+constexpr int OFF_BAR = OFF_F32 + F32_DEPTH * F32_SLOT;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 
 enum { EPI_MSG = 0, EPI_R, EPI_Z, EPI_HB, EPI_Q, EPI_DHX, EPI_DM, EPI_DHMSG };
@@ -55,9 +58,9 @@ struct Job {
     int li0, li1, li2;
     float *out0, *out1, *out2;
     int lo0, lo1, lo2;
-    const float *deg, *msg_b;        // EPI_MSG: deg (rows, 4); msg_b + n0 * 4 (the reference's b[c*E+e])
 };
 struct Args {
+    CUtensorMap tmap[MAXJ][MAXB];    // K-block b of job j as a 2-D fp32 tensor (rows x 64 kt[b] columns, row stride lda[b]); box 128 x 64
     Job job[MAXJ];
     int njobs, NC;                   // NC = columns per job: 64 or 128
     long rows;
@@ -79,6 +82,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
 }
+// tcgen05.ld 16x256b.x2: 16 TMEM lanes x 16 columns; thread t gets, for column group j (8 columns) and row half rh,
+// registers 4 j + 2 rh + {0, 1} = (lane t / 4 + 8 rh, columns 8 j + 2 (t % 4) + {0, 1})
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <bool DBG>
@@ -91,15 +101,21 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
     auto EMPTY = [&](int s) { return s_bar + 8u * (STAGES + s); };
     auto ACCF = [&](int b) { return s_bar + 8u * (2 * STAGES + b); };
     auto ACCE = [&](int b) { return s_bar + 8u * (2 * STAGES + 2 + b); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * STAGES + 4) + 8);
+    auto F32F = [&](int d) { return s_bar + 8u * (2 * STAGES + 4 + d); };
+    auto F32E = [&](int d) { return s_bar + 8u * (2 * STAGES + 4 + F32_DEPTH + d); };
+    auto WFULL = [&](int d) { return s_bar + 8u * (2 * STAGES + 4 + 2 * F32_DEPTH + d); };
+    auto WEMPTY = [&](int d) { return s_bar + 8u * (2 * STAGES + 4 + 2 * F32_DEPTH + WDEPTH + d); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * STAGES + 4 + 2 * F32_DEPTH + 2 * WDEPTH) + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NC = a.NC, njobs = a.njobs;
     const long nrows = a.rows;
     const long ntiles = (nrows + 127) / 128, nitems = ntiles * njobs;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), NCONV_W + 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), NCONV_W); mbar_init(EMPTY(s), 1); }
+        for (int d = 0; d < WDEPTH; ++d) { mbar_init(WFULL(d), 1); mbar_init(WEMPTY(d), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(ACCF(b), 1); mbar_init(ACCE(b), NEPI_W); }
+        for (int d = 0; d < F32_DEPTH; ++d) { mbar_init(F32F(d), 1); mbar_init(F32E(d), NCONV_W); }
         fence_mbar_init();
     }
     if (warp == NEPI_W + NCONV_W + 1) {
@@ -112,21 +128,44 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
     const uint32_t tmem = *tmem_slot;
 
     if (warp == NEPI_W + NCONV_W) {
-        // ===================== producer: packed weight k-tiles
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint32_t wb = (uint32_t)NC * 128u;
-            for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
-                const Job &J = a.job[(int)(w % njobs)];
-                int nk = 0;
-                for (int b = 0; b < J.nblk; ++b) nk += J.kt[b];
-                for (int k = 0; k < nk; ++k) {
-                    mbar_wait_sleep(EMPTY(stage), phase ^ 1, 100);
-                    mbar_expect_tx(FULL(stage), 2 * wb);
-                    const uint32_t dst = sbase + stage * STAGE_BYTES + 2 * PANEL_BYTES;
-                    tma_bulk_g2s(dst, J.wimg + (size_t)k * WSLOT, wb, FULL(stage));
-                    tma_bulk_g2s(dst + PANEL_BYTES, J.wimg + (size_t)k * WSLOT + PANEL_BYTES, wb, FULL(stage));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        // ===================== producer (whole warp): per k-tile the fp32 A rows (one 256-byte bulk copy per row, four
+        // rows per lane, into the fp32 ring) and the packed hi / lo weight tile (lane 0, into the operand stage)
+        uint32_t stage = 0, phase = 0, slot = 0, fphase = 0;
+        const uint32_t wb = (uint32_t)NC * 128u;
+        for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+            const Job &J = a.job[(int)(w % njobs)];
+            const long row0 = (w / njobs) * 128;
+            const int left = nrows - row0 >= 128 ? 128 : (int)(nrows - row0);
+            {   // the item's epilogue inputs towards L2
+                const int lpr = NC / 32;
+                for (int idx = lane; idx < left * lpr; idx += 32) {
+                    const long row = row0 + idx / lpr;
+                    const int c0 = (idx % lpr) * 32;
+                    if (J.in0) prefetch_l2(J.in0 + row * J.li0 + c0);
+                    if (J.in1) prefetch_l2(J.in1 + row * J.li1 + c0);
+                    if (J.in2) prefetch_l2(J.in2 + row * J.li2 + c0);
+                }
+            }
+            int k = 0;
+            for (int b = 0; b < J.nblk; ++b) {
+                for (int kb = 0; kb < J.kt[b]; ++kb, ++k) {
+                    if (lane == 0) {
+                        mbar_wait_sleep(F32E(slot), fphase ^ 1, 100);
+                        mbar_expect_tx(F32F(slot), (uint32_t)F32_SLOT);
+                        // one tensor copy: 128 rows x 64 floats, rows past the end arrive as zeros
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                     ::"r"(sbase + OFF_F32 + slot * F32_SLOT), "l"(&a.tmap[(int)(w % njobs)][b]), "r"(kb * 64), "r"((int)row0),
+                                       "r"(F32F(slot)) : "memory");
+                    }
+                    if (++slot == F32_DEPTH) { slot = 0; fphase ^= 1; }
+                    if (lane == 0) {
+                        mbar_wait_sleep(WEMPTY(stage), phase ^ 1, 100);
+                        mbar_expect_tx(WFULL(stage), 2 * wb);
+                        const uint32_t wd = sbase + OFF_WR + stage * 2 * PANEL_BYTES;
+                        tma_bulk_g2s(wd, J.wimg + (size_t)k * WSLOT, wb, WFULL(stage));
+                        tma_bulk_g2s(wd + PANEL_BYTES, J.wimg + (size_t)k * WSLOT + PANEL_BYTES, wb, WFULL(stage));
+                    }
+                    if (++stage == WDEPTH) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -134,9 +173,9 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
         // ===================== MMA issuer
         if (lane == 0) {
             const uint32_t ID = idesc(NC, 0);
-            uint32_t stage = 0, phase = 0, it = 0;
+            uint32_t stage = 0, phase = 0, ws = 0, wphase = 0, it = 0;
             const bool dbg = DBG && blockIdx.x == 0;
-            long long t_all = dbg ? clock64() : 0, w_full = 0, w_acce = 0, t0 = 0;
+            long long t_all = dbg ? clock64() : 0, w_full = 0, w_wfull = 0, w_acce = 0, t0 = 0;
             for (long w = blockIdx.x; w < nitems; w += gridDim.x, ++it) {
                 const Job &J = a.job[(int)(w % njobs)];
                 int nk = 0;
@@ -149,144 +188,80 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
                 const uint32_t d = tmem + buf * 128;
                 for (int k = 0; k < nk; ++k) {
                     if (dbg) t0 = clock64();
-                    mbar_wait_sleep(FULL(stage), phase, 32);
+                    mbar_wait(WFULL(ws), wphase);
+                    if (dbg) { w_wfull += clock64() - t0; t0 = clock64(); }
+                    mbar_wait(FULL(stage), phase);
                     if (dbg) w_full += clock64() - t0;
                     tc_fence_after();
-                    const uint32_t sa = sbase + stage * STAGE_BYTES;
+                    const uint32_t sa = sbase + stage * STAGE_BYTES, sw = sbase + OFF_WR + ws * 2 * PANEL_BYTES;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t ah = desc_kmajor(sa + ks * 32), al = desc_kmajor(sa + PANEL_BYTES + ks * 32);
-                        const uint64_t wh = desc_kmajor(sa + 2 * PANEL_BYTES + ks * 32), wl = desc_kmajor(sa + 3 * PANEL_BYTES + ks * 32);
+                        const uint64_t wh = desc_kmajor(sw + ks * 32), wl = desc_kmajor(sw + PANEL_BYTES + ks * 32);
                         tc_mma(d, ah, wh, ID, (k | ks) ? 1u : 0u);      // hi . hi
                         tc_mma(d, al, wh, ID, 1u);                      // lo . hi
                         tc_mma(d, ah, wl, ID, 1u);                      // hi . lo
                     }
                     tc_commit(EMPTY(stage));
+                    tc_commit(WEMPTY(ws));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++ws == WDEPTH) { ws = 0; wphase ^= 1; }
                 }
                 tc_commit(ACCF(buf));
             }
-            if (dbg) { a.dbg[0] = clock64() - t_all; a.dbg[1] = w_full; a.dbg[2] = w_acce; }
+            if (dbg) { a.dbg[0] = clock64() - t_all; a.dbg[1] = w_full; a.dbg[2] = w_acce; a.dbg[7] = w_wfull; }
         }
     } else if (warp >= NEPI_W) {
         // ===================== converters: fp32 rows -> bf16 hi / lo K-major panels
         // Thread ct owns the 16-byte piece p = ct & 15 of the rows r0 + 12 u (r0 = ct >> 4, u = 0..10; the last round
-        // only for ct < 128): global source, private slot and swizzled panel offset are a base plus a constant per round.
+        // only for ct < 128): fp32 source and swizzled panel offset are a base plus a constant per round.
         const int ct = tid - 32 * NEPI_W;
         const int r0 = ct >> 4, p = ct & 15;
         const bool last_round = ct < 2048 - (NU - 1) * NCONV;
         const uint32_t sw_a = (uint32_t)r0 * 128u + ((((uint32_t)(p >> 1)) ^ ((uint32_t)r0 & 7u)) << 4) + (uint32_t)(p & 1) * 8u;
         const uint32_t sw_b = (uint32_t)r0 * 128u + ((((uint32_t)(p >> 1)) ^ ((uint32_t)(r0 + 4) & 7u)) << 4) + (uint32_t)(p & 1) * 8u;
-        const uint32_t f32_mine = sbase + OFF_F32 + (uint32_t)ct * 16u;
-        struct Cur { long w; int b, k; };
-        auto valid = [&](const Cur &c) { return c.w < nitems; };
-        auto advance = [&](Cur c) {
-            const Job &J = a.job[(int)(c.w % njobs)];
-            if (++c.k == J.kt[c.b]) { c.k = 0; if (++c.b == J.nblk) { c.b = 0; c.w += gridDim.x; } }
-            return c;
-        };
-        // issue this thread's asynchronous 16-byte copies of a k-tile into its private slots (rows beyond the end: zero-fill)
-        auto issue = [&](const Cur &c, int slot) {
-            const Job &J = a.job[(int)(c.w % njobs)];
-            const long row0 = (c.w / njobs) * 128;
-            const long lda = J.lda[c.b];
-            const float *src = J.A[c.b] + (row0 + r0) * lda + c.k * 64 + p * 4;
-            const long step = 12 * lda;
-            const uint32_t dst = f32_mine + (uint32_t)slot * (NU * NCONV * 16u);
-            if (row0 + 128 <= nrows) {
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    if (u < NU - 1 || last_round)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)u * (NCONV * 16u)), "l"(src) : "memory");
-                    src += step;
-                }
-            } else {
-                const int left = (int)(nrows - row0);
-#pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    const bool live = r0 + 12 * u < left;
-                    if (u < NU - 1 || last_round)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)u * (NCONV * 16u)),
-                                     "l"(live ? src : J.A[c.b]), "r"(live ? 16 : 0) : "memory");
-                    src += step;
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        // pull a k-tile (and, at the first k-tile of an item, the item's epilogue inputs) towards L2: thread ct < 128 = row ct
-        auto prefetch = [&](const Cur &c) {
-            if (ct >= 128) return;
-            const Job &J = a.job[(int)(c.w % njobs)];
-            const long row = (c.w / njobs) * 128 + ct;
-            if (row >= nrows) return;
-            const float *src = J.A[c.b] + row * J.lda[c.b] + c.k * 64;
-            prefetch_l2(src);
-            prefetch_l2(src + 32);
-            if (c.b == 0 && c.k == 0) {
-                for (int c0 = 0; c0 < NC; c0 += 32) {
-                    if (J.in0) prefetch_l2(J.in0 + row * J.li0 + c0);
-                    if (J.in1) prefetch_l2(J.in1 + row * J.li1 + c0);
-                    if (J.in2) prefetch_l2(J.in2 + row * J.li2 + c0);
-                }
-            }
-        };
-        constexpr int PF = 4;
-        uint32_t stage = 0, phase = 0;
-        Cur cur{(long)blockIdx.x, 0, 0};
-        Cur pf = cur;
-        for (int i = 0; i < PF && valid(pf); ++i) {
-            prefetch(pf);
-            pf = advance(pf);
-        }
+        const uint32_t f32_mine = sbase + OFF_F32 + (uint32_t)r0 * 256u + (uint32_t)p * 16u;
         const bool dbg = DBG && blockIdx.x == 0 && ct == 0;
         long long w_empty = 0, w_conv = 0, t0 = 0;
-        // F32_DEPTH k-tiles in flight: one commit group per k-tile (empty groups past the end keep the count uniform)
-        Cur ahead = cur;
-        for (int i = 0; i < F32_DEPTH; ++i) {
-            if (valid(ahead)) { issue(ahead, i); ahead = advance(ahead); }
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        int slot = 0;
-        while (valid(cur)) {
-            if (valid(pf)) {
-                prefetch(pf);
-                pf = advance(pf);
-            }
-            asm volatile("cp.async.wait_group %0;" ::"n"(F32_DEPTH - 1) : "memory");
-            if (dbg) t0 = clock64();
-            mbar_wait_sleep(EMPTY(stage), phase ^ 1, 100);
-            if (dbg) { w_empty += clock64() - t0; t0 = clock64(); }
-            const uint32_t hi = sbase + stage * STAGE_BYTES, mine = f32_mine + (uint32_t)slot * (NU * NCONV * 16u);
+        uint32_t stage = 0, phase = 0, slot = 0, fphase = 0;
+        for (long w = blockIdx.x; w < nitems; w += gridDim.x) {
+            const Job &J = a.job[(int)(w % njobs)];
+            int nk = 0;
+            for (int b = 0; b < J.nblk; ++b) nk += J.kt[b];
+            for (int k = 0; k < nk; ++k) {
+                if (dbg) t0 = clock64();
+                mbar_wait(F32F(slot), fphase);
+                mbar_wait(EMPTY(stage), phase ^ 1);
+                if (dbg) { w_empty += clock64() - t0; t0 = clock64(); }
+                const uint32_t hi = sbase + stage * STAGE_BYTES, mine = f32_mine + slot * F32_SLOT;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                if (u == NU - 1 && !last_round) break;
-                float4 x;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(mine + (uint32_t)u * (NCONV * 16u)));
-                const uint32_t off = hi + ((u & 1) ? sw_b : sw_a) + (uint32_t)u * (12u * 128u);
-                const uint32_t hx = pack_bf16(x.x, x.y), hy = pack_bf16(x.z, x.w);
-                const uint32_t lx = pack_bf16(x.x - __uint_as_float(hx << 16), x.y - __uint_as_float(hx & 0xFFFF0000u));
-                const uint32_t ly = pack_bf16(x.z - __uint_as_float(hy << 16), x.w - __uint_as_float(hy & 0xFFFF0000u));
-                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(off), "r"(hx), "r"(hy) : "memory");
-                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(off + PANEL_BYTES), "r"(lx), "r"(ly) : "memory");
+                for (int u = 0; u < NU; ++u) {
+                    if (u == NU - 1 && !last_round) break;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(mine + (uint32_t)u * (12u * 256u)));
+                    const uint32_t off = hi + ((u & 1) ? sw_b : sw_a) + (uint32_t)u * (12u * 128u);
+                    const uint32_t hx = pack_bf16(x.x, x.y), hy = pack_bf16(x.z, x.w);
+                    const uint32_t lx = pack_bf16(x.x - __uint_as_float(hx << 16), x.y - __uint_as_float(hx & 0xFFFF0000u));
+                    const uint32_t ly = pack_bf16(x.z - __uint_as_float(hy << 16), x.w - __uint_as_float(hy & 0xFFFF0000u));
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(off), "r"(hx), "r"(hy) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(off + PANEL_BYTES), "r"(lx), "r"(ly) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(F32E(slot)); mbar_arrive(FULL(stage)); }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++slot == F32_DEPTH) { slot = 0; fphase ^= 1; }
+                if (dbg) w_conv += clock64() - t0;
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(FULL(stage));
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            // the slot just read is free: refill it with the k-tile F32_DEPTH ahead
-            if (valid(ahead)) { issue(ahead, slot); ahead = advance(ahead); }
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-            if (++slot == F32_DEPTH) slot = 0;
-            cur = advance(cur);
-            if (dbg) w_conv += clock64() - t0;
         }
         if (dbg) { a.dbg[3] = w_empty; a.dbg[4] = w_conv; }
     } else {
-        // ===================== epilogue: TMEM -> pointwise -> global (coalesced through a per-warp transposition block)
-        // warp = TMEM lane quarter (warp & 3) x column half (warp >> 2); 16-column chunks
-        float *stg = reinterpret_cast<float *>(smem + OFF_STG + warp * 2048);
+        // ===================== epilogue: TMEM -> pointwise -> global
+        // warp = TMEM lane quarter (warp & 3) x column half (warp >> 2); 16-column chunks read with the 16x256b shape: a
+        // thread holds column PAIRS of four rows (lane / 4 + 8 rr), so four lanes cover one 32-byte sector of a row and every
+        // global access of the warp moves eight full sectors -- no transposition through shared memory.
         const int q = warp & 3, half = warp >> 2;
-        const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+        const int tr = lane >> 2, tc2 = (lane & 3) * 2;
         const int nch = NC / 32;                               // chunks of this warp
         uint32_t it = 0;
         const bool dbg = DBG && blockIdx.x == 0 && tid == 0;
@@ -295,134 +270,130 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
             const Job &J = a.job[(int)(w % njobs)];
             const int epi = J.epi;
             if (dbg) t0 = clock64();
-            const long wrow0 = (w / njobs) * 128 + 32 * q;           // first row of this warp
-            const long row = wrow0 + lane;
-            const int nlive = nrows - wrow0 >= 32 ? 32 : (int)(nrows - wrow0);   // may be <= 0
+            const long wrow = (w / njobs) * 128 + 32 * q + tr;       // first of this thread's four rows (+ 8 rr)
+            const int live = nrows > wrow ? (int)((nrows - wrow + 7) >> 3) : 0;   // rows rr < live exist
             const uint32_t buf = it & 1, use = it >> 1;
+            const bool u0 = epi == EPI_R || epi == EPI_HB || epi == EPI_Q || epi == EPI_DHMSG || (epi == EPI_DHX && J.in0);
+            const bool u1 = (epi == EPI_HB && J.in1) || epi == EPI_Q || epi == EPI_DHMSG;
+            const bool u2 = epi == EPI_Q;
             mbar_wait_sleep(ACCF(buf), use & 1, 100);
             if (dbg) { w_accf += clock64() - t0; t0 = clock64(); }
             tc_fence_after();
             for (int cc = 0; cc < nch; ++cc) {
-                const int c0 = half * (NC / 2) + cc * 16;
-                auto rp = [nlive, wrow0, c0](const float *p, int ld) {
-                    const float *base = p + wrow0 * ld + c0;
-                    return [=](int r) -> const float * { return r < nlive ? base + r * ld : nullptr; };
+                const int c0 = half * (NC / 2) + cc * 16, col = c0 + tc2;
+                auto LD = [&](const float *p, int ld, float2 (&x)[4][2]) {
+                    const float *b = p + wrow * ld + col;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            x[rr][j] = rr < live ? __ldg(reinterpret_cast<const float2 *>(b + (long)(8 * rr) * ld + 8 * j)) : make_float2(0.f, 0.f);
                 };
-                auto wp = [nlive, wrow0, c0](float *p, int ld) {
-                    float *base = p + wrow0 * ld + c0;
-                    return [=](int r) -> float * { return r < nlive ? base + r * ld : nullptr; };
+                auto ST = [&](float *p, int ld, const float2 (&x)[4][2]) {
+                    float *b = p + wrow * ld + col;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            if (rr < live) *reinterpret_cast<float2 *>(b + (long)(8 * rr) * ld + 8 * j) = x[rr][j];
                 };
                 // the global inputs of the chunk are requested before the accumulator is read
-                float4 x0[4], x1[4];
-                const bool u0 = epi == EPI_R || epi == EPI_HB || epi == EPI_Q || epi == EPI_DHMSG || (epi == EPI_DHX && J.in0);
-                const bool u1 = (epi == EPI_HB && J.in1) || epi == EPI_Q || epi == EPI_DHMSG;
-                if (u0) warp_ldg_rows<16>(x0, lane, rp(J.in0, J.li0));
-                if (u1) warp_ldg_rows<16>(x1, lane, rp(J.in1, J.li1));
-                uint32_t vr[16];
-                tc_ld16(t_lane + buf * 128 + c0, vr);
-                tc_wait_ld();
+                float2 x0[4][2], x1[4][2], x2[4][2], f[4][2];
+                if (u0) LD(J.in0, J.li0, x0);
+                if (u1) LD(J.in1, J.li1, x1);
+                if (u2) LD(J.in2, J.li2, x2);
+                {
+                    uint32_t v0[8], v1[8];
+                    tc_ld_16x256b_x2(tmem + ((uint32_t)(32 * q) << 16) + buf * 128 + c0, v0);
+                    tc_ld_16x256b_x2(tmem + ((uint32_t)(32 * q + 16) << 16) + buf * 128 + c0, v1);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh) {
+                            f[rh][j] = make_float2(__uint_as_float(v0[4 * j + 2 * rh]), __uint_as_float(v0[4 * j + 2 * rh + 1]));
+                            f[2 + rh][j] = make_float2(__uint_as_float(v1[4 * j + 2 * rh]), __uint_as_float(v1[4 * j + 2 * rh + 1]));
+                        }
+                }
                 if (cc == nch - 1) {                                 // every TMEM read of this item is done
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(ACCE(buf));
                 }
-                float f[16], i0[16], i1[16];
-#pragma unroll
-                for (int x = 0; x < 16; ++x) f[x] = __uint_as_float(vr[x]);
-                if (u0) warp_transpose_in<16>(stg, x0, i0, lane);
-                if (u1) warp_transpose_in<16>(stg, x1, i1, lane);
                 if (epi == EPI_R || epi == EPI_Z || epi == EPI_HB) {
 #pragma unroll
-                    for (int x = 0; x < 16; x += 4) {
-                        if (J.bias) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(J.bias + c0 + x));
-                            f[x] += b4.x; f[x + 1] += b4.y; f[x + 2] += b4.z; f[x + 3] += b4.w;
-                        }
+                    for (int j = 0; j < 2; ++j) {
+                        float2 b2 = make_float2(0.f, 0.f);
+                        if (J.bias) b2 = __ldg(reinterpret_cast<const float2 *>(J.bias + col + 8 * j));
                         if (J.bias2) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(J.bias2 + c0 + x));
-                            f[x] += b4.x; f[x + 1] += b4.y; f[x + 2] += b4.z; f[x + 3] += b4.w;
+                            const float2 t2 = __ldg(reinterpret_cast<const float2 *>(J.bias2 + col + 8 * j));
+                            b2.x += t2.x; b2.y += t2.y;
                         }
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) { f[rr][j].x += b2.x; f[rr][j].y += b2.y; }
                     }
                 }
+#define X3_EACH(expr)                                  \
+    _Pragma("unroll") for (int rr = 0; rr < 4; ++rr)   \
+    _Pragma("unroll") for (int j = 0; j < 2; ++j) { expr; }
                 switch (epi) {
-                    case EPI_MSG: {
-                        const float4 d = row < nrows ? __ldg(reinterpret_cast<const float4 *>(J.deg + row * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int x = 0; x < 16; ++x) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(J.msg_b + (c0 + x) * 4));
-                            f[x] += b4.x * d.x + b4.y * d.y + b4.z * d.z + b4.w * d.w;
-                        }
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
-                        break;
-                    }
-                    case EPI_R: {
-#pragma unroll
-                        for (int x = 0; x < 16; ++x) { f[x] = sigmoid_x3(f[x]); i0[x] *= f[x]; }
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
-                        warp_store_rows<16>(stg, i0, lane, wp(J.out1, J.lo1));
+                    case EPI_R: {               // x0 = state
+                        X3_EACH(f[rr][j].x = sigmoid_x3(f[rr][j].x); f[rr][j].y = sigmoid_x3(f[rr][j].y);
+                                x0[rr][j].x *= f[rr][j].x; x0[rr][j].y *= f[rr][j].y)
+                        ST(J.out0, J.lo0, f);
+                        ST(J.out1, J.lo1, x0);
                         break;
                     }
                     case EPI_Z: {
-#pragma unroll
-                        for (int x = 0; x < 16; ++x) f[x] = sigmoid_x3(f[x]);
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
+                        X3_EACH(f[rr][j].x = sigmoid_x3(f[rr][j].x); f[rr][j].y = sigmoid_x3(f[rr][j].y))
+                        ST(J.out0, J.lo0, f);
                         if (J.out1) {           // stateless step: zero r slot and r*state (keeps the merged wgrad contractions exact)
-#pragma unroll
-                            for (int x = 0; x < 16; ++x) f[x] = 0.f;
-                            warp_store_rows<16>(stg, f, lane, wp(J.out1, J.lo1));
-                            warp_store_rows<16>(stg, f, lane, wp(J.out2, J.lo2));
+                            X3_EACH(f[rr][j] = make_float2(0.f, 0.f))
+                            ST(J.out1, J.lo1, f);
+                            ST(J.out2, J.lo2, f);
                         }
                         break;
                     }
-                    case EPI_HB: {              // i0 = z, i1 = state
-#pragma unroll
-                        for (int x = 0; x < 16; ++x) f[x] = tanh_x3(f[x]);
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
+                    case EPI_HB: {              // x0 = z, x1 = state
+                        X3_EACH(f[rr][j].x = tanh_x3(f[rr][j].x); f[rr][j].y = tanh_x3(f[rr][j].y))
+                        ST(J.out0, J.lo0, f);
                         if (u1) {
-#pragma unroll
-                            for (int x = 0; x < 16; ++x) f[x] = i0[x] * f[x] + (1.f - i0[x]) * i1[x];
+                            X3_EACH(f[rr][j].x = x0[rr][j].x * f[rr][j].x + (1.f - x0[rr][j].x) * x1[rr][j].x;
+                                    f[rr][j].y = x0[rr][j].y * f[rr][j].y + (1.f - x0[rr][j].y) * x1[rr][j].y)
                         } else {
-#pragma unroll
-                            for (int x = 0; x < 16; ++x) f[x] = i0[x] * f[x];
+                            X3_EACH(f[rr][j].x *= x0[rr][j].x; f[rr][j].y *= x0[rr][j].y)
                         }
-                        warp_store_rows<16>(stg, f, lane, wp(J.out1, J.lo1));
-                        if (J.out2) warp_store_rows<16>(stg, f, lane, wp(J.out2, J.lo2));
+                        ST(J.out1, J.lo1, f);
+                        if (J.out2) ST(J.out2, J.lo2, f);
                         break;
                     }
-                    case EPI_Q: {               // i0 = state, i1 = r, in2 = ds
-                        float d[16];
-                        warp_load_rows<16>(stg, d, lane, rp(J.in2, J.li2));
-#pragma unroll
-                        for (int x = 0; x < 16; ++x) {
-                            d[x] += f[x] * i1[x];
-                            f[x] = f[x] * i0[x] * i1[x] * (1.f - i1[x]);
-                        }
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
-                        warp_store_rows<16>(stg, d, lane, wp(J.out1, J.lo1));
+                    case EPI_Q: {               // x0 = state, x1 = r, x2 = ds
+                        X3_EACH(x2[rr][j].x += f[rr][j].x * x1[rr][j].x; x2[rr][j].y += f[rr][j].y * x1[rr][j].y;
+                                f[rr][j].x *= x0[rr][j].x * x1[rr][j].x * (1.f - x1[rr][j].x);
+                                f[rr][j].y *= x0[rr][j].y * x1[rr][j].y * (1.f - x1[rr][j].y))
+                        ST(J.out0, J.lo0, f);
+                        ST(J.out1, J.lo1, x2);
                         break;
                     }
                     case EPI_DHX: {
-                        if (u0) {
-#pragma unroll
-                            for (int x = 0; x < 16; ++x) f[x] += i0[x];
-                        }
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
+                        if (u0) { X3_EACH(f[rr][j].x += x0[rr][j].x; f[rr][j].y += x0[rr][j].y) }
+                        ST(J.out0, J.lo0, f);
                         break;
                     }
-                    case EPI_DM:
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
-                        break;
-                    default: {   // EPI_DHMSG
-#pragma unroll
-                        for (int x = 0; x < 16; ++x) f[x] += i0[x] + i1[x];
-                        warp_store_rows<16>(stg, f, lane, wp(J.out0, J.lo0));
+                    case EPI_DHMSG: {
+                        X3_EACH(f[rr][j].x += x0[rr][j].x + x1[rr][j].x; f[rr][j].y += x0[rr][j].y + x1[rr][j].y)
+                        ST(J.out0, J.lo0, f);
                         break;
                     }
+                    default:                    // EPI_MSG (bias rides in the K stream), EPI_DM: the accumulator as it is
+                        ST(J.out0, J.lo0, f);
+                        break;
                 }
+#undef X3_EACH
             }
             if (dbg) w_epi += clock64() - t0;
         }
-        if (dbg) { a.dbg[5] = w_accf; a.dbg[6] = w_epi; a.dbg[7] = it; }
+        if (dbg) { a.dbg[5] = w_accf; a.dbg[6] = w_epi; }
     }
     tc_fence_before();
     __syncthreads();
@@ -435,7 +406,7 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
 // ------------------------------------------------------------------------------------------------ weight images
 // Image of one step's parameters: the k-tiles of the eight jobs in consumption order, per 128-column output chunk.
 //   job        K-blocks (each H/64 k-tiles)                           B element (n = output column, k = K index)
-//   MSG        AH_0 .. AH_3                                           msg_W[(n*4 + e)*H + k]
+//   MSG        AH_0 .. AH_3, deg (one k-tile: columns 0-3 = deg_e)    msg_W[(n*4 + e)*H + k] ; msg_b[n*4 + k] (k < 4)
 //   R          h, m                                                   W_r[n][k] + U_r[n][k] ; W_r[n][H + k]
 //   Z          h, m                                                   W_z[n][k] (+ U_z[n][k] stateful) ; W_z[n][H + k]
 //   HB         h, m, r*h                                              W[n][k] ; W[n][H + k] ; U[n][k]
@@ -444,16 +415,17 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
 //   DM         delta_z, delta_h, delta_r                              W_z[k][H + n] ; W[k][H + n] ; W_r[k][H + n]
 //   DHMSG      P_0 .. P_3                                             msg_W[(k*4 + e)*H + n]
 __host__ __device__ inline int job_blocks(int j) { return (j == EPI_MSG || j == EPI_DHMSG) ? 4 : (j == EPI_Q ? 1 : (j == EPI_R || j == EPI_Z) ? 2 : 3); }
+__host__ __device__ inline int job_ktiles(int j, int H) { return job_blocks(j) * (H / 64) + (j == EPI_MSG ? 1 : 0); }   // per column chunk
 __host__ __device__ inline int job_tile0(int j, int H) {      // first k-tile of job j (chunk 0) inside an image
-    const int kb = H / 64, hc = (H + 127) / 128;
+    const int hc = (H + 127) / 128;
     int t = 0;
-    for (int i = 0; i < j; ++i) t += job_blocks(i) * kb * hc;
+    for (int i = 0; i < j; ++i) t += job_ktiles(i, H) * hc;
     return t;
 }
 __host__ __device__ inline int image_tiles(int H) { return job_tile0(8, H); }
 
 struct PackArgs {
-    const float *msg_W;
+    const float *msg_W, *msg_b;
     bmp_gru_t g;
     int H, stateful;
     uint8_t *img;
@@ -463,15 +435,15 @@ __global__ void __launch_bounds__(256) pack_x3_kernel(const PackArgs a) {
     const int H = a.H, kb = H / 64, hc = (H + 127) / 128, NC = H < 128 ? H : 128;
     int tile = blockIdx.x, j = 0;
     while (j < 7 && tile >= job_tile0(j + 1, H)) ++j;
-    const int local = tile - job_tile0(j, H), per = job_blocks(j) * kb;
-    const int nc = local / per, kk = local % per, b = kk / kb, kbase = (kk % kb) * 64;
+    const int local = tile - job_tile0(j, H), per = job_ktiles(j, H);
+    const int nc = local / per, kk = local % per, b = kk / kb, kbase = (kk % kb) * 64;      // b == 4 (MSG only): the bias k-tile
     (void)hc;
     const bool st = a.stateful != 0;
     auto val = [&](int n, int k) -> float {       // n: global output column, k: column inside K-block b
         const bmp_gru_t &g = a.g;
         const long H2 = 2L * H;
         switch (j) {
-            case EPI_MSG: return a.msg_W[((long)n * 4 + b) * H + k];
+            case EPI_MSG: return b < 4 ? a.msg_W[((long)n * 4 + b) * H + k] : (k < 4 && a.msg_b ? a.msg_b[(long)n * 4 + k] : 0.f);
             case EPI_R: return b == 0 ? (st ? g.W_r[n * H2 + k] + g.U_r[(long)n * H + k] : 0.f) : (st ? g.W_r[n * H2 + H + k] : 0.f);
             case EPI_Z: return b == 0 ? g.W_z[n * H2 + k] + (st ? g.U_z[(long)n * H + k] : 0.f) : g.W_z[n * H2 + H + k];
             case EPI_HB: return b == 0 ? g.W[n * H2 + k] : (b == 1 ? g.W[n * H2 + H + k] : (st ? g.U[(long)n * H + k] : 0.f));
@@ -504,7 +476,8 @@ __global__ void __launch_bounds__(256) pack_x3_kernel(const PackArgs a) {
 // ------------------------------------------------------------------------------------------------ adjacency products
 // The adjacency is the reference's dense fp32 (mb,E,N,N) array; its rows are scanned for non-zeros (a warp ballot) and only
 // those neighbours are accumulated, in ascending order -- the same sum as the dense product, zeros skipped.
-// AH[row][e*H + c] = sum_j A_e[i][j] h[j][c] ; deg[row][e] = sum_j A_e[i][j]        (one CTA per molecule)
+// AH[row][e*H + c] = sum_j A_e[i][j] h[j][c] ; deg[row][e] = sum_j A_e[i][j] (rows of 64 floats, columns 4.. stay zero:
+// the A operand of the bias k-tile)        (one CTA per molecule)
 __global__ void __launch_bounds__(256) agg_fwd_kernel(const float *__restrict__ adj, const float *__restrict__ h, float *__restrict__ AH,
                                                       float *__restrict__ deg, int mb, int N, int H) {
     extern __shared__ __align__(16) float sh[];                  // [N][H]
@@ -545,7 +518,7 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const float *__restrict__ 
             if (deg) {
                 float d = a0 + a1;
                 for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                if (lane == 0) deg[((long)mol * N + i) * 4 + e] = d;
+                if (lane == 0) deg[((long)mol * N + i) * 64 + e] = d;
             }
         }
     }
@@ -638,6 +611,7 @@ static int sm_count() {
 }
 
 static bool shape_ok(int N, int H, int E) { return (H == 64 || H == 128 || H == 256) && E == 4 && N > 0 && N <= BMP_MAX_ATOMS; }
+constexpr long MIN_ROWS = 128;      // one full row tile (the tensor-map box)
 
 struct Layout {
     size_t img_bytes, tmp_off, deg_off, mini_off, total;
@@ -645,7 +619,7 @@ struct Layout {
         img_bytes = (size_t)image_tiles(H) * WSLOT;
         tmp_off = (size_t)T * img_bytes;
         deg_off = tmp_off + (size_t)rows * 4 * H * sizeof(float);
-        mini_off = deg_off + (((size_t)rows * 4 * sizeof(float) + 1023) & ~(size_t)1023);
+        mini_off = deg_off + (((size_t)rows * 64 * sizeof(float) + 1023) & ~(size_t)1023);
         total = mini_off + (inference ? (size_t)rows * 7 * H * sizeof(float) : 0) + 1024;
     }
 };
@@ -653,8 +627,36 @@ struct Layout {
 static long long *g_dbg = nullptr;
 static int g_dbg_slot = 0;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// the driver entry point is looked up at run time: the library keeps loading on a machine without a driver
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
 static int launch_gemm(Args &g, cudaStream_t st) {
     g.dbg = g_dbg ? g_dbg + 8 * (g_dbg_slot++) : nullptr;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("rowgemm3: cuTensorMapEncodeTiled is not available"); return BMP_ECUDA; }
+    for (int j = 0; j < g.njobs; ++j)
+        for (int b = 0; b < g.job[j].nblk; ++b) {
+            const Job &J = g.job[j];
+            const cuuint64_t dims[2] = {(cuuint64_t)64 * J.kt[b], (cuuint64_t)g.rows};
+            const cuuint64_t strides[1] = {(cuuint64_t)J.lda[b] * sizeof(float)};
+            const cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+            const CUresult r = enc(&g.tmap[j][b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)J.A[b], dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("rowgemm3: cuTensorMapEncodeTiled failed (%d)", (int)r); return BMP_ECUDA; }
+        }
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(rowgemm3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -682,12 +684,16 @@ static void image_plan(const S *a, int *img_of) {
     }
 }
 
+static const float *msg_b_of(const bmp_ggnn_fwd_t *a, int t) { return a->msg_b[t]; }
+static const float *msg_b_of(const bmp_ggnn_bwd_t *, int) { return nullptr; }      // the backward jobs do not use the bias tile
+
 template <class S>
 static int pack_images(const S *a, uint8_t *ws, const Layout &L, const int *img_of, cudaStream_t st) {
     for (int t = 0; t < a->n_steps; ++t) {
         if (img_of[t] != t) continue;
         PackArgs p;
         p.msg_W = a->msg_W[t];
+        p.msg_b = msg_b_of(a, t);
         p.g = a->gru[t];
         p.H = a->hidden;
         p.stateful = a->stateful[t];
@@ -699,7 +705,7 @@ static int pack_images(const S *a, uint8_t *ws, const Layout &L, const int *img_
 }
 
 static const uint8_t *job_img(const uint8_t *img, int j, int nc, int H) {
-    return img + ((size_t)job_tile0(j, H) + (size_t)nc * job_blocks(j) * (H / 64)) * WSLOT;
+    return img + ((size_t)job_tile0(j, H) + (size_t)nc * job_ktiles(j, H)) * WSLOT;
 }
 
 }  // namespace x3
@@ -714,12 +720,12 @@ extern "C" void bmp_debug_set_buffer_x3(void *p) { g_dbg = (long long *)p; g_dbg
 // Bytes of workspace the tensor-core fp32 path needs (weight images + per-step temporaries [+ a one-step stash for
 // inference]); 0 = shape not covered (the FFMA kernels of ggnn.cu run instead).
 extern "C" size_t bmp_ggnn_x3_workspace_bytes(int mb, int n_atoms, int hidden, int n_edge, int n_steps, int inference) {
-    if (!shape_ok(n_atoms, hidden, n_edge) || mb <= 0 || n_steps <= 0 || n_steps > BMP_MAX_STEPS) return 0;
+    if (!shape_ok(n_atoms, hidden, n_edge) || (long)mb * n_atoms < MIN_ROWS || n_steps <= 0 || n_steps > BMP_MAX_STEPS) return 0;
     return Layout((long)mb * n_atoms, hidden, n_steps, inference != 0).total;
 }
 
 bool bmp_ggnn_x3_usable(int mb, int N, int H, int E, int T, const void *ws, size_t ws_bytes, const void *state_in, bool inference) {
-    if (!ws || state_in || !shape_ok(N, H, E)) return false;
+    if (!ws || state_in || !shape_ok(N, H, E) || (long)mb * N < MIN_ROWS) return false;
     return ws_bytes >= Layout((long)mb * N, H, T, inference).total;
 }
 
@@ -750,6 +756,7 @@ int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
     }
     if (a->h0_out) cudaMemcpyAsync(a->h0_out, Hs_at(0), RH * sizeof(float), cudaMemcpyDeviceToDevice, st);
 
+    cudaMemsetAsync(deg, 0, (size_t)rows * 64 * sizeof(float), st);
     const size_t agg_smem = (size_t)N * H * sizeof(float);
     cudaFuncSetAttribute(agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
     const int agg_grid = a->mb < 8 * sm_count() ? a->mb : 8 * sm_count();
@@ -767,11 +774,11 @@ int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
         ga.rows = rows; ga.NC = NC; ga.njobs = hc;
         for (int nc = 0; nc < hc; ++nc) {
             Job &J = ga.job[nc];
-            J.nblk = 4;
+            J.nblk = 5;
             for (int e = 0; e < 4; ++e) { J.A[e] = AH + (size_t)e * H; J.lda[e] = 4 * H; J.kt[e] = kb; }
+            J.A[4] = deg; J.lda[4] = 64; J.kt[4] = 1;
             J.wimg = job_img(img, EPI_MSG, nc, H);
             J.epi = EPI_MSG;
-            J.deg = deg; J.msg_b = a->msg_b[t] + (size_t)nc * 128 * 4;
             J.out0 = m + nc * 128; J.lo0 = H;
         }
         if ((rc = launch_gemm(ga, st))) return rc;

@@ -95,6 +95,22 @@ def test_workspace_size_queries_are_host_only_and_consistent():
         assert lib.bmp_ggnn_stash2_bytes(64, H, 6) == 0
 
 
+def test_fp32_tensor_core_workspace_query_is_host_only():
+    """csrc/ggnn_x3.cu: the BMP_MODE_F32 encoder runs on tcgen05 only when the caller hands it this workspace; the size query
+    runs without a GPU and is 0 for the shapes that stay on the FFMA kernels."""
+    lib = __import__("gcnbmp")._capi.lib
+    q = lib.bmp_ggnn_x3_workspace_bytes
+    for H in (64, 128, 256):
+        n = q(4144, 64, H, 4, 6, 0)
+        rows = 4144 * 64
+        assert n > rows * 4 * H * 4 + rows * 64 * 4                     # per-step temporaries (A_e h for 4 bond types, degrees)
+        assert q(4144, 64, H, 4, 6, 1) >= n + rows * 7 * H * 4          # inference: + a one-step stash
+        assert q(2 * 4144, 64, H, 4, 6, 0) > n
+    assert q(4144, 64, 32, 4, 6, 0) == 0 and q(4144, 64, 96, 4, 6, 0) == 0 and q(4144, 64, 128, 3, 6, 0) == 0
+    assert q(1, 64, 128, 4, 6, 0) == 0                                  # fewer rows than one 128-row tile
+    assert q(4144, 64, 128, 4, 17, 0) == 0
+
+
 def test_chainer_adapter_is_import_guarded():
     """the Chainer / CuPy adapter imports without either package and fails loudly, not silently, when used."""
     from gcnbmp import chainer_adapter as B

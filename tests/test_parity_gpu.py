@@ -422,3 +422,52 @@ def test_config_d_model_trains_at_hidden_256_in_fp32():
     for k, v in o["grads"].items():
         if v is not None and np.abs(v).max() > 1e-12:
             assert rel_err(p["grads"][k], v) <= TOL, k
+
+
+@pytest.mark.parametrize("H,T,tied,N,mb", [(128, 3, True, 64, 5), (128, 2, False, 37, 9), (64, 3, True, 50, 7), (256, 2, True, 30, 6)])
+def test_fp32_mode_on_tensor_cores_matches_oracle_and_the_ffma_kernels(H, T, tied, N, mb):
+    """BMP_MODE_F32 with the encoder's contractions on tcgen05 (csrc/ggnn_x3.cu: bf16 hi/lo split, three UMMAs per product) against
+    the fp64 oracle at the mode's 1e-4 bound, against the FFMA kernels of csrc/ggnn.cu (same stash, same results up to rounding), and
+    its stash-free inference path against its training path.  Row counts are not multiples of the 128-row tile (tail tiles)."""
+    import gcnbmp
+    from gcnbmp import functional as Fn, synthetic
+    rng = np.random.default_rng(H + T + N)
+    O = 40
+    atoms, adj = synthetic.random_molecules(rng, mb, N)
+    assert mb * N >= 128 and (mb * N) % 128 != 0
+    params = R.init_params(R.ggnn_mono_shapes(O, H, T, weight_tying=tied), rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    onet = R.GGNNMono(R.P(tab), O, H, T, weight_tying=tied)
+    w_g, w_a = rng.standard_normal((mb, O)), rng.standard_normal((mb, N, H)) * 0.1
+    og = onet(atoms, adj.astype(np.float64))
+    oa = onet.get_atom_array()
+    F.add(F.sum_(F.mul(og, F.const(w_g))), F.sum_(F.mul(oa, F.const(w_a)))).backward()
+    got = {}
+    try:
+        for tc in (True, False):
+            Fn.F32_TENSOR_CORES = tc
+            net = gcnbmp.GGNNMono(O, H, T, weight_tying=tied)
+            net.load_params(params)
+            net.cleargrads()
+            launches0 = gcnbmp._capi.lib.bmp_launch_count()
+            pg = net(atoms, adj)
+            pa = net.get_atom_array()
+            ((pg * torch.tensor(w_g, dtype=torch.float32, device="cuda")).sum() + (pa * torch.tensor(w_a, dtype=torch.float32, device="cuda")).sum()).backward()
+            got[tc] = dict(g=pg.detach().cpu().numpy(), a=pa.detach().cpu().numpy(), grads=net.grad_dict(),
+                           launches=gcnbmp._capi.lib.bmp_launch_count() - launches0)
+            assert rel_err(got[tc]["g"], og.data) <= TOL and rel_err(got[tc]["a"], oa.data) <= TOL
+            for k in params:
+                if tab[k].grad is not None and np.abs(tab[k].grad).max() > 1e-12:
+                    assert rel_err(got[tc]["grads"][k], tab[k].grad) <= TOL, (tc, k)
+            with torch.no_grad():
+                ig = net(atoms, adj)
+                ia = net.get_atom_array()
+            assert rel_err(ig.cpu().numpy(), got[tc]["g"]) <= 1e-6 and rel_err(ia.cpu().numpy(), got[tc]["a"]) <= 1e-6
+    finally:
+        Fn.F32_TENSOR_CORES = True
+    # the two paths are different kernels (a launch per GEMM vs one fused launch) and agree far inside the bound
+    assert got[True]["launches"] > got[False]["launches"] + 4 * T
+    assert rel_err(got[True]["a"], got[False]["a"]) <= 5e-5
+    for k in params:
+        if np.abs(got[False]["grads"][k]).max() > 1e-12:
+            assert rel_err(got[True]["grads"][k], got[False]["grads"][k]) <= 5e-5, k

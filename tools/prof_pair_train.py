@@ -1,4 +1,5 @@
-"""Profiling target: one BF16-mode pair training micro-batch sequence (2048 pairs, config C shapes) through PairTrainer."""
+"""Profiling target: one pair training micro-batch sequence (config C shapes) through PairTrainer; BF16 mode, or MODE_F32
+with BMP_PROF_FP32=1."""
 import os
 import sys
 
@@ -20,7 +21,7 @@ attn = gcnbmp.NieFineCoattention(H, O, 8, activation=gcnbmp.functions.tanh)
 head = gcnbmp.HolE(K, hidden_dims=())
 head.l_out.ensure(O)        # lazily-shaped layer: materialise before the trainer flattens the parameters
 model = gcnbmp.GraphConvPredictorForPair(enc, attn, head)
-enc.mode = attn.mode = gcnbmp.MODE_BF16
+enc.mode = attn.mode = gcnbmp.MODE_F32 if os.environ.get("BMP_PROF_FP32") else gcnbmp.MODE_BF16
 tr = train.PairTrainer(model, chunk=min(mb, 4144))
 dev = lambda x: torch.tensor(x).cuda()
 args = [dev(a1), dev(A1), dev(a2), dev(A2), dev(y)]

@@ -67,7 +67,7 @@ if __name__ == "__main__":
         lib.bmp_debug_set_buffer_x3(C.c_void_p(0))
         torch.cuda.synchronize()
         d = dbg.cpu().numpy().reshape(-1, 8)
-        names = ["total", "mma:FULL", "mma:ACCE", "conv:EMPTY", "conv:work", "epi:ACCF", "epi:work", "items"]
+        names = ["total", "mma:FULL", "mma:ACCE", "conv:EMPTY", "conv:work", "epi:ACCF", "epi:work", "mma:WFULL"]
         for i in list(range(3, 9)) + list(range(18, 24)):
             print("launch %2d: " % i + "  ".join("%s %d" % (n, v) for n, v in zip(names, d[i])))
         sys.exit(0)
