@@ -327,9 +327,10 @@ def run_gpu(args):
             torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / 3
         ach = nmol * fl["encoder"] / (k_ms * 1e-3) / 1e12
-        roof = dict(kernel="ggnn_fwd_kernel<2> (+readout launch)", bound="tensor", achieved=round(ach, 3), peak=pk["bf16_sustained"],
-                    unit="TFLOP/s", frac=round(ach / pk["bf16_sustained"], 5), traffic=None,
-                    note="fp32 FFMA kernel against the bf16 tensor peak (the roofline that bounds the path)")
+        roof = dict(kernel="GGNN encoder forward in BMP_MODE_F32 (agg_fwd + 3 rowgemm3 launches per step, + readout)", bound="tensor",
+                    achieved=round(ach, 3), peak=pk["bf16_sustained"], unit="TFLOP/s", frac=round(ach / pk["bf16_sustained"], 5), traffic=None,
+                    note="fp32-grade encoder (split-bf16 UMMAs: three tensor-core products per algorithmic one) against the bf16 tensor "
+                         "peak, algorithmic FLOPs counted once")
     step_tflops = 3 * fl["pair_fwd"] * value / 1e12 / world
     roof_step = dict(bound="tensor", achieved=round(step_tflops, 2), peak=pk["bf16_sustained"], unit="TFLOP/s per GPU",
                      frac=round(step_tflops / pk["bf16_sustained"], 4),
@@ -344,8 +345,10 @@ def run_gpu(args):
         model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
         fp32_exact = dict(value=round(v32, 1), unit="pairs/s", ms_per_step=round(ms32 / 2, 3), steps=2, warmup=1,
                           e2e=round(e32, 1) if e32 else None, achieved_tflops_step=round(3 * fl["pair_fwd"] * v32 / 1e12 / world, 2),
-                          note="BMP_MODE_F32 (fp32 FFMA forward / backward-data kernels, parameter gradients on tcgen05 with a bf16 hi/lo split = "
-                               "fp32-grade): parity <= 1e-4 vs the oracle (measured 3e-6 at this shape); e2e with float32 host arrays")
+                          note="BMP_MODE_F32: the GGNN encoder's contractions (forward, backward-data, parameter gradients) on tcgen05 at "
+                               "fp32 grade -- every operand a bf16 hi/lo pair, three UMMAs per product, fp32 TMEM accumulate (csrc/ggnn_x3.cu, "
+                               "wgrad_tc.cu); adjacency products, co-attention, readout, HolE in fp32 FFMA.  Parity <= 1e-4 vs the oracle "
+                               "(measured 4e-6 at this shape); e2e with float32 host arrays")
     # ---- informational: BASELINE config D (GGNN H256 T8 + R1 readout + HolE->1, forward only) on this rank's GPU, same inputs ----
     config_d = None
     if rank == 0 and bf16 and not args.no_config_d:
