@@ -6,14 +6,14 @@
 // UMMAs, hi.hi + lo.hi + hi.lo, into an fp32 TMEM accumulator (the lo.lo term is below fp32 rounding).  The step is a
 // short sequence of launches over the FLAT row space (rows = mb * N atoms; the GEMMs never see molecule boundaries):
 //
-//   forward step t        agg_fwd      AH_e = A_e h_t (sparse rows of the dense adjacency, FFMA), deg_e = A_e 1
+//   forward step t        agg          AH_e = A_e h_t (non-zeros of the dense adjacency through bit masks, FFMA), deg_e = A_e 1
 //                         rowgemm3     m   = [AH_0 .. AH_3 | deg] [W_0 .. W_3 | b]^T  (the bias rides as a K block)  -> Ms[t]
 //                         rowgemm3     r,z = sigma([h | m] [W_r + U_r | ..]^T + b), r*h                -> Gs[t], RSs[t]
 //                         rowgemm3     hb  = tanh([h | m | r*h] [W | U]^T + b), h' = z hb + (1 - z) h  -> Gs[t], Hs[t+1]
 //   backward step t       gate_bwd     delta_z, delta_h, g (1 - z)            (pointwise)
 //                         rowgemm3     q = delta_h U -> delta_r, ds += q r
 //                         rowgemm3     dh_x = [dz | dh | dr] [W_z + U_z | W | W_r + U_r]_h (+ ds) ; dm = [..] [..]_m
-//                         agg_bwd      P_e = A_e^T dm                                                  -> Ps[t]
+//                         agg          P_e = A_e^T dm                                                  -> Ps[t]
 //                         rowgemm3     dHs[t] += dh_x + sum_e P_e W_e
 // The parameter gradients stay where they were: bmp_ggnn_backward's contractions over the stash (bmp_wgrad_tc3).
 //
@@ -474,100 +474,80 @@ __global__ void __launch_bounds__(256) pack_x3_kernel(const PackArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ adjacency products
-// The adjacency is the reference's dense fp32 (mb,E,N,N) array; its rows are scanned for non-zeros (a warp ballot) and only
-// those neighbours are accumulated, in ascending order -- the same sum as the dense product, zeros skipped.
-// AH[row][e*H + c] = sum_j A_e[i][j] h[j][c] ; deg[row][e] = sum_j A_e[i][j] (rows of 64 floats, columns 4.. stay zero:
-// the A operand of the bias k-tile)        (one CTA per molecule)
-__global__ void __launch_bounds__(256) agg_fwd_kernel(const float *__restrict__ adj, const float *__restrict__ h, float *__restrict__ AH,
-                                                      float *__restrict__ deg, int mb, int N, int H) {
-    extern __shared__ __align__(16) float sh[];                  // [N][H]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, HV = H / 4;
+// The adjacency is the reference's dense fp32 (mb,E,N,N) array, > 97 % zeros.  It is scanned ONCE per encoder call into bit masks
+// (64 bits per row and per column of every bond type, 4 KB per molecule instead of 64 KB) plus a flag "some non-zero entry is not
+// 1.0"; the per-step products then walk the set bits in ascending order -- the dense sum with the zeros skipped -- and touch the
+// dense array again only when that flag is set (general fp32 weights).
+// masks[mol][0][e][i] bit j = (A_e[i][j] != 0) ; masks[mol][1][e][j] bit i = (A_e[i][j] != 0)
+__global__ void __launch_bounds__(256) adj_mask_kernel(const float *__restrict__ adj, unsigned long long *__restrict__ masks, int *nonbinary,
+                                                       int mb, int N) {
+    __shared__ unsigned long long cm[4 * 64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int mol = blockIdx.x; mol < mb; mol += gridDim.x) {
         __syncthreads();
-        const float4 *src = reinterpret_cast<const float4 *>(h + (long)mol * N * H);
-        for (int idx = tid; idx < N * HV; idx += 256) reinterpret_cast<float4 *>(sh)[idx] = __ldg(src + idx);
+        cm[tid] = 0ull;
+        unsigned long long *out = masks + (size_t)mol * 512;
+        for (int idx = tid; idx < 256; idx += 256) out[idx] = 0ull;        // row masks of the rows i >= N
         __syncthreads();
+        bool odd = false;
         for (int idx = warp; idx < 4 * N; idx += 8) {
             const int e = idx / N, i = idx - e * N;
             const float *arow = adj + (((long)mol * 4 + e) * N + i) * N;
             const float a0 = lane < N ? __ldg(arow + lane) : 0.f, a1 = lane + 32 < N ? __ldg(arow + lane + 32) : 0.f;
-            uint32_t m0 = __ballot_sync(0xffffffffu, a0 != 0.f), m1 = __ballot_sync(0xffffffffu, a1 != 0.f);
-            float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-            auto fma4 = [](float4 &acc, float s, const float4 &x) {
-                acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y); acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
-            };
-            while (m0) {
-                const int j = __ffs(m0) - 1;
-                m0 &= m0 - 1;
-                const float s = __shfl_sync(0xffffffffu, a0, j);
-                const float4 *hr = reinterpret_cast<const float4 *>(sh + j * H);
-                if (lane < HV) fma4(acc0, s, hr[lane]);
-                if (lane + 32 < HV) fma4(acc1, s, hr[lane + 32]);
-            }
-            while (m1) {
-                const int j = __ffs(m1) - 1;
-                m1 &= m1 - 1;
-                const float s = __shfl_sync(0xffffffffu, a1, j);
-                const float4 *hr = reinterpret_cast<const float4 *>(sh + (j + 32) * H);
-                if (lane < HV) fma4(acc0, s, hr[lane]);
-                if (lane + 32 < HV) fma4(acc1, s, hr[lane + 32]);
-            }
-            float4 *out = reinterpret_cast<float4 *>(AH + ((long)mol * N + i) * 4 * H + (long)e * H);
-            if (lane < HV) out[lane] = acc0;
-            if (lane + 32 < HV) out[lane + 32] = acc1;
-            if (deg) {
-                float d = a0 + a1;
-                for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                if (lane == 0) deg[((long)mol * N + i) * 64 + e] = d;
-            }
+            const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a0 != 0.f) |
+                                         ((unsigned long long)__ballot_sync(0xffffffffu, a1 != 0.f) << 32);
+            if (lane == 0) out[e * 64 + i] = m;
+            if (a0 != 0.f) atomicOr(&cm[e * 64 + lane], 1ull << i);
+            if (a1 != 0.f) atomicOr(&cm[e * 64 + lane + 32], 1ull << i);
+            odd = odd || (a0 != 0.f && a0 != 1.f) || (a1 != 0.f && a1 != 1.f);
         }
+        if (__any_sync(0xffffffffu, odd) && lane == 0) *nonbinary = 1;
+        __syncthreads();
+        out[256 + tid] = cm[tid];
     }
 }
 
-// P[row j][e*H + c] = sum_i A_e[i][j] dm[i][c]      (one CTA per molecule; the bond type's tile is transposed through smem)
-__global__ void __launch_bounds__(256) agg_bwd_kernel(const float *__restrict__ adj, const float *__restrict__ dm, float *__restrict__ P,
-                                                      int mb, int N, int H) {
-    extern __shared__ __align__(16) float sh[];                  // [N][H] dm, then [4][N][N + 1] adjacency
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, HV = H / 4, LD = N + 1;
-    float *At = sh + N * H;
+// BWD = false: dst[row i][e*H + c] = sum_j A_e[i][j] src[j][c]  (A_e h; deg[row][e] = sum_j A_e[i][j] into rows of 64 floats, the A
+//              operand of the bias k-tile)
+// BWD = true : dst[row j][e*H + c] = sum_i A_e[i][j] src[i][c]  (A_e^T dm)                                    one CTA per molecule
+template <bool BWD>
+__global__ void __launch_bounds__(256) agg_kernel(const unsigned long long *__restrict__ masks, const int *__restrict__ nonbinary,
+                                                  const float *__restrict__ adj, const float *__restrict__ src, float *__restrict__ dst,
+                                                  float *__restrict__ deg, int mb, int N, int H) {
+    extern __shared__ __align__(16) float sh[];                  // [N][H]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, HV = H / 4;
+    const bool general = *nonbinary != 0;
     for (int mol = blockIdx.x; mol < mb; mol += gridDim.x) {
         __syncthreads();
-        const float4 *src = reinterpret_cast<const float4 *>(dm + (long)mol * N * H);
-        for (int idx = tid; idx < N * HV; idx += 256) reinterpret_cast<float4 *>(sh)[idx] = __ldg(src + idx);
-        const float *am = adj + (long)mol * 4 * N * N;
-        for (int idx = tid; idx < 4 * N * N; idx += 256) {
-            const int ei = idx / N, j = idx - ei * N;
-            At[ei * LD + j] = __ldg(am + idx);
-        }
+        const float4 *s4 = reinterpret_cast<const float4 *>(src + (long)mol * N * H);
+        for (int idx = tid; idx < N * HV; idx += 256) reinterpret_cast<float4 *>(sh)[idx] = __ldg(s4 + idx);
         __syncthreads();
+        const unsigned long long *mk = masks + (size_t)mol * 512 + (BWD ? 256 : 0);
+        const float *am = adj + (long)mol * 4 * N * N;
         for (int idx = warp; idx < 4 * N; idx += 8) {
-            const int e = idx / N, j = idx - e * N;
-            const float *col = At + (long)e * N * LD + j;
-            const float a0 = lane < N ? col[lane * LD] : 0.f, a1 = lane + 32 < N ? col[(lane + 32) * LD] : 0.f;
-            uint32_t m0 = __ballot_sync(0xffffffffu, a0 != 0.f), m1 = __ballot_sync(0xffffffffu, a1 != 0.f);
+            const int e = idx / N, x = idx - e * N;
+            unsigned long long m = __ldg(mk + e * 64 + x);
             float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-            auto fma4 = [](float4 &acc, float s, const float4 &x) {
-                acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y); acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
-            };
-            while (m0) {
-                const int i = __ffs(m0) - 1;
-                m0 &= m0 - 1;
-                const float s = __shfl_sync(0xffffffffu, a0, i);
-                const float4 *hr = reinterpret_cast<const float4 *>(sh + i * H);
-                if (lane < HV) fma4(acc0, s, hr[lane]);
-                if (lane + 32 < HV) fma4(acc1, s, hr[lane + 32]);
+            float d = 0.f;
+            while (m) {
+                const int y = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const float v = general ? __ldg(am + ((long)e * N + (BWD ? y : x)) * N + (BWD ? x : y)) : 1.f;
+                d += v;
+                const float4 *hr = reinterpret_cast<const float4 *>(sh + y * H);
+                if (lane < HV) {
+                    const float4 t = hr[lane];
+                    acc0.x = fmaf(v, t.x, acc0.x); acc0.y = fmaf(v, t.y, acc0.y); acc0.z = fmaf(v, t.z, acc0.z); acc0.w = fmaf(v, t.w, acc0.w);
+                }
+                if (lane + 32 < HV) {
+                    const float4 t = hr[lane + 32];
+                    acc1.x = fmaf(v, t.x, acc1.x); acc1.y = fmaf(v, t.y, acc1.y); acc1.z = fmaf(v, t.z, acc1.z); acc1.w = fmaf(v, t.w, acc1.w);
+                }
             }
-            while (m1) {
-                const int i = __ffs(m1) - 1;
-                m1 &= m1 - 1;
-                const float s = __shfl_sync(0xffffffffu, a1, i);
-                const float4 *hr = reinterpret_cast<const float4 *>(sh + (i + 32) * H);
-                if (lane < HV) fma4(acc0, s, hr[lane]);
-                if (lane + 32 < HV) fma4(acc1, s, hr[lane + 32]);
-            }
-            float4 *out = reinterpret_cast<float4 *>(P + ((long)mol * N + j) * 4 * H + (long)e * H);
+            float4 *out = reinterpret_cast<float4 *>(dst + ((long)mol * N + x) * 4 * H + (long)e * H);
             if (lane < HV) out[lane] = acc0;
             if (lane + 32 < HV) out[lane + 32] = acc1;
+            if (!BWD && deg && lane == 0) deg[((long)mol * N + x) * 64 + e] = d;
         }
     }
 }
@@ -614,12 +594,13 @@ static bool shape_ok(int N, int H, int E) { return (H == 64 || H == 128 || H == 
 constexpr long MIN_ROWS = 128;      // one full row tile (the tensor-map box)
 
 struct Layout {
-    size_t img_bytes, tmp_off, deg_off, mini_off, total;
-    Layout(long rows, int H, int T, bool inference) {
+    size_t img_bytes, tmp_off, deg_off, mask_off, mini_off, total;
+    Layout(long rows, int mb, int H, int T, bool inference) {
         img_bytes = (size_t)image_tiles(H) * WSLOT;
         tmp_off = (size_t)T * img_bytes;
         deg_off = tmp_off + (size_t)rows * 4 * H * sizeof(float);
-        mini_off = deg_off + (((size_t)rows * 64 * sizeof(float) + 1023) & ~(size_t)1023);
+        mask_off = deg_off + (((size_t)rows * 64 * sizeof(float) + 1023) & ~(size_t)1023);      // flag (256 B) + 4 KB of masks per molecule
+        mini_off = mask_off + 256 + (size_t)mb * 4096;
         total = mini_off + (inference ? (size_t)rows * 7 * H * sizeof(float) : 0) + 1024;
     }
 };
@@ -721,12 +702,12 @@ extern "C" void bmp_debug_set_buffer_x3(void *p) { g_dbg = (long long *)p; g_dbg
 // inference]); 0 = shape not covered (the FFMA kernels of ggnn.cu run instead).
 extern "C" size_t bmp_ggnn_x3_workspace_bytes(int mb, int n_atoms, int hidden, int n_edge, int n_steps, int inference) {
     if (!shape_ok(n_atoms, hidden, n_edge) || (long)mb * n_atoms < MIN_ROWS || n_steps <= 0 || n_steps > BMP_MAX_STEPS) return 0;
-    return Layout((long)mb * n_atoms, hidden, n_steps, inference != 0).total;
+    return Layout((long)mb * n_atoms, mb, hidden, n_steps, inference != 0).total;
 }
 
 bool bmp_ggnn_x3_usable(int mb, int N, int H, int E, int T, const void *ws, size_t ws_bytes, const void *state_in, bool inference) {
     if (!ws || state_in || !shape_ok(N, H, E) || (long)mb * N < MIN_ROWS) return false;
-    return ws_bytes >= Layout((long)mb * N, H, T, inference).total;
+    return ws_bytes >= Layout((long)mb * N, mb, H, T, inference).total;
 }
 
 int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
@@ -736,7 +717,7 @@ int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
     const bool inference = !a->Hs;
     if (!inference && (!a->Ms || !a->Gs || !a->RSs)) { set_error("bmp_ggnn_forward: partial stash"); return BMP_EINVAL; }
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
-    const Layout L(rows, H, T, inference);
+    const Layout L(rows, a->mb, H, T, inference);
     int img_of[BMP_MAX_STEPS];
     image_plan(a, img_of);
     int rc;
@@ -757,17 +738,23 @@ int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
     if (a->h0_out) cudaMemcpyAsync(a->h0_out, Hs_at(0), RH * sizeof(float), cudaMemcpyDeviceToDevice, st);
 
     cudaMemsetAsync(deg, 0, (size_t)rows * 64 * sizeof(float), st);
+    int *flag = reinterpret_cast<int *>(ws + L.mask_off);
+    unsigned long long *masks = reinterpret_cast<unsigned long long *>(ws + L.mask_off + 256);
     const size_t agg_smem = (size_t)N * H * sizeof(float);
-    cudaFuncSetAttribute(agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
+    cudaFuncSetAttribute(agg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
     const int agg_grid = a->mb < 8 * sm_count() ? a->mb : 8 * sm_count();
+    cudaMemsetAsync(flag, 0, 256, st);
+    adj_mask_kernel<<<agg_grid, 256, 0, st>>>(a->adj, masks, flag, a->mb, N);
+    count_launch();
+    if ((rc = check_launch("adj_mask_kernel"))) return rc;
     for (int t = 0; t < T; ++t) {
         const bool stf = a->stateful[t] != 0;
         const uint8_t *img = ws + (size_t)img_of[t] * L.img_bytes;
         const bmp_gru_t &G = a->gru[t];
         float *h = Hs_at(t), *hn = Hs_at(t + 1), *m = Ms_at(t), *g = Gs_at(t), *rs = RS_at(t);
-        agg_fwd_kernel<<<agg_grid, 256, agg_smem, st>>>(a->adj, h, AH, t == 0 ? deg : nullptr, a->mb, N, H);
+        agg_kernel<false><<<agg_grid, 256, agg_smem, st>>>(masks, flag, a->adj, h, AH, t == 0 ? deg : nullptr, a->mb, N, H);
         count_launch();
-        if ((rc = check_launch("agg_fwd_kernel"))) return rc;
+        if ((rc = check_launch("agg_kernel"))) return rc;
         Args ga;
         // ---- message
         memset(&ga, 0, sizeof(ga));
@@ -836,7 +823,7 @@ int bmp_ggnn_backward_x3(const bmp_ggnn_bwd_t *a, void *stream) {
     const int H = a->hidden, N = a->n_atoms, T = a->n_steps, NC = H < 128 ? H : 128, hc = (H + 127) / 128, kb = H / 64;
     const long rows = (long)a->mb * N;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
-    const Layout L(rows, H, T, false);
+    const Layout L(rows, a->mb, H, T, false);
     int img_of[BMP_MAX_STEPS];
     image_plan(a, img_of);
     int rc;
@@ -844,9 +831,15 @@ int bmp_ggnn_backward_x3(const bmp_ggnn_bwd_t *a, void *stream) {
     const size_t RH = (size_t)rows * H;
     float *tmp = reinterpret_cast<float *>(ws + L.tmp_off);
     float *ds = tmp, *dhx = tmp + RH, *dm = tmp + 2 * RH;
-    const size_t agg_smem = ((size_t)N * H + 4 * (size_t)N * (N + 1)) * sizeof(float);
-    cudaFuncSetAttribute(agg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
+    int *flag = reinterpret_cast<int *>(ws + L.mask_off);
+    unsigned long long *masks = reinterpret_cast<unsigned long long *>(ws + L.mask_off + 256);
+    const size_t agg_smem = (size_t)N * H * sizeof(float);
+    cudaFuncSetAttribute(agg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
     const int agg_grid = a->mb < 8 * sm_count() ? a->mb : 8 * sm_count();
+    cudaMemsetAsync(flag, 0, 256, st);        // the masks are rebuilt: the workspace need not be the forward's
+    adj_mask_kernel<<<agg_grid, 256, 0, st>>>(a->adj, masks, flag, a->mb, N);
+    count_launch();
+    if ((rc = check_launch("adj_mask_kernel"))) return rc;
     for (int t = T - 1; t >= 0; --t) {
         const bool stf = a->stateful[t] != 0;
         const uint8_t *img = ws + (size_t)img_of[t] * L.img_bytes;
@@ -894,9 +887,9 @@ int bmp_ggnn_backward_x3(const bmp_ggnn_bwd_t *a, void *stream) {
             }
         ga.njobs = nj;
         if ((rc = launch_gemm(ga, st))) return rc;
-        agg_bwd_kernel<<<agg_grid, 256, agg_smem, st>>>(a->adj, dm, a->Ps + (size_t)t * 4 * RH, a->mb, N, H);
+        agg_kernel<true><<<agg_grid, 256, agg_smem, st>>>(masks, flag, a->adj, dm, a->Ps + (size_t)t * 4 * RH, nullptr, a->mb, N, H);
         count_launch();
-        if ((rc = check_launch("agg_bwd_kernel"))) return rc;
+        if ((rc = check_launch("agg_kernel"))) return rc;
         // ---- dHs[t] += dh_x + sum_e P_e W_e
         memset(&ga, 0, sizeof(ga));
         ga.rows = rows; ga.NC = NC; ga.njobs = hc;

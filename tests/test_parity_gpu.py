@@ -424,8 +424,9 @@ def test_config_d_model_trains_at_hidden_256_in_fp32():
             assert rel_err(p["grads"][k], v) <= TOL, k
 
 
-@pytest.mark.parametrize("H,T,tied,N,mb", [(128, 3, True, 64, 5), (128, 2, False, 37, 9), (64, 3, True, 50, 7), (256, 2, True, 30, 6)])
-def test_fp32_mode_on_tensor_cores_matches_oracle_and_the_ffma_kernels(H, T, tied, N, mb):
+@pytest.mark.parametrize("H,T,tied,N,mb,weighted", [(128, 3, True, 64, 5, False), (128, 2, False, 37, 9, True), (64, 3, True, 50, 7, False),
+                                                      (256, 2, True, 30, 6, False)])
+def test_fp32_mode_on_tensor_cores_matches_oracle_and_the_ffma_kernels(H, T, tied, N, mb, weighted):
     """BMP_MODE_F32 with the encoder's contractions on tcgen05 (csrc/ggnn_x3.cu: bf16 hi/lo split, three UMMAs per product) against
     the fp64 oracle at the mode's 1e-4 bound, against the FFMA kernels of csrc/ggnn.cu (same stash, same results up to rounding), and
     its stash-free inference path against its training path.  Row counts are not multiples of the 128-row tile (tail tiles)."""
@@ -434,6 +435,8 @@ def test_fp32_mode_on_tensor_cores_matches_oracle_and_the_ffma_kernels(H, T, tie
     rng = np.random.default_rng(H + T + N)
     O = 40
     atoms, adj = synthetic.random_molecules(rng, mb, N)
+    if weighted:        # general fp32 edge weights (not symmetric): the adjacency bit masks only say WHERE the entries are
+        adj = (adj * rng.uniform(0.25, 1.5, size=adj.shape)).astype(np.float32)
     assert mb * N >= 128 and (mb * N) % 128 != 0
     params = R.init_params(R.ggnn_mono_shapes(O, H, T, weight_tying=tied), rng, dtype=np.float64)
     tab = R.wrap_params(params)
