@@ -79,6 +79,10 @@ if __name__ == "__main__":
         ref, _ = run(H, T, N, mb, tied, False, nmax)
         got, _ = run(H, T, N, mb, tied, True, nmax)
         print("H%d T%d N%d mb%d tied=%s: max rel diff x3 vs FFMA %.2e" % (H, T, N, mb, tied, cmp(got, ref)), flush=True)
+    if "--time256" in sys.argv:
+        for x3 in (False, True):
+            _, ms = run(256, 8, 64, 2048, True, x3, time_it=True)
+            print("H256 T8 N64 2048 molecules x3=%s: fwd %.2f ms bwd(+wgrad) %.2f ms" % (x3, ms[0], ms[1]), flush=True)
     if "--time" in sys.argv:
         for x3 in (False, True):
             _, ms = run(128, 6, 64, 4144, True, x3, time_it=True)
