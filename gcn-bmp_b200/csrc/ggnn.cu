@@ -539,10 +539,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_bwd_big_kernel(const bmp_ggn
     }
 }
 
-static int check_common(int mb, int N, int H, int E, int T, int mode) {
+static int check_common(int mb, int N, int H, int E, int T, int mode, int nmax = BMP_MAX_ATOMS) {
     if (mode != BMP_MODE_F32) { set_error("ggnn fp32 path called with mode %d", mode); return BMP_EINVAL; }
     if (mb <= 0 || T <= 0 || T > BMP_MAX_STEPS) { set_error("ggnn: bad mb=%d or n_steps=%d", mb, T); return BMP_ESHAPE; }
-    if (N <= 0 || N > BMP_MAX_ATOMS) { set_error("ggnn: n_atoms=%d outside 1..%d", N, BMP_MAX_ATOMS); return BMP_ESHAPE; }
+    if (N <= 0 || N > nmax) {
+        set_error("ggnn: n_atoms=%d outside 1..%d (more than %d atoms need BMP_MODE_F32 with the tensor-core workspace: hidden 64/128/256, "
+                  "4 bond types)", N, nmax, BMP_MAX_ATOMS);
+        return BMP_ESHAPE;
+    }
     if (H <= 0 || H > BMP_MAX_HIDDEN || (H & 3)) { set_error("ggnn: hidden=%d must be a multiple of 4 in 4..%d", H, BMP_MAX_HIDDEN); return BMP_ESHAPE; }
     if (E <= 0 || E > 8) { set_error("ggnn: n_edge=%d outside 1..8", E); return BMP_ESHAPE; }
     return BMP_OK;
@@ -568,7 +572,13 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
     if (a->mode == BMP_MODE_BF16) return bmp_ggnn_forward_tc(a, stream);
     if (a->mol_index) { set_error("bmp_ggnn_forward: mol_index (table indirection) is a BMP_MODE_BF16 feature; gather the rows first"); return BMP_ESHAPE; }
     if (a->adj_u8) { set_error("bmp_ggnn_forward: a byte adjacency needs BMP_MODE_BF16"); return BMP_EINVAL; }
-    int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->mode);
+    bool x3 = a->n_steps > 0 && a->n_steps <= BMP_MAX_STEPS &&
+              bmp_ggnn_x3_usable(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->tc_workspace, a->tc_workspace_bytes, a->state_in, a->Hs == nullptr);
+    for (int t = 0; x3 && t < a->n_steps; ++t) {
+        const bmp_gru_t &g = a->gru[t];
+        x3 = aligned16({a->msg_b[t], g.b_Wr, g.b_Ur, g.b_Wz, g.b_Uz, g.b_W, g.b_U});
+    }
+    int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->mode, x3 ? BMP_X3_MAX_ATOMS : BMP_MAX_ATOMS);
     if (rc) return rc;
     for (int t = 0; t < a->n_steps; ++t) {
         const bmp_gru_t &g = a->gru[t];
@@ -586,14 +596,7 @@ extern "C" int bmp_ggnn_forward(const bmp_ggnn_fwd_t *a, void *stream) {
         return BMP_EINVAL;
     }
     const int H = a->hidden;
-    if (bmp_ggnn_x3_usable(a->mb, a->n_atoms, H, a->n_edge, a->n_steps, a->tc_workspace, a->tc_workspace_bytes, a->state_in, a->Hs == nullptr)) {
-        bool al = true;
-        for (int t = 0; t < a->n_steps; ++t) {
-            const bmp_gru_t &g = a->gru[t];
-            al = al && aligned16({a->msg_b[t], g.b_Wr, g.b_Ur, g.b_Wz, g.b_Uz, g.b_W, g.b_U});
-        }
-        if (al) return bmp_ggnn_forward_x3(a, stream);
-    }
+    if (x3) return bmp_ggnn_forward_x3(a, stream);
     const bool sep = a->state_in != nullptr;
     size_t smem = fwd_smem_bytes(H, sep, a->n_edge);
     if (smem > 227 * 1024) {
@@ -630,7 +633,9 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         set_error("bmp_ggnn_backward: null argument");
         return BMP_EINVAL;
     }
-    int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, BMP_MODE_F32);
+    const bool x3_data = a->mode == BMP_MODE_F32 && a->n_steps > 0 && a->n_steps <= BMP_MAX_STEPS &&
+                         bmp_ggnn_x3_usable(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, a->tc_workspace, a->tc_workspace_bytes, a->state_in, false);
+    int rc = check_common(a->mb, a->n_atoms, a->hidden, a->n_edge, a->n_steps, BMP_MODE_F32, x3_data ? BMP_X3_MAX_ATOMS : BMP_MAX_ATOMS);
     if (rc) return rc;
     const int H = a->hidden, T = a->n_steps, E = a->n_edge;
     // BMP_MODE_BF16: parameter-gradient contractions on tcgen05 (bias column sums fused in)
@@ -661,8 +666,6 @@ extern "C" int bmp_ggnn_backward(const bmp_ggnn_bwd_t *a, void *stream) {
         set_error("bmp_ggnn_backward: stash buffers must be 16-byte aligned");
         return BMP_EINVAL;
     }
-    const bool x3_data = a->mode == BMP_MODE_F32 &&
-                         bmp_ggnn_x3_usable(a->mb, a->n_atoms, H, E, T, a->tc_workspace, a->tc_workspace_bytes, a->state_in, false);
     if (tc_data) {
         if ((rc = bmp_ggnn_backward_tc(a, stream))) return rc;
     } else if (x3_data) {

@@ -478,32 +478,34 @@ __global__ void __launch_bounds__(256) pack_x3_kernel(const PackArgs a) {
 // (64 bits per row and per column of every bond type, 4 KB per molecule instead of 64 KB) plus a flag "some non-zero entry is not
 // 1.0"; the per-step products then walk the set bits in ascending order -- the dense sum with the zeros skipped -- and touch the
 // dense array again only when that flag is set (general fp32 weights).
-// masks[mol][0][e][i] bit j = (A_e[i][j] != 0) ; masks[mol][1][e][j] bit i = (A_e[i][j] != 0)
+// masks[mol][0][e][i][w] bit b = (A_e[i][64 w + b] != 0) ; masks[mol][1][e][j][w] bit b = (A_e[64 w + b][j] != 0) ; W = ceil(N / 64) words
 __global__ void __launch_bounds__(256) adj_mask_kernel(const float *__restrict__ adj, unsigned long long *__restrict__ masks, int *nonbinary,
                                                        int mb, int N) {
-    __shared__ unsigned long long cm[4 * 64];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    extern __shared__ unsigned long long cm[];                   // [4][N][W] column masks
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, W = (N + 63) >> 6, per = 4 * N * W;
     for (int mol = blockIdx.x; mol < mb; mol += gridDim.x) {
         __syncthreads();
-        cm[tid] = 0ull;
-        unsigned long long *out = masks + (size_t)mol * 512;
-        for (int idx = tid; idx < 256; idx += 256) out[idx] = 0ull;        // row masks of the rows i >= N
+        for (int idx = tid; idx < per; idx += 256) cm[idx] = 0ull;
+        unsigned long long *out = masks + (size_t)mol * 2 * per;
         __syncthreads();
         bool odd = false;
         for (int idx = warp; idx < 4 * N; idx += 8) {
             const int e = idx / N, i = idx - e * N;
             const float *arow = adj + (((long)mol * 4 + e) * N + i) * N;
-            const float a0 = lane < N ? __ldg(arow + lane) : 0.f, a1 = lane + 32 < N ? __ldg(arow + lane + 32) : 0.f;
-            const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a0 != 0.f) |
-                                         ((unsigned long long)__ballot_sync(0xffffffffu, a1 != 0.f) << 32);
-            if (lane == 0) out[e * 64 + i] = m;
-            if (a0 != 0.f) atomicOr(&cm[e * 64 + lane], 1ull << i);
-            if (a1 != 0.f) atomicOr(&cm[e * 64 + lane + 32], 1ull << i);
-            odd = odd || (a0 != 0.f && a0 != 1.f) || (a1 != 0.f && a1 != 1.f);
+            for (int w = 0; w < W; ++w) {
+                const int j0 = 64 * w + lane, j1 = j0 + 32;
+                const float a0 = j0 < N ? __ldg(arow + j0) : 0.f, a1 = j1 < N ? __ldg(arow + j1) : 0.f;
+                const unsigned long long m = (unsigned long long)__ballot_sync(0xffffffffu, a0 != 0.f) |
+                                             ((unsigned long long)__ballot_sync(0xffffffffu, a1 != 0.f) << 32);
+                if (lane == 0) out[(e * N + i) * W + w] = m;
+                if (a0 != 0.f) atomicOr(&cm[(e * N + j0) * W + (i >> 6)], 1ull << (i & 63));
+                if (a1 != 0.f) atomicOr(&cm[(e * N + j1) * W + (i >> 6)], 1ull << (i & 63));
+                odd = odd || (a0 != 0.f && a0 != 1.f) || (a1 != 0.f && a1 != 1.f);
+            }
         }
         if (__any_sync(0xffffffffu, odd) && lane == 0) *nonbinary = 1;
         __syncthreads();
-        out[256 + tid] = cm[tid];
+        for (int idx = tid; idx < per; idx += 256) out[per + idx] = cm[idx];
     }
 }
 
@@ -515,33 +517,35 @@ __global__ void __launch_bounds__(256) agg_kernel(const unsigned long long *__re
                                                   const float *__restrict__ adj, const float *__restrict__ src, float *__restrict__ dst,
                                                   float *__restrict__ deg, int mb, int N, int H) {
     extern __shared__ __align__(16) float sh[];                  // [N][H]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, HV = H / 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, HV = H / 4, W = (N + 63) >> 6, per = 4 * N * W;
     const bool general = *nonbinary != 0;
     for (int mol = blockIdx.x; mol < mb; mol += gridDim.x) {
         __syncthreads();
         const float4 *s4 = reinterpret_cast<const float4 *>(src + (long)mol * N * H);
         for (int idx = tid; idx < N * HV; idx += 256) reinterpret_cast<float4 *>(sh)[idx] = __ldg(s4 + idx);
         __syncthreads();
-        const unsigned long long *mk = masks + (size_t)mol * 512 + (BWD ? 256 : 0);
+        const unsigned long long *mk = masks + (size_t)mol * 2 * per + (BWD ? per : 0);
         const float *am = adj + (long)mol * 4 * N * N;
         for (int idx = warp; idx < 4 * N; idx += 8) {
             const int e = idx / N, x = idx - e * N;
-            unsigned long long m = __ldg(mk + e * 64 + x);
             float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
             float d = 0.f;
-            while (m) {
-                const int y = __ffsll((long long)m) - 1;
-                m &= m - 1;
-                const float v = general ? __ldg(am + ((long)e * N + (BWD ? y : x)) * N + (BWD ? x : y)) : 1.f;
-                d += v;
-                const float4 *hr = reinterpret_cast<const float4 *>(sh + y * H);
-                if (lane < HV) {
-                    const float4 t = hr[lane];
-                    acc0.x = fmaf(v, t.x, acc0.x); acc0.y = fmaf(v, t.y, acc0.y); acc0.z = fmaf(v, t.z, acc0.z); acc0.w = fmaf(v, t.w, acc0.w);
-                }
-                if (lane + 32 < HV) {
-                    const float4 t = hr[lane + 32];
-                    acc1.x = fmaf(v, t.x, acc1.x); acc1.y = fmaf(v, t.y, acc1.y); acc1.z = fmaf(v, t.z, acc1.z); acc1.w = fmaf(v, t.w, acc1.w);
+            for (int w = 0; w < W; ++w) {
+                unsigned long long m = __ldg(mk + (e * N + x) * W + w);
+                while (m) {
+                    const int y = 64 * w + __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const float v = general ? __ldg(am + ((long)e * N + (BWD ? y : x)) * N + (BWD ? x : y)) : 1.f;
+                    d += v;
+                    const float4 *hr = reinterpret_cast<const float4 *>(sh + y * H);
+                    if (lane < HV) {
+                        const float4 t = hr[lane];
+                        acc0.x = fmaf(v, t.x, acc0.x); acc0.y = fmaf(v, t.y, acc0.y); acc0.z = fmaf(v, t.z, acc0.z); acc0.w = fmaf(v, t.w, acc0.w);
+                    }
+                    if (lane + 32 < HV) {
+                        const float4 t = hr[lane + 32];
+                        acc1.x = fmaf(v, t.x, acc1.x); acc1.y = fmaf(v, t.y, acc1.y); acc1.z = fmaf(v, t.z, acc1.z); acc1.w = fmaf(v, t.w, acc1.w);
+                    }
                 }
             }
             float4 *out = reinterpret_cast<float4 *>(dst + ((long)mol * N + x) * 4 * H + (long)e * H);
@@ -590,17 +594,20 @@ static int sm_count() {
     return sms;
 }
 
-static bool shape_ok(int N, int H, int E) { return (H == 64 || H == 128 || H == 256) && E == 4 && N > 0 && N <= BMP_MAX_ATOMS; }
+// the row GEMMs never see molecule boundaries; the per-molecule adjacency products keep an N x H fp32 tile in shared memory
+static bool shape_ok(int N, int H, int E) {
+    return (H == 64 || H == 128 || H == 256) && E == 4 && N > 0 && N <= BMP_X3_MAX_ATOMS && (size_t)N * H * sizeof(float) <= 160 * 1024;
+}
 constexpr long MIN_ROWS = 128;      // one full row tile (the tensor-map box)
 
 struct Layout {
     size_t img_bytes, tmp_off, deg_off, mask_off, mini_off, total;
-    Layout(long rows, int mb, int H, int T, bool inference) {
+    Layout(long rows, int mb, int N, int H, int T, bool inference) {
         img_bytes = (size_t)image_tiles(H) * WSLOT;
         tmp_off = (size_t)T * img_bytes;
         deg_off = tmp_off + (size_t)rows * 4 * H * sizeof(float);
-        mask_off = deg_off + (((size_t)rows * 64 * sizeof(float) + 1023) & ~(size_t)1023);      // flag (256 B) + 4 KB of masks per molecule
-        mini_off = mask_off + 256 + (size_t)mb * 4096;
+        mask_off = deg_off + (((size_t)rows * 64 * sizeof(float) + 1023) & ~(size_t)1023);      // flag (256 B) + bit masks (4 KB per molecule at N = 64)
+        mini_off = mask_off + 256 + (size_t)mb * 64 * N * ((N + 63) / 64);      // 2 x 4 x N x W words of 8 bytes
         total = mini_off + (inference ? (size_t)rows * 7 * H * sizeof(float) : 0) + 1024;
     }
 };
@@ -702,12 +709,12 @@ extern "C" void bmp_debug_set_buffer_x3(void *p) { g_dbg = (long long *)p; g_dbg
 // inference]); 0 = shape not covered (the FFMA kernels of ggnn.cu run instead).
 extern "C" size_t bmp_ggnn_x3_workspace_bytes(int mb, int n_atoms, int hidden, int n_edge, int n_steps, int inference) {
     if (!shape_ok(n_atoms, hidden, n_edge) || (long)mb * n_atoms < MIN_ROWS || n_steps <= 0 || n_steps > BMP_MAX_STEPS) return 0;
-    return Layout((long)mb * n_atoms, mb, hidden, n_steps, inference != 0).total;
+    return Layout((long)mb * n_atoms, mb, n_atoms, hidden, n_steps, inference != 0).total;
 }
 
 bool bmp_ggnn_x3_usable(int mb, int N, int H, int E, int T, const void *ws, size_t ws_bytes, const void *state_in, bool inference) {
     if (!ws || state_in || !shape_ok(N, H, E) || (long)mb * N < MIN_ROWS) return false;
-    return ws_bytes >= Layout((long)mb * N, mb, H, T, inference).total;
+    return ws_bytes >= Layout((long)mb * N, mb, N, H, T, inference).total;
 }
 
 int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
@@ -717,7 +724,7 @@ int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
     const bool inference = !a->Hs;
     if (!inference && (!a->Ms || !a->Gs || !a->RSs)) { set_error("bmp_ggnn_forward: partial stash"); return BMP_EINVAL; }
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
-    const Layout L(rows, a->mb, H, T, inference);
+    const Layout L(rows, a->mb, N, H, T, inference);
     int img_of[BMP_MAX_STEPS];
     image_plan(a, img_of);
     int rc;
@@ -744,7 +751,7 @@ int bmp_ggnn_forward_x3(const bmp_ggnn_fwd_t *a, void *stream) {
     cudaFuncSetAttribute(agg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
     const int agg_grid = a->mb < 8 * sm_count() ? a->mb : 8 * sm_count();
     cudaMemsetAsync(flag, 0, 256, st);
-    adj_mask_kernel<<<agg_grid, 256, 0, st>>>(a->adj, masks, flag, a->mb, N);
+    adj_mask_kernel<<<agg_grid, 256, (size_t)32 * N * ((N + 63) / 64), st>>>(a->adj, masks, flag, a->mb, N);
     count_launch();
     if ((rc = check_launch("adj_mask_kernel"))) return rc;
     for (int t = 0; t < T; ++t) {
@@ -823,7 +830,7 @@ int bmp_ggnn_backward_x3(const bmp_ggnn_bwd_t *a, void *stream) {
     const int H = a->hidden, N = a->n_atoms, T = a->n_steps, NC = H < 128 ? H : 128, hc = (H + 127) / 128, kb = H / 64;
     const long rows = (long)a->mb * N;
     uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
-    const Layout L(rows, a->mb, H, T, false);
+    const Layout L(rows, a->mb, N, H, T, false);
     int img_of[BMP_MAX_STEPS];
     image_plan(a, img_of);
     int rc;
@@ -837,7 +844,7 @@ int bmp_ggnn_backward_x3(const bmp_ggnn_bwd_t *a, void *stream) {
     cudaFuncSetAttribute(agg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)agg_smem);
     const int agg_grid = a->mb < 8 * sm_count() ? a->mb : 8 * sm_count();
     cudaMemsetAsync(flag, 0, 256, st);        // the masks are rebuilt: the workspace need not be the forward's
-    adj_mask_kernel<<<agg_grid, 256, 0, st>>>(a->adj, masks, flag, a->mb, N);
+    adj_mask_kernel<<<agg_grid, 256, (size_t)32 * N * ((N + 63) / 64), st>>>(a->adj, masks, flag, a->mb, N);
     count_launch();
     if ((rc = check_launch("adj_mask_kernel"))) return rc;
     for (int t = T - 1; t >= 0; --t) {

@@ -408,6 +408,63 @@ def _readout_ws(a, mode, H, O, variant, dev, params):
     return None
 
 
+# ---- molecules with more than 64 atoms ---------------------------------------------------------------------------------
+# The hand-written read-out / co-attention kernels map one padded molecule (pair) of <= 64 atoms onto a CTA.  Larger molecules
+# (the reference pads to the batch maximum, ggnn_preprocessor.py:41 has no cap) take the same formulas composed from library
+# GEMMs (torch.matmul -> cuBLAS) with autograd; the GGNN encoder itself runs them on the fp32 tensor-core path (row GEMMs, any N
+# up to 256).  A functional path for real data, not a tuned one.
+MAX_KERNEL_ATOMS = 64
+_TORCH_ACT = {0: (lambda x: x), 1: torch.tanh, 2: torch.relu, 3: torch.sigmoid}
+
+
+def _readout_large(h, h0, mask, variant, act, act_agg, W_i, b_i, W_j, b_j):
+    if variant == K.READOUT_SUM:
+        return h.sum(dim=1)
+    h1 = torch.cat((h, h0), dim=2) if h0 is not None else h
+    gi = torch.sigmoid(torch.nn.functional.linear(h1, W_i, b_i))
+    gj = _TORCH_ACT[act](torch.nn.functional.linear(h1 if variant == K.READOUT_R1 else h, W_j, b_j))
+    g = gi * gj
+    if mask is not None:
+        g = g * mask.reshape(mask.shape[0], mask.shape[1], 1)
+    return _TORCH_ACT[act_agg](g.sum(dim=1))
+
+
+def readout(h, h0, mask, variant, act, act_agg, W_i, b_i, W_j, b_j, mode=0):
+    """GGNNReadout variants R1 / R2 / SUM: the CUDA kernels, or the library composition above 64 atoms."""
+    if h.shape[1] > MAX_KERNEL_ATOMS:
+        return _readout_large(_f32(h), _f32(h0), _f32(mask), variant, act, act_agg, W_i, b_i, W_j, b_j)
+    return Readout.apply(h, h0, mask, variant, act, act_agg, W_i, b_i, W_j, b_j, mode)
+
+
+def _coattention_large(a1, a2, variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j):
+    H = a1.shape[2]
+    # C[b, i, j] = act(a1_j^T W a2_i + V1^T a1_j + V2^T a2_i + b): i over atoms_2, j over atoms_1 (nie_coattention.py:371-396)
+    C = torch.matmul(a2, torch.matmul(a1, W.reshape(H, H)).transpose(1, 2))
+    C = C + torch.matmul(a1, V1.reshape(H, 1)).transpose(1, 2) + torch.matmul(a2, V2.reshape(H, 1)) + b.reshape(1, 1, 1)
+    C = _TORCH_ACT[act](C)
+    if variant == K.COATTN_POOL:
+        attn_1 = torch.softmax(C.mean(dim=1), dim=1)
+        attn_2 = torch.softmax(C.mean(dim=2), dim=1)
+    else:
+        L_2 = torch.softmax(C, dim=1)
+        L_1 = torch.softmax(C.transpose(1, 2), dim=1)
+        l1, l2 = torch.matmul(a1, lt_1.t()), torch.matmul(a2, lt_2.t())
+        H_1 = torch.tanh(l1 + torch.matmul(L_1, l2))
+        H_2 = torch.tanh(l2 + torch.matmul(L_2, l1))
+        attn_1 = torch.softmax(torch.matmul(H_1, wa_1.t()), dim=1)[:, :, 0]
+        attn_2 = torch.softmax(torch.matmul(H_2, wa_2.t()), dim=1)[:, :, 0]
+    j1 = torch.nn.functional.linear(a1, W_j, b_j)
+    j2 = torch.nn.functional.linear(a2, W_j, b_j)
+    return (attn_1.unsqueeze(2) * j1).sum(dim=1), (attn_2.unsqueeze(2) * j2).sum(dim=1)
+
+
+def coattention(atoms_1, atoms_2, variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j, mode=0):
+    """Fine-grained co-attention (Nie / VQA / Pooling): the CUDA kernels, or the library composition above 64 atoms."""
+    if max(atoms_1.shape[1], atoms_2.shape[1]) > MAX_KERNEL_ATOMS:
+        return _coattention_large(_f32(atoms_1), _f32(atoms_2), variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j)
+    return Coattention.apply(atoms_1, atoms_2, variant, act, W, V1, V2, b, lt_1, lt_2, wa_1, wa_2, W_j, b_j, mode)
+
+
 class Readout(torch.autograd.Function):
     """GGNNReadout variants R1 / R2 / SUM."""
 

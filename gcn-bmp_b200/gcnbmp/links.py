@@ -397,7 +397,7 @@ class GGNNReadout(Link):
         mask = _as_device(is_real_node, torch.float32)
         kin = h.shape[2] * (2 if h0 is not None else 1)
         i, j = self.i_layer.ensure(kin), self.j_layer.ensure(kin)
-        return Fn.Readout.apply(h, h0, mask, K.READOUT_R1, Fn.act_code(self.activation),
+        return Fn.readout(h, h0, mask, K.READOUT_R1, Fn.act_code(self.activation),
                                 Fn.act_code(self.activation_agg), i.W, i.bias, j.W, j.bias,
                                 self.__dict__.get("mode", K.MODE_F32))
 
@@ -498,7 +498,7 @@ class GGNNMono(Link):
     def readout(self, h, h0, step=0):
         idx = step if self.concat_hidden else 0
         i, j = self.i_layers[idx], self.j_layers[idx]
-        return Fn.Readout.apply(h, h0, None, K.READOUT_R2, 0, 0, i.W, i.b, j.W, j.b, self.mode)
+        return Fn.readout(h, h0, None, K.READOUT_R2, 0, 0, i.W, i.b, j.W, j.b, self.mode)
 
     def __call__(self, atom_array, adj, mol_index=None):
         """`mol_index` (extension): int (mb,) -- `atom_array` (U,N) / `adj` (U,E,N,N) are a device-resident drug
@@ -524,7 +524,7 @@ class GGNNMono(Link):
                 raise RuntimeError("gcnbmp: concat_hidden needs the per-step states; call with grad enabled")
             return torch.cat([self.readout(hs[t + 1], h0, t) for t in range(T)], dim=1)
         if self.sum_readout:
-            return Fn.Readout.apply(hT, None, None, K.READOUT_SUM, 0, 0, None, None, None, None)
+            return Fn.readout(hT, None, None, K.READOUT_SUM, 0, 0, None, None, None, None)
         return self.readout(hT, h0, 0)
 
     def get_atom_array(self, step=-1):
@@ -819,7 +819,7 @@ class NieFineCoattention(Link):
 
     def __call__(self, atoms_1, g_1, atoms_2, g_2):
         e = self.energy_layer
-        return Fn.Coattention.apply(
+        return Fn.coattention(
             _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32), K.COATTN_FINE,
             Fn.act_code(self.activation), e.W, e.V1, e.V2, e.b, self.lt_layer_1.W, self.lt_layer_2.W,
             self.attention_layer_1.W, self.attention_layer_2.W, self.j_layer.W, self.j_layer.b,
@@ -994,7 +994,7 @@ class FourierFineCoattention(NieFineCoattention):
         W = e.W[:, :, 0]
         Wf = (Fc.t() @ W @ Fc + Fs.t() @ W @ Fs).unsqueeze(2).contiguous()
         S = (Fc + Fs).t()
-        return Fn.Coattention.apply(a1, a2, K.COATTN_FINE, Fn.act_code(self.activation), Wf, (S @ e.V1).contiguous(), (S @ e.V2).contiguous(),
+        return Fn.coattention(a1, a2, K.COATTN_FINE, Fn.act_code(self.activation), Wf, (S @ e.V1).contiguous(), (S @ e.V2).contiguous(),
                                     2.0 * e.b, self.lt_layer_1.W, self.lt_layer_2.W, self.attention_layer_1.W, self.attention_layer_2.W,
                                     self.j_layer.W, self.j_layer.b, self.__dict__.get("mode", K.MODE_F32))
 
@@ -1040,7 +1040,7 @@ class DeepNieFineCoattention(Link):
         lt1 = torch.cat([z(self.head, H), self.lt_layer_1.W], dim=1)
         lt2 = torch.cat([z(self.head, H), self.lt_layer_2.W], dim=1)
         Wj = torch.cat([z(self.out_dim, H), self.j_layer.W], dim=1)
-        return Fn.Coattention.apply(self._wide(1, a1), self._wide(2, a2), K.COATTN_FINE, Fn.act_code(self.activation),
+        return Fn.coattention(self._wide(1, a1), self._wide(2, a2), K.COATTN_FINE, Fn.act_code(self.activation),
                                     Wb, V1b, V2b, e.b, lt1, lt2, self.attention_layer_1.W, self.attention_layer_2.W,
                                     Wj, self.j_layer.b, self.__dict__.get("mode", K.MODE_F32))
 
@@ -1064,7 +1064,7 @@ class PoolingFineCoattention(Link):
 
     def __call__(self, atoms_1, g_1, atoms_2, g_2):
         e = self.energy_layer
-        return Fn.Coattention.apply(
+        return Fn.coattention(
             _as_device(atoms_1, torch.float32), _as_device(atoms_2, torch.float32), K.COATTN_POOL,
             Fn.act_code(self.activation), e.W, e.V1, e.V2, e.b, None, None, None, None,
             self.j_layer.W, self.j_layer.b, self.__dict__.get("mode", K.MODE_F32))

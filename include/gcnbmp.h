@@ -34,6 +34,8 @@ extern "C" {
 
 #define BMP_MAX_STEPS   16
 #define BMP_MAX_ATOMS   64   /* padded atoms per molecule handled by one CTA */
+#define BMP_X3_MAX_ATOMS 256 /* GGNN encoder in BMP_MODE_F32 with the tensor-core workspace (bmp_ggnn_x3_workspace_bytes): its
+                               row GEMMs never see molecule boundaries; n_atoms * hidden * 4 bytes <= 160 KB */
 #define BMP_MAX_HIDDEN 256
 
 /* activations (chainer.functions.{identity,tanh,relu,sigmoid}) */

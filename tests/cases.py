@@ -41,6 +41,12 @@ def pair_case(name, seed=0, dtype=np.float64):
         # modular GGNN untied (every step stateless) + HolE without attention
         "MU": dict(enc="ggnn", H=16, T=3, tied=False, concat_hidden=False, O=16, attn=None, head=None,
                    hole_hidden=(8,), K=1, mb=3, N1=12, N2=12, activation="identity"),
+        # molecules with more than 64 atoms (the reference pads to the batch maximum, no cap): GGNN encoder on the fp32 tensor-core
+        # path (row GEMMs), read-out / co-attention composed from library GEMMs
+        "L1": dict(enc="mono", H=64, T=3, tied=True, sum_readout=False, O=24, attn="nie", head=8,
+                   hole_hidden=(), K=3, mb=3, N1=100, N2=70),
+        "L2": dict(enc="ggnn", H=128, T=2, tied=True, concat_hidden=False, O=16, attn="pool", head=None,
+                   hole_hidden=(), K=1, mb=2, N1=128, N2=65, activation="tanh"),
         # config B: RelGCN 64->64 x4 (reduced), scale_adj on
         "B": dict(enc="relgcn", ch=[16, 32, 32], O=16, scale_adj=True, attn=None, head=None,
                   hole_hidden=(), K=1, mb=5, N1=30, N2=28),

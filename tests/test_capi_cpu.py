@@ -109,6 +109,9 @@ def test_fp32_tensor_core_workspace_query_is_host_only():
     assert q(4144, 64, 32, 4, 6, 0) == 0 and q(4144, 64, 96, 4, 6, 0) == 0 and q(4144, 64, 128, 3, 6, 0) == 0
     assert q(1, 64, 128, 4, 6, 0) == 0                                  # fewer rows than one 128-row tile
     assert q(4144, 64, 128, 4, 17, 0) == 0
+    # molecules with more than 64 atoms: covered up to 256 atoms while an N x hidden fp32 tile fits the adjacency kernels
+    assert q(100, 128, 128, 4, 3, 0) > 0 and q(100, 256, 128, 4, 3, 0) > 0 and q(100, 100, 256, 4, 3, 0) > 0
+    assert q(100, 257, 128, 4, 3, 0) == 0 and q(100, 256, 256, 4, 3, 0) == 0
 
 
 def test_chainer_adapter_is_import_guarded():

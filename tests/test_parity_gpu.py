@@ -28,6 +28,38 @@ def test_pair_forward_backward_matches_oracle(name):
         assert rel_err(p["grads"][k], o["grads"][k]) <= TOL, (k, rel_err(p["grads"][k], o["grads"][k]))
 
 
+@pytest.mark.parametrize("name", ["L1", "L2"])
+def test_pair_with_more_than_64_atoms_matches_oracle(name):
+    """N in {65, 70, 100, 128}: the reference has no atom cap (ggnn_preprocessor.py:41, max_atoms=-1; concat_mols pads to the batch
+    maximum).  The GGNN encoder runs these on the fp32 tensor-core path (its row GEMMs never see molecule boundaries), read-out and
+    co-attention as library-GEMM compositions of the same formulas; logits, loss and every parameter gradient vs the fp64 oracle."""
+    case = cases.pair_case(name, seed=5)
+    assert max(case["spec"]["N1"], case["spec"]["N2"]) > 64
+    o = cases.oracle_eval(case)
+    p = product.product_eval(case)
+    assert rel_err(p["logits"], o["logits"]) <= TOL
+    assert abs(p["loss"] - float(o["loss"])) <= TOL * max(1.0, abs(float(o["loss"])))
+    assert set(p["grads"]) == set(o["grads"])
+    for k in sorted(o["grads"]):
+        # a gradient that is a cancelling sum over all atom pairs (the scalar energy bias, |ref| ~ 4e-5) is held to 1e-8 absolute
+        err = np.abs(p["grads"][k] - o["grads"][k]).max() / max(np.abs(o["grads"][k]).max(), 1e-4)
+        assert err <= TOL, (k, err)
+    with torch.no_grad():
+        model = product.product_model(case["spec"], case["params"])
+        a1, A1, a2, A2 = case["inputs"]
+        y_eval = model(a1, A1.astype(np.float32), a2, A2.astype(np.float32)).cpu().numpy()
+    assert rel_err(y_eval, o["logits"]) <= TOL
+
+
+def test_more_than_64_atoms_outside_the_tensor_core_shapes_fails_loudly():
+    import gcnbmp
+    from gcnbmp import synthetic
+    atoms, adj = synthetic.random_molecules(np.random.default_rng(0), 3, 80)
+    net = gcnbmp.GGNNMono(16, 32, 2)            # hidden 32: only the <= 64-atom FFMA kernels cover it
+    with pytest.raises(ValueError, match="n_atoms=80"):
+        net(atoms, adj)
+
+
 def test_inference_path_equals_training_path():
     """no_grad takes the stash-free kernel path; outputs must be identical bit for bit."""
     case = cases.pair_case("C", seed=2)
