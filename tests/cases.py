@@ -32,6 +32,9 @@ def pair_case(name, seed=0, dtype=np.float64):
         # the last step] (2 * hidden wide)
         "E3": dict(enc="mono", H=32, T=3, tied=True, sum_readout=True, O=24, attn="nie", head=8, hole_hidden=(), K=5,
                    mb=4, N1=20, N2=17, first_last=True),
+        # the same composition at GGNN hidden 128: the co-attention sees 256-wide atoms
+        "E3B": dict(enc="mono", H=128, T=2, tied=True, sum_readout=True, O=24, attn="nie", head=8, hole_hidden=(), K=5,
+                    mb=3, N1=20, N2=27, first_last=True),
         # headline script: untied message layers, shared GRU, VQA attention, hidden head layers
         "U": dict(enc="mono", H=16, T=3, tied=False, sum_readout=False, O=16, attn="vqa", head=8,
                   hole_hidden=(32, 16), K=1, mb=5, N1=23, N2=31),

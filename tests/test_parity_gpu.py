@@ -51,6 +51,40 @@ def test_pair_with_more_than_64_atoms_matches_oracle(name):
     assert rel_err(y_eval, o["logits"]) <= TOL
 
 
+def test_coattention_on_256_wide_atoms_and_readout_backward_at_hidden_256():
+    """train_ddi_modify_eval3.py:110-134 at GGNN hidden 128 feeds [h_first | h_last] = 256-wide atoms to the co-attention (wider than the
+    shared-memory-resident CUDA kernel holds), and BASELINE config D's read-out (hidden = out_dim = 256) as a training step: both take
+    the library-GEMM composition of the same formulas; every value and gradient vs the fp64 oracle."""
+    case = cases.pair_case("E3B", seed=8)
+    o = cases.oracle_eval(case)
+    p = product.product_eval(case)
+    assert rel_err(p["logits"], o["logits"]) <= TOL
+    for k in sorted(o["grads"]):
+        err = np.abs(p["grads"][k] - o["grads"][k]).max() / max(np.abs(o["grads"][k]).max(), 1e-4)
+        assert err <= TOL, (k, err)
+    import gcnbmp
+    rng = np.random.default_rng(3)
+    mb, N, H, O = 3, 50, 256, 256
+    shapes = {"i_layer/W": (O, 2 * H), "i_layer/b": (O,), "j_layer/W": (O, 2 * H), "j_layer/b": (O,)}
+    params = R.init_params(shapes, rng, dtype=np.float64)
+    tab = R.wrap_params(params)
+    h, h0, w = rng.standard_normal((mb, N, H)) * 0.3, rng.standard_normal((mb, N, H)) * 0.3, rng.standard_normal((mb, O))
+    vh, vh0 = F.param(h), F.param(h0)
+    og = R.GGNNReadout(R.P(tab), O, H, activation="tanh", activation_agg="tanh")(vh, vh0)
+    F.sum_(F.mul(og, F.const(w))).backward()
+    net = gcnbmp.GGNNReadout(O, H, activation=gcnbmp.functions.tanh, activation_agg=gcnbmp.functions.tanh)
+    net.load_params(params)
+    th = torch.tensor(h, dtype=torch.float32, device="cuda", requires_grad=True)
+    th0 = torch.tensor(h0, dtype=torch.float32, device="cuda", requires_grad=True)
+    pg = net(th, th0)
+    (pg * torch.tensor(w, dtype=torch.float32, device="cuda")).sum().backward()
+    assert rel_err(pg.detach().cpu().numpy(), og.data) <= TOL
+    assert rel_err(th.grad.cpu().numpy(), vh.grad) <= TOL and rel_err(th0.grad.cpu().numpy(), vh0.grad) <= TOL
+    g = net.grad_dict()
+    for k in params:
+        assert rel_err(g[k], tab[k].grad) <= TOL, k
+
+
 def test_more_than_64_atoms_outside_the_tensor_core_shapes_fails_loudly():
     import gcnbmp
     from gcnbmp import synthetic
