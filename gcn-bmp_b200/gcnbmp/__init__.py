@@ -10,6 +10,7 @@ from . import functional
 from .functional import pack_adjacency, unpack_adjacency
 from . import metrics
 from . import evaluate
+from . import fused
 from .links import (MAX_ATOMIC_NUM, functions, Link, ChainList, GraphLinear, GGNNUpdate, RelGCNUpdate,
                     GGNNReadout, GGNN, GGNNMono, RelGCN, GIN, GINUpdate, NFP, NFPUpdate, NFPReadout, BiMPM, NieFineCoattention, VQAParallelCoattention,
                     PoolingFineCoattention, AlternatingCoattention, ParallelCoattention, CircularParallelCoattention, GlobalCoattention, NeuralCoattention, FourierFineCoattention, DeepNieFineCoattention, VeryDeepNieFineCoattention, ExtremeDeepNieFineCoattention, HolE, HOLE, MLP, SymMLP, NTN, DistMult, BilinearDiag, GraphConvPredictorForPair,

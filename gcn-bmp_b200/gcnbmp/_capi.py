@@ -45,6 +45,17 @@ class GgnnBwd(C.Structure):
         ("mol_index", fp)]
 
 
+class Pair(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "out_dim", "head", "n_classes", "n_steps", "n_atom_types", "mode",
+                                       "coattn_variant", "coattn_act")] + [
+        ("atoms_1", fp), ("atoms_2", fp), ("adj_1", fp), ("adj_2", fp), ("labels", fp), ("count", C.c_float), ("embed_W", fp),
+        ("msg_W", _A()), ("msg_b", _A()), ("gru", GRU * MAX_STEPS), ("stateful", C.c_int * MAX_STEPS)] + [
+        (n, fp) for n in ("W", "V1", "V2", "b", "lt_1", "lt_2", "wa_1", "wa_2", "W_j", "b_j", "out_W", "out_b", "d_embed_W")] + [
+        ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS)] + [
+        (n, fp) for n in ("d_W", "d_V1", "d_V2", "d_b", "d_lt_1", "d_lt_2", "d_wa_1", "d_wa_2", "d_W_j", "d_b_j", "d_out_W", "d_out_b",
+                          "logits", "loss", "workspace")] + [("workspace_bytes", C.c_size_t)]
+
+
 class Bimpm(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("mb", "n1", "n2", "hidden", "head")] + [
         ("atoms_1", fp), ("atoms_2", fp), ("max_pooling_W", fp), ("att_mean_W", fp), ("att_max_W", fp),
@@ -148,6 +159,8 @@ def _load():
     lib.bmp_ggnn_tc_workspace_bytes.argtypes, lib.bmp_ggnn_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_ggnn_stash2_bytes.argtypes, lib.bmp_ggnn_stash2_bytes.restype = [i, i, i], C.c_size_t
     lib.bmp_ggnn_x3_workspace_bytes.argtypes, lib.bmp_ggnn_x3_workspace_bytes.restype = [i, i, i, i, i, i], C.c_size_t
+    lib.bmp_pair_workspace_bytes.argtypes, lib.bmp_pair_workspace_bytes.restype = [i] * 9, C.c_size_t
+    lib.bmp_pair_forward_backward.argtypes, lib.bmp_pair_forward_backward.restype = [C.c_void_p, vp], C.c_int
     lib.bmp_readout_tc_workspace_bytes.argtypes, lib.bmp_readout_tc_workspace_bytes.restype = [i, i], C.c_size_t
     lib.bmp_coattn_tc_workspace_bytes.argtypes, lib.bmp_coattn_tc_workspace_bytes.restype = [i], C.c_size_t
     lib.bmp_relgcn_tc_workspace_bytes.argtypes, lib.bmp_relgcn_tc_workspace_bytes.restype = [i, i], C.c_size_t
@@ -166,7 +179,7 @@ lib = _load()
 EXPORTS = ["bmp_ggnn_forward", "bmp_ggnn_backward", "bmp_embed_backward", "bmp_relgcn_forward",
            "bmp_relgcn_backward", "bmp_relgcn_tc_workspace_bytes", "bmp_rescale_adj", "bmp_readout_forward", "bmp_readout_backward", "bmp_readout_tc_workspace_bytes", "bmp_coattn_forward",
            "bmp_coattn_backward", "bmp_coattn_tc_workspace_bytes", "bmp_hole_corr_forward", "bmp_hole_corr_backward", "bmp_linear_forward",
-           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_ggnn_x3_workspace_bytes", "bmp_wgrad", "bmp_wgrad_tc", "bmp_wgrad_tc3", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
+           "bmp_linear_backward", "bmp_ggnn_tc_workspace_bytes", "bmp_ggnn_stash2_bytes", "bmp_ggnn_x3_workspace_bytes", "bmp_pair_workspace_bytes", "bmp_pair_forward_backward", "bmp_wgrad", "bmp_wgrad_tc", "bmp_wgrad_tc3", "bmp_colsum", "bmp_sigmoid_ce", "bmp_adam_step",
            "bmp_pair_features_forward", "bmp_pair_features_backward", "bmp_bilinear_forward", "bmp_bilinear_backward", "bmp_grad_hooks",
            "bmp_atoms_bcast_add_act_forward", "bmp_atoms_bcast_add_act_backward", "bmp_atoms_softmax_forward", "bmp_atoms_softmax_backward",
            "bmp_atoms_pool_forward", "bmp_atoms_pool_backward", "bmp_gin_aggregate", "bmp_nfp_gather", "bmp_embed_forward", "bmp_bimpm_forward", "bmp_bimpm_backward", "bmp_bimpm_workspace_bytes",

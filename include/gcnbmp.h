@@ -336,6 +336,41 @@ int bmp_adam_step(float *param, const float *grad, float *m, float *v, int n,
                   float alpha, float beta1, float beta2, float eps,
                   float weight_decay_rate, int step, void *stream);
 
+/* ---- one training step of a drug PAIR batch in ONE call ------------------------
+ * replaces GraphConvPredictorForPair.__call__ + the loss and Chainer's backward through them (train_binary.py:84-118,524)
+ * for the headline composition: the SAME GGNN encoder on both drugs (its final atom states; the co-attention ignores the
+ * graph vectors, nie_coattention.py:335) -> fine-grained co-attention (Nie / VQA; variant POOL with head = 0) -> HolE
+ * (circular correlation, hidden_dims = (), l_out) -> sigmoid cross-entropy (mean over labels != -1).
+ * Writes `logits` (mb, n_classes), ADDS the loss into loss[0] and every parameter gradient into its d_* pointer (the layout
+ * a flat gradient buffer wants: tied steps pass the same pointers).  The caller owns everything, including ONE workspace of
+ * bmp_pair_workspace_bytes(): both encoder stashes (fp32, or the bf16 panel stash in BMP_MODE_BF16), the weight images, the
+ * co-attention temporaries.  BMP_MODE_F32 runs the encoders on the fp32 tensor-core path when the shape is covered.       */
+typedef struct {
+    int mb, n1, n2, hidden, out_dim, head, n_classes, n_steps, n_atom_types, mode;
+    int coattn_variant, coattn_act;
+    const int32_t *atoms_1, *atoms_2;      /* (mb,N1), (mb,N2) */
+    const float   *adj_1, *adj_2;          /* (mb,4,N1,N1), (mb,4,N2,N2) fp32 */
+    const int32_t *labels;                 /* (mb,n_classes), -1 = ignored */
+    float count;                           /* what the loss mean divides by (the GLOBAL count of labels != -1 under data parallelism) */
+    const float *embed_W;
+    const float *msg_W[BMP_MAX_STEPS], *msg_b[BMP_MAX_STEPS];
+    bmp_gru_t    gru[BMP_MAX_STEPS];
+    int          stateful[BMP_MAX_STEPS];
+    const float *W, *V1, *V2, *b, *lt_1, *lt_2, *wa_1, *wa_2, *W_j, *b_j;     /* co-attention, as bmp_coattn_fwd_t */
+    const float *out_W, *out_b;            /* HolE l_out: (n_classes, out_dim), (n_classes) */
+    float *d_embed_W;
+    float *d_msg_W[BMP_MAX_STEPS], *d_msg_b[BMP_MAX_STEPS];
+    bmp_gru_grad_t d_gru[BMP_MAX_STEPS];
+    float *d_W, *d_V1, *d_V2, *d_b, *d_lt_1, *d_lt_2, *d_wa_1, *d_wa_2, *d_W_j, *d_b_j;
+    float *d_out_W, *d_out_b;
+    float *logits, *loss;
+    void  *workspace;
+    size_t workspace_bytes;
+} bmp_pair_t;
+
+size_t bmp_pair_workspace_bytes(int mb, int n1, int n2, int hidden, int out_dim, int head, int n_classes, int n_steps, int mode);
+int bmp_pair_forward_backward(const bmp_pair_t *a, void *stream);
+
 /* ---- remaining link-prediction heads --------------------------------
  * Pair features feeding a Linear stack:
  *   BMP_PAIR_SYM    out (rows, 2*dim) = [l + r | l * r]     SymMLP, models/mlp.py:104-105

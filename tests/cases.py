@@ -41,6 +41,9 @@ def pair_case(name, seed=0, dtype=np.float64):
         # modular GGNN (models/models/ggnn.py) tied + pooling attention
         "M": dict(enc="ggnn", H=32, T=3, tied=True, concat_hidden=False, O=24, attn="pool", head=None,
                   hole_hidden=(), K=1, mb=4, N1=20, N2=18, activation="tanh"),
+        # GGNNMono + pooling attention, ragged sides (the one-call pair step's POOL variant)
+        "M2": dict(enc="mono", H=64, T=3, tied=False, sum_readout=False, O=24, attn="pool", head=None,
+                   hole_hidden=(), K=2, mb=5, N1=40, N2=33),
         # modular GGNN untied (every step stateless) + HolE without attention
         "MU": dict(enc="ggnn", H=16, T=3, tied=False, concat_hidden=False, O=16, attn=None, head=None,
                    hole_hidden=(8,), K=1, mb=3, N1=12, N2=12, activation="identity"),

@@ -33,8 +33,12 @@ def product_model(spec, params):
     return model
 
 
-def product_eval(case):
+def product_eval(case, mode=None):
     model = product_model(case["spec"], case["params"])
+    if mode is not None:
+        model.graph_conv.mode = mode
+        if "attn" in model._children:
+            model.attn.mode = mode
     a1, A1, a2, A2 = case["inputs"]
     model.cleargrads()
     logits = model(a1, A1.astype(np.float32), a2, A2.astype(np.float32))

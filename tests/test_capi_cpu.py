@@ -30,7 +30,8 @@ def test_ctypes_structs_mirror_the_header():
     structs = {"bmp_gru_t": _capi.GRU, "bmp_ggnn_fwd_t": _capi.GgnnFwd, "bmp_ggnn_bwd_t": _capi.GgnnBwd,
                "bmp_relgcn_fwd_t": _capi.RelgcnFwd, "bmp_relgcn_bwd_t": _capi.RelgcnBwd,
                "bmp_readout_fwd_t": _capi.ReadoutFwd, "bmp_readout_bwd_t": _capi.ReadoutBwd,
-               "bmp_coattn_fwd_t": _capi.CoattnFwd, "bmp_coattn_bwd_t": _capi.CoattnBwd, "bmp_bimpm_t": _capi.Bimpm}
+               "bmp_coattn_fwd_t": _capi.CoattnFwd, "bmp_coattn_bwd_t": _capi.CoattnBwd, "bmp_bimpm_t": _capi.Bimpm,
+               "bmp_pair_t": _capi.Pair}
     probes = []
     for cname, cls in structs.items():
         probes.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

@@ -540,3 +540,36 @@ def test_fp32_mode_on_tensor_cores_matches_oracle_and_the_ffma_kernels(H, T, tie
     for k in params:
         if np.abs(got[False]["grads"][k]).max() > 1e-12:
             assert rel_err(got[True]["grads"][k], got[False]["grads"][k]) <= 5e-5, k
+
+
+@pytest.mark.parametrize("name,mode", [("C", "f32"), ("CB", "f32"), ("CB", "bf16"), ("M2", "f32")])
+def test_one_call_pair_step_matches_oracle_and_the_composed_path(name, mode):
+    """bmp_pair_forward_backward (csrc/pair.cu): the whole pair step -- both encoder passes, co-attention, HolE, sigmoid-CE and the
+    backward chain into caller-owned gradient buffers -- as ONE C call, against the fp64 oracle (fp32 mode: 1e-4) and against the
+    composed autograd path through the same kernels (both modes)."""
+    import gcnbmp
+    case = cases.pair_case(name, seed=11)
+    a1, A1, a2, A2 = case["inputs"]
+    A1, A2 = A1.astype(np.float32), A2.astype(np.float32)
+    y = case["labels"]
+    o = cases.oracle_eval(case)
+    ref = product.product_eval(case, mode=gcnbmp.MODE_BF16 if mode == "bf16" else gcnbmp.MODE_F32)
+    model = product.product_model(case["spec"], case["params"])
+    if mode == "bf16":
+        model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
+    assert gcnbmp.fused.supported(model)
+    model.cleargrads()
+    n0 = gcnbmp.launch_count()
+    loss, logits = gcnbmp.fused.pair_forward_backward(model, a1, A1, a2, A2, y)
+    assert gcnbmp.launch_count() > n0
+    grads = model.grad_dict()
+    tol_ref = 1e-5 if mode == "f32" else 2e-3          # same kernels; bf16: atomics order + tape differences
+    assert rel_err(logits.cpu().numpy(), ref["logits"]) <= tol_ref
+    assert abs(float(loss) - ref["loss"]) <= tol_ref * max(1.0, abs(ref["loss"]))
+    for k in sorted(ref["grads"]):
+        assert rel_err(grads[k], ref["grads"][k]) <= max(tol_ref, 2e-5), (k, rel_err(grads[k], ref["grads"][k]))
+    if mode == "f32":
+        assert rel_err(logits.cpu().numpy(), o["logits"]) <= TOL
+        assert abs(float(loss) - float(o["loss"])) <= TOL * max(1.0, abs(float(o["loss"])))
+        for k in sorted(o["grads"]):
+            assert rel_err(grads[k], o["grads"][k]) <= TOL, (k, rel_err(grads[k], o["grads"][k]))
