@@ -186,7 +186,7 @@ def main():
     PairPlain = load_class("train_ddi_modify_eval2.py", "GraphConvPredictorForPair")
     PairEval3 = load_class("train_ddi_modify_eval3.py", "GraphConvPredictorForPair")     # co-attention on [h_first || h_last] atoms
     import cases
-    for cname in ("C", "U", "A", "MU", "B", "CB", "E3"):
+    for cname in ("C", "U", "A", "MU", "B", "CB", "E3", "L1", "E3B"):
         case = cases.pair_case(cname, seed=7)
         sp, params = case["spec"], case["params"]
         if sp["enc"] == "mono":

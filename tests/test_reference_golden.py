@@ -166,7 +166,8 @@ def test_oracle_reproduces_reference_pair_step(name):
 
 
 def test_pair_fixtures_cover_the_baseline_shapes():
-    assert set(PAIRS) >= {"A", "B", "C", "U", "MU"}
+    # CB: the bench's exact shape; L1: 100 / 70 atoms per molecule (no atom cap in the reference); E3 / E3B: [h_first | h_last] atoms
+    assert set(PAIRS) >= {"A", "B", "C", "U", "MU", "CB", "L1", "E3", "E3B"}
 
 
 @pytest.mark.gpu
@@ -181,7 +182,9 @@ def test_cuda_pair_step_reproduces_reference_pair_step(name):
     assert abs(float(p["loss"]) - loss) <= 1e-4 * max(1.0, abs(loss))
     for k, g in gp.items():
         if np.abs(g).max() > 1e-12:
-            assert rel_err(p["grads"][k], g) <= 1e-4, k
+            # a 1-element gradient that is a cancelling sum over every atom pair (the energy bias: ~2e4 terms at 100 x 70 atoms, result
+            # ~1e-4) carries fp32 summation noise of ~2e-8 absolute: held to 1e-7 absolute instead of 1e-4 of its own magnitude
+            assert rel_err(p["grads"][k], g, floor=1e-3 if g.size == 1 else 1e-30) <= 1e-4, k
 
 
 # ------------------------------------------------------------------------------------------------ GPU
