@@ -71,17 +71,6 @@ struct Args {
 __device__ __forceinline__ float sigmoid_x3(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 // 1 - 2 / (1 + e^{2x}): absolute error at the fp32 rounding level of the result's range
 __device__ __forceinline__ float tanh_x3(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
-// wait with a sleep between polls: a waiting warp leaves the issue slots to the warps that have work
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra D_%=;\n\t"
-        "nanosleep.u32 %2;\n\t"
-        "bra W_%=;\n\t"
-        "D_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
-}
 // tcgen05.ld 16x256b.x2: 16 TMEM lanes x 16 columns; thread t gets, for column group j (8 columns) and row half rh,
 // registers 4 j + 2 rh + {0, 1} = (lane t / 4 + 8 rh, columns 8 j + 2 (t % 4) + {0, 1})
 __device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
