@@ -345,6 +345,7 @@ def run_gpu(args):
         model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
         fp32_exact = dict(value=round(v32, 1), unit="pairs/s", ms_per_step=round(ms32 / 2, 3), steps=2, warmup=1,
                           e2e=round(e32, 1) if e32 else None, achieved_tflops_step=round(3 * fl["pair_fwd"] * v32 / 1e12 / world, 2),
+                          frac_of_split_bf16_peak=round(3 * fl["pair_fwd"] * v32 / 1e12 / world / (pk["bf16_sustained"] / 3.0), 4),
                           note="BMP_MODE_F32: the GGNN encoder's contractions (forward, backward-data, parameter gradients) on tcgen05 at "
                                "fp32 grade -- every operand a bf16 hi/lo pair, three UMMAs per product, fp32 TMEM accumulate (csrc/ggnn_x3.cu, "
                                "wgrad_tc.cu); adjacency products, co-attention, readout, HolE in fp32 FFMA.  Parity <= 1e-4 vs the oracle "
