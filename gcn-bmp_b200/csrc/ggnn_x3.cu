@@ -648,13 +648,19 @@ static int launch_gemm(Args &g, cudaStream_t st) {
     return check_launch("rowgemm3_kernel");
 }
 
+static bool same_msg_b(const bmp_ggnn_fwd_t *a, int u, int t) { return a->msg_b[u] == a->msg_b[t]; }
+// the backward struct carries no message bias: two steps that share W_m share their linear link, hence its bias, in every caller
+// of this library; the forward (which packs the images both directions use) compares the pointer
+static bool same_msg_b(const bmp_ggnn_bwd_t *, int, int) { return true; }
+
 // step -> image index (steps that share every parameter pointer and the stateful flag share an image)
 template <class S>
 static void image_plan(const S *a, int *img_of) {
     for (int t = 0; t < a->n_steps; ++t) {
         img_of[t] = t;
         for (int u = 0; u < t; ++u)
-            if (a->msg_W[u] == a->msg_W[t] && same_gru(a->gru[u], a->gru[t]) && (a->stateful[u] != 0) == (a->stateful[t] != 0)) {
+            if (a->msg_W[u] == a->msg_W[t] && same_msg_b(a, u, t) && same_gru(a->gru[u], a->gru[t]) &&
+                (a->stateful[u] != 0) == (a->stateful[t] != 0)) {
                 img_of[t] = img_of[u];
                 break;
             }
