@@ -308,6 +308,12 @@ def _encode(x, adj, state, plan, msgs, grus, embed_W, mode, keep_steps=False, mo
     `keep_steps` (or in fp32 mode with a tape) -- BF16 mode otherwise keeps a bf16 panel stash internally."""
     want = torch.is_grad_enabled()
     H = msgs[0][0].shape[1]
+    if mode == K.MODE_BF16 and adj.shape[-1] > Fn.MAX_KERNEL_ATOMS and mol_index is None:
+        # molecules with more than 64 atoms: the fused tcgen05 encoders hold a two-molecule tile of 64-atom molecules; such batches take
+        # the fp32 tensor-core path (row GEMMs, any N up to 256) -- more accurate, slower, same interface
+        mode = K.MODE_F32
+        if adj.dtype != torch.float32:
+            adj = Fn.unpack_adjacency(adj) if Fn.adj_format(adj) == 2 else adj.to(torch.float32)
     if mode == K.MODE_BF16 and H not in (64, 128, 256) and H < 128 and state is None and msgs[0][0].shape[0] == 4 * H:
         # The tcgen05 encoders exist for hidden 64 / 128 (256 forward only); any other hidden size <= 128 (the paper's 32, the
         # reference's default 16) runs on them ZERO-PADDED to the next of those: padded input columns meet zero weights, a padded

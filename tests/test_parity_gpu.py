@@ -85,6 +85,24 @@ def test_coattention_on_256_wide_atoms_and_readout_backward_at_hidden_256():
         assert rel_err(g[k], tab[k].grad) <= TOL, k
 
 
+def test_bf16_mode_takes_batches_with_more_than_64_atoms_through_the_fp32_tensor_core_path():
+    """A model in BF16 mode does not fail on a batch padded beyond 64 atoms: that batch runs the fp32 tensor-core encoder and the
+    library compositions, i.e. inside the fp32 bound."""
+    import gcnbmp
+    case = cases.pair_case("L1", seed=5)
+    o = cases.oracle_eval(case)
+    p = product.product_eval(case, mode=gcnbmp.MODE_BF16)
+    assert rel_err(p["logits"], o["logits"]) <= TOL
+    for k in sorted(o["grads"]):
+        assert rel_err(p["grads"][k], o["grads"][k], floor=1e-3 if o["grads"][k].size == 1 else 1e-30) <= TOL, k
+    a1, A1, a2, A2 = case["inputs"]
+    model = product.product_model(case["spec"], case["params"])
+    model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
+    with torch.no_grad():           # uint8 adjacency as the BF16-mode callers hold it
+        y8 = model(a1, A1.astype(np.uint8), a2, A2.astype(np.uint8)).cpu().numpy()
+    assert rel_err(y8, o["logits"]) <= TOL
+
+
 def test_more_than_64_atoms_outside_the_tensor_core_shapes_fails_loudly():
     import gcnbmp
     from gcnbmp import synthetic
