@@ -115,6 +115,20 @@ def test_fp32_tensor_core_workspace_query_is_host_only():
     assert q(100, 257, 128, 4, 3, 0) == 0 and q(100, 256, 256, 4, 3, 0) == 0
 
 
+def test_pair_step_workspace_query_is_host_only():
+    """bmp_pair_workspace_bytes (csrc/pair.cu) sizes the ONE caller-owned buffer of bmp_pair_forward_backward without a GPU."""
+    q = __import__("gcnbmp")._capi.lib.bmp_pair_workspace_bytes
+    mb, n1, n2, H, O, hd, K, T = 4144, 64, 64, 128, 128, 8, 86, 6
+    f32, bf16 = q(mb, n1, n2, H, O, hd, K, T, 0), q(mb, n1, n2, H, O, hd, K, T, 1)
+    rows = mb * 64
+    stash = (T + 1) + T + 3 * T + T + 4 * T + (T + 1)                   # Hs, Ms, Gs, RSs, Ps, dHs in units of rows x H floats
+    assert f32 > 2 * stash * rows * H * 4                               # both drugs' fp32 stashes (+ the tensor-core workspace)
+    assert 0 < bf16 < f32                                               # the bf16 panel stash is the smaller tape
+    assert q(mb, n1, n2, 96, O, hd, K, T, 1) == 0                       # no bf16 panel stash at hidden 96
+    assert q(mb, n1, n2, 96, O, hd, K, T, 0) > 0                        # fp32 mode: FFMA encoders cover it
+    assert q(0, n1, n2, H, O, hd, K, T, 0) == 0 and q(mb, n1, n2, H, O, hd, K, 17, 0) == 0
+
+
 def test_chainer_adapter_is_import_guarded():
     """the Chainer / CuPy adapter imports without either package and fails loudly, not silently, when used."""
     from gcnbmp import chainer_adapter as B

@@ -591,3 +591,22 @@ def test_one_call_pair_step_matches_oracle_and_the_composed_path(name, mode):
         assert abs(float(loss) - float(o["loss"])) <= TOL * max(1.0, abs(float(o["loss"])))
         for k in sorted(o["grads"]):
             assert rel_err(grads[k], o["grads"][k]) <= TOL, (k, rel_err(grads[k], o["grads"][k]))
+
+
+def test_one_call_pair_step_refuses_a_short_workspace_and_unsupported_models():
+    import ctypes as C
+    import gcnbmp
+    from gcnbmp import _capi as K
+    a = K.Pair()
+    a.mb, a.n1, a.n2, a.hidden, a.out_dim, a.head, a.n_classes, a.n_steps, a.n_atom_types, a.mode = 4, 20, 20, 32, 16, 8, 3, 2, 117, 0
+    buf = torch.zeros(4096, device="cuda")
+    for f in ("atoms_1", "atoms_2", "adj_1", "adj_2", "labels", "embed_W", "out_W", "logits", "loss", "workspace"):
+        setattr(a, f, C.c_void_p(buf.data_ptr()))
+    a.count, a.workspace_bytes = 12.0, 1024
+    rc = K.lib.bmp_pair_forward_backward(C.byref(a), None)
+    assert rc == -1 and b"workspace" in K.lib.bmp_last_error()
+    case = cases.pair_case("MU", seed=1)            # modular GGNN + HolE without attention: outside the one-call composition
+    model = product.product_model(case["spec"], case["params"])
+    assert not gcnbmp.fused.supported(model)
+    with pytest.raises(ValueError):
+        gcnbmp.fused.pair_forward_backward(model, *[x for x in case["inputs"]], case["labels"])
