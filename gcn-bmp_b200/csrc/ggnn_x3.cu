@@ -46,7 +46,7 @@ constexpr int OFF_F32 = OFF_WR + WDEPTH * 2 * PANEL_BYTES;
 constexpr int OFF_BAR = OFF_F32 + F32_DEPTH * F32_SLOT;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 
-enum { EPI_MSG = 0, EPI_R, EPI_Z, EPI_HB, EPI_Q, EPI_DHX, EPI_DM, EPI_DHMSG };
+enum { EPI_MSG = 0, EPI_R, EPI_Z, EPI_HB, EPI_Q, EPI_DHX, EPI_DM, EPI_DHMSG, EPI_LIN /* accumulator + bias */ };
 
 struct Job {
     const float *A[MAXB];            // K-block b: (rows, 64 * kt[b]) fp32, leading dimension lda[b]
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(ACCE(buf));
                 }
-                if (epi == EPI_R || epi == EPI_Z || epi == EPI_HB) {
+                if (epi == EPI_R || epi == EPI_Z || epi == EPI_HB || epi == EPI_LIN) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         float2 b2 = make_float2(0.f, 0.f);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NT, 1) rowgemm3_kernel(const __grid_constant__
                         ST(J.out0, J.lo0, f);
                         break;
                     }
-                    default:                    // EPI_MSG (bias rides in the K stream), EPI_DM: the accumulator as it is
+                    default:                    // EPI_MSG (bias rides in the K stream), EPI_DM, EPI_LIN: the accumulator as it is
                         ST(J.out0, J.lo0, f);
                         break;
                 }
@@ -699,6 +699,118 @@ using namespace bmp::x3;
 
 // debug: p = device buffer of 8 x n long long; every rowgemm3 launch after this call fills the next 8-slot record
 extern "C" void bmp_debug_set_buffer_x3(void *p) { g_dbg = (long long *)p; g_dbg_slot = 0; }
+
+// ------------------------------------------------------------------------------------------------ gated read-out (forward)
+// models/readout/ggnn_readout.py:42-58 (R1) and models/ggnn_att.py:338-346 (R2) in BMP_MODE_F32: the two linears over all atoms are row
+// GEMMs on the same split-bf16 kernel (pre-activations to a workspace), the gate product and the sum over a molecule's atoms a
+// small kernel.  The backward stays the kernel of readout.cu (it needs h, h0, the weights and g only).
+namespace bmp {
+namespace x3 {
+
+// W (n_out, ldw) row-major, columns [k0, k0 + 64 kt): k-tiles [nc][kk] of the B operand (n = output column)
+__global__ void __launch_bounds__(256) pack_lin_kernel(const float *__restrict__ W, int ldw, int n_out, int k0, int kt, uint8_t *img) {
+    const int tile = blockIdx.x, nc = tile / kt, kk = tile % kt, NC = n_out < 128 ? n_out : 128;
+    uint8_t *dst = img + (size_t)tile * WSLOT;
+    for (int idx = threadIdx.x; idx < NC * 8; idx += 256) {
+        const int c8 = idx % 8, n = idx / 8;          // k fastest: consecutive addresses of one weight row
+        const float *src = W + (long)(nc * 128 + n) * ldw + k0 + kk * 64 + c8 * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            h[x] = pack_bf16(v[2 * x], v[2 * x + 1]);
+            l[x] = pack_bf16(v[2 * x] - __uint_as_float(h[x] << 16), v[2 * x + 1] - __uint_as_float(h[x] & 0xFFFF0000u));
+        }
+        const uint32_t off = sw128(n, c8 * 8);
+        *reinterpret_cast<uint4 *>(dst + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(dst + PANEL_BYTES + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// g[mol][o] = act_agg( sum_n sigmoid(pi[row][o]) * act(pj[row][o]) * mask[row] )
+__global__ void __launch_bounds__(256) readout_reduce_kernel(const float *__restrict__ pi, const float *__restrict__ pj,
+                                                             const float *__restrict__ mask, float *__restrict__ g, int mb, int N, int O,
+                                                             int act, int act_agg) {
+    for (int mol = blockIdx.x; mol < mb; mol += gridDim.x)
+        for (int o = threadIdx.x; o < O; o += 256) {
+            float s = 0.f;
+            for (int n = 0; n < N; ++n) {
+                const long row = (long)mol * N + n;
+                const float v = sigmoidf_(__ldg(pi + row * O + o)) * act_fwd(act, __ldg(pj + row * O + o));
+                s += mask ? v * __ldg(mask + row) : v;
+            }
+            g[(long)mol * O + o] = act_fwd(act_agg, s);
+        }
+}
+
+static bool readout_ok(int mb, int N, int H, int O, int variant) {
+    return (H == 64 || H == 128 || H == 256) && (O == 64 || O == 128 || O == 256) && (long)mb * N >= MIN_ROWS &&
+           (variant == BMP_READOUT_R1 || variant == BMP_READOUT_R2);
+}
+static size_t readout_img_tiles(int H, int O, bool has_h0, int variant) {
+    const int hc = (O + 127) / 128, kb = H / 64;
+    const int blk_i = has_h0 ? 2 : 1, blk_j = (has_h0 && variant == BMP_READOUT_R1) ? 2 : 1;
+    return (size_t)(blk_i + blk_j) * kb * hc;
+}
+
+}  // namespace x3
+}  // namespace bmp
+
+// Bytes of workspace the tensor-core fp32 read-out forward needs (weight images + the two pre-activation arrays); 0 = not covered.
+extern "C" size_t bmp_readout_x3_workspace_bytes(int mb, int n_atoms, int hidden, int out_dim, int variant, int has_h0) {
+    if (!readout_ok(mb, n_atoms, hidden, out_dim, variant)) return 0;
+    return readout_img_tiles(hidden, out_dim, has_h0 != 0, variant) * WSLOT + 2 * (size_t)mb * n_atoms * out_dim * sizeof(float) + 4096;
+}
+
+bool bmp_readout_x3_usable(const bmp_readout_fwd_t *a) {
+    if (a->mode != BMP_MODE_F32 || !a->tc_workspace || !readout_ok(a->mb, a->n_atoms, a->hidden, a->out_dim, a->variant)) return false;
+    if (!aligned16({a->b_i, a->b_j})) return false;
+    return a->tc_workspace_bytes >= bmp_readout_x3_workspace_bytes(a->mb, a->n_atoms, a->hidden, a->out_dim, a->variant, a->h0 != nullptr);
+}
+
+int bmp_readout_forward_x3(const bmp_readout_fwd_t *a, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = a->hidden, O = a->out_dim, N = a->n_atoms, NC = O < 128 ? O : 128, hc = (O + 127) / 128, kb = H / 64;
+    const long rows = (long)a->mb * N;
+    const bool has_h0 = a->h0 != nullptr;
+    const int blk[2] = {has_h0 ? 2 : 1, (has_h0 && a->variant == BMP_READOUT_R1) ? 2 : 1};
+    const int Kin[2] = {blk[0] * H, blk[1] * H};
+    const float *W[2] = {a->W_i, a->W_j}, *bias[2] = {a->b_i, a->b_j};
+    uint8_t *ws = (uint8_t *)(((uintptr_t)a->tc_workspace + 1023) & ~(uintptr_t)1023);
+    uint8_t *img[2] = {ws, ws + (size_t)blk[0] * kb * hc * WSLOT};
+    float *pre = reinterpret_cast<float *>(ws + readout_img_tiles(H, O, has_h0, a->variant) * WSLOT);
+    float *pre_ij[2] = {pre, pre + (size_t)rows * O};
+    int rc;
+    if (!a->tc_images_ready) {
+        for (int w = 0; w < 2; ++w) {
+            // image of linear w: per column chunk the k-tiles of its K blocks in consumption order = all kt = blk * kb tiles of the row
+            pack_lin_kernel<<<blk[w] * kb * hc, 256, 0, st>>>(W[w], Kin[w], O, 0, blk[w] * kb, img[w]);
+            count_launch();
+        }
+        if ((rc = check_launch("pack_lin_kernel"))) return rc;
+    }
+    Args ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.rows = rows; ga.NC = NC;
+    int nj = 0;
+    for (int nc = 0; nc < hc; ++nc)
+        for (int w = 0; w < 2; ++w) {
+            Job &J = ga.job[nj++];
+            J.nblk = blk[w];
+            J.A[0] = a->h; J.A[1] = a->h0; J.lda[0] = J.lda[1] = H; J.kt[0] = J.kt[1] = kb;
+            J.wimg = img[w] + (size_t)nc * blk[w] * kb * WSLOT;
+            J.epi = EPI_LIN;
+            J.bias = bias[w] ? bias[w] + nc * 128 : nullptr;
+            J.out0 = pre_ij[w] + nc * 128; J.lo0 = O;
+        }
+    ga.njobs = nj;
+    if ((rc = launch_gemm(ga, st))) return rc;
+    const int grid = a->mb < 8 * sm_count() ? a->mb : 8 * sm_count();
+    readout_reduce_kernel<<<grid, 256, 0, st>>>(pre_ij[0], pre_ij[1], a->is_real_node, a->g, a->mb, N, O, a->act, a->act_agg);
+    count_launch();
+    return check_launch("readout_reduce_kernel");
+}
 
 // Bytes of workspace the tensor-core fp32 path needs (weight images + per-step temporaries [+ a one-step stash for
 // inference]); 0 = shape not covered (the FFMA kernels of ggnn.cu run instead).

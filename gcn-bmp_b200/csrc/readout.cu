@@ -147,6 +147,9 @@ int bmp_readout_tc(int mb, int N, int H, int O, int variant, int act, int act_ag
                    float *g, const float *dg, float *DU, float *DV, float *dh, float *dh0, void *ws, size_t ws_bytes,
                    bool images_ready, bool bwd, void *stream);   // readout_tc.cu
 
+bool bmp_readout_x3_usable(const bmp_readout_fwd_t *a);                          // ggnn_x3.cu: BMP_MODE_F32 forward on tcgen05 (split bf16)
+int bmp_readout_forward_x3(const bmp_readout_fwd_t *a, void *stream);
+
 extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
     if (!a || !a->g) { set_error("bmp_readout_forward: null argument"); return BMP_EINVAL; }
     int rc = readout_check(a->mb, a->n_atoms, a->hidden, a->out_dim, a->variant, a->h);
@@ -165,6 +168,7 @@ extern "C" int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream) {
                               a->is_real_node, a->W_i, a->b_i, a->W_j, a->b_j, a->g, nullptr, nullptr, nullptr, nullptr, nullptr,
                               a->tc_workspace, a->tc_workspace_bytes, a->tc_images_ready != 0, false, stream);
     }
+    if (bmp_readout_x3_usable(a)) return bmp_readout_forward_x3(a, stream);
     const int Kcat = a->h0 ? 2 * a->hidden : a->hidden;
     size_t smem = sizeof(float) * ((size_t)Kcat * AT + STAGE_FLOATS);
     int grid = a->mb < 148 * 2 ? a->mb : 148 * 2;

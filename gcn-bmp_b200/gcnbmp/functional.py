@@ -405,6 +405,13 @@ def _readout_ws(a, mode, H, O, variant, dev, params):
             ws, a.tc_images_ready = _tc_images("readout", nbytes, dev, params)
             a.mode, a.tc_workspace, a.tc_workspace_bytes = K.MODE_BF16, _p(ws), nbytes
             return ws
+    if mode == K.MODE_F32 and F32_TENSOR_CORES and variant != K.READOUT_SUM and isinstance(a, K.ReadoutFwd):
+        # fp32 mode: the forward's two linears on tcgen05 (bf16 hi/lo split, fp32-grade); the backward kernel is unchanged
+        nbytes = int(K.lib.bmp_readout_x3_workspace_bytes(a.mb, a.n_atoms, H, O, variant, int(bool(a.h0))))
+        if nbytes:
+            ws, a.tc_images_ready = _tc_images("readout_x3", nbytes, dev, params)
+            a.tc_workspace, a.tc_workspace_bytes = _p(ws), nbytes
+            return ws
     return None
 
 

@@ -228,6 +228,9 @@ typedef struct {
 
 int bmp_readout_forward(const bmp_readout_fwd_t *a, void *stream);
 size_t bmp_readout_tc_workspace_bytes(int hidden, int out_dim);   /* 0 = shape not on the tcgen05 path */
+/* BMP_MODE_F32 forward on the tensor cores (both linears as split-bf16 row GEMMs, csrc/ggnn_x3.cu): taken when tc_workspace holds at
+ * least this many bytes; hidden and out_dim in {64,128,256}, variants R1 / R2, mb * n_atoms >= 128; 0 = not covered (FFMA kernel).  */
+size_t bmp_readout_x3_workspace_bytes(int mb, int n_atoms, int hidden, int out_dim, int variant, int has_h0);
 
 /* DU/DV: workspaces (mb*N, O) receiving the pre-activation gradients of the i and
  * j linears; dh/dh0 are ACCUMULATED (+=) so they can point into bmp_ggnn dHs.     */

@@ -610,3 +610,52 @@ def test_one_call_pair_step_refuses_a_short_workspace_and_unsupported_models():
     assert not gcnbmp.fused.supported(model)
     with pytest.raises(ValueError):
         gcnbmp.fused.pair_forward_backward(model, *[x for x in case["inputs"]], case["labels"])
+
+
+@pytest.mark.parametrize("H,O,variant,use_h0,use_mask,nobias,act", [(128, 128, "R2", True, False, False, "identity"),
+                                                                    (64, 256, "R1", True, True, False, "tanh"),
+                                                                    (256, 64, "R1", False, False, True, "relu"),
+                                                                    (128, 128, "R1", True, False, False, "identity")])
+def test_fp32_readout_forward_on_tensor_cores_matches_oracle_and_the_ffma_kernel(H, O, variant, use_h0, use_mask, nobias, act):
+    """BMP_MODE_F32 read-out forward with both linears as split-bf16 row GEMMs (csrc/ggnn_x3.cu) vs the fp64 oracle formulas
+    (ggnn_readout.py:42-58 / ggnn_att.py:338-346) and vs the FFMA kernel; the backward (unchanged kernel) through it."""
+    import gcnbmp
+    from gcnbmp import functional as Fn, _capi as K
+    rng = np.random.default_rng(H + O)
+    mb, N = 7, 41                                     # 287 rows: two full tiles and a tail
+    h, h0 = rng.standard_normal((mb, N, H)) * 0.5, rng.standard_normal((mb, N, H)) * 0.5
+    mask = (rng.random((mb, N)) < 0.7).astype(np.float64) if use_mask else None
+    kin_i = 2 * H if use_h0 else H
+    kin_j = H if variant == "R2" else kin_i
+    Wi, Wj = rng.standard_normal((O, kin_i)) / np.sqrt(kin_i), rng.standard_normal((O, kin_j)) / np.sqrt(kin_j)
+    bi, bj = (None, None) if nobias else (rng.standard_normal(O) * 0.1, rng.standard_normal(O) * 0.1)
+    A = {"identity": lambda x: x, "tanh": np.tanh, "relu": lambda x: np.maximum(x, 0)}[act]
+    h1 = np.concatenate([h, h0], axis=2) if use_h0 else h
+    gi = 1.0 / (1.0 + np.exp(-(h1 @ Wi.T + (0 if bi is None else bi))))
+    gj = A((h if variant == "R2" else h1) @ Wj.T + (0 if bj is None else bj))
+    g = gi * gj
+    if mask is not None:
+        g = g * mask[:, :, None]
+    ref = A(g.sum(axis=1)) if variant == "R1" else g.sum(axis=1)
+    t = lambda x: None if x is None else torch.tensor(x, dtype=torch.float32, device="cuda")
+    code = dict(identity=0, tanh=1, relu=2)[act]
+    args = (t(h), t(h0) if use_h0 else None, t(mask), K.READOUT_R1 if variant == "R1" else K.READOUT_R2, code,
+            code if variant == "R1" else 0, t(Wi), t(bi), t(Wj), t(bj), K.MODE_F32)
+    out = {}
+    try:
+        for tc in (True, False):
+            Fn.F32_TENSOR_CORES = tc
+            n0 = gcnbmp.launch_count()
+            with torch.no_grad():
+                out[tc] = Fn.readout(*args).cpu().numpy()
+            out[(tc, "n")] = gcnbmp.launch_count() - n0
+            assert rel_err(out[tc], ref) <= TOL, (tc, rel_err(out[tc], ref))
+    finally:
+        Fn.F32_TENSOR_CORES = True
+    assert out[(True, "n")] > out[(False, "n")]            # pack + GEMM + reduce vs one fused FFMA launch
+    assert rel_err(out[True], out[False]) <= 2e-5
+    # training through the tensor-core forward: the backward kernel sees the same g
+    hh = t(h).requires_grad_()
+    gg = Fn.readout(hh, *args[1:])
+    gg.sum().backward()
+    assert torch.isfinite(hh.grad).all() and float(hh.grad.abs().max()) > 0
