@@ -349,7 +349,7 @@ def run_gpu(args):
                           frac_of_split_bf16_peak=round(3 * fl["pair_fwd"] * v32 / 1e12 / world / (pk["bf16_sustained"] / 3.0), 4),
                           note="BMP_MODE_F32: the GGNN encoder's contractions (forward, backward-data, parameter gradients) on tcgen05 at "
                                "fp32 grade -- every operand a bf16 hi/lo pair, three UMMAs per product, fp32 TMEM accumulate (csrc/ggnn_x3.cu, "
-                               "wgrad_tc.cu); adjacency products, co-attention, readout, HolE in fp32 FFMA.  Parity <= 1e-4 vs the oracle "
+                               "wgrad_tc.cu), the read-out forward on the same GEMM; adjacency products, co-attention, HolE in fp32 FFMA.  Parity <= 1e-4 vs the oracle "
                                "(measured 4e-6 at this shape); e2e with the host adjacency as uint8, widened on the device; frac_of_split_bf16_peak = "
                                "algorithmic TFLOP/s over a third of the sustained bf16 peak (three tensor-core products per algorithmic one)")
     # ---- informational: BASELINE config D (GGNN H256 T8 + R1 readout + HolE->1, forward only) on this rank's GPU, same inputs ----

@@ -115,6 +115,15 @@ def test_fp32_tensor_core_workspace_query_is_host_only():
     assert q(100, 257, 128, 4, 3, 0) == 0 and q(100, 256, 256, 4, 3, 0) == 0
 
 
+def test_fp32_readout_tensor_core_workspace_query_is_host_only():
+    q = __import__("gcnbmp")._capi.lib.bmp_readout_x3_workspace_bytes
+    n = q(4144, 64, 128, 128, 2, 1)                                      # R2 with h0: i over [h | h0], j over h
+    assert n >= 2 * 4144 * 64 * 128 * 4 + (2 + 1) * 2 * 32768              # two pre-activation arrays + 6 packed hi/lo k-tiles
+    assert q(4144, 64, 128, 128, 1, 1) > n                                 # R1: j sees [h | h0] too
+    assert q(4144, 64, 128, 128, 3, 1) == 0 and q(4144, 64, 96, 128, 1, 1) == 0 and q(4144, 64, 128, 40, 1, 1) == 0
+    assert q(1, 64, 128, 128, 1, 1) == 0                                   # fewer rows than one tile
+
+
 def test_pair_step_workspace_query_is_host_only():
     """bmp_pair_workspace_bytes (csrc/pair.cu) sizes the ONE caller-owned buffer of bmp_pair_forward_backward without a GPU."""
     q = __import__("gcnbmp")._capi.lib.bmp_pair_workspace_bytes
