@@ -117,7 +117,8 @@ extern "C" int bmp_pair_forward_backward(const bmp_pair_t *a, void *stream) {
     Plan pl = make_plan(a->workspace, mb, a->n1, a->n2, H, O, head, K, T, a->mode);
     const int N[2] = {a->n1, a->n2};
     const int32_t *atoms[2] = {a->atoms_1, a->atoms_2};
-    const float *adj[2] = {a->adj_1, a->adj_2};
+    const void *adj[2] = {a->adj_1, a->adj_2};
+    if (a->adj_u8 && !bf16) { set_error("bmp_pair_forward_backward: a byte / bit-packed adjacency needs BMP_MODE_BF16"); return BMP_EINVAL; }
     const float *hT[2];
     float *d_hT[2];
     int rc;
@@ -129,7 +130,7 @@ extern "C" int bmp_pair_forward_backward(const bmp_pair_t *a, void *stream) {
         bmp_ggnn_fwd_t f;
         memset(&f, 0, sizeof(f));
         f.mb = mb; f.n_atoms = N[s]; f.hidden = H; f.n_edge = 4; f.n_steps = T; f.n_atom_types = a->n_atom_types; f.mode = a->mode;
-        f.atoms = atoms[s]; f.embed_W = a->embed_W; f.adj = adj[s];
+        f.atoms = atoms[s]; f.embed_W = a->embed_W; f.adj = reinterpret_cast<const float *>(adj[s]); f.adj_u8 = a->adj_u8;
         for (int t = 0; t < T; ++t) { f.msg_W[t] = a->msg_W[t]; f.msg_b[t] = a->msg_b[t]; f.gru[t] = a->gru[t]; f.stateful[t] = a->stateful[t]; }
         if (bf16) {
             f.h0_out = e.out2; f.h_out = e.out2 + RH; f.stash2 = e.stash2;
@@ -182,7 +183,7 @@ extern "C" int bmp_pair_forward_backward(const bmp_pair_t *a, void *stream) {
         bmp_ggnn_bwd_t g;
         memset(&g, 0, sizeof(g));
         g.mb = mb; g.n_atoms = N[s]; g.hidden = H; g.n_edge = 4; g.n_steps = T; g.mode = a->mode;
-        g.adj = adj[s];
+        g.adj = reinterpret_cast<const float *>(adj[s]); g.adj_u8 = a->adj_u8;
         for (int t = 0; t < T; ++t) {
             g.msg_W[t] = a->msg_W[t]; g.gru[t] = a->gru[t]; g.stateful[t] = a->stateful[t];
             g.d_msg_W[t] = a->d_msg_W[t]; g.d_msg_b[t] = a->d_msg_b[t]; g.d_gru[t] = a->d_gru[t];

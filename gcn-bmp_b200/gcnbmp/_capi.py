@@ -53,7 +53,7 @@ class Pair(C.Structure):
         (n, fp) for n in ("W", "V1", "V2", "b", "lt_1", "lt_2", "wa_1", "wa_2", "W_j", "b_j", "out_W", "out_b", "d_embed_W")] + [
         ("d_msg_W", _A()), ("d_msg_b", _A()), ("d_gru", GRU * MAX_STEPS)] + [
         (n, fp) for n in ("d_W", "d_V1", "d_V2", "d_b", "d_lt_1", "d_lt_2", "d_wa_1", "d_wa_2", "d_W_j", "d_b_j", "d_out_W", "d_out_b",
-                          "logits", "loss", "workspace")] + [("workspace_bytes", C.c_size_t)]
+                          "logits", "loss", "workspace")] + [("workspace_bytes", C.c_size_t), ("adj_u8", C.c_int)]
 
 
 class Bimpm(C.Structure):

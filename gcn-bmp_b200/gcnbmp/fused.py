@@ -33,14 +33,16 @@ def pair_forward_backward(model, atoms_1, adj_1, atoms_2, adj_2, labels, count=N
     dev = torch.device("cuda")
     a1 = torch.as_tensor(atoms_1).to(dev, torch.int32).contiguous()
     a2 = torch.as_tensor(atoms_2).to(dev, torch.int32).contiguous()
-    A1 = torch.as_tensor(adj_1).to(dev, torch.float32).contiguous()
-    A2 = torch.as_tensor(adj_2).to(dev, torch.float32).contiguous()
+    mode = model.graph_conv.__dict__.get("mode", K.MODE_F32)
+    A1, u8 = Fn._adj(torch.as_tensor(adj_1).to(dev), mode)          # BF16 mode keeps a uint8 / bit-packed adjacency as it is
+    A2, u8_2 = Fn._adj(torch.as_tensor(adj_2).to(dev), mode)
+    if u8 != u8_2:
+        raise ValueError("gcnbmp.fused: both adjacencies must use the same storage")
     y = torch.as_tensor(labels).to(dev, torch.int32).contiguous()
     mb, n1, n2 = a1.shape[0], a1.shape[1], a2.shape[1]
     H, O, T, Kc = enc.hidden_dim, attn.out_dim, enc.n_layers, y.shape[1]
     pool = isinstance(attn, links.PoolingFineCoattention)
     hd = 0 if pool else attn.head
-    mode = enc.__dict__.get("mode", K.MODE_F32)
     if count is None:
         count = float((y != -1).sum().item())
 
@@ -53,7 +55,7 @@ def pair_forward_backward(model, atoms_1, adj_1, atoms_2, adj_2, labels, count=N
 
     a = K.Pair()
     a.mb, a.n1, a.n2, a.hidden, a.out_dim, a.head, a.n_classes, a.n_steps = mb, n1, n2, H, O, hd, Kc, T
-    a.n_atom_types, a.mode = enc.embed.W.shape[0], mode
+    a.n_atom_types, a.mode, a.adj_u8 = enc.embed.W.shape[0], mode, u8
     a.coattn_variant, a.coattn_act = (K.COATTN_POOL if pool else K.COATTN_FINE), Fn.act_code(attn.activation)
     a.atoms_1, a.atoms_2, a.adj_1, a.adj_2, a.labels, a.count = _p(a1), _p(a2), _p(A1), _p(A2), _p(y), count
     a.embed_W, a.d_embed_W = _p(enc.embed.W), _p(grad_of(enc.embed.W))

@@ -352,7 +352,7 @@ typedef struct {
     int mb, n1, n2, hidden, out_dim, head, n_classes, n_steps, n_atom_types, mode;
     int coattn_variant, coattn_act;
     const int32_t *atoms_1, *atoms_2;      /* (mb,N1), (mb,N2) */
-    const float   *adj_1, *adj_2;          /* (mb,4,N1,N1), (mb,4,N2,N2) fp32 */
+    const void    *adj_1, *adj_2;          /* (mb,4,N1,N1), (mb,4,N2,N2): fp32, or the storage `adj_u8` names (BMP_MODE_BF16 only) */
     const int32_t *labels;                 /* (mb,n_classes), -1 = ignored */
     float count;                           /* what the loss mean divides by (the GLOBAL count of labels != -1 under data parallelism) */
     const float *embed_W;
@@ -369,6 +369,7 @@ typedef struct {
     float *logits, *loss;
     void  *workspace;
     size_t workspace_bytes;
+    int    adj_u8;                         /* storage of adj_1 / adj_2 as in bmp_ggnn_fwd_t: 0 fp32, 1 bytes, 2 bit-packed rows (BF16 mode) */
 } bmp_pair_t;
 
 size_t bmp_pair_workspace_bytes(int mb, int n1, int n2, int hidden, int out_dim, int head, int n_classes, int n_steps, int mode);

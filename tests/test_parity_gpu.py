@@ -659,3 +659,22 @@ def test_fp32_readout_forward_on_tensor_cores_matches_oracle_and_the_ffma_kernel
     gg = Fn.readout(hh, *args[1:])
     gg.sum().backward()
     assert torch.isfinite(hh.grad).all() and float(hh.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("storage", ["u8", "bits"])
+def test_one_call_pair_step_takes_byte_and_bit_packed_adjacency_in_bf16_mode(storage):
+    import gcnbmp
+    case = cases.pair_case("CB", seed=3)
+    a1, A1, a2, A2 = case["inputs"]
+    y = case["labels"]
+    conv = (lambda A: A.astype(np.uint8)) if storage == "u8" else (lambda A: gcnbmp.pack_adjacency(A.astype(np.float32)))
+    res = []
+    for adjs in ((A1.astype(np.float32), A2.astype(np.float32)), (conv(A1), conv(A2))):
+        model = product.product_model(case["spec"], case["params"])
+        model.graph_conv.mode = model.attn.mode = gcnbmp.MODE_BF16
+        model.cleargrads()
+        loss, logits = gcnbmp.fused.pair_forward_backward(model, a1, adjs[0], a2, adjs[1], y)
+        res.append((float(loss), logits.cpu().numpy(), model.grad_dict()))
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])          # same staged bf16 tiles: bit-identical forward
+    for k in res[0][2]:
+        assert rel_err(res[1][2][k], res[0][2][k]) <= 1e-3, k                          # gradients: atomics order only
